@@ -1,0 +1,14 @@
+"""luisa-compute-rs_b200 — host-side mirror of luisa-compute-rs's runtime / rtx interface over the
+B200 ray-tracing device (liblc_b200.so, C ABI in include/lc_b200_api.h).
+
+The directory name carries a hyphen (it is the reference's name); import it through the
+top-level shim `luisa_compute_rs_b200`.
+"""
+from . import _abi
+from .runtime import Buffer, BufferView, Context, Device, Event, LuisaError, Stream
+from .rtx import (Accel, AccelBuildRequest, AccelOption, AccelUsageHint, Index, Mesh, Ray, SurfaceHit, INVALID,
+                  affine_from_mat4, hit_valid, make_rays, offset_ray_origin)
+
+__all__ = ["Accel", "AccelBuildRequest", "AccelOption", "AccelUsageHint", "Buffer", "BufferView", "Context", "Device", "Event",
+           "Index", "INVALID", "LuisaError", "Mesh", "Ray", "Stream", "SurfaceHit", "affine_from_mat4", "hit_valid", "make_rays",
+           "offset_ray_origin", "_abi"]

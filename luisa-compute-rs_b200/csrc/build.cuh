@@ -1,0 +1,81 @@
+// build.cuh — internal interface between the host-side device object (device.cu) and the
+// kernel translation units (radix_sort.cu, bvh_build.cu, trace.cu).
+#pragma once
+#include "rt_types.cuh"
+#include <cstddef>
+
+namespace lcb {
+
+struct LaunchCounter { unsigned long long count = 0; };
+
+// ---- radix_sort.cu -------------------------------------------------------------------------
+size_t sort_scratch_bytes(uint32_t n, int passes);
+bool sort_pairs(cudaStream_t s, uint32_t n, uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, void *scratch,
+                int begin_bit, int passes, LaunchCounter &lc);
+
+// ---- bvh_build.cu --------------------------------------------------------------------------
+struct TriangleInput {
+    const uint8_t *vertices; size_t vertex_stride;
+    const uint8_t *indices;  // 12-byte uint3 records
+};
+
+// Scratch carved out of one allocation; sizes from build_scratch_layout().
+struct BuildScratch {
+    BuildHeader *header;
+    PrimBox *boxes;          // n
+    uint64_t *keys, *keys_alt;
+    uint32_t *vals, *vals_alt;
+    void *sort_scratch;
+    BinNode *bin;            // n-1
+    int *flags;              // n-1
+    unsigned long long *queue;  // n (collapse work items)
+    size_t total_bytes;
+};
+BuildScratch build_scratch_layout(void *base, uint32_t n);
+
+// Full build: prim boxes -> Morton -> sort -> fused hierarchy+refit -> collapse to WideNode + leaves.
+// `nodes` has capacity `n` nodes; `tris` capacity `n` (BLAS) / `prim_ids` capacity n (TLAS).
+void build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc);
+void build_tlas(cudaStream_t s, uint32_t n_active, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc,
+                WideNode *nodes, uint32_t *prim_ids, LaunchCounter &lc);
+
+// Refit (PreferUpdate): rewrites packed triangles from the current vertex data and recomputes
+// every node's quantised child planes bottom-up.  `parent` / `node_boxes` are side arrays kept
+// from the build.
+struct RefitArrays {
+    uint32_t *parent;      // per wide node: parent index (root: 0xffffffff)
+    float *boxes;          // per wide node: 6 floats, full-precision bounds
+    uint32_t *counters;    // per wide node: arrival counter
+};
+void refit_blas(cudaStream_t s, uint32_t n_nodes, uint32_t n_tris, const TriangleInput &in, WideNode *nodes, PackedTri *tris,
+                const RefitArrays &ra, BuildHeader *header, LaunchCounter &lc);
+void build_refit_arrays(cudaStream_t s, uint32_t n_nodes, const WideNode *nodes, const RefitArrays &ra, LaunchCounter &lc);
+
+// Instance table maintenance (AccelImpl::update, cpu/accel.rs:354-427): expanded modification
+// records are scattered into the device table in one launch.
+// Each record is the complete new state of one slot (the host mirror resolves the reference's
+// flag-ordering rules and sends one record per touched slot).
+struct InstanceModRec {
+    uint32_t index, flags, visibility, user_id;
+    const WideNode *nodes; const PackedTri *tris;
+    float affine[12];
+    float inv[12];
+};
+void apply_instance_mods(cudaStream_t s, InstanceRec *table, const InstanceModRec *mods, uint32_t n_mods, LaunchCounter &lc);
+
+// ---- trace.cu ------------------------------------------------------------------------------
+struct TraceCounters { unsigned long long nodes_visited, tris_tested, rays, instance_entries; };
+
+struct AccelView {
+    const WideNode *tlas_nodes;      // nullptr => empty accel
+    const uint32_t *tlas_prims;      // instance ids referenced by TLAS leaves
+    const InstanceRec *instances;
+    uint32_t instance_count;
+};
+
+void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
+                   TraceCounters *counters /* device, nullable */, LaunchCounter &lc);
+void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
+               LaunchCounter &lc);
+
+}  // namespace lcb

@@ -1,0 +1,472 @@
+// bvh_build.cu — LBVH builder for sm_100a: primitive boxes + centroid bounds, 63-bit Morton
+// codes, onesweep sort (radix_sort.cu), fused bottom-up hierarchy emission + AABB refit with
+// atomic arrival flags (after Apetrei 2014), and collapse of the binary tree into 8-wide
+// 128-byte quantised nodes with packed 48-byte leaf triangles.
+//
+// Replaces what the reference delegates to rtcCommitScene (cpu/accel.rs:258,439) /
+// optixAccelBuild (cuda_primitive.cpp:57-60).  No reference source exists for any of it.
+#include "build.cuh"
+#include <cfloat>
+
+namespace lcb {
+
+namespace {
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr unsigned long long kEmptyItem = ~0ull;
+constexpr int kLeafMax = 3;  // primitives per leaf child (unary count in 3 bits)
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+
+__global__ void k_init_header(BuildHeader *h, unsigned long long *queue, uint32_t n_queue, int *flags, uint32_t n_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
+        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->ticket = 0; h->max_depth = 0; h->error = 0;
+    }
+    for (uint32_t j = i; j < n_queue; j += gridDim.x * blockDim.x) queue[j] = kEmptyItem;
+    for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
+}
+
+// warp-reduce the centroid and fold it into the header's ordered-int bounds
+__device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, BuildHeader *h) {
+    float lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { lo[k] = valid ? c[k] : FLT_MAX; hi[k] = valid ? c[k] : -FLT_MAX; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&h->bounds_lo[k], float_to_ordered(lo[k]));
+            atomicMax(&h->bounds_hi[k], float_to_ordered(hi[k]));
+        }
+    }
+}
+
+__device__ __forceinline__ void load_triangle(const TriangleInput &in, uint32_t prim, float a[3], float b[3], float c[3]) {
+    const uint32_t *ix = reinterpret_cast<const uint32_t *>(in.indices + (size_t)prim * 12);
+    const uint32_t i0 = ix[0], i1 = ix[1], i2 = ix[2];
+    const float *pa = reinterpret_cast<const float *>(in.vertices + (size_t)i0 * in.vertex_stride);
+    const float *pb = reinterpret_cast<const float *>(in.vertices + (size_t)i1 * in.vertex_stride);
+    const float *pc = reinterpret_cast<const float *>(in.vertices + (size_t)i2 * in.vertex_stride);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { a[k] = pa[k]; b[k] = pb[k]; c[k] = pc[k]; }
+}
+
+__global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32_t n, PrimBox *boxes, BuildHeader *h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cen[3] = {0, 0, 0};
+    bool valid = i < n;
+    if (valid) {
+        float a[3], b[3], c[3];
+        load_triangle(in, i, a, b, c);
+        PrimBox pb;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            pb.lo[k] = fmin3(a[k], b[k], c[k]);
+            pb.hi[k] = fmax3(a[k], b[k], c[k]);
+            cen[k] = 0.5f * pb.lo[k] + 0.5f * pb.hi[k];
+        }
+        pb.pad0 = pb.pad1 = 0;
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(pb.lo[0], pb.lo[1], pb.lo[2], 0.f);
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(pb.hi[0], pb.hi[1], pb.hi[2], 0.f);
+    }
+    reduce_centroid_bounds(cen, valid, h);
+}
+
+// World-space box of an instance: union of the BLAS root's (conservatively decoded) child
+// boxes, 8 corners through the affine, padded for the fp32 mismatch between M and M^-1.
+__global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, uint32_t n, const InstanceRec *insts, PrimBox *boxes, BuildHeader *h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cen[3] = {0, 0, 0};
+    bool valid = i < n;
+    if (valid) {
+        const InstanceRec &rec = insts[active[i]];
+        const WideNode &root = rec.nodes[0];
+        float olo[3], ohi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float scale = __uint_as_float((uint32_t)root.e[k] << 23);
+            uint32_t qmin = 0xffff, qmax = 0;
+            for (int c = 0; c < 8; c++) {
+                if (root.meta[c] == 0) continue;
+                qmin = min(qmin, (uint32_t)root.qlo[k][c]);
+                qmax = max(qmax, (uint32_t)root.qhi[k][c]);
+            }
+            olo[k] = __fmaf_rd((float)qmin, scale, root.org[k]);
+            ohi[k] = __fmaf_ru((float)qmax, scale, root.org[k]);
+        }
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int corner = 0; corner < 8; corner++) {
+            float p[3] = {(corner & 1) ? ohi[0] : olo[0], (corner & 2) ? ohi[1] : olo[1], (corner & 4) ? ohi[2] : olo[2]};
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float *m = rec.affine + 4 * r;
+                float w = fmaf(m[0], p[0], fmaf(m[1], p[1], fmaf(m[2], p[2], m[3])));
+                lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+            }
+        }
+        float mag = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) mag = fmaxf(mag, fmaxf(fmaxf(fabsf(lo[k]), fabsf(hi[k])), hi[k] - lo[k]));
+        const float pad = mag * (1.0f / 16384.0f) + FLT_MIN;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { lo[k] -= pad; hi[k] += pad; cen[k] = 0.5f * lo[k] + 0.5f * hi[k]; }
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    reduce_centroid_bounds(cen, valid, h);
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t x) {
+    uint64_t v = x & 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxes, uint32_t n, const BuildHeader *__restrict__ h,
+                                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)i];
+    float4 hi = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)i + 1];
+    float c[3] = {0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z};
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float blo = ordered_to_float(h->bounds_lo[k]), bhi = ordered_to_float(h->bounds_hi[k]);
+        float ext = bhi - blo;
+        float t = ext > 0.f ? (c[k] - blo) / ext : 0.f;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        q[k] = min((uint32_t)(t * 2097152.0f), 2097151u);
+    }
+    keys[i] = expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2);
+    vals[i] = i;
+}
+
+// ---- fused hierarchy + refit ---------------------------------------------------------------
+// Internal node i separates sorted leaves i and i+1.  delta(i) orders the splits: the XOR of
+// adjacent keys, with runs of equal keys split by position bits.
+__device__ __forceinline__ uint64_t split_delta(const uint64_t *__restrict__ keys, uint32_t i) {
+    uint64_t x = keys[i] ^ keys[i + 1];
+    return x ? (x | (1ull << 63)) : (uint64_t)(i ^ (i + 1));
+}
+
+__global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ prim, const PrimBox *__restrict__ boxes,
+                                                   uint32_t n, BinNode *bin, int *flags, BuildHeader *h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = prim[i];
+    float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p];
+    float4 hi = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p + 1];
+    uint32_t left = i, right = i, cur = i | kLeafBit;
+    if (n == 1) {
+        h->root = cur;
+        h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
+        h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+        return;
+    }
+    while (true) {
+        const uint32_t count = right - left + 1;
+        const bool parent_on_right = (left == 0) || (right != n - 1 && split_delta(keys, right) < split_delta(keys, left - 1));
+        uint32_t parent;
+        float4 slo, shi;
+        if (parent_on_right) {  // we are the left child of internal node `right`
+            parent = right;
+            float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
+            pn[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
+            pn[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
+            __threadfence();
+            int other = atomicExch(&flags[parent], (int)left);
+            if (other == -1) return;
+            __threadfence();
+            right = (uint32_t)other;
+            slo = __ldcg(pn + 2); shi = __ldcg(pn + 3);
+        } else {  // right child of internal node `left - 1`
+            parent = left - 1;
+            float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
+            pn[2] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
+            pn[3] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
+            __threadfence();
+            int other = atomicExch(&flags[parent], (int)right);
+            if (other == -1) return;
+            __threadfence();
+            left = (uint32_t)other;
+            slo = __ldcg(pn); shi = __ldcg(pn + 1);
+        }
+        lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
+        hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
+        cur = parent;
+        if (left == 0 && right == n - 1) {
+            h->root = parent;
+            h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
+            h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+            return;
+        }
+    }
+}
+
+// ---- collapse to 8-wide quantised nodes ----------------------------------------------------
+struct Child {
+    float lo[3], hi[3];
+    uint32_t id;     // binary node id (kLeafBit => single sorted leaf)
+    uint32_t count;  // leaves below
+    uint32_t first;  // first sorted position covered
+};
+
+__device__ __forceinline__ float half_area(const Child &c) {
+    float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ void split_child(const BinNode *__restrict__ bin, const Child &c, Child &l, Child &r) {
+    const float4 *pn = reinterpret_cast<const float4 *>(&bin[c.id]);
+    float4 a = pn[0], b = pn[1], cc = pn[2], d = pn[3];
+    l.lo[0] = a.x; l.lo[1] = a.y; l.lo[2] = a.z; l.id = __float_as_uint(a.w);
+    l.hi[0] = b.x; l.hi[1] = b.y; l.hi[2] = b.z; l.count = __float_as_uint(b.w);
+    r.lo[0] = cc.x; r.lo[1] = cc.y; r.lo[2] = cc.z; r.id = __float_as_uint(cc.w);
+    r.hi[0] = d.x; r.hi[1] = d.y; r.hi[2] = d.z; r.count = __float_as_uint(d.w);
+    l.first = c.id + 1 - l.count;  // internal node c.id sits between sorted leaves c.id and c.id+1
+    r.first = c.id + 1;
+}
+
+struct LeafSinkTriangles {
+    TriangleInput in; PackedTri *tris;
+    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const {
+        float a[3], b[3], c[3];
+        load_triangle(in, prim, a, b, c);
+        float4 *o = reinterpret_cast<float4 *>(&tris[dst]);
+        o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
+        o[1] = make_float4(b[0], b[1], b[2], 0.f);
+        o[2] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+};
+struct LeafSinkInstances {
+    const uint32_t *active; uint32_t *prim_ids;
+    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const { prim_ids[dst] = active[prim]; }
+};
+
+// Quantise [lo,hi] of one child against the node frame, conservatively (directed rounding).
+__device__ __forceinline__ void quantise_axis(float clo, float chi, float org, float inv_scale, uint16_t &qlo, uint16_t &qhi) {
+    float l = floorf(__fmul_rd(__fsub_rd(clo, org), inv_scale));
+    float u = ceilf(__fmul_ru(__fsub_ru(chi, org), inv_scale));
+    l = fminf(fmaxf(l, 0.f), 65535.f);
+    u = fminf(fmaxf(u, 0.f), 65535.f);
+    qlo = (uint16_t)l; qhi = (uint16_t)u;
+}
+
+template <class Sink>
+__global__ void __launch_bounds__(64) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
+                                                 unsigned long long *queue, WideNode *nodes, uint32_t capacity, Sink sink) {
+    while (true) {
+        const uint32_t t = atomicAdd(&h->ticket, 1u);
+        if (t >= capacity) return;
+        unsigned long long item;
+        while (true) {
+            item = *reinterpret_cast<volatile unsigned long long *>(queue + t);
+            if (item != kEmptyItem) break;
+            if (*reinterpret_cast<volatile uint32_t *>(&h->emitted) >= n) return;
+            if (*reinterpret_cast<volatile uint32_t *>(&h->error) != 0) return;
+            __nanosleep(100);
+        }
+        const uint32_t bnode = (uint32_t)item, depth = (uint32_t)(item >> 32);
+        Child c[8];
+        int nc;
+        if (bnode & kLeafBit) {  // single-primitive tree
+            nc = 1;
+            for (int k = 0; k < 3; k++) { c[0].lo[k] = h->root_lo[k]; c[0].hi[k] = h->root_hi[k]; }
+            c[0].id = bnode; c[0].count = 1; c[0].first = bnode & ~kLeafBit;
+        } else {
+            Child self; self.id = bnode;
+            split_child(bin, self, c[0], c[1]);
+            nc = 2;
+        }
+        // phase 1: open the largest subtree that cannot be a leaf; phase 2: use spare slots to
+        // split multi-primitive leaves (tighter boxes at no traversal cost: all 8 slots are tested anyway)
+        for (int phase = 0; phase < 2; phase++) {
+            const uint32_t limit = phase == 0 ? (uint32_t)kLeafMax : 1u;
+            while (nc < 8) {
+                int best = -1; float best_area = -1.f;
+                for (int j = 0; j < nc; j++) {
+                    if (c[j].count > limit) { float a = half_area(c[j]); if (a > best_area) { best_area = a; best = j; } }
+                }
+                if (best < 0) break;
+                Child l, r;
+                split_child(bin, c[best], l, r);
+                c[best] = l; c[nc++] = r;
+            }
+        }
+        // node frame
+        float nlo[3], nhi[3];
+        for (int k = 0; k < 3; k++) { nlo[k] = c[0].lo[k]; nhi[k] = c[0].hi[k]; }
+        for (int j = 1; j < nc; j++) for (int k = 0; k < 3; k++) { nlo[k] = fminf(nlo[k], c[j].lo[k]); nhi[k] = fmaxf(nhi[k], c[j].hi[k]); }
+        uint8_t e[3]; float inv_scale[3];
+        for (int k = 0; k < 3; k++) {
+            float s = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
+            uint32_t bits = __float_as_uint(s);
+            uint32_t ex = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+            ex = max(ex, 1u); ex = min(ex, 253u);
+            e[k] = (uint8_t)ex;
+            inv_scale[k] = __uint_as_float((254u - ex) << 23);
+        }
+        // octant slot assignment: slot s is visited first by rays whose direction signs are s
+        // (bit k set = negative along axis k); greedy minimum of dot(child centre - node centre, sign_s)
+        int slot_of[8]; uint32_t slot_used = 0, child_done = 0;
+        {
+            float cx[8], cy[8], cz[8];
+            const float mx = 0.5f * (nlo[0] + nhi[0]), my = 0.5f * (nlo[1] + nhi[1]), mz = 0.5f * (nlo[2] + nhi[2]);
+            for (int j = 0; j < nc; j++) {
+                cx[j] = 0.5f * (c[j].lo[0] + c[j].hi[0]) - mx; cy[j] = 0.5f * (c[j].lo[1] + c[j].hi[1]) - my; cz[j] = 0.5f * (c[j].lo[2] + c[j].hi[2]) - mz;
+            }
+            for (int it = 0; it < nc; it++) {
+                float best = FLT_MAX; int bj = -1, bs = -1;
+                for (int j = 0; j < nc; j++) {
+                    if (child_done >> j & 1) continue;
+                    for (int s = 0; s < 8; s++) {
+                        if (slot_used >> s & 1) continue;
+                        float cost = ((s & 1) ? -cx[j] : cx[j]) + ((s & 2) ? -cy[j] : cy[j]) + ((s & 4) ? -cz[j] : cz[j]);
+                        if (cost < best) { best = cost; bj = j; bs = s; }
+                    }
+                }
+                if (bj < 0) {  // only NaN costs left: place in the first free slot
+                    for (int j = 0; j < nc && bj < 0; j++) if (!(child_done >> j & 1)) bj = j;
+                    bs = __ffs(~slot_used & 0xff) - 1;
+                }
+                slot_of[bj] = bs; slot_used |= 1u << bs; child_done |= 1u << bj;
+            }
+        }
+        int child_in_slot[8];
+        for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
+        for (int j = 0; j < nc; j++) child_in_slot[slot_of[j]] = j;
+        uint32_t n_internal = 0, n_prims = 0;
+        for (int j = 0; j < nc; j++) { if (c[j].count > (uint32_t)kLeafMax) n_internal++; else n_prims += c[j].count; }
+        const uint32_t child_base = n_internal ? atomicAdd(&h->node_count, n_internal) : 0u;
+        const uint32_t prim_base = n_prims ? atomicAdd(&h->prim_count, n_prims) : 0u;
+        if (child_base + n_internal > capacity || depth + 1 > (uint32_t)kMaxWideDepth) {
+            atomicExch(&h->error, child_base + n_internal > capacity ? 2u : 1u);
+            return;
+        }
+        WideNode node;
+        for (int k = 0; k < 3; k++) { node.org[k] = nlo[k]; node.e[k] = e[k]; }
+        node.child_base = child_base; node.prim_base = prim_base;
+        uint32_t imask = 0, int_rank = 0, prim_off = 0;
+        for (int s = 0; s < 8; s++) {
+            const int j = child_in_slot[s];
+            if (j < 0) {
+                node.meta[s] = 0;
+                for (int k = 0; k < 3; k++) { node.qlo[k][s] = 0xffff; node.qhi[k][s] = 0; }
+                continue;
+            }
+            for (int k = 0; k < 3; k++) quantise_axis(c[j].lo[k], c[j].hi[k], nlo[k], inv_scale[k], node.qlo[k][s], node.qhi[k][s]);
+            if (c[j].count > (uint32_t)kLeafMax) {
+                imask |= 1u << s;
+                node.meta[s] = (uint8_t)(0x20u | (24u + s));
+                *reinterpret_cast<volatile unsigned long long *>(queue + child_base + int_rank) = (unsigned long long)c[j].id | ((unsigned long long)(depth + 1) << 32);
+                int_rank++;
+            } else {
+                const uint32_t unary = (1u << c[j].count) - 1u;
+                node.meta[s] = (uint8_t)((unary << 5) | prim_off);
+                for (uint32_t q = 0; q < c[j].count; q++) sink.emit(prim_base + prim_off + q, prim_sorted[c[j].first + q]);
+                prim_off += c[j].count;
+            }
+        }
+        node.imask = (uint8_t)imask;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&node);
+        uint4 *dst = reinterpret_cast<uint4 *>(&nodes[t]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) dst[q] = src[q];
+        atomicMax(&h->max_depth, depth + 1);
+        if (n_prims) { __threadfence(); atomicAdd(&h->emitted, n_prims); }
+    }
+}
+
+__global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) {
+    *reinterpret_cast<volatile unsigned long long *>(queue) = (unsigned long long)h->root;
+}
+
+template <class Sink>
+void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc) {
+    k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals); lc.count++;
+    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, 8, lc);
+    const uint64_t *keys = in_alt ? sc.keys_alt : sc.keys;
+    const uint32_t *vals = in_alt ? sc.vals_alt : sc.vals;
+    k_hierarchy<<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header); lc.count++;
+    // seed the collapse queue with the binary root (device-side, no host round trip)
+    k_seed_queue<<<1, 1, 0, s>>>(sc.header, sc.queue); lc.count++;
+    uint32_t blocks = (n + 63) / 64;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_collapse<Sink><<<blocks, 64, 0, s>>>(sc.bin, vals, n, sc.header, sc.queue, nodes, n, sink); lc.count++;
+}
+
+}  // namespace
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+BuildScratch build_scratch_layout(void *base, uint32_t n) {
+    BuildScratch sc{};
+    uint8_t *p = (uint8_t *)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *r = p ? p + off : nullptr; off = align_up(off + bytes, 256); return r; };
+    const size_t nn = n ? n : 1;
+    sc.header = (BuildHeader *)take(sizeof(BuildHeader));
+    sc.boxes = (PrimBox *)take(nn * sizeof(PrimBox));
+    sc.keys = (uint64_t *)take(nn * 8);
+    sc.keys_alt = (uint64_t *)take(nn * 8);
+    sc.vals = (uint32_t *)take(nn * 4);
+    sc.vals_alt = (uint32_t *)take(nn * 4);
+    sc.sort_scratch = take(sort_scratch_bytes(n, 8));
+    sc.bin = (BinNode *)take(nn * sizeof(BinNode));
+    sc.flags = (int *)take(nn * 4);
+    sc.queue = (unsigned long long *)take(nn * 8);
+    sc.total_bytes = off;
+    return sc;
+}
+
+void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc) {
+    uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.queue, n, sc.flags, n); lc.count++;
+    k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
+    LeafSinkTriangles sink{in, tris};
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
+}
+
+void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,
+                uint32_t *prim_ids, LaunchCounter &lc) {
+    uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.queue, n, sc.flags, n); lc.count++;
+    k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
+    LeafSinkInstances sink{active_ids, prim_ids};
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
+}
+
+// ---- instance table scatter ----------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_apply_instance_mods(InstanceRec *table, const InstanceModRec *mods, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const InstanceModRec &m = mods[i];
+    InstanceRec &r = table[m.index];
+    // `flags` here are already resolved by the host mirror (which applies the reference's
+    // ordering rules); the record carries the full new state of the slot.
+    for (int k = 0; k < 12; k++) { r.inv[k] = m.inv[k]; r.affine[k] = m.affine[k]; }
+    r.nodes = m.nodes; r.tris = m.tris;
+    r.visibility = m.visibility; r.user_id = m.user_id; r.flags = m.flags; r.pad = 0;
+}
+
+void apply_instance_mods(cudaStream_t s, InstanceRec *table, const InstanceModRec *mods, uint32_t n_mods, LaunchCounter &lc) {
+    if (!n_mods) return;
+    k_apply_instance_mods<<<(n_mods + 127) / 128, 128, 0, s>>>(table, mods, n_mods); lc.count++;
+}
+
+}  // namespace lcb

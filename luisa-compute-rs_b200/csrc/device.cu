@@ -1,0 +1,759 @@
+// device.cu — the far side of luisa-compute-rs's DeviceInterface for the "b200" device.
+//
+// Mirrors the behaviour of the reference CPU backend object model
+// (luisa_compute_backend_impl/src/cpu/{mod.rs,stream.rs,accel.rs,resource.rs}) for the hot path:
+// handles are raw pointers to backend objects, buffers are zero-initialised device memory,
+// streams execute command lists in order and fire the completion callback exactly once from a
+// stream-owned host thread, MeshBuild / AccelBuild run the CUDA builder, and every failure is
+// logged through the logger callback and aborts (backend_impl/src/lib.rs:101-131).
+// Slots outside the hot path log "unsupported" and abort — there is no CPU fallback anywhere.
+#include "../../include/lc_b200_api.h"
+#include "build.cuh"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace lcb;
+
+namespace {
+
+// ---- logging / errors ------------------------------------------------------------------------
+std::atomic<void (*)(lcb_logger_message)> g_logger{nullptr};
+std::atomic<unsigned long long> g_launches{0};
+
+void log_msg(const char *level, const char *fmt, ...) {
+    char buf[2048];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    auto cb = g_logger.load();
+    if (cb) { lcb_logger_message m{"lc_b200", level, buf}; cb(m); }
+    else if (level[0] == 'E' || level[0] == 'W' || getenv("LC_B200_LOG")) fprintf(stderr, "[lc_b200][%s] %s\n", level, buf);
+}
+
+[[noreturn]] void fatal(const char *fmt, ...) {
+    char buf[2048];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    log_msg("E", "%s", buf);
+    fprintf(stderr, "[lc_b200] fatal: %s\n", buf);
+    fflush(stderr);
+    abort();
+}
+
+#define CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t err__ = (expr);                                                                        \
+        if (err__ != cudaSuccess) fatal("CUDA error %s at %s:%d: %s", cudaGetErrorName(err__), __FILE__, __LINE__, cudaGetErrorString(err__)); \
+    } while (0)
+
+// ---- IR type walking (create_buffer's &CArc<ir::Type>) ----------------------------------------
+// Layouts: LC/include/luisa/rust/ir_common.h (CArcSharedBlock, CBoxedSlice) and ir.hpp:187-232.
+struct IrArcBlock { void *ptr; std::atomic<size_t> ref_count; void (*destructor)(void *); };
+struct IrSlice { void *ptr; size_t len; void *destructor; };
+enum IrTypeTag : int32_t { IR_VOID, IR_USERDATA, IR_PRIMITIVE, IR_VECTOR, IR_MATRIX, IR_STRUCT, IR_ARRAY, IR_OPAQUE };
+struct IrVectorElement { int32_t tag; int32_t pad; union { int32_t primitive; IrArcBlock *vector; } u; };
+struct IrVectorType { IrVectorElement element; uint32_t length; };
+struct IrType {
+    int32_t tag; int32_t pad;
+    union {
+        int32_t primitive;
+        IrVectorType vector;  // also MatrixType{element, dimension}
+        struct { IrSlice fields; size_t alignment; size_t size; } struct_;
+        struct { IrArcBlock *element; size_t length; } array;
+    } u;
+};
+
+size_t ir_primitive_size(int32_t p) {  // ir.rs:214-231
+    static const size_t sz[12] = {1, 1, 1, 2, 2, 4, 4, 8, 8, 2, 4, 8};
+    if (p < 0 || p >= 12) fatal("bad IR primitive %d", p);
+    return sz[p];
+}
+size_t ir_vector_size(const IrVectorType &v);
+size_t ir_vector_element_size(const IrVectorElement &e) {
+    return e.tag == 0 ? ir_primitive_size(e.u.primitive) : ir_vector_size(*(const IrVectorType *)e.u.vector->ptr);
+}
+size_t ir_vector_size(const IrVectorType &v) {  // ir.rs:234-251: 3-vectors of scalars are padded to 4
+    size_t el = ir_vector_element_size(v.element);
+    uint32_t len = v.length;
+    if (v.element.tag == 0) { uint32_t four = len / 4, rem = len % 4; len = rem <= 2 ? four * 4 + rem : four * 4 + 4; }
+    return el * len;
+}
+size_t ir_type_size(const IrType *t);
+size_t ir_type_alignment(const IrType *t) {  // ir.rs:356-369
+    switch (t->tag) {
+        case IR_VOID: case IR_USERDATA: return 0;
+        case IR_PRIMITIVE: return ir_primitive_size(t->u.primitive);
+        case IR_STRUCT: return t->u.struct_.alignment;
+        case IR_VECTOR: case IR_MATRIX: {
+            size_t el = ir_primitive_size(t->u.vector.element.u.primitive);
+            uint32_t dim = t->u.vector.length == 3 ? 4 : t->u.vector.length;
+            size_t a = el * dim; return a < 16 ? a : 16;
+        }
+        case IR_ARRAY: return ir_type_alignment((const IrType *)t->u.array.element->ptr);
+        default: fatal("unsupported IR type tag %d", t->tag);
+    }
+}
+size_t ir_type_size(const IrType *t) {  // ir.rs:325-335
+    switch (t->tag) {
+        case IR_VOID: case IR_USERDATA: return 0;
+        case IR_PRIMITIVE: return ir_primitive_size(t->u.primitive);
+        case IR_STRUCT: return t->u.struct_.size;
+        case IR_VECTOR: return ir_vector_size(t->u.vector);
+        case IR_MATRIX: {  // ir.rs:275-293
+            uint32_t d = t->u.vector.length;
+            uint32_t cols = d == 2 ? 2u : 4u;
+            return ir_primitive_size(t->u.vector.element.u.primitive) * cols * d;
+        }
+        case IR_ARRAY: return ir_type_size((const IrType *)t->u.array.element->ptr) * t->u.array.length;
+        default: fatal("unsupported IR type tag %d", t->tag);
+    }
+}
+
+// ---- backend objects ---------------------------------------------------------------------------
+struct BufferObj { uint8_t *ptr = nullptr; size_t size = 0; bool owned = true; };
+
+struct MeshObj {
+    lcb_accel_option option{};
+    bool built = false;
+    uint32_t n_tris = 0;
+    uint64_t generation = 0;  // bumped whenever nodes/tris are re-allocated
+    WideNode *nodes = nullptr; PackedTri *tris = nullptr;
+    uint32_t n_nodes = 0, n_packed = 0, node_capacity = 0;
+    lcb_build_stats stats{};
+    std::mutex mu;
+};
+
+struct InstanceHost {  // AccelImpl::Instance, cpu/accel.rs:270-296
+    float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    uint32_t user_id = 0, visible = 0xff;
+    bool opaque = true, valid = false;
+    MeshObj *mesh = nullptr;
+    uint64_t mesh_generation = 0;
+};
+
+struct AccelObj {
+    lcb_accel_option option{};
+    std::vector<InstanceHost> instances;
+    InstanceRec *table = nullptr; uint32_t table_capacity = 0;
+    WideNode *tlas_nodes = nullptr; uint32_t *tlas_prims = nullptr; uint32_t *active_ids = nullptr; uint32_t tlas_capacity = 0;
+    uint32_t n_active = 0;
+    lcb_build_stats stats{};
+    std::mutex mu;
+};
+
+struct EventObj {
+    std::mutex mu; std::condition_variable cv;
+    std::map<uint64_t, cudaEvent_t> signalled;  // value -> event recorded at the signal point
+};
+
+struct DeviceObj;
+
+struct StreamObj {
+    DeviceObj *dev = nullptr;
+    cudaStream_t stream = nullptr;
+    unsigned long long *work_counter = nullptr;   // device: ray-pool counter for trace launches on this stream
+    struct Pending { cudaEvent_t ev; lcb_dispatch_callback cb; uint8_t *ctx; std::vector<void *> host_frees; };
+    std::mutex mu; std::condition_variable cv, drained;
+    std::deque<Pending> pending;
+    bool stop = false; size_t in_flight = 0;
+    std::thread worker;
+
+    void run() {
+        for (;;) {
+            Pending p;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !pending.empty(); });
+                if (pending.empty()) return;
+                p = std::move(pending.front()); pending.pop_front();
+            }
+            cudaError_t e = cudaEventSynchronize(p.ev);
+            if (e != cudaSuccess) fatal("stream failed: %s", cudaGetErrorString(e));
+            cudaEventDestroy(p.ev);
+            for (void *h : p.host_frees) cudaFreeHost(h);
+            if (p.cb) p.cb(p.ctx);
+            { std::lock_guard<std::mutex> lk(mu); in_flight--; }
+            drained.notify_all();
+        }
+    }
+    void push(Pending &&p) {
+        { std::lock_guard<std::mutex> lk(mu); pending.push_back(std::move(p)); in_flight++; }
+        cv.notify_all();
+    }
+    void wait_drained() { std::unique_lock<std::mutex> lk(mu); drained.wait(lk, [&] { return in_flight == 0; }); }
+};
+
+struct DeviceObj {
+    int ordinal = 0;
+    LaunchCounter lc;
+    StreamObj *internal = nullptr;  // used by the *_host entry points
+    // grow-only device staging for the host entry points
+    uint8_t *stage_rays = nullptr, *stage_out = nullptr; size_t stage_rays_cap = 0, stage_out_cap = 0;
+    std::mutex mu;
+};
+
+template <class T> T *as(uint64_t h) { if (h == 0 || h == LCB_INVALID_HANDLE) fatal("invalid resource handle"); return reinterpret_cast<T *>(h); }
+DeviceObj *dev_of(lcb_device d) { return as<DeviceObj>(d.id); }
+void bind(DeviceObj *d) { CUDA_CHECK(cudaSetDevice(d->ordinal)); }
+void flush_launches(DeviceObj *d) { g_launches += d->lc.count; d->lc.count = 0; }
+
+// ---- buffers -----------------------------------------------------------------------------------
+lcb_created_buffer create_buffer(lcb_device dev, const void *ir_type, size_t count, void *ext_mem) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    if (!ir_type) fatal("create_buffer: null type");
+    const IrArcBlock *blk = *reinterpret_cast<IrArcBlock *const *>(ir_type);
+    const IrType *ty = blk ? reinterpret_cast<const IrType *>(blk->ptr) : nullptr;
+    if (!ty) fatal("create_buffer: null CArc<Type>");
+    const size_t stride = ir_type_size(ty);
+    const size_t total = ty->tag == IR_VOID ? count : stride * count;  // cpu/mod.rs:57-61
+    auto *b = new BufferObj;
+    b->size = total;
+    if (ext_mem) { b->ptr = (uint8_t *)ext_mem; b->owned = false; }
+    else {
+        CUDA_CHECK(cudaMalloc(&b->ptr, total ? total : 16));
+        CUDA_CHECK(cudaMemset(b->ptr, 0, total ? total : 16));  // BufferImpl::new zero-initialises (cpu/resource.rs:126-133)
+    }
+    lcb_created_buffer out{};
+    out.resource.handle = (uint64_t)b; out.resource.native_handle = b->ptr;
+    out.element_stride = stride; out.total_size_bytes = total;
+    return out;
+}
+void destroy_buffer(lcb_device dev, lcb_buffer h) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    BufferObj *b = as<BufferObj>(h.id);
+    if (b->owned) CUDA_CHECK(cudaFree(b->ptr));
+    delete b;
+}
+
+// ---- streams -----------------------------------------------------------------------------------
+StreamObj *make_stream(DeviceObj *d) {
+    auto *s = new StreamObj; s->dev = d;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaMalloc(&s->work_counter, 256));
+    s->worker = std::thread([s] { s->run(); });
+    return s;
+}
+lcb_created create_stream(lcb_device dev, int32_t) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = make_stream(d);
+    return lcb_created{(uint64_t)s, (void *)s->stream};
+}
+void synchronize_stream(lcb_device dev, lcb_stream h) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(h.id);
+    CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    s->wait_drained();
+}
+void free_stream(StreamObj *s) {
+    CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    s->wait_drained();
+    { std::lock_guard<std::mutex> lk(s->mu); s->stop = true; }
+    s->cv.notify_all();
+    s->worker.join();
+    cudaFree(s->work_counter);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+void destroy_stream(lcb_device dev, lcb_stream h) { DeviceObj *d = dev_of(dev); bind(d); free_stream(as<StreamObj>(h.id)); }
+
+// ---- mesh build (GeometryImpl::build_mesh, cpu/accel.rs:205-260) ---------------------------------
+void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
+    MeshObj *m = as<MeshObj>(c.mesh.id);
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (c.index_stride != 12) fatal("Index stride must be 12 (got %zu).", c.index_stride);  // api/runtime.cpp:191-193
+    if (c.vertex_stride < 12) fatal("vertex stride must be >= 12 (got %zu)", c.vertex_stride);
+    BufferObj *vb = as<BufferObj>(c.vertex_buffer.id), *ib = as<BufferObj>(c.index_buffer.id);
+    if (c.vertex_buffer_offset + c.vertex_buffer_size > vb->size) fatal("MeshBuild: vertex range exceeds buffer");
+    if (c.index_buffer_offset + c.index_buffer_size > ib->size) fatal("MeshBuild: index range exceeds buffer");
+    const uint32_t n = (uint32_t)(c.index_buffer_size / c.index_stride);
+    TriangleInput in{vb->ptr + c.vertex_buffer_offset, c.vertex_stride, ib->ptr + c.index_buffer_offset};
+    // PreferUpdate on a built mesh is a vertex-update refit in the reference (accel.rs:251-257); until the
+    // refit kernels land we rebuild, which yields the same traversal results.
+    cudaStream_t st = s->stream;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    if (m->nodes) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
+    if (m->tris) { CUDA_CHECK(cudaFreeAsync(m->tris, st)); m->tris = nullptr; }
+    m->built = true; m->n_tris = n; m->generation++;
+    m->n_nodes = m->n_packed = 0;
+    memset(&m->stats, 0, sizeof(m->stats));
+    m->stats.primitive_count = n;
+    if (n == 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return; }
+    BuildScratch layout = build_scratch_layout(nullptr, n);
+    void *scratch = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&scratch, layout.total_bytes, st));
+    BuildScratch sc = build_scratch_layout(scratch, n);
+    WideNode *nodes = nullptr; PackedTri *tris = nullptr;
+    CUDA_CHECK(cudaMallocAsync((void **)&nodes, (size_t)n * sizeof(WideNode), st));
+    CUDA_CHECK(cudaMallocAsync((void **)&tris, (size_t)n * sizeof(PackedTri), st));
+    build_blas(st, n, in, sc, nodes, tris, d->lc);
+    BuildHeader hdr;
+    CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
+    if (hdr.error) fatal("BVH build failed (code %u: %s)", hdr.error, hdr.error == 1 ? "tree deeper than the traversal stack" : "node capacity exceeded");
+    if (hdr.emitted != n || hdr.prim_count != n) fatal("BVH build inconsistent: emitted %u of %u primitives", hdr.emitted, n);
+    m->n_nodes = hdr.node_count; m->n_packed = hdr.prim_count;
+    if (m->option.allow_compaction && hdr.node_count < n) {
+        WideNode *cn = nullptr;
+        CUDA_CHECK(cudaMallocAsync((void **)&cn, (size_t)hdr.node_count * sizeof(WideNode), st));
+        CUDA_CHECK(cudaMemcpyAsync(cn, nodes, (size_t)hdr.node_count * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaFreeAsync(nodes, st));
+        nodes = cn; m->node_capacity = hdr.node_count;
+    } else m->node_capacity = n;
+    CUDA_CHECK(cudaFreeAsync(scratch, st));
+    CUDA_CHECK(cudaEventRecord(e1, st));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    m->nodes = nodes; m->tris = tris;
+    m->stats.wide_node_count = hdr.node_count; m->stats.packed_tri_count = hdr.prim_count;
+    m->stats.bvh_bytes = (uint64_t)m->node_capacity * sizeof(WideNode) + (uint64_t)n * sizeof(PackedTri);
+    m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.build_ms = ms;
+}
+
+// ---- accel build (AccelImpl::update, cpu/accel.rs:324-447) ---------------------------------------
+void invert_affine(const float m[12], float inv[12]) {
+    // double adjugate inverse, one rounding to fp32 (restated independently in oracle.c)
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double tx = m[3], ty = m[7], tz = m[11];
+    const double c00 = e * i - f * h, c01 = c * h - b * i, c02 = b * f - c * e;
+    const double c10 = f * g - d * i, c11 = a * i - c * g, c12 = c * d - a * f;
+    const double c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+    const double det = a * c00 + b * c10 + c * c20;
+    const double r = 1.0 / det;
+    const double n00 = c00 * r, n01 = c01 * r, n02 = c02 * r, n10 = c10 * r, n11 = c11 * r, n12 = c12 * r, n20 = c20 * r, n21 = c21 * r, n22 = c22 * r;
+    inv[0] = (float)n00; inv[1] = (float)n01; inv[2] = (float)n02; inv[3] = (float)(-(n00 * tx + n01 * ty + n02 * tz));
+    inv[4] = (float)n10; inv[5] = (float)n11; inv[6] = (float)n12; inv[7] = (float)(-(n10 * tx + n11 * ty + n12 * tz));
+    inv[8] = (float)n20; inv[9] = (float)n21; inv[10] = (float)n22; inv[11] = (float)(-(n20 * tx + n21 * ty + n22 * tz));
+}
+
+void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
+    AccelObj *a = as<AccelObj>(c.accel.id);
+    std::lock_guard<std::mutex> lk(a->mu);
+    cudaStream_t st = s->stream;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    const uint32_t n = c.instance_count;
+    a->instances.resize(n);  // grow with default (invalid) slots / pop from the back (accel.rs:345-353)
+    std::vector<uint8_t> touched(n, 0);
+    for (size_t k = 0; k < c.modifications_count; k++) {
+        const lcb_accel_modification &m = c.modifications[k];
+        if (m.index >= n) fatal("AccelBuild: modification index %u out of range (%u instances)", m.index, n);
+        InstanceHost &in = a->instances[m.index];
+        touched[m.index] = 1;
+        if (m.flags & LCB_MOD_PRIMITIVE) {  // accel.rs:355-377: resets mask/opaque, takes affine + user_id as given
+            MeshObj *mesh = as<MeshObj>(m.mesh);
+            if (!mesh->built) fatal("Mesh not built");
+            memcpy(in.affine, m.affine, sizeof(in.affine));
+            in.visible = 0xff; in.user_id = m.user_id; in.opaque = true; in.valid = true; in.mesh = mesh;
+        }
+        if (m.flags & LCB_MOD_OPAQUE_ON) in.opaque = true;
+        else if (m.flags & LCB_MOD_OPAQUE_OFF) in.opaque = false;
+        if (m.flags & LCB_MOD_TRANSFORM) { if (!in.valid) fatal("AccelBuild: TRANSFORM on an empty instance slot"); memcpy(in.affine, m.affine, sizeof(in.affine)); }
+        if (m.flags & LCB_MOD_VISIBILITY) { if (!in.valid) fatal("AccelBuild: VISIBILITY on an empty instance slot"); in.visible = m.visibility; }
+        if (m.flags & LCB_MOD_USER_ID) { if (!in.valid) fatal("AccelBuild: USER_ID on an empty instance slot"); in.user_id = m.user_id; }
+    }
+    // device table capacity
+    if (n > a->table_capacity) {
+        InstanceRec *nt = nullptr;
+        uint32_t cap = n < 16 ? 16 : n + n / 2;
+        CUDA_CHECK(cudaMallocAsync((void **)&nt, (size_t)cap * sizeof(InstanceRec), st));
+        CUDA_CHECK(cudaMemsetAsync(nt, 0, (size_t)cap * sizeof(InstanceRec), st));
+        if (a->table) {
+            CUDA_CHECK(cudaMemcpyAsync(nt, a->table, (size_t)a->table_capacity * sizeof(InstanceRec), cudaMemcpyDeviceToDevice, st));
+            CUDA_CHECK(cudaFreeAsync(a->table, st));
+        }
+        a->table = nt; a->table_capacity = cap;
+    }
+    // one record per touched slot, plus slots whose mesh was re-allocated since they were last resolved
+    // (what update_accel_instance_handles does for OptiX, cuda_builtin_kernels.cu:42-50)
+    std::vector<InstanceModRec> recs;
+    std::vector<uint32_t> active;
+    for (uint32_t i = 0; i < n; i++) {
+        InstanceHost &in = a->instances[i];
+        if (in.valid && in.mesh->generation != in.mesh_generation) touched[i] = 1;
+        if (in.valid && in.mesh->n_tris > 0) active.push_back(i);
+        if (!touched[i]) continue;
+        InstanceModRec r{};
+        r.index = i; r.visibility = in.visible; r.user_id = in.user_id;
+        r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u);
+        memcpy(r.affine, in.affine, sizeof(r.affine));
+        invert_affine(in.affine, r.inv);
+        if (in.valid) { r.nodes = in.mesh->nodes; r.tris = in.mesh->tris; in.mesh_generation = in.mesh->generation; }
+        recs.push_back(r);
+    }
+    std::vector<void *> host_frees;
+    if (!recs.empty()) {
+        InstanceModRec *h = nullptr, *dv = nullptr;
+        CUDA_CHECK(cudaMallocHost((void **)&h, recs.size() * sizeof(InstanceModRec)));
+        memcpy(h, recs.data(), recs.size() * sizeof(InstanceModRec));
+        CUDA_CHECK(cudaMallocAsync((void **)&dv, recs.size() * sizeof(InstanceModRec), st));
+        CUDA_CHECK(cudaMemcpyAsync(dv, h, recs.size() * sizeof(InstanceModRec), cudaMemcpyHostToDevice, st));
+        apply_instance_mods(st, a->table, dv, (uint32_t)recs.size(), d->lc);
+        CUDA_CHECK(cudaFreeAsync(dv, st));
+        host_frees.push_back(h);
+    }
+    a->stats.primitive_count = n;
+    if (c.update_instance_buffer_only) {  // accel.rs:428-430
+        if (!host_frees.empty()) { CUDA_CHECK(cudaStreamSynchronize(st)); for (void *h : host_frees) cudaFreeHost(h); }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return;
+    }
+    // TLAS over the active instances (request is ignored, as on the CPU backend: stream.rs:418-428)
+    const uint32_t na = (uint32_t)active.size();
+    a->n_active = na;
+    if (na > a->tlas_capacity) {
+        if (a->tlas_nodes) { CUDA_CHECK(cudaFreeAsync(a->tlas_nodes, st)); CUDA_CHECK(cudaFreeAsync(a->tlas_prims, st)); CUDA_CHECK(cudaFreeAsync(a->active_ids, st)); }
+        uint32_t cap = na < 16 ? 16 : na + na / 2;
+        CUDA_CHECK(cudaMallocAsync((void **)&a->tlas_nodes, (size_t)cap * sizeof(WideNode), st));
+        CUDA_CHECK(cudaMallocAsync((void **)&a->tlas_prims, (size_t)cap * 4, st));
+        CUDA_CHECK(cudaMallocAsync((void **)&a->active_ids, (size_t)cap * 4, st));
+        a->tlas_capacity = cap;
+    }
+    if (na) {
+        uint32_t *h = nullptr;
+        CUDA_CHECK(cudaMallocHost((void **)&h, (size_t)na * 4));
+        memcpy(h, active.data(), (size_t)na * 4);
+        CUDA_CHECK(cudaMemcpyAsync(a->active_ids, h, (size_t)na * 4, cudaMemcpyHostToDevice, st));
+        host_frees.push_back(h);
+        BuildScratch layout = build_scratch_layout(nullptr, na);
+        void *scratch = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&scratch, layout.total_bytes, st));
+        BuildScratch sc = build_scratch_layout(scratch, na);
+        build_tlas(st, na, a->active_ids, a->table, sc, a->tlas_nodes, a->tlas_prims, d->lc);
+        BuildHeader hdr;
+        CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaFreeAsync(scratch, st));
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (hdr.error) fatal("TLAS build failed (code %u)", hdr.error);
+        if (hdr.emitted != na) fatal("TLAS build inconsistent: emitted %u of %u instances", hdr.emitted, na);
+        a->stats.wide_node_count = hdr.node_count; a->stats.packed_tri_count = hdr.prim_count; a->stats.max_depth = hdr.max_depth;
+        a->stats.bvh_bytes = (uint64_t)hdr.node_count * sizeof(WideNode) + (uint64_t)n * sizeof(InstanceRec);
+    } else {
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        a->stats.wide_node_count = 0; a->stats.packed_tri_count = 0; a->stats.max_depth = 0; a->stats.bvh_bytes = 0;
+    }
+    for (void *h : host_frees) cudaFreeHost(h);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    a->stats.build_ms = ms; a->stats.was_refit = 0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+AccelView view_of(AccelObj *a) {
+    AccelView v{};
+    v.tlas_nodes = a->n_active ? a->tlas_nodes : nullptr;
+    v.tlas_prims = a->tlas_prims; v.instances = a->table; v.instance_count = (uint32_t)a->instances.size();
+    return v;
+}
+
+// ---- dispatch (RustBackend::dispatch + StreamImpl::dispatch, cpu/mod.rs:168-180, stream.rs:213-446) ----
+void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch_callback cb, uint8_t *ctx) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id);
+    cudaStream_t st = s->stream;
+    for (size_t i = 0; i < list.commands_count; i++) {
+        const lcb_command &c = list.commands[i];
+        switch (c.tag) {
+            case LCB_CMD_BUFFER_UPLOAD: {
+                // pageable-source cudaMemcpyAsync returns once the source has been staged, which is the
+                // "snapshot upload payloads before returning" contract of stream.rs:47-64
+                BufferObj *b = as<BufferObj>(c.u.buffer_upload.buffer.id);
+                if (c.u.buffer_upload.offset + c.u.buffer_upload.size > b->size) fatal("BufferUpload out of range");
+                if (c.u.buffer_upload.size) CUDA_CHECK(cudaMemcpyAsync(b->ptr + c.u.buffer_upload.offset, c.u.buffer_upload.data, c.u.buffer_upload.size, cudaMemcpyHostToDevice, st));
+                break;
+            }
+            case LCB_CMD_BUFFER_DOWNLOAD: {
+                BufferObj *b = as<BufferObj>(c.u.buffer_download.buffer.id);
+                if (c.u.buffer_download.offset + c.u.buffer_download.size > b->size) fatal("BufferDownload out of range");
+                if (c.u.buffer_download.size) CUDA_CHECK(cudaMemcpyAsync(c.u.buffer_download.data, b->ptr + c.u.buffer_download.offset, c.u.buffer_download.size, cudaMemcpyDeviceToHost, st));
+                break;
+            }
+            case LCB_CMD_BUFFER_COPY: {
+                BufferObj *src = as<BufferObj>(c.u.buffer_copy.src.id), *dst = as<BufferObj>(c.u.buffer_copy.dst.id);
+                if (c.u.buffer_copy.src_offset + c.u.buffer_copy.size > src->size || c.u.buffer_copy.dst_offset + c.u.buffer_copy.size > dst->size) fatal("BufferCopy out of range");
+                if (c.u.buffer_copy.size) CUDA_CHECK(cudaMemcpyAsync(dst->ptr + c.u.buffer_copy.dst_offset, src->ptr + c.u.buffer_copy.src_offset, c.u.buffer_copy.size, cudaMemcpyDeviceToDevice, st));
+                break;
+            }
+            case LCB_CMD_MESH_BUILD: mesh_build(d, s, c.u.mesh_build); break;
+            case LCB_CMD_ACCEL_BUILD: accel_build(d, s, c.u.accel_build); break;
+            default:
+                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: textures, bindless arrays, shader dispatch, "
+                      "curves and procedural primitives are \"next\" rows)", c.tag);
+        }
+    }
+    flush_launches(d);
+    StreamObj::Pending p{};
+    CUDA_CHECK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(p.ev, st));
+    p.cb = cb; p.ctx = ctx;
+    s->push(std::move(p));
+}
+
+// ---- events (timeline semantics, cpu/resource.rs:10-44, cpu/mod.rs:367-402) -----------------------
+lcb_created create_event(lcb_device dev) { bind(dev_of(dev)); auto *e = new EventObj; return lcb_created{(uint64_t)e, e}; }
+void destroy_event(lcb_device dev, lcb_event h) {
+    bind(dev_of(dev));
+    EventObj *e = as<EventObj>(h.id);
+    for (auto &kv : e->signalled) cudaEventDestroy(kv.second);
+    delete e;
+}
+void signal_event(lcb_device dev, lcb_event h, lcb_stream sh, uint64_t value) {
+    bind(dev_of(dev));
+    EventObj *e = as<EventObj>(h.id); StreamObj *s = as<StreamObj>(sh.id);
+    cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ev, s->stream));
+    { std::lock_guard<std::mutex> lk(e->mu); auto it = e->signalled.find(value); if (it != e->signalled.end()) { cudaEventDestroy(it->second); } e->signalled[value] = ev; }
+    e->cv.notify_all();
+}
+cudaEvent_t event_for(EventObj *e, uint64_t value) {  // first signal with value >= requested; blocks until one was issued
+    std::unique_lock<std::mutex> lk(e->mu);
+    e->cv.wait(lk, [&] { return e->signalled.lower_bound(value) != e->signalled.end(); });
+    return e->signalled.lower_bound(value)->second;
+}
+void synchronize_event(lcb_device dev, lcb_event h, uint64_t value) { bind(dev_of(dev)); CUDA_CHECK(cudaEventSynchronize(event_for(as<EventObj>(h.id), value))); }
+void wait_event(lcb_device dev, lcb_event h, lcb_stream sh, uint64_t value) {
+    bind(dev_of(dev));
+    CUDA_CHECK(cudaStreamWaitEvent(as<StreamObj>(sh.id)->stream, event_for(as<EventObj>(h.id), value), 0));
+}
+bool is_event_completed(lcb_device dev, lcb_event h, uint64_t value) {
+    bind(dev_of(dev));
+    EventObj *e = as<EventObj>(h.id);
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->signalled.lower_bound(value);
+    if (it == e->signalled.end()) return false;
+    return cudaEventQuery(it->second) == cudaSuccess;
+}
+
+// ---- mesh / accel objects ------------------------------------------------------------------------
+lcb_created create_mesh(lcb_device dev, const lcb_accel_option *opt) { bind(dev_of(dev)); auto *m = new MeshObj; if (opt) m->option = *opt; return lcb_created{(uint64_t)m, m}; }
+void destroy_mesh(lcb_device dev, lcb_mesh h) {
+    bind(dev_of(dev));
+    MeshObj *m = as<MeshObj>(h.id);
+    if (m->nodes) cudaFree(m->nodes);
+    if (m->tris) cudaFree(m->tris);
+    delete m;
+}
+lcb_created create_accel(lcb_device dev, const lcb_accel_option *opt) { bind(dev_of(dev)); auto *a = new AccelObj; if (opt) a->option = *opt; return lcb_created{(uint64_t)a, a}; }
+void destroy_accel(lcb_device dev, lcb_accel h) {
+    bind(dev_of(dev));
+    AccelObj *a = as<AccelObj>(h.id);
+    if (a->table) cudaFree(a->table);
+    if (a->tlas_nodes) { cudaFree(a->tlas_nodes); cudaFree(a->tlas_prims); cudaFree(a->active_ids); }
+    delete a;
+}
+
+// ---- out-of-scope slots: loud failure -------------------------------------------------------------
+#define UNSUPPORTED(what) fatal("%s is outside the B200 ray-tracing device's scope (SURVEY.md §8: hot path only; no fallback)", what)
+lcb_created create_texture(lcb_device, int32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, bool, bool) { UNSUPPORTED("create_texture"); }
+void destroy_texture(lcb_device, lcb_texture) { UNSUPPORTED("destroy_texture"); }
+lcb_created create_bindless_array(lcb_device, size_t) { UNSUPPORTED("create_bindless_array"); }
+void destroy_bindless_array(lcb_device, lcb_bindless) { UNSUPPORTED("destroy_bindless_array"); }
+lcb_created_swapchain create_swapchain(lcb_device, const lcb_swapchain_option *, lcb_stream) { UNSUPPORTED("create_swapchain"); }
+void present_display_in_stream(lcb_device, lcb_stream, lcb_swapchain, lcb_texture) { UNSUPPORTED("present_display_in_stream"); }
+void destroy_swapchain(lcb_device, lcb_swapchain) { UNSUPPORTED("destroy_swapchain"); }
+lcb_created_shader create_shader(lcb_device, lcb_kernel_module, const lcb_shader_option *) { UNSUPPORTED("create_shader (IR -> CUDA lowering, SURVEY.md §8f rank 1)"); }
+void destroy_shader(lcb_device, lcb_shader) { UNSUPPORTED("destroy_shader"); }
+lcb_created create_curve(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_curve"); }
+void destroy_curve(lcb_device, lcb_curve) { UNSUPPORTED("destroy_curve"); }
+lcb_created create_procedural_primitive(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_procedural_primitive"); }
+void destroy_procedural_primitive(lcb_device, lcb_procedural) { UNSUPPORTED("destroy_procedural_primitive"); }
+
+void *native_handle(lcb_device dev) { return dev_of(dev); }
+uint32_t compute_warp_size(lcb_device) { return 32; }
+char *query(lcb_device, const char *name) {
+    // backend/lib.rs:447-457: "" reads as None on the Rust side
+    const char *v = "";
+    if (name && strcmp(name, "device_name") == 0) v = "b200";
+    char *out = (char *)malloc(strlen(v) + 1); strcpy(out, v); return out;
+}
+lcb_pinned_memory_ext pinned_memory_ext(lcb_device) { return lcb_pinned_memory_ext{nullptr, nullptr, nullptr}; }
+lcb_denoiser_ext denoiser_ext(lcb_device) { return lcb_denoiser_ext{nullptr, nullptr, nullptr, nullptr, nullptr}; }  // data == nullptr => invalid (api_types:1020-1024)
+
+void destroy_device(lcb_device_interface iface) {
+    DeviceObj *d = dev_of(iface.device); bind(d);
+    if (d->internal) free_stream(d->internal);
+    if (d->stage_rays) cudaFree(d->stage_rays);
+    if (d->stage_out) cudaFree(d->stage_out);
+    flush_launches(d);
+    delete d;
+}
+
+// ---- library interface -----------------------------------------------------------------------------
+void set_logger_callback(void (*cb)(lcb_logger_message)) { g_logger.store(cb); }
+lcb_context create_context(const char *) { return lcb_context{1}; }
+void destroy_context(lcb_context) {}
+void free_string(char *s) { free(s); }
+
+lcb_device_interface create_device(lcb_context, const char *name, const char *json) {
+    if (!name || (strcmp(name, "b200") != 0 && strcmp(name, "cuda-b200") != 0))
+        fatal("device \"%s\" is not served by this library (only \"b200\"); there is no CPU fallback", name ? name : "(null)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) fatal("no CUDA device available (%s); the b200 device has no CPU fallback", cudaGetErrorString(e));
+    int ordinal = 0;
+    if (const char *env = getenv("LC_B200_DEVICE")) ordinal = atoi(env);
+    else if (const char *lr = getenv("LOCAL_RANK")) ordinal = atoi(lr) % count;
+    if (json) { const char *p = strstr(json, "\"device_index\""); if (p && (p = strchr(p, ':'))) ordinal = atoi(p + 1); }
+    if (ordinal < 0 || ordinal >= count) fatal("device index %d out of range (%d devices)", ordinal, count);
+    CUDA_CHECK(cudaSetDevice(ordinal));
+    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, ordinal));
+    if (prop.major != 10) fatal("device %d is sm_%d%d; this library contains sm_100a code only", ordinal, prop.major, prop.minor);
+    auto *d = new DeviceObj; d->ordinal = ordinal;
+    d->internal = make_stream(d);
+    log_msg("I", "b200 device %d: %s, %d SMs, %.1f GB", ordinal, prop.name, prop.multiProcessorCount, prop.totalGlobalMem / 1e9);
+    lcb_device_interface t{};
+    t.device = lcb_device{(uint64_t)d};
+    t.destroy_device = destroy_device; t.create_buffer = create_buffer; t.destroy_buffer = destroy_buffer;
+    t.create_texture = create_texture; t.native_handle = native_handle; t.compute_warp_size = compute_warp_size;
+    t.destroy_texture = destroy_texture; t.create_bindless_array = create_bindless_array; t.destroy_bindless_array = destroy_bindless_array;
+    t.create_stream = create_stream; t.destroy_stream = destroy_stream; t.synchronize_stream = synchronize_stream; t.dispatch = dispatch;
+    t.create_swapchain = create_swapchain; t.present_display_in_stream = present_display_in_stream; t.destroy_swapchain = destroy_swapchain;
+    t.create_shader = create_shader; t.destroy_shader = destroy_shader;
+    t.create_event = create_event; t.destroy_event = destroy_event; t.signal_event = signal_event; t.synchronize_event = synchronize_event;
+    t.wait_event = wait_event; t.is_event_completed = is_event_completed;
+    t.create_mesh = create_mesh; t.destroy_mesh = destroy_mesh; t.create_curve = create_curve; t.destroy_curve = destroy_curve;
+    t.create_procedural_primitive = create_procedural_primitive; t.destroy_procedural_primitive = destroy_procedural_primitive;
+    t.create_accel = create_accel; t.destroy_accel = destroy_accel; t.query = query;
+    t.pinned_memory_ext = pinned_memory_ext; t.denoiser_ext = denoiser_ext;
+    return t;
+}
+
+void ensure_stage(uint8_t *&p, size_t &cap, size_t need) {
+    if (need <= cap) return;
+    if (p) CUDA_CHECK(cudaFree(p));
+    cap = need + need / 4;
+    CUDA_CHECK(cudaMalloc(&p, cap));
+}
+
+}  // namespace
+
+// ================================= exported symbols ===================================================
+
+extern "C" {
+
+lcb_lib_interface luisa_compute_lib_interface(void) {
+    lcb_lib_interface l{};
+    l.inner = nullptr; l.set_logger_callback = set_logger_callback; l.create_context = create_context;
+    l.destroy_context = destroy_context; l.create_device = create_device; l.free_string = free_string;
+    return l;
+}
+
+void lc_b200_trace_closest(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer hits, size_t hits_offset,
+                           uint64_t count, uint32_t mask) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id); AccelObj *a = as<AccelObj>(ah.id);
+    BufferObj *rb = as<BufferObj>(rays.id), *hb = as<BufferObj>(hits.id);
+    if (rays_offset % 16 || hits_offset % 8) fatal("trace_closest: misaligned offsets");
+    if (rays_offset + count * 32 > rb->size || hits_offset + count * 24 > hb->size) fatal("trace_closest: %llu rays exceed the buffers", (unsigned long long)count);
+    if (count) trace_closest(s->stream, view_of(a), rb->ptr + rays_offset, hb->ptr + hits_offset, count, mask, s->work_counter, nullptr, d->lc);
+    flush_launches(d);
+}
+
+void lc_b200_trace_any(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer occ, size_t occ_offset, uint64_t count,
+                       uint32_t mask) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id); AccelObj *a = as<AccelObj>(ah.id);
+    BufferObj *rb = as<BufferObj>(rays.id), *ob = as<BufferObj>(occ.id);
+    if (rays_offset % 16 || occ_offset % 4) fatal("trace_any: misaligned offsets");
+    if (rays_offset + count * 32 > rb->size || occ_offset + count * 4 > ob->size) fatal("trace_any: %llu rays exceed the buffers", (unsigned long long)count);
+    if (count) trace_any(s->stream, view_of(a), rb->ptr + rays_offset, (uint32_t *)(ob->ptr + occ_offset), count, mask, s->work_counter, d->lc);
+    flush_launches(d);
+}
+
+void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer hits, size_t hits_offset,
+                                   uint64_t count, uint32_t mask, lcb_trace_counters *out) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id); AccelObj *a = as<AccelObj>(ah.id);
+    BufferObj *rb = as<BufferObj>(rays.id), *hb = as<BufferObj>(hits.id);
+    if (rays_offset + count * 32 > rb->size || hits_offset + count * 24 > hb->size) fatal("trace_closest_counted: rays exceed the buffers");
+    TraceCounters *ctr = nullptr;
+    CUDA_CHECK(cudaMallocAsync((void **)&ctr, sizeof(TraceCounters), s->stream));
+    CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(TraceCounters), s->stream));
+    if (count) trace_closest(s->stream, view_of(a), rb->ptr + rays_offset, hb->ptr + hits_offset, count, mask, s->work_counter, ctr, d->lc);
+    TraceCounters h{};
+    CUDA_CHECK(cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_CHECK(cudaFreeAsync(ctr, s->stream));
+    CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    out->nodes_visited = h.nodes_visited; out->tris_tested = h.tris_tested; out->rays = h.rays; out->instance_entries = h.instance_entries;
+    flush_launches(d);
+}
+
+void lc_b200_trace_closest_host(lcb_device dev, lcb_accel ah, const lcb_ray *rays, lcb_surface_hit *hits, uint64_t count, uint32_t mask) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    AccelObj *a = as<AccelObj>(ah.id);
+    if (!count) return;
+    std::lock_guard<std::mutex> lk(d->mu);
+    ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
+    ensure_stage(d->stage_out, d->stage_out_cap, count * 24);
+    cudaStream_t st = d->internal->stream;
+    CUDA_CHECK(cudaMemcpyAsync(d->stage_rays, rays, count * 32, cudaMemcpyHostToDevice, st));
+    trace_closest(st, view_of(a), d->stage_rays, d->stage_out, count, mask, d->internal->work_counter, nullptr, d->lc);
+    CUDA_CHECK(cudaMemcpyAsync(hits, d->stage_out, count * 24, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    flush_launches(d);
+}
+
+void lc_b200_trace_any_host(lcb_device dev, lcb_accel ah, const lcb_ray *rays, uint32_t *occluded, uint64_t count, uint32_t mask) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    AccelObj *a = as<AccelObj>(ah.id);
+    if (!count) return;
+    std::lock_guard<std::mutex> lk(d->mu);
+    ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
+    ensure_stage(d->stage_out, d->stage_out_cap, count * 4);
+    cudaStream_t st = d->internal->stream;
+    CUDA_CHECK(cudaMemcpyAsync(d->stage_rays, rays, count * 32, cudaMemcpyHostToDevice, st));
+    trace_any(st, view_of(a), d->stage_rays, (uint32_t *)d->stage_out, count, mask, d->internal->work_counter, d->lc);
+    CUDA_CHECK(cudaMemcpyAsync(occluded, d->stage_out, count * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    flush_launches(d);
+}
+
+void lc_b200_instance_transform(lcb_device, lcb_accel ah, uint32_t i, float *out) {
+    AccelObj *a = as<AccelObj>(ah.id); std::lock_guard<std::mutex> lk(a->mu);
+    if (i >= a->instances.size()) fatal("instance_transform: index %u out of range", i);
+    memcpy(out, a->instances[i].affine, 48);
+}
+uint32_t lc_b200_instance_user_id(lcb_device, lcb_accel ah, uint32_t i) {
+    AccelObj *a = as<AccelObj>(ah.id); std::lock_guard<std::mutex> lk(a->mu);
+    if (i >= a->instances.size()) fatal("instance_user_id: index %u out of range", i);
+    return a->instances[i].user_id;
+}
+uint32_t lc_b200_instance_visibility_mask(lcb_device, lcb_accel ah, uint32_t i) {
+    AccelObj *a = as<AccelObj>(ah.id); std::lock_guard<std::mutex> lk(a->mu);
+    if (i >= a->instances.size()) fatal("instance_visibility_mask: index %u out of range", i);
+    if (!a->instances[i].valid) fatal("instance_visibility_mask: empty instance slot %u", i);  // accel.rs:556
+    return a->instances[i].visible;
+}
+
+void lc_b200_mesh_stats(lcb_device, lcb_mesh h, lcb_build_stats *out) { MeshObj *m = as<MeshObj>(h.id); std::lock_guard<std::mutex> lk(m->mu); *out = m->stats; }
+void lc_b200_accel_stats(lcb_device, lcb_accel h, lcb_build_stats *out) { AccelObj *a = as<AccelObj>(h.id); std::lock_guard<std::mutex> lk(a->mu); *out = a->stats; }
+
+void *lc_b200_stream_native(lcb_device, lcb_stream h) { return (void *)as<StreamObj>(h.id)->stream; }
+void *lc_b200_buffer_native(lcb_device, lcb_buffer h) { return as<BufferObj>(h.id)->ptr; }
+int lc_b200_device_ordinal(lcb_device dev) { return dev_of(dev)->ordinal; }
+uint64_t lc_b200_kernel_launch_count(void) { return g_launches.load(); }
+const char *lc_b200_version(void) { return "lc_b200 0.1 (sm_100a; LBVH + 8-wide quantised BVH; canonical fp32 watertight)"; }
+
+const void *lc_b200_make_ir_type(size_t size, size_t alignment) {
+    // leaked on purpose: type blocks live for the process, like the frontend's interned types
+    auto *ty = new IrType; memset(ty, 0, sizeof(*ty));
+    if (size == 0) ty->tag = IR_VOID;
+    else { ty->tag = IR_STRUCT; ty->u.struct_.fields = IrSlice{nullptr, 0, nullptr}; ty->u.struct_.alignment = alignment; ty->u.struct_.size = size; }
+    auto *blk = new IrArcBlock; blk->ptr = ty; blk->ref_count.store(1); blk->destructor = nullptr;
+    auto **arc = new IrArcBlock *; *arc = blk;
+    return arc;
+}
+
+}  // extern "C"

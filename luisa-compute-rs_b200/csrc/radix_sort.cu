@@ -1,0 +1,203 @@
+// radix_sort.cu — onesweep LSD radix sort of (uint64 key, uint32 value) pairs for the LBVH builder.
+//
+// One histogram pre-pass counts all digits of all passes; every pass is then a single kernel
+// ("one sweep" over the data): tiles take dynamic tickets, rank their keys with warp-level
+// __match_any_sync multi-split, and obtain their global digit offsets through a chained scan
+// with decoupled look-back (Adinets & Merrill 2022; Merrill & Garland 2016).  Stable.
+//
+// HBM traffic per pass: read 12 B + write 12 B per pair.  Histogram pre-pass: read 8 B per key.
+#include "build.cuh"
+
+namespace lcb {
+
+namespace {
+
+constexpr int kRadix = 256;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItems = 16;
+constexpr int kTile = kSortThreads * kItems;  // 4096 pairs per tile
+constexpr uint32_t kFlagAgg = 1u << 30, kFlagPrefix = 2u << 30, kValueMask = (1u << 30) - 1;
+constexpr int kSmallSortMax = 2048;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// Histogram of every 8-bit digit of every pass in one read of the keys.
+__global__ void __launch_bounds__(256) k_sort_histogram(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ ghist,
+                                                         int begin_bit, int passes) {
+    __shared__ uint32_t sh[8 * kRadix];
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint64_t k = keys[i] >> begin_bit;
+        for (int p = 0; p < passes; p++) {
+            atomicAdd(&sh[p * kRadix + (uint32_t)(k & 0xff)], 1u);
+            k >>= 8;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+        uint32_t c = sh[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// Exclusive scan of each pass's 256 bins (one block per pass).
+__global__ void __launch_bounds__(256) k_sort_scan(uint32_t *ghist) {
+    __shared__ uint32_t sh[kRadix];
+    uint32_t *h = ghist + blockIdx.x * kRadix;
+    uint32_t v = h[threadIdx.x];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < kRadix; off <<= 1) {
+        uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    h[threadIdx.x] = sh[threadIdx.x] - v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n, int shift,
+                                                                const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *ticket) {
+    __shared__ uint32_t warp_hist[kSortWarps][kRadix];
+    __shared__ uint32_t digit_base[kRadix];
+    __shared__ uint32_t tile_s;
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t base = tile * kTile + warp * (32 * kItems);
+
+    uint64_t key[kItems];
+    uint16_t rank[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        uint32_t idx = base + j * 32 + lane;
+        key[j] = idx < n ? kin[idx] : ~0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        uint32_t idx = base + j * 32 + lane;
+        bool valid = idx < n;
+        uint32_t d = (uint32_t)(key[j] >> shift) & 0xff;
+        uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (0x100u + lane));
+        int leader = __ffs(m) - 1;
+        uint32_t pre = 0;
+        if (valid && (int)lane == leader) {
+            pre = warp_hist[warp][d];
+            warp_hist[warp][d] = pre + __popc(m);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[j] = (uint16_t)(pre + __popc(m & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    {   // thread d owns digit d: warp offsets inside the tile, then decoupled look-back
+        const uint32_t d = threadIdx.x;
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) { uint32_t c = warp_hist[w][d]; warp_hist[w][d] = total; total += c; }
+        uint32_t *mine = status + (size_t)tile * kRadix + d;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st_volatile_u32(mine, kFlagPrefix | total);
+        } else {
+            st_volatile_u32(mine, kFlagAgg | total);
+            int look = (int)tile - 1;
+            while (true) {
+                uint32_t v = ld_volatile_u32(status + (size_t)look * kRadix + d);
+                uint32_t f = v >> 30;
+                if (f == 0) continue;
+                excl += v & kValueMask;
+                if (f == 2) break;
+                look--;
+            }
+            st_volatile_u32(mine, kFlagPrefix | (excl + total));
+        }
+        digit_base[d] = gbase[d] + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        uint32_t idx = base + j * 32 + lane;
+        if (idx < n) {
+            uint32_t d = (uint32_t)(key[j] >> shift) & 0xff;
+            uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[j];
+            kout[pos] = key[j];
+            vout[pos] = vin[idx];
+        }
+    }
+}
+
+// n <= 2048: one block, bitonic sort of (key, value) in shared memory; (key, value) compared
+// lexicographically so the result equals the stable sort when values are the input positions.
+__global__ void __launch_bounds__(1024) k_sort_small(uint64_t *keys, uint32_t *vals, uint32_t n) {
+    __shared__ uint64_t sk[kSmallSortMax];
+    __shared__ uint32_t sv[kSmallSortMax];
+    for (uint32_t i = threadIdx.x; i < kSmallSortMax; i += blockDim.x) {
+        sk[i] = i < n ? keys[i] : ~0ull;
+        sv[i] = i < n ? vals[i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= kSmallSortMax; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < kSmallSortMax; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    bool up = (i & k) == 0;
+                    uint64_t a = sk[i], b = sk[ixj];
+                    uint32_t va = sv[i], vb = sv[ixj];
+                    bool gt = a > b || (a == b && va > vb);
+                    if (gt == up) { sk[i] = b; sk[ixj] = a; sv[i] = vb; sv[ixj] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = sk[i]; vals[i] = sv[i]; }
+}
+
+}  // namespace
+
+size_t sort_scratch_bytes(uint32_t n, int passes) {
+    if (n <= (uint32_t)kSmallSortMax) return 256;
+    size_t tiles = (n + kTile - 1) / kTile;
+    return (size_t)8 * kRadix * 4 + 256 + (size_t)passes * tiles * kRadix * 4;
+}
+
+// Sorts by bits [begin_bit, begin_bit + 8*passes).  Returns true if the result is in (keys_alt, vals_alt).
+bool sort_pairs(cudaStream_t s, uint32_t n, uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, void *scratch,
+                int begin_bit, int passes, LaunchCounter &lc) {
+    if (n <= 1) return false;
+    if (n <= (uint32_t)kSmallSortMax) {
+        k_sort_small<<<1, 1024, 0, s>>>(keys, vals, n); lc.count++;
+        return false;
+    }
+    const size_t tiles = (n + kTile - 1) / kTile;
+    uint32_t *ghist = (uint32_t *)scratch;
+    uint32_t *tickets = ghist + 8 * kRadix;
+    uint32_t *status = tickets + 64;
+    cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n, passes), s);
+    int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
+    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+    k_sort_histogram<<<hist_blocks, 256, 0, s>>>(keys, n, ghist, begin_bit, passes); lc.count++;
+    k_sort_scan<<<passes, kRadix, 0, s>>>(ghist); lc.count++;
+    uint64_t *ki = keys, *ko = keys_alt;
+    uint32_t *vi = vals, *vo = vals_alt;
+    for (int p = 0; p < passes; p++) {
+        k_sort_onesweep<<<(unsigned)tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, begin_bit + 8 * p, ghist + p * kRadix,
+                                                                  status + (size_t)p * tiles * kRadix, tickets + p);
+        lc.count++;
+        uint64_t *tk = ki; ki = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
+    }
+    return (passes & 1) != 0;
+}
+
+}  // namespace lcb

@@ -1,0 +1,104 @@
+// rt_types.cuh — HBM-resident data layouts of the B200 ray-tracing device.
+//
+// Everything the traversal kernels touch is laid out for full-line access:
+//   WideNode   128 B, 128-byte aligned : one L2 line / four 32 B sectors, fetched as 8 x LDG.128
+//   PackedTri   48 B,  16-byte aligned : three float4 (v0|prim, v1, v2)
+//   InstanceRec 96 B,  16-byte aligned : six float4
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lcb {
+
+// 8-wide BVH node with 16-bit quantised child planes (a compressed-wide-BVH in the spirit of
+// Ylitie, Karras, Laine 2017, widened so that a node is exactly one 128-byte line).
+//   child plane k of child i :  org[k] + q[k][i] * 2^(e[k]-127)
+//   meta[i] : 0 = empty slot
+//             internal child : 0x20 | (24 + i)                      (i = slot)
+//             leaf child     : (unary count 1|3|7) << 5 | first prim offset (0..23)
+//   imask   : bit i set <=> slot i is an internal child; internal children are stored
+//             contiguously from child_base in ascending slot order
+//   prim_base : first PackedTri (BLAS) / first entry of the instance-id list (TLAS)
+struct alignas(128) WideNode {
+    float org[3];
+    uint8_t e[3];
+    uint8_t imask;
+    uint32_t child_base;
+    uint32_t prim_base;
+    uint8_t meta[8];
+    uint16_t qlo[3][8];
+    uint16_t qhi[3][8];
+};
+static_assert(sizeof(WideNode) == 128, "WideNode must be one 128-byte line");
+
+struct alignas(16) PackedTri {
+    float v0[3]; uint32_t prim;
+    float v1[3]; uint32_t pad1;
+    float v2[3]; uint32_t pad2;
+};
+static_assert(sizeof(PackedTri) == 48, "PackedTri is 48 bytes");
+
+// One slot of the instance table (what AccelImpl keeps per instance, cpu/accel.rs:270-296).
+struct alignas(16) InstanceRec {
+    float inv[12];            // world -> object, row-major 3x4
+    const WideNode *nodes;    // BLAS nodes (nullptr: empty mesh or invalid slot)
+    const PackedTri *tris;    // BLAS packed triangles
+    uint32_t visibility;
+    uint32_t user_id;
+    uint32_t flags;           // bit0 valid, bit1 opaque
+    uint32_t pad;
+    float affine[12];         // object -> world as given by the frontend (for instance_transform)
+};
+static_assert(sizeof(InstanceRec) == 128, "InstanceRec is 128 bytes");
+
+// Binary LBVH node produced by the fused hierarchy+refit kernel, consumed by the collapse.
+// child id: bit31 set -> leaf, low bits = position in the sorted primitive order.
+// Each child owns two float4 so the two arriving threads never write the same 16 bytes.
+struct alignas(16) BinNode {
+    float llo[3]; uint32_t left;
+    float lhi[3]; uint32_t lcount;
+    float rlo[3]; uint32_t right;
+    float rhi[3]; uint32_t rcount;
+};
+static_assert(sizeof(BinNode) == 64, "BinNode is 64 bytes");
+
+struct alignas(16) PrimBox { float lo[3]; uint32_t pad0; float hi[3]; uint32_t pad1; };
+
+// device-side scratch header of one build
+struct BuildHeader {
+    int bounds_lo[3];   // ordered-int encoded float min of centroids
+    int bounds_hi[3];
+    uint32_t root;          // binary root id
+    uint32_t node_count;    // wide nodes allocated
+    uint32_t prim_count;    // packed prims allocated
+    uint32_t emitted;       // primitives emitted into leaves
+    uint32_t ticket;        // collapse work tickets
+    uint32_t max_depth;
+    uint32_t error;         // nonzero: builder failure code
+    uint32_t pad[3];
+    float root_lo[3]; float pad1;
+    float root_hi[3]; float pad2;
+};
+
+constexpr int kMaxWideDepth = 40;   // builder fails loudly beyond this; traversal stack is sized for it
+constexpr int kTraversalStack = 96; // >= TLAS depth + 3 + BLAS depth
+
+__host__ __device__ inline int float_to_ordered(float f) {
+    int i;
+#ifdef __CUDA_ARCH__
+    i = __float_as_int(f);
+#else
+    memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ inline float ordered_to_float(int i) {
+    i = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+}  // namespace lcb

@@ -1,0 +1,337 @@
+// trace.cu — persistent-thread two-level traversal of the 8-wide quantised BVH.
+//
+// Replaces rtcIntersect1 / rtcOccluded1 behind AccelImpl::trace_closest / trace_any
+// (cpu/accel.rs:449-535) for whole buffers of rays.
+//
+// Execution model: one ray per lane; warps are persistent and refill idle lanes every
+// iteration from a warp-local pool of ray indices that is topped up with ONE global atomic per
+// 128 rays (warp-synchronous work distribution, ballots only).  Each iteration is "if-if":
+// every lane that owns a node group pops one child and tests its 8 quantised child boxes,
+// then every lane that owns primitives tests them, so the warp stays converged on the two
+// expensive code regions.  A node is one 128-byte line fetched as 8 x LDG.128; the traversal
+// stack holds one (child_base, hit mask) group per level and lives in local memory.
+//
+// The per-triangle arithmetic is the canonical fp32 sequence documented in DESIGN.md §3 and
+// restated independently in oracle/oracle.c: every operation is an explicit round-to-nearest
+// intrinsic so that nvcc cannot contract or reorder it.  Box culling is conservative with
+// respect to that arithmetic (planes padded by 2^-20 of the L-inf distance to the node), so
+// results do not depend on the tree.
+#include "build.cuh"
+
+namespace lcb {
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kTraceThreads = 128;
+constexpr int kChunk = 128;  // ray indices fetched per global atomic
+
+struct RaySetup {
+    float ox, oy, oz, dx, dy, dz;  // ray in the current space (world or object)
+    float ix, iy, iz;              // clamped reciprocal direction for slab tests
+    float sx, sy, sz;              // shear constants of the canonical triangle test
+    int kz;
+    uint32_t octinv;               // 7 ^ sign bits (bit k = direction negative along k)
+};
+
+__device__ __forceinline__ float safe_rcp(float d) {
+    // |d| < 1e-20 is treated as 1e-20 with d's sign bit: keeps slab arithmetic finite; culling stays conservative
+    float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
+    return __frcp_rn(a);
+}
+
+__device__ __forceinline__ void finish_setup(RaySetup &r) {
+    r.ix = safe_rcp(r.dx); r.iy = safe_rcp(r.dy); r.iz = safe_rcp(r.dz);
+    const uint32_t sgn = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
+    r.octinv = 7u ^ sgn;
+    int kz = 0;
+    float m = fabsf(r.dx);
+    if (fabsf(r.dy) > m) { kz = 1; m = fabsf(r.dy); }
+    if (fabsf(r.dz) > m) { kz = 2; }
+    r.kz = kz;
+    const float dz = kz == 0 ? r.dx : (kz == 1 ? r.dy : r.dz);
+    const float dx = kz == 0 ? r.dy : (kz == 1 ? r.dz : r.dx);
+    const float dy = kz == 0 ? r.dz : (kz == 1 ? r.dx : r.dy);
+    r.sx = __fdiv_rn(dx, dz);
+    r.sy = __fdiv_rn(dy, dz);
+    r.sz = __frcp_rn(dz);
+}
+
+__device__ __forceinline__ void setup_world(RaySetup &r, const float4 a, const float4 b) {
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = b.x; r.dy = b.y; r.dz = b.z;
+    finish_setup(r);
+}
+
+// world -> object with the canonical nested-fma order
+__device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
+    r.ox = __fmaf_rn(m0.x, wo.x, __fmaf_rn(m0.y, wo.y, __fmaf_rn(m0.z, wo.z, m0.w)));
+    r.oy = __fmaf_rn(m1.x, wo.x, __fmaf_rn(m1.y, wo.y, __fmaf_rn(m1.z, wo.z, m1.w)));
+    r.oz = __fmaf_rn(m2.x, wo.x, __fmaf_rn(m2.y, wo.y, __fmaf_rn(m2.z, wo.z, m2.w)));
+    r.dx = __fmaf_rn(m0.x, wd.x, __fmaf_rn(m0.y, wd.y, __fmul_rn(m0.z, wd.z)));
+    r.dy = __fmaf_rn(m1.x, wd.x, __fmaf_rn(m1.y, wd.y, __fmul_rn(m1.z, wd.z)));
+    r.dz = __fmaf_rn(m2.x, wd.x, __fmaf_rn(m2.y, wd.y, __fmul_rn(m2.z, wd.z)));
+    finish_setup(r);
+}
+
+__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
+__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+
+// Tests the 8 children of one node.  Returns the hit mask: bits 24..31 internal children in
+// traversal priority order for this ray's octant, bits 0..23 leaf primitives.
+__device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ node, const RaySetup &r, float tmin, float tmax,
+                                                   uint32_t &child_base, uint32_t &prim_base, uint32_t &imask) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(node);
+    const uint4 n0 = __ldg(p), n1 = __ldg(p + 1);
+    const bool neg_x = (r.octinv & 1u) == 0, neg_y = (r.octinv & 2u) == 0, neg_z = (r.octinv & 4u) == 0;
+    // near/far plane vectors by direction sign: free, it is only an address
+    const uint4 qnx = __ldg(p + (neg_x ? 5 : 2)), qfx = __ldg(p + (neg_x ? 2 : 5));
+    const uint4 qny = __ldg(p + (neg_y ? 6 : 3)), qfy = __ldg(p + (neg_y ? 3 : 6));
+    const uint4 qnz = __ldg(p + (neg_z ? 7 : 4)), qfz = __ldg(p + (neg_z ? 4 : 7));
+    child_base = n1.x; prim_base = n1.y; imask = n0.w >> 24;
+    const float sclx = __uint_as_float((n0.w & 0xffu) << 23), scly = __uint_as_float((n0.w & 0xff00u) << 15), sclz = __uint_as_float((n0.w & 0xff0000u) << 7);
+    const float rx = __uint_as_float(n0.x) - r.ox, ry = __uint_as_float(n0.y) - r.oy, rz = __uint_as_float(n0.z) - r.oz;
+    // conservative padding: 2^-20 of the L-inf distance from the ray origin to the far side of the node frame
+    const float R = fmaxf(fmaxf(fabsf(rx) + 65535.0f * sclx, fabsf(ry) + 65535.0f * scly), fabsf(rz) + 65535.0f * sclz);
+    const float pad = R * (1.0f / 1048576.0f);
+    const float ax = sclx * r.ix, ay = scly * r.iy, az = sclz * r.iz;
+    const float cx = rx * r.ix, cy = ry * r.iy, cz = rz * r.iz;
+    const float px = pad * fabsf(r.ix), py = pad * fabsf(r.iy), pz = pad * fabsf(r.iz);
+    const float bnx = cx - px, bfx = cx + px, bny = cy - py, bfy = cy + py, bnz = cz - pz, bfz = cz + pz;
+    uint32_t hits = 0;
+#define LCB_CHILD(I, WORD, CONV, METAWORD, METASHIFT)                                                        \
+    {                                                                                                        \
+        const float tn = fmaxf(fmaxf(fmaf(CONV(qnx.WORD), ax, bnx), fmaf(CONV(qny.WORD), ay, bny)),          \
+                               fmaxf(fmaf(CONV(qnz.WORD), az, bnz), tmin));                                  \
+        const float tf = fminf(fminf(fmaf(CONV(qfx.WORD), ax, bfx), fmaf(CONV(qfy.WORD), ay, bfy)),          \
+                               fminf(fmaf(CONV(qfz.WORD), az, bfz), tmax));                                  \
+        if (tn <= tf) {                                                                                      \
+            const uint32_t meta = (METAWORD >> METASHIFT) & 0xffu;                                           \
+            const uint32_t low = meta & 0x1fu;                                                               \
+            const uint32_t bit = low >= 24u ? 24u + ((uint32_t)(I) ^ r.octinv) : low;                        \
+            hits |= (meta >> 5) << bit;                                                                      \
+        }                                                                                                    \
+    }
+    LCB_CHILD(0, x, q16_lo, n1.z, 0)
+    LCB_CHILD(1, x, q16_hi, n1.z, 8)
+    LCB_CHILD(2, y, q16_lo, n1.z, 16)
+    LCB_CHILD(3, y, q16_hi, n1.z, 24)
+    LCB_CHILD(4, z, q16_lo, n1.w, 0)
+    LCB_CHILD(5, z, q16_hi, n1.w, 8)
+    LCB_CHILD(6, w, q16_lo, n1.w, 16)
+    LCB_CHILD(7, w, q16_hi, n1.w, 24)
+#undef LCB_CHILD
+    return hits;
+}
+
+__device__ __forceinline__ float pick(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+
+// The canonical fp32 ray/triangle evaluation (oracle.c canon_tri).
+__device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin, float tmax, const float4 v0, const float4 v1, const float4 v2,
+                                                   float &t_out, float &u_out, float &v_out) {
+    const float a0 = __fsub_rn(v0.x, r.ox), a1 = __fsub_rn(v0.y, r.oy), a2 = __fsub_rn(v0.z, r.oz);
+    const float b0 = __fsub_rn(v1.x, r.ox), b1 = __fsub_rn(v1.y, r.oy), b2 = __fsub_rn(v1.z, r.oz);
+    const float c0 = __fsub_rn(v2.x, r.ox), c1 = __fsub_rn(v2.y, r.oy), c2 = __fsub_rn(v2.z, r.oz);
+    const int kz = r.kz;
+    const float a_z = pick(kz, a0, a1, a2), a_x = pick(kz, a1, a2, a0), a_y = pick(kz, a2, a0, a1);
+    const float b_z = pick(kz, b0, b1, b2), b_x = pick(kz, b1, b2, b0), b_y = pick(kz, b2, b0, b1);
+    const float c_z = pick(kz, c0, c1, c2), c_x = pick(kz, c1, c2, c0), c_y = pick(kz, c2, c0, c1);
+    const float ax = __fmaf_rn(-r.sx, a_z, a_x), ay = __fmaf_rn(-r.sy, a_z, a_y);
+    const float bx = __fmaf_rn(-r.sx, b_z, b_x), by = __fmaf_rn(-r.sy, b_z, b_y);
+    const float cx = __fmaf_rn(-r.sx, c_z, c_x), cy = __fmaf_rn(-r.sy, c_z, c_y);
+    float U = __fsub_rn(__fmul_rn(cx, by), __fmul_rn(cy, bx));
+    float V = __fsub_rn(__fmul_rn(ax, cy), __fmul_rn(ay, cx));
+    float W = __fsub_rn(__fmul_rn(bx, ay), __fmul_rn(by, ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = __double2float_rn(__dsub_rn(__dmul_rn((double)cx, (double)by), __dmul_rn((double)cy, (double)bx)));
+        V = __double2float_rn(__dsub_rn(__dmul_rn((double)ax, (double)cy), __dmul_rn((double)ay, (double)cx)));
+        W = __double2float_rn(__dsub_rn(__dmul_rn((double)bx, (double)ay), __dmul_rn((double)by, (double)ax)));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    if (det == 0.0f) return false;
+    const float az = __fmul_rn(r.sz, a_z), bz = __fmul_rn(r.sz, b_z), cz = __fmul_rn(r.sz, c_z);
+    const float T = __fmaf_rn(U, az, __fmaf_rn(V, bz, __fmul_rn(W, cz)));
+    const float rdet = __frcp_rn(det);
+    const float t = __fmul_rn(T, rdet);
+    if (!(t > tmin && t <= tmax)) return false;
+    t_out = t; u_out = __fmul_rn(V, rdet); v_out = __fmul_rn(W, rdet);
+    return true;
+}
+
+template <bool ANY, bool COUNTERS>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out, unsigned long long count,
+                                                         uint32_t mask, unsigned long long *work_counter, TraceCounters *ctr) {
+    uint2 stack[kTraversalStack];
+    const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
+
+    // warp-uniform pool of ray indices
+    unsigned long long pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+
+    bool has_ray = false;
+    unsigned long long ray_idx = 0;
+    RaySetup r;
+    float tmin = 0.f, tbest = 0.f, ray_tmax = 0.f;
+    uint32_t hit_inst = 0xffffffffu, hit_prim = 0xffffffffu;
+    float hit_u = 0.f, hit_v = 0.f;
+    uint32_t cur_inst = 0xffffffffu;
+    const WideNode *nodes = acc.tlas_nodes;
+    const PackedTri *tris = nullptr;
+    uint2 G = make_uint2(0, 0);
+    int sp = 0;
+    unsigned long long n_nodes = 0, n_tris = 0, n_inst = 0, n_rays = 0;
+
+    for (;;) {
+        // ---- refill idle lanes ------------------------------------------------------------
+        const uint32_t idle = __ballot_sync(kFull, !has_ray);
+        if (idle) {
+            if (pool_next == pool_end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)kChunk);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= count) { exhausted = true; }
+                else { pool_next = base; pool_end = base + kChunk < count ? base + kChunk : count; }
+            }
+            if (pool_next == pool_end) {
+                if (idle == kFull) break;  // nothing left anywhere in this warp
+            } else {
+                const unsigned long long mine = pool_next + __popc(idle & lt_mask);
+                if (!has_ray && mine < pool_end) {
+                    ray_idx = mine;
+                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                    setup_world(r, ra, rb);
+                    tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
+                    hit_inst = 0xffffffffu; hit_prim = 0xffffffffu; hit_u = 0.f; hit_v = 0.f;
+                    cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+                    sp = 0;
+                    G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
+                    has_ray = true;
+                    if (COUNTERS) n_rays++;
+                }
+                const unsigned long long adv = pool_next + __popc(idle);
+                pool_next = adv < pool_end ? adv : pool_end;
+            }
+        }
+        if (!has_ray) continue;
+
+        bool done = false;
+        uint2 Gt = make_uint2(0, 0);
+        // ---- node phase -------------------------------------------------------------------
+        if (G.y & 0xff000000u) {
+            const uint32_t bit = 31u - __clz(G.y);
+            G.y &= ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ r.octinv;
+            const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
+            const WideNode *node = nodes + (G.x + rel);
+            if (G.y & 0xff000000u) stack[sp++] = G;
+            uint32_t child_base, prim_base, imask;
+            const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
+            if (COUNTERS) n_nodes++;
+            G = make_uint2(child_base, (hits & 0xff000000u) | imask);
+            Gt = make_uint2(prim_base, hits & 0x00ffffffu);
+        } else {
+            Gt = G;
+            G = make_uint2(0, 0);
+        }
+        // ---- primitive phase --------------------------------------------------------------
+        while (Gt.y) {
+            const uint32_t bit = __ffs(Gt.y) - 1;
+            Gt.y &= Gt.y - 1;
+            if (cur_inst == 0xffffffffu) {
+                // TLAS leaf: enter an instance
+                const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
+                const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
+                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
+                if ((meta.x & mask) == 0u) continue;
+                if (Gt.y) stack[sp++] = Gt;
+                if (G.y & 0xff000000u) stack[sp++] = G;
+                stack[sp++] = make_uint2(0u, 0u);  // sentinel: return to world space
+                const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+                const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+                nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+                tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                setup_object(r, ra, rb, m0, m1, m2);
+                cur_inst = inst;
+                G = make_uint2(0u, 0x80000000u);
+                Gt.y = 0;
+                if (COUNTERS) n_inst++;
+            } else {
+                const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
+                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                if (COUNTERS) n_tris++;
+                float t, u, v;
+                if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, u, v)) {
+                    if (ANY) { done = true; hit_inst = cur_inst; break; }
+                    const uint32_t prim = __float_as_uint(v0.w);
+                    const bool better = t < tbest || hit_inst == 0xffffffffu ||
+                                        (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
+                    if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; }
+                }
+            }
+        }
+        // ---- pop phase --------------------------------------------------------------------
+        if (!done && (G.y & 0xff000000u) == 0u) {
+            for (;;) {
+                if (sp == 0) { done = true; break; }
+                G = stack[--sp];
+                if (G.y != 0u) break;
+                // sentinel: back to world space
+                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                setup_world(r, ra, rb);
+                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+            }
+        }
+        if (done) {
+            if (ANY) {
+                reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
+            } else {
+                uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
+                o[0] = make_uint2(hit_inst, hit_prim);
+                o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
+                o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), 0u);
+            }
+            has_ray = false;
+        }
+    }
+    if (COUNTERS) {
+        atomicAdd(&ctr->nodes_visited, n_nodes);
+        atomicAdd(&ctr->tris_tested, n_tris);
+        atomicAdd(&ctr->instance_entries, n_inst);
+        atomicAdd(&ctr->rays, n_rays);
+    }
+}
+
+template <bool ANY, bool COUNTERS>
+void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uint64_t count, uint32_t mask, unsigned long long *work_counter,
+            TraceCounters *ctr, LaunchCounter &lc) {
+    static int blocks_per_sm = 0, sms = 0;
+    if (!blocks_per_sm) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<ANY, COUNTERS>, kTraceThreads, 0);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
+    unsigned long long want = (count + kTraceThreads - 1) / kTraceThreads;
+    unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid == 0) return;
+    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr);
+    lc.count++;
+}
+
+}  // namespace
+
+void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
+                   TraceCounters *counters, LaunchCounter &lc) {
+    if (counters) launch<false, true>(s, a, rays, hits, count, mask, work_counter, counters, lc);
+    else launch<false, false>(s, a, rays, hits, count, mask, work_counter, nullptr, lc);
+}
+
+void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
+               LaunchCounter &lc) {
+    launch<true, false>(s, a, rays, occluded, count, mask, work_counter, nullptr, lc);
+}
+
+}  // namespace lcb

@@ -1,0 +1,586 @@
+/*
+ * oracle.c — CPU restatement of the reference ray-tracing hot path.  See oracle.h for the
+ * reference file:line map.  TEST INFRASTRUCTURE ONLY (checker + CPU baseline), never the
+ * product path.  PARITY UNPINNED (Embree, the reference's arithmetic, is absent).
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -shared -fPIC (see oracle/Makefile).  -ffp-contract=off
+ * is REQUIRED: the canonical arithmetic below is defined operation by operation.
+ */
+#define _GNU_SOURCE
+#include "oracle.h"
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define MOD_PRIMITIVE 1u
+#define MOD_TRANSFORM 2u
+#define MOD_OPAQUE_ON 4u
+#define MOD_OPAQUE_OFF 8u
+#define MOD_VISIBILITY 16u
+#define MOD_USER_ID 32u
+
+/* ------------------------------------------------------------------------------------ */
+/* scene model                                                                           */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct bvh_node {
+    float lo[3], hi[3];
+    uint32_t left;  /* internal: index of left child (right = left+1); leaf: first prim slot */
+    uint32_t count; /* 0 = internal */
+} bvh_node;
+
+typedef struct mesh {
+    const uint8_t *verts;
+    size_t vstride, nverts;
+    const uint8_t *indices;
+    size_t istride, ntris;
+    int built;
+    bvh_node *nodes;
+    uint32_t n_nodes;
+    uint32_t *prims;
+} mesh;
+
+/* accel.rs:270-296 */
+typedef struct instance {
+    float affine[12];
+    float inv[12];
+    uint32_t user_id, visible;
+    int opaque, valid;
+    uint64_t mesh;
+} instance;
+
+struct oracle_scene {
+    mesh *meshes;
+    size_t n_meshes, cap_meshes;
+    instance *insts;
+    size_t n_insts, cap_insts;
+};
+
+static void die(const char *msg) {
+    fprintf(stderr, "[oracle] fatal: %s\n", msg);
+    abort(); /* reference aborts on every error: backend_impl/src/lib.rs:101-131 */
+}
+
+oracle_scene *oracle_scene_new(void) { return (oracle_scene *)calloc(1, sizeof(oracle_scene)); }
+
+void oracle_scene_free(oracle_scene *s) {
+    if (!s) return;
+    for (size_t i = 0; i < s->n_meshes; i++) { free(s->meshes[i].nodes); free(s->meshes[i].prims); }
+    free(s->meshes);
+    free(s->insts);
+    free(s);
+}
+
+uint64_t oracle_mesh_new(oracle_scene *s) {
+    if (s->n_meshes == s->cap_meshes) {
+        s->cap_meshes = s->cap_meshes ? 2 * s->cap_meshes : 8;
+        s->meshes = (mesh *)realloc(s->meshes, s->cap_meshes * sizeof(mesh));
+    }
+    memset(&s->meshes[s->n_meshes], 0, sizeof(mesh));
+    return s->n_meshes++;
+}
+
+void oracle_mesh_set(oracle_scene *s, uint64_t id, const void *vertices, size_t vstride, size_t nverts,
+                     const void *indices, size_t istride, size_t ntris) {
+    if (id >= s->n_meshes) die("bad mesh id");
+    if (istride != 12) die("index stride must be 12 (api/runtime.cpp:191)");
+    mesh *m = &s->meshes[id];
+    m->verts = (const uint8_t *)vertices; m->vstride = vstride; m->nverts = nverts;
+    m->indices = (const uint8_t *)indices; m->istride = istride; m->ntris = ntris;
+}
+
+static inline void tri_verts(const mesh *m, uint32_t prim, const float **a, const float **b, const float **c) {
+    const uint32_t *ix = (const uint32_t *)(m->indices + (size_t)prim * m->istride);
+    *a = (const float *)(m->verts + (size_t)ix[0] * m->vstride);
+    *b = (const float *)(m->verts + (size_t)ix[1] * m->vstride);
+    *c = (const float *)(m->verts + (size_t)ix[2] * m->vstride);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* CPU BVH: binned SAH, leaves <= 4 triangles.  Only an accelerator for the oracle.      */
+/* ------------------------------------------------------------------------------------ */
+
+#define NBINS 16
+typedef struct { float lo[3], hi[3]; } box3;
+static inline void box_empty(box3 *b) { for (int k = 0; k < 3; k++) { b->lo[k] = FLT_MAX; b->hi[k] = -FLT_MAX; } }
+static inline void box_grow(box3 *b, const box3 *o) { for (int k = 0; k < 3; k++) { if (o->lo[k] < b->lo[k]) b->lo[k] = o->lo[k]; if (o->hi[k] > b->hi[k]) b->hi[k] = o->hi[k]; } }
+static inline float box_area(const box3 *b) {
+    float dx = b->hi[0] - b->lo[0], dy = b->hi[1] - b->lo[1], dz = b->hi[2] - b->lo[2];
+    if (dx < 0) return 0.f;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+typedef struct { uint32_t node, first, count; } build_task;
+
+void oracle_mesh_commit(oracle_scene *s, uint64_t id) {
+    if (id >= s->n_meshes) die("bad mesh id");
+    mesh *m = &s->meshes[id];
+    free(m->nodes); free(m->prims); m->nodes = NULL; m->prims = NULL; m->n_nodes = 0;
+    m->built = 1;
+    size_t n = m->ntris;
+    if (n == 0) return;
+    box3 *tb = (box3 *)malloc(n * sizeof(box3));
+    float *cen = (float *)malloc(n * 3 * sizeof(float));
+    m->prims = (uint32_t *)malloc(n * sizeof(uint32_t));
+    m->nodes = (bvh_node *)malloc((2 * n) * sizeof(bvh_node));
+    for (size_t i = 0; i < n; i++) {
+        const float *a, *b, *c; tri_verts(m, (uint32_t)i, &a, &b, &c);
+        for (int k = 0; k < 3; k++) {
+            float lo = fminf(a[k], fminf(b[k], c[k])), hi = fmaxf(a[k], fmaxf(b[k], c[k]));
+            tb[i].lo[k] = lo; tb[i].hi[k] = hi; cen[3 * i + k] = 0.5f * lo + 0.5f * hi;
+        }
+        m->prims[i] = (uint32_t)i;
+    }
+    size_t cap = 64, top = 0;
+    build_task *stack = (build_task *)malloc(cap * sizeof(build_task));
+    uint32_t n_nodes = 1;
+    stack[top++] = (build_task){0, 0, (uint32_t)n};
+    while (top) {
+        build_task t = stack[--top];
+        bvh_node *nd = &m->nodes[t.node];
+        box3 nb, cb; box_empty(&nb); box_empty(&cb);
+        for (uint32_t i = t.first; i < t.first + t.count; i++) {
+            uint32_t p = m->prims[i];
+            box_grow(&nb, &tb[p]);
+            for (int k = 0; k < 3; k++) { float c = cen[3 * p + k]; if (c < cb.lo[k]) cb.lo[k] = c; if (c > cb.hi[k]) cb.hi[k] = c; }
+        }
+        memcpy(nd->lo, nb.lo, 12); memcpy(nd->hi, nb.hi, 12);
+        if (t.count <= 4) { nd->left = t.first; nd->count = t.count; continue; }
+        /* binned SAH over the 3 axes */
+        int best_axis = -1, best_bin = -1; float best_cost = FLT_MAX;
+        for (int ax = 0; ax < 3; ax++) {
+            float ext = cb.hi[ax] - cb.lo[ax];
+            if (!(ext > 0)) continue;
+            box3 bb[NBINS]; uint32_t bc[NBINS];
+            for (int j = 0; j < NBINS; j++) { box_empty(&bb[j]); bc[j] = 0; }
+            float scale = NBINS / ext;
+            for (uint32_t i = t.first; i < t.first + t.count; i++) {
+                uint32_t p = m->prims[i];
+                int j = (int)((cen[3 * p + ax] - cb.lo[ax]) * scale); if (j >= NBINS) j = NBINS - 1; if (j < 0) j = 0;
+                bc[j]++; box_grow(&bb[j], &tb[p]);
+            }
+            float la[NBINS], ra[NBINS]; uint32_t lc[NBINS], rc[NBINS];
+            box3 acc; box_empty(&acc); uint32_t c = 0;
+            for (int j = 0; j < NBINS - 1; j++) { box_grow(&acc, &bb[j]); c += bc[j]; la[j] = box_area(&acc); lc[j] = c; }
+            box_empty(&acc); c = 0;
+            for (int j = NBINS - 1; j > 0; j--) { box_grow(&acc, &bb[j]); c += bc[j]; ra[j - 1] = box_area(&acc); rc[j - 1] = c; }
+            for (int j = 0; j < NBINS - 1; j++) {
+                if (lc[j] == 0 || rc[j] == 0) continue;
+                float cost = la[j] * lc[j] + ra[j] * rc[j];
+                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = j; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) {
+            mid = t.first + t.count / 2; /* all centroids coincide: split by position in list */
+        } else {
+            float ext = cb.hi[best_axis] - cb.lo[best_axis], scale = NBINS / ext;
+            uint32_t i = t.first, j = t.first + t.count;
+            while (i < j) {
+                uint32_t p = m->prims[i];
+                int b = (int)((cen[3 * p + best_axis] - cb.lo[best_axis]) * scale); if (b >= NBINS) b = NBINS - 1; if (b < 0) b = 0;
+                if (b <= best_bin) i++; else { j--; m->prims[i] = m->prims[j]; m->prims[j] = p; }
+            }
+            mid = i;
+            if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
+        }
+        nd->left = n_nodes; nd->count = 0;
+        n_nodes += 2;
+        if (top + 2 > cap) { cap *= 2; stack = (build_task *)realloc(stack, cap * sizeof(build_task)); }
+        stack[top++] = (build_task){nd->left, t.first, mid - t.first};
+        stack[top++] = (build_task){nd->left + 1, mid, t.first + t.count - mid};
+    }
+    m->n_nodes = n_nodes;
+    free(stack); free(tb); free(cen);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* AccelImpl::update — accel.rs:324-447                                                  */
+/* ------------------------------------------------------------------------------------ */
+
+void oracle_invert_affine(const float m[12], float inv[12]) {
+    /* double adjugate inverse of the 3x3 part, translation = -inv*t, one rounding to fp32 */
+    double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    double tx = m[3], ty = m[7], tz = m[11];
+    double c00 = e * i - f * h, c01 = c * h - b * i, c02 = b * f - c * e;
+    double c10 = f * g - d * i, c11 = a * i - c * g, c12 = c * d - a * f;
+    double c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+    double det = a * c00 + b * c10 + c * c20;
+    double r = 1.0 / det;
+    double n00 = c00 * r, n01 = c01 * r, n02 = c02 * r;
+    double n10 = c10 * r, n11 = c11 * r, n12 = c12 * r;
+    double n20 = c20 * r, n21 = c21 * r, n22 = c22 * r;
+    inv[0] = (float)n00; inv[1] = (float)n01; inv[2] = (float)n02; inv[3] = (float)(-(n00 * tx + n01 * ty + n02 * tz));
+    inv[4] = (float)n10; inv[5] = (float)n11; inv[6] = (float)n12; inv[7] = (float)(-(n10 * tx + n11 * ty + n12 * tz));
+    inv[8] = (float)n20; inv[9] = (float)n21; inv[10] = (float)n22; inv[11] = (float)(-(n20 * tx + n21 * ty + n22 * tz));
+}
+
+static const float IDENTITY[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+
+void oracle_accel_update(oracle_scene *s, uint32_t instance_count, const oracle_mod *mods, size_t n_mods) {
+    /* grow with default (invalid) instances / shrink by popping: accel.rs:345-353 */
+    if (instance_count > s->cap_insts) {
+        s->cap_insts = instance_count;
+        s->insts = (instance *)realloc(s->insts, s->cap_insts * sizeof(instance));
+    }
+    for (size_t i = s->n_insts; i < instance_count; i++) {
+        instance *in = &s->insts[i];
+        memset(in, 0, sizeof(*in));
+        memcpy(in->affine, IDENTITY, sizeof(IDENTITY)); memcpy(in->inv, IDENTITY, sizeof(IDENTITY));
+        in->visible = 0xff; in->opaque = 1; in->valid = 0;
+    }
+    s->n_insts = instance_count;
+    for (size_t k = 0; k < n_mods; k++) {
+        const oracle_mod *m = &mods[k];
+        if (m->index >= s->n_insts) die("modification index out of range");
+        instance *in = &s->insts[m->index];
+        if (m->flags & MOD_PRIMITIVE) { /* accel.rs:355-377: resets mask/opaque, takes affine + user_id as given */
+            if (m->mesh >= s->n_meshes || !s->meshes[m->mesh].built) die("Mesh not built");
+            memcpy(in->affine, m->affine, sizeof(in->affine));
+            in->visible = 0xff; in->user_id = m->user_id; in->opaque = 1; in->valid = 1; in->mesh = m->mesh;
+        }
+        if (m->flags & MOD_OPAQUE_ON) in->opaque = 1;
+        else if (m->flags & MOD_OPAQUE_OFF) in->opaque = 0;
+        if (m->flags & MOD_TRANSFORM) { if (!in->valid) die("TRANSFORM on empty instance"); memcpy(in->affine, m->affine, sizeof(in->affine)); }
+        if (m->flags & MOD_VISIBILITY) { if (!in->valid) die("VISIBILITY on empty instance"); in->visible = m->visibility; }
+        if (m->flags & MOD_USER_ID) { if (!in->valid) die("USER_ID on empty instance"); in->user_id = m->user_id; }
+    }
+    for (size_t i = 0; i < s->n_insts; i++) oracle_invert_affine(s->insts[i].affine, s->insts[i].inv);
+}
+
+void oracle_instance_transform(const oracle_scene *s, uint32_t i, float a[12]) { memcpy(a, s->insts[i].affine, 48); }
+uint32_t oracle_instance_user_id(const oracle_scene *s, uint32_t i) { return s->insts[i].user_id; }
+uint32_t oracle_instance_visibility(const oracle_scene *s, uint32_t i) { return s->insts[i].visible; }
+uint32_t oracle_instance_count(const oracle_scene *s) { return (uint32_t)s->n_insts; }
+
+/* ------------------------------------------------------------------------------------ */
+/* The canonical fp32 arithmetic                                                         */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct ray_frame { /* per (ray, instance) */
+    float o[3], d[3];
+    int kx, ky, kz;
+    float sx, sy, sz;
+} ray_frame;
+
+/* world -> object: o' = Minv*o + t (nested fmaf, innermost = z term + translation), d' = Minv*d */
+static inline void xform_ray(const float inv[12], const float o[3], const float d[3], ray_frame *f) {
+    for (int r = 0; r < 3; r++) {
+        const float *m = inv + 4 * r;
+        f->o[r] = fmaf(m[0], o[0], fmaf(m[1], o[1], fmaf(m[2], o[2], m[3])));
+        f->d[r] = fmaf(m[0], d[0], fmaf(m[1], d[1], m[2] * d[2]));
+    }
+    int kz = 0;
+    if (fabsf(f->d[1]) > fabsf(f->d[0])) kz = 1;
+    if (fabsf(f->d[2]) > fabsf(f->d[kz])) kz = 2;
+    int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
+    if (f->d[kz] < 0.0f) { int t = kx; kx = ky; ky = t; }
+    f->kx = kx; f->ky = ky; f->kz = kz;
+    f->sx = f->d[kx] / f->d[kz];
+    f->sy = f->d[ky] / f->d[kz];
+    f->sz = 1.0f / f->d[kz];
+}
+
+/* Watertight edge-function test (after Woop, Benthin, Wald 2013) with this fixed op order. */
+static inline int canon_tri(const ray_frame *f, float tmin, float tmax, const float *v0, const float *v1, const float *v2,
+                            float *t_out, float *u_out, float *v_out) {
+    const int kx = f->kx, ky = f->ky, kz = f->kz;
+    const float a_x = v0[kx] - f->o[kx], a_y = v0[ky] - f->o[ky], a_z = v0[kz] - f->o[kz];
+    const float b_x = v1[kx] - f->o[kx], b_y = v1[ky] - f->o[ky], b_z = v1[kz] - f->o[kz];
+    const float c_x = v2[kx] - f->o[kx], c_y = v2[ky] - f->o[ky], c_z = v2[kz] - f->o[kz];
+    const float ax = fmaf(-f->sx, a_z, a_x), ay = fmaf(-f->sy, a_z, a_y);
+    const float bx = fmaf(-f->sx, b_z, b_x), by = fmaf(-f->sy, b_z, b_y);
+    const float cx = fmaf(-f->sx, c_z, c_x), cy = fmaf(-f->sy, c_z, c_y);
+    float U = cx * by - cy * bx;
+    float V = ax * cy - ay * cx;
+    float W = bx * ay - by * ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)((double)cx * (double)by - (double)cy * (double)bx);
+        V = (float)((double)ax * (double)cy - (double)ay * (double)cx);
+        W = (float)((double)bx * (double)ay - (double)by * (double)ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return 0;
+    const float det = (U + V) + W;
+    if (det == 0.0f) return 0;
+    const float az = f->sz * a_z, bz = f->sz * b_z, cz = f->sz * c_z;
+    const float T = fmaf(U, az, fmaf(V, bz, W * cz));
+    const float rdet = 1.0f / det;
+    const float t = T * rdet;
+    if (!(t > tmin && t <= tmax)) return 0;
+    *t_out = t; *u_out = V * rdet; *v_out = W * rdet;
+    return 1;
+}
+
+int oracle_canonical_triangle(const float o[3], const float d[3], float tmin, float tmax,
+                              const float v0[3], const float v1[3], const float v2[3], float *t, float *u, float *v) {
+    ray_frame f; xform_ray(IDENTITY, o, d, &f);
+    return canon_tri(&f, tmin, tmax, v0, v1, v2, t, u, v);
+}
+
+typedef struct best_hit { float t, u, v; uint32_t inst, prim; int found; } best_hit;
+
+static inline void consider(best_hit *b, float t, float u, float v, uint32_t inst, uint32_t prim) {
+    /* closest; ties -> lowest (inst, prim) */
+    if (!b->found || t < b->t || (t == b->t && (inst < b->inst || (inst == b->inst && prim < b->prim)))) {
+        b->found = 1; b->t = t; b->u = u; b->v = v; b->inst = inst; b->prim = prim;
+    }
+}
+
+/* conservative slab test in double against the box padded by 2^-18 * Linf(ray origin, box) */
+static inline int box_cull(const float lo[3], const float hi[3], const float o[3], const float d[3], double tmin, double tbest,
+                           double *tnear_out) {
+    double R = 0.0;
+    for (int k = 0; k < 3; k++) { double a = fabs((double)lo[k] - o[k]), b = fabs((double)hi[k] - o[k]); if (a > R) R = a; if (b > R) R = b; }
+    const double pad = R * (1.0 / 262144.0) + 1e-30;
+    double tn = -INFINITY, tf = INFINITY;
+    for (int k = 0; k < 3; k++) {
+        double l = (double)lo[k] - pad - o[k], h = (double)hi[k] + pad - o[k];
+        if (d[k] == 0.0f) { if (l > 0.0 || h < 0.0) return 1; continue; }
+        double inv = 1.0 / (double)d[k];
+        double t0 = l * inv, t1 = h * inv;
+        if (t0 > t1) { double s = t0; t0 = t1; t1 = s; }
+        if (t0 > tn) tn = t0;
+        if (t1 < tf) tf = t1;
+    }
+    if (tn > tf) return 1;
+    if (tf < tmin) return 1;
+    if (tn > tbest) return 1;
+    *tnear_out = tn;
+    return 0;
+}
+
+static void mesh_closest(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, int mode) {
+    if (m->ntris == 0) return;
+    if (mode == 0) {
+        for (uint32_t p = 0; p < m->ntris; p++) {
+            const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+            float t, u, v;
+            if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v)) consider(best, t, u, v, inst, p);
+        }
+        return;
+    }
+    uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    while (top) {
+        const bvh_node *nd = &m->nodes[stack[--top]];
+        double tn;
+        double tb = best->found ? (double)best->t : (double)tmax;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tb, &tn)) continue;
+        if (nd->count) {
+            for (uint32_t i = 0; i < nd->count; i++) {
+                uint32_t p = m->prims[nd->left + i];
+                const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+                float t, u, v;
+                if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v)) consider(best, t, u, v, inst, p);
+            }
+        } else {
+            if (top + 2 > 128) die("oracle BVH stack overflow");
+            /* near child last so it is popped first */
+            const bvh_node *l = &m->nodes[nd->left];
+            int ax = 0; float e = nd->hi[0] - nd->lo[0];
+            if (nd->hi[1] - nd->lo[1] > e) { ax = 1; e = nd->hi[1] - nd->lo[1]; }
+            if (nd->hi[2] - nd->lo[2] > e) ax = 2;
+            const bvh_node *r = l + 1;
+            int left_first = (l->lo[ax] + l->hi[ax] <= r->lo[ax] + r->hi[ax]) == (f->d[ax] >= 0);
+            if (left_first) { stack[top++] = nd->left + 1; stack[top++] = nd->left; }
+            else { stack[top++] = nd->left; stack[top++] = nd->left + 1; }
+        }
+    }
+}
+
+static int mesh_any(const mesh *m, const ray_frame *f, float tmin, float tmax, int mode) {
+    if (m->ntris == 0) return 0;
+    float t, u, v;
+    if (mode == 0) {
+        for (uint32_t p = 0; p < m->ntris; p++) {
+            const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+            if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v)) return 1;
+        }
+        return 0;
+    }
+    uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    while (top) {
+        const bvh_node *nd = &m->nodes[stack[--top]];
+        double tn;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tmax, &tn)) continue;
+        if (nd->count) {
+            for (uint32_t i = 0; i < nd->count; i++) {
+                const float *a, *b, *c; tri_verts(m, m->prims[nd->left + i], &a, &b, &c);
+                if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v)) return 1;
+            }
+        } else {
+            if (top + 2 > 128) die("oracle BVH stack overflow");
+            stack[top++] = nd->left; stack[top++] = nd->left + 1;
+        }
+    }
+    return 0;
+}
+
+/* AccelImpl::trace_closest — accel.rs:449-509 (hit/miss encoding :485-508) */
+static void closest_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask, oracle_hit *h, int mode) {
+    best_hit best; memset(&best, 0, sizeof(best));
+    for (uint32_t i = 0; i < s->n_insts; i++) {
+        const instance *in = &s->insts[i];
+        if (!in->valid || (in->visible & mask) == 0) continue;
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        mesh_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode);
+    }
+    if (best.found) { h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->t = best.t; }
+    else { h->inst = UINT32_MAX; h->prim = UINT32_MAX; h->u = 0.f; h->v = 0.f; h->t = r->tmax; }
+    h->pad = 0;
+}
+
+/* AccelImpl::trace_any — accel.rs:511-535 */
+static uint32_t any_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask, int mode) {
+    for (uint32_t i = 0; i < s->n_insts; i++) {
+        const instance *in = &s->insts[i];
+        if (!in->valid || (in->visible & mask) == 0) continue;
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        if (mesh_any(&s->meshes[in->mesh], &f, r->tmin, r->tmax, mode)) return 1;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* double-precision ground truth (Moeller-Trumbore), with ambiguity flags                */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct truth_state {
+    double t_best; uint32_t inst, prim; double u, v; int found;
+    double t_second;          /* second-best certain hit */
+    double t_uncertain;       /* smallest t of a near-edge candidate (hit or near miss) */
+    int boundary;             /* some candidate's t within rounding of tmin/tmax */
+} truth_state;
+
+static inline void truth_tri(const double o[3], const double d[3], double tmin, double tmax, const float *a, const float *b, const float *c,
+                             uint32_t inst, uint32_t prim, truth_state *st) {
+    double e1[3], e2[3], p[3], s[3], q[3];
+    for (int k = 0; k < 3; k++) { e1[k] = (double)b[k] - a[k]; e2[k] = (double)c[k] - a[k]; s[k] = o[k] - a[k]; }
+    p[0] = d[1] * e2[2] - d[2] * e2[1]; p[1] = d[2] * e2[0] - d[0] * e2[2]; p[2] = d[0] * e2[1] - d[1] * e2[0];
+    double det = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+    if (det == 0.0) return;
+    double inv = 1.0 / det;
+    double u = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inv;
+    q[0] = s[1] * e1[2] - s[2] * e1[1]; q[1] = s[2] * e1[0] - s[0] * e1[2]; q[2] = s[0] * e1[1] - s[1] * e1[0];
+    double v = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) * inv;
+    double t = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv;
+    double w = 1.0 - u - v;
+    double bmin = fmin(u, fmin(v, w));
+    const double EB = 1e-4, ET = 1e-5;
+    if (bmin < -EB) return;
+    double lo = tmin - fabs(tmin) * ET - 1e-30, hi = tmax + fabs(tmax) * ET;
+    if (!(t >= lo && t <= hi)) return;
+    if (fabs(t - tmin) <= fabs(tmin) * ET + 1e-30 || fabs(t - tmax) <= fabs(tmax) * ET) st->boundary = 1;
+    if (bmin < EB) { if (t < st->t_uncertain) st->t_uncertain = t; }
+    if (bmin < 0.0 || !(t > tmin && t <= tmax)) return;
+    if (!st->found || t < st->t_best || (t == st->t_best && (inst < st->inst || (inst == st->inst && prim < st->prim)))) {
+        if (st->found && st->t_best < st->t_second) st->t_second = st->t_best;
+        st->found = 1; st->t_best = t; st->inst = inst; st->prim = prim; st->u = u; st->v = v;
+    } else if (t < st->t_second) st->t_second = t;
+}
+
+static void truth_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask, oracle_hit *h, uint8_t *amb, int mode) {
+    truth_state st; memset(&st, 0, sizeof(st)); st.t_second = INFINITY; st.t_uncertain = INFINITY;
+    for (uint32_t i = 0; i < s->n_insts; i++) {
+        const instance *in = &s->insts[i];
+        if (!in->valid || (in->visible & mask) == 0) continue;
+        const mesh *m = &s->meshes[in->mesh];
+        if (m->ntris == 0) continue;
+        double o[3], d[3]; float of[3], df[3];
+        for (int k = 0; k < 3; k++) {
+            const float *mm = in->inv + 4 * k;
+            o[k] = (double)mm[0] * r->o[0] + (double)mm[1] * r->o[1] + (double)mm[2] * r->o[2] + (double)mm[3];
+            d[k] = (double)mm[0] * r->d[0] + (double)mm[1] * r->d[1] + (double)mm[2] * r->d[2];
+            of[k] = (float)o[k]; df[k] = (float)d[k];
+        }
+        if (mode == 0) {
+            for (uint32_t p = 0; p < m->ntris; p++) { const float *a, *b, *c; tri_verts(m, p, &a, &b, &c); truth_tri(o, d, r->tmin, r->tmax, a, b, c, i, p, &st); }
+        } else {
+            uint32_t stack[128]; int top = 0; stack[top++] = 0;
+            while (top) {
+                const bvh_node *nd = &m->nodes[stack[--top]];
+                double tn, tb = st.found ? st.t_best * (1.0 + 1e-4) + 1e-30 : (double)r->tmax * (1.0 + 1e-4);
+                if (box_cull(nd->lo, nd->hi, of, df, (double)r->tmin * (1.0 - 1e-4) - 1e-30, tb, &tn)) continue;
+                if (nd->count) {
+                    for (uint32_t j = 0; j < nd->count; j++) { uint32_t p = m->prims[nd->left + j]; const float *a, *b, *c; tri_verts(m, p, &a, &b, &c); truth_tri(o, d, r->tmin, r->tmax, a, b, c, i, p, &st); }
+                } else { if (top + 2 > 128) die("oracle BVH stack overflow"); stack[top++] = nd->left; stack[top++] = nd->left + 1; }
+            }
+        }
+    }
+    int ambiguous = st.boundary;
+    if (st.found) {
+        h->inst = st.inst; h->prim = st.prim; h->u = (float)st.u; h->v = (float)st.v; h->t = (float)st.t_best;
+        double lim = st.t_best + fabs(st.t_best) * 1e-5 + 1e-30;
+        if (st.t_second <= lim) ambiguous = 1;
+        if (st.t_uncertain <= lim) ambiguous = 1;
+    } else {
+        h->inst = UINT32_MAX; h->prim = UINT32_MAX; h->u = 0.f; h->v = 0.f; h->t = r->tmax;
+        if (st.t_uncertain < INFINITY) ambiguous = 1;
+    }
+    h->pad = 0;
+    if (amb) *amb = (uint8_t)ambiguous;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* StreamImpl::parallel_for — stream.rs:185-209: N workers, atomic counter, block = 64    */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct job {
+    const oracle_scene *s; const oracle_ray *rays; uint64_t n; uint32_t mask; int mode; int kind;
+    oracle_hit *hits; uint32_t *occ; uint8_t *amb;
+    uint64_t counter;
+} job;
+
+static void *worker(void *arg) {
+    job *j = (job *)arg;
+    for (;;) {
+        uint64_t i0 = __atomic_fetch_add(&j->counter, 64, __ATOMIC_RELAXED);
+        if (i0 >= j->n) break;
+        uint64_t i1 = i0 + 64 < j->n ? i0 + 64 : j->n;
+        for (uint64_t i = i0; i < i1; i++) {
+            if (j->kind == 0) closest_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->mode);
+            else if (j->kind == 1) j->occ[i] = any_one(j->s, &j->rays[i], j->mask, j->mode);
+            else truth_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->amb ? &j->amb[i] : NULL, j->mode);
+        }
+    }
+    return NULL;
+}
+
+int oracle_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+
+static void run(job *j, int threads) {
+    if (threads <= 0) threads = oracle_hw_threads();
+    if (threads > 256) threads = 256;
+    if (threads == 1 || j->n <= 64) { worker(j); return; }
+    pthread_t th[256];
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+}
+
+void oracle_trace_closest(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, int mode, int threads) {
+    job j = {s, rays, n, mask, mode, 0, hits, NULL, NULL, 0}; run(&j, threads);
+}
+void oracle_trace_any(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, uint32_t *occ, int mode, int threads) {
+    job j = {s, rays, n, mask, mode, 1, NULL, occ, NULL, 0}; run(&j, threads);
+}
+void oracle_trace_closest_f64(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, uint8_t *amb, int mode, int threads) {
+    job j = {s, rays, n, mask, mode, 2, hits, NULL, amb, 0}; run(&j, threads);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* offset_ray_origin — lc/src/rtx.rs:517-535                                             */
+/* ------------------------------------------------------------------------------------ */
+
+void oracle_offset_ray_origin(const float p[3], const float n[3], float out[3]) {
+    const float origin = 1.0f / 32.0f, float_scale = 1.0f / 65536.0f, int_scale = 256.0f;
+    for (int k = 0; k < 3; k++) {
+        int32_t of_i = (int32_t)(int_scale * n[k]);
+        int32_t bits; memcpy(&bits, &p[k], 4);
+        int32_t p_i = bits + (p[k] < 0.0f ? -of_i : of_i);
+        float pf; memcpy(&pf, &p_i, 4);
+        out[k] = fabsf(p[k]) < origin ? p[k] + float_scale * n[k] : pf;
+    }
+}

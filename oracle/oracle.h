@@ -1,0 +1,97 @@
+/*
+ * oracle.h — CPU restatement of the reference's ray-tracing hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under luisa-compute-rs_b200/ may link, import or call
+ * this; it is used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs as the checker and the CPU baseline.
+ *
+ * PARITY UNPINNED: the arithmetic of the reference path lives in Embree 4 (crate
+ * embree_sys 0.1.11, git 6a0a591d, LC/src/rust/Cargo.lock:267-274), which is not vendored
+ * under /root/reference and cannot be built here (no cargo, no clang, no Embree); the
+ * reference holds no golden hit vectors for it.  This file restates
+ * the *semantics* the reference wraps around Embree, file by file:
+ *
+ *   cpu/accel.rs:205-260   GeometryImpl::build_mesh       -> oracle_mesh_set()
+ *   cpu/accel.rs:324-447   AccelImpl::update              -> oracle_accel_update()
+ *   cpu/accel.rs:449-509   AccelImpl::trace_closest       -> oracle_trace_closest()
+ *   cpu/accel.rs:511-535   AccelImpl::trace_any           -> oracle_trace_any()
+ *   cpu/accel.rs:537-558   instance_* accessors           -> oracle_instance_*()
+ *   cpu/stream.rs:185-209  StreamImpl::parallel_for       -> the worker pool used by trace_*
+ *   lc/src/rtx.rs:517-535  offset_ray_origin              -> oracle_offset_ray_origin()
+ *
+ * and fixes, where Embree leaves it open, ONE canonical per-triangle arithmetic (fp32,
+ * round-to-nearest, no contraction other than the explicit fmaf calls) so that results
+ * are a pure function of (scene, ray) and independent of any acceleration structure:
+ * see `oracle_canonical_triangle()` in oracle.c.  The GPU kernels implement the same
+ * arithmetic and must match it bit for bit on inst, prim, t and barycentrics.
+ * A second, double-precision Moeller-Trumbore evaluation (`oracle_trace_closest_f64`) is
+ * the geometric ground truth used to report the ambiguity ("tie") rate and to check
+ * the 1e-5 relative tolerance on t / barycentrics.
+ */
+#ifndef LC_B200_ORACLE_H
+#define LC_B200_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct __attribute__((aligned(16))) oracle_ray { float o[3], tmin, d[3], tmax; } oracle_ray; /* 32 B */
+typedef struct __attribute__((aligned(8))) oracle_hit { uint32_t inst, prim; float u, v, t; uint32_t pad; } oracle_hit; /* 24 B */
+
+typedef struct oracle_mod { /* = api::AccelBuildModification, 72 B */
+    uint32_t index, user_id, flags, visibility;
+    uint64_t mesh; /* oracle mesh id */
+    float affine[12];
+} oracle_mod;
+
+typedef struct oracle_scene oracle_scene;
+
+oracle_scene *oracle_scene_new(void);
+void oracle_scene_free(oracle_scene *);
+
+/* Meshes alias caller memory like Embree shared buffers (accel.rs:217-237): the oracle keeps
+ * the pointers and re-reads them at every commit.  Returns mesh id. */
+uint64_t oracle_mesh_new(oracle_scene *);
+void oracle_mesh_set(oracle_scene *, uint64_t mesh, const void *vertices, size_t vertex_stride, size_t vertex_count,
+                     const void *indices, size_t index_stride, size_t triangle_count);
+/* (Re)build the per-mesh CPU BVH after the vertex data changed. */
+void oracle_mesh_commit(oracle_scene *, uint64_t mesh);
+
+/* AccelImpl::update (accel.rs:324-447). */
+void oracle_accel_update(oracle_scene *, uint32_t instance_count, const oracle_mod *mods, size_t n_mods);
+
+void oracle_instance_transform(const oracle_scene *, uint32_t inst, float affine[12]);
+uint32_t oracle_instance_user_id(const oracle_scene *, uint32_t inst);
+uint32_t oracle_instance_visibility(const oracle_scene *, uint32_t inst);
+uint32_t oracle_instance_count(const oracle_scene *);
+
+/* mode: 0 = brute force over every triangle of every instance (definition),
+ *       1 = CPU BVH (same results, checked against mode 0 in tests).
+ * threads: worker count (<=0: all online cores); workers pull 64-ray blocks from an atomic
+ * counter, the scheme of StreamImpl::parallel_for. */
+void oracle_trace_closest(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, int mode, int threads);
+void oracle_trace_any(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, uint32_t *occluded, int mode, int threads);
+
+/* Double-precision ground truth.  ambiguous[i] (may be NULL) is set to 1 when the fp32
+ * answer is not forced: a second candidate lies within rel 1e-6 of the closest t, or some
+ * triangle's nearest barycentric (hit or near miss, |b| < 1e-5) is within rounding of an edge
+ * at a t that could change the answer. */
+void oracle_trace_closest_f64(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, uint8_t *ambiguous, int mode, int threads);
+
+/* lc/src/rtx.rs:517-535 */
+void oracle_offset_ray_origin(const float p[3], const float n[3], float out[3]);
+
+/* The canonical single ray/triangle evaluation, exported for unit tests.
+ * Returns 1 and fills t,u,v when tmin < t <= tmax. */
+int oracle_canonical_triangle(const float o[3], const float d[3], float tmin, float tmax,
+                              const float v0[3], const float v1[3], const float v2[3], float *t, float *u, float *v);
+
+/* world->object 3x4 (row-major) from the instance affine: double adjugate inverse rounded to fp32. */
+void oracle_invert_affine(const float m[12], float inv[12]);
+
+int oracle_hw_threads(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

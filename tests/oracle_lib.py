@@ -1,0 +1,148 @@
+"""ctypes binding of oracle/liboracle.so — the checker.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "liboracle.so")
+_lib = None
+
+
+class Mod(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("user_id", C.c_uint32), ("flags", C.c_uint32), ("visibility", C.c_uint32),
+                ("mesh", C.c_uint64), ("affine", C.c_float * 12)]
+
+
+def build():
+    subprocess.run(["make", "-C", os.path.join(_ROOT, "oracle")], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.oracle_scene_new.restype = C.c_void_p
+        L.oracle_scene_free.argtypes = [C.c_void_p]
+        L.oracle_mesh_new.argtypes = [C.c_void_p]
+        L.oracle_mesh_new.restype = C.c_uint64
+        L.oracle_mesh_set.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.oracle_mesh_commit.argtypes = [C.c_void_p, C.c_uint64]
+        L.oracle_accel_update.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Mod), C.c_size_t]
+        L.oracle_instance_transform.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+        L.oracle_instance_user_id.argtypes = [C.c_void_p, C.c_uint32]
+        L.oracle_instance_user_id.restype = C.c_uint32
+        L.oracle_instance_visibility.argtypes = [C.c_void_p, C.c_uint32]
+        L.oracle_instance_visibility.restype = C.c_uint32
+        L.oracle_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_trace_closest_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_offset_ray_origin.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_canonical_triangle.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float] + [C.POINTER(C.c_float)] * 6
+        L.oracle_canonical_triangle.restype = C.c_int
+        L.oracle_invert_affine.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_hw_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+HIT = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("committed_ray_t", "<f4"), ("_pad", "<u4")])
+BRUTE, BVH = 0, 1
+
+
+class OracleScene:
+    def __init__(self):
+        self.L = lib()
+        self.s = C.c_void_p(self.L.oracle_scene_new())
+        self.keep = []
+
+    def add_mesh(self, verts, tris, stride=None):
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        tris = np.ascontiguousarray(tris, dtype=np.uint32)
+        self.keep += [verts, tris]
+        m = self.L.oracle_mesh_new(self.s)
+        self.L.oracle_mesh_set(self.s, m, verts.ctypes.data, stride or verts.strides[0], verts.shape[0], tris.ctypes.data, 12, tris.shape[0])
+        self.L.oracle_mesh_commit(self.s, m)
+        return m
+
+    def commit_mesh(self, m):
+        self.L.oracle_mesh_commit(self.s, m)
+
+    def update(self, instance_count, mods):
+        arr = (Mod * max(len(mods), 1))()
+        for i, m in enumerate(mods):
+            arr[i] = Mod(m["index"], m.get("user_id", 0), m["flags"], m.get("visibility", 0), m.get("mesh", 0),
+                         (C.c_float * 12)(*np.asarray(m.get("affine", [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]), dtype=np.float32).reshape(12)))
+        self.L.oracle_accel_update(self.s, instance_count, arr, len(mods))
+
+    def trace_closest(self, rays, mask=0xFF, mode=BVH, threads=0):
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(rays.shape[0], dtype=HIT)
+        self.L.oracle_trace_closest(self.s, rays.ctypes.data, rays.shape[0], mask, hits.ctypes.data, mode, threads)
+        return hits
+
+    def trace_any(self, rays, mask=0xFF, mode=BVH, threads=0):
+        rays = np.ascontiguousarray(rays)
+        occ = np.zeros(rays.shape[0], dtype=np.uint32)
+        self.L.oracle_trace_any(self.s, rays.ctypes.data, rays.shape[0], mask, occ.ctypes.data, mode, threads)
+        return occ
+
+    def truth(self, rays, mask=0xFF, mode=BVH, threads=0):
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(rays.shape[0], dtype=HIT)
+        amb = np.zeros(rays.shape[0], dtype=np.uint8)
+        self.L.oracle_trace_closest_f64(self.s, rays.ctypes.data, rays.shape[0], mask, hits.ctypes.data, amb.ctypes.data, mode, threads)
+        return hits, amb
+
+    def instance_transform(self, i):
+        out = (C.c_float * 12)()
+        self.L.oracle_instance_transform(self.s, i, out)
+        return np.array(out, dtype=np.float32).reshape(3, 4)
+
+    def instance_user_id(self, i):
+        return self.L.oracle_instance_user_id(self.s, i)
+
+    def instance_visibility(self, i):
+        return self.L.oracle_instance_visibility(self.s, i)
+
+    def close(self):
+        if self.s:
+            self.L.oracle_scene_free(self.s)
+            self.s = None
+
+
+def scene_from_desc(desc):
+    """Build an OracleScene from tests.scenes.SceneDesc with the modification sequence Accel::push_mesh records."""
+    o = OracleScene()
+    ids = [o.add_mesh(v, t) for v, t in desc.meshes]
+    mods = []
+    for k, inst in enumerate(desc.instances):
+        flags = 1 | 2 | 16 | 32 | (4 if inst["opaque"] else 8)
+        mods.append(dict(index=k, user_id=inst["user_id"], flags=flags, visibility=inst["mask"], mesh=ids[inst["mesh"]], affine=inst["transform"].reshape(12)))
+    o.update(len(desc.instances), mods)
+    return o
+
+
+def offset_ray_origin(p, n):
+    L = lib()
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    n = np.ascontiguousarray(n, dtype=np.float32)
+    out = np.empty_like(p)
+    fp = C.POINTER(C.c_float)
+    for i in range(p.shape[0]):
+        L.oracle_offset_ray_origin(p[i].ctypes.data_as(fp), n[i].ctypes.data_as(fp), out[i].ctypes.data_as(fp))
+    return out
+
+
+def canonical_triangle(o, d, tmin, tmax, v0, v1, v2):
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (o, d, v0, v1, v2)]
+    t, u, v = C.c_float(), C.c_float(), C.c_float()
+    ok = L.oracle_canonical_triangle(arrs[0].ctypes.data_as(fp), arrs[1].ctypes.data_as(fp), tmin, tmax, arrs[2].ctypes.data_as(fp),
+                                     arrs[3].ctypes.data_as(fp), arrs[4].ctypes.data_as(fp), C.byref(t), C.byref(u), C.byref(v))
+    return (bool(ok), t.value, u.value, v.value)
