@@ -151,9 +151,9 @@ __device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin
     if (det == 0.0f) return false;
     const float az = __fmul_rn(r.sz, a_z), bz = __fmul_rn(r.sz, b_z), cz = __fmul_rn(r.sz, c_z);
     const float T = __fmaf_rn(U, az, __fmaf_rn(V, bz, __fmul_rn(W, cz)));
-    const float rdet = __frcp_rn(det);
-    const float t = __fmul_rn(T, rdet);
+    const float t = __fdiv_rn(T, det);
     if (!(t > tmin && t <= tmax)) return false;
+    const float rdet = __frcp_rn(det);
     t_out = t; u_out = __fmul_rn(V, rdet); v_out = __fmul_rn(W, rdet);
     return true;
 }

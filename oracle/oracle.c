@@ -308,9 +308,9 @@ static inline int canon_tri(const ray_frame *f, float tmin, float tmax, const fl
     if (det == 0.0f) return 0;
     const float az = f->sz * a_z, bz = f->sz * b_z, cz = f->sz * c_z;
     const float T = fmaf(U, az, fmaf(V, bz, W * cz));
-    const float rdet = 1.0f / det;
-    const float t = T * rdet;
+    const float t = T / det; /* IEEE division: t is correctly rounded from (T, det) */
     if (!(t > tmin && t <= tmax)) return 0;
+    const float rdet = 1.0f / det;
     *t_out = t; *u_out = V * rdet; *v_out = W * rdet;
     return 1;
 }

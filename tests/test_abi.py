@@ -1,0 +1,61 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every symbol include/lc_b200_api.h declares, and the
+ctypes mirror has the sizes the reference's cbindgen header produces.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import luisa_compute_rs_b200 as lc
+
+abi = lc._abi
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = abi.load_library()
+    header = open(os.path.join(ROOT, "include", "lc_b200_api.h")).read()
+    declared = set(re.findall(r"^LCB_EXPORT[^;(]*?\b(\w+)\s*\(", header, re.M))
+    assert declared == set(abi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.lc_b200_version()
+
+
+def test_lib_interface_table_is_populated():
+    iface = abi.load_library().luisa_compute_lib_interface()
+    for f in ("set_logger_callback", "create_context", "destroy_context", "create_device", "free_string"):
+        assert C.cast(getattr(iface, f), C.c_void_p).value
+    ctx = iface.create_context(b".")
+    iface.destroy_context(ctx)
+
+
+def test_struct_sizes_match_reference_header():
+    # sizes measured from LC/include/luisa/rust/api_types.h with gcc
+    assert C.sizeof(abi.Command) == 88
+    assert C.sizeof(abi.CmdMeshBuild) == 80
+    assert C.sizeof(abi.CmdAccelBuild) == 40
+    assert C.sizeof(abi.AccelModification) == 72
+    assert C.sizeof(abi.AccelOption) == 8
+    assert C.sizeof(abi.DeviceInterface) == 288
+    assert C.sizeof(abi.LibInterface) == 48
+    assert C.sizeof(abi.CreatedBuffer) == 32
+    assert lc.Ray.itemsize == 32 and lc.SurfaceHit.itemsize == 24 and lc.Index.itemsize == 12
+
+
+def test_make_ir_type_blocks_have_the_ir_layout():
+    lib = abi.load_library()
+    p = lib.lc_b200_make_ir_type(12, 4)       # -> &CArc<Type>: pointer to {inner*}
+    inner = C.cast(p, C.POINTER(C.c_void_p))[0]
+    type_ptr = C.cast(inner, C.POINTER(C.c_void_p))[0]   # CArcSharedBlock.ptr at offset 0
+    tag = C.cast(type_ptr, C.POINTER(C.c_int32))[0]
+    assert tag == 5  # Type::Struct
+    size = C.cast(type_ptr + 8 + 24 + 8, C.POINTER(C.c_size_t))[0]  # union@8: fields slice (24) | alignment | size
+    assert size == 12
+    v = lib.lc_b200_make_ir_type(0, 0)
+    inner = C.cast(v, C.POINTER(C.c_void_p))[0]
+    assert C.cast(C.cast(inner, C.POINTER(C.c_void_p))[0], C.POINTER(C.c_int32))[0] == 0  # Type::Void
+
+
+def test_affine_packing_matches_into_affine3x4():
+    import numpy as np
+    m = np.arange(16, dtype=np.float32).reshape(4, 4)
+    assert lc.affine_from_mat4(m).tolist() == list(range(12))

@@ -1,0 +1,321 @@
+"""GPU parity tests: every query goes through the C ABI (luisa_compute_lib_interface -> DeviceInterface.dispatch and the
+lc_b200_* batch entry points) and is compared bit-for-bit with the oracle on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+
+import luisa_compute_rs_b200 as lc
+import oracle_lib as ol
+import scenes
+from harness import DeviceScene, assert_hits_equal, compare_with_truth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def check_scene(device, desc, rays, masks=(0xFF,), stride=12, any_hit=True):
+    o = ol.scene_from_desc(desc)
+    d = DeviceScene(device, desc, vertex_stride=stride)
+    try:
+        for mask in masks:
+            want = o.trace_closest(rays, mask, ol.BVH)
+            got = d.trace_closest(rays, mask)
+            assert_hits_equal(got, want, f"mask {mask:#x}")
+            if any_hit:
+                assert np.array_equal(d.trace_any(rays, mask), o.trace_any(rays, mask, ol.BVH))
+    finally:
+        d.destroy(); o.close()
+
+
+def test_device_identity(device):
+    assert device.name() == "b200"
+    assert device.query("no_such_property") is None
+
+
+def test_c1_triangle(device):
+    rays = scenes.c1_rays(256, 256)
+    check_scene(device, scenes.c1_triangle(), rays)
+    g = np.load(os.path.join(GOLDEN, "c1_closed_form_64.npz"))
+    d = DeviceScene(device, scenes.c1_triangle())
+    hits = d.trace_closest(scenes.c1_rays(64, 64))
+    clear = g["edge_margin"] > 1e-5
+    assert np.array_equal((hits["inst"] != lc.INVALID)[clear], g["hit"][clear])
+    v = (hits["inst"] != lc.INVALID) & clear
+    assert np.max(np.abs(hits["committed_ray_t"][v] - g["t"][v]) / g["t"][v]) < 1e-5
+    assert np.max(np.abs(hits["bary"][v] - g["bary"][v])) < 1e-5
+    d.destroy()
+
+
+def test_c2_cornell_primary_and_golden(device):
+    desc = scenes.c2_cornell()
+    check_scene(device, desc, scenes.c2_primary_rays(256, 256))
+    g = np.load(os.path.join(GOLDEN, "cornell_primary_48.npz"))
+    d = DeviceScene(device, desc)
+    hits = d.trace_closest(scenes.c2_primary_rays(48, 48))
+    assert np.array_equal(hits["inst"], g["inst"]) and np.array_equal(hits["prim"], g["prim"])
+    assert np.array_equal(hits["committed_ray_t"].view(np.uint32), g["t_bits"])
+    assert np.array_equal(hits["bary"].view(np.uint32), g["bary_bits"])
+    d.destroy()
+
+
+def test_c2_cornell_secondary_rays(device):
+    """diffuse bounce + shadow rays started on surfaces with offset_ray_origin (path_tracer.rs:383-428)"""
+    desc = scenes.c2_cornell()
+    o = ol.scene_from_desc(desc)
+    prim = scenes.c2_primary_rays(128, 128)
+    h = o.trace_closest(prim)
+    v = h["inst"] != lc.INVALID
+    p = prim["orig"][v] + prim["dir"][v] * h["committed_ray_t"][v][:, None]
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=p.shape).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    sec = scenes.make_rays(lc.offset_ray_origin(p, d), d, 0.0, np.float32(3.4e38))
+    dev = DeviceScene(device, desc)
+    assert_hits_equal(dev.trace_closest(sec), o.trace_closest(sec), "secondary")
+    light = np.array([-0.005, 1.98, -0.03], np.float32)
+    dl = light - p
+    dist = np.linalg.norm(dl, axis=1).astype(np.float32)
+    sh = scenes.make_rays(p, dl / dist[:, None], 1e-4, dist * np.float32(0.999))
+    assert np.array_equal(dev.trace_any(sh), o.trace_any(sh))
+    dev.destroy(); o.close()
+
+
+@pytest.mark.parametrize("n_tris,n_rays,seed", [(1, 2000, 1), (2, 2000, 2), (3, 2000, 3), (4, 3000, 4), (9, 3000, 5), (100, 20000, 6),
+                                                (5000, 100000, 7), (200000, 400000, 8)])
+def test_soup_closest_and_any(device, n_tris, n_rays, seed):
+    desc = scenes.c3_soup(n_tris, seed=seed)
+    check_scene(device, desc, scenes.incoherent_rays(n_rays, seed=100 + seed))
+
+
+def test_soup_vs_f64_truth_and_tie_rate(device):
+    desc = scenes.c3_soup(50000)
+    rays = scenes.incoherent_rays(300000)
+    o = ol.scene_from_desc(desc)
+    d = DeviceScene(device, desc)
+    got = d.trace_closest(rays)
+    truth, amb = o.truth(rays)
+    r = compare_with_truth(got, truth, amb)
+    print("truth comparison:", r)
+    assert r["mismatches"] == 0           # inst/prim identical outside reported ties
+    assert r["t_rel_err"] < 1e-5 and r["bary_abs_err"] < 1e-5
+    assert r["tie_rate"] < 0.01
+    d.destroy(); o.close()
+
+
+def test_float3_stride_16_vertices(device):
+    check_scene(device, scenes.c3_soup(3000, seed=21), scenes.incoherent_rays(20000, seed=22), stride=16)
+
+
+def test_instances_transforms_masks_user_ids(device):
+    desc = scenes.instanced_scene(2000, 10)
+    rays = scenes.incoherent_rays(200000, lo=-1.0, hi=8.0, seed=31)
+    check_scene(device, desc, rays, masks=(0xFF, 0xF0, 0x01, 0x0))
+    d = DeviceScene(device, desc)
+    o = ol.scene_from_desc(desc)
+    for i in range(10):
+        assert d.accel.instance_user_id(i) == o.instance_user_id(i) == 100 + i
+        assert d.accel.instance_visibility_mask(i) == o.instance_visibility(i)
+        assert np.array_equal(d.accel.instance_transform(i), o.instance_transform(i))
+    d.destroy(); o.close()
+
+
+def test_scaled_and_sheared_instance(device):
+    s = scenes.SceneDesc()
+    m = s.add_mesh(*scenes.random_soup(500, 41, extent=0.1))
+    s.add_instance(m, np.array([[2.0, 0.3, 0, 1], [0, 0.5, 0.1, -2], [0.2, 0, 3.0, 0.5]], np.float32))
+    s.add_instance(m, np.array([[0.1, 0, 0, 3], [0, 0.1, 0, 0], [0, 0, 0.1, 0]], np.float32))
+    check_scene(device, s, scenes.incoherent_rays(100000, lo=-3.0, hi=5.0, seed=42))
+
+
+def test_ties_lowest_ids_and_coincident_geometry(device):
+    s = scenes.SceneDesc()
+    v = [[0, 0, 1], [1, 0, 1], [0, 1, 1]]
+    m = s.add_mesh(v + v + v, [[6, 7, 8], [3, 4, 5], [0, 1, 2]])
+    s.add_instance(m); s.add_instance(m); s.add_instance(m)
+    rng = np.random.default_rng(9)
+    o = np.concatenate([rng.random((5000, 2), dtype=np.float32), np.zeros((5000, 1), np.float32)], 1)
+    rays = scenes.make_rays(o, np.tile(np.float32([0, 0, 1]), (5000, 1)), 0.0, 10.0)
+    check_scene(device, s, rays)
+    d = DeviceScene(device, s)
+    h = d.trace_closest(rays)
+    hit = h["inst"] != lc.INVALID
+    assert hit.sum() > 1000 and np.all(h["inst"][hit] == 0) and np.all(h["prim"][hit] == 0)
+    d.destroy()
+
+
+def test_shared_edges_are_watertight_grid(device):
+    verts, tris = scenes.terrain(65)
+    s = scenes.SceneDesc(); s.add_instance(s.add_mesh(verts, tris))
+    rng = np.random.default_rng(10)
+    n = 200000
+    o = np.stack([rng.random(n, dtype=np.float32) * 0.98 + 0.01, np.full(n, 2.0, np.float32), rng.random(n, dtype=np.float32) * 0.98 + 0.01], 1)
+    # a share of rays aimed exactly at grid vertices and edges
+    gv = verts[rng.integers(0, verts.shape[0], n // 4)]
+    o[: n // 4, 0] = np.clip(gv[:, 0], 0.01, 0.99); o[: n // 4, 2] = np.clip(gv[:, 2], 0.01, 0.99)
+    rays = scenes.make_rays(o, np.tile(np.float32([0, -1, 0]), (n, 1)), 0.0, 10.0)
+    check_scene(device, s, rays)
+    d = DeviceScene(device, s)
+    assert (d.trace_closest(rays)["inst"] != lc.INVALID).all()   # no ray slips between triangles
+    d.destroy()
+
+
+def test_terrain_grazing_and_axis_aligned_rays(device):
+    verts, tris = scenes.terrain(200)
+    s = scenes.SceneDesc(); s.add_instance(s.add_mesh(verts, tris))
+    rng = np.random.default_rng(12)
+    n = 100000
+    o = np.stack([rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32) * 0.2, rng.random(n, dtype=np.float32)], 1)
+    d = np.zeros((n, 3), np.float32)
+    ax = rng.integers(0, 3, n)
+    d[np.arange(n), ax] = rng.choice(np.float32([-1, 1]), n)     # exactly axis-aligned: zero direction components
+    d[n // 2:] += rng.normal(scale=1e-3, size=(n - n // 2, 3)).astype(np.float32)
+    check_scene(device, s, scenes.make_rays(o, d, 0.0, 10.0))
+
+
+def test_hit_interval_and_backfaces(device):
+    s = scenes.SceneDesc()
+    s.add_instance(s.add_mesh([[0, 0, 1], [1, 0, 1], [0, 1, 1]], [[0, 1, 2]]))
+    o = ol.scene_from_desc(s)
+    t = o.trace_closest(scenes.make_rays([[0.2, 0.2, 0]], [[0, 0, 1]], 0.0, 10.0))["committed_ray_t"][0]
+    below = np.nextafter(t, np.float32(0))
+    rays = scenes.make_rays([[0.2, 0.2, 0]] * 5 + [[0.2, 0.2, 2]], [[0, 0, 1]] * 5 + [[0, 0, -1]], [0, t, below, 0, 0, 0], [t, 2, 2, below, 10, 10])
+    check_scene(device, s, rays)
+    d = DeviceScene(device, s)
+    assert (d.trace_closest(rays)["inst"] != lc.INVALID).tolist() == [True, False, True, False, True, True]
+    d.destroy()
+
+
+def test_empty_inputs(device):
+    s = scenes.SceneDesc()
+    s.add_instance(s.add_mesh(*scenes.random_soup(50, 3)))
+    d = DeviceScene(device, s)
+    assert d.trace_closest(np.zeros(0, dtype=lc.Ray)).shape == (0,)
+    d.destroy()
+    # accel without instances, and an instance of an empty mesh: every ray misses with t = tmax
+    rays = scenes.incoherent_rays(1000)
+    empty = scenes.SceneDesc()
+    d = DeviceScene(device, empty)
+    h = d.trace_closest(rays)
+    assert (h["inst"] == lc.INVALID).all() and np.array_equal(h["committed_ray_t"], rays["tmax"]) and not d.trace_any(rays).any()
+    d.destroy()
+    e2 = scenes.SceneDesc()
+    e2.add_instance(e2.add_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)))
+    e2.add_instance(e2.add_mesh(*scenes.random_soup(10, 4)))
+    check_scene(device, e2, rays)
+
+
+def test_degenerate_triangles_and_zero_direction(device):
+    s = scenes.SceneDesc()
+    s.add_instance(s.add_mesh([[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, 2], [1, 0, 2], [2, 0, 2], [0, 0, 3], [1, 0, 3], [0, 1, 3]], [[0, 1, 2], [3, 4, 5], [6, 7, 8]]))
+    rays = scenes.make_rays([[0.1, 0.1, 0], [0, 0, 0], [0.5, 0, 0], [0, 0, 0]], [[0, 0, 1], [0, 0, 0], [0, 0, 1], [0, 0, 1]], 0.0, 10.0)
+    check_scene(device, s, rays)
+
+
+def test_duplicate_centroids_deep_tree(device):
+    """thousands of triangles with identical Morton codes exercise the equal-key split path"""
+    rng = np.random.default_rng(13)
+    n = 6000
+    base = np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    v = np.tile(base, (n, 1, 1)).astype(np.float32)
+    v[:, :, 2] = (rng.integers(0, 4, n) * np.float32(0.25))[:, None]   # only 4 distinct planes
+    s = scenes.SceneDesc()
+    s.add_instance(s.add_mesh(v.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)))
+    o = np.concatenate([rng.random((20000, 2), dtype=np.float32) * 0.5, np.full((20000, 1), -1, np.float32)], 1)
+    check_scene(device, s, scenes.make_rays(o, np.tile(np.float32([0, 0, 1]), (20000, 1)), 0.0, 10.0))
+
+
+def test_rebuild_after_vertex_update_and_accel_modifications(device):
+    verts, tris = scenes.random_soup(4000, 51, extent=0.05)
+    rays = scenes.incoherent_rays(50000, seed=52)
+    vb = device.create_buffer_from_array(verts); ib = device.create_buffer_from_array(tris)
+    mesh = device.create_mesh(vb.view(), ib.view(), lc.AccelOption(allow_update=True))
+    mesh.build()
+    accel = device.create_accel()
+    accel.push_mesh(mesh); accel.build()
+    o = ol.OracleScene()
+    ov = verts.copy()
+    om = o.add_mesh(ov, tris)
+    o.update(1, [dict(index=0, flags=1 | 2 | 4 | 16 | 32, visibility=0xFF, mesh=om)])
+    assert_hits_equal(accel.intersect_host(rays), o.trace_closest(rays), "initial")
+    # the BVH aliases user buffers (accel.rs:217-237): rewrite vertices, PreferUpdate, rebuild the accel
+    ov += np.float32(0.01) * np.sin(40 * ov[:, [1, 2, 0]]).astype(np.float32)
+    vb.view().copy_from(ov); o.commit_mesh(om)
+    mesh.build(lc.AccelBuildRequest.PREFER_UPDATE); accel.build(lc.AccelBuildRequest.PREFER_UPDATE)
+    assert_hits_equal(accel.intersect_host(rays), o.trace_closest(rays), "after vertex update")
+    # second instance, moved; then visibility change; then pop
+    t = np.eye(4, dtype=np.float32); t[:3, 3] = [0.5, 0.1, -0.2]
+    accel.push_mesh(mesh, t, 0x0F); accel.build()
+    o.update(2, [dict(index=1, flags=1 | 2 | 4 | 16 | 32, visibility=0x0F, mesh=om, affine=t[:3].reshape(12))])
+    for mask in (0xFF, 0xF0):
+        assert_hits_equal(accel.intersect_host(rays, mask), o.trace_closest(rays, mask), f"two instances {mask:#x}")
+    accel.set_visibility_on_update(0, 0x10); accel.set_transform_on_update(1, np.eye(4, dtype=np.float32)); accel.build()
+    o.update(2, [dict(index=0, flags=16, visibility=0x10), dict(index=1, flags=2)])
+    for mask in (0xFF, 0x10, 0x0F):
+        assert_hits_equal(accel.intersect_host(rays, mask), o.trace_closest(rays, mask), f"modified {mask:#x}")
+    accel.pop(); accel.build(); o.update(1, [])
+    assert_hits_equal(accel.intersect_host(rays), o.trace_closest(rays), "after pop")
+    assert np.array_equal(accel.intersect_any_host(rays), o.trace_any(rays))
+    accel.destroy(); mesh.destroy(); vb.destroy(); ib.destroy(); o.close()
+
+
+def test_stream_ordering_events_and_callbacks(device):
+    s1, s2 = device.create_stream(), device.create_stream()
+    a = device.create_buffer(1 << 16, 4); b = device.create_buffer(1 << 16, 4)
+    src = np.arange(1 << 16, dtype=np.uint32)
+    dst = np.zeros_like(src)
+    fired = []
+    ev = device.create_event()
+    s1.submit([a.view().copy_from_async(src), a.view().copy_to_buffer_async(b.view())], callback=lambda: fired.append(1))
+    ev.signal(s1, 1)
+    ev.wait(s2, 1)
+    s2.submit([b.view().copy_to_async(dst)], callback=lambda: fired.append(2))
+    s2.synchronize(); s1.synchronize()
+    assert np.array_equal(src, dst) and sorted(fired) == [1, 2] and ev.is_completed(1)
+    ev.synchronize(1)
+    assert np.array_equal(device.create_buffer(100, 12).view().to_numpy(np.uint8), np.zeros(1200, np.uint8))  # zero-initialised
+    s1.destroy(); s2.destroy(); ev.destroy(); a.destroy(); b.destroy()
+
+
+def test_counted_traversal_matches_and_reports_work(device):
+    desc = scenes.c3_soup(20000, seed=61)
+    rays = scenes.incoherent_rays(50000, seed=62)
+    d = DeviceScene(device, desc)
+    o = ol.scene_from_desc(desc)
+    rb = device.create_buffer_from_array(rays); hb = device.create_buffer(rays.shape[0], 24, 8)
+    c = d.accel.intersect_counted(rb, hb)
+    assert_hits_equal(hb.view().to_numpy(lc.SurfaceHit), o.trace_closest(rays), "counted")
+    assert c["rays"] == rays.shape[0] and c["nodes_visited"] > rays.shape[0] and c["tris_tested"] > 0
+    st = d.meshes[0].stats()
+    assert st["primitive_count"] == 20000 and st["packed_tri_count"] == 20000 and 0 < st["wide_node_count"] < 20000
+    assert lc._abi.load_library().lc_b200_kernel_launch_count() > 0
+    rb.destroy(); hb.destroy(); d.destroy(); o.close()
+
+
+def test_full_size_properties_c3(device):
+    """At BASELINE size (1M triangles, 16M rays) the oracle is too slow; check size-independent properties instead:
+    any-hit == (closest-hit found), reversed-ray reciprocity of t, idempotence, and a 64k-ray sample against the oracle."""
+    n_tris, n_rays = 1_000_000, 1 << 24
+    desc = scenes.c3_soup(n_tris)
+    d = DeviceScene(device, desc)
+    rays = scenes.incoherent_rays(n_rays)
+    h1 = d.accel.intersect_host(rays)
+    h2 = d.accel.intersect_host(rays)
+    assert h1.tobytes() == h2.tobytes()                                   # deterministic / idempotent
+    occ = d.accel.intersect_any_host(rays)
+    hit = h1["inst"] != lc.INVALID
+    assert np.array_equal(occ != 0, hit)                                  # any-hit consistent with closest-hit
+    assert 0.5 < hit.mean() < 1.0
+    assert np.all(h1["committed_ray_t"][hit] > rays["tmin"][hit]) and np.all(h1["prim"][hit] < n_tris) and np.all(h1["inst"][hit] == 0)
+    b = h1["bary"][hit]
+    assert np.all(b >= -1e-6) and np.all(b.sum(1) <= 1 + 1e-6)
+    # clipping the ray just short of the hit must miss that primitive; clipping at the hit must keep it
+    sub = np.nonzero(hit)[0][:200000]
+    r2 = rays[sub].copy(); r2["tmax"] = h1["committed_ray_t"][sub]
+    assert np.array_equal(d.accel.intersect_host(r2)["prim"], h1["prim"][sub])
+    r2["tmax"] = np.nextafter(h1["committed_ray_t"][sub], np.float32(0))
+    assert (d.accel.intersect_host(r2)["inst"] == lc.INVALID).all()
+    o = ol.scene_from_desc(desc)
+    pick = np.random.default_rng(1).integers(0, n_rays, 65536)
+    assert_hits_equal(h1[pick], o.trace_closest(rays[pick]), "1M-triangle sample")
+    d.destroy(); o.close()
