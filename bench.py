@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 ray-tracing device.
+
+Metric (BASELINE.json): Mrays/s closest-hit on incoherent rays, with BVH build ms beside it, as absolute numbers and as a
+fraction of the measured HBM roofline.  Workload at every N: C3 of BASELINE.json — a 1 000 000-triangle random soup and
+16 777 216 incoherent rays per GPU (`configs[2]`, the configuration the metric is quoted on; configs[1], the Cornell path
+tracer, needs the IR->CUDA lowering that SURVEY.md §8f ranks "next").  A step = one trace_closest pass over the ray batch.
+
+  python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                   the CPU arm: the oracle port on all host cores, bounded sample
+
+Scaling is weak: Accel replicated (every rank builds it from the same seeded data), each rank traces its own 16 Mi-ray
+batch, no collective on the data path; hits stay on the GPU that traced them.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_TRIS = 1_000_000
+N_RAYS = 1 << 24
+METRIC = "closest_hit_incoherent_mrays_per_s"
+UNIT = "Mrays/s"
+WORKLOAD = "C3: 1M-triangle random soup (seed 0x5EED0001), 16Mi incoherent rays per GPU (seed 0x5EED0002+rank), trace_closest"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(n_sample, threads=0, repeats=1):
+    """The oracle port (BVH mode) on `threads` host threads over the first n_sample rays of rank 0's batch.  Returns Mrays/s."""
+    import oracle_lib as ol
+    import scenes
+    desc = scenes.c3_soup(N_TRIS)
+    t0 = time.perf_counter()
+    o = ol.scene_from_desc(desc)
+    build_s = time.perf_counter() - t0
+    rays = scenes.incoherent_rays(n_sample, seed=0x5EED0002)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        o.trace_closest(rays, 0xFF, ol.BVH, threads)
+        best = min(best, time.perf_counter() - t0)
+    o.close()
+    return n_sample / best / 1e6, build_s, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import oracle_lib as ol
+    cores = ol.lib().oracle_hw_threads()
+    n_sample = 1 << 20
+    import scenes
+    desc = scenes.c3_soup(N_TRIS)
+    o = ol.scene_from_desc(desc)
+    rays = scenes.incoherent_rays(n_sample, seed=0x5EED0002)
+    for _ in range(args.warmup):
+        o.trace_closest(rays[: n_sample // 8], 0xFF, ol.BVH, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.trace_closest(rays, 0xFF, ol.BVH, 0)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n_sample / dt / 1e6
+    sample = f"first {n_sample} rays of the C3 batch per step against the full 1M-triangle scene; oracle port (binned-SAH binary BVH, canonical fp32 triangle test), not Embree"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tris", type=int, default=N_TRIS)
+    ap.add_argument("--rays", type=int, default=N_RAYS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / cpu legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    warmup = max(args.warmup, 3) if not args.profile else args.warmup
+
+    import torch
+    import torch.distributed as dist
+    import luisa_compute_rs_b200 as lc
+    import scenes
+
+    torch.cuda.set_device(local_rank)
+    os.environ["LC_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = lc.Context()
+    dev = ctx.create_device("b200")
+    lib = lc._abi.load_library()
+
+    # ---- scene: replicated on every rank, built by the device --------------------------------------------------
+    verts, tris = scenes.random_soup(args.tris, 0x5EED0001)
+    vb = dev.create_buffer_from_array(verts)
+    ib = dev.create_buffer_from_array(tris)
+    mesh = dev.create_mesh(vb.view(), ib.view(), lc.AccelOption())
+    build_ms = []
+    for _ in range(4):
+        mesh.build(lc.AccelBuildRequest.FORCE_BUILD)
+        build_ms.append(mesh.stats()["build_ms"])
+    mstats = mesh.stats()
+    accel = dev.create_accel()
+    accel.push_mesh(mesh)
+    accel.build()
+    tlas_ms = accel.stats()["build_ms"]
+
+    # ---- rays: resident in HBM before the timed region -------------------------------------------------------------
+    n = args.rays
+    rays_h = torch.from_numpy(scenes.incoherent_rays(n, seed=0x5EED0002 + rank).view(np.uint8).reshape(-1)).pin_memory()
+    hits_h = torch.empty(n * 24, dtype=torch.uint8).pin_memory()
+    rb = dev.create_buffer(n, 32, 16)
+    hb = dev.create_buffer(n, 24, 8)
+    ob = dev.create_buffer(n, 4, 4)
+    rb.view().copy_from(rays_h.numpy().view(lc.Ray))
+    stream = dev.create_stream()
+    ext = torch.cuda.ExternalStream(stream.cuda_stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        accel.intersect(rb, hb, n, 0xFF, stream)
+    stream.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.lc_b200_kernel_launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(ext)
+    for k in range(args.steps):
+        accel.intersect(rb, hb, n, 0xFF, stream)
+        evs[k + 1].record(ext)
+    stream.synchronize()
+    barrier()
+    launches = lib.lc_b200_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3) / 1e6
+    kernel_ms = float(np.mean(step_ms))
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD if (args.tris, args.rays) == (N_TRIS, N_RAYS) else f"C3-shaped: {args.tris} triangles, {args.rays} rays per GPU",
+                   "triangles": args.tris, "rays_per_gpu": n, "parallelism": f"rays sharded x{world}, accel replicated",
+                   "l2": "ray + hit buffers (896 MiB) exceed the 126 MB L2; the BVH (~60 MB) is L2-resident by nature of the workload"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "build": {"blas_ms": float(min(build_ms)), "blas_ms_all": [float(x) for x in build_ms], "tlas_ms": float(tlas_ms),
+                  "wide_nodes": int(mstats["wide_node_count"]), "bvh_bytes": int(mstats["bvh_bytes"]), "max_depth": int(mstats["max_depth"])},
+    }
+
+    if rank == 0 and not args.profile:
+        # ---- roofline of the dominant kernel (k_trace): algorithmic bytes from the instrumented kernel on the same inputs ----
+        ctr = accel.intersect_counted(rb, hb, n, 0xFF, stream)
+        algo_bytes = n * (32 + 24) + 128 * ctr["nodes_visited"] + 48 * ctr["tris_tested"]
+        peak, how = measured_peaks()
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        build_bytes = 12 * args.tris + 12 * verts.shape[0] + mstats["bvh_bytes"]
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                           "peak_source": how, "kernel": "k_trace<closest>", "algorithmic_bytes_per_launch": int(algo_bytes),
+                           "nodes_per_ray": ctr["nodes_visited"] / n, "tris_per_ray": ctr["tris_tested"] / n,
+                           "note": "logical (L1/L2-inclusive) bytes per SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test",
+                           "build_achieved_gbs": build_bytes / (min(build_ms) * 1e-3) / 1e9, "build_frac": build_bytes / (min(build_ms) * 1e-3) / 1e9 / peak}
+        # ---- any-hit on the same batch (C3's shadow set), reported beside the headline ----
+        hits_np = np.empty(n, dtype=lc.SurfaceHit)
+        hb.view().copy_to(hits_np)
+        shadow = scenes.shadow_rays_from_hits(rays_h.numpy().view(lc.Ray), hits_np)
+        rb2 = dev.create_buffer_from_array(shadow)
+        for _ in range(2):
+            accel.intersect_any(rb2, ob, n, 0xFF, stream)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(5):
+            accel.intersect_any(rb2, ob, n, 0xFF, stream)
+        e1.record(ext)
+        stream.synchronize()
+        out["any_hit"] = {"value": n * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": UNIT, "hit_rate": float((hits_np["inst"] != lc.INVALID).mean())}
+        rb2.destroy()
+
+    if not args.profile:
+        # ---- end to end through the C ABI host entry point: pinned host rays in, pinned host hits out, every step ----
+        accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out["e2e"] = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 24,
+                      "api": "lc_b200_trace_closest_host (chunked H2D / trace / D2H pipeline)"}
+        got = hits_h.numpy().view(lc.SurfaceHit)
+        chk = np.empty(n, dtype=lc.SurfaceHit)
+        accel.intersect(rb, hb, n, 0xFF, stream)
+        stream.synchronize()
+        hb.view().copy_to(chk)
+        assert got.tobytes() == chk.tobytes(), "host and device entry points disagree"
+
+    if world > 1 and not args.profile:
+        # the one collective of the path: gather of a 4K Float4 framebuffer's tiles over NCCL
+        import luisa_compute_rs_b200.sharding as sh
+        per_rank = sh.padded_tile_count(3840, 2160, world) * sh.TILE * sh.TILE
+        local = torch.zeros(per_rank, 4, device="cuda")
+        sh.gather_tiles(local, dist, world)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            sh.gather_tiles(local, dist, world)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["framebuffer_gather"] = {"ms": float(t.item()), "bytes_total": int(per_rank * 16 * world), "collective": "ncclAllGather 4K Float4 tiles"}
+
+    if rank == 0 and world == 1 and not args.no_cpu and not args.profile:
+        import oracle_lib as ol
+        cores = ol.lib().oracle_hw_threads()
+        n_sample = 1 << 20
+        v, cpu_build_s, cpu_s = cpu_leg(n_sample)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"first {n_sample} rays of the batch ({cpu_s:.1f} s) on the full 1M-triangle scene; oracle port (binned-SAH binary BVH built in {cpu_build_s:.1f} s single-threaded), not Embree"}
+
+    if rank == 0:
+        print(json.dumps(out))
+    for b in (rb, hb, ob, vb, ib):
+        b.destroy()
+    accel.destroy(); mesh.destroy(); stream.destroy(); dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@
 #include "../../include/lc_b200_api.h"
 #include "build.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdarg>
@@ -195,6 +196,7 @@ struct DeviceObj {
     int ordinal = 0;
     LaunchCounter lc;
     StreamObj *internal = nullptr;  // used by the *_host entry points
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H lanes of the pipelined host entry points
     // grow-only device staging for the host entry points
     uint8_t *stage_rays = nullptr, *stage_out = nullptr; size_t stage_rays_cap = 0, stage_out_cap = 0;
     std::mutex mu;
@@ -584,6 +586,8 @@ lcb_denoiser_ext denoiser_ext(lcb_device) { return lcb_denoiser_ext{nullptr, nul
 void destroy_device(lcb_device_interface iface) {
     DeviceObj *d = dev_of(iface.device); bind(d);
     if (d->internal) free_stream(d->internal);
+    if (d->copy_in) cudaStreamDestroy(d->copy_in);
+    if (d->copy_out) cudaStreamDestroy(d->copy_out);
     if (d->stage_rays) cudaFree(d->stage_rays);
     if (d->stage_out) cudaFree(d->stage_out);
     flush_launches(d);
@@ -612,6 +616,8 @@ lcb_device_interface create_device(lcb_context, const char *name, const char *js
     if (prop.major != 10) fatal("device %d is sm_%d%d; this library contains sm_100a code only", ordinal, prop.major, prop.minor);
     auto *d = new DeviceObj; d->ordinal = ordinal;
     d->internal = make_stream(d);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
     log_msg("I", "b200 device %d: %s, %d SMs, %.1f GB", ordinal, prop.name, prop.multiProcessorCount, prop.totalGlobalMem / 1e9);
     lcb_device_interface t{};
     t.device = lcb_device{(uint64_t)d};
@@ -690,34 +696,45 @@ void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, 
     flush_launches(d);
 }
 
-void lc_b200_trace_closest_host(lcb_device dev, lcb_accel ah, const lcb_ray *rays, lcb_surface_hit *hits, uint64_t count, uint32_t mask) {
-    DeviceObj *d = dev_of(dev); bind(d);
-    AccelObj *a = as<AccelObj>(ah.id);
-    if (!count) return;
+// Host-buffer entry points.  The batch is cut into 1 Mi-ray chunks that flow through three lanes — H2D copy,
+// traversal, D2H copy — on three streams chained by events, so PCIe transfers in both directions overlap the kernel.
+static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays, void *out, size_t out_stride, uint64_t count, uint32_t mask, bool any) {
     std::lock_guard<std::mutex> lk(d->mu);
     ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
-    ensure_stage(d->stage_out, d->stage_out_cap, count * 24);
-    cudaStream_t st = d->internal->stream;
-    CUDA_CHECK(cudaMemcpyAsync(d->stage_rays, rays, count * 32, cudaMemcpyHostToDevice, st));
-    trace_closest(st, view_of(a), d->stage_rays, d->stage_out, count, mask, d->internal->work_counter, nullptr, d->lc);
-    CUDA_CHECK(cudaMemcpyAsync(hits, d->stage_out, count * 24, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    ensure_stage(d->stage_out, d->stage_out_cap, count * out_stride);
+    const uint64_t chunk = 1ull << 20;
+    const size_t n_chunks = (size_t)((count + chunk - 1) / chunk);
+    std::vector<cudaEvent_t> ev(2 * n_chunks);
+    for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t sk = d->internal->stream;
+    const AccelView view = view_of(a);
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint64_t first = c * chunk, n = std::min(chunk, count - first);
+        CUDA_CHECK(cudaMemcpyAsync(d->stage_rays + first * 32, rays + first, n * 32, cudaMemcpyHostToDevice, d->copy_in));
+        CUDA_CHECK(cudaEventRecord(ev[2 * c], d->copy_in));
+        CUDA_CHECK(cudaStreamWaitEvent(sk, ev[2 * c], 0));
+        if (any) trace_any(sk, view, d->stage_rays + first * 32, (uint32_t *)(d->stage_out + first * out_stride), n, mask, d->internal->work_counter, d->lc);
+        else trace_closest(sk, view, d->stage_rays + first * 32, d->stage_out + first * out_stride, n, mask, d->internal->work_counter, nullptr, d->lc);
+        CUDA_CHECK(cudaEventRecord(ev[2 * c + 1], sk));
+        CUDA_CHECK(cudaStreamWaitEvent(d->copy_out, ev[2 * c + 1], 0));
+        CUDA_CHECK(cudaMemcpyAsync((uint8_t *)out + first * out_stride, d->stage_out + first * out_stride, n * out_stride, cudaMemcpyDeviceToHost, d->copy_out));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(d->copy_out));
+    CUDA_CHECK(cudaStreamSynchronize(sk));
+    for (auto &e : ev) cudaEventDestroy(e);
     flush_launches(d);
+}
+
+void lc_b200_trace_closest_host(lcb_device dev, lcb_accel ah, const lcb_ray *rays, lcb_surface_hit *hits, uint64_t count, uint32_t mask) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    if (!count) return;
+    trace_host_pipelined(d, as<AccelObj>(ah.id), rays, hits, 24, count, mask, false);
 }
 
 void lc_b200_trace_any_host(lcb_device dev, lcb_accel ah, const lcb_ray *rays, uint32_t *occluded, uint64_t count, uint32_t mask) {
     DeviceObj *d = dev_of(dev); bind(d);
-    AccelObj *a = as<AccelObj>(ah.id);
     if (!count) return;
-    std::lock_guard<std::mutex> lk(d->mu);
-    ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
-    ensure_stage(d->stage_out, d->stage_out_cap, count * 4);
-    cudaStream_t st = d->internal->stream;
-    CUDA_CHECK(cudaMemcpyAsync(d->stage_rays, rays, count * 32, cudaMemcpyHostToDevice, st));
-    trace_any(st, view_of(a), d->stage_rays, (uint32_t *)d->stage_out, count, mask, d->internal->work_counter, d->lc);
-    CUDA_CHECK(cudaMemcpyAsync(occluded, d->stage_out, count * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    flush_launches(d);
+    trace_host_pipelined(d, as<AccelObj>(ah.id), rays, occluded, 4, count, mask, true);
 }
 
 void lc_b200_instance_transform(lcb_device, lcb_accel ah, uint32_t i, float *out) {

@@ -158,6 +158,27 @@ __device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin
     return true;
 }
 
+// Reported barycentrics of the winning triangle: one double-precision Moeller-Trumbore evaluation on the
+// canonical object-space ray (fixed operation order; oracle.c refine_bary).  Once per ray, off the hot loop.
+__device__ __forceinline__ void refine_bary(const RaySetup &r, const float4 v0, const float4 v1, const float4 v2, float &u_io, float &v_io) {
+    const double e1x = __dsub_rn((double)v1.x, (double)v0.x), e1y = __dsub_rn((double)v1.y, (double)v0.y), e1z = __dsub_rn((double)v1.z, (double)v0.z);
+    const double e2x = __dsub_rn((double)v2.x, (double)v0.x), e2y = __dsub_rn((double)v2.y, (double)v0.y), e2z = __dsub_rn((double)v2.z, (double)v0.z);
+    const double sx = __dsub_rn((double)r.ox, (double)v0.x), sy = __dsub_rn((double)r.oy, (double)v0.y), sz = __dsub_rn((double)r.oz, (double)v0.z);
+    const double dx = r.dx, dy = r.dy, dz = r.dz;
+    const double px = __dsub_rn(__dmul_rn(dy, e2z), __dmul_rn(dz, e2y));
+    const double py = __dsub_rn(__dmul_rn(dz, e2x), __dmul_rn(dx, e2z));
+    const double pz = __dsub_rn(__dmul_rn(dx, e2y), __dmul_rn(dy, e2x));
+    const double det = __dadd_rn(__dadd_rn(__dmul_rn(e1x, px), __dmul_rn(e1y, py)), __dmul_rn(e1z, pz));
+    if (det == 0.0) return;
+    const double inv = __ddiv_rn(1.0, det);
+    const double u = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx, px), __dmul_rn(sy, py)), __dmul_rn(sz, pz)), inv);
+    const double qx = __dsub_rn(__dmul_rn(sy, e1z), __dmul_rn(sz, e1y));
+    const double qy = __dsub_rn(__dmul_rn(sz, e1x), __dmul_rn(sx, e1z));
+    const double qz = __dsub_rn(__dmul_rn(sx, e1y), __dmul_rn(sy, e1x));
+    const double v = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, qx), __dmul_rn(dy, qy)), __dmul_rn(dz, qz)), inv);
+    u_io = __double2float_rn(u); v_io = __double2float_rn(v);
+}
+
 template <bool ANY, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out, unsigned long long count,
                                                          uint32_t mask, unsigned long long *work_counter, TraceCounters *ctr) {
@@ -172,7 +193,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
     unsigned long long ray_idx = 0;
     RaySetup r;
     float tmin = 0.f, tbest = 0.f, ray_tmax = 0.f;
-    uint32_t hit_inst = 0xffffffffu, hit_prim = 0xffffffffu;
+    uint32_t hit_inst = 0xffffffffu, hit_prim = 0xffffffffu, hit_slot = 0;  // hit_slot: index of the winning PackedTri
     float hit_u = 0.f, hit_v = 0.f;
     uint32_t cur_inst = 0xffffffffu;
     const WideNode *nodes = acc.tlas_nodes;
@@ -266,7 +287,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
                     const uint32_t prim = __float_as_uint(v0.w);
                     const bool better = t < tbest || hit_inst == 0xffffffffu ||
                                         (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
-                    if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; }
+                    if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; hit_slot = Gt.x + bit; }
                 }
             }
         }
@@ -286,6 +307,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
             if (ANY) {
                 reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
             } else {
+                if (hit_inst != 0xffffffffu) {
+                    const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + hit_inst);
+                    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+                    const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+                    const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + hit_slot);
+                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                    setup_object(r, ra, rb, m0, m1, m2);
+                    refine_bary(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), hit_u, hit_v);
+                }
                 uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
                 o[0] = make_uint2(hit_inst, hit_prim);
                 o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));

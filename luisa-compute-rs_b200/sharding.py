@@ -1,0 +1,79 @@
+"""Multi-GPU partitioning of the ray-query path: one process per GPU, meshes + Accel replicated
+(every rank runs the deterministic build itself from the same vertex/index data — no broadcast), rays or image
+tiles partitioned, and ONE collective: the gather of per-rank results (framebuffer tiles / hit records) over NCCL.
+
+Host-side logic only; torch.distributed is the plumbing (gloo in CPU tests, NCCL on the GPUs).
+"""
+import numpy as np
+
+TILE = 64  # pixels per tile edge
+
+
+def ray_slice(n_rays, rank, world):
+    """Contiguous, balanced [begin, end) slice of a ray batch for `rank`."""
+    base, rem = divmod(n_rays, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _part1by1(v):
+    v = v.astype(np.uint64) & np.uint64(0xFFFF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+    v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+    return v
+
+
+def tile_order(width, height, tile=TILE):
+    """Tiles of the image sorted along a Morton curve; returns (tx, ty) arrays in assignment order."""
+    nx, ny = (width + tile - 1) // tile, (height + tile - 1) // tile
+    ty, tx = np.divmod(np.arange(nx * ny), nx)
+    code = _part1by1(tx) | (_part1by1(ty) << np.uint64(1))
+    order = np.argsort(code, kind="stable")
+    return tx[order], ty[order]
+
+
+def tiles_of_rank(width, height, rank, world, tile=TILE):
+    """Round-robin along the Morton curve: tile k of the curve belongs to rank k % world."""
+    tx, ty = tile_order(width, height, tile)
+    sel = np.arange(tx.shape[0]) % world == rank
+    return tx[sel], ty[sel]
+
+
+def pixels_of_tiles(tx, ty, width, height, tile=TILE):
+    """Global pixel indices (row-major) of the given tiles, tile after tile, clipped at the image border, plus a
+    validity mask for the padded tail (every tile contributes tile*tile entries so ranks have equal counts)."""
+    oy, ox = np.divmod(np.arange(tile * tile), tile)
+    px = tx[:, None] * tile + ox[None, :]
+    py = ty[:, None] * tile + oy[None, :]
+    valid = (px < width) & (py < height)
+    idx = np.where(valid, py * width + px, 0)
+    return idx.reshape(-1), valid.reshape(-1)
+
+
+def padded_tile_count(width, height, world, tile=TILE):
+    nx, ny = (width + tile - 1) // tile, (height + tile - 1) // tile
+    return -(-(nx * ny) // world)
+
+
+def gather_tiles(local, dist_module, world):
+    """all_gather of equally sized per-rank tile buffers (torch tensors).  Returns a (world, ...) tensor on every rank."""
+    import torch
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist_module.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1))
+    return out
+
+
+def untile(gathered, width, height, world, tile=TILE):
+    """Scatter gathered per-rank tile buffers (numpy, shape (world, tiles_per_rank*tile*tile, C)) back into an image."""
+    channels = gathered.shape[-1]
+    img = np.zeros((height * width, channels), dtype=gathered.dtype)
+    per_rank = padded_tile_count(width, height, world, tile)
+    for r in range(world):
+        tx, ty = tiles_of_rank(width, height, r, world, tile)
+        idx, valid = pixels_of_tiles(tx, ty, width, height, tile)
+        buf = gathered[r, : tx.shape[0] * tile * tile]
+        img[idx[valid]] = buf[valid]
+        assert tx.shape[0] <= per_rank
+    return img.reshape(height, width, channels)

@@ -330,6 +330,24 @@ static inline void consider(best_hit *b, float t, float u, float v, uint32_t ins
     }
 }
 
+/* Reported barycentrics: the winning triangle is re-evaluated once in double (Moeller-Trumbore on the
+ * canonical object-space ray, fixed operation order, no contraction) and rounded to fp32.  The fp32 edge
+ * functions decide hit/miss and ordering; this only tightens the (u, v) that is handed to shading. */
+static inline void refine_bary(const ray_frame *f, const float *a, const float *b, const float *c, float *u_io, float *v_io) {
+    const double e1x = (double)b[0] - (double)a[0], e1y = (double)b[1] - (double)a[1], e1z = (double)b[2] - (double)a[2];
+    const double e2x = (double)c[0] - (double)a[0], e2y = (double)c[1] - (double)a[1], e2z = (double)c[2] - (double)a[2];
+    const double sx = (double)f->o[0] - (double)a[0], sy = (double)f->o[1] - (double)a[1], sz = (double)f->o[2] - (double)a[2];
+    const double dx = f->d[0], dy = f->d[1], dz = f->d[2];
+    const double px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;
+    const double det = (e1x * px + e1y * py) + e1z * pz;
+    if (det == 0.0) return;
+    const double inv = 1.0 / det;
+    const double u = ((sx * px + sy * py) + sz * pz) * inv;
+    const double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+    const double v = ((dx * qx + dy * qy) + dz * qz) * inv;
+    *u_io = (float)u; *v_io = (float)v;
+}
+
 /* conservative slab test in double against the box padded by 2^-18 * Linf(ray origin, box) */
 static inline int box_cull(const float lo[3], const float hi[3], const float o[3], const float d[3], double tmin, double tbest,
                            double *tnear_out) {
@@ -428,7 +446,13 @@ static void closest_one(const oracle_scene *s, const oracle_ray *r, uint32_t mas
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
         mesh_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode);
     }
-    if (best.found) { h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->t = best.t; }
+    if (best.found) {
+        const instance *in = &s->insts[best.inst];
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best.prim, &a, &b, &c);
+        refine_bary(&f, a, b, c, &best.u, &best.v);
+        h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->t = best.t;
+    }
     else { h->inst = UINT32_MAX; h->prim = UINT32_MAX; h->u = 0.f; h->v = 0.f; h->t = r->tmax; }
     h->pad = 0;
 }
