@@ -17,6 +17,8 @@
 // respect to that arithmetic (planes padded by 2^-20 of the L-inf distance to the node), so
 // results do not depend on the tree.
 #include "build.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace lcb {
 
@@ -73,8 +75,11 @@ __device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const
     finish_setup(r);
 }
 
-__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
-__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+// 16-bit plane index -> float 2^23 + q in ONE byte-permute (no int->float conversion, no subtraction): the 2^23
+// bias is folded into the per-node plane offsets below, at the price of half a quantisation step of rounding
+// slop that the padding absorbs (one extra step, 2^-16 of the node extent).
+__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
 // Tests the 8 children of one node.  Returns the hit mask: bits 24..31 internal children in
 // traversal priority order for this ray's octant, bits 0..23 leaf primitives.
@@ -95,8 +100,10 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
     const float pad = R * (1.0f / 1048576.0f);
     const float ax = sclx * r.ix, ay = scly * r.iy, az = sclz * r.iz;
     const float cx = rx * r.ix, cy = ry * r.iy, cz = rz * r.iz;
-    const float px = pad * fabsf(r.ix), py = pad * fabsf(r.iy), pz = pad * fabsf(r.iz);
-    const float bnx = cx - px, bfx = cx + px, bny = cy - py, bfy = cy + py, bnz = cz - pz, bfz = cz + pz;
+    const float px = fmaf(pad, fabsf(r.ix), fabsf(ax)), py = fmaf(pad, fabsf(r.iy), fabsf(ay)), pz = fmaf(pad, fabsf(r.iz), fabsf(az));
+    const float bnx = fmaf(-8388608.0f, ax, cx - px), bfx = fmaf(-8388608.0f, ax, cx + px);
+    const float bny = fmaf(-8388608.0f, ay, cy - py), bfy = fmaf(-8388608.0f, ay, cy + py);
+    const float bnz = fmaf(-8388608.0f, az, cz - pz), bfz = fmaf(-8388608.0f, az, cz + pz);
     uint32_t hits = 0;
 #define LCB_CHILD(I, WORD, CONV, METAWORD, METASHIFT)                                                        \
     {                                                                                                        \
@@ -179,10 +186,15 @@ __device__ __forceinline__ void refine_bary(const RaySetup &r, const float4 v0, 
     u_io = __double2float_rn(u); v_io = __double2float_rn(v);
 }
 
+// Scheduling weights of the phase vote (lanes wanting a phase x weight; highest score runs).
+struct PhaseWeights { int node, tri, inst, fetch; };
+
+constexpr int kSavedSlots = 7;  // stack[0..6] hold the world-space RaySetup while the ray is inside an instance
+
 template <bool ANY, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out, unsigned long long count,
-                                                         uint32_t mask, unsigned long long *work_counter, TraceCounters *ctr) {
-    uint2 stack[kTraversalStack];
+                                                         uint32_t mask, unsigned long long *work_counter, TraceCounters *ctr, PhaseWeights w) {
+    uint2 stack[kSavedSlots + kTraversalStack];
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
 
     // warp-uniform pool of ray indices
@@ -198,130 +210,140 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
     uint32_t cur_inst = 0xffffffffu;
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
-    uint2 G = make_uint2(0, 0);
-    int sp = 0;
+    uint2 G = make_uint2(0, 0), Gt = make_uint2(0, 0);
+    int sp = kSavedSlots;
     unsigned long long n_nodes = 0, n_tris = 0, n_inst = 0, n_rays = 0;
 
     for (;;) {
-        // ---- refill idle lanes ------------------------------------------------------------
-        const uint32_t idle = __ballot_sync(kFull, !has_ray);
-        if (idle) {
-            if (pool_next == pool_end && !exhausted) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)kChunk);
-                base = __shfl_sync(kFull, base, 0);
-                if (base >= count) { exhausted = true; }
-                else { pool_next = base; pool_end = base + kChunk < count ? base + kChunk : count; }
-            }
-            if (pool_next == pool_end) {
-                if (idle == kFull) break;  // nothing left anywhere in this warp
-            } else {
-                const unsigned long long mine = pool_next + __popc(idle & lt_mask);
-                if (!has_ray && mine < pool_end) {
-                    ray_idx = mine;
-                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                    setup_world(r, ra, rb);
-                    tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
-                    hit_inst = 0xffffffffu; hit_prim = 0xffffffffu; hit_u = 0.f; hit_v = 0.f;
-                    cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
-                    sp = 0;
-                    G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
-                    has_ray = true;
-                    if (COUNTERS) n_rays++;
+        // ---- normalise: every lane that owns a ray either has pending work or retires ----------
+        while (has_ray && Gt.y == 0u && (G.y & 0xff000000u) == 0u) {
+            if (sp == kSavedSlots) {
+                if (ANY) {
+                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
+                } else {
+                    uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
+                    o[0] = make_uint2(hit_inst, hit_prim);
+                    o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
+                    // the pad word carries the winning PackedTri slot to k_refine, which clears it
+                    o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), hit_slot);
                 }
-                const unsigned long long adv = pool_next + __popc(idle);
-                pool_next = adv < pool_end ? adv : pool_end;
+                has_ray = false;
+                break;
             }
+            const uint2 e = stack[--sp];
+            if (e.y == 0u) {  // sentinel: back to world space, restore the saved setup
+                const uint2 s0 = stack[0], s1 = stack[1], s2 = stack[2], s3 = stack[3], s4 = stack[4], s5 = stack[5], s6 = stack[6];
+                r.ox = __uint_as_float(s0.x); r.oy = __uint_as_float(s0.y); r.oz = __uint_as_float(s1.x);
+                r.dx = __uint_as_float(s1.y); r.dy = __uint_as_float(s2.x); r.dz = __uint_as_float(s2.y);
+                r.ix = __uint_as_float(s3.x); r.iy = __uint_as_float(s3.y); r.iz = __uint_as_float(s4.x);
+                r.sx = __uint_as_float(s4.y); r.sy = __uint_as_float(s5.x); r.sz = __uint_as_float(s5.y);
+                r.kz = (int)s6.x; r.octinv = s6.y;
+                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+            } else if (e.y & 0xff000000u) G = e;
+            else Gt = e;
         }
-        if (!has_ray) continue;
+        // ---- vote ---------------------------------------------------------------------------
+        const bool in_blas = cur_inst != 0xffffffffu;
+        const uint32_t m_tri = __ballot_sync(kFull, has_ray && Gt.y != 0u && in_blas);
+        const uint32_t m_inst = __ballot_sync(kFull, has_ray && Gt.y != 0u && !in_blas);
+        const uint32_t m_node = __ballot_sync(kFull, has_ray && Gt.y == 0u);
+        const uint32_t m_idle = __ballot_sync(kFull, !has_ray);
+        const bool can_fetch = !(exhausted && pool_next == pool_end);
+        const int s_node = __popc(m_node) * w.node, s_tri = __popc(m_tri) * w.tri, s_inst = __popc(m_inst) * w.inst;
+        const int s_fetch = can_fetch ? __popc(m_idle) * w.fetch : 0;
+        const int best = max(max(s_node, s_tri), max(s_inst, s_fetch));
+        if (best == 0) break;  // no lane owns a ray and none can be fetched
 
-        bool done = false;
-        uint2 Gt = make_uint2(0, 0);
-        // ---- node phase -------------------------------------------------------------------
-        if (G.y & 0xff000000u) {
-            const uint32_t bit = 31u - __clz(G.y);
-            G.y &= ~(1u << bit);
-            const uint32_t slot = (bit - 24u) ^ r.octinv;
-            const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
-            const WideNode *node = nodes + (G.x + rel);
-            if (G.y & 0xff000000u) stack[sp++] = G;
-            uint32_t child_base, prim_base, imask;
-            const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
-            if (COUNTERS) n_nodes++;
-            G = make_uint2(child_base, (hits & 0xff000000u) | imask);
-            Gt = make_uint2(prim_base, hits & 0x00ffffffu);
-        } else {
-            Gt = G;
-            G = make_uint2(0, 0);
-        }
-        // ---- primitive phase --------------------------------------------------------------
-        while (Gt.y) {
-            const uint32_t bit = __ffs(Gt.y) - 1;
-            Gt.y &= Gt.y - 1;
-            if (cur_inst == 0xffffffffu) {
-                // TLAS leaf: enter an instance
-                const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
-                const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
-                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
-                if ((meta.x & mask) == 0u) continue;
-                if (Gt.y) stack[sp++] = Gt;
-                if (G.y & 0xff000000u) stack[sp++] = G;
-                stack[sp++] = make_uint2(0u, 0u);  // sentinel: return to world space
-                const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
-                const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
-                nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
-                tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                setup_object(r, ra, rb, m0, m1, m2);
-                cur_inst = inst;
-                G = make_uint2(0u, 0x80000000u);
-                Gt.y = 0;
-                if (COUNTERS) n_inst++;
-            } else {
+        if (s_tri == best) {
+            // ---- triangle phase: one canonical test per participating lane -----------------
+            if (has_ray && Gt.y != 0u && in_blas) {
+                const uint32_t bit = __ffs(Gt.y) - 1;
+                Gt.y &= Gt.y - 1;
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 if (COUNTERS) n_tris++;
                 float t, u, v;
                 if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, u, v)) {
-                    if (ANY) { done = true; hit_inst = cur_inst; break; }
-                    const uint32_t prim = __float_as_uint(v0.w);
-                    const bool better = t < tbest || hit_inst == 0xffffffffu ||
-                                        (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
-                    if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; hit_slot = Gt.x + bit; }
+                    if (ANY) {
+                        hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = kSavedSlots;  // retire at the next normalise
+                    } else {
+                        const uint32_t prim = __float_as_uint(v0.w);
+                        const bool better = t < tbest || hit_inst == 0xffffffffu ||
+                                            (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
+                        if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; hit_slot = Gt.x + bit; }
+                    }
                 }
             }
-        }
-        // ---- pop phase --------------------------------------------------------------------
-        if (!done && (G.y & 0xff000000u) == 0u) {
-            for (;;) {
-                if (sp == 0) { done = true; break; }
-                G = stack[--sp];
-                if (G.y != 0u) break;
-                // sentinel: back to world space
-                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                setup_world(r, ra, rb);
-                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+        } else if (s_node == best) {
+            // ---- node phase: pop one child of the node group, test its 8 children ----------
+            if (has_ray && Gt.y == 0u) {
+                const uint32_t bit = 31u - __clz(G.y);
+                G.y &= ~(1u << bit);
+                const uint32_t slot = (bit - 24u) ^ r.octinv;
+                const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
+                const WideNode *node = nodes + (G.x + rel);
+                if (G.y & 0xff000000u) stack[sp++] = G;
+                uint32_t child_base, prim_base, imask;
+                const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
+                if (COUNTERS) n_nodes++;
+                G = make_uint2(child_base, (hits & 0xff000000u) | imask);
+                Gt = make_uint2(prim_base, hits & 0x00ffffffu);
             }
-        }
-        if (done) {
-            if (ANY) {
-                reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
-            } else {
-                if (hit_inst != 0xffffffffu) {
-                    const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + hit_inst);
+        } else if (s_inst == best) {
+            // ---- instance phase: TLAS leaf -> transform the ray and descend into the BLAS ---
+            if (has_ray && Gt.y != 0u && !in_blas) {
+                const uint32_t bit = __ffs(Gt.y) - 1;
+                Gt.y &= Gt.y - 1;
+                const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
+                const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
+                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
+                if ((meta.x & mask) != 0u) {
+                    if (Gt.y) stack[sp++] = Gt;
+                    if (G.y & 0xff000000u) stack[sp++] = G;
+                    stack[sp++] = make_uint2(0u, 0u);  // sentinel
+                    stack[0] = make_uint2(__float_as_uint(r.ox), __float_as_uint(r.oy)); stack[1] = make_uint2(__float_as_uint(r.oz), __float_as_uint(r.dx));
+                    stack[2] = make_uint2(__float_as_uint(r.dy), __float_as_uint(r.dz)); stack[3] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
+                    stack[4] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.sx)); stack[5] = make_uint2(__float_as_uint(r.sy), __float_as_uint(r.sz));
+                    stack[6] = make_uint2((uint32_t)r.kz, r.octinv);
                     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
-                    const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + hit_slot);
-                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                    setup_object(r, ra, rb, m0, m1, m2);
-                    refine_bary(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), hit_u, hit_v);
+                    nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+                    tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                    const float4 wo = make_float4(r.ox, r.oy, r.oz, 0.f), wd = make_float4(r.dx, r.dy, r.dz, 0.f);
+                    setup_object(r, wo, wd, m0, m1, m2);
+                    cur_inst = inst;
+                    G = make_uint2(0u, 0x80000000u);
+                    Gt = make_uint2(0u, 0u);
+                    if (COUNTERS) n_inst++;
                 }
-                uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
-                o[0] = make_uint2(hit_inst, hit_prim);
-                o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
-                o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), 0u);
             }
-            has_ray = false;
+        } else {
+            // ---- fetch phase: refill idle lanes from the warp-local pool --------------------
+            if (pool_next == pool_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)kChunk);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= count) exhausted = true;
+                else { pool_next = base; pool_end = base + kChunk < count ? base + kChunk : count; }
+            }
+            if (pool_next != pool_end) {
+                const unsigned long long mine = pool_next + __popc(m_idle & lt_mask);
+                if (!has_ray && mine < pool_end) {
+                    ray_idx = mine;
+                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                    setup_world(r, ra, rb);
+                    tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
+                    hit_inst = 0xffffffffu; hit_prim = 0xffffffffu; hit_u = 0.f; hit_v = 0.f; hit_slot = 0;
+                    cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+                    sp = kSavedSlots;
+                    G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
+                    Gt = make_uint2(0u, 0u);
+                    has_ray = true;
+                    if (COUNTERS) n_rays++;
+                }
+                const unsigned long long adv = pool_next + __popc(m_idle);
+                pool_next = adv < pool_end ? adv : pool_end;
+            }
         }
     }
     if (COUNTERS) {
@@ -330,6 +352,40 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
         atomicAdd(&ctr->instance_entries, n_inst);
         atomicAdd(&ctr->rays, n_rays);
     }
+}
+
+// Second pass of closest-hit queries: reported barycentrics of every hit, one thread per ray, fully converged.
+__global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__restrict__ rays, uint2 *__restrict__ hits, unsigned long long count) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint2 h0 = hits[3 * i], h2 = hits[3 * i + 2];
+    if (h0.x == 0xffffffffu) { if (h2.y) hits[3 * i + 2] = make_uint2(h2.x, 0u); return; }
+    uint2 h1 = hits[3 * i + 1];
+    const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h0.x);
+    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+    const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+    const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + h2.y);
+    const float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
+    RaySetup r;
+    r.ox = __fmaf_rn(m0.x, ra.x, __fmaf_rn(m0.y, ra.y, __fmaf_rn(m0.z, ra.z, m0.w)));
+    r.oy = __fmaf_rn(m1.x, ra.x, __fmaf_rn(m1.y, ra.y, __fmaf_rn(m1.z, ra.z, m1.w)));
+    r.oz = __fmaf_rn(m2.x, ra.x, __fmaf_rn(m2.y, ra.y, __fmaf_rn(m2.z, ra.z, m2.w)));
+    r.dx = __fmaf_rn(m0.x, rb.x, __fmaf_rn(m0.y, rb.y, __fmul_rn(m0.z, rb.z)));
+    r.dy = __fmaf_rn(m1.x, rb.x, __fmaf_rn(m1.y, rb.y, __fmul_rn(m1.z, rb.z)));
+    r.dz = __fmaf_rn(m2.x, rb.x, __fmaf_rn(m2.y, rb.y, __fmul_rn(m2.z, rb.z)));
+    float u = __uint_as_float(h1.x), v = __uint_as_float(h1.y);
+    refine_bary(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), u, v);
+    hits[3 * i + 1] = make_uint2(__float_as_uint(u), __float_as_uint(v));
+    hits[3 * i + 2] = make_uint2(h2.x, 0u);
+}
+
+PhaseWeights phase_weights() {
+    static PhaseWeights w = [] {
+        PhaseWeights d{1, 1, 1, 2};
+        if (const char *e = getenv("LC_B200_PHASE_WEIGHTS")) sscanf(e, "%d,%d,%d,%d", &d.node, &d.tri, &d.inst, &d.fetch);
+        return d;
+    }();
+    return w;
 }
 
 template <bool ANY, bool COUNTERS>
@@ -347,8 +403,12 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
     unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid == 0) return;
-    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr);
+    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, phase_weights());
     lc.count++;
+    if (!ANY) {
+        k_refine<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), reinterpret_cast<uint2 *>(out), count);
+        lc.count++;
+    }
 }
 
 }  // namespace

@@ -74,7 +74,7 @@ class Device:
         """`Device::create_buffer_from_slice`: element = one row of `arr` (or one item of a structured array)."""
         arr = np.ascontiguousarray(arr)
         count = arr.shape[0]
-        stride = arr.nbytes // max(count, 1) if count else arr.dtype.itemsize
+        stride = int(np.prod(arr.shape[1:], dtype=np.int64)) * arr.dtype.itemsize
         buf = self.create_buffer(count, stride, min(stride & -stride, 16) if stride else 4)
         buf.view().copy_from(arr)
         return buf
