@@ -1,0 +1,81 @@
+"""Host-side logic of the multi-GPU partitioning, on CPU: ray slices, Morton tile assignment and the one
+collective of the path (all-gather of equal-sized per-rank tile buffers) over gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import luisa_compute_rs_b200.sharding as sh
+
+
+def test_ray_slices_partition_the_batch():
+    for n in (0, 1, 7, 1000, (1 << 24) + 3):
+        for world in (1, 2, 3, 4, 8):
+            edges = [sh.ray_slice(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("w,h", [(3840, 2160), (1024, 1024), (100, 70), (64, 64)])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_tiles_cover_every_pixel_exactly_once(w, h, world):
+    seen = np.zeros(w * h, np.int32)
+    counts = []
+    for r in range(world):
+        tx, ty = sh.tiles_of_rank(w, h, r, world)
+        idx, valid = sh.pixels_of_tiles(tx, ty, w, h)
+        np.add.at(seen, idx[valid], 1)
+        counts.append(tx.shape[0])
+        assert tx.shape[0] <= sh.padded_tile_count(w, h, world)
+    assert (seen == 1).all()
+    assert max(counts) - min(counts) <= 1   # balanced along the Morton curve
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, w, h, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank "renders" its tiles: pixel value = f(global pixel index), independent of the partition
+    tx, ty = sh.tiles_of_rank(w, h, rank, world)
+    idx, valid = sh.pixels_of_tiles(tx, ty, w, h)
+    per_rank = sh.padded_tile_count(w, h, world) * sh.TILE * sh.TILE
+    local = torch.zeros(per_rank, 4)
+    vals = torch.from_numpy(np.stack([idx, idx * 2, idx % 7, np.ones_like(idx)], 1).astype(np.float32))
+    vals[~torch.from_numpy(valid)] = 0
+    local[: idx.shape[0]] = vals
+    g = sh.gather_tiles(local, dist, world)
+    img = sh.untile(g.numpy(), w, h, world)
+    np.save(os.path.join(out_dir, f"img{rank}.npy"), img)
+    # ray batches: each rank contributes its contiguous slice of a global hit buffer
+    n = 1001
+    b, e = sh.ray_slice(n, rank, world)
+    pad = -(-n // world)
+    mine = torch.full((pad,), -1, dtype=torch.int64)
+    mine[: e - b] = torch.arange(b, e)
+    allr = sh.gather_tiles(mine, dist, world)
+    flat = torch.cat([allr[r, : sh.ray_slice(n, r, world)[1] - sh.ray_slice(n, r, world)[0]] for r in range(world)])
+    assert torch.equal(flat, torch.arange(n))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_reassembles_the_framebuffer(tmp_path):
+    w, h, world = 200, 136, 2
+    mp.spawn(_worker, args=(world, _free_port(), w, h, str(tmp_path)), nprocs=world, join=True)
+    px = np.arange(w * h)
+    want = np.stack([px, px * 2, px % 7, np.ones_like(px)], 1).astype(np.float32).reshape(h, w, 4)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"img{r}.npy"), want)
