@@ -29,8 +29,10 @@ __global__ void k_init_header(BuildHeader *h, unsigned long long *queue, uint32_
     for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
 }
 
-// warp-reduce the centroid and fold it into the header's ordered-int bounds
+// block-reduce the centroid (shuffles, then one shared-memory round) and fold it into the header's ordered-int
+// bounds: 6 atomics per block instead of per warp
 __device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, BuildHeader *h) {
+    __shared__ float s_lo[8][3], s_hi[8][3];
     float lo[3], hi[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) { lo[k] = valid ? c[k] : FLT_MAX; hi[k] = valid ? c[k] : -FLT_MAX; }
@@ -42,11 +44,19 @@ __device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, B
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
         }
     }
-    if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
+    const int warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            atomicMin(&h->bounds_lo[k], float_to_ordered(lo[k]));
-            atomicMax(&h->bounds_hi[k], float_to_ordered(hi[k]));
+        for (int k = 0; k < 3; k++) { s_lo[warp][k] = lo[k]; s_hi[warp][k] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        float l = s_lo[0][k], u = s_hi[0][k];
+        for (int w = 1; w < n_warps; w++) { l = fminf(l, s_lo[w][k]); u = fmaxf(u, s_hi[w][k]); }
+        if (l <= u) {
+            atomicMin(&h->bounds_lo[k], float_to_ordered(l));
+            atomicMax(&h->bounds_hi[k], float_to_ordered(u));
         }
     }
 }

@@ -614,6 +614,11 @@ lcb_device_interface create_device(lcb_context, const char *name, const char *js
     CUDA_CHECK(cudaSetDevice(ordinal));
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, ordinal));
     if (prop.major != 10) fatal("device %d is sm_%d%d; this library contains sm_100a code only", ordinal, prop.major, prop.minor);
+    {   // builds allocate scratch + result arrays stream-ordered; keep freed blocks in the pool instead of returning
+        // them to the driver at every synchronisation (the default threshold of 0 makes each rebuild re-map memory)
+        cudaMemPool_t pool; CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, ordinal));
+        unsigned long long keep = ~0ull; CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     auto *d = new DeviceObj; d->ordinal = ordinal;
     d->internal = make_stream(d);
     CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));

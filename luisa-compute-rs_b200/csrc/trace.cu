@@ -9,7 +9,10 @@
 // every lane that owns a node group pops one child and tests its 8 quantised child boxes,
 // then every lane that owns primitives tests them, so the warp stays converged on the two
 // expensive code regions.  A node is one 128-byte line fetched as 8 x LDG.128; the traversal
-// stack holds one (child_base, hit mask) group per level and lives in local memory.
+// stack holds one (child_base, hit mask) group per level: the first kSmemStack levels live in
+// shared memory laid out [level][thread] (bank = f(thread) only, so pushes and pops at
+// divergent depths are conflict-free), deeper levels spill to local memory.  Leaving an
+// instance re-reads the 32-byte ray instead of keeping the world-space setup on the stack.
 //
 // The per-triangle arithmetic is the canonical fp32 sequence documented in DESIGN.md §3 and
 // restated independently in oracle/oracle.c: every operation is an explicit round-to-nearest
@@ -27,6 +30,9 @@ namespace {
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
+#ifndef LCB_TRACE_MIN_BLOCKS
+#define LCB_TRACE_MIN_BLOCKS 6
+#endif
 
 struct RaySetup {
     float ox, oy, oz, dx, dy, dz;  // ray in the current space (world or object)
@@ -81,6 +87,13 @@ __device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const
 __device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
 __device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
+// each byte -> 0xff if its top bit is set, else 0x00 (prmt sign-replicate mode; __byte_perm masks the selector's msb away)
+__device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
+    return d;
+}
+
 // Tests the 8 children of one node.  Returns the hit mask: bits 24..31 internal children in
 // traversal priority order for this ray's octant, bits 0..23 leaf primitives.
 __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ node, const RaySetup &r, float tmin, float tmax,
@@ -104,28 +117,32 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
     const float bnx = fmaf(-8388608.0f, ax, cx - px), bfx = fmaf(-8388608.0f, ax, cx + px);
     const float bny = fmaf(-8388608.0f, ay, cy - py), bfy = fmaf(-8388608.0f, ay, cy + py);
     const float bnz = fmaf(-8388608.0f, az, cz - pz), bfz = fmaf(-8388608.0f, az, cz + pz);
+    // hit-mask construction on 4 meta bytes at a time (after Ylitie et al. 2017): per child only a byte extract,
+    // a shift and a select remain.  Internal children (low 5 bits >= 24) get their bit index XORed with the
+    // ray octant so that __clz order is front-to-back order.
+    const uint32_t oct4 = r.octinv * 0x01010101u;
+    const uint32_t inner_lo = sign_extend_bytes((n1.z & (n1.z << 1) & 0x10101010u) << 3);  // 0xff per internal child
+    const uint32_t inner_hi = sign_extend_bytes((n1.w & (n1.w << 1) & 0x10101010u) << 3);
+    const uint32_t idx_lo = (n1.z ^ (oct4 & inner_lo)) & 0x1f1f1f1fu, idx_hi = (n1.w ^ (oct4 & inner_hi)) & 0x1f1f1f1fu;
+    const uint32_t bits_lo = (n1.z >> 5) & 0x07070707u, bits_hi = (n1.w >> 5) & 0x07070707u;
     uint32_t hits = 0;
-#define LCB_CHILD(I, WORD, CONV, METAWORD, METASHIFT)                                                        \
+#define LCB_CHILD(WORD, CONV, BITS, IDX, SHIFT)                                                              \
     {                                                                                                        \
         const float tn = fmaxf(fmaxf(fmaf(CONV(qnx.WORD), ax, bnx), fmaf(CONV(qny.WORD), ay, bny)),          \
                                fmaxf(fmaf(CONV(qnz.WORD), az, bnz), tmin));                                  \
         const float tf = fminf(fminf(fmaf(CONV(qfx.WORD), ax, bfx), fmaf(CONV(qfy.WORD), ay, bfy)),          \
                                fminf(fmaf(CONV(qfz.WORD), az, bfz), tmax));                                  \
-        if (tn <= tf) {                                                                                      \
-            const uint32_t meta = (METAWORD >> METASHIFT) & 0xffu;                                           \
-            const uint32_t low = meta & 0x1fu;                                                               \
-            const uint32_t bit = low >= 24u ? 24u + ((uint32_t)(I) ^ r.octinv) : low;                        \
-            hits |= (meta >> 5) << bit;                                                                      \
-        }                                                                                                    \
+        const uint32_t b = ((BITS >> SHIFT) & 0xffu) << ((IDX >> SHIFT) & 31u);                              \
+        hits |= tn <= tf ? b : 0u;                                                                           \
     }
-    LCB_CHILD(0, x, q16_lo, n1.z, 0)
-    LCB_CHILD(1, x, q16_hi, n1.z, 8)
-    LCB_CHILD(2, y, q16_lo, n1.z, 16)
-    LCB_CHILD(3, y, q16_hi, n1.z, 24)
-    LCB_CHILD(4, z, q16_lo, n1.w, 0)
-    LCB_CHILD(5, z, q16_hi, n1.w, 8)
-    LCB_CHILD(6, w, q16_lo, n1.w, 16)
-    LCB_CHILD(7, w, q16_hi, n1.w, 24)
+    LCB_CHILD(x, q16_lo, bits_lo, idx_lo, 0)
+    LCB_CHILD(x, q16_hi, bits_lo, idx_lo, 8)
+    LCB_CHILD(y, q16_lo, bits_lo, idx_lo, 16)
+    LCB_CHILD(y, q16_hi, bits_lo, idx_lo, 24)
+    LCB_CHILD(z, q16_lo, bits_hi, idx_hi, 0)
+    LCB_CHILD(z, q16_hi, bits_hi, idx_hi, 8)
+    LCB_CHILD(w, q16_lo, bits_hi, idx_hi, 16)
+    LCB_CHILD(w, q16_hi, bits_hi, idx_hi, 24)
 #undef LCB_CHILD
     return hits;
 }
@@ -189,13 +206,17 @@ __device__ __forceinline__ void refine_bary(const RaySetup &r, const float4 v0, 
 // Scheduling weights of the phase vote (lanes wanting a phase x weight; highest score runs).
 struct PhaseWeights { int node, tri, inst, fetch; };
 
-constexpr int kSavedSlots = 7;  // stack[0..6] hold the world-space RaySetup while the ray is inside an instance
+constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
+constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
 
 template <bool ANY, bool COUNTERS>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out, unsigned long long count,
-                                                         uint32_t mask, unsigned long long *work_counter, TraceCounters *ctr, PhaseWeights w) {
-    uint2 stack[kSavedSlots + kTraversalStack];
+__global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out,
+                                                                               unsigned long long count, uint32_t mask, unsigned long long *work_counter,
+                                                                               TraceCounters *ctr, PhaseWeights w) {
+    __shared__ uint2 s_stack[kSmemStack * kTraceThreads];
+    uint2 l_stack[kLocalStack];
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
+    uint2 *const my_stack = s_stack + threadIdx.x;
 
     // warp-uniform pool of ray indices
     unsigned long long pool_next = 0, pool_end = 0;
@@ -211,43 +232,25 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
     uint2 G = make_uint2(0, 0), Gt = make_uint2(0, 0);
-    int sp = kSavedSlots;
+    int sp = 0;
     unsigned long long n_nodes = 0, n_tris = 0, n_inst = 0, n_rays = 0;
 
+#define LCB_PUSH(E)                                                          \
+    {                                                                        \
+        if (sp < kSmemStack) my_stack[sp * kTraceThreads] = (E);             \
+        else l_stack[sp - kSmemStack] = (E);                                 \
+        sp++;                                                                \
+    }
+
     for (;;) {
-        // ---- normalise: every lane that owns a ray either has pending work or retires ----------
-        while (has_ray && Gt.y == 0u && (G.y & 0xff000000u) == 0u) {
-            if (sp == kSavedSlots) {
-                if (ANY) {
-                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
-                } else {
-                    uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
-                    o[0] = make_uint2(hit_inst, hit_prim);
-                    o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
-                    // the pad word carries the winning PackedTri slot to k_refine, which clears it
-                    o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), hit_slot);
-                }
-                has_ray = false;
-                break;
-            }
-            const uint2 e = stack[--sp];
-            if (e.y == 0u) {  // sentinel: back to world space, restore the saved setup
-                const uint2 s0 = stack[0], s1 = stack[1], s2 = stack[2], s3 = stack[3], s4 = stack[4], s5 = stack[5], s6 = stack[6];
-                r.ox = __uint_as_float(s0.x); r.oy = __uint_as_float(s0.y); r.oz = __uint_as_float(s1.x);
-                r.dx = __uint_as_float(s1.y); r.dy = __uint_as_float(s2.x); r.dz = __uint_as_float(s2.y);
-                r.ix = __uint_as_float(s3.x); r.iy = __uint_as_float(s3.y); r.iz = __uint_as_float(s4.x);
-                r.sx = __uint_as_float(s4.y); r.sy = __uint_as_float(s5.x); r.sz = __uint_as_float(s5.y);
-                r.kz = (int)s6.x; r.octinv = s6.y;
-                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
-            } else if (e.y & 0xff000000u) G = e;
-            else Gt = e;
-        }
+        // Invariant: every lane that owns a ray has pending work (a non-empty node group G or primitive group Gt).
         // ---- vote ---------------------------------------------------------------------------
         const bool in_blas = cur_inst != 0xffffffffu;
-        const uint32_t m_tri = __ballot_sync(kFull, has_ray && Gt.y != 0u && in_blas);
-        const uint32_t m_inst = __ballot_sync(kFull, has_ray && Gt.y != 0u && !in_blas);
+        const bool want_prims = has_ray && Gt.y != 0u;
+        const uint32_t m_tri = __ballot_sync(kFull, want_prims && in_blas);
+        const uint32_t m_inst = __ballot_sync(kFull, want_prims && !in_blas);
         const uint32_t m_node = __ballot_sync(kFull, has_ray && Gt.y == 0u);
-        const uint32_t m_idle = __ballot_sync(kFull, !has_ray);
+        const uint32_t m_idle = ~(m_tri | m_inst | m_node);
         const bool can_fetch = !(exhausted && pool_next == pool_end);
         const int s_node = __popc(m_node) * w.node, s_tri = __popc(m_tri) * w.tri, s_inst = __popc(m_inst) * w.inst;
         const int s_fetch = can_fetch ? __popc(m_idle) * w.fetch : 0;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
 
         if (s_tri == best) {
             // ---- triangle phase: one canonical test per participating lane -----------------
-            if (has_ray && Gt.y != 0u && in_blas) {
+            if (want_prims && in_blas) {
                 const uint32_t bit = __ffs(Gt.y) - 1;
                 Gt.y &= Gt.y - 1;
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
                 float t, u, v;
                 if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, u, v)) {
                     if (ANY) {
-                        hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = kSavedSlots;  // retire at the next normalise
+                        hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = 0;  // retires in the tail below
                     } else {
                         const uint32_t prim = __float_as_uint(v0.w);
                         const bool better = t < tbest || hit_inst == 0xffffffffu ||
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
                 const uint32_t slot = (bit - 24u) ^ r.octinv;
                 const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
                 const WideNode *node = nodes + (G.x + rel);
-                if (G.y & 0xff000000u) stack[sp++] = G;
+                if (G.y & 0xff000000u) LCB_PUSH(G)
                 uint32_t child_base, prim_base, imask;
                 const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
                 if (COUNTERS) n_nodes++;
@@ -291,20 +294,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
             }
         } else if (s_inst == best) {
             // ---- instance phase: TLAS leaf -> transform the ray and descend into the BLAS ---
-            if (has_ray && Gt.y != 0u && !in_blas) {
+            if (want_prims && !in_blas) {
                 const uint32_t bit = __ffs(Gt.y) - 1;
                 Gt.y &= Gt.y - 1;
                 const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
                 const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
                 const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
                 if ((meta.x & mask) != 0u) {
-                    if (Gt.y) stack[sp++] = Gt;
-                    if (G.y & 0xff000000u) stack[sp++] = G;
-                    stack[sp++] = make_uint2(0u, 0u);  // sentinel
-                    stack[0] = make_uint2(__float_as_uint(r.ox), __float_as_uint(r.oy)); stack[1] = make_uint2(__float_as_uint(r.oz), __float_as_uint(r.dx));
-                    stack[2] = make_uint2(__float_as_uint(r.dy), __float_as_uint(r.dz)); stack[3] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
-                    stack[4] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.sx)); stack[5] = make_uint2(__float_as_uint(r.sy), __float_as_uint(r.sz));
-                    stack[6] = make_uint2((uint32_t)r.kz, r.octinv);
+                    if (Gt.y) LCB_PUSH(Gt)
+                    if (G.y & 0xff000000u) LCB_PUSH(G)
+                    LCB_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
                     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                     nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
@@ -335,7 +334,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
                     tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
                     hit_inst = 0xffffffffu; hit_prim = 0xffffffffu; hit_u = 0.f; hit_v = 0.f; hit_slot = 0;
                     cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
-                    sp = kSavedSlots;
+                    sp = 0;
                     G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
                     Gt = make_uint2(0u, 0u);
                     has_ray = true;
@@ -345,7 +344,37 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(AccelView acc, const fl
                 pool_next = adv < pool_end ? adv : pool_end;
             }
         }
+
+        // ---- tail: lanes that ran out of work pop the next group, or retire -------------------
+        if (has_ray && Gt.y == 0u && (G.y & 0xff000000u) == 0u) {
+            bool retire = false;
+            for (;;) {
+                if (sp == 0) { retire = true; break; }
+                --sp;
+                const uint2 e = sp < kSmemStack ? my_stack[sp * kTraceThreads] : l_stack[sp - kSmemStack];
+                if (e.y & 0xff000000u) { G = e; break; }
+                if (e.y != 0u) { Gt = e; break; }
+                // sentinel: the instance is exhausted, back to world space
+                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+                if (sp == 0) { retire = true; break; }  // nothing left in the TLAS either: skip the re-setup
+                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                setup_world(r, ra, rb);
+            }
+            if (retire) {
+                if (ANY) {
+                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
+                } else {
+                    uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
+                    o[0] = make_uint2(hit_inst, hit_prim);
+                    o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
+                    // the pad word carries the winning PackedTri slot to k_refine, which clears it
+                    o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), hit_slot);
+                }
+                has_ray = false;
+            }
+        }
     }
+#undef LCB_PUSH
     if (COUNTERS) {
         atomicAdd(&ctr->nodes_visited, n_nodes);
         atomicAdd(&ctr->tris_tested, n_tris);
@@ -381,7 +410,7 @@ __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__r
 
 PhaseWeights phase_weights() {
     static PhaseWeights w = [] {
-        PhaseWeights d{1, 1, 1, 2};
+        PhaseWeights d{2, 3, 3, 4};
         if (const char *e = getenv("LC_B200_PHASE_WEIGHTS")) sscanf(e, "%d,%d,%d,%d", &d.node, &d.tri, &d.inst, &d.fetch);
         return d;
     }();
