@@ -3,22 +3,24 @@
 // Replaces rtcIntersect1 / rtcOccluded1 behind AccelImpl::trace_closest / trace_any
 // (cpu/accel.rs:449-535) for whole buffers of rays.
 //
-// Execution model: one ray per lane; warps are persistent and refill idle lanes every
-// iteration from a warp-local pool of ray indices that is topped up with ONE global atomic per
-// 128 rays (warp-synchronous work distribution, ballots only).  Each iteration is "if-if":
-// every lane that owns a node group pops one child and tests its 8 quantised child boxes,
-// then every lane that owns primitives tests them, so the warp stays converged on the two
-// expensive code regions.  A node is one 128-byte line fetched as 8 x LDG.128; the traversal
-// stack holds one (child_base, hit mask) group per level: the first kSmemStack levels live in
-// shared memory laid out [level][thread] (bank = f(thread) only, so pushes and pops at
-// divergent depths are conflict-free), deeper levels spill to local memory.  Leaving an
-// instance re-reads the 32-byte ray instead of keeping the world-space setup on the stack.
+// Execution model: one ray per lane; warps are persistent and refill idle lanes from a
+// warp-local pool of ray indices that is topped up with ONE global atomic per 128 rays
+// (warp-synchronous work distribution, ballots only).  Every trip of the main loop is
+// "if-if" with postponing (after Aila & Laine 2009 and Ylitie et al. 2017): all lanes that own a
+// node group pop one child and test its 8 quantised child boxes, then the lanes that hold
+// primitives test ONE of them; a group that is not exhausted by that is postponed (pushed) if
+// the lane still has node work, so that the warp returns to the wide node step together.
+// A node is one 128-byte line fetched as 8 x LDG.128.  The traversal stack holds one
+// (child_base, hit mask) group per level: the first kSmemStack levels live in shared memory
+// laid out [level][thread] (bank = f(thread) only, so pushes and pops at divergent depths are
+// conflict-free), deeper levels spill to local memory.  Leaving an instance re-reads the
+// 32-byte ray instead of keeping the world-space setup on the stack.
 //
 // The per-triangle arithmetic is the canonical fp32 sequence documented in DESIGN.md §3 and
 // restated independently in oracle/oracle.c: every operation is an explicit round-to-nearest
 // intrinsic so that nvcc cannot contract or reorder it.  Box culling is conservative with
 // respect to that arithmetic (planes padded by 2^-20 of the L-inf distance to the node), so
-// results do not depend on the tree.
+// results do not depend on the tree nor on the schedule.
 #include "build.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -28,11 +30,14 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
 #define LCB_TRACE_MIN_BLOCKS 6
 #endif
+constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
+constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
 
 struct RaySetup {
     float ox, oy, oz, dx, dy, dz;  // ray in the current space (world or object)
@@ -71,21 +76,26 @@ __device__ __forceinline__ void setup_world(RaySetup &r, const float4 a, const f
 }
 
 // world -> object with the canonical nested-fma order
-__device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
+__device__ __forceinline__ void transform_ray(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
     r.ox = __fmaf_rn(m0.x, wo.x, __fmaf_rn(m0.y, wo.y, __fmaf_rn(m0.z, wo.z, m0.w)));
     r.oy = __fmaf_rn(m1.x, wo.x, __fmaf_rn(m1.y, wo.y, __fmaf_rn(m1.z, wo.z, m1.w)));
     r.oz = __fmaf_rn(m2.x, wo.x, __fmaf_rn(m2.y, wo.y, __fmaf_rn(m2.z, wo.z, m2.w)));
     r.dx = __fmaf_rn(m0.x, wd.x, __fmaf_rn(m0.y, wd.y, __fmul_rn(m0.z, wd.z)));
     r.dy = __fmaf_rn(m1.x, wd.x, __fmaf_rn(m1.y, wd.y, __fmul_rn(m1.z, wd.z)));
     r.dz = __fmaf_rn(m2.x, wd.x, __fmaf_rn(m2.y, wd.y, __fmul_rn(m2.z, wd.z)));
+}
+
+__device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
+    transform_ray(r, wo, wd, m0, m1, m2);
     finish_setup(r);
 }
 
 // 16-bit plane index -> float 2^23 + q in ONE byte-permute (no int->float conversion, no subtraction): the 2^23
 // bias is folded into the per-node plane offsets below, at the price of half a quantisation step of rounding
-// slop that the padding absorbs (one extra step, 2^-16 of the node extent).
-__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
-__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
+// slop that the padding absorbs (one extra step, 2^-16 of the node extent).  The constant sits in the first
+// operand so that the selector is an immediate and 0x4B000000 lives in one register for the whole kernel.
+__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3254)); }
+__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3276)); }
 
 // each byte -> 0xff if its top bit is set, else 0x00 (prmt sign-replicate mode; __byte_perm masks the selector's msb away)
 __device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
@@ -149,9 +159,10 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
 
 __device__ __forceinline__ float pick(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
 
-// The canonical fp32 ray/triangle evaluation (oracle.c canon_tri).
+// The canonical fp32 ray/triangle evaluation (oracle.c canon_tri).  The traversal loop only needs
+// the decision and t; (V, W, det) are handed back so that the barycentrics can be formed where they are needed.
 __device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin, float tmax, const float4 v0, const float4 v1, const float4 v2,
-                                                   float &t_out, float &u_out, float &v_out) {
+                                                   float &t_out, float &V_out, float &W_out, float &det_out) {
     const float a0 = __fsub_rn(v0.x, r.ox), a1 = __fsub_rn(v0.y, r.oy), a2 = __fsub_rn(v0.z, r.oz);
     const float b0 = __fsub_rn(v1.x, r.ox), b1 = __fsub_rn(v1.y, r.oy), b2 = __fsub_rn(v1.z, r.oz);
     const float c0 = __fsub_rn(v2.x, r.ox), c1 = __fsub_rn(v2.y, r.oy), c2 = __fsub_rn(v2.z, r.oz);
@@ -177,14 +188,14 @@ __device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin
     const float T = __fmaf_rn(U, az, __fmaf_rn(V, bz, __fmul_rn(W, cz)));
     const float t = __fdiv_rn(T, det);
     if (!(t > tmin && t <= tmax)) return false;
-    const float rdet = __frcp_rn(det);
-    t_out = t; u_out = __fmul_rn(V, rdet); v_out = __fmul_rn(W, rdet);
+    t_out = t; V_out = V; W_out = W; det_out = det;
     return true;
 }
 
 // Reported barycentrics of the winning triangle: one double-precision Moeller-Trumbore evaluation on the
 // canonical object-space ray (fixed operation order; oracle.c refine_bary).  Once per ray, off the hot loop.
-__device__ __forceinline__ void refine_bary(const RaySetup &r, const float4 v0, const float4 v1, const float4 v2, float &u_io, float &v_io) {
+// Returns false when the double determinant vanishes (the canonical fp32 barycentrics stand).
+__device__ __forceinline__ bool refine_bary(const RaySetup &r, const float4 v0, const float4 v1, const float4 v2, float &u_out, float &v_out) {
     const double e1x = __dsub_rn((double)v1.x, (double)v0.x), e1y = __dsub_rn((double)v1.y, (double)v0.y), e1z = __dsub_rn((double)v1.z, (double)v0.z);
     const double e2x = __dsub_rn((double)v2.x, (double)v0.x), e2y = __dsub_rn((double)v2.y, (double)v0.y), e2z = __dsub_rn((double)v2.z, (double)v0.z);
     const double sx = __dsub_rn((double)r.ox, (double)v0.x), sy = __dsub_rn((double)r.oy, (double)v0.y), sz = __dsub_rn((double)r.oz, (double)v0.z);
@@ -193,26 +204,26 @@ __device__ __forceinline__ void refine_bary(const RaySetup &r, const float4 v0, 
     const double py = __dsub_rn(__dmul_rn(dz, e2x), __dmul_rn(dx, e2z));
     const double pz = __dsub_rn(__dmul_rn(dx, e2y), __dmul_rn(dy, e2x));
     const double det = __dadd_rn(__dadd_rn(__dmul_rn(e1x, px), __dmul_rn(e1y, py)), __dmul_rn(e1z, pz));
-    if (det == 0.0) return;
+    if (det == 0.0) return false;
     const double inv = __ddiv_rn(1.0, det);
     const double u = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx, px), __dmul_rn(sy, py)), __dmul_rn(sz, pz)), inv);
     const double qx = __dsub_rn(__dmul_rn(sy, e1z), __dmul_rn(sz, e1y));
     const double qy = __dsub_rn(__dmul_rn(sz, e1x), __dmul_rn(sx, e1z));
     const double qz = __dsub_rn(__dmul_rn(sx, e1y), __dmul_rn(sy, e1x));
     const double v = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, qx), __dmul_rn(dy, qy)), __dmul_rn(dz, qz)), inv);
-    u_io = __double2float_rn(u); v_io = __double2float_rn(v);
+    u_out = __double2float_rn(u); v_out = __double2float_rn(v);
+    return true;
 }
 
-// Scheduling weights of the phase vote (lanes wanting a phase x weight; highest score runs).
-struct PhaseWeights { int node, tri, inst, fetch; };
-
-constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
-constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
+// Scheduling knob of the traversal loop (LC_B200_TRACE_TUNE = "fetch_min").
+struct TraceTune {
+    int fetch_min;      // refill when at least this many lanes are idle
+};
 
 template <bool ANY, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out,
                                                                                unsigned long long count, uint32_t mask, unsigned long long *work_counter,
-                                                                               TraceCounters *ctr, PhaseWeights w) {
+                                                                               TraceCounters *ctr, TraceTune tune) {
     __shared__ uint2 s_stack[kSmemStack * kTraceThreads];
     uint2 l_stack[kLocalStack];
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
@@ -226,9 +237,8 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
     unsigned long long ray_idx = 0;
     RaySetup r;
     float tmin = 0.f, tbest = 0.f, ray_tmax = 0.f;
-    uint32_t hit_inst = 0xffffffffu, hit_prim = 0xffffffffu, hit_slot = 0;  // hit_slot: index of the winning PackedTri
-    float hit_u = 0.f, hit_v = 0.f;
-    uint32_t cur_inst = 0xffffffffu;
+    uint32_t hit_inst = kNone, hit_prim = kNone, hit_slot = 0;  // hit_slot: index of the winning PackedTri
+    uint32_t cur_inst = kNone;
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
     uint2 G = make_uint2(0, 0), Gt = make_uint2(0, 0);
@@ -244,108 +254,105 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
 
     for (;;) {
         // Invariant: every lane that owns a ray has pending work (a non-empty node group G or primitive group Gt).
-        // ---- vote ---------------------------------------------------------------------------
-        const bool in_blas = cur_inst != 0xffffffffu;
-        const bool want_prims = has_ray && Gt.y != 0u;
-        const uint32_t m_tri = __ballot_sync(kFull, want_prims && in_blas);
-        const uint32_t m_inst = __ballot_sync(kFull, want_prims && !in_blas);
-        const uint32_t m_node = __ballot_sync(kFull, has_ray && Gt.y == 0u);
-        const uint32_t m_idle = ~(m_tri | m_inst | m_node);
-        const bool can_fetch = !(exhausted && pool_next == pool_end);
-        const int s_node = __popc(m_node) * w.node, s_tri = __popc(m_tri) * w.tri, s_inst = __popc(m_inst) * w.inst;
-        const int s_fetch = can_fetch ? __popc(m_idle) * w.fetch : 0;
-        const int best = max(max(s_node, s_tri), max(s_inst, s_fetch));
-        if (best == 0) break;  // no lane owns a ray and none can be fetched
-
-        if (s_tri == best) {
-            // ---- triangle phase: one canonical test per participating lane -----------------
-            if (want_prims && in_blas) {
-                const uint32_t bit = __ffs(Gt.y) - 1;
-                Gt.y &= Gt.y - 1;
-                const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
-                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-                if (COUNTERS) n_tris++;
-                float t, u, v;
-                if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, u, v)) {
-                    if (ANY) {
-                        hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = 0;  // retires in the tail below
-                    } else {
-                        const uint32_t prim = __float_as_uint(v0.w);
-                        const bool better = t < tbest || hit_inst == 0xffffffffu ||
-                                            (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
-                        if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_u = u; hit_v = v; hit_slot = Gt.x + bit; }
+        // ---- fetch: refill idle lanes from the warp-local pool ------------------------------------------------
+        const uint32_t m_idle = __ballot_sync(kFull, !has_ray);
+        if (m_idle != 0u) {
+            const bool can_fetch = !(exhausted && pool_next == pool_end);
+            if (!can_fetch) {
+                if (m_idle == kFull) break;
+            } else if (__popc(m_idle) >= tune.fetch_min || m_idle == kFull) {
+                if (pool_next == pool_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)kChunk);
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base >= count) exhausted = true;
+                    else { pool_next = base; pool_end = base + kChunk < count ? base + kChunk : count; }
+                }
+                if (pool_next != pool_end) {
+                    const unsigned long long mine = pool_next + __popc(m_idle & lt_mask);
+                    if (!has_ray && mine < pool_end) {
+                        ray_idx = mine;
+                        const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                        setup_world(r, ra, rb);
+                        tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
+                        hit_inst = kNone; hit_prim = kNone; hit_slot = 0;
+                        cur_inst = kNone; nodes = acc.tlas_nodes; tris = nullptr;
+                        sp = 0;
+                        G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
+                        Gt = make_uint2(0u, 0u);
+                        has_ray = true;
+                        if (COUNTERS) n_rays++;
                     }
-                }
-            }
-        } else if (s_node == best) {
-            // ---- node phase: pop one child of the node group, test its 8 children ----------
-            if (has_ray && Gt.y == 0u) {
-                const uint32_t bit = 31u - __clz(G.y);
-                G.y &= ~(1u << bit);
-                const uint32_t slot = (bit - 24u) ^ r.octinv;
-                const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
-                const WideNode *node = nodes + (G.x + rel);
-                if (G.y & 0xff000000u) LCB_PUSH(G)
-                uint32_t child_base, prim_base, imask;
-                const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
-                if (COUNTERS) n_nodes++;
-                G = make_uint2(child_base, (hits & 0xff000000u) | imask);
-                Gt = make_uint2(prim_base, hits & 0x00ffffffu);
-            }
-        } else if (s_inst == best) {
-            // ---- instance phase: TLAS leaf -> transform the ray and descend into the BLAS ---
-            if (want_prims && !in_blas) {
-                const uint32_t bit = __ffs(Gt.y) - 1;
-                Gt.y &= Gt.y - 1;
-                const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
-                const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
-                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
-                if ((meta.x & mask) != 0u) {
-                    if (Gt.y) LCB_PUSH(Gt)
-                    if (G.y & 0xff000000u) LCB_PUSH(G)
-                    LCB_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
-                    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
-                    const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
-                    nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
-                    tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                    const float4 wo = make_float4(r.ox, r.oy, r.oz, 0.f), wd = make_float4(r.dx, r.dy, r.dz, 0.f);
-                    setup_object(r, wo, wd, m0, m1, m2);
-                    cur_inst = inst;
-                    G = make_uint2(0u, 0x80000000u);
-                    Gt = make_uint2(0u, 0u);
-                    if (COUNTERS) n_inst++;
-                }
-            }
-        } else {
-            // ---- fetch phase: refill idle lanes from the warp-local pool --------------------
-            if (pool_next == pool_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)kChunk);
-                base = __shfl_sync(kFull, base, 0);
-                if (base >= count) exhausted = true;
-                else { pool_next = base; pool_end = base + kChunk < count ? base + kChunk : count; }
-            }
-            if (pool_next != pool_end) {
-                const unsigned long long mine = pool_next + __popc(m_idle & lt_mask);
-                if (!has_ray && mine < pool_end) {
-                    ray_idx = mine;
-                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                    setup_world(r, ra, rb);
-                    tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
-                    hit_inst = 0xffffffffu; hit_prim = 0xffffffffu; hit_u = 0.f; hit_v = 0.f; hit_slot = 0;
-                    cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
-                    sp = 0;
-                    G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
-                    Gt = make_uint2(0u, 0u);
-                    has_ray = true;
-                    if (COUNTERS) n_rays++;
-                }
-                const unsigned long long adv = pool_next + __popc(m_idle);
-                pool_next = adv < pool_end ? adv : pool_end;
+                    const unsigned long long adv = pool_next + __popc(m_idle);
+                    pool_next = adv < pool_end ? adv : pool_end;
+                } else if (m_idle == kFull) break;  // the batch is exhausted and no lane owns a ray
             }
         }
 
-        // ---- tail: lanes that ran out of work pop the next group, or retire -------------------
+        // ---- node step: pop the nearest child of the node group, test its 8 children ----------------------------
+        if (has_ray && Gt.y == 0u && (G.y & 0xff000000u) != 0u) {
+            const uint32_t bit = 31u - __clz(G.y);
+            G.y &= ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ r.octinv;
+            const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
+            const WideNode *node = nodes + (G.x + rel);
+            if (G.y & 0xff000000u) LCB_PUSH(G)
+            uint32_t child_base, prim_base, imask;
+            const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
+            if (COUNTERS) n_nodes++;
+            G = make_uint2(child_base, (hits & 0xff000000u) | imask);
+            Gt = make_uint2(prim_base, hits & 0x00ffffffu);
+        }
+
+        // ---- primitive step: one triangle (or one instance entry) per lane that holds a primitive group -----------
+        if (has_ray && Gt.y != 0u) {
+            {
+                const uint32_t bit = __ffs(Gt.y) - 1;
+                Gt.y &= Gt.y - 1;
+                if (cur_inst != kNone) {
+                    const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
+                    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                    if (COUNTERS) n_tris++;
+                    float t, V, W, det;
+                    if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, V, W, det)) {
+                        if (ANY) {
+                            hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = 0;  // retires in the tail below
+                        } else {
+                            const uint32_t prim = __float_as_uint(v0.w);
+                            const bool better = t < tbest || hit_inst == kNone ||
+                                                (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
+                            if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_slot = Gt.x + bit; }
+                        }
+                    }
+                } else {
+                    // TLAS leaf: transform the ray and descend into the instance's BLAS
+                    const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
+                    const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
+                    const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
+                    if ((meta.x & mask) != 0u) {
+                        if (Gt.y) LCB_PUSH(Gt)
+                        if (G.y & 0xff000000u) LCB_PUSH(G)
+                        LCB_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
+                        const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+                        const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+                        nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+                        tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                        const float4 wo = make_float4(r.ox, r.oy, r.oz, 0.f), wd = make_float4(r.dx, r.dy, r.dz, 0.f);
+                        setup_object(r, wo, wd, m0, m1, m2);
+                        cur_inst = inst;
+                        G = make_uint2(0u, 0x80000000u);
+                        Gt = make_uint2(0u, 0u);
+                        if (COUNTERS) n_inst++;
+                    }
+                }
+            }
+            // A lane whose group is not exhausted by this one test postpones the rest (pushes it) when it still has
+            // node work: on incoherent rays, returning to the wide node step with the whole warp beats draining the
+            // group with a few stragglers (tune sweep in profiles/r01_trace_tune_sweep.txt).
+            if (Gt.y != 0u && (G.y & 0xff000000u) != 0u) { LCB_PUSH(Gt) Gt.y = 0u; }
+        }
+
+        // ---- tail: lanes that ran out of work pop the next group, or retire ------------------------------------------
         if (has_ray && Gt.y == 0u && (G.y & 0xff000000u) == 0u) {
             bool retire = false;
             for (;;) {
@@ -355,20 +362,19 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                 if (e.y & 0xff000000u) { G = e; break; }
                 if (e.y != 0u) { Gt = e; break; }
                 // sentinel: the instance is exhausted, back to world space
-                cur_inst = 0xffffffffu; nodes = acc.tlas_nodes; tris = nullptr;
+                cur_inst = kNone; nodes = acc.tlas_nodes; tris = nullptr;
                 if (sp == 0) { retire = true; break; }  // nothing left in the TLAS either: skip the re-setup
                 const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
                 setup_world(r, ra, rb);
             }
             if (retire) {
                 if (ANY) {
-                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != 0xffffffffu ? 1u : 0u;
+                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != kNone ? 1u : 0u;
                 } else {
                     uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
                     o[0] = make_uint2(hit_inst, hit_prim);
-                    o[1] = make_uint2(__float_as_uint(hit_u), __float_as_uint(hit_v));
-                    // the pad word carries the winning PackedTri slot to k_refine, which clears it
-                    o[2] = make_uint2(__float_as_uint(hit_inst != 0xffffffffu ? tbest : ray_tmax), hit_slot);
+                    // barycentrics are formed by k_refine; the pad word carries the winning PackedTri slot to it
+                    o[2] = make_uint2(__float_as_uint(hit_inst != kNone ? tbest : ray_tmax), hit_slot);
                 }
                 has_ray = false;
             }
@@ -383,38 +389,41 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
     }
 }
 
-// Second pass of closest-hit queries: reported barycentrics of every hit, one thread per ray, fully converged.
+// Second pass of closest-hit queries: barycentrics of every hit, one thread per ray, fully converged.  The f64
+// evaluation is the reported value (oracle.c refine_bary); if its determinant vanishes the canonical fp32 ones stand.
 __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__restrict__ rays, uint2 *__restrict__ hits, unsigned long long count) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint2 h0 = hits[3 * i], h2 = hits[3 * i + 2];
-    if (h0.x == 0xffffffffu) { if (h2.y) hits[3 * i + 2] = make_uint2(h2.x, 0u); return; }
-    uint2 h1 = hits[3 * i + 1];
+    if (h0.x == kNone) { hits[3 * i + 1] = make_uint2(0u, 0u); hits[3 * i + 2] = make_uint2(h2.x, 0u); return; }
     const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h0.x);
     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
     const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + h2.y);
     const float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     RaySetup r;
-    r.ox = __fmaf_rn(m0.x, ra.x, __fmaf_rn(m0.y, ra.y, __fmaf_rn(m0.z, ra.z, m0.w)));
-    r.oy = __fmaf_rn(m1.x, ra.x, __fmaf_rn(m1.y, ra.y, __fmaf_rn(m1.z, ra.z, m1.w)));
-    r.oz = __fmaf_rn(m2.x, ra.x, __fmaf_rn(m2.y, ra.y, __fmaf_rn(m2.z, ra.z, m2.w)));
-    r.dx = __fmaf_rn(m0.x, rb.x, __fmaf_rn(m0.y, rb.y, __fmul_rn(m0.z, rb.z)));
-    r.dy = __fmaf_rn(m1.x, rb.x, __fmaf_rn(m1.y, rb.y, __fmul_rn(m1.z, rb.z)));
-    r.dz = __fmaf_rn(m2.x, rb.x, __fmaf_rn(m2.y, rb.y, __fmul_rn(m2.z, rb.z)));
-    float u = __uint_as_float(h1.x), v = __uint_as_float(h1.y);
-    refine_bary(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), u, v);
+    transform_ray(r, ra, rb, m0, m1, m2);
+    float u = 0.f, v = 0.f;
+    if (!refine_bary(r, v0, v1, v2, u, v)) {
+        finish_setup(r);
+        float t, V, W, det;
+        if (canonical_triangle(r, -INFINITY, INFINITY, v0, v1, v2, t, V, W, det)) {
+            const float rdet = __frcp_rn(det);
+            u = __fmul_rn(V, rdet); v = __fmul_rn(W, rdet);
+        }
+    }
     hits[3 * i + 1] = make_uint2(__float_as_uint(u), __float_as_uint(v));
     hits[3 * i + 2] = make_uint2(h2.x, 0u);
 }
 
-PhaseWeights phase_weights() {
-    static PhaseWeights w = [] {
-        PhaseWeights d{2, 3, 3, 4};
-        if (const char *e = getenv("LC_B200_PHASE_WEIGHTS")) sscanf(e, "%d,%d,%d,%d", &d.node, &d.tri, &d.inst, &d.fetch);
+TraceTune trace_tune() {
+    static TraceTune t = [] {
+        TraceTune d{6};
+        if (const char *e = getenv("LC_B200_TRACE_TUNE")) sscanf(e, "%d", &d.fetch_min);
         return d;
     }();
-    return w;
+    return t;
 }
 
 template <bool ANY, bool COUNTERS>
@@ -432,7 +441,7 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
     unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid == 0) return;
-    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, phase_weights());
+    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, trace_tune());
     lc.count++;
     if (!ANY) {
         k_refine<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), reinterpret_cast<uint2 *>(out), count);
