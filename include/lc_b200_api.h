@@ -325,7 +325,7 @@ LCB_EXPORT uint32_t lc_b200_instance_visibility_mask(lcb_device, lcb_accel, uint
 typedef struct lcb_build_stats {
     uint64_t primitive_count;  /* triangles (mesh) or instances (accel) */
     uint64_t wide_node_count;  /* 128-byte nodes */
-    uint64_t packed_tri_count; /* 48-byte leaf triangles */
+    uint64_t packed_tri_count; /* 64-byte leaf triangle records (36 B of vertices + prim id used) */
     uint64_t bvh_bytes;        /* nodes + packed triangles as allocated after compaction */
     uint32_t max_depth;        /* wide-tree depth */
     uint32_t was_refit;        /* 1 if PreferUpdate took the refit path */

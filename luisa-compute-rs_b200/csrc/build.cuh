@@ -71,6 +71,7 @@ struct AccelView {
     const uint32_t *tlas_prims;      // instance ids referenced by TLAS leaves
     const InstanceRec *instances;
     uint32_t instance_count;
+    float world_lo[3], world_hi[3];  // bounds of the TLAS root (ray reordering quantises origins against them)
 };
 
 void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,

@@ -1,7 +1,7 @@
 // bvh_build.cu — LBVH builder for sm_100a: primitive boxes + centroid bounds, 63-bit Morton
 // codes, onesweep sort (radix_sort.cu), fused bottom-up hierarchy emission + AABB refit with
 // atomic arrival flags (after Apetrei 2014), and collapse of the binary tree into 8-wide
-// 128-byte quantised nodes with packed 48-byte leaf triangles.
+// 128-byte quantised nodes with packed 64-byte leaf triangles.
 //
 // Replaces what the reference delegates to rtcCommitScene (cpu/accel.rs:258,439) /
 // optixAccelBuild (cuda_primitive.cpp:57-60).  No reference source exists for any of it.
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, 
             uint32_t qmin = 0xffff, qmax = 0;
             for (int c = 0; c < 8; c++) {
                 if (root.meta[c] == 0) continue;
-                qmin = min(qmin, (uint32_t)root.qlo[k][c]);
-                qmax = max(qmax, (uint32_t)root.qhi[k][c]);
+                qmin = min(qmin, (uint32_t)root.q[k][0][c]);
+                qmax = max(qmax, (uint32_t)root.q[k][1][c]);
             }
             olo[k] = __fmaf_rd((float)qmin, scale, root.org[k]);
             ohi[k] = __fmaf_ru((float)qmax, scale, root.org[k]);
@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(64) k_collapse(const BinNode *__restrict__ bin
             const int j = child_in_slot[s];
             if (j < 0) {
                 node.meta[s] = 0;
-                for (int k = 0; k < 3; k++) { node.qlo[k][s] = 0xffff; node.qhi[k][s] = 0; }
+                for (int k = 0; k < 3; k++) { node.q[k][0][s] = 0xffff; node.q[k][1][s] = 0; }
                 continue;
             }
-            for (int k = 0; k < 3; k++) quantise_axis(c[j].lo[k], c[j].hi[k], nlo[k], inv_scale[k], node.qlo[k][s], node.qhi[k][s]);
+            for (int k = 0; k < 3; k++) quantise_axis(c[j].lo[k], c[j].hi[k], nlo[k], inv_scale[k], node.q[k][0][s], node.q[k][1][s]);
             if (c[j].count > (uint32_t)kLeafMax) {
                 imask |= 1u << s;
                 node.meta[s] = (uint8_t)(0x20u | (24u + s));

@@ -146,6 +146,7 @@ struct AccelObj {
     InstanceRec *table = nullptr; uint32_t table_capacity = 0;
     WideNode *tlas_nodes = nullptr; uint32_t *tlas_prims = nullptr; uint32_t *active_ids = nullptr; uint32_t tlas_capacity = 0;
     uint32_t n_active = 0;
+    float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     lcb_build_stats stats{};
     std::mutex mu;
 };
@@ -440,6 +441,7 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (hdr.error) fatal("TLAS build failed (code %u)", hdr.error);
         if (hdr.emitted != na) fatal("TLAS build inconsistent: emitted %u of %u instances", hdr.emitted, na);
+        for (int k = 0; k < 3; k++) { a->world_lo[k] = hdr.root_lo[k]; a->world_hi[k] = hdr.root_hi[k]; }
         a->stats.wide_node_count = hdr.node_count; a->stats.packed_tri_count = hdr.prim_count; a->stats.max_depth = hdr.max_depth;
         a->stats.bvh_bytes = (uint64_t)hdr.node_count * sizeof(WideNode) + (uint64_t)n * sizeof(InstanceRec);
     } else {
@@ -457,6 +459,7 @@ AccelView view_of(AccelObj *a) {
     AccelView v{};
     v.tlas_nodes = a->n_active ? a->tlas_nodes : nullptr;
     v.tlas_prims = a->tlas_prims; v.instances = a->table; v.instance_count = (uint32_t)a->instances.size();
+    for (int k = 0; k < 3; k++) { v.world_lo[k] = a->world_lo[k]; v.world_hi[k] = a->world_hi[k]; }
     return v;
 }
 

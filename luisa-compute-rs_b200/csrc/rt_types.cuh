@@ -1,9 +1,12 @@
 // rt_types.cuh — HBM-resident data layouts of the B200 ray-tracing device.
 //
-// Everything the traversal kernels touch is laid out for full-line access:
-//   WideNode   128 B, 128-byte aligned : one L2 line / four 32 B sectors, fetched as 8 x LDG.128
-//   PackedTri   48 B,  16-byte aligned : three float4 (v0|prim, v1, v2)
-//   InstanceRec 96 B,  16-byte aligned : six float4
+// Everything the traversal kernels touch is laid out for full-sector access with sm_100's 256-bit loads
+// (LDG.E.ENL2.256: one 32-byte sector per lane and instruction — on divergent addresses the L1TEX data pipe
+// charges per lane and instruction, so wider loads are what relieves it; tools/micro/gather256.cu):
+//   WideNode    128 B, 128-byte aligned : one L2 line = four sectors, fetched as 4 x LDG.256
+//                                         (header | x planes lo,hi | y planes lo,hi | z planes lo,hi)
+//   PackedTri    64 B,  64-byte aligned : LDG.256 (v0|prim, v1) + LDG.128 (v2); 16 B spare
+//   InstanceRec 128 B,  16-byte aligned : eight float4
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,17 +29,17 @@ struct alignas(128) WideNode {
     uint32_t child_base;
     uint32_t prim_base;
     uint8_t meta[8];
-    uint16_t qlo[3][8];
-    uint16_t qhi[3][8];
+    uint16_t q[3][2][8];  // [axis][0 = lower plane, 1 = upper plane][slot]
 };
 static_assert(sizeof(WideNode) == 128, "WideNode must be one 128-byte line");
 
-struct alignas(16) PackedTri {
+struct alignas(64) PackedTri {
     float v0[3]; uint32_t prim;
     float v1[3]; uint32_t pad1;
     float v2[3]; uint32_t pad2;
+    uint32_t spare[4];
 };
-static_assert(sizeof(PackedTri) == 48, "PackedTri is 48 bytes");
+static_assert(sizeof(PackedTri) == 64, "PackedTri is 64 bytes");
 
 // One slot of the instance table (what AccelImpl keeps per instance, cpu/accel.rs:270-296).
 struct alignas(16) InstanceRec {

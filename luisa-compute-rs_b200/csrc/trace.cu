@@ -10,7 +10,8 @@
 // node group pop one child and test its 8 quantised child boxes, then the lanes that hold
 // primitives test ONE of them; a group that is not exhausted by that is postponed (pushed) if
 // the lane still has node work, so that the warp returns to the wide node step together.
-// A node is one 128-byte line fetched as 8 x LDG.128.  The traversal stack holds one
+// A node is one 128-byte line fetched as 4 x LDG.256 (sm_100's 256-bit loads halve the L1TEX
+// wavefronts of the divergent node fetch; near/far planes are then picked with register selects).  The traversal stack holds one
 // (child_base, hit mask) group per level: the first kSmemStack levels live in shared memory
 // laid out [level][thread] (bank = f(thread) only, so pushes and pops at divergent depths are
 // conflict-free), deeper levels spill to local memory.  Leaving an instance re-reads the
@@ -34,7 +35,7 @@ constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
-#define LCB_TRACE_MIN_BLOCKS 6
+#define LCB_TRACE_MIN_BLOCKS 7
 #endif
 constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
 constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
@@ -97,6 +98,16 @@ __device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const
 __device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3254)); }
 __device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3276)); }
 
+// 256-bit read-only global load (LDG.E.ENL2.256.CONSTANT): one full 32-byte sector per lane and instruction
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ldg256(const void *p) {
+    U8 r;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
 // each byte -> 0xff if its top bit is set, else 0x00 (prmt sign-replicate mode; __byte_perm masks the selector's msb away)
 __device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
     uint32_t d;
@@ -109,12 +120,17 @@ __device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
 __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ node, const RaySetup &r, float tmin, float tmax,
                                                    uint32_t &child_base, uint32_t &prim_base, uint32_t &imask) {
     const uint4 *p = reinterpret_cast<const uint4 *>(node);
-    const uint4 n0 = __ldg(p), n1 = __ldg(p + 1);
+    const U8 H = ldg256(p), X = ldg256(p + 2), Y = ldg256(p + 4), Z = ldg256(p + 6);
+    const uint4 n0 = make_uint4(H.v[0], H.v[1], H.v[2], H.v[3]), n1 = make_uint4(H.v[4], H.v[5], H.v[6], H.v[7]);
     const bool neg_x = (r.octinv & 1u) == 0, neg_y = (r.octinv & 2u) == 0, neg_z = (r.octinv & 4u) == 0;
-    // near/far plane vectors by direction sign: free, it is only an address
-    const uint4 qnx = __ldg(p + (neg_x ? 5 : 2)), qfx = __ldg(p + (neg_x ? 2 : 5));
-    const uint4 qny = __ldg(p + (neg_y ? 6 : 3)), qfy = __ldg(p + (neg_y ? 3 : 6));
-    const uint4 qnz = __ldg(p + (neg_z ? 7 : 4)), qfz = __ldg(p + (neg_z ? 4 : 7));
+    // near/far plane vectors by direction sign (words 0..3 = lower planes, 4..7 = upper planes of the 8 slots)
+#define LCB_NEAR(V, NEG) make_uint4(NEG ? V.v[4] : V.v[0], NEG ? V.v[5] : V.v[1], NEG ? V.v[6] : V.v[2], NEG ? V.v[7] : V.v[3])
+#define LCB_FAR(V, NEG) make_uint4(NEG ? V.v[0] : V.v[4], NEG ? V.v[1] : V.v[5], NEG ? V.v[2] : V.v[6], NEG ? V.v[3] : V.v[7])
+    const uint4 qnx = LCB_NEAR(X, neg_x), qfx = LCB_FAR(X, neg_x);
+    const uint4 qny = LCB_NEAR(Y, neg_y), qfy = LCB_FAR(Y, neg_y);
+    const uint4 qnz = LCB_NEAR(Z, neg_z), qfz = LCB_FAR(Z, neg_z);
+#undef LCB_NEAR
+#undef LCB_FAR
     child_base = n1.x; prim_base = n1.y; imask = n0.w >> 24;
     const float sclx = __uint_as_float((n0.w & 0xffu) << 23), scly = __uint_as_float((n0.w & 0xff00u) << 15), sclz = __uint_as_float((n0.w & 0xff0000u) << 7);
     const float rx = __uint_as_float(n0.x) - r.ox, ry = __uint_as_float(n0.y) - r.oy, rz = __uint_as_float(n0.z) - r.oz;
@@ -223,7 +239,7 @@ struct TraceTune {
 template <bool ANY, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out,
                                                                                unsigned long long count, uint32_t mask, unsigned long long *work_counter,
-                                                                               TraceCounters *ctr, TraceTune tune) {
+                                                                               TraceCounters *ctr, TraceTune tune, const uint32_t *__restrict__ order) {
     __shared__ uint2 s_stack[kSmemStack * kTraceThreads];
     uint2 l_stack[kLocalStack];
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                 if (pool_next != pool_end) {
                     const unsigned long long mine = pool_next + __popc(m_idle & lt_mask);
                     if (!has_ray && mine < pool_end) {
-                        ray_idx = mine;
+                        ray_idx = order ? (unsigned long long)__ldg(order + mine) : mine;
                         const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
                         setup_world(r, ra, rb);
                         tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
@@ -311,7 +327,10 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                 Gt.y &= Gt.y - 1;
                 if (cur_inst != kNone) {
                     const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
-                    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                    const U8 t01 = ldg256(tp);
+                    const float4 v2 = __ldg(tp + 2);
+                    const float4 v0 = make_float4(__uint_as_float(t01.v[0]), __uint_as_float(t01.v[1]), __uint_as_float(t01.v[2]), __uint_as_float(t01.v[3]));
+                    const float4 v1 = make_float4(__uint_as_float(t01.v[4]), __uint_as_float(t01.v[5]), __uint_as_float(t01.v[6]), 0.f);
                     if (COUNTERS) n_tris++;
                     float t, V, W, det;
                     if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, V, W, det)) {
@@ -417,6 +436,59 @@ __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__r
     hits[3 * i + 2] = make_uint2(h2.x, 0u);
 }
 
+// ---- ray reordering ---------------------------------------------------------------------------------------------------
+// Incoherent batches are traced in the order of a (origin cell, direction bin) key so that the lanes of a warp walk
+// the same part of the tree: k_ray_keys builds the keys, the builder's onesweep sort orders them, k_trace fetches
+// ray indices through the sorted permutation.  Results are written by original index and do not depend on the
+// order (the arithmetic per ray is fixed), so this is purely a scheduling decision.
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 10 bits -> every third bit
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_ray_keys(const float4 *__restrict__ rays, uint32_t count, float3 lo, float3 inv_ext, int origin_bits, int dir_bits,
+                                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
+    const float cells = (float)(1u << origin_bits), bins = (float)(1u << dir_bits);
+    const uint32_t cmax = (1u << origin_bits) - 1u, bmax = (1u << dir_bits) - 1u;
+    // NaN-safe clamps (fminf/fmaxf return the non-NaN operand)
+    const uint32_t ox = min((uint32_t)fminf(fmaxf((a.x - lo.x) * inv_ext.x * cells, 0.f), 1023.f), cmax);
+    const uint32_t oy = min((uint32_t)fminf(fmaxf((a.y - lo.y) * inv_ext.y * cells, 0.f), 1023.f), cmax);
+    const uint32_t oz = min((uint32_t)fminf(fmaxf((a.z - lo.z) * inv_ext.z * cells, 0.f), 1023.f), cmax);
+    const float m = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fabsf(b.z));
+    const float s = m > 0.f ? 0.5f / m : 0.f;
+    const uint32_t dx = min((uint32_t)fminf(fmaxf((b.x * s + 0.5f) * bins, 0.f), 1023.f), bmax);
+    const uint32_t dy = min((uint32_t)fminf(fmaxf((b.y * s + 0.5f) * bins, 0.f), 1023.f), bmax);
+    const uint32_t dz = min((uint32_t)fminf(fmaxf((b.z * s + 0.5f) * bins, 0.f), 1023.f), bmax);
+    const uint32_t okey = spread3(ox) | (spread3(oy) << 1) | (spread3(oz) << 2);
+    const uint32_t dkey = spread3(dx) | (spread3(dy) << 1) | (spread3(dz) << 2);
+    // direction octant (the top Morton digit of the direction) leads, then the origin cell, then the finer direction bits
+    const uint32_t dlow_bits = 3 * (dir_bits - 1);
+    const uint32_t octant = dkey >> dlow_bits, dlow = dkey & ((1u << dlow_bits) - 1u);
+    keys[i] = ((uint64_t)octant << (3 * origin_bits + dlow_bits)) | ((uint64_t)okey << dlow_bits) | dlow;
+    vals[i] = i;
+}
+
+struct RaySortConfig { int enabled; unsigned long long min_count; int origin_bits, dir_bits; };
+RaySortConfig ray_sort_config() {
+    static RaySortConfig c = [] {
+        RaySortConfig d{0, 1ull << 18, 5, 3};  // off by default: no gain on uniformly incoherent batches (profiles/r01_ray_sort_sweep.txt)
+        if (const char *e = getenv("LC_B200_RAY_SORT")) sscanf(e, "%d,%llu,%d,%d", &d.enabled, &d.min_count, &d.origin_bits, &d.dir_bits);
+        if (d.origin_bits < 1) d.origin_bits = 1;
+        if (d.origin_bits > 10) d.origin_bits = 10;
+        if (d.dir_bits < 1) d.dir_bits = 1;
+        if (d.dir_bits > 6) d.dir_bits = 6;
+        return d;
+    }();
+    return c;
+}
+
 TraceTune trace_tune() {
     static TraceTune t = [] {
         TraceTune d{6};
@@ -425,6 +497,8 @@ TraceTune trace_tune() {
     }();
     return t;
 }
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <bool ANY, bool COUNTERS>
 void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uint64_t count, uint32_t mask, unsigned long long *work_counter,
@@ -436,13 +510,39 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<ANY, COUNTERS>, kTraceThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
     unsigned long long want = (count + kTraceThreads - 1) / kTraceThreads;
     unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid == 0) return;
-    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, trace_tune());
+    // ray reordering for large batches
+    const RaySortConfig rs = ray_sort_config();
+    const uint32_t *order = nullptr;
+    void *scratch = nullptr;
+    if (rs.enabled && a.tlas_nodes && count >= rs.min_count && count < (1ull << 31)) {
+        const uint32_t n = (uint32_t)count;
+        const int key_bits = 3 * rs.origin_bits + 3 * rs.dir_bits, passes = (key_bits + 7) / 8;
+        const size_t kb = align256((size_t)n * 8), vb = align256((size_t)n * 4), sb = align256(sort_scratch_bytes(n, passes));
+        if (cudaMallocAsync(&scratch, 2 * kb + 2 * vb + sb, s) == cudaSuccess) {
+            uint8_t *p = (uint8_t *)scratch;
+            uint64_t *keys = (uint64_t *)p, *keys_alt = (uint64_t *)(p + kb);
+            uint32_t *vals = (uint32_t *)(p + 2 * kb), *vals_alt = (uint32_t *)(p + 2 * kb + vb);
+            float3 lo = make_float3(a.world_lo[0], a.world_lo[1], a.world_lo[2]), inv;
+            inv.x = a.world_hi[0] > a.world_lo[0] ? 1.f / (a.world_hi[0] - a.world_lo[0]) : 0.f;
+            inv.y = a.world_hi[1] > a.world_lo[1] ? 1.f / (a.world_hi[1] - a.world_lo[1]) : 0.f;
+            inv.z = a.world_hi[2] > a.world_lo[2] ? 1.f / (a.world_hi[2] - a.world_lo[2]) : 0.f;
+            k_ray_keys<<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4 *>(rays), n, lo, inv, rs.origin_bits, rs.dir_bits, keys, vals);
+            lc.count++;
+            const bool in_alt = sort_pairs(s, n, keys, vals, keys_alt, vals_alt, p + 2 * kb + 2 * vb, 0, passes, lc);
+            order = in_alt ? vals_alt : vals;
+        } else {
+            (void)cudaGetLastError();  // no memory for the permutation: trace in submission order
+            scratch = nullptr;
+        }
+    }
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
+    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, trace_tune(), order);
     lc.count++;
+    if (scratch) cudaFreeAsync(scratch, s);
     if (!ANY) {
         k_refine<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), reinterpret_cast<uint2 *>(out), count);
         lc.count++;
