@@ -461,6 +461,101 @@ void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const In
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
 }
 
+// ---- refit (MeshBuild with PreferUpdate on an updatable mesh; GeometryImpl::build_mesh, cpu/accel.rs:251-258) ----
+// Topology, slot assignment and primitive order of the wide tree are kept; packed triangles are re-read from the
+// (aliased) user vertex buffer and every node's frame and quantised child planes are recomputed bottom-up.  Threads
+// start at the nodes without internal children; a node is processed by the last of its internal children to arrive
+// (atomic counter), exactly once.
+__global__ void __launch_bounds__(256) k_refit_parents(const WideNode *__restrict__ nodes, uint32_t n_nodes, uint32_t *parent, uint32_t *counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (i == 0) parent[0] = 0xffffffffu;
+    counters[i] = 0;
+    const uint32_t imask = nodes[i].imask, base = nodes[i].child_base;
+    const uint32_t n_int = __popc(imask);
+    for (uint32_t r = 0; r < n_int; r++) parent[base + r] = i;
+}
+
+__global__ void __launch_bounds__(256) k_refit_reset(uint32_t *counters, uint32_t n_nodes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) counters[i] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_refit(TriangleInput in, WideNode *nodes, PackedTri *tris, uint32_t n_nodes, const uint32_t *__restrict__ parent,
+                                               float *boxes, uint32_t *counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (nodes[i].imask != 0) return;  // reached later through its children
+    while (true) {
+        WideNode node = nodes[i];
+        float clo[8][3], chi[8][3];
+        float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        uint32_t int_rank = 0;
+        for (int s = 0; s < 8; s++) {
+            const uint32_t meta = node.meta[s];
+            if (meta == 0) continue;
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            if (node.imask >> s & 1) {
+                const float *b = boxes + 6 * (size_t)(node.child_base + int_rank);
+                for (int k = 0; k < 3; k++) { lo[k] = __ldcg(b + k); hi[k] = __ldcg(b + 3 + k); }
+                int_rank++;
+            } else {
+                const uint32_t count = __popc(meta >> 5), first = node.prim_base + (meta & 31u);
+                for (uint32_t q = 0; q < count; q++) {
+                    PackedTri &pt = tris[first + q];
+                    const uint32_t prim = pt.prim;
+                    float a[3], b[3], c[3];
+                    load_triangle(in, prim, a, b, c);
+                    float4 *o = reinterpret_cast<float4 *>(&pt);
+                    o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
+                    o[1] = make_float4(b[0], b[1], b[2], 0.f);
+                    o[2] = make_float4(c[0], c[1], c[2], 0.f);
+                    for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], fmin3(a[k], b[k], c[k])); hi[k] = fmaxf(hi[k], fmax3(a[k], b[k], c[k])); }
+                }
+            }
+            for (int k = 0; k < 3; k++) { clo[s][k] = lo[k]; chi[s][k] = hi[k]; nlo[k] = fminf(nlo[k], lo[k]); nhi[k] = fmaxf(nhi[k], hi[k]); }
+        }
+        float inv_scale[3];
+        for (int k = 0; k < 3; k++) {
+            float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
+            uint32_t bits = __float_as_uint(sc);
+            uint32_t ex = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+            ex = max(ex, 1u); ex = min(ex, 253u);
+            node.e[k] = (uint8_t)ex; node.org[k] = nlo[k];
+            inv_scale[k] = __uint_as_float((254u - ex) << 23);
+        }
+        for (int s = 0; s < 8; s++) {
+            if (node.meta[s] == 0) continue;
+            for (int k = 0; k < 3; k++) quantise_axis(clo[s][k], chi[s][k], nlo[k], inv_scale[k], node.q[k][0][s], node.q[k][1][s]);
+        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(&node);
+        uint4 *dst = reinterpret_cast<uint4 *>(&nodes[i]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) dst[q] = src[q];
+        float *b = boxes + 6 * (size_t)i;
+        for (int k = 0; k < 3; k++) { __stcg(b + k, nlo[k]); __stcg(b + 3 + k, nhi[k]); }
+        const uint32_t p = parent[i];
+        if (p == 0xffffffffu) return;
+        __threadfence();
+        const uint32_t arrived = atomicAdd(&counters[p], 1u) + 1u;
+        if (arrived != (uint32_t)__popc(nodes[p].imask)) return;
+        __threadfence();
+        i = p;
+    }
+}
+
+void build_refit_arrays(cudaStream_t s, uint32_t n_nodes, const WideNode *nodes, const RefitArrays &ra, LaunchCounter &lc) {
+    if (!n_nodes) return;
+    k_refit_parents<<<(n_nodes + 255) / 256, 256, 0, s>>>(nodes, n_nodes, ra.parent, ra.counters); lc.count++;
+}
+
+void refit_blas(cudaStream_t s, uint32_t n_nodes, uint32_t n_tris, const TriangleInput &in, WideNode *nodes, PackedTri *tris, const RefitArrays &ra,
+                BuildHeader *, LaunchCounter &lc) {
+    if (!n_nodes || !n_tris) return;
+    k_refit_reset<<<(n_nodes + 255) / 256, 256, 0, s>>>(ra.counters, n_nodes); lc.count++;
+    k_refit<<<(n_nodes + 127) / 128, 128, 0, s>>>(in, nodes, tris, n_nodes, ra.parent, ra.boxes, ra.counters); lc.count++;
+}
+
 // ---- instance table scatter ----------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_apply_instance_mods(InstanceRec *table, const InstanceModRec *mods, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -128,6 +128,7 @@ struct MeshObj {
     uint64_t generation = 0;  // bumped whenever nodes/tris are re-allocated
     WideNode *nodes = nullptr; PackedTri *tris = nullptr;
     uint32_t n_nodes = 0, n_packed = 0, node_capacity = 0;
+    RefitArrays refit{nullptr, nullptr, nullptr};  // side arrays of the refit path, allocated at the first PreferUpdate
     lcb_build_stats stats{};
     std::mutex mu;
 };
@@ -278,12 +279,32 @@ void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     if (c.index_buffer_offset + c.index_buffer_size > ib->size) fatal("MeshBuild: index range exceeds buffer");
     const uint32_t n = (uint32_t)(c.index_buffer_size / c.index_stride);
     TriangleInput in{vb->ptr + c.vertex_buffer_offset, c.vertex_stride, ib->ptr + c.index_buffer_offset};
-    // PreferUpdate on a built mesh is a vertex-update refit in the reference (accel.rs:251-257); until the
-    // refit kernels land we rebuild, which yields the same traversal results.
     cudaStream_t st = s->stream;
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, st));
+    // PreferUpdate on a built, updatable mesh is a vertex-update refit (accel.rs:251-257; the OptiX backend's rule —
+    // rebuild when updates are not allowed, the mesh was never built or its size changed — is cuda_mesh.cpp:42-68).
+    // The BVH aliases the user buffers like Embree's shared geometry buffers (accel.rs:217-237): vertices are re-read now.
+    if (c.request == LCB_REQUEST_PREFER_UPDATE && m->built && m->option.allow_update && n == m->n_tris && n > 0 && m->nodes) {
+        if (!m->refit.parent) {
+            CUDA_CHECK(cudaMallocAsync((void **)&m->refit.parent, (size_t)m->n_nodes * 4, st));
+            CUDA_CHECK(cudaMallocAsync((void **)&m->refit.boxes, (size_t)m->n_nodes * 24, st));
+            CUDA_CHECK(cudaMallocAsync((void **)&m->refit.counters, (size_t)m->n_nodes * 4, st));
+            build_refit_arrays(st, m->n_nodes, m->nodes, m->refit, d->lc);
+        }
+        refit_blas(st, m->n_nodes, n, in, m->nodes, m->tris, m->refit, nullptr, d->lc);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        m->stats.was_refit = 1; m->stats.build_ms = ms;
+        return;
+    }
+    if (m->refit.parent) {
+        CUDA_CHECK(cudaFreeAsync(m->refit.parent, st)); CUDA_CHECK(cudaFreeAsync(m->refit.boxes, st)); CUDA_CHECK(cudaFreeAsync(m->refit.counters, st));
+        m->refit = RefitArrays{nullptr, nullptr, nullptr};
+    }
     if (m->nodes) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
     if (m->tris) { CUDA_CHECK(cudaFreeAsync(m->tris, st)); m->tris = nullptr; }
     m->built = true; m->n_tris = n; m->generation++;
@@ -548,6 +569,7 @@ void destroy_mesh(lcb_device dev, lcb_mesh h) {
     MeshObj *m = as<MeshObj>(h.id);
     if (m->nodes) cudaFree(m->nodes);
     if (m->tris) cudaFree(m->tris);
+    if (m->refit.parent) { cudaFree(m->refit.parent); cudaFree(m->refit.boxes); cudaFree(m->refit.counters); }
     delete m;
 }
 lcb_created create_accel(lcb_device dev, const lcb_accel_option *opt) { bind(dev_of(dev)); auto *a = new AccelObj; if (opt) a->option = *opt; return lcb_created{(uint64_t)a, a}; }

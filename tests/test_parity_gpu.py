@@ -259,6 +259,49 @@ def test_rebuild_after_vertex_update_and_accel_modifications(device):
     accel.destroy(); mesh.destroy(); vb.destroy(); ib.destroy(); o.close()
 
 
+def test_prefer_update_refit_terrain_frames(device):
+    """C4-shaped: a height field animated over frames; MeshBuild(PreferUpdate) on an updatable mesh refits in place
+    (stats.was_refit), a non-updatable mesh rebuilds; both must give the oracle's hits for the CURRENT vertices."""
+    nx = 120
+    verts, tris = scenes.terrain(nx)
+    rng = np.random.default_rng(77)
+    n = 60000
+    o = np.stack([rng.random(n, dtype=np.float32), np.full(n, 0.5, np.float32), rng.random(n, dtype=np.float32)], 1)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d[:, 1] = -np.abs(d[:, 1]) - 0.2
+    rays = scenes.make_rays(o, d, 0.0, 10.0)
+    ora = ol.OracleScene()
+    ov = verts.copy()
+    om = ora.add_mesh(ov, tris)
+    ora.update(1, [dict(index=0, flags=1 | 2 | 4 | 16 | 32, visibility=0xFF, mesh=om)])
+    objs = []
+    for allow in (True, False):
+        vb = device.create_buffer_from_array(verts); ib = device.create_buffer_from_array(tris)
+        mesh = device.create_mesh(vb.view(), ib.view(), lc.AccelOption(allow_update=allow))
+        mesh.build()
+        accel = device.create_accel(); accel.push_mesh(mesh); accel.build()
+        objs.append((vb, ib, mesh, accel))
+    for frame in range(1, 5):
+        fv, _ = scenes.terrain(nx, frame=frame * 7)
+        if frame == 3:
+            fv = fv.copy(); fv[:, 1] += np.float32(0.3)      # large displacement: boxes must follow, not just grow
+        ov[:] = fv; ora.commit_mesh(om)
+        want = ora.trace_closest(rays)
+        for (vb, ib, mesh, accel), allow in zip(objs, (True, False)):
+            vb.view().copy_from(fv)
+            mesh.build(lc.AccelBuildRequest.PREFER_UPDATE); accel.build(lc.AccelBuildRequest.PREFER_UPDATE)
+            assert mesh.stats()["was_refit"] == (1 if allow else 0)
+            assert_hits_equal(accel.intersect_host(rays), want, f"frame {frame} allow_update={allow}")
+            assert np.array_equal(accel.intersect_any_host(rays), ora.trace_any(rays))
+    # a ForceBuild after refits starts from scratch again
+    vb, ib, mesh, accel = objs[0]
+    mesh.build(lc.AccelBuildRequest.FORCE_BUILD); accel.build()
+    assert mesh.stats()["was_refit"] == 0
+    assert_hits_equal(accel.intersect_host(rays), ora.trace_closest(rays), "rebuild after refits")
+    for vb, ib, mesh, accel in objs:
+        accel.destroy(); mesh.destroy(); vb.destroy(); ib.destroy()
+    ora.close()
+
+
 def test_stream_ordering_events_and_callbacks(device):
     s1, s2 = device.create_stream(), device.create_stream()
     a = device.create_buffer(1 << 16, 4); b = device.create_buffer(1 << 16, 4)
