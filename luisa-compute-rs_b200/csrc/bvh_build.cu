@@ -1,4 +1,4 @@
-// bvh_build.cu — LBVH builder for sm_100a: primitive boxes + centroid bounds, 63-bit Morton
+// bvh_build.cu — LBVH builder for sm_100a: primitive boxes + centroid bounds, 48-bit Morton
 // codes, onesweep sort (radix_sort.cu), fused bottom-up hierarchy emission + AABB refit with
 // atomic arrival flags (after Apetrei 2014), and collapse of the binary tree into 8-wide
 // 128-byte quantised nodes with packed 64-byte leaf triangles.
@@ -13,19 +13,17 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr unsigned long long kEmptyItem = ~0ull;
 constexpr int kLeafMax = 3;  // primitives per leaf child (unary count in 3 bits)
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
 
-__global__ void k_init_header(BuildHeader *h, unsigned long long *queue, uint32_t n_queue, int *flags, uint32_t n_flags) {
+__global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
-        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->ticket = 0; h->max_depth = 0; h->error = 0;
+        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->bar_count = 0; h->bar_release = 0; h->max_depth = 0; h->error = 0;
     }
-    for (uint32_t j = i; j < n_queue; j += gridDim.x * blockDim.x) queue[j] = kEmptyItem;
     for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
 }
 
@@ -162,7 +160,8 @@ __global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxe
         t = fminf(fmaxf(t, 0.f), 1.f);
         q[k] = min((uint32_t)(t * 2097152.0f), 2097151u);
     }
-    keys[i] = expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2);
+    // the top 48 bits of the 63-bit code (16 bits per axis): six 8-bit sort passes; equal keys are split by position
+    keys[i] = (expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2)) >> 15;
     vals[i] = i;
 }
 
@@ -201,8 +200,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
             __threadfence();
             int other = atomicExch(&flags[parent], (int)left);
             if (other == -1) return;
-            __threadfence();
-            right = (uint32_t)other;
+            right = (uint32_t)other;  // the sibling fenced before its exchange; its box is read at L2 (__ldcg) below
             slo = __ldcg(pn + 2); shi = __ldcg(pn + 3);
         } else {  // right child of internal node `left - 1`
             parent = left - 1;
@@ -212,7 +210,6 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
             __threadfence();
             int other = atomicExch(&flags[parent], (int)right);
             if (other == -1) return;
-            __threadfence();
             left = (uint32_t)other;
             slo = __ldcg(pn); shi = __ldcg(pn + 1);
         }
@@ -252,16 +249,12 @@ __device__ __forceinline__ void split_child(const BinNode *__restrict__ bin, con
     r.first = c.id + 1;
 }
 
+// The collapse only records which primitive lands in which packed slot; k_pack_tris then gathers the vertices of
+// all slots at once (one thread per slot: the index -> vertex gather is a chain of dependent DRAM reads that must not
+// sit on the collapse's per-node critical path).
 struct LeafSinkTriangles {
-    TriangleInput in; PackedTri *tris;
-    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const {
-        float a[3], b[3], c[3];
-        load_triangle(in, prim, a, b, c);
-        float4 *o = reinterpret_cast<float4 *>(&tris[dst]);
-        o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
-        o[1] = make_float4(b[0], b[1], b[2], 0.f);
-        o[2] = make_float4(c[0], c[1], c[2], 0.f);
-    }
+    PackedTri *tris;
+    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const { tris[dst].prim = prim; }
 };
 struct LeafSinkInstances {
     const uint32_t *active; uint32_t *prim_ids;
@@ -277,147 +270,245 @@ __device__ __forceinline__ void quantise_axis(float clo, float chi, float org, f
     qlo = (uint16_t)l; qhi = (uint16_t)u;
 }
 
+// One 8-lane group per wide node, lane j holding child j in registers: the split search, the node frame, the greedy
+// octant slot assignment and the quantisation are 3-step shuffle reductions inside the group instead of serial loops
+// over local-memory arrays; the finished node is assembled in shared memory and leaves as one coalesced 128-byte
+// store.  The kernel is launched cooperatively (all CTAs co-resident) and walks the wide tree level by level: the
+// nodes of a level are a contiguous id range handed out CTA-strided, children and leaf slots are allocated with ONE
+// 64-bit atomic per CTA and step (same-address atomics serialise at L2: one per node was the bottleneck), and a grid
+// barrier whose last arriver snapshots node_count separates the levels — no polling.
+constexpr int kCollapseThreads = 256;
+constexpr int kCollapseGroups = kCollapseThreads / 8;
+
 template <class Sink>
-__global__ void __launch_bounds__(64) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
-                                                 unsigned long long *queue, WideNode *nodes, uint32_t capacity, Sink sink) {
-    while (true) {
-        const uint32_t t = atomicAdd(&h->ticket, 1u);
-        if (t >= capacity) return;
-        unsigned long long item;
-        while (true) {
-            item = *reinterpret_cast<volatile unsigned long long *>(queue + t);
-            if (item != kEmptyItem) break;
-            if (*reinterpret_cast<volatile uint32_t *>(&h->emitted) >= n) return;
-            if (*reinterpret_cast<volatile uint32_t *>(&h->error) != 0) return;
-            __nanosleep(100);
-        }
-        const uint32_t bnode = (uint32_t)item, depth = (uint32_t)(item >> 32);
-        Child c[8];
-        int nc;
-        if (bnode & kLeafBit) {  // single-primitive tree
-            nc = 1;
-            for (int k = 0; k < 3; k++) { c[0].lo[k] = h->root_lo[k]; c[0].hi[k] = h->root_hi[k]; }
-            c[0].id = bnode; c[0].count = 1; c[0].first = bnode & ~kLeafBit;
-        } else {
-            Child self; self.id = bnode;
-            split_child(bin, self, c[0], c[1]);
-            nc = 2;
-        }
-        // phase 1: open the largest subtree that cannot be a leaf; phase 2: use spare slots to
-        // split multi-primitive leaves (tighter boxes at no traversal cost: all 8 slots are tested anyway)
-        for (int phase = 0; phase < 2; phase++) {
-            const uint32_t limit = phase == 0 ? (uint32_t)kLeafMax : 1u;
-            while (nc < 8) {
-                int best = -1; float best_area = -1.f;
-                for (int j = 0; j < nc; j++) {
-                    if (c[j].count > limit) { float a = half_area(c[j]); if (a > best_area) { best_area = a; best = j; } }
+__global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
+                                                               unsigned long long *queue, WideNode *nodes, uint32_t capacity, Sink sink) {
+    __shared__ WideNode s_node[kCollapseGroups];
+    __shared__ uint32_t s_int[kCollapseGroups], s_prm[kCollapseGroups];
+    __shared__ unsigned long long s_base;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7u, grp = threadIdx.x >> 3;
+    const uint32_t gmask = 0xffu << (lane & 24u);
+    const uint32_t below = gmask & ((1u << lane) - 1u);  // lanes of this group below me
+    WideNode &out = s_node[grp];
+#define GSHFL(V, SRC) __shfl_sync(gmask, V, SRC, 8)
+#define GXOR(V, M) __shfl_xor_sync(gmask, V, M, 8)
+    uint32_t level_begin = 0, level_end = 1;
+    for (uint32_t depth = 0; level_begin < level_end; depth++) {
+      const uint32_t level_n = level_end - level_begin;
+      for (uint32_t base = blockIdx.x * kCollapseGroups; base < level_n; base += gridDim.x * kCollapseGroups) {
+        const bool active = base + grp < level_n;
+        const uint32_t t = level_begin + base + grp;
+        // ================= phase A: choose the (up to) 8 children and their slots =================
+        Child c;  // after phase A: the child of slot `sub`
+        for (int k = 0; k < 3; k++) { c.lo[k] = FLT_MAX; c.hi[k] = -FLT_MAX; }
+        c.id = 0; c.count = 0; c.first = 0;
+        bool occupied = false;
+        float nlo[3] = {0.f, 0.f, 0.f}; uint32_t ex[3] = {1u, 1u, 1u}; float inv_scale[3] = {0.f, 0.f, 0.f};
+        if (active) {
+            const uint32_t bnode = (uint32_t)__ldcg(queue + t);  // written by another CTA in the previous level: read at L2
+            Child mine = c;
+            uint32_t nc;
+            if (bnode & kLeafBit) {  // single-primitive tree
+                nc = 1;
+                if (sub == 0) {
+                    for (int k = 0; k < 3; k++) { mine.lo[k] = h->root_lo[k]; mine.hi[k] = h->root_hi[k]; }
+                    mine.id = bnode; mine.count = 1; mine.first = bnode & ~kLeafBit;
                 }
-                if (best < 0) break;
-                Child l, r;
-                split_child(bin, c[best], l, r);
-                c[best] = l; c[nc++] = r;
+            } else {
+                Child self, l, r; self.id = bnode;
+                split_child(bin, self, l, r);
+                nc = 2;
+                if (sub == 0) mine = l; else if (sub == 1) mine = r;
             }
-        }
-        // node frame
-        float nlo[3], nhi[3];
-        for (int k = 0; k < 3; k++) { nlo[k] = c[0].lo[k]; nhi[k] = c[0].hi[k]; }
-        for (int j = 1; j < nc; j++) for (int k = 0; k < 3; k++) { nlo[k] = fminf(nlo[k], c[j].lo[k]); nhi[k] = fmaxf(nhi[k], c[j].hi[k]); }
-        uint8_t e[3]; float inv_scale[3];
-        for (int k = 0; k < 3; k++) {
-            float s = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
-            uint32_t bits = __float_as_uint(s);
-            uint32_t ex = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
-            ex = max(ex, 1u); ex = min(ex, 253u);
-            e[k] = (uint8_t)ex;
-            inv_scale[k] = __uint_as_float((254u - ex) << 23);
-        }
-        // octant slot assignment: slot s is visited first by rays whose direction signs are s
-        // (bit k set = negative along axis k); greedy minimum of dot(child centre - node centre, sign_s)
-        int slot_of[8]; uint32_t slot_used = 0, child_done = 0;
-        {
-            float cx[8], cy[8], cz[8];
-            const float mx = 0.5f * (nlo[0] + nhi[0]), my = 0.5f * (nlo[1] + nhi[1]), mz = 0.5f * (nlo[2] + nhi[2]);
-            for (int j = 0; j < nc; j++) {
-                cx[j] = 0.5f * (c[j].lo[0] + c[j].hi[0]) - mx; cy[j] = 0.5f * (c[j].lo[1] + c[j].hi[1]) - my; cz[j] = 0.5f * (c[j].lo[2] + c[j].hi[2]) - mz;
+            // phase 0: open the largest subtree that cannot be a leaf; phase 1: use spare slots to split multi-primitive
+            // leaves (tighter boxes at no traversal cost: all 8 slots are tested anyway)
+            for (int phase = 0; phase < 2; phase++) {
+                const uint32_t limit = phase == 0 ? (uint32_t)kLeafMax : 1u;
+                while (nc < 8) {
+                    float a = (sub < nc && mine.count > limit) ? half_area(mine) : -1.f;
+                    uint32_t who = sub;
+#pragma unroll
+                    for (int m = 1; m < 8; m <<= 1) {  // argmax, ties -> lowest lane
+                        const float oa = GXOR(a, m); const uint32_t ow = GXOR(who, m);
+                        if (oa > a || (oa == a && ow < who)) { a = oa; who = ow; }
+                    }
+                    if (a < 0.f) break;
+                    Child p, l, r;
+                    p.id = GSHFL(mine.id, who);
+                    split_child(bin, p, l, r);
+                    if (sub == who) mine = l; else if (sub == nc) mine = r;
+                    nc++;
+                }
             }
-            for (int it = 0; it < nc; it++) {
-                float best = FLT_MAX; int bj = -1, bs = -1;
-                for (int j = 0; j < nc; j++) {
-                    if (child_done >> j & 1) continue;
-                    for (int s = 0; s < 8; s++) {
-                        if (slot_used >> s & 1) continue;
-                        float cost = ((s & 1) ? -cx[j] : cx[j]) + ((s & 2) ? -cy[j] : cy[j]) + ((s & 4) ? -cz[j] : cz[j]);
-                        if (cost < best) { best = cost; bj = j; bs = s; }
+            const bool valid = sub < nc;
+            // ---- node frame ----
+            float nhi[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                nlo[k] = mine.lo[k]; nhi[k] = mine.hi[k];  // invalid lanes hold (+max, -max)
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1) { nlo[k] = fminf(nlo[k], GXOR(nlo[k], m)); nhi[k] = fmaxf(nhi[k], GXOR(nhi[k], m)); }
+                const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
+                const uint32_t bits = __float_as_uint(sc);
+                uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+                e = max(e, 1u); e = min(e, 253u);
+                ex[k] = e;
+                inv_scale[k] = __uint_as_float((254u - e) << 23);
+            }
+            // ---- octant slot assignment: slot s is visited first by rays whose direction signs are s (bit k set =
+            // negative along axis k); greedy global minimum of dot(child centre - node centre, sign_s), ties -> lowest
+            // child, then lowest slot ----
+            const float cx = 0.5f * (mine.lo[0] + mine.hi[0]) - 0.5f * (nlo[0] + nhi[0]);
+            const float cy = 0.5f * (mine.lo[1] + mine.hi[1]) - 0.5f * (nlo[1] + nhi[1]);
+            const float cz = 0.5f * (mine.lo[2] + mine.hi[2]) - 0.5f * (nlo[2] + nhi[2]);
+            uint32_t slot_used = 0, my_slot = 8;
+            for (uint32_t it = 0; it < nc; it++) {
+                float best = FLT_MAX; uint32_t bs = 8;
+                if (valid && my_slot == 8) {
+#pragma unroll
+                    for (uint32_t sl = 0; sl < 8; sl++) {
+                        if (slot_used >> sl & 1u) continue;
+                        const float cost = ((sl & 1) ? -cx : cx) + ((sl & 2) ? -cy : cy) + ((sl & 4) ? -cz : cz);
+                        if (cost < best) { best = cost; bs = sl; }
                     }
                 }
-                if (bj < 0) {  // only NaN costs left: place in the first free slot
-                    for (int j = 0; j < nc && bj < 0; j++) if (!(child_done >> j & 1)) bj = j;
-                    bs = __ffs(~slot_used & 0xff) - 1;
-                }
-                slot_of[bj] = bs; slot_used |= 1u << bs; child_done |= 1u << bj;
-            }
-        }
-        int child_in_slot[8];
-        for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
-        for (int j = 0; j < nc; j++) child_in_slot[slot_of[j]] = j;
-        uint32_t n_internal = 0, n_prims = 0;
-        for (int j = 0; j < nc; j++) { if (c[j].count > (uint32_t)kLeafMax) n_internal++; else n_prims += c[j].count; }
-        const uint32_t child_base = n_internal ? atomicAdd(&h->node_count, n_internal) : 0u;
-        const uint32_t prim_base = n_prims ? atomicAdd(&h->prim_count, n_prims) : 0u;
-        if (child_base + n_internal > capacity || depth + 1 > (uint32_t)kMaxWideDepth) {
-            atomicExch(&h->error, child_base + n_internal > capacity ? 2u : 1u);
-            return;
-        }
-        WideNode node;
-        for (int k = 0; k < 3; k++) { node.org[k] = nlo[k]; node.e[k] = e[k]; }
-        node.child_base = child_base; node.prim_base = prim_base;
-        uint32_t imask = 0, int_rank = 0, prim_off = 0;
-        for (int s = 0; s < 8; s++) {
-            const int j = child_in_slot[s];
-            if (j < 0) {
-                node.meta[s] = 0;
-                for (int k = 0; k < 3; k++) { node.q[k][0][s] = 0xffff; node.q[k][1][s] = 0; }
-                continue;
-            }
-            for (int k = 0; k < 3; k++) quantise_axis(c[j].lo[k], c[j].hi[k], nlo[k], inv_scale[k], node.q[k][0][s], node.q[k][1][s]);
-            if (c[j].count > (uint32_t)kLeafMax) {
-                imask |= 1u << s;
-                node.meta[s] = (uint8_t)(0x20u | (24u + s));
-                *reinterpret_cast<volatile unsigned long long *>(queue + child_base + int_rank) = (unsigned long long)c[j].id | ((unsigned long long)(depth + 1) << 32);
-                int_rank++;
-            } else {
-                const uint32_t unary = (1u << c[j].count) - 1u;
-                node.meta[s] = (uint8_t)((unary << 5) | prim_off);
-                for (uint32_t q = 0; q < c[j].count; q++) sink.emit(prim_base + prim_off + q, prim_sorted[c[j].first + q]);
-                prim_off += c[j].count;
-            }
-        }
-        node.imask = (uint8_t)imask;
-        const uint4 *src = reinterpret_cast<const uint4 *>(&node);
-        uint4 *dst = reinterpret_cast<uint4 *>(&nodes[t]);
+                uint32_t who = (valid && my_slot == 8 && bs != 8) ? sub : 8u;
 #pragma unroll
-        for (int q = 0; q < 8; q++) dst[q] = src[q];
-        atomicMax(&h->max_depth, depth + 1);
-        if (n_prims) { __threadfence(); atomicAdd(&h->emitted, n_prims); }
+                for (int m = 1; m < 8; m <<= 1) {
+                    const float ob = GXOR(best, m); const uint32_t ow = GXOR(who, m), os = GXOR(bs, m);
+                    if (ow != 8u && (who == 8u || ob < best || (ob == best && ow < who))) { best = ob; who = ow; bs = os; }
+                }
+                if (who == 8u) {  // only NaN costs left: lowest unassigned child takes the lowest free slot
+                    who = __ffs(__ballot_sync(gmask, valid && my_slot == 8) >> (lane & 24u)) - 1;
+                    bs = __ffs(~slot_used & 0xffu) - 1;
+                }
+                if (sub == who) my_slot = bs;
+                slot_used |= 1u << bs;
+            }
+            // ---- bring the children into slot order: lane s now holds the child of slot s ----
+            uint32_t src = 8;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) { const uint32_t sj = GSHFL(my_slot, j); if (sj == sub) src = j; }
+            const uint32_t from = src & 7u;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { c.lo[k] = GSHFL(mine.lo[k], from); c.hi[k] = GSHFL(mine.hi[k], from); }
+            c.id = GSHFL(mine.id, from); c.count = GSHFL(mine.count, from); c.first = GSHFL(mine.first, from);
+            occupied = src != 8;
+        }
+        const bool is_int = occupied && c.count > (uint32_t)kLeafMax;
+        const bool is_leaf = occupied && !is_int;
+        const uint32_t int_ballot = __ballot_sync(gmask, is_int);
+        const uint32_t n_internal = __popc(int_ballot), int_rank = __popc(int_ballot & below);
+        uint32_t leaf_count = is_leaf ? c.count : 0u, prim_off = leaf_count;
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) { const uint32_t o = __shfl_up_sync(gmask, prim_off, m, 8); if (sub >= (uint32_t)m) prim_off += o; }
+        const uint32_t n_prims = GSHFL(prim_off, 7);
+        prim_off -= leaf_count;  // exclusive
+        // ================= allocation: one 64-bit atomic per CTA and step =================
+        if (sub == 0) { s_int[grp] = n_internal; s_prm[grp] = n_prims; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t ti = 0, tp = 0;
+            for (int g = 0; g < kCollapseGroups; g++) { const uint32_t a = s_int[g], b = s_prm[g]; s_int[g] = ti; s_prm[g] = tp; ti += a; tp += b; }
+            s_base = (ti | tp) ? atomicAdd(reinterpret_cast<unsigned long long *>(&h->node_count), (unsigned long long)ti | ((unsigned long long)tp << 32)) : 0ull;
+        }
+        __syncthreads();
+        const uint32_t child_base = (uint32_t)s_base + s_int[grp], prim_base = (uint32_t)(s_base >> 32) + s_prm[grp];
+        __syncthreads();  // s_int / s_prm / s_base are rewritten by the next step
+        if (!active) continue;
+        if (child_base + n_internal > capacity || depth + 1 > (uint32_t)kMaxWideDepth) {
+            if (sub == 0) atomicExch(&h->error, child_base + n_internal > capacity ? 2u : 1u);
+            continue;  // every CTA still has to reach the barrier; the level loop ends on the error flag
+        }
+        // ================= phase B: assemble the node in shared memory, store it as one 128-byte line =================
+        if (sub == 0) {
+            for (int k = 0; k < 3; k++) { out.org[k] = nlo[k]; out.e[k] = (uint8_t)ex[k]; }
+            out.imask = (uint8_t)(int_ballot >> (lane & 24u));
+            out.child_base = child_base; out.prim_base = prim_base;
+        }
+        if (!occupied) {
+            out.meta[sub] = 0;
+            for (int k = 0; k < 3; k++) { out.q[k][0][sub] = 0xffff; out.q[k][1][sub] = 0; }
+        } else {
+            for (int k = 0; k < 3; k++) quantise_axis(c.lo[k], c.hi[k], nlo[k], inv_scale[k], out.q[k][0][sub], out.q[k][1][sub]);
+            if (is_int) {
+                out.meta[sub] = (uint8_t)(0x20u | (24u + sub));
+                __stcg(queue + child_base + int_rank, (unsigned long long)c.id);
+            } else {
+                out.meta[sub] = (uint8_t)((((1u << c.count) - 1u) << 5) | prim_off);
+                for (uint32_t q = 0; q < c.count; q++) sink.emit(prim_base + prim_off + q, prim_sorted[c.first + q]);
+            }
+        }
+        __syncwarp(gmask);
+        reinterpret_cast<uint4 *>(&nodes[t])[sub] = reinterpret_cast<const uint4 *>(&out)[sub];
+        __syncwarp(gmask);
+      }
+      // ---- grid barrier; the last CTA to arrive publishes the end of the next level -------------------------------
+      __syncthreads();
+      if (threadIdx.x == 0) {
+          __threadfence();
+          const uint32_t arrived = atomicAdd(&h->bar_count, 1u) + 1u;
+          if (arrived == gridDim.x * (depth + 1)) {
+              const uint32_t err = *reinterpret_cast<volatile uint32_t *>(&h->error);
+              const uint32_t end = *reinterpret_cast<volatile uint32_t *>(&h->node_count);
+              h->level_end[depth + 1] = err ? level_end : end;  // an error ends the walk: the next level is empty
+              h->max_depth = depth + 1;
+              h->emitted = *reinterpret_cast<volatile uint32_t *>(&h->prim_count);
+              __threadfence();
+              atomicExch(&h->bar_release, depth + 1);
+          } else {
+              while (*reinterpret_cast<volatile uint32_t *>(&h->bar_release) < depth + 1) __nanosleep(64);
+          }
+          __threadfence();
+      }
+      __syncthreads();
+      level_begin = level_end;
+      level_end = *reinterpret_cast<volatile uint32_t *>(&h->level_end[depth + 1]);
     }
+#undef GSHFL
+#undef GXOR
 }
 
-__global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) {
-    *reinterpret_cast<volatile unsigned long long *>(queue) = (unsigned long long)h->root;
+// One thread per packed slot: gather the slot's triangle (id recorded by the collapse, or kept from the last build when
+// refitting) through the index buffer and write the 48 used bytes of the record.
+__global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, PackedTri *tris, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t prim = tris[i].prim;
+    float a[3], b[3], c[3];
+    load_triangle(in, prim, a, b, c);
+    float4 *o = reinterpret_cast<float4 *>(&tris[i]);
+    o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
+    o[1] = make_float4(b[0], b[1], b[2], 0.f);
+    o[2] = make_float4(c[0], c[1], c[2], 0.f);
 }
+
+__global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) { queue[0] = (unsigned long long)h->root; }
 
 template <class Sink>
 void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc) {
     k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals); lc.count++;
-    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, 8, lc);
+    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, 6, lc);
     const uint64_t *keys = in_alt ? sc.keys_alt : sc.keys;
     const uint32_t *vals = in_alt ? sc.vals_alt : sc.vals;
     k_hierarchy<<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header); lc.count++;
     // seed the collapse queue with the binary root (device-side, no host round trip)
     k_seed_queue<<<1, 1, 0, s>>>(sc.header, sc.queue); lc.count++;
-    uint32_t blocks = (n + 63) / 64;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_collapse<Sink><<<blocks, 64, 0, s>>>(sc.bin, vals, n, sc.header, sc.queue, nodes, n, sink); lc.count++;
+    // one 8-lane group per wide node of the widest level; cooperative launch: the grid must be co-resident for the barrier
+    static int max_blocks = 0;
+    if (!max_blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse<Sink>, kCollapseThreads, 0);
+        max_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    uint32_t blocks = (n / 6 + kCollapseGroups - 1) / kCollapseGroups + 1;
+    if (blocks > (uint32_t)max_blocks) blocks = (uint32_t)max_blocks;
+    const BinNode *a_bin = sc.bin; const uint32_t *a_vals = vals; uint32_t a_n = n, a_cap = n; BuildHeader *a_h = sc.header;
+    unsigned long long *a_queue = sc.queue; WideNode *a_nodes = nodes; Sink a_sink = sink;
+    void *args[] = {&a_bin, &a_vals, &a_n, &a_h, &a_queue, &a_nodes, &a_cap, &a_sink};
+    cudaLaunchCooperativeKernel((const void *)k_collapse<Sink>, dim3(blocks), dim3(kCollapseThreads), args, 0, s); lc.count++;
 }
 
 }  // namespace
@@ -446,16 +537,17 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
 
 void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.queue, n, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
-    LeafSinkTriangles sink{in, tris};
+    LeafSinkTriangles sink{tris};
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
+    k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
 }
 
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,
                 uint32_t *prim_ids, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.queue, n, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
     LeafSinkInstances sink{active_ids, prim_ids};
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
@@ -481,7 +573,7 @@ __global__ void __launch_bounds__(256) k_refit_reset(uint32_t *counters, uint32_
     if (i < n_nodes) counters[i] = 0;
 }
 
-__global__ void __launch_bounds__(128) k_refit(TriangleInput in, WideNode *nodes, PackedTri *tris, uint32_t n_nodes, const uint32_t *__restrict__ parent,
+__global__ void __launch_bounds__(128) k_refit(WideNode *nodes, const PackedTri *tris, uint32_t n_nodes, const uint32_t *__restrict__ parent,
                                                float *boxes, uint32_t *counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
@@ -502,15 +594,11 @@ __global__ void __launch_bounds__(128) k_refit(TriangleInput in, WideNode *nodes
             } else {
                 const uint32_t count = __popc(meta >> 5), first = node.prim_base + (meta & 31u);
                 for (uint32_t q = 0; q < count; q++) {
-                    PackedTri &pt = tris[first + q];
-                    const uint32_t prim = pt.prim;
-                    float a[3], b[3], c[3];
-                    load_triangle(in, prim, a, b, c);
-                    float4 *o = reinterpret_cast<float4 *>(&pt);
-                    o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
-                    o[1] = make_float4(b[0], b[1], b[2], 0.f);
-                    o[2] = make_float4(c[0], c[1], c[2], 0.f);
-                    for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], fmin3(a[k], b[k], c[k])); hi[k] = fmaxf(hi[k], fmax3(a[k], b[k], c[k])); }
+                    const float4 *pt = reinterpret_cast<const float4 *>(&tris[first + q]);  // refreshed by k_pack_tris just before
+                    const float4 a = pt[0], b = pt[1], c = pt[2];
+                    lo[0] = fminf(lo[0], fmin3(a.x, b.x, c.x)); hi[0] = fmaxf(hi[0], fmax3(a.x, b.x, c.x));
+                    lo[1] = fminf(lo[1], fmin3(a.y, b.y, c.y)); hi[1] = fmaxf(hi[1], fmax3(a.y, b.y, c.y));
+                    lo[2] = fminf(lo[2], fmin3(a.z, b.z, c.z)); hi[2] = fmaxf(hi[2], fmax3(a.z, b.z, c.z));
                 }
             }
             for (int k = 0; k < 3; k++) { clo[s][k] = lo[k]; chi[s][k] = hi[k]; nlo[k] = fminf(nlo[k], lo[k]); nhi[k] = fmaxf(nhi[k], hi[k]); }
@@ -553,7 +641,8 @@ void refit_blas(cudaStream_t s, uint32_t n_nodes, uint32_t n_tris, const Triangl
                 BuildHeader *, LaunchCounter &lc) {
     if (!n_nodes || !n_tris) return;
     k_refit_reset<<<(n_nodes + 255) / 256, 256, 0, s>>>(ra.counters, n_nodes); lc.count++;
-    k_refit<<<(n_nodes + 127) / 128, 128, 0, s>>>(in, nodes, tris, n_nodes, ra.parent, ra.boxes, ra.counters); lc.count++;
+    k_pack_tris<<<(n_tris + 255) / 256, 256, 0, s>>>(in, tris, n_tris); lc.count++;
+    k_refit<<<(n_nodes + 127) / 128, 128, 0, s>>>(nodes, tris, n_nodes, ra.parent, ra.boxes, ra.counters); lc.count++;
 }
 
 // ---- instance table scatter ----------------------------------------------------------------

@@ -148,6 +148,7 @@ struct AccelObj {
     WideNode *tlas_nodes = nullptr; uint32_t *tlas_prims = nullptr; uint32_t *active_ids = nullptr; uint32_t tlas_capacity = 0;
     uint32_t n_active = 0;
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of modification records + active ids (grow-only; every build ends synchronised)
     lcb_build_stats stats{};
     std::mutex mu;
 };
@@ -416,20 +417,24 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         if (in.valid) { r.nodes = in.mesh->nodes; r.tris = in.mesh->tris; in.mesh_generation = in.mesh->generation; }
         recs.push_back(r);
     }
-    std::vector<void *> host_frees;
+    // one pinned staging block: [records | active ids]
+    const size_t rec_bytes = recs.size() * sizeof(InstanceModRec), act_bytes = active.size() * 4;
+    if (rec_bytes + act_bytes > a->h_stage_cap) {
+        if (a->h_stage) cudaFreeHost(a->h_stage);
+        a->h_stage_cap = (rec_bytes + act_bytes) * 2 + 4096;
+        CUDA_CHECK(cudaMallocHost((void **)&a->h_stage, a->h_stage_cap));
+    }
     if (!recs.empty()) {
-        InstanceModRec *h = nullptr, *dv = nullptr;
-        CUDA_CHECK(cudaMallocHost((void **)&h, recs.size() * sizeof(InstanceModRec)));
-        memcpy(h, recs.data(), recs.size() * sizeof(InstanceModRec));
-        CUDA_CHECK(cudaMallocAsync((void **)&dv, recs.size() * sizeof(InstanceModRec), st));
-        CUDA_CHECK(cudaMemcpyAsync(dv, h, recs.size() * sizeof(InstanceModRec), cudaMemcpyHostToDevice, st));
+        InstanceModRec *dv = nullptr;
+        memcpy(a->h_stage, recs.data(), rec_bytes);
+        CUDA_CHECK(cudaMallocAsync((void **)&dv, rec_bytes, st));
+        CUDA_CHECK(cudaMemcpyAsync(dv, a->h_stage, rec_bytes, cudaMemcpyHostToDevice, st));
         apply_instance_mods(st, a->table, dv, (uint32_t)recs.size(), d->lc);
         CUDA_CHECK(cudaFreeAsync(dv, st));
-        host_frees.push_back(h);
     }
     a->stats.primitive_count = n;
     if (c.update_instance_buffer_only) {  // accel.rs:428-430
-        if (!host_frees.empty()) { CUDA_CHECK(cudaStreamSynchronize(st)); for (void *h : host_frees) cudaFreeHost(h); }
+        CUDA_CHECK(cudaStreamSynchronize(st));  // the staging block is reused by the next build
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return;
     }
@@ -445,11 +450,8 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         a->tlas_capacity = cap;
     }
     if (na) {
-        uint32_t *h = nullptr;
-        CUDA_CHECK(cudaMallocHost((void **)&h, (size_t)na * 4));
-        memcpy(h, active.data(), (size_t)na * 4);
-        CUDA_CHECK(cudaMemcpyAsync(a->active_ids, h, (size_t)na * 4, cudaMemcpyHostToDevice, st));
-        host_frees.push_back(h);
+        memcpy(a->h_stage + rec_bytes, active.data(), act_bytes);
+        CUDA_CHECK(cudaMemcpyAsync(a->active_ids, a->h_stage + rec_bytes, act_bytes, cudaMemcpyHostToDevice, st));
         BuildScratch layout = build_scratch_layout(nullptr, na);
         void *scratch = nullptr;
         CUDA_CHECK(cudaMallocAsync(&scratch, layout.total_bytes, st));
@@ -470,7 +472,6 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         a->stats.wide_node_count = 0; a->stats.packed_tri_count = 0; a->stats.max_depth = 0; a->stats.bvh_bytes = 0;
     }
-    for (void *h : host_frees) cudaFreeHost(h);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     a->stats.build_ms = ms; a->stats.was_refit = 0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -578,6 +579,7 @@ void destroy_accel(lcb_device dev, lcb_accel h) {
     AccelObj *a = as<AccelObj>(h.id);
     if (a->table) cudaFree(a->table);
     if (a->tlas_nodes) { cudaFree(a->tlas_nodes); cudaFree(a->tlas_prims); cudaFree(a->active_ids); }
+    if (a->h_stage) cudaFreeHost(a->h_stage);
     delete a;
 }
 

@@ -8,6 +8,7 @@
 //   PackedTri    64 B,  64-byte aligned : LDG.256 (v0|prim, v1) + LDG.128 (v2); 16 B spare
 //   InstanceRec 128 B,  16-byte aligned : eight float4
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -72,16 +73,18 @@ struct BuildHeader {
     int bounds_lo[3];   // ordered-int encoded float min of centroids
     int bounds_hi[3];
     uint32_t root;          // binary root id
-    uint32_t node_count;    // wide nodes allocated
-    uint32_t prim_count;    // packed prims allocated
-    uint32_t emitted;       // primitives emitted into leaves
-    uint32_t ticket;        // collapse work tickets
+    uint32_t emitted;       // primitives emitted into leaves (= prim_count after a complete collapse)
+    uint32_t node_count;    // wide nodes allocated   } one 8-byte aligned pair: the collapse allocates both
+    uint32_t prim_count;    // packed prims allocated } with a single 64-bit atomic per CTA and step
+    uint32_t bar_count;     // collapse: grid barrier arrivals
     uint32_t max_depth;
     uint32_t error;         // nonzero: builder failure code
-    uint32_t pad[3];
+    uint32_t bar_release;   // collapse: last released level
     float root_lo[3]; float pad1;
     float root_hi[3]; float pad2;
+    uint32_t level_end[48]; // collapse: node_count snapshot taken by the last arriver of each level's barrier
 };
+static_assert(offsetof(BuildHeader, node_count) % 8 == 0, "node_count/prim_count must form an aligned 64-bit word");
 
 constexpr int kMaxWideDepth = 40;   // builder fails loudly beyond this; traversal stack is sized for it
 constexpr int kTraversalStack = 96; // >= TLAS depth + 3 + BLAS depth

@@ -1,0 +1,3 @@
+#!/bin/bash
+timeout 600 python bench.py > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; echo "bench rc=$?"; cat gpurun_out/bench_b.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c4.csv python tools/scene_bench.py --config c4 --frames 1 > gpurun_out/ncu_c4.log 2>&1; echo "ncu rc=$?"
