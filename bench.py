@@ -43,7 +43,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons (B200_PROFILING.md recipe).  Started before the warm-up (nvidia-smi takes a few
+    hundred ms to deliver its first row) and polled every 20 ms; `stop(t0, t1)` summarises the rows whose arrival time
+    falls inside the timed region [t0, t1] (host clock), falling back to the rows since warm-up began if the region was
+    shorter than one polling interval."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -54,8 +57,8 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -63,20 +66,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in self.rows if t >= t0 - 1.0]
+            window = "warm-up + timed region (timed region shorter than one polling interval)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(names, r[3:7]):
@@ -84,7 +97,8 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def cpu_leg(n_sample, threads=0, repeats=1):
@@ -110,7 +124,7 @@ def run_reference(args, rank):
         return
     import oracle_lib as ol
     cores = ol.lib().oracle_hw_threads()
-    n_sample = 1 << 20
+    n_sample = 1 << 22
     import scenes
     desc = scenes.c3_soup(N_TRIS)
     o = ol.scene_from_desc(desc)
@@ -135,7 +149,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tris", type=int, default=N_TRIS)
@@ -177,8 +191,11 @@ def main():
     mstats = mesh.stats()
     accel = dev.create_accel()
     accel.push_mesh(mesh)
-    accel.build()
-    tlas_ms = accel.stats()["build_ms"]
+    tlas_all = []
+    for _ in range(3):
+        accel.build()
+        tlas_all.append(accel.stats()["build_ms"])
+    tlas_ms = min(tlas_all)
 
     # ---- rays: resident in HBM before the timed region -------------------------------------------------------------
     n = args.rays
@@ -197,13 +214,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
     for _ in range(warmup):
         accel.intersect(rb, hb, n, 0xFF, stream)
     stream.synchronize()
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t_region0 = time.perf_counter()
     launches0 = lib.lc_b200_kernel_launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(ext)
@@ -212,8 +231,9 @@ def main():
         evs[k + 1].record(ext)
     stream.synchronize()
     barrier()
+    t_region1 = time.perf_counter()
     launches = lib.lc_b200_kernel_launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     total_ms = float(sum(step_ms))
     if world > 1:
@@ -305,7 +325,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu and not args.profile:
         import oracle_lib as ol
         cores = ol.lib().oracle_hw_threads()
-        n_sample = 1 << 20
+        n_sample = min(n, 1 << 24)   # ~7 s on 16 cores: the whole batch
         v, cpu_build_s, cpu_s = cpu_leg(n_sample)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"first {n_sample} rays of the batch ({cpu_s:.1f} s) on the full 1M-triangle scene; oracle port (binned-SAH binary BVH built in {cpu_build_s:.1f} s single-threaded), not Embree"}

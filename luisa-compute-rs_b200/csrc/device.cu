@@ -198,7 +198,7 @@ struct StreamObj {
 struct DeviceObj {
     int ordinal = 0;
     LaunchCounter lc;
-    StreamObj *internal = nullptr;  // used by the *_host entry points
+    StreamObj *internal = nullptr, *internal2 = nullptr;  // traversal lanes of the *_host entry points (alternating chunks)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H lanes of the pipelined host entry points
     // grow-only device staging for the host entry points
     uint8_t *stage_rays = nullptr, *stage_out = nullptr; size_t stage_rays_cap = 0, stage_out_cap = 0;
@@ -613,6 +613,7 @@ lcb_denoiser_ext denoiser_ext(lcb_device) { return lcb_denoiser_ext{nullptr, nul
 void destroy_device(lcb_device_interface iface) {
     DeviceObj *d = dev_of(iface.device); bind(d);
     if (d->internal) free_stream(d->internal);
+    if (d->internal2) free_stream(d->internal2);
     if (d->copy_in) cudaStreamDestroy(d->copy_in);
     if (d->copy_out) cudaStreamDestroy(d->copy_out);
     if (d->stage_rays) cudaFree(d->stage_rays);
@@ -647,7 +648,7 @@ lcb_device_interface create_device(lcb_context, const char *name, const char *js
         unsigned long long keep = ~0ull; CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     auto *d = new DeviceObj; d->ordinal = ordinal;
-    d->internal = make_stream(d);
+    d->internal = make_stream(d); d->internal2 = make_stream(d);
     CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
     log_msg("I", "b200 device %d: %s, %d SMs, %.1f GB", ordinal, prop.name, prop.multiProcessorCount, prop.totalGlobalMem / 1e9);
@@ -728,31 +729,40 @@ void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, 
     flush_launches(d);
 }
 
-// Host-buffer entry points.  The batch is cut into 1 Mi-ray chunks that flow through three lanes — H2D copy,
-// traversal, D2H copy — on three streams chained by events, so PCIe transfers in both directions overlap the kernel.
+// Host-buffer entry points.  The batch is cut into chunks that flow through three lanes — H2D copy, traversal, D2H
+// copy — chained by events, so PCIe transfers in both directions overlap the kernels.  Consecutive chunks are traced on
+// two alternating streams (each with its own ray-pool counter) so that the tail of one persistent launch overlaps the
+// start of the next.
+static uint64_t host_chunk_rays() {
+    static uint64_t c = [] { uint64_t v = 1ull << 20; if (const char *e = getenv("LC_B200_HOST_CHUNK")) v = strtoull(e, nullptr, 10); return v < 1024 ? 1024 : v; }();
+    return c;
+}
+
 static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays, void *out, size_t out_stride, uint64_t count, uint32_t mask, bool any) {
     std::lock_guard<std::mutex> lk(d->mu);
     ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
     ensure_stage(d->stage_out, d->stage_out_cap, count * out_stride);
-    const uint64_t chunk = 1ull << 20;
+    const uint64_t chunk = host_chunk_rays();
     const size_t n_chunks = (size_t)((count + chunk - 1) / chunk);
     std::vector<cudaEvent_t> ev(2 * n_chunks);
     for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaStream_t sk = d->internal->stream;
+    StreamObj *lanes[2] = {d->internal, d->internal2};
     const AccelView view = view_of(a);
     for (size_t c = 0; c < n_chunks; c++) {
         const uint64_t first = c * chunk, n = std::min(chunk, count - first);
+        StreamObj *k = lanes[c & 1];
         CUDA_CHECK(cudaMemcpyAsync(d->stage_rays + first * 32, rays + first, n * 32, cudaMemcpyHostToDevice, d->copy_in));
         CUDA_CHECK(cudaEventRecord(ev[2 * c], d->copy_in));
-        CUDA_CHECK(cudaStreamWaitEvent(sk, ev[2 * c], 0));
-        if (any) trace_any(sk, view, d->stage_rays + first * 32, (uint32_t *)(d->stage_out + first * out_stride), n, mask, d->internal->work_counter, d->lc);
-        else trace_closest(sk, view, d->stage_rays + first * 32, d->stage_out + first * out_stride, n, mask, d->internal->work_counter, nullptr, d->lc);
-        CUDA_CHECK(cudaEventRecord(ev[2 * c + 1], sk));
+        CUDA_CHECK(cudaStreamWaitEvent(k->stream, ev[2 * c], 0));
+        if (any) trace_any(k->stream, view, d->stage_rays + first * 32, (uint32_t *)(d->stage_out + first * out_stride), n, mask, k->work_counter, d->lc);
+        else trace_closest(k->stream, view, d->stage_rays + first * 32, d->stage_out + first * out_stride, n, mask, k->work_counter, nullptr, d->lc);
+        CUDA_CHECK(cudaEventRecord(ev[2 * c + 1], k->stream));
         CUDA_CHECK(cudaStreamWaitEvent(d->copy_out, ev[2 * c + 1], 0));
         CUDA_CHECK(cudaMemcpyAsync((uint8_t *)out + first * out_stride, d->stage_out + first * out_stride, n * out_stride, cudaMemcpyDeviceToHost, d->copy_out));
     }
     CUDA_CHECK(cudaStreamSynchronize(d->copy_out));
-    CUDA_CHECK(cudaStreamSynchronize(sk));
+    CUDA_CHECK(cudaStreamSynchronize(lanes[0]->stream));
+    CUDA_CHECK(cudaStreamSynchronize(lanes[1]->stream));
     for (auto &e : ev) cudaEventDestroy(e);
     flush_launches(d);
 }
