@@ -309,6 +309,28 @@ LCB_EXPORT void lc_b200_trace_closest(lcb_device, lcb_stream, lcb_accel, lcb_buf
 LCB_EXPORT void lc_b200_trace_any(lcb_device, lcb_stream, lcb_accel, lcb_buffer rays, size_t rays_offset,
                                   lcb_buffer occluded, size_t occluded_offset, uint64_t count, uint32_t mask);
 
+/* Batch form of RayQuery (defs::Accel::ray_query, cpu_kernel_defs/src/lib.rs:124; AccelImpl::ray_query,
+ * cpu/accel.rs:582-800; frontend RayQueryBase rtx.rs:672-756): for i < count, committed[i] is the CommittedHit of
+ * `accel.traverse(rays[i], mask)` (terminate_on_first = false, IR RayTracingQueryAll) or `traverse_any` (true,
+ * RayTracingQueryAny).  Triangles of opaque instances commit without a callback; each triangle candidate of a
+ * NON-opaque instance (AccelBuildModification OPAQUE_OFF) is handed to the candidate hook, which stands in for the
+ * DSL's on_surface_hit closure until kernels are lowered from IR: a device-side pure function selected by `filter`.
+ * A query that commits nothing returns {inst = prim = ~0, bary = 0, hit_type = 0 (Miss), t = 0}. */
+enum {
+    LCB_FILTER_COMMIT_ALL = 0, /* candidate.commit() unconditionally */
+    LCB_FILTER_BARY_DISC = 1,  /* examples/ray_query.rs:148-162: commit iff |uvw.xy|, |uvw.yz|, |uvw.xz| < radius */
+    LCB_FILTER_PRIM_BITS = 2,  /* commit iff bit (first_bit[inst] + prim) of `bits` is set (cut-out table) */
+    LCB_FILTER_REJECT_ALL = 3  /* never commit: non-opaque instances are invisible */
+};
+typedef struct lcb_candidate_filter {
+    int32_t kind;
+    float radius;        /* BARY_DISC */
+    lcb_buffer bits;     /* PRIM_BITS: uint32 words */
+    lcb_buffer first_bit; /* PRIM_BITS: one uint32 per instance slot */
+} lcb_candidate_filter;
+LCB_EXPORT void lc_b200_ray_query(lcb_device, lcb_stream, lcb_accel, lcb_buffer rays, size_t rays_offset, lcb_buffer committed, size_t committed_offset,
+                                  uint64_t count, uint32_t mask, bool terminate_on_first, const lcb_candidate_filter *filter);
+
 /* Host-buffer forms: pinned staging, H2D, trace, D2H, synchronous.  These are the
  * "e2e" calls measured by bench.py. */
 LCB_EXPORT void lc_b200_trace_closest_host(lcb_device, lcb_accel, const lcb_ray *rays, lcb_surface_hit *hits, uint64_t count, uint32_t mask);

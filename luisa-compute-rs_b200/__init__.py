@@ -6,9 +6,9 @@ top-level shim `luisa_compute_rs_b200`.
 """
 from . import _abi
 from .runtime import Buffer, BufferView, Context, Device, Event, LuisaError, Stream
-from .rtx import (Accel, AccelBuildRequest, AccelOption, AccelUsageHint, Index, Mesh, Ray, SurfaceHit, INVALID,
+from .rtx import (Accel, AccelBuildRequest, AccelOption, AccelUsageHint, CommittedHit, HitType, Index, Mesh, Ray, SurfaceCandidateFilter, SurfaceHit, INVALID,
                   affine_from_mat4, hit_valid, make_rays, offset_ray_origin)
 
-__all__ = ["Accel", "AccelBuildRequest", "AccelOption", "AccelUsageHint", "Buffer", "BufferView", "Context", "Device", "Event",
+__all__ = ["Accel", "AccelBuildRequest", "AccelOption", "AccelUsageHint", "CommittedHit", "HitType", "SurfaceCandidateFilter", "Buffer", "BufferView", "Context", "Device", "Event",
            "Index", "INVALID", "LuisaError", "Mesh", "Ray", "Stream", "SurfaceHit", "affine_from_mat4", "hit_valid", "make_rays",
            "offset_ray_origin", "_abi"]

@@ -191,7 +191,16 @@ EXPORTED_SYMBOLS = [
     "lc_b200_trace_any_host", "lc_b200_instance_transform", "lc_b200_instance_user_id", "lc_b200_instance_visibility_mask",
     "lc_b200_mesh_stats", "lc_b200_accel_stats", "lc_b200_trace_closest_counted", "lc_b200_stream_native",
     "lc_b200_buffer_native", "lc_b200_device_ordinal", "lc_b200_kernel_launch_count", "lc_b200_version", "lc_b200_make_ir_type",
+    "lc_b200_ray_query",
 ]
+
+
+class CandidateFilter(C.Structure):
+    """lcb_candidate_filter: the candidate hook of the batch RayQuery entry point."""
+    _fields_ = [("kind", C.c_int32), ("radius", C.c_float), ("bits", Handle), ("first_bit", Handle)]
+
+
+FILTER_COMMIT_ALL, FILTER_BARY_DISC, FILTER_PRIM_BITS, FILTER_REJECT_ALL = 0, 1, 2, 3
 
 _lib = None
 
@@ -214,6 +223,8 @@ def load_library(path=None):
     lib.lc_b200_trace_closest.restype = None
     lib.lc_b200_trace_any.argtypes = [H, H, H, H, C.c_size_t, H, C.c_size_t, C.c_uint64, C.c_uint32]
     lib.lc_b200_trace_any.restype = None
+    lib.lc_b200_ray_query.argtypes = [H, H, H, H, C.c_size_t, H, C.c_size_t, C.c_uint64, C.c_uint32, C.c_bool, C.POINTER(CandidateFilter)]
+    lib.lc_b200_ray_query.restype = None
     lib.lc_b200_trace_closest_counted.argtypes = [H, H, H, H, C.c_size_t, H, C.c_size_t, C.c_uint64, C.c_uint32, C.POINTER(TraceCounters)]
     lib.lc_b200_trace_closest_counted.restype = None
     lib.lc_b200_trace_closest_host.argtypes = [H, H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]

@@ -74,9 +74,20 @@ struct AccelView {
     float world_lo[3], world_hi[3];  // bounds of the TLAS root (ray reordering quantises origins against them)
 };
 
+// Candidate hook of the batch RayQuery entry points (evaluated on device for triangles of non-opaque instances).
+struct CandidateFilter {
+    int kind;                  // 0 commit all, 1 barycentric disc (examples/ray_query.rs), 2 per-primitive cut-out bits, 3 reject all
+    float radius;              // kind 1
+    const uint32_t *bits;      // kind 2: bit (first_bit[inst] + prim) set => commit
+    const uint32_t *first_bit; // kind 2: one entry per instance slot
+};
+
 void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
                    TraceCounters *counters /* device, nullable */, LaunchCounter &lc);
 void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
                LaunchCounter &lc);
+
+void ray_query(cudaStream_t s, const AccelView &a, const void *rays, void *committed_hits, uint64_t count, uint32_t mask, bool terminate_on_first,
+               const CandidateFilter &filter, unsigned long long *work_counter, LaunchCounter &lc);
 
 }  // namespace lcb

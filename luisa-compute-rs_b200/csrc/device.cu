@@ -711,6 +711,27 @@ void lc_b200_trace_any(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer r
     flush_launches(d);
 }
 
+void lc_b200_ray_query(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer committed, size_t committed_offset,
+                       uint64_t count, uint32_t mask, bool terminate_on_first, const lcb_candidate_filter *filter) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id); AccelObj *a = as<AccelObj>(ah.id);
+    BufferObj *rb = as<BufferObj>(rays.id), *hb = as<BufferObj>(committed.id);
+    if (rays_offset % 16 || committed_offset % 8) fatal("ray_query: misaligned offsets");
+    if (rays_offset + count * 32 > rb->size || committed_offset + count * 24 > hb->size) fatal("ray_query: %llu rays exceed the buffers", (unsigned long long)count);
+    CandidateFilter f{LCB_FILTER_COMMIT_ALL, 0.f, nullptr, nullptr};
+    if (filter) {
+        if (filter->kind < 0 || filter->kind > LCB_FILTER_REJECT_ALL) fatal("ray_query: unknown candidate filter %d", filter->kind);
+        f.kind = filter->kind; f.radius = filter->radius;
+        if (filter->kind == LCB_FILTER_PRIM_BITS) {
+            BufferObj *bits = as<BufferObj>(filter->bits.id), *first = as<BufferObj>(filter->first_bit.id);
+            if (first->size < a->instances.size() * 4) fatal("ray_query: first_bit needs one uint32 per instance slot");
+            f.bits = (const uint32_t *)bits->ptr; f.first_bit = (const uint32_t *)first->ptr;
+        }
+    }
+    if (count) ray_query(s->stream, view_of(a), rb->ptr + rays_offset, hb->ptr + committed_offset, count, mask, terminate_on_first, f, s->work_counter, d->lc);
+    flush_launches(d);
+}
+
 void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer hits, size_t hits_offset,
                                    uint64_t count, uint32_t mask, lcb_trace_counters *out) {
     DeviceObj *d = dev_of(dev); bind(d);

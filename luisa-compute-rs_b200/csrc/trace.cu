@@ -236,10 +236,39 @@ struct TraceTune {
     int fetch_min;      // refill when at least this many lanes are idle
 };
 
-template <bool ANY, bool COUNTERS>
+// What a launch computes.  kQueryAll / kQueryAny are the batch forms of RayQuery (AccelImpl::ray_query,
+// cpu/accel.rs:582-800; frontend rtx.rs:672-756): triangles of OPAQUE instances commit like in kClosest, candidates of
+// NON-opaque instances go through the candidate hook (the on_surface_hit callback) and only count when it commits.
+enum TraceMode : int { kClosest = 0, kAny = 1, kQueryAll = 2, kQueryAny = 3 };
+
+// The candidate hook of the batch RayQuery: a pure function of the candidate (so the committed hit does not depend on
+// traversal order).  A lowered DSL kernel would pass its own callable here.  Mirrored by oracle.c `filter_accept`.
+__device__ __forceinline__ bool candidate_commits(const CandidateFilter &f, uint32_t inst, uint32_t prim, float u, float v) {
+    switch (f.kind) {
+        case 0: return true;                                       // commit every candidate
+        case 1: {                                                  // examples/ray_query.rs:148-162: |uvw.xy|, |uvw.yz|, |uvw.xz| < r
+            const float w = __fsub_rn(__fsub_rn(1.0f, u), v);      // uvw = (1-u-v, u, v)
+            const float r2 = __fmul_rn(f.radius, f.radius);
+            const float xy = __fmaf_rn(w, w, __fmul_rn(u, u)), yz = __fmaf_rn(u, u, __fmul_rn(v, v)), xz = __fmaf_rn(w, w, __fmul_rn(v, v));
+            return xy < r2 && yz < r2 && xz < r2;
+        }
+        case 2: {                                                  // per-primitive cut-out bits: bit (first_bit[inst] + prim)
+            const uint32_t b = __ldg(f.first_bit + inst) + prim;
+            return (__ldg(f.bits + (b >> 5)) >> (b & 31u)) & 1u;
+        }
+        default: return false;                                     // reject every candidate
+    }
+}
+
+template <int MODE, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out,
                                                                                unsigned long long count, uint32_t mask, unsigned long long *work_counter,
-                                                                               TraceCounters *ctr, TraceTune tune, const uint32_t *__restrict__ order) {
+                                                                               TraceCounters *ctr, TraceTune tune, const uint32_t *__restrict__ order,
+                                                                               CandidateFilter filter) {
+    constexpr bool ANY = MODE == kAny;
+    constexpr bool QUERY = MODE == kQueryAll || MODE == kQueryAny;
+    constexpr bool FIRST = MODE == kAny || MODE == kQueryAny;  // stop at the first committed hit
+    bool cur_opaque = true;
     __shared__ uint2 s_stack[kSmemStack * kTraceThreads];
     uint2 l_stack[kLocalStack];
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
@@ -334,13 +363,21 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     if (COUNTERS) n_tris++;
                     float t, V, W, det;
                     if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, V, W, det)) {
-                        if (ANY) {
-                            hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = 0;  // retires in the tail below
-                        } else {
-                            const uint32_t prim = __float_as_uint(v0.w);
-                            const bool better = t < tbest || hit_inst == kNone ||
-                                                (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
-                            if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_slot = Gt.x + bit; }
+                        const uint32_t prim = __float_as_uint(v0.w);
+                        bool commit = true;
+                        if (QUERY && !cur_opaque) {  // candidate hook sees the canonical fp32 barycentrics
+                            const float rdet = __frcp_rn(det);
+                            commit = candidate_commits(filter, cur_inst, prim, __fmul_rn(V, rdet), __fmul_rn(W, rdet));
+                        }
+                        if (commit) {
+                            if (ANY) {
+                                hit_inst = cur_inst; Gt.y = 0u; G.y = 0u; sp = 0;  // retires in the tail below
+                            } else {
+                                const bool better = t < tbest || hit_inst == kNone ||
+                                                    (t == tbest && (cur_inst < hit_inst || (cur_inst == hit_inst && prim < hit_prim)));
+                                if (better) { tbest = t; hit_inst = cur_inst; hit_prim = prim; hit_slot = Gt.x + bit; }
+                                if (FIRST) { Gt.y = 0u; G.y = 0u; sp = 0; }
+                            }
                         }
                     }
                 } else {
@@ -359,6 +396,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                         const float4 wo = make_float4(r.ox, r.oy, r.oz, 0.f), wd = make_float4(r.dx, r.dy, r.dz, 0.f);
                         setup_object(r, wo, wd, m0, m1, m2);
                         cur_inst = inst;
+                        if (QUERY) cur_opaque = (meta.z & 2u) != 0u;
                         G = make_uint2(0u, 0x80000000u);
                         Gt = make_uint2(0u, 0u);
                         if (COUNTERS) n_inst++;
@@ -410,11 +448,18 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
 
 // Second pass of closest-hit queries: barycentrics of every hit, one thread per ray, fully converged.  The f64
 // evaluation is the reported value (oracle.c refine_bary); if its determinant vanishes the canonical fp32 ones stand.
+// COMMITTED selects the record layout: SurfaceHit {inst, prim, u, v, t, pad} or CommittedHit {inst, prim, u, v, hit_type, t}.
+template <bool COMMITTED>
 __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__restrict__ rays, uint2 *__restrict__ hits, unsigned long long count) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint2 h0 = hits[3 * i], h2 = hits[3 * i + 2];
-    if (h0.x == kNone) { hits[3 * i + 1] = make_uint2(0u, 0u); hits[3 * i + 2] = make_uint2(h2.x, 0u); return; }
+    if (h0.x == kNone) {
+        hits[3 * i + 1] = make_uint2(0u, 0u);
+        // a RayQuery that commits nothing leaves its zero-initialised CommittedHit (cpu_resource.h:320-331): hit_type Miss, t = 0
+        hits[3 * i + 2] = COMMITTED ? make_uint2(0u /* HitType::Miss */, 0u) : make_uint2(h2.x, 0u);
+        return;
+    }
     const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h0.x);
     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
@@ -433,7 +478,7 @@ __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__r
         }
     }
     hits[3 * i + 1] = make_uint2(__float_as_uint(u), __float_as_uint(v));
-    hits[3 * i + 2] = make_uint2(h2.x, 0u);
+    hits[3 * i + 2] = COMMITTED ? make_uint2(1u /* HitType::Triangle */, h2.x) : make_uint2(h2.x, 0u);
 }
 
 // ---- ray reordering ---------------------------------------------------------------------------------------------------
@@ -500,14 +545,15 @@ TraceTune trace_tune() {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-template <bool ANY, bool COUNTERS>
+template <int MODE, bool COUNTERS>
 void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-            TraceCounters *ctr, LaunchCounter &lc) {
+            TraceCounters *ctr, LaunchCounter &lc, const CandidateFilter &filter = CandidateFilter{0, 0.f, nullptr, nullptr}) {
+    constexpr bool ANY = MODE == kAny;
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<ANY, COUNTERS>, kTraceThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<MODE, COUNTERS>, kTraceThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     unsigned long long want = (count + kTraceThreads - 1) / kTraceThreads;
@@ -540,11 +586,11 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
         }
     }
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
-    k_trace<ANY, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, trace_tune(), order);
+    k_trace<MODE, COUNTERS><<<(unsigned)grid, kTraceThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, work_counter, ctr, trace_tune(), order, filter);
     lc.count++;
     if (scratch) cudaFreeAsync(scratch, s);
     if (!ANY) {
-        k_refine<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), reinterpret_cast<uint2 *>(out), count);
+        k_refine<MODE == kQueryAll || MODE == kQueryAny><<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), reinterpret_cast<uint2 *>(out), count);
         lc.count++;
     }
 }
@@ -553,13 +599,19 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
 
 void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
                    TraceCounters *counters, LaunchCounter &lc) {
-    if (counters) launch<false, true>(s, a, rays, hits, count, mask, work_counter, counters, lc);
-    else launch<false, false>(s, a, rays, hits, count, mask, work_counter, nullptr, lc);
+    if (counters) launch<kClosest, true>(s, a, rays, hits, count, mask, work_counter, counters, lc);
+    else launch<kClosest, false>(s, a, rays, hits, count, mask, work_counter, nullptr, lc);
 }
 
 void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
                LaunchCounter &lc) {
-    launch<true, false>(s, a, rays, occluded, count, mask, work_counter, nullptr, lc);
+    launch<kAny, false>(s, a, rays, occluded, count, mask, work_counter, nullptr, lc);
+}
+
+void ray_query(cudaStream_t s, const AccelView &a, const void *rays, void *committed_hits, uint64_t count, uint32_t mask, bool terminate_on_first,
+               const CandidateFilter &filter, unsigned long long *work_counter, LaunchCounter &lc) {
+    if (terminate_on_first) launch<kQueryAny, false>(s, a, rays, committed_hits, count, mask, work_counter, nullptr, lc, filter);
+    else launch<kQueryAll, false>(s, a, rays, committed_hits, count, mask, work_counter, nullptr, lc, filter);
 }
 
 }  // namespace lcb

@@ -30,7 +30,46 @@ Ray = np.dtype([("orig", "<f4", (3,)), ("tmin", "<f4"), ("dir", "<f4", (3,)), ("
 SurfaceHit = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("committed_ray_t", "<f4"), ("_pad", "<u4")])
 # rtx.rs:536
 Index = np.dtype(("<u4", (3,)))
-assert Ray.itemsize == 32 and SurfaceHit.itemsize == 24
+# rtx.rs:477-485 — 24 bytes, align 8; hit_type: 0 miss, 1 surface (triangle), 2 procedural (rtx.rs:486-493)
+CommittedHit = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("hit_type", "<u4"), ("committed_ray_t", "<f4")])
+assert Ray.itemsize == 32 and SurfaceHit.itemsize == 24 and CommittedHit.itemsize == 24
+
+
+class HitType:  # rtx.rs:486-493
+    MISS = 0
+    SURFACE = 1
+    PROCEDURAL = 2
+
+
+class SurfaceCandidateFilter:
+    """Stand-in for the `on_surface_hit(|candidate| ...)` closure of `AccelVar::traverse` (rtx.rs:871-902) in the batch
+    form: a device-side pure predicate over the candidate (inst, prim, bary) that decides `candidate.commit()`."""
+
+    def __init__(self, kind=abi.FILTER_COMMIT_ALL, radius=0.0, bits=None, first_bit=None):
+        self.kind, self.radius, self.bits, self.first_bit = kind, radius, bits, first_bit
+
+    @staticmethod
+    def commit_all():
+        return SurfaceCandidateFilter(abi.FILTER_COMMIT_ALL)
+
+    @staticmethod
+    def reject_all():
+        return SurfaceCandidateFilter(abi.FILTER_REJECT_ALL)
+
+    @staticmethod
+    def bary_disc(radius):
+        """examples/ray_query.rs:148-162"""
+        return SurfaceCandidateFilter(abi.FILTER_BARY_DISC, radius=radius)
+
+    @staticmethod
+    def prim_bits(bits_buffer, first_bit_buffer):
+        return SurfaceCandidateFilter(abi.FILTER_PRIM_BITS, bits=bits_buffer, first_bit=first_bit_buffer)
+
+    def _c(self):
+        f = abi.CandidateFilter(self.kind, self.radius, abi.Handle(0), abi.Handle(0))
+        if self.kind == abi.FILTER_PRIM_BITS:
+            f.bits, f.first_bit = self.bits.handle, self.first_bit.handle
+        return f
 
 INVALID = 0xFFFFFFFF
 
@@ -189,6 +228,19 @@ class Accel:
         rv, ov = _as_view(rays), _as_view(occluded)
         n = rv.size // 32 if count is None else count
         self.device.lib.lc_b200_trace_any(self.device.handle, s.handle, self.handle, rv.buffer.handle, rv.offset, ov.buffer.handle, ov.offset, n, mask)
+
+    def traverse(self, rays, committed, count=None, mask=0xFF, on_surface_hit=None, stream=None, terminate_on_first=False):
+        """Batch form of `accel.traverse(ray, opts).on_surface_hit(f).trace()` (rtx.rs:871-902, 678-755): CommittedHit per ray."""
+        s = stream or self.device.default_stream()
+        rv, hv = _as_view(rays), _as_view(committed)
+        n = rv.size // 32 if count is None else count
+        f = (on_surface_hit or SurfaceCandidateFilter.commit_all())._c()
+        self.device.lib.lc_b200_ray_query(self.device.handle, s.handle, self.handle, rv.buffer.handle, rv.offset, hv.buffer.handle, hv.offset, n, mask,
+                                          terminate_on_first, C.byref(f))
+
+    def traverse_any(self, rays, committed, count=None, mask=0xFF, on_surface_hit=None, stream=None):
+        """`accel.traverse_any` (rtx.rs:884-902): terminate on the first committed hit."""
+        self.traverse(rays, committed, count, mask, on_surface_hit, stream, terminate_on_first=True)
 
     trace_closest = intersect   # rtx.rs:819-843 deprecated alias
     trace_any = intersect_any   # rtx.rs:844-870 deprecated alias

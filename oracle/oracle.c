@@ -371,6 +371,60 @@ static inline int box_cull(const float lo[3], const float hi[3], const float o[3
     return 0;
 }
 
+/* the candidate hook of the batch RayQuery (mirrors trace.cu candidate_commits operation by operation) */
+static inline int filter_accept(const oracle_filter *flt, uint32_t inst, uint32_t prim, float u, float v) {
+    switch (flt->kind) {
+        case 0: return 1;
+        case 1: {
+            const float w = (1.0f - u) - v;
+            const float r2 = flt->radius * flt->radius;
+            const float xy = fmaf(w, w, u * u), yz = fmaf(u, u, v * v), xz = fmaf(w, w, v * v);
+            return xy < r2 && yz < r2 && xz < r2;
+        }
+        case 2: { uint32_t b = flt->first_bit[inst] + prim; return (flt->bits[b >> 5] >> (b & 31u)) & 1u; }
+        default: return 0;
+    }
+}
+
+/* flt == NULL: every hit counts (trace_closest); else candidates are filtered (non-opaque instances of a RayQuery).
+ * first != 0: return after the first counted hit. */
+static void mesh_closest_filtered(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, int mode,
+                                  const oracle_filter *flt, int first) {
+    if (m->ntris == 0) return;
+    if (mode == 0) {
+        for (uint32_t p = 0; p < m->ntris; p++) {
+            const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+            float t, u, v;
+            if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v) && (!flt || filter_accept(flt, inst, p, u, v))) {
+                consider(best, t, u, v, inst, p);
+                if (first) return;
+            }
+        }
+        return;
+    }
+    uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    while (top) {
+        const bvh_node *nd = &m->nodes[stack[--top]];
+        double tn;
+        double tb = best->found ? (double)best->t : (double)tmax;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tb, &tn)) continue;
+        if (nd->count) {
+            for (uint32_t i = 0; i < nd->count; i++) {
+                uint32_t p = m->prims[nd->left + i];
+                const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+                float t, u, v;
+                if (canon_tri(f, tmin, tmax, a, b, c, &t, &u, &v) && (!flt || filter_accept(flt, inst, p, u, v))) {
+                    consider(best, t, u, v, inst, p);
+                    if (first) return;
+                }
+            }
+        } else {
+            if (top + 2 > 128) die("oracle BVH stack overflow");
+            stack[top++] = nd->left; stack[top++] = nd->left + 1;
+        }
+    }
+}
+
 static void mesh_closest(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, int mode) {
     if (m->ntris == 0) return;
     if (mode == 0) {
@@ -468,6 +522,24 @@ static uint32_t any_one(const oracle_scene *s, const oracle_ray *r, uint32_t mas
     return 0;
 }
 
+/* AccelImpl::ray_query — accel.rs:582-800 (triangles) */
+static void query_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask, int first, const oracle_filter *flt, oracle_committed_hit *h, int mode) {
+    best_hit best; memset(&best, 0, sizeof(best));
+    for (uint32_t i = 0; i < s->n_insts && !(first && best.found); i++) {
+        const instance *in = &s->insts[i];
+        if (!in->valid || (in->visible & mask) == 0) continue;
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        mesh_closest_filtered(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode, in->opaque ? NULL : flt, first);
+    }
+    if (best.found) {
+        const instance *in = &s->insts[best.inst];
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best.prim, &a, &b, &c);
+        refine_bary(&f, a, b, c, &best.u, &best.v);
+        h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->hit_type = 1; h->t = best.t;
+    } else { h->inst = UINT32_MAX; h->prim = UINT32_MAX; h->u = 0.f; h->v = 0.f; h->hit_type = 0; h->t = 0.f; }
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* double-precision ground truth (Moeller-Trumbore), with ambiguity flags                */
 /* ------------------------------------------------------------------------------------ */
@@ -556,6 +628,7 @@ typedef struct job {
     const oracle_scene *s; const oracle_ray *rays; uint64_t n; uint32_t mask; int mode; int kind;
     oracle_hit *hits; uint32_t *occ; uint8_t *amb;
     uint64_t counter;
+    const oracle_filter *flt; oracle_committed_hit *committed; int first;
 } job;
 
 static void *worker(void *arg) {
@@ -567,7 +640,8 @@ static void *worker(void *arg) {
         for (uint64_t i = i0; i < i1; i++) {
             if (j->kind == 0) closest_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->mode);
             else if (j->kind == 1) j->occ[i] = any_one(j->s, &j->rays[i], j->mask, j->mode);
-            else truth_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->amb ? &j->amb[i] : NULL, j->mode);
+            else if (j->kind == 2) truth_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->amb ? &j->amb[i] : NULL, j->mode);
+            else query_one(j->s, &j->rays[i], j->mask, j->first, j->flt, &j->committed[i], j->mode);
         }
     }
     return NULL;
@@ -585,13 +659,18 @@ static void run(job *j, int threads) {
 }
 
 void oracle_trace_closest(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 0, hits, NULL, NULL, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 0, hits, NULL, NULL, 0, NULL, NULL, 0}; run(&j, threads);
 }
 void oracle_trace_any(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, uint32_t *occ, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 1, NULL, occ, NULL, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 1, NULL, occ, NULL, 0, NULL, NULL, 0}; run(&j, threads);
 }
 void oracle_trace_closest_f64(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, uint8_t *amb, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 2, hits, NULL, amb, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 2, hits, NULL, amb, 0, NULL, NULL, 0}; run(&j, threads);
+}
+void oracle_ray_query(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
+                      oracle_committed_hit *out, int mode, int threads) {
+    static const oracle_filter commit_all = {0, 0.f, NULL, NULL};
+    job j = {s, rays, n, mask, mode, 3, NULL, NULL, NULL, 0, filter ? filter : &commit_all, out, terminate_on_first}; run(&j, threads);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -73,6 +73,19 @@ uint32_t oracle_instance_count(const oracle_scene *);
 void oracle_trace_closest(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, int mode, int threads);
 void oracle_trace_any(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, uint32_t *occluded, int mode, int threads);
 
+/* AccelImpl::ray_query (accel.rs:582-800) in batch form, triangles only: opaque instances commit their hits without
+ * a callback, every triangle candidate of a NON-opaque instance (accel.rs:378-394 enables the filter only there) is
+ * shown to the candidate hook with its canonical fp32 barycentrics and counts only if the hook commits.  The hook is
+ * the same small set of pure predicates the device offers (include/lc_b200_api.h LCB_FILTER_*).  NB the reference CPU
+ * backend records a committed hit only inside its callbacks, so there opaque triangles never reach `rq.hit`; this
+ * restatement follows the frontend's documented semantics (and the DX/OptiX backends): opaque triangles commit.
+ * terminate_on_first = RayTracingQueryAny (rtcOccluded1): WHICH hit is reported is then traversal-order dependent.
+ * Nothing committed -> {~0, ~0, (0,0), hit_type 0, t 0} (the zero-initialised RayQuery of cpu_resource.h:320-331). */
+typedef struct __attribute__((aligned(8))) oracle_committed_hit { uint32_t inst, prim; float u, v; uint32_t hit_type; float t; } oracle_committed_hit;
+typedef struct oracle_filter { int kind; float radius; const uint32_t *bits; const uint32_t *first_bit; } oracle_filter;
+void oracle_ray_query(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
+                      oracle_committed_hit *out, int mode, int threads);
+
 /* Double-precision ground truth.  ambiguous[i] (may be NULL) is set to 1 when the fp32
  * answer is not forced: a second candidate lies within rel 1e-6 of the closest t, or some
  * triangle's nearest barycentric (hit or near miss, |b| < 1e-5) is within rounding of an edge

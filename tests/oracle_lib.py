@@ -11,6 +11,10 @@ _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 _lib = None
 
 
+class Filter(C.Structure):
+    _fields_ = [("kind", C.c_int), ("radius", C.c_float), ("bits", C.c_void_p), ("first_bit", C.c_void_p)]
+
+
 class Mod(C.Structure):
     _fields_ = [("index", C.c_uint32), ("user_id", C.c_uint32), ("flags", C.c_uint32), ("visibility", C.c_uint32),
                 ("mesh", C.c_uint64), ("affine", C.c_float * 12)]
@@ -41,6 +45,7 @@ def lib():
         L.oracle_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
         L.oracle_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
         L.oracle_trace_closest_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_ray_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(Filter), C.c_void_p, C.c_int, C.c_int]
         L.oracle_offset_ray_origin.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.oracle_canonical_triangle.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float] + [C.POINTER(C.c_float)] * 6
         L.oracle_canonical_triangle.restype = C.c_int
@@ -51,6 +56,7 @@ def lib():
 
 
 HIT = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("committed_ray_t", "<f4"), ("_pad", "<u4")])
+COMMITTED = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("hit_type", "<u4"), ("committed_ray_t", "<f4")])
 BRUTE, BVH = 0, 1
 
 
@@ -90,6 +96,16 @@ class OracleScene:
         occ = np.zeros(rays.shape[0], dtype=np.uint32)
         self.L.oracle_trace_any(self.s, rays.ctypes.data, rays.shape[0], mask, occ.ctypes.data, mode, threads)
         return occ
+
+    def ray_query(self, rays, mask=0xFF, terminate_on_first=False, kind=0, radius=0.0, bits=None, first_bit=None, mode=BVH, threads=0):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.shape[0], dtype=COMMITTED)
+        f = Filter(kind, radius, None, None)
+        if bits is not None:
+            bits = np.ascontiguousarray(bits, dtype=np.uint32); first_bit = np.ascontiguousarray(first_bit, dtype=np.uint32)
+            f.bits, f.first_bit = bits.ctypes.data, first_bit.ctypes.data
+        self.L.oracle_ray_query(self.s, rays.ctypes.data, rays.shape[0], mask, int(terminate_on_first), C.byref(f), out.ctypes.data, mode, threads)
+        return out
 
     def truth(self, rays, mask=0xFF, mode=BVH, threads=0):
         rays = np.ascontiguousarray(rays)

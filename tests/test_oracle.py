@@ -157,3 +157,38 @@ def test_degenerate_inputs():
     assert a["prim"][0] == 2 and a["inst"][1] == 0xFFFFFFFF  # zero direction never hits
     empty = ol.OracleScene(); empty.update(0, [])
     assert empty.trace_closest(rays)["inst"].tolist() == [0xFFFFFFFF] * 3
+
+
+def test_ray_query_semantics():
+    """RayQuery (accel.rs:582-800): opaque instances commit without a callback, candidates of non-opaque instances go through
+    the hook; commit-all == trace_closest; reject-all hides non-opaque instances; BVH == brute force; nothing committed -> Miss."""
+    s = scenes.SceneDesc()
+    m = s.add_mesh(*scenes.random_soup(400, 5, extent=0.2))
+    s.add_instance(m, opaque=False)
+    t = scenes.IDENTITY34.copy(); t[:, 3] = [0.3, 0.1, 0]
+    s.add_instance(m, t, opaque=True)
+    o = ol.scene_from_desc(s)
+    rays = scenes.incoherent_rays(4000, seed=3)
+    closest = o.trace_closest(rays)
+    q = o.ray_query(rays, kind=0)
+    assert np.array_equal(q["inst"], closest["inst"]) and np.array_equal(q["prim"], closest["prim"])
+    hit = q["hit_type"] == 1
+    assert np.array_equal(hit, closest["inst"] != 0xFFFFFFFF)
+    assert np.array_equal(q["committed_ray_t"][hit], closest["committed_ray_t"][hit]) and np.all(q["committed_ray_t"][~hit] == 0)
+    assert np.array_equal(q["bary"][hit], closest["bary"][hit])
+    rej = o.ray_query(rays, kind=3)
+    assert np.all(rej["inst"][rej["hit_type"] == 1] == 1)        # only the opaque instance is ever committed
+    only_opaque = o.trace_closest(rays, mask=0xFF)                  # reference: same scene traced with instance 0 removed
+    s2 = scenes.SceneDesc(); m2 = s2.add_mesh(*scenes.random_soup(400, 5, extent=0.2)); s2.add_instance(m2, mask=0); s2.add_instance(m2, t)
+    o2 = ol.scene_from_desc(s2)
+    c2 = o2.trace_closest(rays)
+    assert np.array_equal(rej["prim"], c2["prim"]) and np.array_equal(rej["hit_type"] == 1, c2["inst"] != 0xFFFFFFFF)
+    for kind, kw in ((1, dict(radius=0.8)), (2, dict(bits=np.random.default_rng(1).integers(0, 2**32, 26, dtype=np.uint64).astype(np.uint32), first_bit=[0, 400]))):
+        a = o.ray_query(rays, kind=kind, **kw)
+        b = o.ray_query(rays, kind=kind, mode=ol.BRUTE, **kw)
+        assert a.tobytes() == b.tobytes()
+        n_a = (a["hit_type"] == 1).sum()
+        assert (rej["hit_type"] == 1).sum() <= n_a <= hit.sum()
+        anyq = o.ray_query(rays, terminate_on_first=True, kind=kind, **kw)
+        assert np.array_equal(anyq["hit_type"], a["hit_type"])   # which hit is order dependent, whether one exists is not
+    o.close(); o2.close()

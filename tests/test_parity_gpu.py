@@ -302,6 +302,49 @@ def test_prefer_update_refit_terrain_frames(device):
     ora.close()
 
 
+def test_ray_query_candidates_and_opaque_instances(device):
+    """Batch RayQuery (traverse / traverse_any) against the oracle: mixed opaque / non-opaque instances, every candidate hook."""
+    s = scenes.SceneDesc()
+    m0 = s.add_mesh(*scenes.random_soup(3000, 71, extent=0.08))
+    m1 = s.add_mesh(*scenes.random_soup(500, 72, extent=0.15))
+    s.add_instance(m0, opaque=False)
+    t = scenes.rotation_y(30.0); t[:, 3] = [0.2, 0.1, -0.1]
+    s.add_instance(m1, t, opaque=True)
+    t2 = scenes.IDENTITY34.copy(); t2[:, 3] = [-0.1, 0.0, 0.2]
+    s.add_instance(m1, t2, opaque=False, mask=0x0F)
+    rays = scenes.incoherent_rays(150000, seed=73)
+    o = ol.scene_from_desc(s)
+    d = DeviceScene(device, s)
+    n = rays.shape[0]
+    rb = device.create_buffer_from_array(rays); hb = device.create_buffer(n, 24, 8)
+    rng = np.random.default_rng(74)
+    first_bit = np.array([0, 3000, 3500], np.uint32)
+    bits = rng.integers(0, 2**32, 4000 // 32 + 1, dtype=np.uint64).astype(np.uint32)
+    bb = device.create_buffer_from_array(bits); fb = device.create_buffer_from_array(first_bit)
+    cases = [(lc.SurfaceCandidateFilter.commit_all(), dict(kind=0)), (lc.SurfaceCandidateFilter.reject_all(), dict(kind=3)),
+             (lc.SurfaceCandidateFilter.bary_disc(0.8), dict(kind=1, radius=0.8)), (lc.SurfaceCandidateFilter.bary_disc(0.55), dict(kind=1, radius=0.55)),
+             (lc.SurfaceCandidateFilter.prim_bits(bb, fb), dict(kind=2, bits=bits, first_bit=first_bit))]
+    for flt, kw in cases:
+        for mask in (0xFF, 0xF0):
+            d.accel.traverse(rb, hb, n, mask, flt)
+            got = hb.view().to_numpy(lc.CommittedHit)
+            want = o.ray_query(rays, mask, False, **kw)
+            assert got.tobytes() == want.tobytes(), f"traverse {kw.get('kind')} mask {mask:#x}: {(got != want).sum()} rays differ"
+            d.accel.traverse_any(rb, hb, n, mask, flt)
+            got_any = hb.view().to_numpy(lc.CommittedHit)
+            assert np.array_equal(got_any["hit_type"], want["hit_type"])
+            h = got_any["hit_type"] == 1       # the reported first hit is a real committed candidate inside the ray interval
+            assert np.all(got_any["committed_ray_t"][h] > rays["tmin"][h]) and np.all(got_any["committed_ray_t"][h] >= want["committed_ray_t"][h])
+    # commit-all equals trace_closest
+    d.accel.traverse(rb, hb, n, 0xFF, None)
+    q = hb.view().to_numpy(lc.CommittedHit)
+    c = d.trace_closest(rays)
+    assert np.array_equal(q["inst"], c["inst"]) and np.array_equal(q["prim"], c["prim"]) and np.array_equal(q["bary"], c["bary"])
+    for b in (rb, hb, bb, fb):
+        b.destroy()
+    d.destroy(); o.close()
+
+
 def test_stream_ordering_events_and_callbacks(device):
     s1, s2 = device.create_stream(), device.create_stream()
     a = device.create_buffer(1 << 16, 4); b = device.create_buffer(1 << 16, 4)
