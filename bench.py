@@ -173,6 +173,8 @@ def main():
     torch.cuda.set_device(local_rank)
     os.environ["LC_B200_DEVICE"] = str(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; the contract is ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = lc.Context()
@@ -297,7 +299,7 @@ def main():
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        out["e2e"] = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 24,
+        out["e2e"] = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * n * 24,
                       "api": "lc_b200_trace_closest_host (chunked H2D / trace / D2H pipeline)"}
         got = hits_h.numpy().view(lc.SurfaceHit)
         chk = np.empty(n, dtype=lc.SurfaceHit)

@@ -13,7 +13,10 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr int kLeafMax = 3;  // primitives per leaf child (unary count in 3 bits)
+#ifndef LCB_LEAF_MAX
+#define LCB_LEAF_MAX 2
+#endif
+constexpr int kLeafMax = LCB_LEAF_MAX;  // primitives per leaf child (unary count in 3 bits)
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }

@@ -34,7 +34,7 @@ def test_device_identity(device):
 
 
 def test_c1_triangle(device):
-    rays = scenes.c1_rays(256, 256)
+    rays = scenes.c1_rays(1024, 1024)  # C1 at BASELINE size
     check_scene(device, scenes.c1_triangle(), rays)
     g = np.load(os.path.join(GOLDEN, "c1_closed_form_64.npz"))
     d = DeviceScene(device, scenes.c1_triangle())
@@ -49,7 +49,7 @@ def test_c1_triangle(device):
 
 def test_c2_cornell_primary_and_golden(device):
     desc = scenes.c2_cornell()
-    check_scene(device, desc, scenes.c2_primary_rays(256, 256))
+    check_scene(device, desc, scenes.c2_primary_rays(1024, 1024))  # C2 primary rays at BASELINE size
     g = np.load(os.path.join(GOLDEN, "cornell_primary_48.npz"))
     d = DeviceScene(device, desc)
     hits = d.trace_closest(scenes.c2_primary_rays(48, 48))
