@@ -331,6 +331,24 @@ typedef struct lcb_candidate_filter {
 LCB_EXPORT void lc_b200_ray_query(lcb_device, lcb_stream, lcb_accel, lcb_buffer rays, size_t rays_offset, lcb_buffer committed, size_t committed_offset,
                                   uint64_t count, uint32_t mask, bool terminate_on_first, const lcb_candidate_filter *filter);
 
+/* The kernel of luisa_compute/examples/path_tracer.rs:247-455 (Cornell box path tracer: LCG sampler, area-light MIS,
+ * cosine-weighted bounces, Russian roulette) in the form the IR -> CUDA lowering will emit: one thread per pixel calling
+ * the single-ray traversal routines.  One call = one `path_tracer.dispatch([w, h, 1], &acc_img, &seed_img, &accel, &res)`
+ * (path_tracer.rs:541-548): `image` (w*h float4, accumulated radiance + sample count) and `seed_image` (w*h uint32) are
+ * read and updated.  vertex_heap[i] / index_heap[i] are the [f32;3] vertex and Index buffers of instance i (the
+ * example's bindless heaps).  If ray_counts_out is non-null the call synchronises and returns the number of closest-hit
+ * and any-hit rays traced by this dispatch. */
+typedef struct lcb_path_tracer_args {
+    lcb_accel accel;
+    const lcb_buffer *vertex_heap;
+    const lcb_buffer *index_heap;
+    uint32_t heap_size;
+    lcb_buffer image, seed_image;
+    uint32_t width, height, spp_per_dispatch, max_depth; /* example: 32 spp per dispatch, depth 10 */
+    float tan_half_fov;                                  /* tan(0.5 * 27.8 deg) in fp32, path_tracer.rs:293-302 */
+} lcb_path_tracer_args;
+LCB_EXPORT void lc_b200_example_path_tracer(lcb_device, lcb_stream, const lcb_path_tracer_args *, uint64_t ray_counts_out[2]);
+
 /* Host-buffer forms: pinned staging, H2D, trace, D2H, synchronous.  These are the
  * "e2e" calls measured by bench.py. */
 LCB_EXPORT void lc_b200_trace_closest_host(lcb_device, lcb_accel, const lcb_ray *rays, lcb_surface_hit *hits, uint64_t count, uint32_t mask);

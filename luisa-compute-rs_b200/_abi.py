@@ -191,8 +191,15 @@ EXPORTED_SYMBOLS = [
     "lc_b200_trace_any_host", "lc_b200_instance_transform", "lc_b200_instance_user_id", "lc_b200_instance_visibility_mask",
     "lc_b200_mesh_stats", "lc_b200_accel_stats", "lc_b200_trace_closest_counted", "lc_b200_stream_native",
     "lc_b200_buffer_native", "lc_b200_device_ordinal", "lc_b200_kernel_launch_count", "lc_b200_version", "lc_b200_make_ir_type",
-    "lc_b200_ray_query",
+    "lc_b200_ray_query", "lc_b200_example_path_tracer",
 ]
+
+
+class PathTracerArgs(C.Structure):
+    """lcb_path_tracer_args"""
+    _fields_ = [("accel", Handle), ("vertex_heap", C.POINTER(Handle)), ("index_heap", C.POINTER(Handle)), ("heap_size", C.c_uint32),
+                ("image", Handle), ("seed_image", Handle), ("width", C.c_uint32), ("height", C.c_uint32), ("spp_per_dispatch", C.c_uint32),
+                ("max_depth", C.c_uint32), ("tan_half_fov", C.c_float)]
 
 
 class CandidateFilter(C.Structure):
@@ -225,6 +232,8 @@ def load_library(path=None):
     lib.lc_b200_trace_any.restype = None
     lib.lc_b200_ray_query.argtypes = [H, H, H, H, C.c_size_t, H, C.c_size_t, C.c_uint64, C.c_uint32, C.c_bool, C.POINTER(CandidateFilter)]
     lib.lc_b200_ray_query.restype = None
+    lib.lc_b200_example_path_tracer.argtypes = [H, H, C.POINTER(PathTracerArgs), C.POINTER(C.c_uint64)]
+    lib.lc_b200_example_path_tracer.restype = None
     lib.lc_b200_trace_closest_counted.argtypes = [H, H, H, H, C.c_size_t, H, C.c_size_t, C.c_uint64, C.c_uint32, C.POINTER(TraceCounters)]
     lib.lc_b200_trace_closest_counted.restype = None
     lib.lc_b200_trace_closest_host.argtypes = [H, H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]

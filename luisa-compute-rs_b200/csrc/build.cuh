@@ -90,4 +90,9 @@ void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *o
 void ray_query(cudaStream_t s, const AccelView &a, const void *rays, void *committed_hits, uint64_t count, uint32_t mask, bool terminate_on_first,
                const CandidateFilter &filter, unsigned long long *work_counter, LaunchCounter &lc);
 
+// ---- path_tracer.cu ------------------------------------------------------------------------
+void launch_path_tracer(cudaStream_t s, const AccelView &accel, const float *const *vertex_heap, const uint32_t *const *index_heap, float4 *image,
+                        uint32_t *seed_image, uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov,
+                        unsigned long long *ray_counters, LaunchCounter &lc);
+
 }  // namespace lcb

@@ -732,6 +732,37 @@ void lc_b200_ray_query(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer r
     flush_launches(d);
 }
 
+void lc_b200_example_path_tracer(lcb_device dev, lcb_stream sh, const lcb_path_tracer_args *args, uint64_t ray_counts_out[2]) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    StreamObj *s = as<StreamObj>(sh.id); AccelObj *a = as<AccelObj>(args->accel.id);
+    BufferObj *img = as<BufferObj>(args->image.id), *seed = as<BufferObj>(args->seed_image.id);
+    const size_t px = (size_t)args->width * args->height;
+    if (img->size < px * 16 || seed->size < px * 4) fatal("path_tracer: image / seed buffers are smaller than %u x %u", args->width, args->height);
+    if (args->heap_size < a->instances.size()) fatal("path_tracer: heaps must cover every instance slot");
+    // device-side pointer tables of the two bindless heaps + the ray counters, in one stream-ordered scratch block
+    const size_t table = (size_t)args->heap_size * sizeof(void *);
+    std::vector<const void *> host(2 * args->heap_size);
+    for (uint32_t i = 0; i < args->heap_size; i++) {
+        host[i] = as<BufferObj>(args->vertex_heap[i].id)->ptr;
+        host[args->heap_size + i] = as<BufferObj>(args->index_heap[i].id)->ptr;
+    }
+    uint8_t *scratch = nullptr;
+    CUDA_CHECK(cudaMallocAsync((void **)&scratch, 2 * table + 16, s->stream));
+    CUDA_CHECK(cudaMemcpyAsync(scratch, host.data(), 2 * table, cudaMemcpyHostToDevice, s->stream));  // pageable source: staged before returning
+    CUDA_CHECK(cudaMemsetAsync(scratch + 2 * table, 0, 16, s->stream));
+    launch_path_tracer(s->stream, view_of(a), (const float *const *)scratch, (const uint32_t *const *)(scratch + table), (float4 *)img->ptr,
+                       (uint32_t *)seed->ptr, args->width, args->height, args->spp_per_dispatch, args->max_depth, args->tan_half_fov,
+                       (unsigned long long *)(scratch + 2 * table), d->lc);
+    if (ray_counts_out) {
+        unsigned long long h[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(h, scratch + 2 * table, 16, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        ray_counts_out[0] = h[0]; ray_counts_out[1] = h[1];
+    }
+    CUDA_CHECK(cudaFreeAsync(scratch, s->stream));
+    flush_launches(d);
+}
+
 void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, lcb_buffer rays, size_t rays_offset, lcb_buffer hits, size_t hits_offset,
                                    uint64_t count, uint32_t mask, lcb_trace_counters *out) {
     DeviceObj *d = dev_of(dev); bind(d);

@@ -22,7 +22,7 @@
 // intrinsic so that nvcc cannot contract or reorder it.  Box culling is conservative with
 // respect to that arithmetic (planes padded by 2^-20 of the L-inf distance to the node), so
 // results do not depend on the tree nor on the schedule.
-#include "build.cuh"
+#include "trace_device.cuh"
 #include <cstdio>
 #include <cstdlib>
 
@@ -31,7 +31,6 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
@@ -39,197 +38,6 @@ constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #endif
 constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
 constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
-
-struct RaySetup {
-    float ox, oy, oz, dx, dy, dz;  // ray in the current space (world or object)
-    float ix, iy, iz;              // clamped reciprocal direction for slab tests
-    float sx, sy, sz;              // shear constants of the canonical triangle test
-    int kz;
-    uint32_t octinv;               // 7 ^ sign bits (bit k = direction negative along k)
-};
-
-__device__ __forceinline__ float safe_rcp(float d) {
-    // |d| < 1e-20 is treated as 1e-20 with d's sign bit: keeps slab arithmetic finite; culling stays conservative
-    float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
-    return __frcp_rn(a);
-}
-
-__device__ __forceinline__ void finish_setup(RaySetup &r) {
-    r.ix = safe_rcp(r.dx); r.iy = safe_rcp(r.dy); r.iz = safe_rcp(r.dz);
-    const uint32_t sgn = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
-    r.octinv = 7u ^ sgn;
-    int kz = 0;
-    float m = fabsf(r.dx);
-    if (fabsf(r.dy) > m) { kz = 1; m = fabsf(r.dy); }
-    if (fabsf(r.dz) > m) { kz = 2; }
-    r.kz = kz;
-    const float dz = kz == 0 ? r.dx : (kz == 1 ? r.dy : r.dz);
-    const float dx = kz == 0 ? r.dy : (kz == 1 ? r.dz : r.dx);
-    const float dy = kz == 0 ? r.dz : (kz == 1 ? r.dx : r.dy);
-    r.sx = __fdiv_rn(dx, dz);
-    r.sy = __fdiv_rn(dy, dz);
-    r.sz = __frcp_rn(dz);
-}
-
-__device__ __forceinline__ void setup_world(RaySetup &r, const float4 a, const float4 b) {
-    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = b.x; r.dy = b.y; r.dz = b.z;
-    finish_setup(r);
-}
-
-// world -> object with the canonical nested-fma order
-__device__ __forceinline__ void transform_ray(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
-    r.ox = __fmaf_rn(m0.x, wo.x, __fmaf_rn(m0.y, wo.y, __fmaf_rn(m0.z, wo.z, m0.w)));
-    r.oy = __fmaf_rn(m1.x, wo.x, __fmaf_rn(m1.y, wo.y, __fmaf_rn(m1.z, wo.z, m1.w)));
-    r.oz = __fmaf_rn(m2.x, wo.x, __fmaf_rn(m2.y, wo.y, __fmaf_rn(m2.z, wo.z, m2.w)));
-    r.dx = __fmaf_rn(m0.x, wd.x, __fmaf_rn(m0.y, wd.y, __fmul_rn(m0.z, wd.z)));
-    r.dy = __fmaf_rn(m1.x, wd.x, __fmaf_rn(m1.y, wd.y, __fmul_rn(m1.z, wd.z)));
-    r.dz = __fmaf_rn(m2.x, wd.x, __fmaf_rn(m2.y, wd.y, __fmul_rn(m2.z, wd.z)));
-}
-
-__device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const float4 wd, const float4 m0, const float4 m1, const float4 m2) {
-    transform_ray(r, wo, wd, m0, m1, m2);
-    finish_setup(r);
-}
-
-// 16-bit plane index -> float 2^23 + q in ONE byte-permute (no int->float conversion, no subtraction): the 2^23
-// bias is folded into the per-node plane offsets below, at the price of half a quantisation step of rounding
-// slop that the padding absorbs (one extra step, 2^-16 of the node extent).  The constant sits in the first
-// operand so that the selector is an immediate and 0x4B000000 lives in one register for the whole kernel.
-__device__ __forceinline__ float q16_lo(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3254)); }
-__device__ __forceinline__ float q16_hi(uint32_t w) { return __uint_as_float(__byte_perm(0x4B000000u, w, 0x3276)); }
-
-// 256-bit read-only global load (LDG.E.ENL2.256.CONSTANT): one full 32-byte sector per lane and instruction
-struct U8 { uint32_t v[8]; };
-__device__ __forceinline__ U8 ldg256(const void *p) {
-    U8 r;
-    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-
-// each byte -> 0xff if its top bit is set, else 0x00 (prmt sign-replicate mode; __byte_perm masks the selector's msb away)
-__device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
-    return d;
-}
-
-// Tests the 8 children of one node.  Returns the hit mask: bits 24..31 internal children in
-// traversal priority order for this ray's octant, bits 0..23 leaf primitives.
-__device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ node, const RaySetup &r, float tmin, float tmax,
-                                                   uint32_t &child_base, uint32_t &prim_base, uint32_t &imask) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(node);
-    const U8 H = ldg256(p), X = ldg256(p + 2), Y = ldg256(p + 4), Z = ldg256(p + 6);
-    const uint4 n0 = make_uint4(H.v[0], H.v[1], H.v[2], H.v[3]), n1 = make_uint4(H.v[4], H.v[5], H.v[6], H.v[7]);
-    const bool neg_x = (r.octinv & 1u) == 0, neg_y = (r.octinv & 2u) == 0, neg_z = (r.octinv & 4u) == 0;
-    // near/far plane vectors by direction sign (words 0..3 = lower planes, 4..7 = upper planes of the 8 slots)
-#define LCB_NEAR(V, NEG) make_uint4(NEG ? V.v[4] : V.v[0], NEG ? V.v[5] : V.v[1], NEG ? V.v[6] : V.v[2], NEG ? V.v[7] : V.v[3])
-#define LCB_FAR(V, NEG) make_uint4(NEG ? V.v[0] : V.v[4], NEG ? V.v[1] : V.v[5], NEG ? V.v[2] : V.v[6], NEG ? V.v[3] : V.v[7])
-    const uint4 qnx = LCB_NEAR(X, neg_x), qfx = LCB_FAR(X, neg_x);
-    const uint4 qny = LCB_NEAR(Y, neg_y), qfy = LCB_FAR(Y, neg_y);
-    const uint4 qnz = LCB_NEAR(Z, neg_z), qfz = LCB_FAR(Z, neg_z);
-#undef LCB_NEAR
-#undef LCB_FAR
-    child_base = n1.x; prim_base = n1.y; imask = n0.w >> 24;
-    const float sclx = __uint_as_float((n0.w & 0xffu) << 23), scly = __uint_as_float((n0.w & 0xff00u) << 15), sclz = __uint_as_float((n0.w & 0xff0000u) << 7);
-    const float rx = __uint_as_float(n0.x) - r.ox, ry = __uint_as_float(n0.y) - r.oy, rz = __uint_as_float(n0.z) - r.oz;
-    // conservative padding: 2^-20 of the L-inf distance from the ray origin to the far side of the node frame
-    const float R = fmaxf(fmaxf(fabsf(rx) + 65535.0f * sclx, fabsf(ry) + 65535.0f * scly), fabsf(rz) + 65535.0f * sclz);
-    const float pad = R * (1.0f / 1048576.0f);
-    const float ax = sclx * r.ix, ay = scly * r.iy, az = sclz * r.iz;
-    const float cx = rx * r.ix, cy = ry * r.iy, cz = rz * r.iz;
-    const float px = fmaf(pad, fabsf(r.ix), fabsf(ax)), py = fmaf(pad, fabsf(r.iy), fabsf(ay)), pz = fmaf(pad, fabsf(r.iz), fabsf(az));
-    const float bnx = fmaf(-8388608.0f, ax, cx - px), bfx = fmaf(-8388608.0f, ax, cx + px);
-    const float bny = fmaf(-8388608.0f, ay, cy - py), bfy = fmaf(-8388608.0f, ay, cy + py);
-    const float bnz = fmaf(-8388608.0f, az, cz - pz), bfz = fmaf(-8388608.0f, az, cz + pz);
-    // hit-mask construction on 4 meta bytes at a time (after Ylitie et al. 2017): per child only a byte extract,
-    // a shift and a select remain.  Internal children (low 5 bits >= 24) get their bit index XORed with the
-    // ray octant so that __clz order is front-to-back order.
-    const uint32_t oct4 = r.octinv * 0x01010101u;
-    const uint32_t inner_lo = sign_extend_bytes((n1.z & (n1.z << 1) & 0x10101010u) << 3);  // 0xff per internal child
-    const uint32_t inner_hi = sign_extend_bytes((n1.w & (n1.w << 1) & 0x10101010u) << 3);
-    const uint32_t idx_lo = (n1.z ^ (oct4 & inner_lo)) & 0x1f1f1f1fu, idx_hi = (n1.w ^ (oct4 & inner_hi)) & 0x1f1f1f1fu;
-    const uint32_t bits_lo = (n1.z >> 5) & 0x07070707u, bits_hi = (n1.w >> 5) & 0x07070707u;
-    uint32_t hits = 0;
-#define LCB_CHILD(WORD, CONV, BITS, IDX, SHIFT)                                                              \
-    {                                                                                                        \
-        const float tn = fmaxf(fmaxf(fmaf(CONV(qnx.WORD), ax, bnx), fmaf(CONV(qny.WORD), ay, bny)),          \
-                               fmaxf(fmaf(CONV(qnz.WORD), az, bnz), tmin));                                  \
-        const float tf = fminf(fminf(fmaf(CONV(qfx.WORD), ax, bfx), fmaf(CONV(qfy.WORD), ay, bfy)),          \
-                               fminf(fmaf(CONV(qfz.WORD), az, bfz), tmax));                                  \
-        const uint32_t b = ((BITS >> SHIFT) & 0xffu) << ((IDX >> SHIFT) & 31u);                              \
-        hits |= tn <= tf ? b : 0u;                                                                           \
-    }
-    LCB_CHILD(x, q16_lo, bits_lo, idx_lo, 0)
-    LCB_CHILD(x, q16_hi, bits_lo, idx_lo, 8)
-    LCB_CHILD(y, q16_lo, bits_lo, idx_lo, 16)
-    LCB_CHILD(y, q16_hi, bits_lo, idx_lo, 24)
-    LCB_CHILD(z, q16_lo, bits_hi, idx_hi, 0)
-    LCB_CHILD(z, q16_hi, bits_hi, idx_hi, 8)
-    LCB_CHILD(w, q16_lo, bits_hi, idx_hi, 16)
-    LCB_CHILD(w, q16_hi, bits_hi, idx_hi, 24)
-#undef LCB_CHILD
-    return hits;
-}
-
-__device__ __forceinline__ float pick(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
-
-// The canonical fp32 ray/triangle evaluation (oracle.c canon_tri).  The traversal loop only needs
-// the decision and t; (V, W, det) are handed back so that the barycentrics can be formed where they are needed.
-__device__ __forceinline__ bool canonical_triangle(const RaySetup &r, float tmin, float tmax, const float4 v0, const float4 v1, const float4 v2,
-                                                   float &t_out, float &V_out, float &W_out, float &det_out) {
-    const float a0 = __fsub_rn(v0.x, r.ox), a1 = __fsub_rn(v0.y, r.oy), a2 = __fsub_rn(v0.z, r.oz);
-    const float b0 = __fsub_rn(v1.x, r.ox), b1 = __fsub_rn(v1.y, r.oy), b2 = __fsub_rn(v1.z, r.oz);
-    const float c0 = __fsub_rn(v2.x, r.ox), c1 = __fsub_rn(v2.y, r.oy), c2 = __fsub_rn(v2.z, r.oz);
-    const int kz = r.kz;
-    const float a_z = pick(kz, a0, a1, a2), a_x = pick(kz, a1, a2, a0), a_y = pick(kz, a2, a0, a1);
-    const float b_z = pick(kz, b0, b1, b2), b_x = pick(kz, b1, b2, b0), b_y = pick(kz, b2, b0, b1);
-    const float c_z = pick(kz, c0, c1, c2), c_x = pick(kz, c1, c2, c0), c_y = pick(kz, c2, c0, c1);
-    const float ax = __fmaf_rn(-r.sx, a_z, a_x), ay = __fmaf_rn(-r.sy, a_z, a_y);
-    const float bx = __fmaf_rn(-r.sx, b_z, b_x), by = __fmaf_rn(-r.sy, b_z, b_y);
-    const float cx = __fmaf_rn(-r.sx, c_z, c_x), cy = __fmaf_rn(-r.sy, c_z, c_y);
-    float U = __fsub_rn(__fmul_rn(cx, by), __fmul_rn(cy, bx));
-    float V = __fsub_rn(__fmul_rn(ax, cy), __fmul_rn(ay, cx));
-    float W = __fsub_rn(__fmul_rn(bx, ay), __fmul_rn(by, ax));
-    if (U == 0.0f || V == 0.0f || W == 0.0f) {
-        U = __double2float_rn(__dsub_rn(__dmul_rn((double)cx, (double)by), __dmul_rn((double)cy, (double)bx)));
-        V = __double2float_rn(__dsub_rn(__dmul_rn((double)ax, (double)cy), __dmul_rn((double)ay, (double)cx)));
-        W = __double2float_rn(__dsub_rn(__dmul_rn((double)bx, (double)ay), __dmul_rn((double)by, (double)ax)));
-    }
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    const float det = __fadd_rn(__fadd_rn(U, V), W);
-    if (det == 0.0f) return false;
-    const float az = __fmul_rn(r.sz, a_z), bz = __fmul_rn(r.sz, b_z), cz = __fmul_rn(r.sz, c_z);
-    const float T = __fmaf_rn(U, az, __fmaf_rn(V, bz, __fmul_rn(W, cz)));
-    const float t = __fdiv_rn(T, det);
-    if (!(t > tmin && t <= tmax)) return false;
-    t_out = t; V_out = V; W_out = W; det_out = det;
-    return true;
-}
-
-// Reported barycentrics of the winning triangle: one double-precision Moeller-Trumbore evaluation on the
-// canonical object-space ray (fixed operation order; oracle.c refine_bary).  Once per ray, off the hot loop.
-// Returns false when the double determinant vanishes (the canonical fp32 barycentrics stand).
-__device__ __forceinline__ bool refine_bary(const RaySetup &r, const float4 v0, const float4 v1, const float4 v2, float &u_out, float &v_out) {
-    const double e1x = __dsub_rn((double)v1.x, (double)v0.x), e1y = __dsub_rn((double)v1.y, (double)v0.y), e1z = __dsub_rn((double)v1.z, (double)v0.z);
-    const double e2x = __dsub_rn((double)v2.x, (double)v0.x), e2y = __dsub_rn((double)v2.y, (double)v0.y), e2z = __dsub_rn((double)v2.z, (double)v0.z);
-    const double sx = __dsub_rn((double)r.ox, (double)v0.x), sy = __dsub_rn((double)r.oy, (double)v0.y), sz = __dsub_rn((double)r.oz, (double)v0.z);
-    const double dx = r.dx, dy = r.dy, dz = r.dz;
-    const double px = __dsub_rn(__dmul_rn(dy, e2z), __dmul_rn(dz, e2y));
-    const double py = __dsub_rn(__dmul_rn(dz, e2x), __dmul_rn(dx, e2z));
-    const double pz = __dsub_rn(__dmul_rn(dx, e2y), __dmul_rn(dy, e2x));
-    const double det = __dadd_rn(__dadd_rn(__dmul_rn(e1x, px), __dmul_rn(e1y, py)), __dmul_rn(e1z, pz));
-    if (det == 0.0) return false;
-    const double inv = __ddiv_rn(1.0, det);
-    const double u = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx, px), __dmul_rn(sy, py)), __dmul_rn(sz, pz)), inv);
-    const double qx = __dsub_rn(__dmul_rn(sy, e1z), __dmul_rn(sz, e1y));
-    const double qy = __dsub_rn(__dmul_rn(sz, e1x), __dmul_rn(sx, e1z));
-    const double qz = __dsub_rn(__dmul_rn(sx, e1y), __dmul_rn(sy, e1x));
-    const double v = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, qx), __dmul_rn(dy, qy)), __dmul_rn(dz, qz)), inv);
-    u_out = __double2float_rn(u); v_out = __double2float_rn(v);
-    return true;
-}
 
 // Scheduling knob of the traversal loop (LC_B200_TRACE_TUNE = "fetch_min").
 struct TraceTune {

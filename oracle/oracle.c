@@ -629,7 +629,9 @@ typedef struct job {
     oracle_hit *hits; uint32_t *occ; uint8_t *amb;
     uint64_t counter;
     const oracle_filter *flt; oracle_committed_hit *committed; int first;
+    const struct pt_job *pt;
 } job;
+static void pt_pixel(const struct pt_job *pt, const oracle_scene *s, uint64_t pixel);
 
 static void *worker(void *arg) {
     job *j = (job *)arg;
@@ -641,7 +643,8 @@ static void *worker(void *arg) {
             if (j->kind == 0) closest_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->mode);
             else if (j->kind == 1) j->occ[i] = any_one(j->s, &j->rays[i], j->mask, j->mode);
             else if (j->kind == 2) truth_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->amb ? &j->amb[i] : NULL, j->mode);
-            else query_one(j->s, &j->rays[i], j->mask, j->first, j->flt, &j->committed[i], j->mode);
+            else if (j->kind == 3) query_one(j->s, &j->rays[i], j->mask, j->first, j->flt, &j->committed[i], j->mode);
+            else pt_pixel(j->pt, j->s, i);
         }
     }
     return NULL;
@@ -659,18 +662,18 @@ static void run(job *j, int threads) {
 }
 
 void oracle_trace_closest(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 0, hits, NULL, NULL, 0, NULL, NULL, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 0, hits, NULL, NULL, 0, NULL, NULL, 0, NULL}; run(&j, threads);
 }
 void oracle_trace_any(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, uint32_t *occ, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 1, NULL, occ, NULL, 0, NULL, NULL, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 1, NULL, occ, NULL, 0, NULL, NULL, 0, NULL}; run(&j, threads);
 }
 void oracle_trace_closest_f64(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, oracle_hit *hits, uint8_t *amb, int mode, int threads) {
-    job j = {s, rays, n, mask, mode, 2, hits, NULL, amb, 0, NULL, NULL, 0}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 2, hits, NULL, amb, 0, NULL, NULL, 0, NULL}; run(&j, threads);
 }
 void oracle_ray_query(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
                       oracle_committed_hit *out, int mode, int threads) {
     static const oracle_filter commit_all = {0, 0.f, NULL, NULL};
-    job j = {s, rays, n, mask, mode, 3, NULL, NULL, NULL, 0, filter ? filter : &commit_all, out, terminate_on_first}; run(&j, threads);
+    job j = {s, rays, n, mask, mode, 3, NULL, NULL, NULL, 0, filter ? filter : &commit_all, out, terminate_on_first, NULL}; run(&j, threads);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -686,4 +689,160 @@ void oracle_offset_ray_origin(const float p[3], const float n[3], float out[3]) 
         float pf; memcpy(&pf, &p_i, 4);
         out[k] = fabsf(p[k]) < origin ? p[k] + float_scale * n[k] : pf;
     }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* examples/path_tracer.rs:247-455 — the caller of the path on config C2                 */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct v3 { float x, y, z; } v3;
+static inline v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 vmul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 vdiv(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+static inline float vdot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline float vlength(v3 a) { return sqrtf(vdot(a, a)); }
+static inline v3 vnormalize(v3 a) { return vdiv(a, vlength(a)); }
+static inline v3 voffset(v3 p, v3 n) { float pi[3] = {p.x, p.y, p.z}, ni[3] = {n.x, n.y, n.z}, o[3]; oracle_offset_ray_origin(pi, ni, o); return V(o[0], o[1], o[2]); }
+
+static inline void sincos_2pi(float u, float *s, float *c) {
+    const float kf = floorf(u * 4.0f + 0.5f);
+    const float r = u - kf * 0.25f;
+    const float x = r * 6.28318530717958647692f;
+    const float x2 = x * x;
+    float sp = fmaf(x2, 2.7557319e-6f, -1.9841270e-4f);
+    sp = fmaf(sp, x2, 8.3333333e-3f);
+    sp = fmaf(sp, x2, -1.6666667e-1f);
+    sp = fmaf(sp * x2, x, x);
+    float cp = fmaf(x2, 2.4801587e-5f, -1.3888889e-3f);
+    cp = fmaf(cp, x2, 4.1666667e-2f);
+    cp = fmaf(cp, x2, -0.5f);
+    cp = fmaf(cp, x2, 1.0f);
+    const int k = (int)kf & 3;
+    *s = k == 0 ? sp : k == 1 ? cp : k == 2 ? -sp : -cp;
+    *c = k == 0 ? cp : k == 1 ? -sp : k == 2 ? -cp : sp;
+}
+
+static inline float lcg(uint32_t *state) {
+    *state = 1664525u * *state + 1013904223u;
+    return (float)(*state & 0x00ffffffu) * (1.0f / 16777216.0f);
+}
+
+struct pt_job {
+    const float *const *vertex_heap; const uint32_t *const *index_heap; float *image; uint32_t *seeds;
+    uint32_t width, height, spp, max_depth; float tan_half_fov; int mode;
+    uint64_t n_closest, n_any;
+};
+
+static void pt_pixel(const struct pt_job *ptc, const oracle_scene *s, uint64_t pixel) {
+    struct pt_job *pt = (struct pt_job *)ptc;
+    static const float mats[8][3] = {{0.725f, 0.710f, 0.680f}, {0.725f, 0.710f, 0.680f}, {0.725f, 0.710f, 0.680f}, {0.140f, 0.450f, 0.091f},
+                                     {0.630f, 0.065f, 0.050f}, {0.725f, 0.710f, 0.680f}, {0.725f, 0.710f, 0.680f}, {0.000f, 0.000f, 0.000f}};
+    const float FRAC_1_PI = 0.318309886183790671537767526745028724f, F32_MAX = 3.40282347e+38f;
+    const uint32_t cx = (uint32_t)(pixel % pt->width), cy = (uint32_t)(pixel / pt->width);
+    const float frame_size = (float)(pt->width < pt->height ? pt->width : pt->height);
+    uint32_t state = pt->seeds[pixel];
+    const float rx = lcg(&state), ry = lcg(&state);
+    const float px = ((float)cx + rx) / frame_size * 2.0f - 1.0f, py = ((float)cy + ry) / frame_size * 2.0f - 1.0f;
+    v3 radiance = V(0.f, 0.f, 0.f);
+    uint64_t n_closest = 0, n_any = 0;
+    const v3 light_position = V(-0.24f, 1.98f, 0.16f);
+    const v3 light_u = vsub(V(-0.24f, 1.98f, -0.22f), light_position), light_v = vsub(V(0.23f, 1.98f, 0.16f), light_position);
+    const v3 light_emission = V(17.0f, 12.0f, 4.0f);
+    const float light_area = vlength(vcross(light_u, light_v));
+    const v3 light_normal = vnormalize(vcross(light_u, light_v));
+    for (uint32_t sample = 0; sample < pt->spp; sample++) {
+        const v3 cam = V(-0.01f, 0.995f, 5.0f);
+        const v3 pix = vadd(cam, V(px * 1.0f * pt->tan_half_fov, py * -1.0f * pt->tan_half_fov, -1.0f));
+        v3 ray_o = cam, ray_d = vnormalize(vsub(pix, cam));
+        float ray_tmin = 0.0f, ray_tmax = F32_MAX;
+        v3 beta = V(1.f, 1.f, 1.f);
+        float pdf_bsdf = 0.0f;
+        uint32_t depth = 0;
+        while (depth < pt->max_depth) {
+            oracle_ray r = {{ray_o.x, ray_o.y, ray_o.z}, ray_tmin, {ray_d.x, ray_d.y, ray_d.z}, ray_tmax};
+            oracle_hit hit;
+            closest_one(s, &r, 0xffu, &hit, pt->mode);
+            n_closest++;
+            if (hit.inst == UINT32_MAX) break;
+            const float *vb = pt->vertex_heap[hit.inst];
+            const uint32_t *tri = pt->index_heap[hit.inst] + 3 * (size_t)hit.prim;
+            const uint32_t i0 = tri[0], i1 = tri[1], i2 = tri[2];
+            const v3 p0 = V(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2]), p1 = V(vb[3 * i1], vb[3 * i1 + 1], vb[3 * i1 + 2]), p2 = V(vb[3 * i2], vb[3 * i2 + 1], vb[3 * i2 + 2]);
+            const v3 p = vadd(vadd(vscale(p0, (1.0f - hit.u) - hit.v), vscale(p1, hit.u)), vscale(p2, hit.v));
+            const v3 n = vnormalize(vcross(vsub(p1, p0), vsub(p2, p0)));
+            const float cos_wi = -vdot(ray_d, n);
+            if (cos_wi < 1e-4f) break;
+            const v3 pp = voffset(p, n);
+            const v3 albedo = V(mats[hit.inst & 7u][0], mats[hit.inst & 7u][1], mats[hit.inst & 7u][2]);
+            if (hit.inst == 7u) {
+                if (depth == 0u) radiance = vadd(radiance, light_emission);
+                else {
+                    const v3 d = vsub(p, ray_o);
+                    const float pdf_light = vdot(d, d) / (light_area * cos_wi);
+                    const float mis_weight = pdf_bsdf / fmaxf(pdf_bsdf + pdf_light, 1e-4f);
+                    radiance = vadd(radiance, vmul(V(mis_weight * beta.x, mis_weight * beta.y, mis_weight * beta.z), light_emission));
+                }
+                break;
+            } else {
+                const float ux_light = lcg(&state), uy_light = lcg(&state);
+                const v3 p_light = vadd(vadd(light_position, V(ux_light * light_u.x, ux_light * light_u.y, ux_light * light_u.z)),
+                                        V(uy_light * light_v.x, uy_light * light_v.y, uy_light * light_v.z));
+                const v3 pp_light = voffset(p_light, light_normal);
+                const float d_light = vlength(vsub(pp, pp_light));
+                const v3 wi_light = vnormalize(vsub(pp_light, pp));
+                const v3 so = voffset(pp, n);
+                oracle_ray sr = {{so.x, so.y, so.z}, 0.0f, {wi_light.x, wi_light.y, wi_light.z}, d_light};
+                const int occluded = (int)any_one(s, &sr, 0xffu, pt->mode);
+                n_any++;
+                const float cos_wi_light = vdot(wi_light, n);
+                const float cos_light = -vdot(light_normal, wi_light);
+                if (!occluded && cos_wi_light > 1e-4f && cos_light > 1e-4f) {
+                    const float pdf_light = (d_light * d_light) / (light_area * cos_light);
+                    const float pdf_b = cos_wi_light * FRAC_1_PI;
+                    const float mis_weight = pdf_light / fmaxf(pdf_light + pdf_b, 1e-4f);
+                    const v3 bsdf = vscale(vscale(albedo, FRAC_1_PI), cos_wi_light);
+                    radiance = vadd(radiance, vdiv(vmul(vscale(vmul(beta, bsdf), mis_weight), light_emission), fmaxf(pdf_light, 1e-4f)));
+                }
+            }
+            const v3 binormal = fabsf(n.x) > fabsf(n.z) ? V(-n.y, n.x, 0.0f) : V(0.0f, -n.z, n.y);
+            const v3 tangent = vnormalize(vcross(binormal, n));
+            const float ux = lcg(&state), uy = lcg(&state);
+            const float rr0 = sqrtf(ux);
+            float sphi, cphi;
+            sincos_2pi(uy, &sphi, &cphi);
+            const v3 local = V(rr0 * cphi, rr0 * sphi, sqrtf(1.0f - ux));
+            const v3 new_direction = vadd(vadd(vscale(tangent, local.x), vscale(binormal, local.y)), vscale(n, local.z));
+            ray_o = pp; ray_d = new_direction; ray_tmin = 0.0f; ray_tmax = F32_MAX;
+            beta = vmul(beta, albedo);
+            pdf_bsdf = cos_wi * FRAC_1_PI;
+            const float l = vdot(V(0.212671f, 0.715160f, 0.072169f), beta);
+            if (l == 0.0f) break;
+            const float q = fmaxf(l, 0.05f);
+            const float rr = lcg(&state);
+            if (rr > q) break;
+            beta = vdiv(beta, q);
+            depth += 1;
+        }
+    }
+    radiance = vdiv(radiance, (float)pt->spp);
+    pt->seeds[pixel] = state;
+    if (isnan(radiance.x) || isnan(radiance.y) || isnan(radiance.z)) radiance = V(0.f, 0.f, 0.f);
+    radiance = V(fminf(fmaxf(radiance.x, 0.0f), 30.0f), fminf(fmaxf(radiance.y, 0.0f), 30.0f), fminf(fmaxf(radiance.z, 0.0f), 30.0f));
+    float *px4 = pt->image + 4 * pixel;
+    px4[0] = radiance.x + px4[0]; px4[1] = radiance.y + px4[1]; px4[2] = radiance.z + px4[2]; px4[3] = px4[3] + 1.0f;
+    __atomic_fetch_add(&pt->n_closest, n_closest, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&pt->n_any, n_any, __ATOMIC_RELAXED);
+}
+
+void oracle_path_tracer(const oracle_scene *s, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
+                        uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, int threads,
+                        uint64_t ray_counts_out[2]) {
+    struct pt_job pt = {vertex_heap, index_heap, image_rgba, seed_image, width, height, spp_per_dispatch, max_depth, tan_half_fov, 1, 0, 0};
+    job j = {s, NULL, (uint64_t)width * height, 0xff, 1, 4, NULL, NULL, NULL, 0, NULL, NULL, 0, &pt};
+    run(&j, threads);
+    if (ray_counts_out) { ray_counts_out[0] = pt.n_closest; ray_counts_out[1] = pt.n_any; }
 }

@@ -86,6 +86,14 @@ typedef struct oracle_filter { int kind; float radius; const uint32_t *bits; con
 void oracle_ray_query(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
                       oracle_committed_hit *out, int mode, int threads);
 
+/* CPU restatement of the kernel of luisa_compute/examples/path_tracer.rs:247-455 over this oracle's trace functions (one
+ * dispatch: spp_per_dispatch samples per pixel, image += radiance, w += 1, seeds advanced).  Same operation order as
+ * luisa-compute-rs_b200/csrc/path_tracer.cu (which is compiled without FMA contraction), same fixed sin/cos polynomial,
+ * so the two images agree bit for bit.  vertex_heap[i] / index_heap[i]: tightly packed [f32;3] / [u32;3] of instance i. */
+void oracle_path_tracer(const oracle_scene *, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
+                        uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, int threads,
+                        uint64_t ray_counts_out[2]);
+
 /* Double-precision ground truth.  ambiguous[i] (may be NULL) is set to 1 when the fp32
  * answer is not forced: a second candidate lies within rel 1e-6 of the closest t, or some
  * triangle's nearest barycentric (hit or near miss, |b| < 1e-5) is within rounding of an edge

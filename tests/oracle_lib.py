@@ -46,6 +46,8 @@ def lib():
         L.oracle_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
         L.oracle_trace_closest_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_ray_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(Filter), C.c_void_p, C.c_int, C.c_int]
+        L.oracle_path_tracer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
+                                         C.c_int, C.POINTER(C.c_uint64)]
         L.oracle_offset_ray_origin.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.oracle_canonical_triangle.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float] + [C.POINTER(C.c_float)] * 6
         L.oracle_canonical_triangle.restype = C.c_int
@@ -141,6 +143,17 @@ def scene_from_desc(desc):
         mods.append(dict(index=k, user_id=inst["user_id"], flags=flags, visibility=inst["mask"], mesh=ids[inst["mesh"]], affine=inst["transform"].reshape(12)))
     o.update(len(desc.instances), mods)
     return o
+
+
+def path_tracer_dispatch(oracle_scene, meshes, image, seeds, width, height, spp, max_depth, tan_half_fov, threads=0):
+    """One dispatch of the CPU restatement of examples/path_tracer.rs; `image` (h,w,4 float32) and `seeds` (h*w uint32) are updated in place."""
+    vs = [np.ascontiguousarray(v, np.float32) for v, _ in meshes]
+    ts = [np.ascontiguousarray(t, np.uint32) for _, t in meshes]
+    vh = (C.c_void_p * len(vs))(*[v.ctypes.data for v in vs])
+    ih = (C.c_void_p * len(ts))(*[t.ctypes.data for t in ts])
+    counts = (C.c_uint64 * 2)()
+    lib().oracle_path_tracer(oracle_scene.s, vh, ih, image.ctypes.data, seeds.ctypes.data, width, height, spp, max_depth, float(tan_half_fov), threads, counts)
+    return counts[0], counts[1]
 
 
 def offset_ray_origin(p, n):

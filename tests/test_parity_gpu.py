@@ -345,6 +345,34 @@ def test_ray_query_candidates_and_opaque_instances(device):
     d.destroy(); o.close()
 
 
+def test_c2_path_tracer_image_is_bit_identical_to_the_cpu_restatement(device):
+    """Config C2: the kernel of examples/path_tracer.rs (hand-lowered, csrc/path_tracer.cu, per-thread trace_closest / trace_any)
+    against its CPU restatement over the oracle: same LCG streams, same operation order -> identical accumulation image, seeds and ray counts."""
+    import luisa_compute_rs_b200.examples as ex
+    desc = scenes.c2_cornell()
+    w, h, spp, dispatches = 160, 128, 8, 3
+    pt = ex.PathTracer(device, desc.meshes, w, h)
+    o = ol.scene_from_desc(desc)
+    img = np.zeros((h, w, 4), np.float32); seeds = ex.seed_image(w, h)
+    cpu_rays = [0, 0]
+    for _ in range(dispatches):
+        pt.dispatch(spp, ex.MAX_DEPTH)
+        c = ol.path_tracer_dispatch(o, desc.meshes, img, seeds, w, h, spp, ex.MAX_DEPTH, ex.TAN_HALF_FOV)
+        cpu_rays[0] += c[0]; cpu_rays[1] += c[1]
+    got_img, got_seeds = pt.download()
+    assert np.array_equal(got_seeds, seeds)
+    assert pt.rays == cpu_rays and cpu_rays[0] > w * h * spp * dispatches
+    assert np.array_equal(got_img.view(np.uint32), img.view(np.uint32)), f"{(got_img != img).any(axis=2).sum()} of {w * h} pixels differ"
+    rgb = got_img[..., :3] / got_img[..., 3:4]
+    assert np.all(got_img[..., 3] == dispatches) and 0.05 < rgb.mean() < 1.0 and not np.isnan(rgb).any()
+    # depth knob (BASELINE.json quotes depth 5; the example's loop bound is 10): still identical
+    pt2 = ex.PathTracer(device, desc.meshes, 64, 64)
+    img2 = np.zeros((64, 64, 4), np.float32); seeds2 = ex.seed_image(64, 64)
+    pt2.dispatch(4, 5); ol.path_tracer_dispatch(o, desc.meshes, img2, seeds2, 64, 64, 4, 5, ex.TAN_HALF_FOV)
+    assert np.array_equal(pt2.download()[0].view(np.uint32), img2.view(np.uint32))
+    pt.destroy(); pt2.destroy(); o.close()
+
+
 def test_stream_ordering_events_and_callbacks(device):
     s1, s2 = device.create_stream(), device.create_stream()
     a = device.create_buffer(1 << 16, 4); b = device.create_buffer(1 << 16, 4)
