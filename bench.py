@@ -146,6 +146,24 @@ def run_reference(args, rank):
     }))
 
 
+NCU_SUMMARY = "profiles/r01g_k_trace_ncu_full_summary.csv"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_trace<closest> per launch on this workload, from the committed
+    `ncu --set full` capture of `bench.py --profile` (bytes); None if the summary is not there."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, NCU_SUMMARY)):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * scale[f[1]]
+        return tot or None
+    except OSError:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,8 +282,8 @@ def main():
         peak, how = measured_peaks()
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         build_bytes = 12 * args.tris + 12 * verts.shape[0] + mstats["bvh_bytes"]
-        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                           "peak_source": how, "kernel": "k_trace<closest>", "algorithmic_bytes_per_launch": int(algo_bytes),
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                           "traffic_source": NCU_SUMMARY, "peak_source": how, "kernel": "k_trace<closest>", "algorithmic_bytes_per_launch": int(algo_bytes),
                            "nodes_per_ray": ctr["nodes_visited"] / n, "tris_per_ray": ctr["tris_tested"] / n,
                            "note": "logical (L1/L2-inclusive) bytes per SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test",
                            "build_achieved_gbs": build_bytes / (min(build_ms) * 1e-3) / 1e9, "build_frac": build_bytes / (min(build_ms) * 1e-3) / 1e9 / peak}
