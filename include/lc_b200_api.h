@@ -398,6 +398,21 @@ LCB_EXPORT const char *lc_b200_version(void);
  * and lives for the process. */
 LCB_EXPORT const void *lc_b200_make_ir_type(size_t size, size_t alignment);
 
+/* ---- IR -> CUDA lowering (create_shader), inspection entry points --------------------------------------------------
+ * create_shader(LCKernelModule{ptr}) lowers the frontend's SSA IR (`*const ir::KernelModule`, proxy.rs:188-193;
+ * layouts LC/include/luisa/rust/ir.hpp) to CUDA C++ whose ray-tracing builtins call this library's traversal
+ * routines, compiles it with NVRTC for sm_100a and launches it on ShaderDispatch — the job of
+ * cpu/codegen/cpp.rs + cpu/shader.rs + cpu/stream.rs:330-440 in the reference.  These three calls expose the
+ * stages for tests and tooling; none of them needs a GPU.
+ *   lc_b200_ir_lower_source      : the generated translation unit (malloc'd; release with LibInterface.free_string)
+ *   lc_b200_shader_compile_check : lower + NVRTC compile without loading; returns 0 on success, *log (malloc'd)
+ *                                  carries the lowering diagnostic or the NVRTC log
+ *   lc_b200_ir_layout_json       : sizeof / offsetof / discriminants of this library's view of the IR
+ *                                  (compared against the reference header's, tests/golden/ir_layout_reference.json) */
+LCB_EXPORT char *lc_b200_ir_lower_source(const void *kernel_module);
+LCB_EXPORT int lc_b200_shader_compile_check(const void *kernel_module, bool fast_math, char **log);
+LCB_EXPORT const char *lc_b200_ir_layout_json(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,8 +74,83 @@ class CmdAccelBuild(C.Structure):
                 ("update_instance_buffer_only", C.c_bool)]
 
 
+class CmdBufferTexture(C.Structure):
+    """BufferToTextureCopyCommand / TextureToBufferCopyCommand (api_types:516-541)"""
+    _fields_ = [("buffer", Handle), ("buffer_offset", C.c_size_t), ("texture", Handle), ("storage", C.c_int32), ("level", C.c_uint32), ("size", C.c_uint32 * 3)]
+
+
+class CmdTextureTransfer(C.Structure):
+    """TextureUploadCommand / TextureDownloadCommand (api_types:543-566)"""
+    _fields_ = [("texture", Handle), ("storage", C.c_int32), ("level", C.c_uint32), ("size", C.c_uint32 * 3), ("data", C.c_void_p)]
+
+
+class CmdTextureCopy(C.Structure):
+    _fields_ = [("storage", C.c_int32), ("src", Handle), ("dst", Handle), ("size", C.c_uint32 * 3), ("src_level", C.c_uint32), ("dst_level", C.c_uint32)]
+
+
+class _ArgBuffer(C.Structure):
+    _fields_ = [("buffer", Handle), ("offset", C.c_size_t), ("size", C.c_size_t)]
+
+
+class _ArgTexture(C.Structure):
+    _fields_ = [("texture", Handle), ("level", C.c_uint32)]
+
+
+class _ArgUniform(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+class _ArgUnion(C.Union):
+    _fields_ = [("buffer", _ArgBuffer), ("texture", _ArgTexture), ("uniform", _ArgUniform), ("bindless", Handle), ("accel", Handle)]
+
+
+class Argument(C.Structure):
+    """api_types Argument (lib.rs:454-484)"""
+    _fields_ = [("tag", C.c_int32), ("u", _ArgUnion)]
+
+
+ARG_BUFFER, ARG_TEXTURE, ARG_UNIFORM, ARG_BINDLESS, ARG_ACCEL = range(5)
+
+
+class CmdShaderDispatch(C.Structure):
+    _fields_ = [("shader", Handle), ("dispatch_size", C.c_uint32 * 3), ("args", C.POINTER(Argument)), ("args_count", C.c_size_t)]
+
+
+class Sampler(C.Structure):
+    _fields_ = [("filter", C.c_int32), ("address", C.c_int32)]
+
+
+class BindlessBufferUpdate(C.Structure):
+    _fields_ = [("op", C.c_int32), ("handle", Handle), ("offset", C.c_size_t)]
+
+
+class BindlessTextureUpdate(C.Structure):
+    _fields_ = [("op", C.c_int32), ("handle", Handle), ("sampler", Sampler)]
+
+
+class BindlessModification(C.Structure):
+    """BindlessArrayUpdateModification (api_types:697-704)"""
+    _fields_ = [("slot", C.c_size_t), ("buffer", BindlessBufferUpdate), ("tex2d", BindlessTextureUpdate), ("tex3d", BindlessTextureUpdate)]
+
+
+BINDLESS_NONE, BINDLESS_EMPLACE, BINDLESS_REMOVE = 0, 1, 2
+
+
+class CmdBindlessUpdate(C.Structure):
+    _fields_ = [("handle", Handle), ("modifications", C.POINTER(BindlessModification)), ("modifications_count", C.c_size_t)]
+
+
+class ShaderOption(C.Structure):
+    """api_types ShaderOption (lib.rs:828-846)"""
+    _fields_ = [("enable_cache", C.c_bool), ("enable_fast_math", C.c_bool), ("enable_debug_info", C.c_bool), ("compile_only", C.c_bool), ("time_trace", C.c_bool),
+                ("max_registers", C.c_uint32), ("name", C.c_char_p), ("native_include", C.c_char_p)]
+
+
 class _CmdUnion(C.Union):
     _fields_ = [("buffer_upload", CmdBufferUpload), ("buffer_download", CmdBufferDownload), ("buffer_copy", CmdBufferCopy),
+                ("buffer_to_texture", CmdBufferTexture), ("texture_to_buffer", CmdBufferTexture), ("texture_upload", CmdTextureTransfer),
+                ("texture_download", CmdTextureTransfer), ("texture_copy", CmdTextureCopy), ("shader_dispatch", CmdShaderDispatch),
+                ("bindless_update", CmdBindlessUpdate),
                 ("mesh_build", CmdMeshBuild), ("accel_build", CmdAccelBuild), ("_raw", C.c_uint8 * 80)]
 
 
@@ -85,8 +160,10 @@ class Command(C.Structure):
 
 assert C.sizeof(Command) == 88 and Command.u.offset == 8
 assert C.sizeof(AccelModification) == 72 and C.sizeof(AccelOption) == 8
+assert C.sizeof(Argument) == 32 and C.sizeof(BindlessModification) == 80 and C.sizeof(CmdShaderDispatch) == 40
 
 CMD_BUFFER_UPLOAD, CMD_BUFFER_DOWNLOAD, CMD_BUFFER_COPY = 0, 1, 2
+CMD_BUFFER_TO_TEXTURE, CMD_TEXTURE_TO_BUFFER, CMD_TEXTURE_DOWNLOAD, CMD_TEXTURE_COPY = 3, 4, 6, 7
 CMD_TEXTURE_UPLOAD, CMD_SHADER_DISPATCH, CMD_MESH_BUILD, CMD_CURVE_BUILD, CMD_PROCEDURAL_BUILD, CMD_ACCEL_BUILD, CMD_BINDLESS_UPDATE = 5, 8, 9, 10, 11, 12, 13
 
 MOD_PRIMITIVE, MOD_TRANSFORM, MOD_OPAQUE_ON, MOD_OPAQUE_OFF, MOD_VISIBILITY, MOD_USER_ID = 1, 2, 4, 8, 16, 32
@@ -191,7 +268,7 @@ EXPORTED_SYMBOLS = [
     "lc_b200_trace_any_host", "lc_b200_instance_transform", "lc_b200_instance_user_id", "lc_b200_instance_visibility_mask",
     "lc_b200_mesh_stats", "lc_b200_accel_stats", "lc_b200_trace_closest_counted", "lc_b200_stream_native",
     "lc_b200_buffer_native", "lc_b200_device_ordinal", "lc_b200_kernel_launch_count", "lc_b200_version", "lc_b200_make_ir_type",
-    "lc_b200_ray_query", "lc_b200_example_path_tracer",
+    "lc_b200_ray_query", "lc_b200_example_path_tracer", "lc_b200_ir_lower_source", "lc_b200_shader_compile_check", "lc_b200_ir_layout_json",
 ]
 
 
@@ -262,6 +339,12 @@ def load_library(path=None):
     lib.lc_b200_version.restype = C.c_char_p
     lib.lc_b200_make_ir_type.argtypes = [C.c_size_t, C.c_size_t]
     lib.lc_b200_make_ir_type.restype = C.c_void_p
+    lib.lc_b200_ir_lower_source.argtypes = [C.c_void_p]
+    lib.lc_b200_ir_lower_source.restype = C.c_void_p
+    lib.lc_b200_shader_compile_check.argtypes = [C.c_void_p, C.c_bool, C.POINTER(C.c_void_p)]
+    lib.lc_b200_shader_compile_check.restype = C.c_int
+    lib.lc_b200_ir_layout_json.argtypes = []
+    lib.lc_b200_ir_layout_json.restype = C.c_char_p
     if path is None:
         _lib = lib
     return lib

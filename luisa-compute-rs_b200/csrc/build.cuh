@@ -66,13 +66,7 @@ void apply_instance_mods(cudaStream_t s, InstanceRec *table, const InstanceModRe
 // ---- trace.cu ------------------------------------------------------------------------------
 struct TraceCounters { unsigned long long nodes_visited, tris_tested, rays, instance_entries; };
 
-struct AccelView {
-    const WideNode *tlas_nodes;      // nullptr => empty accel
-    const uint32_t *tlas_prims;      // instance ids referenced by TLAS leaves
-    const InstanceRec *instances;
-    uint32_t instance_count;
-    float world_lo[3], world_hi[3];  // bounds of the TLAS root (ray reordering quantises origins against them)
-};
+// AccelView: rt_types.cuh (shared with NVRTC-compiled kernels)
 
 // Candidate hook of the batch RayQuery entry points (evaluated on device for triangles of non-opaque instances).
 struct CandidateFilter {

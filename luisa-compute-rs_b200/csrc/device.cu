@@ -9,6 +9,7 @@
 // Slots outside the hot path log "unsupported" and abort — there is no CPU fallback anywhere.
 #include "../../include/lc_b200_api.h"
 #include "build.cuh"
+#include "shader.h"
 
 #include <algorithm>
 #include <atomic>
@@ -20,6 +21,7 @@
 #include <deque>
 #include <map>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -152,6 +154,13 @@ struct AccelObj {
     lcb_build_stats stats{};
     std::mutex mu;
 };
+
+// Textures: one mip level, texels row-major in device memory (the CPU backend tiles its textures, cpu/texture.rs; uploads and
+// downloads present the same row-major image to the user either way).  storage = api PixelStorage (api_types:366-383).
+struct TextureObj { uint8_t *ptr = nullptr; uint32_t dim = 2, width = 1, height = 1, depth = 1; int32_t storage = 0; size_t pixel_bytes = 4, bytes = 0; };
+
+// Bindless arrays (cpu/resource.rs:60-124): a slot table mirrored on the host; BindlessArrayUpdate uploads touched slots.
+struct BindlessObj { std::vector<HostBindlessSlot> host; HostBindlessSlot *device = nullptr; std::mutex mu; };
 
 struct EventObj {
     std::mutex mu; std::condition_variable cv;
@@ -485,6 +494,10 @@ AccelView view_of(AccelObj *a) {
     return v;
 }
 
+size_t texture_region_bytes(const TextureObj *t, int32_t storage, uint32_t level, const uint32_t size[3], const char *what);
+void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &c);
+void bindless_update(StreamObj *s, const lcb_cmd_bindless_update &c);
+
 // ---- dispatch (RustBackend::dispatch + StreamImpl::dispatch, cpu/mod.rs:168-180, stream.rs:213-446) ----
 void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch_callback cb, uint8_t *ctx) {
     DeviceObj *d = dev_of(dev); bind(d);
@@ -513,11 +526,42 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
                 if (c.u.buffer_copy.size) CUDA_CHECK(cudaMemcpyAsync(dst->ptr + c.u.buffer_copy.dst_offset, src->ptr + c.u.buffer_copy.src_offset, c.u.buffer_copy.size, cudaMemcpyDeviceToDevice, st));
                 break;
             }
+            case LCB_CMD_TEXTURE_UPLOAD: {
+                TextureObj *t = as<TextureObj>(c.u.texture_upload.texture.id);
+                const size_t n = texture_region_bytes(t, c.u.texture_upload.storage, c.u.texture_upload.level, c.u.texture_upload.size, "TextureUpload");
+                if (n) CUDA_CHECK(cudaMemcpyAsync(t->ptr, c.u.texture_upload.data, n, cudaMemcpyHostToDevice, st));
+                break;
+            }
+            case LCB_CMD_TEXTURE_DOWNLOAD: {
+                TextureObj *t = as<TextureObj>(c.u.texture_download.texture.id);
+                const size_t n = texture_region_bytes(t, c.u.texture_download.storage, c.u.texture_download.level, c.u.texture_download.size, "TextureDownload");
+                if (n) CUDA_CHECK(cudaMemcpyAsync(c.u.texture_download.data, t->ptr, n, cudaMemcpyDeviceToHost, st));
+                break;
+            }
+            case LCB_CMD_TEXTURE_COPY: {
+                TextureObj *src = as<TextureObj>(c.u.texture_copy.src.id), *dst = as<TextureObj>(c.u.texture_copy.dst.id);
+                const size_t n = texture_region_bytes(src, c.u.texture_copy.storage, c.u.texture_copy.src_level, c.u.texture_copy.size, "TextureCopy(src)");
+                if (texture_region_bytes(dst, c.u.texture_copy.storage, c.u.texture_copy.dst_level, c.u.texture_copy.size, "TextureCopy(dst)") != n) fatal("TextureCopy: size mismatch");
+                if (n) CUDA_CHECK(cudaMemcpyAsync(dst->ptr, src->ptr, n, cudaMemcpyDeviceToDevice, st));
+                break;
+            }
+            case LCB_CMD_BUFFER_TO_TEXTURE: case LCB_CMD_TEXTURE_TO_BUFFER: {
+                const lcb_cmd_buffer_texture &bt = c.tag == LCB_CMD_BUFFER_TO_TEXTURE ? c.u.buffer_to_texture : c.u.texture_to_buffer;
+                BufferObj *b = as<BufferObj>(bt.buffer.id); TextureObj *t = as<TextureObj>(bt.texture.id);
+                const size_t n = texture_region_bytes(t, bt.storage, bt.level, bt.size, "Buffer<->Texture copy");
+                if (bt.buffer_offset + n > b->size) fatal("Buffer<->Texture copy: buffer range out of bounds");
+                if (n) {
+                    if (c.tag == LCB_CMD_BUFFER_TO_TEXTURE) CUDA_CHECK(cudaMemcpyAsync(t->ptr, b->ptr + bt.buffer_offset, n, cudaMemcpyDeviceToDevice, st));
+                    else CUDA_CHECK(cudaMemcpyAsync(b->ptr + bt.buffer_offset, t->ptr, n, cudaMemcpyDeviceToDevice, st));
+                }
+                break;
+            }
+            case LCB_CMD_SHADER_DISPATCH: shader_dispatch(d, s, c.u.shader_dispatch); break;
+            case LCB_CMD_BINDLESS_UPDATE: bindless_update(s, c.u.bindless_update); break;
             case LCB_CMD_MESH_BUILD: mesh_build(d, s, c.u.mesh_build); break;
             case LCB_CMD_ACCEL_BUILD: accel_build(d, s, c.u.accel_build); break;
             default:
-                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: textures, bindless arrays, shader dispatch, "
-                      "curves and procedural primitives are \"next\" rows)", c.tag);
+                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: curves and procedural primitives are \"next\" rows)", c.tag);
         }
     }
     flush_launches(d);
@@ -583,17 +627,144 @@ void destroy_accel(lcb_device dev, lcb_accel h) {
     delete a;
 }
 
+// ---- textures (cpu/texture.rs, cpu/mod.rs:85-120) ---------------------------------------------------------------------
+int32_t format_to_storage(int32_t format) {  // PixelFormat::storage, api_types:345-385
+    static const int8_t map[30] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 10, 11, 12, 13, 14};
+    if (format < 0 || format >= 30) fatal("pixel format %d (packed / block-compressed) is not supported by the B200 device", format);
+    return map[format];
+}
+size_t storage_pixel_bytes(int32_t storage) {  // PixelStorage::size, api_types:285-306
+    static const size_t sz[15] = {1, 2, 4, 2, 4, 8, 4, 8, 16, 2, 4, 8, 4, 8, 16};
+    if (storage < 0 || storage >= 15) fatal("pixel storage %d is not supported by the B200 device", storage);
+    return sz[storage];
+}
+lcb_created create_texture(lcb_device dev, int32_t format, uint32_t dim, uint32_t w, uint32_t h, uint32_t d, uint32_t mips, bool, bool) {
+    DeviceObj *dv = dev_of(dev); bind(dv);
+    if (dim != 2 && dim != 3) fatal("create_texture: dimension must be 2 or 3 (got %u)", dim);
+    if (mips > 1) fatal("create_texture: mipmapped textures are outside the ray-tracing device's scope (got %u levels)", mips);
+    auto *t = new TextureObj;
+    t->dim = dim; t->width = w; t->height = h; t->depth = dim == 2 ? 1 : d;
+    t->storage = format_to_storage(format); t->pixel_bytes = storage_pixel_bytes(t->storage);
+    t->bytes = (size_t)t->width * t->height * t->depth * t->pixel_bytes;
+    CUDA_CHECK(cudaMalloc(&t->ptr, t->bytes ? t->bytes : 16));
+    CUDA_CHECK(cudaMemset(t->ptr, 0, t->bytes ? t->bytes : 16));
+    return lcb_created{(uint64_t)t, t->ptr};
+}
+void destroy_texture(lcb_device dev, lcb_texture h) { bind(dev_of(dev)); TextureObj *t = as<TextureObj>(h.id); cudaFree(t->ptr); delete t; }
+size_t texture_region_bytes(const TextureObj *t, int32_t storage, uint32_t level, const uint32_t size[3], const char *what) {
+    if (level != 0) fatal("%s: mip level %u of a single-level texture", what, level);
+    if (storage != t->storage) fatal("%s: storage %d does not match the texture's storage %d", what, storage, t->storage);
+    if (size[0] != t->width || size[1] != t->height || (t->dim == 3 && size[2] != t->depth)) fatal("%s: region %ux%ux%u is not the whole level (%ux%ux%u)", what, size[0], size[1], size[2], t->width, t->height, t->depth);
+    return t->bytes;
+}
+HostTextureArg texture_arg(const TextureObj *t) { return HostTextureArg{t->ptr, t->width, t->height, t->depth, (uint32_t)t->storage}; }
+
+// ---- bindless arrays -------------------------------------------------------------------------------------------------------
+lcb_created create_bindless_array(lcb_device dev, size_t size) {
+    bind(dev_of(dev));
+    auto *b = new BindlessObj;
+    b->host.assign(size, HostBindlessSlot{});
+    CUDA_CHECK(cudaMalloc((void **)&b->device, (size ? size : 1) * sizeof(HostBindlessSlot)));
+    CUDA_CHECK(cudaMemset(b->device, 0, (size ? size : 1) * sizeof(HostBindlessSlot)));
+    return lcb_created{(uint64_t)b, b->device};
+}
+void destroy_bindless_array(lcb_device dev, lcb_bindless h) { bind(dev_of(dev)); BindlessObj *b = as<BindlessObj>(h.id); cudaFree(b->device); delete b; }
+void bindless_update(StreamObj *s, const lcb_cmd_bindless_update &c) {  // BindlessArrayImpl::update, cpu/resource.rs:76-124
+    BindlessObj *b = as<BindlessObj>(c.handle.id);
+    std::lock_guard<std::mutex> lk(b->mu);
+    size_t lo = SIZE_MAX, hi = 0;
+    for (size_t i = 0; i < c.modifications_count; i++) {
+        const lcb_bindless_modification &m = c.modifications[i];
+        if (m.slot >= b->host.size()) fatal("BindlessArrayUpdate: slot %zu out of range (%zu slots)", m.slot, b->host.size());
+        HostBindlessSlot &slot = b->host[m.slot];
+        if (m.buffer.op == 1) {
+            BufferObj *buf = as<BufferObj>(m.buffer.handle.id);
+            if (m.buffer.offset > buf->size) fatal("BindlessArrayUpdate: buffer offset beyond the buffer");
+            slot.buffer = buf->ptr + m.buffer.offset; slot.buffer_size = buf->size - m.buffer.offset;
+        } else if (m.buffer.op == 2) { slot.buffer = nullptr; slot.buffer_size = 0; }
+        if (m.tex2d.op == 1) slot.tex2d = texture_arg(as<TextureObj>(m.tex2d.handle.id)); else if (m.tex2d.op == 2) slot.tex2d = HostTextureArg{};
+        if (m.tex3d.op == 1) slot.tex3d = texture_arg(as<TextureObj>(m.tex3d.handle.id)); else if (m.tex3d.op == 2) slot.tex3d = HostTextureArg{};
+        lo = std::min(lo, m.slot); hi = std::max(hi, m.slot + 1);
+    }
+    if (lo < hi)  // pageable source: staged before the call returns, the host table may change right after
+        CUDA_CHECK(cudaMemcpyAsync(b->device + lo, b->host.data() + lo, (hi - lo) * sizeof(HostBindlessSlot), cudaMemcpyHostToDevice, s->stream));
+}
+
+// ---- shaders (ShaderImpl, cpu/shader.rs; dispatch cpu/stream.rs:330-440) ------------------------------------------------------
+lcb_created_shader create_shader(lcb_device dev, lcb_kernel_module km, const lcb_shader_option *opt) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    std::string log;
+    ShaderObj *s = nullptr;
+    try {
+        s = shader_create(reinterpret_cast<const ir::KernelModule *>(km.ptr), opt && opt->enable_fast_math, opt && opt->compile_only, opt ? opt->name : nullptr, log);
+    } catch (const std::exception &e) { fatal("create_shader: %s", e.what()); }
+    if (!log.empty()) log_msg("W", "create_shader: NVRTC log:\n%s", log.c_str());
+    lcb_created_shader out{};
+    out.resource.handle = (uint64_t)s; out.resource.native_handle = s;
+    for (int k = 0; k < 3; k++) out.block_size[k] = shader_lowered(s).block_size[k];
+    return out;
+}
+void destroy_shader(lcb_device dev, lcb_shader h) { bind(dev_of(dev)); shader_destroy(as<ShaderObj>(h.id)); }
+
+AccelView view_of(AccelObj *a);
+void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &c) {
+    ShaderObj *sh = as<ShaderObj>(c.shader.id);
+    const LoweredKernel &k = shader_lowered(sh);
+    if (c.args_count != k.args.size()) fatal("ShaderDispatch: %zu arguments given, the kernel takes %zu (runtime.rs:1517)", c.args_count, k.args.size());
+    std::vector<uint8_t> block(k.param_bytes, 0);
+    HostLaunch launch{{c.dispatch_size[0], c.dispatch_size[1], c.dispatch_size[2]}, 0};
+    memcpy(block.data(), &launch, sizeof(launch));
+    auto put_buffer = [&](const ParamSlot &p, uint64_t handle, size_t offset, size_t size) {
+        BufferObj *b = as<BufferObj>(handle);
+        if (offset + size > b->size) fatal("ShaderDispatch: buffer view [%zu, +%zu) exceeds the buffer (%zu bytes)", offset, size, b->size);
+        HostBufferArg a{b->ptr + offset, size}; memcpy(block.data() + p.offset, &a, sizeof(a));
+    };
+    auto put_texture = [&](const ParamSlot &p, uint64_t handle, uint32_t level) {
+        if (level != 0) fatal("ShaderDispatch: texture level %u of a single-level texture", level);
+        HostTextureArg a = texture_arg(as<TextureObj>(handle)); memcpy(block.data() + p.offset, &a, sizeof(a));
+    };
+    auto put_bindless = [&](const ParamSlot &p, uint64_t handle) {
+        BindlessObj *b = as<BindlessObj>(handle);
+        HostBindlessArg a{b->device, b->host.size()}; memcpy(block.data() + p.offset, &a, sizeof(a));
+    };
+    auto put_accel = [&](const ParamSlot &p, uint64_t handle) {
+        AccelObj *ao = as<AccelObj>(handle);
+        HostAccelArg a{view_of(ao), ao->table}; memcpy(block.data() + p.offset, &a, sizeof(a));
+    };
+    for (const ParamSlot &p : k.captures) {  // bound at create_shader time (KernelModule.captures, cpu/mod.rs:296-301)
+        switch (p.kind) {
+            case ParamSlot::Buffer: put_buffer(p, p.binding.buffer.handle, p.binding.buffer.offset, p.binding.buffer.size); break;
+            case ParamSlot::Texture: put_texture(p, p.binding.texture.handle, p.binding.texture.level); break;
+            case ParamSlot::Bindless: put_bindless(p, p.binding.bindless_array); break;
+            case ParamSlot::Accel: put_accel(p, p.binding.accel); break;
+            default: fatal("ShaderDispatch: bad capture kind");
+        }
+    }
+    for (size_t i = 0; i < k.args.size(); i++) {
+        const ParamSlot &p = k.args[i];
+        const lcb_argument &a = c.args[i];
+        static const int want[5] = {LCB_ARG_BUFFER, LCB_ARG_TEXTURE, LCB_ARG_BINDLESS, LCB_ARG_ACCEL, LCB_ARG_UNIFORM};
+        if (a.tag != want[p.kind]) fatal("ShaderDispatch: argument %zu has tag %d, the kernel expects %d", i, a.tag, want[p.kind]);
+        switch (p.kind) {
+            case ParamSlot::Buffer: put_buffer(p, a.u.buffer.buffer.id, a.u.buffer.offset, a.u.buffer.size); break;
+            case ParamSlot::Texture: put_texture(p, a.u.texture.texture.id, a.u.texture.level); break;
+            case ParamSlot::Bindless: put_bindless(p, a.u.bindless.id); break;
+            case ParamSlot::Accel: put_accel(p, a.u.accel.id); break;
+            case ParamSlot::Uniform:
+                if (a.u.uniform.size != p.size) fatal("ShaderDispatch: uniform %zu has %zu bytes, the kernel expects %zu", i, a.u.uniform.size, p.size);
+                memcpy(block.data() + p.offset, a.u.uniform.data, p.size);
+                break;
+        }
+    }
+    try { shader_launch(sh, s->stream, block.data(), c.dispatch_size); } catch (const std::exception &e) { fatal("ShaderDispatch: %s", e.what()); }
+    d->lc.count++;
+}
+
 // ---- out-of-scope slots: loud failure -------------------------------------------------------------
 #define UNSUPPORTED(what) fatal("%s is outside the B200 ray-tracing device's scope (SURVEY.md §8: hot path only; no fallback)", what)
-lcb_created create_texture(lcb_device, int32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, bool, bool) { UNSUPPORTED("create_texture"); }
-void destroy_texture(lcb_device, lcb_texture) { UNSUPPORTED("destroy_texture"); }
-lcb_created create_bindless_array(lcb_device, size_t) { UNSUPPORTED("create_bindless_array"); }
-void destroy_bindless_array(lcb_device, lcb_bindless) { UNSUPPORTED("destroy_bindless_array"); }
 lcb_created_swapchain create_swapchain(lcb_device, const lcb_swapchain_option *, lcb_stream) { UNSUPPORTED("create_swapchain"); }
 void present_display_in_stream(lcb_device, lcb_stream, lcb_swapchain, lcb_texture) { UNSUPPORTED("present_display_in_stream"); }
 void destroy_swapchain(lcb_device, lcb_swapchain) { UNSUPPORTED("destroy_swapchain"); }
-lcb_created_shader create_shader(lcb_device, lcb_kernel_module, const lcb_shader_option *) { UNSUPPORTED("create_shader (IR -> CUDA lowering, SURVEY.md §8f rank 1)"); }
-void destroy_shader(lcb_device, lcb_shader) { UNSUPPORTED("destroy_shader"); }
 lcb_created create_curve(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_curve"); }
 void destroy_curve(lcb_device, lcb_curve) { UNSUPPORTED("destroy_curve"); }
 lcb_created create_procedural_primitive(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_procedural_primitive"); }
@@ -856,6 +1027,22 @@ void *lc_b200_buffer_native(lcb_device, lcb_buffer h) { return as<BufferObj>(h.i
 int lc_b200_device_ordinal(lcb_device dev) { return dev_of(dev)->ordinal; }
 uint64_t lc_b200_kernel_launch_count(void) { return g_launches.load(); }
 const char *lc_b200_version(void) { return "lc_b200 0.1 (sm_100a; LBVH + 8-wide quantised BVH; canonical fp32 watertight)"; }
+
+// The CUDA source the lowering produces for a KernelModule (malloc'd; release with free_string).  No GPU needed.
+char *lc_b200_ir_lower_source(const void *kernel_module) {
+    LoweredKernel k;
+    try { lower_kernel(reinterpret_cast<const ir::KernelModule *>(kernel_module), k); } catch (const std::exception &e) { fatal("%s", e.what()); }
+    char *out = (char *)malloc(k.source.size() + 1); memcpy(out, k.source.c_str(), k.source.size() + 1); return out;
+}
+// Lower + NVRTC-compile without loading the module (no GPU needed).  Returns 0 on success; *log (malloc'd, may be empty) holds the
+// lowering diagnostic or the NVRTC log.
+int lc_b200_shader_compile_check(const void *kernel_module, bool fast_math, char **log) {
+    std::string l; int rc = 0;
+    try { ShaderObj *s = shader_create(reinterpret_cast<const ir::KernelModule *>(kernel_module), fast_math, true, nullptr, l); shader_destroy(s); }
+    catch (const std::exception &e) { l = e.what(); rc = 1; }
+    if (log) { *log = (char *)malloc(l.size() + 1); memcpy(*log, l.c_str(), l.size() + 1); }
+    return rc;
+}
 
 const void *lc_b200_make_ir_type(size_t size, size_t alignment) {
     // leaked on purpose: type blocks live for the process, like the frontend's interned types

@@ -1,0 +1,869 @@
+// ir_lower.cpp — lowering of the frontend's SSA IR (ir::KernelModule) to CUDA C++ for NVRTC.
+//
+// Row 9 of SURVEY.md §8a / rank 1 of §8f: the reference reaches the ray-tracing hot path from DSL kernel bodies through
+// generated code — cpu/codegen/cpp.rs walks the IR and prints C++ whose RT builtins call the Accel vtable
+// (cpp.rs:1334-1472).  This file is the B200 counterpart: it walks the same IR (layouts: ir_layout.h) and prints one CUDA
+// translation unit against lc_device_lib.cuh, in which RayTracingTraceClosest / TraceAny become calls to the per-thread
+// traversal of trace_device.cuh.  Structure mirrored from the reference so results can be compared construct by construct:
+//   * one `const T` per value node, locals as mutable variables, GetElementPtr as C++ references (cpp.rs:1022-1029 uses pointers);
+//   * phi nodes are forward-declared at function top and assigned at the end of every incoming block (cpp.rs:1882-1910);
+//   * GenericLoop lowers to `for(;;){ prepare; if(!cond) break; do { body } while(false); if(loop_break) break; update; }`
+//     with Break = {loop_break = true; break;} and Continue = break (cpp.rs:1700-1743);
+//   * callables become __device__ functions taking by-value arguments as const references and by-reference arguments as
+//     references (cpp.rs:412-510), deduplicated by module address;
+//   * captures are kernel parameters bound at create_shader time, arguments are bound per dispatch (cpp.rs:1928-1990).
+// Differences by design: kernel parameters travel as one by-value struct (lc_params) whose layout is computed here AND
+// static_assert-ed inside the generated source; Switch lowers to an if-chain so that Break keeps its loop meaning.
+#include "shader.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace lcb {
+namespace {
+
+using namespace ir;
+
+const char *const kFuncNames[] = {
+#define X(name) #name,
+#include "ir_funcs.inc"
+#undef X
+};
+
+[[noreturn]] void fail(const std::string &what) { throw std::runtime_error("IR lowering: " + what); }
+
+std::string slice_to_string(const Slice<uint8_t> &s) { return std::string(reinterpret_cast<const char *>(s.ptr), s.len ? (s.ptr[s.len - 1] == 0 ? s.len - 1 : s.len) : 0); }
+
+size_t prim_size(int32_t p) {
+    static const size_t sz[12] = {1, 1, 1, 2, 2, 4, 4, 8, 8, 2, 4, 8};
+    if (p < 0 || p >= 12) fail("bad primitive tag");
+    return sz[p];
+}
+const char *prim_c(int32_t p) {
+    static const char *n[12] = {"bool", "int8_t", "uint8_t", "int16_t", "uint16_t", "int32_t", "uint32_t", "int64_t", "uint64_t", nullptr, "float", "double"};
+    if (p < 0 || p >= 12) fail("bad primitive tag");
+    if (!n[p]) fail("Float16 values are not supported by the B200 lowering");
+    return n[p];
+}
+const char *prim_vec(int32_t p) {
+    static const char *n[12] = {"bool", "char", "uchar", "short", "ushort", "int", "uint", "long", "ulong", nullptr, "float", "double"};
+    if (!n[p]) fail("Float16 vectors are not supported by the B200 lowering");
+    return n[p];
+}
+bool prim_is_float(int32_t p) { return p == P_Float16 || p == P_Float32 || p == P_Float64; }
+
+// size / alignment rules of ir.rs:215-369
+size_t type_size(const Type *t);
+size_t type_align(const Type *t);
+int32_t vec_prim(const VectorElementType &e) {
+    if (e.tag != VectorElementType::Scalar) fail("vectors of vectors are not supported");
+    return e.scalar;
+}
+size_t type_size(const Type *t) {
+    switch (t->tag) {
+        case Type::Void: case Type::UserData: return 0;
+        case Type::Primitive: return prim_size(t->primitive);
+        case Type::Vector: { uint32_t n = t->vector.length; return prim_size(vec_prim(t->vector.element)) * (n == 3 ? 4 : n); }
+        case Type::Matrix: { uint32_t d = t->matrix.dimension; return prim_size(vec_prim(t->matrix.element)) * (d == 2 ? 2 : 4) * d; }
+        case Type::Struct: return t->struct_.size;
+        case Type::Array: return type_size(t->array.element.get()) * t->array.length;
+        default: fail("opaque types have no size");
+    }
+}
+size_t type_align(const Type *t) {
+    switch (t->tag) {
+        case Type::Void: case Type::UserData: return 1;
+        case Type::Primitive: return prim_size(t->primitive);
+        case Type::Vector: { uint32_t n = t->vector.length == 3 ? 4 : t->vector.length; size_t a = prim_size(vec_prim(t->vector.element)) * n; return a < 16 ? a : 16; }
+        case Type::Matrix: { uint32_t n = t->matrix.dimension == 3 ? 4 : t->matrix.dimension; size_t a = 4 * n; return a < 16 ? a : 16; }
+        case Type::Struct: return t->struct_.alignment;
+        case Type::Array: return type_align(t->array.element.get());
+        default: fail("opaque types have no alignment");
+    }
+}
+bool type_is_void(const Type *t) { return !t || t->tag == Type::Void; }
+bool type_is_bool(const Type *t) { return (t->tag == Type::Primitive && t->primitive == P_Bool) || (t->tag == Type::Vector && vec_prim(t->vector.element) == P_Bool); }
+bool type_is_float(const Type *t) {
+    return (t->tag == Type::Primitive && prim_is_float(t->primitive)) || (t->tag == Type::Vector && prim_is_float(vec_prim(t->vector.element))) || t->tag == Type::Matrix;
+}
+const Type *type_extract(const Type *t, size_t i) {  // ir.rs:313-323
+    switch (t->tag) {
+        case Type::Array: return t->array.element.get();
+        case Type::Struct: if (i >= t->struct_.fields.len) fail("struct field index out of range"); return t->struct_.fields[i].get();
+        default: return nullptr;  // vector / matrix elements are handled by the callers
+    }
+}
+
+struct TypeTable {
+    std::map<std::string, std::string> struct_names;  // structural key -> C++ name
+    std::string defs;
+    std::string name(const Type *t) {
+        if (!t) return "void";
+        switch (t->tag) {
+            case Type::Void: return "void";
+            case Type::Primitive: return prim_c(t->primitive);
+            case Type::Vector: {
+                if (t->vector.length < 2 || t->vector.length > 4) fail("vector length must be 2..4");
+                return std::string("lc_") + prim_vec(vec_prim(t->vector.element)) + std::to_string(t->vector.length);
+            }
+            case Type::Matrix: {
+                if (vec_prim(t->matrix.element) != P_Float32) fail("only f32 matrices exist (ir.rs:275-293)");
+                const std::string d = std::to_string(t->matrix.dimension);
+                return "lc_float" + d + "x" + d;
+            }
+            case Type::Array: return "lc_array<" + name(t->array.element.get()) + ", " + std::to_string(t->array.length) + ">";
+            case Type::Struct: {
+                std::string key = "{";
+                std::vector<std::string> fields;
+                for (const auto &f : t->struct_.fields) { fields.push_back(name(f.get())); key += fields.back() + ";"; }
+                key += "}a" + std::to_string(t->struct_.alignment) + "s" + std::to_string(t->struct_.size);
+                auto it = struct_names.find(key);
+                if (it != struct_names.end()) return it->second;
+                const std::string n = "lc_s" + std::to_string(struct_names.size());
+                struct_names[key] = n;
+                std::ostringstream o;
+                o << "struct alignas(" << t->struct_.alignment << ") " << n << " {\n";
+                for (size_t i = 0; i < fields.size(); i++) o << "    " << fields[i] << " f" << i << ";\n";
+                o << "};\nstatic_assert(sizeof(" << n << ") == " << t->struct_.size << ", \"struct layout differs from the IR's\");\n";
+                defs += o.str();
+                return n;
+            }
+            case Type::Opaque: fail("opaque type " + slice_to_string(t->opaque) + " (RayQuery objects inside DSL kernels are served by the batch entry point lc_b200_ray_query)");
+            default: fail("unsupported type tag " + std::to_string(t->tag));
+        }
+    }
+};
+
+std::string float_literal(float v) {
+    uint32_t b; memcpy(&b, &v, 4);
+    char buf[64]; snprintf(buf, sizeof(buf), "__uint_as_float(0x%08xu) /* %.9g */", b, (double)v);
+    return buf;
+}
+std::string double_literal(double v) {
+    uint64_t b; memcpy(&b, &v, 8);
+    char buf[96]; snprintf(buf, sizeof(buf), "__longlong_as_double(0x%016llxll) /* %.17g */", (unsigned long long)b, v);
+    return buf;
+}
+std::string prim_literal(int32_t p, const uint8_t *d) {
+    char buf[64];
+    switch (p) {
+        case P_Bool: return *d ? "true" : "false";
+        case P_Int8: snprintf(buf, sizeof(buf), "int8_t(%d)", (int)*(const int8_t *)d); return buf;
+        case P_Uint8: snprintf(buf, sizeof(buf), "uint8_t(%u)", (unsigned)*d); return buf;
+        case P_Int16: { int16_t v; memcpy(&v, d, 2); snprintf(buf, sizeof(buf), "int16_t(%d)", (int)v); return buf; }
+        case P_Uint16: { uint16_t v; memcpy(&v, d, 2); snprintf(buf, sizeof(buf), "uint16_t(%u)", (unsigned)v); return buf; }
+        case P_Int32: { int32_t v; memcpy(&v, d, 4); snprintf(buf, sizeof(buf), "int32_t(0x%08xu)", (unsigned)v); return buf; }
+        case P_Uint32: { uint32_t v; memcpy(&v, d, 4); snprintf(buf, sizeof(buf), "%uu", v); return buf; }
+        case P_Int64: { int64_t v; memcpy(&v, d, 8); snprintf(buf, sizeof(buf), "int64_t(0x%016llxull)", (unsigned long long)v); return buf; }
+        case P_Uint64: { uint64_t v; memcpy(&v, d, 8); snprintf(buf, sizeof(buf), "%lluull", (unsigned long long)v); return buf; }
+        case P_Float32: { float v; memcpy(&v, d, 4); return float_literal(v); }
+        case P_Float64: { double v; memcpy(&v, d, 8); return double_literal(v); }
+        default: fail("Float16 constants are not supported");
+    }
+}
+
+// Const::Generic payload -> C++ expression (the reference: codegen/mod.rs decode_const_data)
+std::string decode_const(TypeTable &tt, const Type *t, const uint8_t *d, size_t avail) {
+    if (type_size(t) > avail) fail("constant data shorter than its type");
+    switch (t->tag) {
+        case Type::Primitive: return prim_literal(t->primitive, d);
+        case Type::Vector: {
+            const int32_t p = vec_prim(t->vector.element);
+            std::string s = tt.name(t) + "(";
+            for (uint32_t i = 0; i < t->vector.length; i++) s += (i ? ", " : "") + prim_literal(p, d + i * prim_size(p));
+            return s + ")";
+        }
+        case Type::Matrix: {
+            const uint32_t n = t->matrix.dimension; const size_t col = 4 * (n == 3 ? 4 : n);
+            std::string s = "lc_make_mat(";
+            for (uint32_t c = 0; c < n; c++) {
+                s += std::string(c ? ", " : "") + "lc_float" + std::to_string(n) + "(";
+                for (uint32_t k = 0; k < n; k++) s += (k ? ", " : "") + prim_literal(P_Float32, d + c * col + k * 4);
+                s += ")";
+            }
+            return s + ")";
+        }
+        case Type::Array: {
+            const size_t es = type_size(t->array.element.get());
+            std::string s = tt.name(t) + "{{";
+            for (size_t i = 0; i < t->array.length; i++) s += (i ? ", " : "") + decode_const(tt, t->array.element.get(), d + i * es, es);
+            return s + "}}";
+        }
+        case Type::Struct: {
+            std::string s = tt.name(t) + "{";
+            size_t off = 0;
+            for (size_t i = 0; i < t->struct_.fields.len; i++) {
+                const Type *f = t->struct_.fields[i].get();
+                const size_t a = type_align(f); off = (off + a - 1) / a * a;
+                s += (i ? ", " : "") + decode_const(tt, f, d + off, avail - off);
+                off += type_size(f);
+            }
+            return s + "}";
+        }
+        default: fail("unsupported constant type");
+    }
+}
+
+struct Globals {
+    TypeTable types;
+    std::vector<std::string> messages;
+    std::unordered_map<NodeRef, std::string> resources;  // kernel captures + arguments -> expression valid in every function
+    std::unordered_map<const void *, std::string> callables;
+    std::string callable_defs;
+    std::string shared_decls;
+};
+
+struct PhiMap {
+    std::vector<NodeRef> phis;
+    std::unordered_map<const BasicBlock *, std::vector<NodeRef>> per_block;
+};
+
+template <class F> void for_each_node(const BasicBlock *bb, F &&f) {
+    if (!bb || !bb->first) fail("null basic block");
+    for (NodeRef cur = node(bb->first)->next; cur && cur != bb->last; cur = node(cur)->next) f(cur);
+}
+
+void collect_phis(const BasicBlock *bb, PhiMap &pm) {
+    for_each_node(bb, [&](NodeRef n) {
+        const Instruction *ins = node(n)->instruction.get();
+        switch (ins->tag) {
+            case Instruction::Phi:
+                pm.phis.push_back(n);
+                for (const auto &inc : ins->phi) pm.per_block[inc.block.ptr].push_back(n);
+                break;
+            case Instruction::If: collect_phis(ins->if_.true_branch.ptr, pm); collect_phis(ins->if_.false_branch.ptr, pm); break;
+            case Instruction::Loop: collect_phis(ins->loop.body.ptr, pm); break;
+            case Instruction::GenericLoop:
+                collect_phis(ins->generic_loop.prepare.ptr, pm); collect_phis(ins->generic_loop.body.ptr, pm); collect_phis(ins->generic_loop.update.ptr, pm);
+                break;
+            case Instruction::Switch:
+                collect_phis(ins->switch_.default_.ptr, pm);
+                for (const auto &c : ins->switch_.cases) collect_phis(c.block.ptr, pm);
+                break;
+            case Instruction::AdDetach: collect_phis(ins->ad_detach.ptr, pm); break;
+            default: break;
+        }
+    });
+}
+
+struct FunctionEmitter {
+    Globals &g;
+    std::unordered_map<NodeRef, std::string> names;
+    std::unordered_set<NodeRef> visited;
+    std::string body, decls;
+    PhiMap phis;
+    int indent = 1;
+    bool in_generic_loop = false;
+    bool is_callable = false;
+
+    explicit FunctionEmitter(Globals &gl) : g(gl) {}
+
+    void line(const std::string &s) { body.append((size_t)indent * 4, ' '); body += s; body += '\n'; }
+    std::string tname(const Type *t) { return g.types.name(t); }
+    const Type *ntype(NodeRef n) { return node(n)->type_.get(); }
+
+    std::string ref(NodeRef n) {
+        if (!n) fail("use of INVALID_REF");
+        auto it = names.find(n);
+        if (it != names.end()) return it->second;
+        auto gi = g.resources.find(n);
+        if (gi != g.resources.end()) return gi->second;
+        const Instruction *ins = node(n)->instruction.get();
+        const char *prefix;
+        switch (ins->tag) {
+            case Instruction::Local: prefix = "v"; break;
+            case Instruction::Const: prefix = "c"; break;
+            case Instruction::Call: prefix = "f"; break;
+            case Instruction::Phi: prefix = "phi"; break;
+            case Instruction::Shared: prefix = "smem"; break;
+            case Instruction::Buffer: case Instruction::Bindless: case Instruction::Texture2D: case Instruction::Texture3D: case Instruction::Accel:
+            case Instruction::Uniform: case Instruction::Argument:
+                fail("resource / argument node that is neither a capture nor an argument of the module");
+            default: fail("instruction tag " + std::to_string(ins->tag) + " does not produce a value");
+        }
+        std::string nm = prefix + std::to_string(names.size());
+        names[n] = nm;
+        return nm;
+    }
+
+    int32_t const_i32(NodeRef n) {  // NodeRef::get_i32, ir.rs:998-1030, :1509-1514
+        const Instruction *ins = node(n)->instruction.get();
+        if (ins->tag != Instruction::Const) fail("index operand is not a constant");
+        const Const &c = ins->const_;
+        switch (c.tag) {
+            case Const::Int8: return c.i8; case Const::Uint8: return c.u8; case Const::Int16: return c.i16; case Const::Uint16: return c.u16;
+            case Const::Int32: return c.i32; case Const::Uint32: return (int32_t)c.u32; case Const::Int64: return (int32_t)c.i64; case Const::Uint64: return (int32_t)c.u64;
+            case Const::One: return 1; case Const::Zero: return 0;
+            default: fail("index constant is not an integer");
+        }
+    }
+    bool is_const(NodeRef n) { return node(n)->instruction.get()->tag == Instruction::Const; }
+
+    // cpp.rs:278-300
+    std::string access_chain(std::string var, const Type *ty, const Slice<NodeRef> &args, size_t first) {
+        static const char *xyzw[4] = {"x", "y", "z", "w"};
+        for (size_t i = first; i < args.len; i++) {
+            const NodeRef idx = args[i];
+            if (ty->tag == Type::Vector) {
+                if (i != args.len - 1) fail("vector element access must end the access chain");
+                if (is_const(idx)) { int32_t k = const_i32(idx); if (k < 0 || k >= (int32_t)ty->vector.length) fail("vector index out of range"); var += std::string(".") + xyzw[k]; }
+                else var += "[" + ref(idx) + "]";
+                return var;
+            } else if (ty->tag == Type::Matrix) {
+                var += "[" + ref(idx) + "]";
+                if (i + 1 < args.len) {
+                    const NodeRef e = args[++i];
+                    if (i != args.len - 1) fail("matrix element access must end the access chain");
+                    var += "[" + ref(e) + "]";
+                }
+                return var;
+            } else if (ty->tag == Type::Array) {
+                var += "[" + ref(idx) + "]";
+                ty = type_extract(ty, 0);
+            } else if (ty->tag == Type::Struct) {
+                const int32_t k = const_i32(idx);
+                var += ".f" + std::to_string(k);
+                ty = type_extract(ty, (size_t)k);
+            } else fail("access chain into a scalar");
+        }
+        return var;
+    }
+
+    void emit_const(NodeRef n) {
+        const Instruction *ins = node(n)->instruction.get();
+        const Const &c = ins->const_;
+        const Type *t = ntype(n);
+        const std::string ts = tname(t), v = ref(n);
+        std::string e;
+        switch (c.tag) {
+            case Const::Zero: e = "lc_zero<" + ts + ">()"; break;
+            case Const::One: e = "lc_one<" + ts + ">()"; break;
+            case Const::Bool: e = c.b ? "true" : "false"; break;
+            case Const::Int8: e = prim_literal(P_Int8, (const uint8_t *)&c.i8); break;
+            case Const::Uint8: e = prim_literal(P_Uint8, (const uint8_t *)&c.u8); break;
+            case Const::Int16: e = prim_literal(P_Int16, (const uint8_t *)&c.i16); break;
+            case Const::Uint16: e = prim_literal(P_Uint16, (const uint8_t *)&c.u16); break;
+            case Const::Int32: e = prim_literal(P_Int32, (const uint8_t *)&c.i32); break;
+            case Const::Uint32: e = prim_literal(P_Uint32, (const uint8_t *)&c.u32); break;
+            case Const::Int64: e = prim_literal(P_Int64, (const uint8_t *)&c.i64); break;
+            case Const::Uint64: e = prim_literal(P_Uint64, (const uint8_t *)&c.u64); break;
+            case Const::Float32: e = float_literal(c.f32); break;
+            case Const::Float64: e = double_literal(c.f64); break;
+            case Const::Generic: e = decode_const(g.types, c.generic.type.get(), c.generic.bytes.ptr, c.generic.bytes.len); break;
+            default: fail("Float16 constants are not supported");
+        }
+        line("const " + ts + " " + v + " = " + e + ";");
+    }
+
+    std::string join(const std::vector<std::string> &a, size_t from = 0) {
+        std::string s;
+        for (size_t i = from; i < a.size(); i++) s += (i > from ? ", " : "") + a[i];
+        return s;
+    }
+
+    std::string callable_name(const Arc<CallableModule> &arc);
+
+    // atomics: (buffer, index, access chain..., operands) or (shared, access chain..., operands)  — cpp.rs:301-326
+    std::string atomic_target(const Slice<NodeRef> &args, size_t n_operands) {
+        const NodeRef target = args[0];
+        const Instruction *ti = node(target)->instruction.get();
+        Slice<NodeRef> chain = args; chain.len = args.len - n_operands;
+        if (ti->tag == Instruction::Buffer) {
+            const std::string base = "lc_buffer_ref<" + tname(ntype(target)) + ">(" + ref(target) + ", " + ref(args[1]) + ")";
+            return access_chain(base, ntype(target), chain, 2);
+        }
+        return access_chain(ref(target), ntype(target), chain, 1);
+    }
+
+    void emit_call(NodeRef n) {
+        const Instruction *ins = node(n)->instruction.get();
+        const Func &f = ins->call.func;
+        const Slice<NodeRef> &args = ins->call.args;
+        const Type *rt = ntype(n);
+        const bool is_void = type_is_void(rt);
+        const std::string ts = tname(rt);
+        std::vector<std::string> a;
+        for (NodeRef r : args) a.push_back(ref(r));
+        auto need = [&](size_t k) { if (a.size() != k) fail(std::string(kFuncNames[f.tag]) + " expects " + std::to_string(k) + " operands, got " + std::to_string(a.size())); };
+        auto value = [&](const std::string &e) { if (is_void) line(e + ";"); else line("const " + ts + " " + ref(n) + " = " + e + ";"); };
+        auto bin = [&](const char *op) { need(2); value(a[0] + " " + op + " " + a[1]); };
+        auto fn = [&](const char *name) { value(std::string(name) + "(" + join(a) + ")"); };
+        if (f.tag < 0 || f.tag >= Func::COUNT) fail("unknown Func discriminant " + std::to_string(f.tag));
+        switch (f.tag) {
+            case Func::Add: bin("+"); break;
+            case Func::Sub: bin("-"); break;
+            case Func::Mul: bin("*"); break;
+            case Func::Div: bin("/"); break;
+            case Func::Rem: need(2); if (type_is_float(rt)) value("lc_fmod(" + a[0] + ", " + a[1] + ")"); else value(a[0] + " % " + a[1]); break;
+            case Func::BitAnd: bin("&"); break;
+            case Func::BitOr: bin("|"); break;
+            case Func::BitXor: bin("^"); break;
+            case Func::Shl: bin("<<"); break;
+            case Func::Shr: bin(">>"); break;
+            case Func::RotLeft: fn("lc_rotl"); break;
+            case Func::RotRight: fn("lc_rotr"); break;
+            case Func::Eq: bin("=="); break;
+            case Func::Ne: bin("!="); break;
+            case Func::Lt: bin("<"); break;
+            case Func::Le: bin("<="); break;
+            case Func::Gt: bin(">"); break;
+            case Func::Ge: bin(">="); break;
+            case Func::MatCompMul: need(2); value(a[0] + ".comp_mul(" + a[1] + ")"); break;
+            case Func::Neg: need(1); value("-" + a[0]); break;
+            case Func::Not: need(1); value("!" + a[0]); break;
+            case Func::BitNot: need(1); value((type_is_bool(rt) ? "!" : "~") + a[0]); break;
+            case Func::All: fn("lc_all"); break;
+            case Func::Any: fn("lc_any"); break;
+            case Func::Select: need(3); value("lc_select(" + a[2] + ", " + a[1] + ", " + a[0] + ")"); break;  // (cond, t, f), cpp.rs:1149-1157
+            case Func::Clamp: fn("lc_clamp"); break;
+            case Func::Lerp: fn("lc_lerp"); break;
+            case Func::Step: fn("lc_step"); break;
+            case Func::SmoothStep: fn("lc_smoothstep"); break;
+            case Func::Saturate: fn("lc_saturate"); break;
+            case Func::Abs: fn("lc_abs"); break;
+            case Func::Min: fn("lc_min"); break;
+            case Func::Max: fn("lc_max"); break;
+            case Func::ReduceSum: fn("lc_reduce_sum"); break;
+            case Func::ReduceProd: fn("lc_reduce_prod"); break;
+            case Func::ReduceMin: fn("lc_reduce_min"); break;
+            case Func::ReduceMax: fn("lc_reduce_max"); break;
+            case Func::Clz: fn("lc_clz"); break;
+            case Func::Ctz: fn("lc_ctz"); break;
+            case Func::PopCount: fn("lc_popcount"); break;
+            case Func::Reverse: fn("lc_reverse"); break;
+            case Func::IsInf: fn("lc_isinf"); break;
+            case Func::IsNan: fn("lc_isnan"); break;
+            case Func::Acos: fn("lc_acos"); break;
+            case Func::Acosh: fn("lc_acosh"); break;
+            case Func::Asin: fn("lc_asin"); break;
+            case Func::Asinh: fn("lc_asinh"); break;
+            case Func::Atan: fn("lc_atan"); break;
+            case Func::Atan2: fn("lc_atan2"); break;
+            case Func::Atanh: fn("lc_atanh"); break;
+            case Func::Cos: fn("lc_cos"); break;
+            case Func::Cosh: fn("lc_cosh"); break;
+            case Func::Sin: fn("lc_sin"); break;
+            case Func::Sinh: fn("lc_sinh"); break;
+            case Func::Tan: fn("lc_tan"); break;
+            case Func::Tanh: fn("lc_tanh"); break;
+            case Func::Exp: fn("lc_exp"); break;
+            case Func::Exp2: fn("lc_exp2"); break;
+            case Func::Exp10: fn("lc_exp10"); break;
+            case Func::Log: fn("lc_log"); break;
+            case Func::Log2: fn("lc_log2"); break;
+            case Func::Log10: fn("lc_log10"); break;
+            case Func::Powi: fn("lc_powi"); break;
+            case Func::Powf: fn("lc_pow"); break;
+            case Func::Sqrt: fn("lc_sqrt"); break;
+            case Func::Rsqrt: fn("lc_rsqrt"); break;
+            case Func::Ceil: fn("lc_ceil"); break;
+            case Func::Floor: fn("lc_floor"); break;
+            case Func::Fract: fn("lc_fract"); break;
+            case Func::Trunc: fn("lc_trunc"); break;
+            case Func::Round: fn("lc_round"); break;
+            case Func::Fma: fn("lc_fma"); break;
+            case Func::Copysign: fn("lc_copysign"); break;
+            case Func::Cross: fn("lc_cross"); break;
+            case Func::Dot: fn("lc_dot"); break;
+            case Func::OuterProduct: fn("lc_outer_product"); break;
+            case Func::Length: fn("lc_length"); break;
+            case Func::LengthSquared: fn("lc_length_squared"); break;
+            case Func::Normalize: fn("lc_normalize"); break;
+            case Func::Faceforward: fn("lc_faceforward"); break;
+            case Func::Distance: fn("lc_distance"); break;
+            case Func::Reflect: fn("lc_reflect"); break;
+            case Func::Determinant: fn("lc_determinant"); break;
+            case Func::Transpose: fn("lc_transpose"); break;
+            case Func::Inverse: fn("lc_inverse"); break;
+            case Func::SynchronizeBlock: line("__syncthreads();"); break;
+            case Func::WarpIsFirstActiveLane: value("lc_warp_is_first_active_lane()"); break;
+            case Func::WarpFirstActiveLane: value("lc_warp_first_active_lane()"); break;
+            case Func::WarpActiveAllEqual: fn("lc_warp_active_all_equal"); break;
+            case Func::WarpActiveBitAnd: fn("lc_warp_active_bit_and"); break;
+            case Func::WarpActiveBitOr: fn("lc_warp_active_bit_or"); break;
+            case Func::WarpActiveBitXor: fn("lc_warp_active_bit_xor"); break;
+            case Func::WarpActiveCountBits: fn("lc_warp_active_count_bits"); break;
+            case Func::WarpActiveMax: fn("lc_warp_active_max"); break;
+            case Func::WarpActiveMin: fn("lc_warp_active_min"); break;
+            case Func::WarpActiveProduct: fn("lc_warp_active_product"); break;
+            case Func::WarpActiveSum: fn("lc_warp_active_sum"); break;
+            case Func::WarpActiveAll: fn("lc_warp_active_all"); break;
+            case Func::WarpActiveAny: fn("lc_warp_active_any"); break;
+            case Func::WarpActiveBitMask: fn("lc_warp_active_bit_mask"); break;
+            case Func::WarpPrefixCountBits: fn("lc_warp_prefix_count_bits"); break;
+            case Func::WarpPrefixSum: fn("lc_warp_prefix_sum"); break;
+            case Func::WarpPrefixProduct: fn("lc_warp_prefix_product"); break;
+            case Func::WarpReadLaneAt: fn("lc_warp_read_lane_at"); break;
+            case Func::WarpReadFirstLane: fn("lc_warp_read_first_lane"); break;
+            case Func::WarpSize: value("32u"); break;
+            case Func::WarpLaneId: value("(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u"); break;
+
+            case Func::ZeroInitializer: value("lc_zero<" + ts + ">()"); break;
+            case Func::Assume: line("lc_assume(" + join(a) + ");"); break;
+            case Func::Assert: need(1); g.messages.push_back(slice_to_string(f.message)); line("lc_assert(" + a[0] + ", " + std::to_string(g.messages.size() - 1) + ");"); break;
+            case Func::Unreachable:
+                g.messages.push_back(slice_to_string(f.message));
+                if (!is_void) line(ts + " " + ref(n) + "{};");
+                line("lc_trap(\"unreachable\", " + std::to_string(g.messages.size() - 1) + ");");
+                break;
+            case Func::ThreadId: value("lc_thread_id()"); break;
+            case Func::BlockId: value("lc_block_id()"); break;
+            case Func::DispatchId: value("lc_dispatch_id()"); break;
+            case Func::DispatchSize: value("lc_uint3(p.launch.dispatch_size[0], p.launch.dispatch_size[1], p.launch.dispatch_size[2])"); break;
+
+            case Func::Load: need(1); value(a[0]); break;
+            case Func::Cast:
+                need(1);
+                if (rt->tag == Type::Primitive) value(rt->primitive == P_Bool ? "(" + a[0] + " != 0)" : "static_cast<" + ts + ">(" + a[0] + ")");
+                else if (rt->tag == Type::Vector) value("lc_vec_cast<" + std::string(prim_c(vec_prim(rt->vector.element))) + ">(" + a[0] + ")");
+                else fail("Cast to a non-scalar, non-vector type");
+                break;
+            case Func::Bitcast: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ")"); break;
+            case Func::ExtractElement: value(access_chain(a[0], ntype(args[0]), args, 1)); break;
+            case Func::InsertElement: {  // (aggregate, value, indices...)
+                const std::string v = ref(n);
+                line(ts + " " + v + "_m = " + a[0] + ";");
+                line(access_chain(v + "_m", ntype(args[0]), args, 2) + " = " + a[1] + ";");
+                line("const " + ts + " &" + v + " = " + v + "_m;");
+                break;
+            }
+            case Func::GetElementPtr: line(ts + " &" + ref(n) + " = " + access_chain(a[0], ntype(args[0]), args, 1) + ";"); break;
+            case Func::Struct: value(ts + "{" + join(a) + "}"); break;
+            case Func::Array: value(ts + "{{" + join(a) + "}}"); break;
+            case Func::Vec: case Func::Vec2: case Func::Vec3: case Func::Vec4: value(ts + "(" + join(a) + ")"); break;
+            case Func::Mat2: case Func::Mat3: case Func::Mat4: value("lc_make_mat(" + join(a) + ")"); break;
+            case Func::Mat: need(1); value(ts + "::full(" + a[0] + ")"); break;
+            case Func::Permute: {
+                static const char *xyzw[4] = {"x", "y", "z", "w"};
+                std::string e = ts + "(";
+                for (size_t i = 1; i < args.len; i++) { const int32_t k = const_i32(args[i]); if (k < 0 || k > 3) fail("Permute index out of range"); e += (i > 1 ? ", " : "") + a[0] + "." + xyzw[k]; }
+                value(e + ")");
+                break;
+            }
+
+            case Func::BufferRead: need(2); value("lc_buffer_read<" + tname(ntype(args[0])) + ">(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::BufferWrite: need(3); line("lc_buffer_write<" + tname(ntype(args[0])) + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ");"); break;
+            case Func::BufferSize: need(1); value("static_cast<" + ts + ">(lc_buffer_size<" + tname(ntype(args[0])) + ">(" + a[0] + "))"); break;
+            case Func::BufferAddress: need(1); value("lc_buffer_address(" + a[0] + ")"); break;
+            case Func::ByteBufferRead: need(2); value("lc_byte_buffer_read<" + ts + ">(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::ByteBufferWrite: need(3); line("lc_byte_buffer_write<" + tname(ntype(args[2])) + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ");"); break;
+            case Func::ByteBufferSize: need(1); value("static_cast<" + ts + ">(lc_buffer_size<uint8_t>(" + a[0] + "))"); break;
+            case Func::Texture2dRead: need(2); value("lc_texture2d_read<" + ts + ">(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::Texture2dWrite: need(3); line("lc_texture2d_write<" + tname(ntype(args[2])) + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ");"); break;
+            case Func::Texture2dSize: need(1); value("lc_texture2d_size(" + a[0] + ")"); break;
+            case Func::Texture3dRead: need(2); value("lc_texture3d_read<" + ts + ">(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::Texture3dWrite: need(3); line("lc_texture3d_write<" + tname(ntype(args[2])) + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ");"); break;
+            case Func::Texture3dSize: need(1); value("lc_texture3d_size(" + a[0] + ")"); break;
+            case Func::BindlessBufferRead: need(3); value("lc_bindless_buffer_read<" + ts + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessBufferWrite: need(4); line("lc_bindless_buffer_write<" + tname(ntype(args[3])) + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ", " + a[3] + ");"); break;
+            case Func::BindlessByteBufferRead: need(3); value("lc_bindless_byte_buffer_read<" + ts + ">(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessBufferSize: need(3); value("static_cast<" + ts + ">(lc_bindless_buffer_size(" + a[0] + ", " + a[1] + ", " + a[2] + "))"); break;
+            case Func::BindlessBufferAddress: need(2); value("lc_bindless_buffer_address(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::BindlessTexture2dRead: need(3); value("lc_bindless_texture2d_read(" + join(a) + ")"); break;
+            case Func::BindlessTexture3dRead: need(3); value("lc_bindless_texture3d_read(" + join(a) + ")"); break;
+            case Func::BindlessTexture2dSize: need(2); value("lc_bindless_texture2d_size(" + join(a) + ")"); break;
+            case Func::BindlessTexture3dSize: need(2); value("lc_bindless_texture3d_size(" + join(a) + ")"); break;
+
+            case Func::AtomicExchange: value("lc_atomic_exchange(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicCompareExchange: value("lc_atomic_compare_exchange(&" + atomic_target(args, 2) + ", " + a[a.size() - 2] + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchAdd: value("lc_atomic_fetch_add(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchSub: value("lc_atomic_fetch_sub(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchAnd: value("lc_atomic_fetch_and(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchOr: value("lc_atomic_fetch_or(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchXor: value("lc_atomic_fetch_xor(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchMin: value("lc_atomic_fetch_min(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+            case Func::AtomicFetchMax: value("lc_atomic_fetch_max(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
+
+            // rows 5, 6, 8 of SURVEY.md §8a — cpp.rs:1334-1400
+            case Func::RayTracingTraceClosest: need(3); value("lc_bit_cast<" + ts + ">(lc_trace_closest(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + "))"); break;
+            case Func::RayTracingTraceAny: need(3); value("lc_trace_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ")"); break;
+            case Func::RayTracingInstanceTransform: need(2); value("lc_accel_instance_transform(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::RayTracingInstanceVisibilityMask: need(2); value("lc_accel_instance_visibility_mask(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::RayTracingInstanceUserId: need(2); value("lc_accel_instance_user_id(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::RayTracingSetInstanceVisibility: need(3); line("lc_set_instance_visibility(" + join(a) + ");"); break;
+            case Func::RayTracingSetInstanceUserId: need(3); line("lc_set_instance_user_id(" + join(a) + ");"); break;
+
+            case Func::Callable: {
+                const std::string name = callable_name(f.callable);
+                std::string call = name + "(p";
+                for (const auto &s : a) call += ", " + s;
+                value(call + ")");
+                break;
+            }
+            case Func::ShaderExecutionReorder: break;  // a scheduling hint (cpp.rs:1002-1010); the persistent traversal has no use for it
+            case Func::PropagateGrad: case Func::RequiresGradient: break;
+            case Func::Detach: need(1); value(a[0]); break;
+            default:
+                fail(std::string("Func::") + kFuncNames[f.tag] + " is outside the ray-tracing subset lowered for the B200 device (SURVEY.md §8f-1)");
+        }
+    }
+
+    void emit_block_content(const BasicBlock *bb) {
+        for_each_node(bb, [&](NodeRef n) { emit(n); });
+        auto it = phis.per_block.find(bb);
+        if (it != phis.per_block.end()) {
+            for (NodeRef phi : it->second) {
+                const Instruction *pi = node(phi)->instruction.get();
+                for (const auto &inc : pi->phi)
+                    if (inc.block.ptr == bb) { line(ref(phi) + " = " + ref(inc.value) + ";"); break; }
+            }
+        }
+    }
+    void emit_block(const BasicBlock *bb) {
+        line("{");
+        indent++;
+        emit_block_content(bb);
+        indent--;
+        line("}");
+    }
+
+    void emit(NodeRef n) {
+        if (!visited.insert(n).second) return;
+        const Instruction *ins = node(n)->instruction.get();
+        if (!ins) fail("node without instruction");
+        switch (ins->tag) {
+            case Instruction::Buffer: case Instruction::Bindless: case Instruction::Texture2D: case Instruction::Texture3D: case Instruction::Accel:
+            case Instruction::Uniform: case Instruction::Shared: case Instruction::Argument: case Instruction::UserData: case Instruction::Comment:
+                break;
+            case Instruction::Invalid: fail("Instruction::Invalid inside a block");
+            case Instruction::Local: line(tname(ntype(n)) + " " + ref(n) + " = " + ref(ins->local.init) + ";"); break;
+            case Instruction::Const: emit_const(n); break;
+            case Instruction::Update: line(ref(ins->update.var) + " = " + ref(ins->update.value) + ";"); break;
+            case Instruction::Call: emit_call(n); break;
+            case Instruction::Phi: decls += "    " + tname(ntype(n)) + " " + ref(n) + "{};\n"; break;
+            case Instruction::Return:
+                if (ins->return_) line("return " + ref(ins->return_) + ";"); else line("return;");
+                break;
+            case Instruction::Loop: {  // do { body } while (cond)  — cpp.rs:1683-1699
+                const bool old = in_generic_loop; in_generic_loop = false;
+                line("for (;;) {");
+                indent++;
+                emit_block_content(ins->loop.body.ptr);
+                line("if (!(" + ref(ins->loop.cond) + ")) break;");
+                indent--;
+                line("}");
+                in_generic_loop = old;
+                break;
+            }
+            case Instruction::GenericLoop: {
+                const bool old = in_generic_loop; in_generic_loop = true;
+                line("for (;;) {");
+                indent++;
+                line("bool loop_break = false;");
+                emit_block_content(ins->generic_loop.prepare.ptr);
+                line("if (!(" + ref(ins->generic_loop.cond) + ")) break;");
+                line("do");
+                emit_block(ins->generic_loop.body.ptr);
+                line("while (false);");
+                line("if (loop_break) break;");
+                emit_block(ins->generic_loop.update.ptr);
+                indent--;
+                line("}");
+                in_generic_loop = old;
+                break;
+            }
+            case Instruction::Break:
+                if (in_generic_loop) line("loop_break = true;");
+                line("break;");
+                break;
+            case Instruction::Continue: line(in_generic_loop ? "break;" : "continue;"); break;
+            case Instruction::If:
+                line("if (" + ref(ins->if_.cond) + ")");
+                emit_block(ins->if_.true_branch.ptr);
+                line("else");
+                emit_block(ins->if_.false_branch.ptr);
+                break;
+            case Instruction::Switch: {
+                const std::string v = ref(ins->switch_.value);
+                bool first = true;
+                for (const auto &c : ins->switch_.cases) {
+                    line(std::string(first ? "if (" : "else if (") + v + " == " + std::to_string(c.value) + ")");
+                    emit_block(c.block.ptr);
+                    first = false;
+                }
+                if (!first) line("else");
+                emit_block(ins->switch_.default_.ptr);
+                break;
+            }
+            case Instruction::Print: {
+                std::string fmt = slice_to_string(ins->print.fmt), out, argl;
+                size_t ai = 0;
+                for (size_t i = 0; i < fmt.size(); i++) {
+                    if (fmt[i] == '{' && i + 1 < fmt.size() && fmt[i + 1] == '}') {
+                        if (ai >= ins->print.args.len) fail("print: more placeholders than arguments");
+                        const NodeRef an = ins->print.args[ai++];
+                        const Type *t = ntype(an);
+                        const int32_t p = t->tag == Type::Primitive ? t->primitive : (t->tag == Type::Vector ? vec_prim(t->vector.element) : -1);
+                        if (p < 0) fail("print: only scalars and vectors can be printed");
+                        const char *spec = prim_is_float(p) ? "%g" : (p == P_Int64 ? "%lld" : (p == P_Uint64 ? "%llu" : (p == P_Uint32 || p == P_Uint16 || p == P_Uint8 || p == P_Bool ? "%u" : "%d")));
+                        const char *cast = prim_is_float(p) ? "(double)" : (p == P_Int64 ? "(long long)" : (p == P_Uint64 ? "(unsigned long long)" : (p == P_Uint32 || p == P_Uint16 || p == P_Uint8 || p == P_Bool ? "(unsigned)" : "(int)")));
+                        if (t->tag == Type::Vector) {
+                            static const char *xyzw[4] = {"x", "y", "z", "w"};
+                            out += "(";
+                            for (uint32_t k = 0; k < t->vector.length; k++) { out += std::string(k ? ", " : "") + spec; argl += std::string(", ") + cast + ref(an) + "." + xyzw[k]; }
+                            out += ")";
+                        } else { out += spec; argl += std::string(", ") + cast + ref(an); }
+                        i++;
+                    } else if ((fmt[i] == '{' || fmt[i] == '}') && i + 1 < fmt.size() && fmt[i + 1] == fmt[i]) { out += fmt[i]; i++; }
+                    else if (fmt[i] == '%') out += "%%";
+                    else if (fmt[i] == '"') out += "\\\"";
+                    else if (fmt[i] == '\\') out += "\\\\";
+                    else if (fmt[i] == '\n') out += "\\n";
+                    else out += fmt[i];
+                }
+                line("printf(\"" + out + "\\n\"" + argl + ");");
+                break;
+            }
+            case Instruction::AdScope: case Instruction::AdDetach:
+                fail("autodiff scopes must be removed by the frontend's transform pipeline before create_shader");
+            case Instruction::RayQuery:
+                fail("Instruction::RayQuery inside a DSL kernel is not lowered; RayQuery traversals are served in batch form by lc_b200_ray_query (SURVEY.md §8a row 7)");
+            default: fail("unknown instruction tag " + std::to_string(ins->tag));
+        }
+    }
+};
+
+std::string FunctionEmitter::callable_name(const Arc<CallableModule> &arc) {
+    const CallableModule *cm = arc.get();
+    if (!cm) fail("null callable");
+    auto it = g.callables.find(arc.inner);
+    if (it != g.callables.end()) return it->second;
+    if (cm->cpu_custom_ops.len) fail("CpuCustomOp callables cannot run on the GPU");
+    FunctionEmitter ce(g);
+    ce.is_callable = true;
+    std::string params = "const lc_params &p";
+    for (size_t i = 0; i < cm->args.len; i++) {
+        const NodeRef an = cm->args[i];
+        const Instruction *ai = node(an)->instruction.get();
+        const std::string v = "ca_" + std::to_string(i);
+        switch (ai->tag) {
+            case Instruction::Accel: params += ", const lc_accel &" + v; break;
+            case Instruction::Bindless: params += ", const lc_bindless &" + v; break;
+            case Instruction::Buffer: params += ", const lc_buffer &" + v; break;
+            case Instruction::Texture2D: case Instruction::Texture3D: params += ", const lc_texture &" + v; break;
+            case Instruction::Argument: params += std::string(", ") + (ai->argument.by_value ? "const " : "") + tname(node(an)->type_.get()) + " &" + v; break;
+            default: fail("unsupported callable parameter kind " + std::to_string(ai->tag));
+        }
+        ce.names[an] = v;
+    }
+    for (const auto &cap : cm->captures)
+        if (!g.resources.count(cap.node)) fail("a callable captures a resource that the kernel does not capture (cpp.rs:2015-2017)");
+    collect_phis(cm->module.entry.ptr, ce.phis);
+    ce.emit_block_content(cm->module.entry.ptr);
+    const std::string name = "lc_callable_" + std::to_string(g.callables.size());
+    g.callables[arc.inner] = name;
+    g.callable_defs += "__device__ " + tname(cm->ret_type.get()) + " " + name + "(" + params + ") {\n" + ce.decls + ce.body + "}\n\n";
+    return name;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+void lower_kernel(const KernelModule *km, LoweredKernel &out) {
+    if (!km) fail("null KernelModule");
+    if (km->module.kind != MK_Kernel) fail("module kind is not Kernel");
+    if (km->module.flags != 0) fail("module still requires an autodiff transform (flags != NONE)");
+    if (km->cpu_custom_ops.len) fail("CpuCustomOp cannot run on the GPU");
+    Globals g;
+    FunctionEmitter fe(g);
+    out = LoweredKernel{};
+    for (int k = 0; k < 3; k++) out.block_size[k] = km->block_size[k] ? km->block_size[k] : 1;
+    if ((uint64_t)out.block_size[0] * out.block_size[1] * out.block_size[2] > 1024) fail("block size exceeds 1024 threads");
+
+    // parameter block: launch record, captures, arguments
+    std::ostringstream params, asserts;
+    size_t off = sizeof(HostLaunch), max_align = 4;
+    params << "struct lc_params {\n    lc_launch launch;\n";
+    auto add = [&](NodeRef n, const std::string &member, bool is_capture, const Binding *b) {
+        const Instruction *ins = node(n)->instruction.get();
+        ParamSlot s; s.is_capture = is_capture; if (b) s.binding = *b;
+        std::string ty; size_t size, align;
+        switch (ins->tag) {
+            case Instruction::Buffer: s.kind = ParamSlot::Buffer; ty = "lc_buffer"; size = sizeof(HostBufferArg); align = 8; break;
+            case Instruction::Texture2D: case Instruction::Texture3D: s.kind = ParamSlot::Texture; ty = "lc_texture"; size = sizeof(HostTextureArg); align = 8; break;
+            case Instruction::Bindless: s.kind = ParamSlot::Bindless; ty = "lc_bindless"; size = sizeof(HostBindlessArg); align = 8; break;
+            case Instruction::Accel: s.kind = ParamSlot::Accel; ty = "lc_accel"; size = sizeof(HostAccelArg); align = 8; break;
+            case Instruction::Uniform: {
+                if (is_capture) fail("uniform captures do not exist");
+                const Type *t = node(n)->type_.get();
+                s.kind = ParamSlot::Uniform; ty = g.types.name(t); size = type_size(t); align = type_align(t);
+                break;
+            }
+            default: fail("kernel parameter of unsupported kind " + std::to_string(ins->tag));
+        }
+        off = align_up(off, align);
+        s.offset = off; s.size = size;
+        off += size;
+        params << "    " << ty << " " << member << ";\n";
+        // members are laid out sequentially at their natural alignment, so size + alignment of every member pin all offsets
+        asserts << "static_assert(sizeof(" << ty << ") == " << size << " && alignof(" << ty << ") == " << align << ", \"parameter block layout: " << member << " at byte " << s.offset << "\");\n";
+        max_align = std::max(max_align, align);
+        g.resources[n] = "p." + member;
+        (is_capture ? out.captures : out.args).push_back(s);
+    };
+    for (size_t i = 0; i < km->captures.len; i++) {
+        const Capture &c = km->captures[i];
+        const Instruction *ins = node(c.node)->instruction.get();
+        const bool ok = (ins->tag == Instruction::Buffer && c.binding.tag == Binding::Buffer) ||
+                        ((ins->tag == Instruction::Texture2D || ins->tag == Instruction::Texture3D) && c.binding.tag == Binding::Texture) ||
+                        (ins->tag == Instruction::Bindless && c.binding.tag == Binding::BindlessArray) || (ins->tag == Instruction::Accel && c.binding.tag == Binding::Accel);
+        if (!ok) fail("capture " + std::to_string(i) + ": node kind and binding kind disagree");
+        add(c.node, "c" + std::to_string(i), true, &c.binding);
+    }
+    for (size_t i = 0; i < km->args.len; i++) add(km->args[i], "a" + std::to_string(i), false, nullptr);
+    params << "};\n";
+    out.param_bytes = align_up(off, 16);
+    if (out.param_bytes > 4000) fail("kernel parameter block exceeds 4 KB");
+
+    // shared memory
+    for (size_t i = 0; i < km->shared.len; i++) {
+        const NodeRef s = km->shared[i];
+        const std::string nm = "smem" + std::to_string(i);
+        fe.names[s] = nm;
+        g.shared_decls += "    __shared__ " + g.types.name(node(s)->type_.get()) + " " + nm + ";\n";
+    }
+
+    collect_phis(km->module.entry.ptr, fe.phis);
+    fe.emit_block_content(km->module.entry.ptr);
+
+    std::ostringstream src;
+    src << "// generated by lc_b200 (ir_lower.cpp) — do not edit\n#include \"lc_device_lib.cuh\"\n\n"
+        << g.types.defs << "\n" << params.str() << asserts.str()
+        << "static_assert(sizeof(lc_params) == " << align_up(off, max_align) << ", \"parameter block size\");\n\n"
+        << g.callable_defs
+        << "extern \"C\" __global__ void __launch_bounds__(" << (out.block_size[0] * out.block_size[1] * out.block_size[2]) << ") lc_kernel(const lc_params p) {\n"
+        << g.shared_decls
+        << "    {   // partial edge blocks are clipped to dispatch_size (cpu/stream.rs:384-404)\n"
+        << "        const lc_uint3 id = lc_dispatch_id();\n"
+        << "        if (id.x >= p.launch.dispatch_size[0] || id.y >= p.launch.dispatch_size[1] || id.z >= p.launch.dispatch_size[2]) return;\n"
+        << "    }\n"
+        << fe.decls << fe.body << "}\n";
+    out.source = src.str();
+    out.messages = g.messages;
+}
+
+}  // namespace lcb
+
+// ---- layout self-description (compared with tests/golden/ir_layout_reference.json) ---------------------------------------------
+extern "C" __attribute__((visibility("default"))) const char *lc_b200_ir_layout_json(void) {
+    namespace M = lcb::ir;
+    static std::string s = [] {
+        std::ostringstream o;
+        int n = 0;
+        o << "{";
+#define K(key, RV, MV) o << (n++ ? ", " : "") << "\"" << key << "\": " << (size_t)(MV);
+#include "ir_layout_keys.inc"
+#undef K
+        o << "}";
+        return o.str();
+    }();
+    return s.c_str();
+}

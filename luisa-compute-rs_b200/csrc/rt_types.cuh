@@ -8,9 +8,20 @@
 //   PackedTri    64 B,  64-byte aligned : LDG.256 (v0|prim, v1) + LDG.128 (v2); 16 B spare
 //   InstanceRec 128 B,  16-byte aligned : eight float4
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC (IR-lowered kernels, shader.cu): no host headers; the fixed-width names and offsetof come from the compiler
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#else
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
+#endif
 
 namespace lcb {
 
@@ -84,7 +95,18 @@ struct BuildHeader {
     float root_hi[3]; float pad2;
     uint32_t level_end[48]; // collapse: node_count snapshot taken by the last arriver of each level's barrier
 };
+#ifndef __CUDACC_RTC__
 static_assert(offsetof(BuildHeader, node_count) % 8 == 0, "node_count/prim_count must form an aligned 64-bit word");
+#endif
+
+// What a traversal needs to know about one acceleration structure (by value in kernel parameters).
+struct AccelView {
+    const WideNode *tlas_nodes;      // nullptr => empty accel
+    const uint32_t *tlas_prims;      // instance ids referenced by TLAS leaves
+    const InstanceRec *instances;
+    uint32_t instance_count;
+    float world_lo[3], world_hi[3];  // bounds of the TLAS root (ray reordering quantises origins against them)
+};
 
 constexpr int kMaxWideDepth = 40;   // builder fails loudly beyond this; traversal stack is sized for it
 constexpr int kTraversalStack = 96; // >= TLAS depth + 3 + BLAS depth

@@ -2,7 +2,11 @@
 // trace from inside their own threads (path_tracer.cu; an IR-lowered DSL kernel would include this header the same way
 // the CPU backend's generated code includes cpu_resource.h and calls lc_trace_closest / lc_trace_any, cpu_resource.h:288-294).
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "rt_types.cuh"
+#else
 #include "build.cuh"
+#endif
 
 namespace lcb {
 

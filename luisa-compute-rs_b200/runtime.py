@@ -102,6 +102,22 @@ class Device:
     def create_event(self):
         return Event(self)
 
+    def create_tex2d(self, format, width, height):
+        """`Device::create_tex2d::<T>(storage, w, h, mips=1)` (runtime.rs:529-570)."""
+        return Texture(self, format, 2, width, height, 1)
+
+    def create_tex3d(self, format, width, height, depth):
+        return Texture(self, format, 3, width, height, depth)
+
+    def create_bindless_array(self, slots):
+        """`Device::create_bindless_array(slots)` (runtime.rs:572-600)."""
+        return BindlessArray(self, slots)
+
+    def create_shader(self, kernel_module_ptr, fast_math=False, name=None, keep=None):
+        """`Device::create_kernel` -> DeviceInterface::create_shader(LCKernelModule{ptr}, &ShaderOption) (runtime.rs:1226-1260).
+        `kernel_module_ptr`: address of an ir::KernelModule (ir.KernelBuilder.finish()); `keep`: the builder that owns it."""
+        return Shader(self, kernel_module_ptr, fast_math, name, keep)
+
     def query(self, name):
         p = self.iface.query(self.handle, name.encode())
         if not p:
@@ -200,6 +216,177 @@ class BufferView:
         out = np.empty(self.size // np.dtype(dtype).itemsize, dtype=dtype)
         self.copy_to(out)
         return out
+
+
+PIXEL_FORMATS = {  # api_types PixelFormat discriminants (lib.rs:310-362) -> (numpy dtype, channels)
+    "R8Uint": (1, np.uint8, 1), "R8Unorm": (2, np.uint8, 1), "Rg8Unorm": (5, np.uint8, 2), "Rgba8Uint": (7, np.uint8, 4), "Rgba8Unorm": (8, np.uint8, 4),
+    "R16Uint": (10, np.uint16, 1), "R16Unorm": (11, np.uint16, 1), "Rgba16Unorm": (17, np.uint16, 4),
+    "R32Sint": (18, np.int32, 1), "R32Uint": (19, np.uint32, 1), "Rg32Uint": (21, np.uint32, 2), "Rgba32Sint": (22, np.int32, 4), "Rgba32Uint": (23, np.uint32, 4),
+    "R16f": (24, np.float16, 1), "Rgba16f": (26, np.float16, 4), "R32f": (27, np.float32, 1), "Rg32f": (28, np.float32, 2), "Rgba32f": (29, np.float32, 4),
+}
+_FORMAT_TO_STORAGE = [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 10, 11, 12, 13, 14]
+
+
+class Texture:
+    """`Tex2d<T>` / `Tex3d<T>` (runtime.rs:529-570): one mip level, row-major texels on upload / download."""
+
+    def __init__(self, device, format, dim, width, height, depth):
+        self.device = device
+        self.format_id, self.dtype, self.channels = PIXEL_FORMATS[format]
+        self.storage = _FORMAT_TO_STORAGE[self.format_id]
+        self.dim, self.width, self.height, self.depth = dim, width, height, depth
+        info = device.iface.create_texture(device.handle, self.format_id, dim, width, height, depth, 1, False, False)
+        self.handle = abi.Handle(info.handle)
+        self._alive = True
+
+    @property
+    def shape(self):
+        return ((self.depth,) if self.dim == 3 else ()) + (self.height, self.width) + ((self.channels,) if self.channels > 1 else ())
+
+    def _transfer(self, tag, arr):
+        if arr.dtype != self.dtype or arr.shape != self.shape or not arr.flags["C_CONTIGUOUS"]:
+            raise LuisaError(f"texture transfer needs a C-contiguous {np.dtype(self.dtype).name} array of shape {self.shape}")
+        cmd = abi.Command()
+        cmd.tag = tag
+        t = abi.CmdTextureTransfer(self.handle, self.storage, 0, (C.c_uint32 * 3)(self.width, self.height, self.depth), arr.ctypes.data)
+        if tag == abi.CMD_TEXTURE_UPLOAD:
+            cmd.u.texture_upload = t
+        else:
+            cmd.u.texture_download = t
+        return HostCommand(cmd, keep=[arr, self])
+
+    def copy_from_async(self, arr):
+        return self._transfer(abi.CMD_TEXTURE_UPLOAD, np.ascontiguousarray(arr))
+
+    def copy_to_async(self, arr):
+        return self._transfer(abi.CMD_TEXTURE_DOWNLOAD, arr)
+
+    def copy_from(self, arr):
+        s = self.device.default_stream()
+        s.submit([self.copy_from_async(arr)])
+        s.synchronize()
+
+    def to_numpy(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        s = self.device.default_stream()
+        s.submit([self.copy_to_async(out)])
+        s.synchronize()
+        return out
+
+    def destroy(self):
+        if self._alive and not self.device._closed:
+            self.device.iface.destroy_texture(self.device.handle, self.handle)
+        self._alive = False
+
+
+class BindlessArray:
+    """`BindlessArray` (runtime.rs:572-700): emplace_*_async queue modifications, update_async emits the command."""
+
+    def __init__(self, device, slots):
+        self.device = device
+        self.slots = slots
+        self.handle = abi.Handle(device.iface.create_bindless_array(device.handle, slots).handle)
+        self._mods = {}
+        self._keep = {}
+        self._alive = True
+
+    def _mod(self, slot):
+        if slot not in self._mods:
+            m = abi.BindlessModification()
+            m.slot = slot
+            self._mods[slot] = m
+        return self._mods[slot]
+
+    def emplace_buffer_async(self, slot, buffer, offset=0):
+        m = self._mod(slot)
+        m.buffer = abi.BindlessBufferUpdate(abi.BINDLESS_EMPLACE, buffer.handle, offset)
+        self._keep[("b", slot)] = buffer
+
+    def emplace_tex2d_async(self, slot, texture):
+        m = self._mod(slot)
+        m.tex2d = abi.BindlessTextureUpdate(abi.BINDLESS_EMPLACE, texture.handle, abi.Sampler(0, 0))
+        self._keep[("t2", slot)] = texture
+
+    def remove_buffer_async(self, slot):
+        self._mod(slot).buffer = abi.BindlessBufferUpdate(abi.BINDLESS_REMOVE, abi.Handle(0xFFFFFFFFFFFFFFFF), 0)
+        self._keep.pop(("b", slot), None)
+
+    def update_async(self):
+        mods = list(self._mods.values())
+        self._mods = {}
+        arr = (abi.BindlessModification * max(len(mods), 1))(*mods)
+        cmd = abi.Command()
+        cmd.tag = abi.CMD_BINDLESS_UPDATE
+        cmd.u.bindless_update = abi.CmdBindlessUpdate(self.handle, arr, len(mods))
+        return HostCommand(cmd, keep=[arr, self])
+
+    def update(self):
+        s = self.device.default_stream()
+        s.submit([self.update_async()])
+        s.synchronize()
+
+    def destroy(self):
+        if self._alive and not self.device._closed:
+            self.device.iface.destroy_bindless_array(self.device.handle, self.handle)
+        self._alive = False
+
+
+class Shader:
+    """A compiled kernel (`RawKernel`, runtime.rs:1262-1330): `dispatch_async(dispatch_size, *args)` emits api::Command::ShaderDispatch
+    with one Argument per kernel argument, in order (KernelArg::encode, runtime.rs:1332-1500)."""
+
+    def __init__(self, device, kernel_module_ptr, fast_math=False, name=None, keep=None):
+        self.device = device
+        self._keep = keep
+        opt = abi.ShaderOption(True, fast_math, False, False, False, 0, name.encode() if name else None, None)
+        info = device.iface.create_shader(device.handle, abi.KernelModule(kernel_module_ptr), C.byref(opt))
+        self.handle = abi.Handle(info.resource.handle)
+        self.block_size = tuple(info.block_size)
+        self._alive = True
+
+    def dispatch_async(self, dispatch_size, *args):
+        from .rtx import Accel
+        n = len(args)
+        arr = (abi.Argument * max(n, 1))()
+        keep = [arr, self]
+        for i, a in enumerate(args):
+            if isinstance(a, BufferView):
+                arr[i].tag = abi.ARG_BUFFER
+                arr[i].u.buffer = abi._ArgBuffer(a.buffer.handle, a.offset, a.size)
+            elif isinstance(a, Buffer):
+                arr[i].tag = abi.ARG_BUFFER
+                arr[i].u.buffer = abi._ArgBuffer(a.handle, 0, a.size_bytes)
+            elif isinstance(a, Texture):
+                arr[i].tag = abi.ARG_TEXTURE
+                arr[i].u.texture = abi._ArgTexture(a.handle, 0)
+            elif isinstance(a, BindlessArray):
+                arr[i].tag = abi.ARG_BINDLESS
+                arr[i].u.bindless = a.handle
+            elif isinstance(a, Accel):
+                arr[i].tag = abi.ARG_ACCEL
+                arr[i].u.accel = a.handle
+            else:  # uniform: a numpy scalar / array / bytes holding the value in the IR type's layout
+                data = np.ascontiguousarray(a) if not isinstance(a, (bytes, bytearray)) else np.frombuffer(bytes(a), dtype=np.uint8)
+                arr[i].tag = abi.ARG_UNIFORM
+                arr[i].u.uniform = abi._ArgUniform(data.ctypes.data, data.nbytes)
+                keep.append(data)
+                continue
+            keep.append(a)
+        ds = tuple(dispatch_size) + (1,) * (3 - len(dispatch_size))
+        cmd = abi.Command()
+        cmd.tag = abi.CMD_SHADER_DISPATCH
+        cmd.u.shader_dispatch = abi.CmdShaderDispatch(self.handle, (C.c_uint32 * 3)(*ds), arr, n)
+        return HostCommand(cmd, keep=keep)
+
+    def dispatch(self, dispatch_size, *args):
+        s = self.device.default_stream()
+        s.submit([self.dispatch_async(dispatch_size, *args)])
+        s.synchronize()
+
+    def destroy(self):
+        if self._alive and not self.device._closed:
+            self.device.iface.destroy_shader(self.device.handle, self.handle)
+        self._alive = False
 
 
 class HostCommand:
