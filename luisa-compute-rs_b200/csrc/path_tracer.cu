@@ -25,7 +25,8 @@ __device__ __forceinline__ V3 operator/(V3 a, float s) { return V3{a.x / s, a.y 
 __device__ __forceinline__ float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ V3 normalize(V3 a) { return a / length(a); }
+// lc_normalize(v) = v * rsqrt(dot(v, v)) with rsqrt(x) = 1 / sqrt(x): cpu/codegen/device_math.h:3588, cpu_prelude.h:7
+__device__ __forceinline__ V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
 
 // lc/src/rtx.rs:517-535
 __device__ __forceinline__ V3 offset_ray_origin(V3 p, V3 n) {

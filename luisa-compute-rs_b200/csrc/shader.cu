@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <stdexcept>
+#include <string>
 
 namespace lcb {
 
@@ -35,11 +36,23 @@ struct Nvrtc {
 
 const Nvrtc &nvrtc() {
     static Nvrtc api = [] {
-        const char *candidates[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12"};
+        // The traversal header uses 256-bit global loads (PTX ISA 8.8): NVRTC older than 12.9 cannot assemble them.  A process
+        // that imported PyTorch already holds torch's bundled (older) libnvrtc.so.12 under that soname, so the toolkit's copy is
+        // looked up by path first and every candidate is checked for its version.
+        const char *candidates[] = {getenv("LC_B200_NVRTC"), "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12",
+                                    "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12", "libnvrtc.so"};
         void *h = nullptr;
-        if (const char *env = getenv("LC_B200_NVRTC")) h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
-        for (const char *c : candidates) if (!h) h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
-        if (!h) throw std::runtime_error("create_shader needs NVRTC (libnvrtc.so.12) and it could not be loaded; set LC_B200_NVRTC to its path");
+        std::string seen;
+        for (const char *c : candidates) {
+            if (!c || h) continue;
+            void *lib = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+            if (!lib) continue;
+            int major = 0, minor = 0;
+            auto version = (int (*)(int *, int *))dlsym(lib, "nvrtcVersion");
+            if (version && version(&major, &minor) == 0 && (major > 12 || (major == 12 && minor >= 9))) h = lib;
+            else { seen += std::string(" ") + c + " (" + std::to_string(major) + "." + std::to_string(minor) + ")"; dlclose(lib); }
+        }
+        if (!h) throw std::runtime_error("create_shader needs NVRTC >= 12.9 (libnvrtc.so.12) and none could be loaded; tried:" + seen + "; set LC_B200_NVRTC to its path");
         Nvrtc a{};
         auto sym = [&](const char *n) { void *p = dlsym(h, n); if (!p) throw std::runtime_error(std::string("NVRTC symbol missing: ") + n); return p; };
         a.CreateProgram = (decltype(a.CreateProgram))sym("nvrtcCreateProgram");

@@ -1,0 +1,238 @@
+"""The DSL kernels of the reference's ray-tracing examples, built as ir::KernelModule values (the form `create_shader` receives).
+
+With no Rust toolchain in the image the `track!` closures of luisa_compute/examples/{raytracing,path_tracer}.rs cannot be run
+through the real frontend, so they are transcribed here statement by statement onto `ir.KernelBuilder`, emitting for every DSL
+operation the `Func` / `Instruction` the frontend emits (lang/types/*.rs operators -> Func::Add.., `Var::load/store` ->
+Load / Update, `if` -> If + Phi, `while` / `for` -> GenericLoop, `Callable::new_static` -> Func::Callable, struct / vector
+constructors -> Func::Struct / Vec3, `lc_info!`-free).  The device lowers them with the same code path a Rust-built module
+would take (csrc/ir_lower.cpp): resources arrive as captures and arguments exactly as in the examples.
+"""
+import math
+
+import numpy as np
+
+from . import ir
+from .ir import Func
+
+
+def common_types(k):
+    """Ray / SurfaceHit / Index as the IR sees them (rtx.rs:329-366: Ray is #[repr(C, align(16))], hit structs align(8))."""
+    f3 = k.array(k.f32, 3)
+    ray = k.struct([f3, k.f32, f3, k.f32], align=16)
+    hit = k.struct([k.u32, k.u32, k.f322, k.f32], align=8)
+    return f3, ray, hit
+
+
+def _to_array3(k, v, f3):
+    """Expr::<[f32; 3]>::from(Float3)"""
+    return k.call(Func.Array, [v.x, v.y, v.z], f3)
+
+
+def _to_float3(k, a):
+    """Float3::from([f32; 3])"""
+    return k.vec(k.f323, a.extract(0), a.extract(1), a.extract(2))
+
+
+def make_ray(k, ray_ty, f3, o, d, tmin, tmax):
+    return k.make_struct(ray_ty, _to_array3(k, o, f3), k.lit(k.f32, tmin), _to_array3(k, d, f3), k.lit(k.f32, tmax))
+
+
+def offset_ray_origin(k, p, n):
+    """rtx.rs:517-535"""
+    origin, float_scale, int_scale = 1.0 / 32.0, 1.0 / 65536.0, 256.0
+    of_i = (k.f(int_scale) * n).cast(k.i323)
+    p_i = p.bitcast(k.i323) + p.lt(0.0).select(-of_i, of_i)
+    return p.abs().lt(origin).select(p + k.f(float_scale) * n, p_i.bitcast(k.f323))
+
+
+def raytracing_kernel(accel_handle, image_handle, width, height):
+    """examples/raytracing.rs:44-71 — `Kernel::<fn()>`: the accel and the Byte4 image are captures."""
+    k = ir.KernelBuilder(block_size=(16, 16, 1))
+    f3, ray_ty, hit_ty = common_types(k)
+    accel = k.capture_accel(accel_handle)
+    img = k.capture_tex2d(k.f324, image_handle)
+
+    def body():
+        px = k.dispatch_id().permute(0, 1)
+        xy = px.cast(k.f322) / k.vec(k.f322, float(width), float(height))
+        xy = k.f(2.0) * xy - 1.0
+        o = k.vec(k.f323, 0.0, 0.0, -1.0)
+        d = (k.vec(k.f323, xy.x, xy.y, 0.0) - o).normalize()
+        ray = make_ray(k, ray_ty, f3, o, d, 1e-3, 1e9)
+        hit = accel.trace_closest(ray, 0xFF, hit_ty)
+        bary = hit.extract(2)
+        color = hit.extract(0).ne(0xFFFFFFFF).select(k.vec(k.f323, bary.x, bary.y, 1.0), k.vec(k.f323, 0.0, 0.0, 0.0))
+        img.tex_write(px, k.vec(k.f324, color.x, color.y, color.z, 1.0))
+    k.body(body)
+    k.finish()
+    return k
+
+
+CBOX_MATERIALS = [(0.725, 0.710, 0.680)] * 3 + [(0.140, 0.450, 0.091), (0.630, 0.065, 0.050)] + [(0.725, 0.710, 0.680)] * 2 + [(0.0, 0.0, 0.0)]
+SPP_PER_DISPATCH = 32
+FRAC_1_PI = float(np.float32(0.318309886183790671537767526745028724))
+F32_MAX = float(np.finfo(np.float32).max)
+TAN_HALF_FOV = float(np.float32(np.tan(np.float32(0.5) * (np.float32(27.8) * np.float32(np.pi) / np.float32(180.0)))))
+
+
+def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=SPP_PER_DISPATCH, max_depth=10, polynomial_sincos=False):
+    """examples/path_tracer.rs:247-455 — `Kernel::<fn(Tex2d<Float4>, Tex2d<u32>, Accel, Uint2)>`; the two bindless heaps are captures.
+
+    polynomial_sincos=False emits Func::Sin / Func::Cos for the hemisphere sample like the example.  True replaces them by a
+    callable evaluating the fixed polynomial of csrc/path_tracer.cu / oracle.c (sincos_2pi), so that the random walks are
+    bit-reproducible against the CPU restatement (libm and libdevice differ in the last ulp of sin / cos)."""
+    k = ir.KernelBuilder(block_size=(16, 16, 1))
+    f3, ray_ty, hit_ty = common_types(k)
+    index_ty = k.array(k.u32, 3)
+    onb_ty = k.struct([k.f323, k.f323, k.f323])
+    vertex_heap = k.capture_bindless(vertex_heap_handle)
+    index_heap = k.capture_bindless(index_heap_handle)
+    image = k.arg_tex2d(k.f324)
+    seed_image = k.arg_tex2d(k.u32)
+    accel = k.arg_accel()
+    resolution = k.arg_uniform(k.u322)
+
+    def lcg_body(state):  # path_tracer.rs:271-279
+        state.store(k.u(1664525) * state.load() + k.u(1013904223))
+        k.return_((state.load() & k.u(0x00FFFFFF)).cast(k.f32) * k.f(1.0 / 16777216.0))
+    lcg = k.callable([(k.u32, False)], k.f32, lcg_body)
+
+    def sincos_body(u, s_out, c_out):  # csrc/path_tracer.cu sincos_2pi, in IR operations
+        kf = (u * 4.0 + 0.5).floor()
+        r = u - kf * 0.25
+        x = r * k.f(6.28318530717958647692)
+        x2 = x * x
+        sp = x2.fma(k.f(2.7557319e-6), k.f(-1.9841270e-4))
+        sp = sp.fma(x2, k.f(8.3333333e-3))
+        sp = sp.fma(x2, k.f(-1.6666667e-1))
+        sp = (sp * x2).fma(x, x)
+        cp = x2.fma(k.f(2.4801587e-5), k.f(-1.3888889e-3))
+        cp = cp.fma(x2, k.f(4.1666667e-2))
+        cp = cp.fma(x2, k.f(-0.5))
+        cp = cp.fma(x2, k.f(1.0))
+        q = kf.cast(k.i32) & k.i(3)
+        s_out.store(q.eq(0).select(sp, q.eq(1).select(cp, q.eq(2).select(-sp, -cp))))
+        c_out.store(q.eq(0).select(cp, q.eq(1).select(-sp, q.eq(2).select(-cp, sp))))
+        k.return_()
+    sincos = k.callable([(k.f32, True), (k.f32, False), (k.f32, False)], k.void, sincos_body) if polynomial_sincos else None
+
+    def body():
+        materials = k.const(k.array(k.f323, 8), CBOX_MATERIALS)
+        coord = k.dispatch_id().permute(0, 1)
+        frame_size = k.min(resolution.x, resolution.y).cast(k.f32)
+        state = k.local_zero(k.u32)
+        state.store(seed_image.tex_read(coord))
+        rx = lcg(state)
+        ry = lcg(state)
+        pixel = (coord.cast(k.f322) + k.vec(k.f322, rx, ry)) / frame_size * 2.0 - 1.0
+        radiance = k.local_zero(k.f323)
+        radiance.store(k.vec(k.f323, 0.0, 0.0, 0.0))
+        sample = k.local_zero(k.u32)
+
+        def sample_body():
+            p = pixel * k.vec(k.f322, 1.0, -1.0)
+            origin = k.vec(k.f323, -0.01, 0.995, 5.0)
+            pixel3 = origin + k.vec(k.f323, p.x * k.f(TAN_HALF_FOV), p.y * k.f(TAN_HALF_FOV), -1.0)
+            direction = (pixel3 - origin).normalize()
+            ray = k.local_zero(ray_ty)
+            ray.store(make_ray(k, ray_ty, f3, origin, direction, 0.0, F32_MAX))
+            beta = k.local_zero(k.f323)
+            beta.store(k.vec(k.f323, 1.0, 1.0, 1.0))
+            pdf_bsdf = k.local_zero(k.f32)
+            pdf_bsdf.store(k.f(0.0))
+            light_position = k.vec(k.f323, -0.24, 1.98, 0.16)
+            light_u = k.vec(k.f323, -0.24, 1.98, -0.22) - light_position
+            light_v = k.vec(k.f323, 0.23, 1.98, 0.16) - light_position
+            light_emission = k.vec(k.f323, 17.0, 12.0, 4.0)
+            light_area = light_u.cross(light_v).length()
+            light_normal = light_u.cross(light_v).normalize()
+            depth = k.local_zero(k.u32)
+
+            def bounce():
+                hit = accel.trace_closest(ray.load(), 0xFF, hit_ty)
+                inst, prim, bary = hit.extract(0), hit.extract(1), hit.extract(2)
+                k.if_(inst.ne(0xFFFFFFFF).not_(), lambda: k.break_())
+                tri = index_heap.bindless_buffer_read(inst, prim, index_ty)
+                p0 = _to_float3(k, vertex_heap.bindless_buffer_read(inst, tri.extract(0), f3))
+                p1 = _to_float3(k, vertex_heap.bindless_buffer_read(inst, tri.extract(1), f3))
+                p2 = _to_float3(k, vertex_heap.bindless_buffer_read(inst, tri.extract(2), f3))
+                pnt = (k.f(1.0) - bary.x - bary.y) * p0 + bary.x * p1 + bary.y * p2  # SurfaceHit::interpolate, rtx.rs:384
+                n = (p1 - p0).cross(p2 - p0).normalize()
+                origin_w = _to_float3(k, ray.gep(0).load())
+                direction_w = _to_float3(k, ray.gep(2).load())
+                cos_wi = -direction_w.dot(n)
+                k.if_(cos_wi.lt(1e-4), lambda: k.break_())
+                pp = offset_ray_origin(k, pnt, n)
+                albedo = materials.extract(inst)
+
+                def hit_light():
+                    def first():
+                        radiance.store(radiance.load() + light_emission)
+
+                    def later():
+                        pdf_light = (pnt - origin_w).length_squared() / (light_area * cos_wi)
+                        mis_weight = pdf_bsdf.load() / k.max(pdf_bsdf.load() + pdf_light, k.f(1e-4))
+                        radiance.store(radiance.load() + mis_weight * beta.load() * light_emission)
+                    k.if_(depth.load().eq(0), first, later)
+                    k.break_()
+
+                def sample_light():
+                    ux_light = lcg(state)
+                    uy_light = lcg(state)
+                    p_light = light_position + ux_light * light_u + uy_light * light_v
+                    pp_light = offset_ray_origin(k, p_light, light_normal)
+                    d_light = (pp - pp_light).length()
+                    wi_light = (pp_light - pp).normalize()
+                    shadow_ray = make_ray(k, ray_ty, f3, offset_ray_origin(k, pp, n), wi_light, 0.0, d_light)
+                    occluded = accel.trace_any(shadow_ray, 0xFF)
+                    cos_wi_light = wi_light.dot(n)
+                    cos_light = -light_normal.dot(wi_light)
+
+                    def add_direct():
+                        pdf_light = (d_light * d_light) / (light_area * cos_light)
+                        pdf_b = cos_wi_light * k.f(FRAC_1_PI)
+                        mis_weight = pdf_light / k.max(pdf_light + pdf_b, k.f(1e-4))
+                        bsdf = albedo * k.f(FRAC_1_PI) * cos_wi_light
+                        radiance.store(radiance.load() + beta.load() * bsdf * mis_weight * light_emission / k.max(pdf_light, k.f(1e-4)))
+                    k.if_(occluded.not_() & cos_wi_light.gt(1e-4) & cos_light.gt(1e-4), add_direct)
+                k.if_(inst.eq(7), hit_light, sample_light)
+                # sample BSDF: make_onb (path_tracer.rs:311-321) + cosine_sample_hemisphere (:323-327)
+                binormal = k.if_phi(n.x.abs().gt(n.z.abs()), lambda: k.vec(k.f323, -n.y, n.x, 0.0), lambda: k.vec(k.f323, 0.0, -n.z, n.y))
+                tangent = binormal.cross(n).normalize()
+                onb = k.make_struct(onb_ty, tangent, binormal, n)
+                ux = lcg(state)
+                uy = lcg(state)
+                r = ux.sqrt()
+                if polynomial_sincos:
+                    s_var, c_var = k.local_zero(k.f32), k.local_zero(k.f32)
+                    sincos(uy, s_var, c_var)
+                    sin_phi, cos_phi = s_var.load(), c_var.load()
+                else:
+                    phi = k.f(2.0 * math.pi) * uy
+                    sin_phi, cos_phi = phi.sin(), phi.cos()
+                local = k.vec(k.f323, r * cos_phi, r * sin_phi, (k.f(1.0) - ux).sqrt())
+                new_direction = onb.extract(0) * local.x + onb.extract(1) * local.y + onb.extract(2) * local.z  # Onb::to_world
+                ray.store(make_ray(k, ray_ty, f3, pp, new_direction, 0.0, F32_MAX))
+                beta.store(beta.load() * albedo)
+                pdf_bsdf.store(cos_wi * k.f(FRAC_1_PI))
+                # russian roulette
+                lum = k.vec(k.f323, 0.212671, 0.715160, 0.072169).dot(beta.load())
+                k.if_(lum.eq(0.0), lambda: k.break_())
+                q = k.max(lum, k.f(0.05))
+                rr = lcg(state)
+                k.if_(rr.gt(q), lambda: k.break_())
+                beta.store(beta.load() / q)
+                depth.store(depth.load() + k.u(1))
+            k.generic_loop(lambda: depth.load().lt(max_depth), bounce)
+        k.generic_loop(lambda: sample.load().lt(spp_per_dispatch), sample_body, lambda: sample.store(sample.load() + k.u(1)))
+        radiance.store(radiance.load() / k.f(float(spp_per_dispatch)))
+        seed_image.tex_write(coord, state.load())
+        k.if_(radiance.load().is_nan().any(), lambda: radiance.store(k.vec(k.f323, 0.0, 0.0, 0.0)))
+        clamped = radiance.load().clamp(k.vec(k.f323, k.f(0.0)), k.vec(k.f323, k.f(30.0)))
+        old = image.tex_read(coord)
+        spp = old.w
+        total = clamped + old.permute(0, 1, 2)
+        image.tex_write(coord, k.vec(k.f324, total.x, total.y, total.z, spp + 1.0))
+    k.body(body)
+    k.finish()
+    return k

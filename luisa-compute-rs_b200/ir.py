@@ -399,7 +399,10 @@ class Module:
         if ty.kind == T_PRIMITIVE:
             p = ty.rec.u.primitive
             c.tag = [C_BOOL, C_I8, C_U8, C_I16, C_U16, C_I32, C_U32, C_I64, C_U64, C_F16, C_F32, C_F64][p]
-            setattr(c.u, ["b", "i8", "u8", "i16", "u16", "i32", "u32", "i64", "u64", None, "f32", "f64"][p], value)
+            if p == 9:  # Const::Float16(c_half{bits})
+                c.u.u16 = _struct.unpack("<H", _struct.pack("<e", value))[0]
+            else:
+                setattr(c.u, ["b", "i8", "u8", "i16", "u16", "i32", "u32", "i64", "u64", None, "f32", "f64"][p], value)
         else:
             data = self.pack(ty, value)
             c.tag = C_GENERIC

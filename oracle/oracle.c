@@ -705,7 +705,8 @@ static inline v3 vdiv(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
 static inline float vdot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 static inline v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 static inline float vlength(v3 a) { return sqrtf(vdot(a, a)); }
-static inline v3 vnormalize(v3 a) { return vdiv(a, vlength(a)); }
+/* lc_normalize(v) = v * rsqrt(dot(v, v)) with rsqrt(x) = 1 / sqrt(x): cpu/codegen/device_math.h:3588, cpu_prelude.h:7 */
+static inline v3 vnormalize(v3 a) { return vscale(a, 1.0f / sqrtf(vdot(a, a))); }
 static inline v3 voffset(v3 p, v3 n) { float pi[3] = {p.x, p.y, p.z}, ni[3] = {n.x, n.y, n.z}, o[3]; oracle_offset_ray_origin(pi, ni, o); return V(o[0], o[1], o[2]); }
 
 static inline void sincos_2pi(float u, float *s, float *c) {
