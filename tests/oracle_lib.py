@@ -27,8 +27,7 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # make: a no-op when liboracle.so is newer than oracle.c, and never a stale checker after an edit
         L = C.CDLL(_SO)
         L.oracle_scene_new.restype = C.c_void_p
         L.oracle_scene_free.argtypes = [C.c_void_p]
