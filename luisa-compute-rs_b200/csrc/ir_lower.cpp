@@ -135,7 +135,11 @@ struct TypeTable {
                 defs += o.str();
                 return n;
             }
-            case Type::Opaque: fail("opaque type " + slice_to_string(t->opaque) + " (RayQuery objects inside DSL kernels are served by the batch entry point lc_b200_ray_query)");
+            case Type::Opaque: {
+                const std::string n = slice_to_string(t->opaque);
+                if (n == "LC_RayQueryAll" || n == "LC_RayQueryAny") return "lc_ray_query_state";  // cpp.rs:154-162
+                fail("opaque type " + n + " is not known to the B200 lowering");
+            }
             default: fail("unsupported type tag " + std::to_string(t->tag));
         }
     }
@@ -248,6 +252,7 @@ void collect_phis(const BasicBlock *bb, PhiMap &pm) {
                 for (const auto &c : ins->switch_.cases) collect_phis(c.block.ptr, pm);
                 break;
             case Instruction::AdDetach: collect_phis(ins->ad_detach.ptr, pm); break;
+            case Instruction::RayQuery: collect_phis(ins->ray_query.on_triangle_hit.ptr, pm); collect_phis(ins->ray_query.on_procedural_hit.ptr, pm); break;
             default: break;
         }
     });
@@ -589,6 +594,16 @@ struct FunctionEmitter {
             case Func::RayTracingInstanceUserId: need(2); value("lc_accel_instance_user_id(" + a[0] + ", " + a[1] + ")"); break;
             case Func::RayTracingSetInstanceVisibility: need(3); line("lc_set_instance_visibility(" + join(a) + ");"); break;
             case Func::RayTracingSetInstanceUserId: need(3); line("lc_set_instance_user_id(" + join(a) + ");"); break;
+            // row 7: RayQuery objects (cpp.rs:1401-1472).  The object is a mutable local; Instruction::RayQuery runs the traversal.
+            case Func::RayTracingQueryAll: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_all(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
+            case Func::RayTracingQueryAny: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
+            case Func::RayQueryWorldSpaceRay: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".ray)"); break;
+            case Func::RayQueryTriangleCandidateHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".cur_triangle)"); break;
+            case Func::RayQueryProceduralCandidateHit: need(1); value("lc_zero<" + ts + ">()"); break;  // the device has no procedural primitives: never invoked
+            case Func::RayQueryCommittedHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".hit)"); break;
+            case Func::RayQueryCommitTriangle: need(1); line(a[0] + ".cur_committed = true;"); break;
+            case Func::RayQueryCommitProcedural: need(2); line(a[0] + ".cur_committed = true;"); break;
+            case Func::RayQueryTerminate: need(1); line(a[0] + ".terminated = true;"); break;
 
             case Func::Callable: {
                 const std::string name = callable_name(f.callable);
@@ -723,8 +738,16 @@ struct FunctionEmitter {
             }
             case Instruction::AdScope: case Instruction::AdDetach:
                 fail("autodiff scopes must be removed by the frontend's transform pipeline before create_shader");
-            case Instruction::RayQuery:
-                fail("Instruction::RayQuery inside a DSL kernel is not lowered; RayQuery traversals are served in batch form by lc_b200_ray_query (SURVEY.md §8a row 7)");
+            case Instruction::RayQuery: {  // cpp.rs:1807-1830: the two candidate blocks become callbacks of the traversal
+                const bool old = in_generic_loop; in_generic_loop = false;
+                line("lc_ray_query(" + ref(ins->ray_query.ray_query) + ", [&]()");
+                emit_block(ins->ray_query.on_triangle_hit.ptr);
+                line(", [&]()");
+                emit_block(ins->ray_query.on_procedural_hit.ptr);
+                line(");");
+                in_generic_loop = old;
+                break;
+            }
             default: fail("unknown instruction tag " + std::to_string(ins->tag));
         }
     }

@@ -209,8 +209,14 @@ __device__ __forceinline__ bool refine_bary(const RaySetup &r, const float4 v0, 
 // reference's SurfaceHit convention (miss: inst = prim = ~0, bary = 0, t = ray.tmax); ANY returns only hit / no hit.
 struct DeviceHit { uint32_t inst, prim; float u, v, t; };
 
-template <bool ANY>
-__device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask) {
+// QUERY adds the RayQuery rules (AccelImpl::ray_query, cpu/accel.rs:582-800; batch form: trace.cu kQueryAll / kQueryAny):
+// triangles of NON-opaque instances are candidates handed to `hook(inst, prim, u, v, t)` with the canonical fp32
+// barycentrics; it returns bit 0 = commit (RayQueryCommitTriangle), bit 1 = terminate (RayQueryTerminate).  Triangles of
+// opaque instances commit directly.  `first` ends the traversal at the first committed hit (RayQueryAny).
+struct NoCandidateHook { __device__ __forceinline__ int operator()(uint32_t, uint32_t, float, float, float) const { return 1; } };
+
+template <bool ANY, bool QUERY, class Hook>
+__device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask, bool first, Hook &hook) {
     DeviceHit h{kNone, kNone, 0.f, 0.f, rb.w};
     if (!acc.tlas_nodes) return h;
     uint2 stack[kTraversalStack];
@@ -220,6 +226,7 @@ __device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float
     const float tmin = ra.w, ray_tmax = rb.w;
     float tbest = rb.w;
     uint32_t cur_inst = kNone, hit_slot = 0;
+    bool cur_opaque = true, stop = false;
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
     uint2 G = make_uint2(0u, 0x80000000u), Gt = make_uint2(0u, 0u);
@@ -245,9 +252,19 @@ __device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float
                 float t, V, W, det;
                 if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, V, W, det)) {
                     const uint32_t prim = __float_as_uint(v0.w);
-                    if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; return h; }
-                    const bool better = t < tbest || h.inst == kNone || (t == tbest && (cur_inst < h.inst || (cur_inst == h.inst && prim < h.prim)));
-                    if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; hit_slot = Gt.x + bit; }
+                    bool commit = true;
+                    if (QUERY && !cur_opaque) {
+                        const float rdet = __frcp_rn(det);
+                        const int verdict = hook(cur_inst, prim, __fmul_rn(V, rdet), __fmul_rn(W, rdet), t);
+                        commit = (verdict & 1) != 0; stop = (verdict & 2) != 0;
+                    }
+                    if (commit) {
+                        if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; return h; }
+                        const bool better = t < tbest || h.inst == kNone || (t == tbest && (cur_inst < h.inst || (cur_inst == h.inst && prim < h.prim)));
+                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; hit_slot = Gt.x + bit; }
+                        if (QUERY && first) stop = true;
+                    }
+                    if (QUERY && stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
                 }
             } else {
                 const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
@@ -263,6 +280,7 @@ __device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float
                     tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
                     setup_object(r, ra, rb, m0, m1, m2);
                     cur_inst = inst;
+                    if (QUERY) cur_opaque = (meta.z & 2u) != 0u;
                     G = make_uint2(0u, 0x80000000u);
                     Gt = make_uint2(0u, 0u);
                     break;
@@ -301,6 +319,12 @@ __device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float
         }
     }
     return h;
+}
+
+template <bool ANY>
+__device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask) {
+    NoCandidateHook hook;
+    return trace_one_impl<ANY, false>(acc, ra, rb, mask, false, hook);
 }
 
 }  // namespace lcb

@@ -236,3 +236,32 @@ def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=S
     k.body(body)
     k.finish()
     return k
+
+
+def ray_query_kernel(radius, any_hit=False):
+    """The query of examples/ray_query.rs:135-170 over a ray buffer: `accel.traverse(ray).on_surface_hit(|c| if disc(c.bary) { c.commit() })`,
+    one ray per thread, CommittedHit written per ray.  Args: rays Buffer<Ray>, committed Buffer<CommittedHit>, accel, mask: u32."""
+    k = ir.KernelBuilder(block_size=(128, 1, 1))
+    f3, ray_ty, hit_ty = common_types(k)
+    committed_ty = k.struct([k.u32, k.u32, k.f322, k.u32, k.f32], align=8)
+    rays, out, accel, mask = k.arg_buffer(ray_ty), k.arg_buffer(committed_ty), k.arg_accel(), k.arg_uniform(k.u32)
+
+    def body():
+        i = k.dispatch_id().x
+        rq = accel.query(rays.read(i), mask, any_hit)
+
+        def on_surface_hit():
+            cand = k.call(Func.RayQueryTriangleCandidateHit, [rq], hit_ty)
+            bary = cand.extract(2)
+            u, v = bary.x, bary.y
+            w = k.f(1.0) - u - v
+            r2 = k.f(radius) * k.f(radius)
+            xy = w.fma(w, u * u)
+            yz = u.fma(u, v * v)
+            xz = w.fma(w, v * v)
+            k.if_(xy.lt(r2) & yz.lt(r2) & xz.lt(r2), lambda: k.call(Func.RayQueryCommitTriangle, [rq], k.void))
+        k.ray_query(rq, on_surface_hit, None)
+        out.write(i, k.call(Func.RayQueryCommittedHit, [rq], committed_ty))
+    k.body(body)
+    k.finish()
+    return k

@@ -180,13 +180,17 @@ class _Switch(C.Structure):
     _fields_ = [("value", sz), ("default_", vp), ("cases", Slice)]
 
 
+class _RayQuery(C.Structure):
+    _fields_ = [("ray_query", sz), ("on_triangle_hit", vp), ("on_procedural_hit", vp)]
+
+
 class _Print(C.Structure):
     _fields_ = [("fmt", Slice), ("args", Slice)]
 
 
 class _InstrU(C.Union):
     _fields_ = [("local", _Local), ("argument", _Argument), ("const_", ConstS), ("update", _Update), ("call", _Call), ("phi", Slice), ("return_", sz), ("loop", _Loop),
-                ("generic_loop", _GenericLoop), ("if_", _If), ("switch_", _Switch), ("print", _Print), ("comment", Slice)]
+                ("generic_loop", _GenericLoop), ("if_", _If), ("switch_", _Switch), ("ray_query", _RayQuery), ("print", _Print), ("comment", Slice)]
 
 
 class InstructionS(C.Structure):
@@ -210,7 +214,8 @@ LAYOUT = {  # compared with tests/golden/ir_layout_reference.json
     "offsetof.Func.callable": FuncS.u.offset, "offsetof.Const.float32": ConstS.u.offset, "offsetof.Const.generic.type": ConstS.u.offset + _GenericConst.type.offset,
     "offsetof.Instruction.call.func": InstructionS.u.offset + _Call.func.offset, "offsetof.Instruction.call.args": InstructionS.u.offset + _Call.args.offset,
     "offsetof.Instruction.generic_loop.update": InstructionS.u.offset + _GenericLoop.update.offset, "offsetof.Instruction.if.false_branch": InstructionS.u.offset + _If.false_branch.offset,
-    "offsetof.Instruction.switch.cases": InstructionS.u.offset + _Switch.cases.offset, "offsetof.Node.instruction": NodeS.instruction.offset,
+    "offsetof.Instruction.switch.cases": InstructionS.u.offset + _Switch.cases.offset,
+    "offsetof.Instruction.ray_query.on_procedural_hit": InstructionS.u.offset + _RayQuery.on_procedural_hit.offset, "offsetof.Node.instruction": NodeS.instruction.offset,
 }
 
 
@@ -329,6 +334,13 @@ class Module:
         ty = self._intern(("struct", tuple(f.key for f in fields), a), init, size, a)
         ty.fields = list(fields)
         return ty
+
+    def opaque(self, name):
+        """Type::Opaque(name): "LC_RayQueryAll" / "LC_RayQueryAny" are the RayQuery objects (rtx.rs:672-700)."""
+        def init(t):
+            t.tag = T_OPAQUE
+            t.u.opaque = self.bytes_slice(name.encode())
+        return self._intern(("opaque", name), init, 0, 1)
 
     # shorthand for the common vector types
     def __getattr__(self, name):
@@ -495,6 +507,14 @@ class Module:
         ins = self._raw_instr(I_SWITCH)
         ins.u.switch_.value, ins.u.switch_.default_ = value.ref, db
         ins.u.switch_.cases = self.slice(SwitchCase, [SwitchCase(v, b) for v, b in blocks])
+        self.append(self.void, ins)
+
+    def ray_query(self, rq, on_triangle_fn, on_procedural_fn=None):
+        """Instruction::RayQuery (ir.rs:1251-1255): traverse; the two blocks are the candidate callbacks."""
+        tb, _ = self.block(on_triangle_fn)
+        pb, _ = self.block(on_procedural_fn)
+        ins = self._raw_instr(I_RAYQUERY)
+        ins.u.ray_query.ray_query, ins.u.ray_query.on_triangle_hit, ins.u.ray_query.on_procedural_hit = rq.ref, tb, pb
         self.append(self.void, ins)
 
     def break_(self):
@@ -710,6 +730,11 @@ class Resource(Value):
 
     def trace_any(self, ray, mask):
         return self.m.call(Func.RayTracingTraceAny, [self, ray, self.m.lit(self.m.u32, mask)], self.m.bool)
+
+    def query(self, ray, mask, any=False):
+        """`accel.traverse(ray, opts)` / `traverse_any` (rtx.rs:871-902): the RayQuery object."""
+        m = self.m
+        return m.call(Func.RayTracingQueryAny if any else Func.RayTracingQueryAll, [self, ray, m.lit(m.u32, mask)], m.opaque("LC_RayQueryAny" if any else "LC_RayQueryAll"))
 
     def atomic_fetch_add(self, index, value):
         m = self.m
