@@ -212,6 +212,12 @@ struct DeviceObj {
     // grow-only device staging for the host entry points
     uint8_t *stage_rays = nullptr, *stage_out = nullptr; size_t stage_rays_cap = 0, stage_out_cap = 0;
     std::mutex mu;
+    // Grow-only arena for BLAS builds: the builder's scratch and the full-capacity node array a build is collapsed into before
+    // compaction.  A MeshBuild ends synchronised, so one arena serves every mesh of the device (build_mu serialises them);
+    // rebuilding the same scene every frame (C4) then touches no allocator at all.  Stream-ordered pool allocations of these
+    // multi-GB blocks made a rebuild after a few refits cost 15-30 ms instead of 8 (tools/micro/rebuild_probe.py).
+    uint8_t *build_arena = nullptr; size_t build_arena_cap = 0;
+    std::mutex build_mu;
 };
 
 template <class T> T *as(uint64_t h) { if (h == 0 || h == LCB_INVALID_HANDLE) fatal("invalid resource handle"); return reinterpret_cast<T *>(h); }
@@ -315,40 +321,55 @@ void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
         CUDA_CHECK(cudaFreeAsync(m->refit.parent, st)); CUDA_CHECK(cudaFreeAsync(m->refit.boxes, st)); CUDA_CHECK(cudaFreeAsync(m->refit.counters, st));
         m->refit = RefitArrays{nullptr, nullptr, nullptr};
     }
-    if (m->nodes) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
-    if (m->tris) { CUDA_CHECK(cudaFreeAsync(m->tris, st)); m->tris = nullptr; }
+    // The mesh keeps its triangle block when the triangle count is unchanged and its node block when the new tree fits;
+    // everything transient lives in the device's build arena.
+    if (m->tris && n != m->n_tris) { CUDA_CHECK(cudaFreeAsync(m->tris, st)); m->tris = nullptr; }
+    if (n == 0 && m->nodes) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; m->node_capacity = 0; }
     m->built = true; m->n_tris = n; m->generation++;
     m->n_nodes = m->n_packed = 0;
     memset(&m->stats, 0, sizeof(m->stats));
     m->stats.primitive_count = n;
     if (n == 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return; }
-    BuildScratch layout = build_scratch_layout(nullptr, n);
-    void *scratch = nullptr;
-    CUDA_CHECK(cudaMallocAsync(&scratch, layout.total_bytes, st));
-    BuildScratch sc = build_scratch_layout(scratch, n);
-    WideNode *nodes = nullptr; PackedTri *tris = nullptr;
-    CUDA_CHECK(cudaMallocAsync((void **)&nodes, (size_t)n * sizeof(WideNode), st));
-    CUDA_CHECK(cudaMallocAsync((void **)&tris, (size_t)n * sizeof(PackedTri), st));
-    build_blas(st, n, in, sc, nodes, tris, d->lc);
+    std::lock_guard<std::mutex> arena_lock(d->build_mu);
+    const BuildScratch layout = build_scratch_layout(nullptr, n);
+    const size_t staging_off = (layout.total_bytes + 255) / 256 * 256, staging_bytes = (size_t)n * sizeof(WideNode);
+    const bool compact = m->option.allow_compaction;
+    const size_t arena_need = staging_off + (compact ? staging_bytes : 0);
+    if (arena_need > d->build_arena_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (d->build_arena) CUDA_CHECK(cudaFree(d->build_arena));
+        d->build_arena_cap = arena_need + arena_need / 8;
+        CUDA_CHECK(cudaMalloc((void **)&d->build_arena, d->build_arena_cap));
+    }
+    BuildScratch sc = build_scratch_layout(d->build_arena, n);
+    if (!m->tris) CUDA_CHECK(cudaMallocAsync((void **)&m->tris, (size_t)n * sizeof(PackedTri), st));
+    WideNode *target = nullptr;
+    if (compact) target = reinterpret_cast<WideNode *>(d->build_arena + staging_off);
+    else {
+        if (m->nodes && m->node_capacity != n) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
+        if (!m->nodes) { CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, staging_bytes, st)); m->node_capacity = n; }
+        target = m->nodes;
+    }
+    build_blas(st, n, in, sc, target, m->tris, d->lc);
     BuildHeader hdr;
     CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
     if (hdr.error) fatal("BVH build failed (code %u: %s)", hdr.error, hdr.error == 1 ? "tree deeper than the traversal stack" : "node capacity exceeded");
     if (hdr.emitted != n || hdr.prim_count != n) fatal("BVH build inconsistent: emitted %u of %u primitives", hdr.emitted, n);
     m->n_nodes = hdr.node_count; m->n_packed = hdr.prim_count;
-    if (m->option.allow_compaction && hdr.node_count < n) {
-        WideNode *cn = nullptr;
-        CUDA_CHECK(cudaMallocAsync((void **)&cn, (size_t)hdr.node_count * sizeof(WideNode), st));
-        CUDA_CHECK(cudaMemcpyAsync(cn, nodes, (size_t)hdr.node_count * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
-        CUDA_CHECK(cudaFreeAsync(nodes, st));
-        nodes = cn; m->node_capacity = hdr.node_count;
-    } else m->node_capacity = n;
-    CUDA_CHECK(cudaFreeAsync(scratch, st));
+    if (compact) {
+        // keep the old block if the new tree fits without wasting more than a quarter of it
+        if (m->nodes && (m->node_capacity < hdr.node_count || (size_t)m->node_capacity * 3 > (size_t)hdr.node_count * 4 + 1024)) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
+        if (!m->nodes) {
+            m->node_capacity = hdr.node_count + hdr.node_count / 16;
+            CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, (size_t)m->node_capacity * sizeof(WideNode), st));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(m->nodes, target, (size_t)hdr.node_count * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+    }
     CUDA_CHECK(cudaEventRecord(e1, st));
     CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    m->nodes = nodes; m->tris = tris;
     m->stats.wide_node_count = hdr.node_count; m->stats.packed_tri_count = hdr.prim_count;
     m->stats.bvh_bytes = (uint64_t)m->node_capacity * sizeof(WideNode) + (uint64_t)n * sizeof(PackedTri);
     m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.build_ms = ms;
@@ -789,6 +810,7 @@ void destroy_device(lcb_device_interface iface) {
     if (d->copy_out) cudaStreamDestroy(d->copy_out);
     if (d->stage_rays) cudaFree(d->stage_rays);
     if (d->stage_out) cudaFree(d->stage_out);
+    if (d->build_arena) cudaFree(d->build_arena);
     flush_launches(d);
     delete d;
 }

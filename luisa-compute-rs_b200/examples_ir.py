@@ -68,6 +68,23 @@ def raytracing_kernel(accel_handle, image_handle, width, height):
     return k
 
 
+def raytracing_rays(width, height):
+    """The rays `raytracing_kernel` generates, evaluated on the host in the kernel's fp32 operation order
+    (normalize = v * (1 / sqrt(dot(v, v))), device_math.h:3588): rows of (o, tmin, d, tmax), pixel-major."""
+    f = np.float32
+    ys, xs = np.meshgrid(np.arange(height, dtype=np.float32), np.arange(width, dtype=np.float32), indexing="ij")
+    x = f(2.0) * (xs / f(width)) - f(1.0)
+    y = f(2.0) * (ys / f(height)) - f(1.0)
+    dx, dy, dz = x - f(0.0), y - f(0.0), np.full_like(x, f(0.0) - f(-1.0))
+    inv = f(1.0) / np.sqrt((dx * dx + dy * dy) + dz * dz)
+    rays = np.zeros((height * width, 8), np.float32)
+    rays[:, 2] = -1.0
+    rays[:, 3] = f(1e-3)
+    rays[:, 4:7] = np.stack([dx * inv, dy * inv, dz * inv], -1).reshape(-1, 3)
+    rays[:, 7] = f(1e9)
+    return rays
+
+
 CBOX_MATERIALS = [(0.725, 0.710, 0.680)] * 3 + [(0.140, 0.450, 0.091), (0.630, 0.065, 0.050)] + [(0.725, 0.710, 0.680)] * 2 + [(0.0, 0.0, 0.0)]
 SPP_PER_DISPATCH = 32
 FRAC_1_PI = float(np.float32(0.318309886183790671537767526745028724))
