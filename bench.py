@@ -137,7 +137,7 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     v = n_sample / dt / 1e6
     sample = f"first {n_sample} rays of the C3 batch per step against the full 1M-triangle scene; oracle port (binned-SAH binary BVH, canonical fp32 triangle test), not Embree"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
@@ -191,8 +191,6 @@ def main():
     torch.cuda.set_device(local_rank)
     os.environ["LC_B200_DEVICE"] = str(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; the contract is ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = lc.Context()
@@ -351,7 +349,7 @@ def main():
                                "sample": f"first {n_sample} rays of the batch ({cpu_s:.1f} s) on the full 1M-triangle scene; oracle port (binned-SAH binary BVH built in {cpu_build_s:.1f} s single-threaded), not Embree"}
 
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     for b in (rb, hb, ob, vb, ib):
         b.destroy()
     accel.destroy(); mesh.destroy(); stream.destroy(); dev.close()
@@ -359,5 +357,21 @@ def main():
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries below us write there too (NCCL prints its version banner on stdout at
+    any NCCL_DEBUG level >= VERSION): keep the real stdout aside for the final line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    _claim_stdout()
     main()

@@ -282,3 +282,175 @@ def ray_query_kernel(radius, any_hit=False):
     k.body(body)
     k.finish()
     return k
+
+
+def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64):
+    """BASELINE config C5: the path tracer of examples/path_tracer.rs generalised to an instanced scene and to tile sharding
+    (SURVEY.md §8d / §8e).  One thread per pixel of a 64x64 tile; `tiles[k]` names the global tile a rank's k-th local tile is
+    (Morton round-robin, sharding.tiles_of_rank), results accumulate in a packed per-rank tile buffer that ONE all-gather
+    assembles.  The random stream is keyed by the GLOBAL pixel index and the frame number, so the image does not depend on
+    the number of GPUs.  Differences from the Cornell kernel: pinhole camera given by `camera` (origin, forward, right, up,
+    tan_half_fov), object-space vertices go through RayTracingInstanceTransform, normals face the viewer, a constant sky, one
+    emissive quad `light` = (position, u, v, emission, instance index), albedo by instance.
+    Args: tiles Buffer<u32>, out Buffer<Float4>, accel, params {resolution: Uint2, frame: u32, n_local_tiles: u32},
+    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s)."""
+    k = ir.KernelBuilder(block_size=(16, 16, 1))
+    f3, ray_ty, hit_ty = common_types(k)
+    index_ty = k.array(k.u32, 3)
+    params_ty = k.struct([k.u322, k.u32, k.u32])
+    vertex_heap = k.capture_bindless(vertex_heap_handle)
+    index_heap = k.capture_bindless(index_heap_handle)
+    tiles, out, accel, params = k.arg_buffer(k.u32), k.arg_buffer(k.f324), k.arg_accel(), k.arg_uniform(params_ty)
+    counters = k.arg_buffer(k.u64)
+    cam_o, cam_f, cam_r, cam_u, tan_half = camera
+    l_pos, l_u, l_v, l_emission, l_inst = light
+    palette = [(0.55, 0.50, 0.42), (0.42, 0.55, 0.40), (0.60, 0.45, 0.38), (0.45, 0.48, 0.58), (0.58, 0.56, 0.40), (0.40, 0.52, 0.52), (0.52, 0.42, 0.50), (0.50, 0.50, 0.50)]
+    albedos = [palette[i % 8] for i in range(n_instances)]
+    albedos[l_inst] = (0.0, 0.0, 0.0)
+
+    def lcg_body(state):
+        state.store(k.u(1664525) * state.load() + k.u(1013904223))
+        k.return_((state.load() & k.u(0x00FFFFFF)).cast(k.f32) * k.f(1.0 / 16777216.0))
+    lcg = k.callable([(k.u32, False)], k.f32, lcg_body)
+
+    def hash_body(v):  # PCG output permutation (Jarzynski & Olano 2020), integer-exact on every device
+        s = v * k.u(747796405) + k.u(2891336453)
+        w = ((s >> ((s >> k.u(28)) + k.u(4))) ^ s) * k.u(277803737)
+        k.return_((w >> k.u(22)) ^ w)
+    pcg = k.callable([(k.u32, True)], k.u32, hash_body)
+
+    def sincos_body(u, s_out, c_out):
+        kf = (u * 4.0 + 0.5).floor()
+        x = (u - kf * 0.25) * k.f(6.28318530717958647692)
+        x2 = x * x
+        sp = x2.fma(k.f(2.7557319e-6), k.f(-1.9841270e-4)).fma(x2, k.f(8.3333333e-3)).fma(x2, k.f(-1.6666667e-1))
+        sp = (sp * x2).fma(x, x)
+        cp = x2.fma(k.f(2.4801587e-5), k.f(-1.3888889e-3)).fma(x2, k.f(4.1666667e-2)).fma(x2, k.f(-0.5)).fma(x2, k.f(1.0))
+        q = kf.cast(k.i32) & k.i(3)
+        s_out.store(q.eq(0).select(sp, q.eq(1).select(cp, q.eq(2).select(-sp, -cp))))
+        c_out.store(q.eq(0).select(cp, q.eq(1).select(-sp, q.eq(2).select(-cp, sp))))
+        k.return_()
+    sincos = k.callable([(k.f32, True), (k.f32, False), (k.f32, False)], k.void, sincos_body)
+
+    def body():
+        materials = k.const(k.array(k.f323, n_instances), albedos)
+        res = params.extract(0)
+        frame = params.extract(1)
+        did = k.dispatch_id()
+        lx, gy = did.x, did.y
+        local_tile, ly = gy / k.u(tile), gy % k.u(tile)
+        tiles_x = (res.x + k.u(tile - 1)) / k.u(tile)
+        tile_id = tiles.read(local_tile)
+        px = (tile_id % tiles_x) * k.u(tile) + lx
+        py = (tile_id / tiles_x) * k.u(tile) + ly
+        k.if_((px.ge(res.x) | py.ge(res.y)), lambda: k.return_())
+        slot = local_tile * k.u(tile * tile) + ly * k.u(tile) + lx
+        state = k.local_zero(k.u32)
+        state.store(pcg(pcg(py * res.x + px) + frame))
+        radiance = k.local_zero(k.f323)
+        sample = k.local_zero(k.u32)
+        n_closest, n_any = k.local_zero(k.u32), k.local_zero(k.u32)
+        sky = k.vec(k.f323, 0.20, 0.25, 0.32)
+        light_position = k.vec(k.f323, *l_pos)
+        light_u, light_v = k.vec(k.f323, *l_u), k.vec(k.f323, *l_v)
+        light_emission = k.vec(k.f323, *l_emission)
+        light_area = light_u.cross(light_v).length()
+        light_normal = light_u.cross(light_v).normalize()
+        aspect = res.x.cast(k.f32) / res.y.cast(k.f32)
+
+        def sample_body():
+            jx, jy = lcg(state), lcg(state)
+            sx = ((px.cast(k.f32) + jx) / res.x.cast(k.f32) * 2.0 - 1.0) * k.f(tan_half) * aspect
+            sy = (k.f(1.0) - (py.cast(k.f32) + jy) / res.y.cast(k.f32) * 2.0) * k.f(tan_half)
+            origin = k.vec(k.f323, *cam_o)
+            direction = (k.vec(k.f323, *cam_f) + sx * k.vec(k.f323, *cam_r) + sy * k.vec(k.f323, *cam_u)).normalize()
+            ray = k.local_zero(ray_ty)
+            ray.store(make_ray(k, ray_ty, f3, origin, direction, 1e-4, F32_MAX))
+            beta = k.local_zero(k.f323)
+            beta.store(k.vec(k.f323, 1.0, 1.0, 1.0))
+            pdf_bsdf = k.local_zero(k.f32)
+            depth = k.local_zero(k.u32)
+
+            def bounce():
+                hit = accel.trace_closest(ray.load(), 0xFF, hit_ty)
+                n_closest.store(n_closest.load() + k.u(1))
+                inst, prim, bary = hit.extract(0), hit.extract(1), hit.extract(2)
+
+                def missed():
+                    radiance.store(radiance.load() + beta.load() * sky)
+                    k.break_()
+                k.if_(inst.eq(0xFFFFFFFF), missed)
+                tri = index_heap.bindless_buffer_read(inst, prim, index_ty)
+                xf = k.call(Func.RayTracingInstanceTransform, [accel, inst], k.matrix(4))
+
+                def world(i):
+                    p = _to_float3(k, vertex_heap.bindless_buffer_read(inst, tri.extract(i), f3))
+                    return (xf * k.vec(k.f324, p.x, p.y, p.z, 1.0)).permute(0, 1, 2)
+                p0, p1, p2 = world(0), world(1), world(2)
+                pnt = (k.f(1.0) - bary.x - bary.y) * p0 + bary.x * p1 + bary.y * p2
+                ng = (p1 - p0).cross(p2 - p0).normalize()
+                origin_w = _to_float3(k, ray.gep(0).load())
+                direction_w = _to_float3(k, ray.gep(2).load())
+                n = direction_w.dot(ng).gt(0.0).select(-ng, ng)
+                cos_wi = -direction_w.dot(n)
+                k.if_(cos_wi.lt(1e-4), lambda: k.break_())
+                pp = offset_ray_origin(k, pnt, n)
+                albedo = materials.extract(inst)
+
+                def hit_light():
+                    def first():
+                        radiance.store(radiance.load() + light_emission)
+
+                    def later():
+                        pdf_light = (pnt - origin_w).length_squared() / (light_area * cos_wi)
+                        mis_weight = pdf_bsdf.load() / k.max(pdf_bsdf.load() + pdf_light, k.f(1e-4))
+                        radiance.store(radiance.load() + mis_weight * beta.load() * light_emission)
+                    k.if_(depth.load().eq(0), first, later)
+                    k.break_()
+
+                def sample_light():
+                    p_light = light_position + lcg(state) * light_u + lcg(state) * light_v
+                    pp_light = offset_ray_origin(k, p_light, light_normal)
+                    d_light = (pp - pp_light).length()
+                    wi_light = (pp_light - pp).normalize()
+                    shadow_ray = make_ray(k, ray_ty, f3, offset_ray_origin(k, pp, n), wi_light, 0.0, d_light)
+                    occluded = accel.trace_any(shadow_ray, 0xFF)
+                    n_any.store(n_any.load() + k.u(1))
+                    cos_wi_light = wi_light.dot(n)
+                    cos_light = -light_normal.dot(wi_light)
+
+                    def add_direct():
+                        pdf_light = (d_light * d_light) / (light_area * cos_light)
+                        pdf_b = cos_wi_light * k.f(FRAC_1_PI)
+                        mis_weight = pdf_light / k.max(pdf_light + pdf_b, k.f(1e-4))
+                        bsdf = albedo * k.f(FRAC_1_PI) * cos_wi_light
+                        radiance.store(radiance.load() + beta.load() * bsdf * mis_weight * light_emission / k.max(pdf_light, k.f(1e-4)))
+                    k.if_(occluded.not_() & cos_wi_light.gt(1e-4) & cos_light.gt(1e-4), add_direct)
+                k.if_(inst.eq(l_inst), hit_light, sample_light)
+                binormal = k.if_phi(n.x.abs().gt(n.z.abs()), lambda: k.vec(k.f323, -n.y, n.x, 0.0), lambda: k.vec(k.f323, 0.0, -n.z, n.y)).normalize()
+                tangent = binormal.cross(n).normalize()
+                ux, uy = lcg(state), lcg(state)
+                r = ux.sqrt()
+                s_var, c_var = k.local_zero(k.f32), k.local_zero(k.f32)
+                sincos(uy, s_var, c_var)
+                new_direction = tangent * (r * c_var.load()) + binormal * (r * s_var.load()) + n * (k.f(1.0) - ux).sqrt()
+                ray.store(make_ray(k, ray_ty, f3, pp, new_direction, 0.0, F32_MAX))
+                beta.store(beta.load() * albedo)
+                pdf_bsdf.store(cos_wi * k.f(FRAC_1_PI))
+                lum = k.vec(k.f323, 0.212671, 0.715160, 0.072169).dot(beta.load())
+                k.if_(lum.eq(0.0), lambda: k.break_())
+                q = k.max(lum, k.f(0.05))
+                k.if_(lcg(state).gt(q), lambda: k.break_())
+                beta.store(beta.load() / q)
+                depth.store(depth.load() + k.u(1))
+            k.generic_loop(lambda: depth.load().lt(max_depth), bounce)
+        k.generic_loop(lambda: sample.load().lt(spp_per_dispatch), sample_body, lambda: sample.store(sample.load() + k.u(1)))
+        rad = radiance.load() / k.f(float(spp_per_dispatch))
+        rad = rad.is_nan().any().select(k.vec(k.f323, 0.0, 0.0, 0.0), rad).clamp(k.vec(k.f323, k.f(0.0)), k.vec(k.f323, k.f(30.0)))
+        old = out.read(slot)
+        out.write(slot, k.vec(k.f324, rad.x + old.x, rad.y + old.y, rad.z + old.z, old.w + 1.0))
+        counters.atomic_fetch_add(0, n_closest.load().cast(k.u64))
+        counters.atomic_fetch_add(1, n_any.load().cast(k.u64))
+    k.body(body)
+    k.finish()
+    return k
