@@ -398,6 +398,11 @@ LCB_EXPORT const char *lc_b200_version(void);
  * and lives for the process. */
 LCB_EXPORT const void *lc_b200_make_ir_type(size_t size, size_t alignment);
 
+/* Which algorithm forms the binary tree of a MeshBuild: -1 follow AccelOption.hint (FastTrace: chosen per mesh, FastBuild: LBVH),
+ * 0 LBVH split rule, 1 PLOC (agglomerative clustering), 2 chosen per mesh.  Returns the previous setting.  Hits never depend on it
+ * (the traversal's arithmetic is tree-independent); only build time and Mrays/s do.  Initial value: environment LC_B200_BUILDER. */
+LCB_EXPORT int lc_b200_set_builder(int builder);
+
 /* ---- IR -> CUDA lowering (create_shader), inspection entry points --------------------------------------------------
  * create_shader(LCKernelModule{ptr}) lowers the frontend's SSA IR (`*const ir::KernelModule`, proxy.rs:188-193;
  * layouts LC/include/luisa/rust/ir.hpp) to CUDA C++ whose ray-tracing builtins call this library's traversal

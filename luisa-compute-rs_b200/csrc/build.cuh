@@ -19,6 +19,8 @@ struct TriangleInput {
     const uint8_t *indices;  // 12-byte uint3 records
 };
 
+struct PlocState { uint32_t n_clusters; uint32_t n_nodes; uint32_t iterations; uint32_t pad; };
+
 // Scratch carved out of one allocation; sizes from build_scratch_layout().
 struct BuildScratch {
     BuildHeader *header;
@@ -29,13 +31,19 @@ struct BuildScratch {
     BinNode *bin;            // n-1
     int *flags;              // n-1
     unsigned long long *queue;  // n (collapse work items)
+    float4 *ploc_a, *ploc_b;    // PLOC cluster arrays (2 float4 per cluster), double-buffered
+    uint32_t *ploc_counts;      // per-tile survivor counts / offsets
+    PlocState *ploc_state;
     size_t total_bytes;
 };
 BuildScratch build_scratch_layout(void *base, uint32_t n);
 
 // Full build: prim boxes -> Morton -> sort -> fused hierarchy+refit -> collapse to WideNode + leaves.
 // `nodes` has capacity `n` nodes; `tris` capacity `n` (BLAS) / `prim_ids` capacity n (TLAS).
-void build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc);
+// builder: how the binary tree over the Morton-sorted primitives is formed — the LBVH split rule (k_hierarchy), PLOC (agglomerative
+// clustering, k_ploc_*), or chosen per mesh from the primitives' overlap (kBuilderAuto).
+enum { kBuilderLbvh = 0, kBuilderPloc = 1, kBuilderAuto = 2 };
+void build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder);
 void build_tlas(cudaStream_t s, uint32_t n_active, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc,
                 WideNode *nodes, uint32_t *prim_ids, LaunchCounter &lc);
 

@@ -7,6 +7,7 @@
 // optixAccelBuild (cuda_primitive.cpp:57-60).  No reference source exists for any of it.
 #include "build.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace lcb {
 
@@ -26,15 +27,17 @@ __global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags) {
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
         h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->bar_count = 0; h->bar_release = 0; h->max_depth = 0; h->error = 0;
+        h->prim_area_sum = 0.f;
     }
     for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
 }
 
 // block-reduce the centroid (shuffles, then one shared-memory round) and fold it into the header's ordered-int
 // bounds: 6 atomics per block instead of per warp
-__device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, BuildHeader *h) {
-    __shared__ float s_lo[8][3], s_hi[8][3];
+__device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, BuildHeader *h, float area = 0.f) {
+    __shared__ float s_lo[8][3], s_hi[8][3], s_area[8];
     float lo[3], hi[3];
+    if (!valid) area = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; k++) { lo[k] = valid ? c[k] : FLT_MAX; hi[k] = valid ? c[k] : -FLT_MAX; }
 #pragma unroll
@@ -44,13 +47,20 @@ __device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, B
             lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
         }
+        area += __shfl_xor_sync(0xffffffffu, area, off);
     }
     const int warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { s_lo[warp][k] = lo[k]; s_hi[warp][k] = hi[k]; }
+        s_area[warp] = area;
     }
     __syncthreads();
+    if (threadIdx.x == 3) {
+        float a = 0.f;
+        for (int w = 0; w < n_warps; w++) a += s_area[w];
+        if (a > 0.f) atomicAdd(&h->prim_area_sum, a);
+    }
     if (threadIdx.x < 3) {
         const int k = threadIdx.x;
         float l = s_lo[0][k], u = s_hi[0][k];
@@ -75,6 +85,7 @@ __device__ __forceinline__ void load_triangle(const TriangleInput &in, uint32_t 
 __global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32_t n, PrimBox *boxes, BuildHeader *h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float cen[3] = {0, 0, 0};
+    float area = 0.f;
     bool valid = i < n;
     if (valid) {
         float a[3], b[3], c[3];
@@ -89,8 +100,10 @@ __global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32
         pb.pad0 = pb.pad1 = 0;
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(pb.lo[0], pb.lo[1], pb.lo[2], 0.f);
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(pb.hi[0], pb.hi[1], pb.hi[2], 0.f);
+        const float dx = pb.hi[0] - pb.lo[0], dy = pb.hi[1] - pb.lo[1], dz = pb.hi[2] - pb.lo[2];
+        area = dx * dy + dy * dz + dz * dx;
     }
-    reduce_centroid_bounds(cen, valid, h);
+    reduce_centroid_bounds(cen, valid, h, area);
 }
 
 // World-space box of an instance: union of the BLAS root's (conservatively decoded) child
@@ -228,12 +241,177 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
     }
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018; fused search + merge after Benthin et al. 2022) ----
+// The alternative to k_hierarchy for AccelUsageHint::FastTrace.  The Morton-sorted primitives start as one cluster each.  Every
+// iteration, each cluster looks r positions to the left and right for the neighbour whose union box has the smallest surface
+// area; mutual nearest neighbours merge into a new binary node, and the surviving clusters are compacted in order.  The result
+// is a BinNode array of the same shape k_hierarchy produces (child boxes, ids, leaf counts), so the collapse is shared.
+// Per iteration: k_ploc_step (search + merge + survivor flags + per-block counts), k_ploc_scan (one block: exclusive scan of the
+// block counts, publishes the new cluster count), k_ploc_compact (ordered scatter).  A cluster is two float4:
+// (lo.xyz, id) and (hi.xyz, leaf count).
+constexpr int kPlocTile = 256;
+constexpr int kPlocMaxRadius = 16;
+
+
+__global__ void __launch_bounds__(256) k_ploc_init(const uint32_t *__restrict__ prim, const PrimBox *__restrict__ boxes, uint32_t n, float4 *clusters, PlocState *st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { st->n_clusters = n; st->n_nodes = 0; st->iterations = 0; }
+    if (i >= n) return;
+    const uint32_t p = prim[i];
+    const float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p], hi = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p + 1];
+    clusters[2 * (size_t)i] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(i | kLeafBit));
+    clusters[2 * (size_t)i + 1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(1u));
+}
+
+__device__ __forceinline__ float union_half_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(kPlocTile) k_ploc_step(const float4 *__restrict__ in, float4 *__restrict__ out, uint32_t *__restrict__ keep, uint32_t *__restrict__ block_counts,
+                                                         BinNode *bin, PlocState *st, int radius, int forced) {
+    __shared__ float4 s_lo[kPlocTile + 4 * kPlocMaxRadius], s_hi[kPlocTile + 4 * kPlocMaxRadius];
+    __shared__ int s_nn[kPlocTile + 2 * kPlocMaxRadius];
+    __shared__ uint32_t s_warp[kPlocTile / 32], s_node_base;
+    const uint32_t n = st->n_clusters;
+    const int base = (int)(blockIdx.x * kPlocTile);
+    if (n <= 1 || (uint32_t)base >= n) return;
+    const int r = radius, span = kPlocTile + 4 * r, first = base - 2 * r;
+    for (int t = threadIdx.x; t < span; t += kPlocTile) {
+        const int i = first + t;
+        if (i >= 0 && (uint32_t)i < n) { s_lo[t] = in[2 * (size_t)i]; s_hi[t] = in[2 * (size_t)i + 1]; }
+    }
+    __syncthreads();
+    // nearest neighbour (smallest union area, ties -> lower index) of every cluster of the tile and of r clusters on either side
+    for (int t = threadIdx.x; t < kPlocTile + 2 * r; t += kPlocTile) {
+        const int i = base - r + t;
+        int best = -1;
+        if (i >= 0 && (uint32_t)i < n) {
+            const float4 lo = s_lo[i - first], hi = s_hi[i - first];
+            if (forced) {  // pair (2k, 2k+1): halves the cluster count whatever the geometry (see run_pipeline_after_boxes)
+                best = (uint32_t)(i ^ 1) < n ? (i ^ 1) : -1;
+            } else {
+                // smallest union area; among equal areas the "buddy" i ^ 1 first (so that a run of identical boxes pairs up
+                // instead of forming a chain with a single mutual pair), then the lower index.  The order is symmetric in (i, j).
+                float best_a = FLT_MAX;
+                bool best_buddy = false;
+                for (int j = i - r; j <= i + r; j++) {
+                    if (j == i || j < 0 || (uint32_t)j >= n) continue;
+                    const float a = union_half_area(lo, hi, s_lo[j - first], s_hi[j - first]);
+                    const bool buddy = (i ^ 1) == j;
+                    if (best < 0 || a < best_a || (a == best_a && buddy && !best_buddy)) { best_a = a; best = j; best_buddy = buddy; }
+                }
+            }
+        }
+        s_nn[t] = best;
+    }
+    __syncthreads();
+    const int i = base + (int)threadIdx.x;
+    bool valid = (uint32_t)i < n, merge = false, survive = valid;
+    int j = -1;
+    if (valid) {
+        j = s_nn[i - (base - r)];
+        const bool mutual = j >= 0 && s_nn[j - (base - r)] == i;
+        merge = mutual && i < j;
+        survive = !(mutual && i > j);
+    }
+    // node ids: one atomic per block
+    const uint32_t merge_ballot = __ballot_sync(0xffffffffu, merge), lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(merge_ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kPlocTile / 32; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_node_base = tot ? atomicAdd(&st->n_nodes, tot) : 0u;
+    }
+    __syncthreads();
+    if (valid) {
+        float4 lo = s_lo[i - first], hi = s_hi[i - first];
+        if (merge) {
+            const uint32_t id = s_node_base + s_warp[warp] + __popc(merge_ballot & ((1u << lane) - 1u));
+            const float4 olo = s_lo[j - first], ohi = s_hi[j - first];
+            float4 *pn = reinterpret_cast<float4 *>(&bin[id]);
+            pn[0] = lo; pn[1] = hi; pn[2] = olo; pn[3] = ohi;   // (box, child id | leaf count) of the left and right child
+            const uint32_t count = __float_as_uint(hi.w) + __float_as_uint(ohi.w);
+            lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), __uint_as_float(id));
+            hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), __uint_as_float(count));
+        }
+        out[2 * (size_t)i] = lo; out[2 * (size_t)i + 1] = hi;
+        keep[i] = survive ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t keep_ballot = __ballot_sync(0xffffffffu, survive);
+    if (lane == 0) s_warp[warp] = __popc(keep_ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kPlocTile / 32; w++) tot += s_warp[w];
+        block_counts[blockIdx.x] = tot;
+    }
+}
+
+// one block: exclusive scan of the per-tile survivor counts, in place; publishes the new cluster count
+__global__ void __launch_bounds__(1024) k_ploc_scan(uint32_t *block_counts, PlocState *st) {
+    __shared__ uint32_t s_warp[32], s_carry;
+    const uint32_t n = st->n_clusters;
+    if (n <= 1) { if (threadIdx.x == 0) st->pad = 0; return; }  // nothing left to compact
+    const uint32_t n_blocks = (n + kPlocTile - 1) / kPlocTile;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < n_blocks ? block_counts[b] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= (uint32_t)o) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= (uint32_t)o) w += y; }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0u) + s_carry;
+        if (b < n_blocks) block_counts[b] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st->pad = n; st->n_clusters = s_carry; st->iterations++; }  // pad: the cluster count the compaction reads from
+}
+
+// ordered compaction of the survivors; `n_before` is implied by the block-count array (blocks past it hold stale data and exit)
+__global__ void __launch_bounds__(kPlocTile) k_ploc_compact(const float4 *__restrict__ in, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ block_offsets,
+                                                            float4 *__restrict__ out, const PlocState *st) {
+    __shared__ uint32_t s_warp[kPlocTile / 32];
+    const uint32_t n_before = st->pad;
+    const uint32_t i = blockIdx.x * kPlocTile + threadIdx.x;
+    if (n_before <= 1 || blockIdx.x * kPlocTile >= n_before) return;
+    const bool k = i < n_before && keep[i] != 0u;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, k), lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t off = block_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; w++) off += s_warp[w];
+    if (k) {
+        const uint32_t dst = off + __popc(ballot & ((1u << lane) - 1u));
+        out[2 * (size_t)dst] = in[2 * (size_t)i]; out[2 * (size_t)dst + 1] = in[2 * (size_t)i + 1];
+    }
+}
+
+__global__ void k_ploc_finish(const float4 *clusters, const PlocState *st, BuildHeader *h) {
+    if (st->n_clusters != 1) { h->error = 3u; return; }
+    const float4 lo = clusters[0], hi = clusters[1];
+    h->root = __float_as_uint(lo.w);
+    h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
+    h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+}
+
 // ---- collapse to 8-wide quantised nodes ----------------------------------------------------
 struct Child {
     float lo[3], hi[3];
     uint32_t id;     // binary node id (kLeafBit => single sorted leaf)
     uint32_t count;  // leaves below
-    uint32_t first;  // first sorted position covered
 };
 
 __device__ __forceinline__ float half_area(const Child &c) {
@@ -248,8 +426,6 @@ __device__ __forceinline__ void split_child(const BinNode *__restrict__ bin, con
     l.hi[0] = b.x; l.hi[1] = b.y; l.hi[2] = b.z; l.count = __float_as_uint(b.w);
     r.lo[0] = cc.x; r.lo[1] = cc.y; r.lo[2] = cc.z; r.id = __float_as_uint(cc.w);
     r.hi[0] = d.x; r.hi[1] = d.y; r.hi[2] = d.z; r.count = __float_as_uint(d.w);
-    l.first = c.id + 1 - l.count;  // internal node c.id sits between sorted leaves c.id and c.id+1
-    r.first = c.id + 1;
 }
 
 // The collapse only records which primitive lands in which packed slot; k_pack_tris then gathers the vertices of
@@ -304,7 +480,7 @@ __global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__
         // ================= phase A: choose the (up to) 8 children and their slots =================
         Child c;  // after phase A: the child of slot `sub`
         for (int k = 0; k < 3; k++) { c.lo[k] = FLT_MAX; c.hi[k] = -FLT_MAX; }
-        c.id = 0; c.count = 0; c.first = 0;
+        c.id = 0; c.count = 0;
         bool occupied = false;
         float nlo[3] = {0.f, 0.f, 0.f}; uint32_t ex[3] = {1u, 1u, 1u}; float inv_scale[3] = {0.f, 0.f, 0.f};
         if (active) {
@@ -315,7 +491,7 @@ __global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__
                 nc = 1;
                 if (sub == 0) {
                     for (int k = 0; k < 3; k++) { mine.lo[k] = h->root_lo[k]; mine.hi[k] = h->root_hi[k]; }
-                    mine.id = bnode; mine.count = 1; mine.first = bnode & ~kLeafBit;
+                    mine.id = bnode; mine.count = 1;
                 }
             } else {
                 Child self, l, r; self.id = bnode;
@@ -395,7 +571,7 @@ __global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__
             const uint32_t from = src & 7u;
 #pragma unroll
             for (int k = 0; k < 3; k++) { c.lo[k] = GSHFL(mine.lo[k], from); c.hi[k] = GSHFL(mine.hi[k], from); }
-            c.id = GSHFL(mine.id, from); c.count = GSHFL(mine.count, from); c.first = GSHFL(mine.first, from);
+            c.id = GSHFL(mine.id, from); c.count = GSHFL(mine.count, from);
             occupied = src != 8;
         }
         const bool is_int = occupied && c.count > (uint32_t)kLeafMax;
@@ -439,7 +615,17 @@ __global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__
                 __stcg(queue + child_base + int_rank, (unsigned long long)c.id);
             } else {
                 out.meta[sub] = (uint8_t)((((1u << c.count) - 1u) << 5) | prim_off);
-                for (uint32_t q = 0; q < c.count; q++) sink.emit(prim_base + prim_off + q, prim_sorted[c.first + q]);
+                // the (at most kLeafMax) leaves below this child, left to right; valid for any binary tree (LBVH or PLOC)
+                uint32_t todo[4], sp = 0, q = 0;
+                todo[sp++] = c.id;
+                while (sp) {
+                    const uint32_t id = todo[--sp];
+                    if (id & kLeafBit) sink.emit(prim_base + prim_off + q++, prim_sorted[id & ~kLeafBit]);
+                    else {
+                        const float4 *pn = reinterpret_cast<const float4 *>(&bin[id]);
+                        todo[sp++] = __float_as_uint(pn[2].w); todo[sp++] = __float_as_uint(pn[0].w);
+                    }
+                }
             }
         }
         __syncwarp(gmask);
@@ -489,12 +675,43 @@ __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, PackedTri *
 __global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) { queue[0] = (unsigned long long)h->root; }
 
 template <class Sink>
-void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc) {
+void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc, bool ploc) {
     k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals); lc.count++;
     bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, 6, lc);
     const uint64_t *keys = in_alt ? sc.keys_alt : sc.keys;
     const uint32_t *vals = in_alt ? sc.vals_alt : sc.vals;
-    k_hierarchy<<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header); lc.count++;
+    if (ploc && n > 1) {
+        static const int radius = [] { int r = 8; if (const char *e = getenv("LC_B200_PLOC_RADIUS")) r = atoi(e); return r < 1 ? 1 : (r > kPlocMaxRadius ? kPlocMaxRadius : r); }();
+        const uint32_t tiles = (n + kPlocTile - 1) / kPlocTile;
+        float4 *a = sc.ploc_a, *b = sc.ploc_b;
+        uint32_t *keep = reinterpret_cast<uint32_t *>(sc.flags);
+        k_ploc_init<<<(n + 255) / 256, 256, 0, s>>>(vals, sc.boxes, n, a, sc.ploc_state); lc.count++;
+        // Mutual nearest neighbours always exist, so every iteration merges; in practice the cluster count shrinks by a third to a
+        // half per iteration.  Iterations are launched in chunks with the whole-array grid (tiles past the live count exit at
+        // once) and the live count is read back between chunks; the grid follows it.
+        // Adversarial inputs (distances growing monotonically along the order) can leave one mutual pair per iteration: after 60
+        // iterations the remaining clusters are paired by position, which halves their number per iteration.
+        uint32_t live = n;
+        for (int chunk = 0; live > 1; chunk++) {
+            const int iters = chunk == 0 ? 12 : 8;
+            const int forced = chunk >= 7 ? 1 : 0;
+            const uint32_t live_tiles = (live + kPlocTile - 1) / kPlocTile;
+            for (int it = 0; it < iters; it++) {
+                k_ploc_step<<<live_tiles, kPlocTile, 0, s>>>(a, b, keep, sc.ploc_counts, sc.bin, sc.ploc_state, radius, forced);
+                k_ploc_scan<<<1, 1024, 0, s>>>(sc.ploc_counts, sc.ploc_state);
+                k_ploc_compact<<<live_tiles, kPlocTile, 0, s>>>(b, keep, sc.ploc_counts, a, sc.ploc_state);
+                lc.count += 3;
+            }
+            PlocState st;
+            cudaMemcpyAsync(&st, sc.ploc_state, sizeof(st), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            live = st.n_clusters;
+        }
+        (void)tiles;
+        k_ploc_finish<<<1, 1, 0, s>>>(a, sc.ploc_state, sc.header); lc.count++;
+    } else {
+        k_hierarchy<<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header); lc.count++;
+    }
     // seed the collapse queue with the binary root (device-side, no host round trip)
     k_seed_queue<<<1, 1, 0, s>>>(sc.header, sc.queue); lc.count++;
     // one 8-lane group per wide node of the widest level; cooperative launch: the grid must be co-resident for the barrier
@@ -534,16 +751,33 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
     sc.bin = (BinNode *)take(nn * sizeof(BinNode));
     sc.flags = (int *)take(nn * 4);
     sc.queue = (unsigned long long *)take(nn * 8);
+    sc.ploc_a = (float4 *)take(nn * 32);
+    sc.ploc_b = (float4 *)take(nn * 32);
+    sc.ploc_counts = (uint32_t *)take((nn / kPlocTile + 2) * 4);
+    sc.ploc_state = (PlocState *)take(sizeof(PlocState));
     sc.total_bytes = off;
     return sc;
 }
 
-void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc) {
+void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
+    bool use_ploc = builder == kBuilderPloc;
+    if (builder == kBuilderAuto && n > 1) {
+        // PLOC pays off where primitives tile a surface (terrain, C4 / C5: +11 % Mrays/s) and loses to the spatial-median splits of
+        // the LBVH where they overlap volumetrically (random soup, C3: -10 %); profiles/r01m_builder_sweep.txt.  The two cases are
+        // told apart by how many times the primitives' boxes cover the box of their centroids.
+        BuildHeader hdr;
+        cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        float ext[3];
+        for (int k = 0; k < 3; k++) ext[k] = ordered_to_float(hdr.bounds_hi[k]) - ordered_to_float(hdr.bounds_lo[k]);
+        const float scene = ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0];
+        use_ploc = scene > 0.f && hdr.prim_area_sum < 4.0f * scene;
+    }
     LeafSinkTriangles sink{tris};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, use_ploc);
     k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
 }
 
@@ -553,7 +787,7 @@ void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const In
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
     LeafSinkInstances sink{active_ids, prim_ids};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc);
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);  // a handful of instances: the LBVH order is as good as any
 }
 
 // ---- refit (MeshBuild with PreferUpdate on an updatable mesh; GeometryImpl::build_mesh, cpu/accel.rs:251-258) ----

@@ -33,6 +33,8 @@ namespace {
 // ---- logging / errors ------------------------------------------------------------------------
 std::atomic<void (*)(lcb_logger_message)> g_logger{nullptr};
 std::atomic<unsigned long long> g_launches{0};
+// -1: follow AccelOption.hint; otherwise kBuilderLbvh / kBuilderPloc / kBuilderAuto for every mesh (LC_B200_BUILDER, lc_b200_set_builder)
+std::atomic<int> g_builder_override{[] { const char *e = getenv("LC_B200_BUILDER"); return !e ? -1 : (strcmp(e, "ploc") == 0 ? 1 : (strcmp(e, "auto") == 0 ? 2 : (strcmp(e, "lbvh") == 0 ? 0 : -1))); }()};
 
 void log_msg(const char *level, const char *fmt, ...) {
     char buf[2048];
@@ -350,7 +352,12 @@ void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
         if (!m->nodes) { CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, staging_bytes, st)); m->node_capacity = n; }
         target = m->nodes;
     }
-    build_blas(st, n, in, sc, target, m->tris, d->lc);
+    // AccelUsageHint (api_types:204-212; the CPU backend maps it to Embree build quality, cpu/accel.rs:49-63): FastTrace (the default)
+    // lets the builder choose between PLOC and the LBVH split rule per mesh, FastBuild always takes the LBVH.
+    // LC_B200_BUILDER=lbvh|ploc|auto overrides.
+    const int forced = g_builder_override.load();
+    const int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
+    build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
     BuildHeader hdr;
     CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
@@ -1064,6 +1071,11 @@ int lc_b200_shader_compile_check(const void *kernel_module, bool fast_math, char
     catch (const std::exception &e) { l = e.what(); rc = 1; }
     if (log) { *log = (char *)malloc(l.size() + 1); memcpy(*log, l.c_str(), l.size() + 1); }
     return rc;
+}
+
+int lc_b200_set_builder(int builder) {
+    if (builder < -1 || builder > kBuilderAuto) fatal("lc_b200_set_builder: unknown builder %d", builder);
+    return g_builder_override.exchange(builder);
 }
 
 const void *lc_b200_make_ir_type(size_t size, size_t alignment) {

@@ -91,7 +91,7 @@ struct BuildHeader {
     uint32_t max_depth;
     uint32_t error;         // nonzero: builder failure code
     uint32_t bar_release;   // collapse: last released level
-    float root_lo[3]; float pad1;
+    float root_lo[3]; float prim_area_sum;  // sum of the primitives' box half-areas (builder choice, bvh_build.cu)
     float root_hi[3]; float pad2;
     uint32_t level_end[48]; // collapse: node_count snapshot taken by the last arriver of each level's barrier
 };

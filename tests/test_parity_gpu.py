@@ -433,3 +433,38 @@ def test_full_size_properties_c3(device):
     pick = np.random.default_rng(1).integers(0, n_rays, 65536)
     assert_hits_equal(h1[pick], o.trace_closest(rays[pick]), "1M-triangle sample")
     d.destroy(); o.close()
+
+
+@pytest.mark.parametrize("builder", [0, 1, 2], ids=["lbvh", "ploc", "auto"])
+def test_hits_do_not_depend_on_the_builder(device, builder):
+    """LBVH split rule, PLOC clustering or the per-mesh choice: the canonical arithmetic makes hits tree-independent, so every
+    builder must reproduce the oracle bit for bit — soup, terrain (PLOC's home turf), thousands of identical boxes (PLOC's
+    degenerate case: equal distances everywhere), tiny meshes and an instanced scene."""
+    lib = lc._abi.load_library()
+    prev = lib.lc_b200_set_builder(builder)
+    try:
+        check_scene(device, scenes.c3_soup(30000), scenes.incoherent_rays(60000, seed=91))
+        s = scenes.SceneDesc(); s.add_instance(s.add_mesh(*scenes.terrain(160)))
+        rays = scenes.incoherent_rays(60000, seed=92); rays["orig"][:, 1] = rays["orig"][:, 1] * 0.3 + 0.05
+        check_scene(device, s, rays)
+        rng = np.random.default_rng(93)
+        n = 5000
+        v = np.tile(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0]]), (n, 1, 1)).astype(np.float32)
+        v[:, :, 2] = (rng.integers(0, 3, n) * np.float32(0.5))[:, None]
+        s = scenes.SceneDesc(); s.add_instance(s.add_mesh(v.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)))
+        o = np.concatenate([rng.random((5000, 2), dtype=np.float32) * 0.5, np.full((5000, 1), -1, np.float32)], 1)
+        check_scene(device, s, scenes.make_rays(o, np.tile(np.float32([0, 0, 1]), (5000, 1)), 0.0, 10.0))
+        for k in (1, 2, 3, 5, 17):
+            check_scene(device, scenes.c3_soup(k, seed=94 + k), scenes.incoherent_rays(3000, seed=95))
+        check_scene(device, scenes.instanced_scene(1500, 10, seed=96), scenes.incoherent_rays(40000, seed=97, lo=-1.0, hi=7.0))
+        # points on a line with geometrically growing gaps: one mutual pair per PLOC iteration until the forced pairing takes over
+        m = 3000
+        x = np.cumsum(np.float32(1.01) ** np.arange(m, dtype=np.float32)).astype(np.float32)
+        x /= x[-1]
+        v = np.zeros((m, 3, 3), np.float32)
+        v[:, :, 0] = x[:, None]; v[:, 1, 1] = 1e-3; v[:, 2, 2] = 1e-3
+        s = scenes.SceneDesc(); s.add_instance(s.add_mesh(v.reshape(-1, 3), np.arange(3 * m, dtype=np.uint32).reshape(-1, 3)))
+        r2 = scenes.incoherent_rays(20000, seed=98); r2["orig"][:, 1:] *= np.float32(2e-3); r2["dir"][:, 0] *= np.float32(0.05)
+        check_scene(device, s, r2)
+    finally:
+        lib.lc_b200_set_builder(prev)
