@@ -468,3 +468,90 @@ def test_hits_do_not_depend_on_the_builder(device, builder):
         check_scene(device, s, r2)
     finally:
         lib.lc_b200_set_builder(prev)
+
+
+def _camera_rays(w, h, origin, look_at, fov_deg=45.0):
+    o = np.asarray(origin, np.float32)
+    f = np.asarray(look_at, np.float32) - o; f /= np.linalg.norm(f)
+    r = np.cross(f, np.float32([0, 1, 0])); r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    t = np.float32(np.tan(np.radians(fov_deg) / 2))
+    x = ((np.arange(w, dtype=np.float32) + 0.5) / w * 2 - 1) * t * np.float32(w / h)
+    y = (1 - (np.arange(h, dtype=np.float32) + 0.5) / h * 2) * t
+    d = (f[None, None, :] + x[None, :, None] * r[None, None, :] + y[:, None, None] * u[None, None, :]).reshape(-1, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return scenes.make_rays(np.broadcast_to(o, d.shape), d, np.float32(1e-4), np.float32(1e30))
+
+
+def test_full_size_properties_c4_terrain_refit_and_rebuild(device):
+    """Config C4 at BASELINE size (3164 x 3164 vertices = 20,009,138 triangles, 3840 x 2160 primary rays): a PreferUpdate refit of the
+    displaced terrain must give exactly the hits of a fresh ForceBuild on the same vertices (hits are tree-independent), under both
+    builders; any-hit == closest-hit found; and a ray sample equals the oracle on the full mesh."""
+    lib = lc._abi.load_library()
+    verts, tris = scenes.terrain(3164)
+    assert tris.shape[0] == 20_009_138
+    rays = _camera_rays(3840, 2160, [0.5, 0.6, -0.6], [0.5, 0.0, 0.5])
+    n = rays.shape[0]
+    vb = device.create_buffer_from_array(verts); ib = device.create_buffer_from_array(tris)
+    mesh = device.create_mesh(vb.view(), ib.view(), lc.AccelOption(allow_update=True))
+    accel = device.create_accel(lc.AccelOption(allow_update=True)); accel.push_mesh(mesh)
+    rb = device.create_buffer_from_array(rays); hb = device.create_buffer(n, 24, 8); ob = device.create_buffer(n, 4, 4)
+
+    def trace():
+        accel.intersect(rb, hb, n); device.default_stream().synchronize()
+        return hb.view().to_numpy(lc.SurfaceHit)
+    moved = verts.copy(); moved[:, 1] += np.float32(0.01) * np.sin(np.float32(40.0) * verts[:, 0] + np.float32(0.3)).astype(np.float32)
+    results = {}
+    for builder in (0, 1):
+        prev = lib.lc_b200_set_builder(builder)
+        try:
+            vb.view().copy_from(verts)
+            mesh.build(lc.AccelBuildRequest.FORCE_BUILD); accel.build()
+            results[builder, "base"] = trace()
+            vb.view().copy_from(moved)
+            mesh.build(lc.AccelBuildRequest.PREFER_UPDATE); assert mesh.stats()["was_refit"] == 1
+            accel.build(lc.AccelBuildRequest.PREFER_UPDATE)
+            refit = trace()
+            mesh.build(lc.AccelBuildRequest.FORCE_BUILD); assert mesh.stats()["was_refit"] == 0
+            accel.build()
+            results[builder, "moved"] = trace()
+            assert refit.tobytes() == results[builder, "moved"].tobytes(), "refit and rebuild disagree"
+        finally:
+            lib.lc_b200_set_builder(prev)
+    assert results[0, "base"].tobytes() == results[1, "base"].tobytes() and results[0, "moved"].tobytes() == results[1, "moved"].tobytes()
+    h = results[1, "moved"]
+    hit = h["inst"] != lc.INVALID
+    assert 0.2 < hit.mean() < 0.6 and (results[0, "base"]["prim"] != h["prim"]).any()
+    accel.intersect_any(rb, ob, n); device.default_stream().synchronize()
+    assert np.array_equal(ob.view().to_numpy(np.uint32) != 0, hit)
+    desc = scenes.SceneDesc(); desc.add_instance(desc.add_mesh(moved, tris))
+    o = ol.scene_from_desc(desc)
+    pick = np.random.default_rng(5).integers(0, n, 30000)
+    assert_hits_equal(h[pick], o.trace_closest(rays[pick]), "20M-triangle terrain sample")
+    o.close()
+    for r in (rb, hb, ob):
+        r.destroy()
+    accel.destroy(); mesh.destroy(); vb.destroy(); ib.destroy()
+
+
+def test_full_size_properties_c5_instanced(device):
+    """Config C5 at BASELINE size: one 4,999,122-triangle terrain instanced 10x (yaw 36 deg * k on a 5 x 2 grid), 4K primary rays:
+    determinism, any-hit consistency, every hit inside its instance's triangle range, and a ray sample against the oracle."""
+    verts, tris = scenes.terrain(1582)
+    desc = scenes.SceneDesc()
+    mid = desc.add_mesh(verts, tris)
+    for k in range(10):
+        t = scenes.rotation_y(36.0 * k); t[:, 3] = [1.2 * (k % 5), 0.0, 1.2 * (k // 5)]
+        desc.add_instance(mid, t)
+    assert desc.triangle_count() == 49_991_220
+    d = DeviceScene(device, desc)
+    rays = _camera_rays(3840, 2160, [3.0, 2.5, -3.0], [3.0, 0.0, 1.0])
+    h1 = d.trace_closest(rays); h2 = d.trace_closest(rays)
+    assert h1.tobytes() == h2.tobytes()
+    hit = h1["inst"] != lc.INVALID
+    assert np.array_equal(d.trace_any(rays) != 0, hit) and 0.15 < hit.mean() < 0.6
+    assert np.all(h1["inst"][hit] < 10) and np.all(h1["prim"][hit] < tris.shape[0]) and len(np.unique(h1["inst"][hit])) == 10
+    o = ol.scene_from_desc(desc)
+    pick = np.random.default_rng(6).integers(0, rays.shape[0], 30000)
+    assert_hits_equal(h1[pick], o.trace_closest(rays[pick]), "50M-triangle instanced sample")
+    d.destroy(); o.close()
