@@ -68,6 +68,11 @@ class CmdMeshBuild(C.Structure):
                 ("index_buffer_offset", C.c_size_t), ("index_buffer_size", C.c_size_t), ("index_stride", C.c_size_t)]
 
 
+class CmdProceduralBuild(C.Structure):
+    """ProceduralPrimitiveBuildCommand (api_types:633-641)"""
+    _fields_ = [("handle", Handle), ("request", C.c_int32), ("aabb_buffer", Handle), ("aabb_offset", C.c_size_t), ("aabb_count", C.c_size_t)]
+
+
 class CmdAccelBuild(C.Structure):
     _fields_ = [("accel", Handle), ("request", C.c_int32), ("instance_count", C.c_uint32),
                 ("modifications", C.POINTER(AccelModification)), ("modifications_count", C.c_size_t),
@@ -150,7 +155,7 @@ class _CmdUnion(C.Union):
     _fields_ = [("buffer_upload", CmdBufferUpload), ("buffer_download", CmdBufferDownload), ("buffer_copy", CmdBufferCopy),
                 ("buffer_to_texture", CmdBufferTexture), ("texture_to_buffer", CmdBufferTexture), ("texture_upload", CmdTextureTransfer),
                 ("texture_download", CmdTextureTransfer), ("texture_copy", CmdTextureCopy), ("shader_dispatch", CmdShaderDispatch),
-                ("bindless_update", CmdBindlessUpdate),
+                ("bindless_update", CmdBindlessUpdate), ("procedural_build", CmdProceduralBuild),
                 ("mesh_build", CmdMeshBuild), ("accel_build", CmdAccelBuild), ("_raw", C.c_uint8 * 80)]
 
 

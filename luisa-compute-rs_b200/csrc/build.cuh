@@ -44,6 +44,8 @@ BuildScratch build_scratch_layout(void *base, uint32_t n);
 // clustering, k_ploc_*), or chosen per mesh from the primitives' overlap (kBuilderAuto).
 enum { kBuilderLbvh = 0, kBuilderPloc = 1, kBuilderAuto = 2 };
 void build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder);
+// Procedural primitives: a BLAS over user AABBs (24-byte {min, max} records); leaf slots hold the box and the primitive id.
+void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc);
 void build_tlas(cudaStream_t s, uint32_t n_active, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc,
                 WideNode *nodes, uint32_t *prim_ids, LaunchCounter &lc);
 

@@ -106,6 +106,38 @@ __global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32
     reduce_centroid_bounds(cen, valid, h, area);
 }
 
+// Procedural primitives (ProceduralPrimitiveBuild, api_types:633-641): the user's AABBs {min[3], max[3]} (rtx.rs:339-345, 24 B) are
+// the primitive boxes (GeometryImpl::build_procedural's bounds_func, cpu/accel.rs:93-104).
+__global__ void __launch_bounds__(256) k_aabb_boxes(const uint8_t *__restrict__ aabbs, uint32_t n, PrimBox *boxes, BuildHeader *h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cen[3] = {0, 0, 0};
+    float area = 0.f;
+    bool valid = i < n;
+    if (valid) {
+        const float *a = reinterpret_cast<const float *>(aabbs + (size_t)i * 24);
+        float lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(a[k], a[3 + k]); hi[k] = fmaxf(a[k], a[3 + k]); cen[k] = 0.5f * lo[k] + 0.5f * hi[k]; }
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        area = dx * dy + dy * dz + dz * dx;
+    }
+    reduce_centroid_bounds(cen, valid, h, area);
+}
+
+// leaf records of a procedural BLAS: the primitive's box and id in the PackedTri slot the collapse assigned
+__global__ void __launch_bounds__(256) k_pack_aabbs(const uint8_t *__restrict__ aabbs, PackedTri *tris, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t prim = tris[i].prim;
+    const float *a = reinterpret_cast<const float *>(aabbs + (size_t)prim * 24);
+    float4 *o = reinterpret_cast<float4 *>(&tris[i]);
+    o[0] = make_float4(fminf(a[0], a[3]), fminf(a[1], a[4]), fminf(a[2], a[5]), __uint_as_float(prim));
+    o[1] = make_float4(fmaxf(a[0], a[3]), fmaxf(a[1], a[4]), fmaxf(a[2], a[5]), 0.f);
+    o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // World-space box of an instance: union of the BLAS root's (conservatively decoded) child
 // boxes, 8 corners through the affine, padded for the fp32 mismatch between M and M^-1.
 __global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, uint32_t n, const InstanceRec *insts, PrimBox *boxes, BuildHeader *h) {
@@ -779,6 +811,15 @@ void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const Build
     LeafSinkTriangles sink{tris};
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, use_ploc);
     k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
+}
+
+void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc) {
+    uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_aabb_boxes<<<(n + 255) / 256, 256, 0, s>>>(aabbs, n, sc.boxes, sc.header); lc.count++;
+    LeafSinkTriangles sink{slots};
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);
+    k_pack_aabbs<<<(n + 255) / 256, 256, 0, s>>>(aabbs, slots, n); lc.count++;
 }
 
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,

@@ -128,6 +128,7 @@ struct BufferObj { uint8_t *ptr = nullptr; size_t size = 0; bool owned = true; }
 struct MeshObj {
     lcb_accel_option option{};
     bool built = false;
+    bool procedural = false;  // created by create_procedural_primitive: leaves are user AABBs, hits come from the RayQuery callback
     uint32_t n_tris = 0;
     uint64_t generation = 0;  // bumped whenever nodes/tris are re-allocated
     WideNode *nodes = nullptr; PackedTri *tris = nullptr;
@@ -287,8 +288,11 @@ void free_stream(StreamObj *s) {
 void destroy_stream(lcb_device dev, lcb_stream h) { DeviceObj *d = dev_of(dev); bind(d); free_stream(as<StreamObj>(h.id)); }
 
 // ---- mesh build (GeometryImpl::build_mesh, cpu/accel.rs:205-260) ---------------------------------
+void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs);
+
 void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     MeshObj *m = as<MeshObj>(c.mesh.id);
+    if (m->procedural) fatal("MeshBuild on a procedural primitive handle");
     std::lock_guard<std::mutex> lk(m->mu);
     if (c.index_stride != 12) fatal("Index stride must be 12 (got %zu).", c.index_stride);  // api/runtime.cpp:191-193
     if (c.vertex_stride < 12) fatal("vertex stride must be >= 12 (got %zu)", c.vertex_stride);
@@ -297,6 +301,21 @@ void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     if (c.index_buffer_offset + c.index_buffer_size > ib->size) fatal("MeshBuild: index range exceeds buffer");
     const uint32_t n = (uint32_t)(c.index_buffer_size / c.index_stride);
     TriangleInput in{vb->ptr + c.vertex_buffer_offset, c.vertex_stride, ib->ptr + c.index_buffer_offset};
+    blas_build(d, s, m, n, c.request, in, nullptr);
+}
+
+// ProceduralPrimitiveBuild (GeometryImpl::build_procedural, cpu/accel.rs:84-141): a BLAS over the user's AABBs; always a full build.
+void procedural_build(DeviceObj *d, StreamObj *s, const lcb_cmd_procedural_build &c) {
+    MeshObj *m = as<MeshObj>(c.handle.id);
+    if (!m->procedural) fatal("ProceduralPrimitiveBuild on a mesh handle");
+    std::lock_guard<std::mutex> lk(m->mu);
+    BufferObj *ab = as<BufferObj>(c.aabb_buffer.id);
+    if (c.aabb_offset + c.aabb_count * 24 > ab->size) fatal("ProceduralPrimitiveBuild: AABB range exceeds buffer");
+    blas_build(d, s, m, (uint32_t)c.aabb_count, LCB_REQUEST_FORCE_BUILD, TriangleInput{nullptr, 0, nullptr}, ab->ptr + c.aabb_offset);
+}
+
+void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs) {
+    struct { int32_t request; } c{request};
     cudaStream_t st = s->stream;
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
@@ -357,7 +376,8 @@ void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     // LC_B200_BUILDER=lbvh|ploc|auto overrides.
     const int forced = g_builder_override.load();
     const int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
-    build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
+    if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
+    else build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
     BuildHeader hdr;
     CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
@@ -448,7 +468,7 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         if (!touched[i]) continue;
         InstanceModRec r{};
         r.index = i; r.visibility = in.visible; r.user_id = in.user_id;
-        r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u);
+        r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u) | (in.valid && in.mesh->procedural ? 4u : 0u);
         memcpy(r.affine, in.affine, sizeof(r.affine));
         invert_affine(in.affine, r.inv);
         if (in.valid) { r.nodes = in.mesh->nodes; r.tris = in.mesh->tris; in.mesh_generation = in.mesh->generation; }
@@ -587,9 +607,10 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
             case LCB_CMD_SHADER_DISPATCH: shader_dispatch(d, s, c.u.shader_dispatch); break;
             case LCB_CMD_BINDLESS_UPDATE: bindless_update(s, c.u.bindless_update); break;
             case LCB_CMD_MESH_BUILD: mesh_build(d, s, c.u.mesh_build); break;
+            case LCB_CMD_PROCEDURAL_BUILD: procedural_build(d, s, c.u.procedural_build); break;
             case LCB_CMD_ACCEL_BUILD: accel_build(d, s, c.u.accel_build); break;
             default:
-                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: curves and procedural primitives are \"next\" rows)", c.tag);
+                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: curves are a \"next\" row)", c.tag);
         }
     }
     flush_launches(d);
@@ -795,8 +816,13 @@ void present_display_in_stream(lcb_device, lcb_stream, lcb_swapchain, lcb_textur
 void destroy_swapchain(lcb_device, lcb_swapchain) { UNSUPPORTED("destroy_swapchain"); }
 lcb_created create_curve(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_curve"); }
 void destroy_curve(lcb_device, lcb_curve) { UNSUPPORTED("destroy_curve"); }
-lcb_created create_procedural_primitive(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_procedural_primitive"); }
-void destroy_procedural_primitive(lcb_device, lcb_procedural) { UNSUPPORTED("destroy_procedural_primitive"); }
+lcb_created create_procedural_primitive(lcb_device dev, const lcb_accel_option *opt) {
+    bind(dev_of(dev));
+    auto *m = new MeshObj; if (opt) m->option = *opt;
+    m->procedural = true;
+    return lcb_created{(uint64_t)m, m};
+}
+void destroy_procedural_primitive(lcb_device dev, lcb_procedural h) { destroy_mesh(dev, lcb_mesh{h.id}); }
 
 void *native_handle(lcb_device dev) { return dev_of(dev); }
 uint32_t compute_warp_size(lcb_device) { return 32; }

@@ -599,10 +599,10 @@ struct FunctionEmitter {
             case Func::RayTracingQueryAny: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
             case Func::RayQueryWorldSpaceRay: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".ray)"); break;
             case Func::RayQueryTriangleCandidateHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".cur_triangle)"); break;
-            case Func::RayQueryProceduralCandidateHit: need(1); value("lc_zero<" + ts + ">()"); break;  // the device has no procedural primitives: never invoked
+            case Func::RayQueryProceduralCandidateHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".cur_procedural)"); break;
             case Func::RayQueryCommittedHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".hit)"); break;
             case Func::RayQueryCommitTriangle: need(1); line(a[0] + ".cur_committed = true;"); break;
-            case Func::RayQueryCommitProcedural: need(2); line(a[0] + ".cur_committed = true;"); break;
+            case Func::RayQueryCommitProcedural: need(2); line(a[0] + ".cur_committed = true; " + a[0] + ".cur_committed_t = " + a[1] + ";"); break;
             case Func::RayQueryTerminate: need(1); line(a[0] + ".terminated = true;"); break;
 
             case Func::Callable: {

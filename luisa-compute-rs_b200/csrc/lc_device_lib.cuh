@@ -467,34 +467,48 @@ __device__ inline bool lc_trace_any(const lc_accel &a, const lc_ray_rec &r, uint
 // {inst, prim, bary, hit_type (0 miss / 1 triangle / 2 procedural), committed_ray_t} (defs:68-77); a query that commits nothing
 // keeps its initial record: inst = prim = ~0, everything else zero (cpu_resource.h:322-331).
 struct alignas(8) lc_committed_hit { uint32_t inst, prim; float u, v; uint32_t hit_type; float t; };
+struct lc_procedural_rec { uint32_t inst, prim; };  // defs::ProceduralHit (defs:100-105)
 struct lc_ray_query_state {
     const lc_accel *accel; lc_ray_rec ray; uint32_t mask; bool terminate_on_first;
-    lc_hit_rec cur_triangle; bool cur_committed, terminated;
+    lc_hit_rec cur_triangle; lc_procedural_rec cur_procedural; float cur_committed_t; bool cur_committed, terminated;
     lc_committed_hit hit;
 };
 __device__ inline lc_ray_query_state lc_make_ray_query(const lc_accel &a, const lc_ray_rec &r, uint32_t mask, bool any) {
     lc_ray_query_state q;
     q.accel = &a; q.ray = r; q.mask = mask; q.terminate_on_first = any;
-    q.cur_triangle = lc_hit_rec{~0u, ~0u, 0.f, 0.f, 0.f, 0u}; q.cur_committed = false; q.terminated = false;
+    q.cur_triangle = lc_hit_rec{~0u, ~0u, 0.f, 0.f, 0.f, 0u}; q.cur_procedural = lc_procedural_rec{~0u, ~0u}; q.cur_committed_t = 0.f;
+    q.cur_committed = false; q.terminated = false;
     q.hit = lc_committed_hit{~0u, ~0u, 0.f, 0.f, 0u, 0.f};
     return q;
 }
 __device__ inline lc_ray_query_state lc_ray_query_all(const lc_accel &a, const lc_ray_rec &r, uint32_t mask) { return lc_make_ray_query(a, r, mask, false); }
 __device__ inline lc_ray_query_state lc_ray_query_any(const lc_accel &a, const lc_ray_rec &r, uint32_t mask) { return lc_make_ray_query(a, r, mask, true); }
-// Instruction::RayQuery: run the traversal; candidates of non-opaque instances go through on_triangle (which may call
-// RayQueryCommitTriangle / RayQueryTerminate on the same object), exactly the contract of AccelImpl::ray_query's filter_fn
-// (cpu/accel.rs:646-690).  The device has no procedural primitives, so on_procedural is never invoked.
-template <class OnTriangle, class OnProcedural> __device__ inline void lc_ray_query(lc_ray_query_state &q, OnTriangle on_triangle, OnProcedural) {
-    auto hook = [&](uint32_t inst, uint32_t prim, float u, float v, float t) -> int {
+// Instruction::RayQuery: run the traversal.  Triangles of non-opaque instances go through on_triangle, AABBs of procedural
+// instances through on_procedural; either may call RayQueryCommit* / RayQueryTerminate on the same object — the contract of
+// AccelImpl::ray_query's filter_fn / intersect_fn (cpu/accel.rs:646-757).  Both see rq.ray with tmax = the closest committed t so far.
+template <class OnTriangle, class OnProcedural> struct lc_query_hook {
+    lc_ray_query_state &q; OnTriangle &on_triangle; OnProcedural &on_procedural;
+    __device__ int triangle(uint32_t inst, uint32_t prim, float u, float v, float t) {
         q.cur_triangle = lc_hit_rec{inst, prim, u, v, t, 0u};
-        q.ray.tmax = t;  // accel.rs:668
+        q.ray.tmax = t;  // accel.rs:668: the filter sees the candidate's t as tfar
         q.cur_committed = false; q.terminated = false;
         on_triangle();
         return (q.cur_committed ? 1 : 0) | (q.terminated ? 2 : 0);
-    };
+    }
+    __device__ int procedural(uint32_t inst, uint32_t prim, float t_far, float &t) {
+        q.cur_procedural = lc_procedural_rec{inst, prim};
+        q.ray.tmax = t_far;  // accel.rs:738
+        q.cur_committed = false; q.terminated = false;
+        on_procedural();
+        t = q.cur_committed_t;
+        return (q.cur_committed ? 1 : 0) | (q.terminated ? 2 : 0);
+    }
+};
+template <class OnTriangle, class OnProcedural> __device__ inline void lc_ray_query(lc_ray_query_state &q, OnTriangle on_triangle, OnProcedural on_procedural) {
+    lc_query_hook<OnTriangle, OnProcedural> hook{q, on_triangle, on_procedural};
     const float4 ra = make_float4(q.ray.o[0], q.ray.o[1], q.ray.o[2], q.ray.tmin), rb = make_float4(q.ray.d[0], q.ray.d[1], q.ray.d[2], q.ray.tmax);
     const lcb::DeviceHit h = lcb::trace_one_impl<false, true>(q.accel->view, ra, rb, q.mask, q.terminate_on_first, hook);
-    if (h.inst != lcb::kNone) q.hit = lc_committed_hit{h.inst, h.prim, h.u, h.v, 1u, h.t};
+    if (h.inst != lcb::kNone) q.hit = lc_committed_hit{h.inst, h.prim, h.u, h.v, h.kind, h.t};
 }
 
 // instance accessors: the transform is returned as the column-major Mat4 built from the row-major 3x4 (stream.rs:582-595)

@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
                     const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
                     const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
-                    if ((meta.x & mask) != 0u) {
+                    // procedural instances (flags bit 2) only produce candidates for a RayQuery's on_procedural_hit callback, which the
+                    // batch entry points do not have: they are skipped, like user geometry without an intersect function in Embree
+                    if ((meta.x & mask) != 0u && (meta.z & 4u) == 0u) {
                         if (Gt.y) LCB_PUSH(Gt)
                         if (G.y & 0xff000000u) LCB_PUSH(G)
                         LCB_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space

@@ -207,17 +207,23 @@ __device__ __forceinline__ bool refine_bary(const RaySetup &r, const float4 v0, 
 // lc_trace_closest / lc_trace_any for device code: the same node test, the same canonical triangle arithmetic and the
 // same tie rule as the batch kernel, as a plain per-thread loop with a local-memory stack.  Returns the hit in the
 // reference's SurfaceHit convention (miss: inst = prim = ~0, bary = 0, t = ray.tmax); ANY returns only hit / no hit.
-struct DeviceHit { uint32_t inst, prim; float u, v, t; };
+struct DeviceHit { uint32_t inst, prim; float u, v, t; uint32_t kind; };  // kind: 0 miss, 1 triangle, 2 procedural (HitType, rtx.rs:510-516)
 
 // QUERY adds the RayQuery rules (AccelImpl::ray_query, cpu/accel.rs:582-800; batch form: trace.cu kQueryAll / kQueryAny):
 // triangles of NON-opaque instances are candidates handed to `hook(inst, prim, u, v, t)` with the canonical fp32
 // barycentrics; it returns bit 0 = commit (RayQueryCommitTriangle), bit 1 = terminate (RayQueryTerminate).  Triangles of
 // opaque instances commit directly.  `first` ends the traversal at the first committed hit (RayQueryAny).
-struct NoCandidateHook { __device__ __forceinline__ int operator()(uint32_t, uint32_t, float, float, float) const { return 1; } };
+// Leaves of procedural instances (user AABBs) are candidates for `hook.procedural(inst, prim, t_far, t)`, which may commit with
+// its own t (RayQueryCommitProcedural); it is accepted when tmin <= t < t_far (cpu/accel.rs:711-713), ties on t going to the
+// lowest (inst, prim) like everywhere else.  Without QUERY procedural instances are not entered at all.
+struct NoCandidateHook {
+    __device__ __forceinline__ int triangle(uint32_t, uint32_t, float, float, float) const { return 1; }
+    __device__ __forceinline__ int procedural(uint32_t, uint32_t, float, float &) const { return 0; }
+};
 
 template <bool ANY, bool QUERY, class Hook>
 __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask, bool first, Hook &hook) {
-    DeviceHit h{kNone, kNone, 0.f, 0.f, rb.w};
+    DeviceHit h{kNone, kNone, 0.f, 0.f, rb.w, 0u};
     if (!acc.tlas_nodes) return h;
     uint2 stack[kTraversalStack];
     int sp = 0;
@@ -226,7 +232,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
     const float tmin = ra.w, ray_tmax = rb.w;
     float tbest = rb.w;
     uint32_t cur_inst = kNone, hit_slot = 0;
-    bool cur_opaque = true, stop = false;
+    bool cur_opaque = true, cur_procedural = false, stop = false;
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
     uint2 G = make_uint2(0u, 0x80000000u), Gt = make_uint2(0u, 0u);
@@ -246,7 +252,17 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
         while (Gt.y != 0u) {
             const uint32_t bit = __ffs(Gt.y) - 1;
             Gt.y &= Gt.y - 1;
-            if (cur_inst != kNone) {
+            if (QUERY && cur_procedural) {
+                const uint32_t prim = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(tris + (Gt.x + bit))).w);
+                float t = 0.f;
+                const int verdict = hook.procedural(cur_inst, prim, tbest, t);
+                stop = (verdict & 2) != 0;
+                if ((verdict & 1) && t >= tmin && (t < tbest || (t == tbest && h.inst != kNone && (cur_inst < h.inst || (cur_inst == h.inst && prim < h.prim))))) {
+                    tbest = t; h.inst = cur_inst; h.prim = prim; h.kind = 2u; hit_slot = Gt.x + bit;
+                    if (first) stop = true;
+                }
+                if (stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
+            } else if (cur_inst != kNone) {
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 float t, V, W, det;
@@ -255,13 +271,13 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                     bool commit = true;
                     if (QUERY && !cur_opaque) {
                         const float rdet = __frcp_rn(det);
-                        const int verdict = hook(cur_inst, prim, __fmul_rn(V, rdet), __fmul_rn(W, rdet), t);
+                        const int verdict = hook.triangle(cur_inst, prim, __fmul_rn(V, rdet), __fmul_rn(W, rdet), t);
                         commit = (verdict & 1) != 0; stop = (verdict & 2) != 0;
                     }
                     if (commit) {
-                        if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; return h; }
+                        if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; h.kind = 1u; return h; }
                         const bool better = t < tbest || h.inst == kNone || (t == tbest && (cur_inst < h.inst || (cur_inst == h.inst && prim < h.prim)));
-                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; hit_slot = Gt.x + bit; }
+                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; h.kind = 1u; hit_slot = Gt.x + bit; }
                         if (QUERY && first) stop = true;
                     }
                     if (QUERY && stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
@@ -270,7 +286,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
                 const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
                 const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);
-                if ((meta.x & mask) != 0u) {
+                if ((meta.x & mask) != 0u && (QUERY || (meta.z & 4u) == 0u)) {
                     if (Gt.y) stack[sp++] = Gt;
                     if (G.y & 0xff000000u) stack[sp++] = G;
                     stack[sp++] = make_uint2(0u, 0u);  // sentinel: below it lies world space
@@ -280,7 +296,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                     tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
                     setup_object(r, ra, rb, m0, m1, m2);
                     cur_inst = inst;
-                    if (QUERY) cur_opaque = (meta.z & 2u) != 0u;
+                    if (QUERY) { cur_opaque = (meta.z & 2u) != 0u; cur_procedural = (meta.z & 4u) != 0u; }
                     G = make_uint2(0u, 0x80000000u);
                     Gt = make_uint2(0u, 0u);
                     break;
@@ -294,15 +310,15 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 const uint2 e = stack[--sp];
                 if (e.y & 0xff000000u) { G = e; break; }
                 if (e.y != 0u) { Gt = e; break; }
-                cur_inst = kNone; nodes = acc.tlas_nodes; tris = nullptr;
+                cur_inst = kNone; cur_procedural = false; nodes = acc.tlas_nodes; tris = nullptr;
                 if (sp == 0) { done = true; break; }
                 setup_world(r, ra, rb);
             }
             if (done) break;
         }
     }
-    if (!ANY && h.inst != kNone) {
-        h.t = tbest;
+    if (!ANY && h.inst != kNone) h.t = tbest;
+    if (!ANY && h.inst != kNone && h.kind == 1u) {
         const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h.inst);
         const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
         const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);

@@ -454,3 +454,44 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
     k.body(body)
     k.finish()
     return k
+
+
+def sphere_query_kernel(translate):
+    """examples/ray_query.rs:125-200 with an analytic sphere test in place of the example's sphere tracing loop: a RayQuery whose
+    on_surface_hit commits every triangle candidate and whose on_procedural_hit intersects the candidate's sphere
+    (`spheres[prim]` = centre.xyz, radius; `translate` = the procedural instance's translation, as in the example) and commits with
+    its own t.  Args: rays Buffer<Ray>, committed Buffer<CommittedHit>, accel, spheres Buffer<Float4>, mask: u32."""
+    k = ir.KernelBuilder(block_size=(128, 1, 1))
+    f3, ray_ty, hit_ty = common_types(k)
+    committed_ty = k.struct([k.u32, k.u32, k.f322, k.u32, k.f32], align=8)
+    procedural_ty = k.struct([k.u32, k.u32])
+    rays, out, accel, spheres, mask = k.arg_buffer(ray_ty), k.arg_buffer(committed_ty), k.arg_accel(), k.arg_buffer(k.f324), k.arg_uniform(k.u32)
+
+    def body():
+        i = k.dispatch_id().x
+        rq = accel.query(rays.read(i), mask)
+
+        def on_surface_hit():
+            k.call(Func.RayQueryCommitTriangle, [rq], k.void)
+
+        def on_procedural_hit():
+            cand = k.call(Func.RayQueryProceduralCandidateHit, [rq], procedural_ty)
+            ray = k.call(Func.RayQueryWorldSpaceRay, [rq], ray_ty)
+            o, d = _to_float3(k, ray.extract(0)), _to_float3(k, ray.extract(2))
+            s = spheres.read(cand.extract(1))
+            centre = s.permute(0, 1, 2) + k.vec(k.f323, *translate)
+            oc = o - centre
+            a = d.dot(d)
+            b = oc.dot(d)
+            c = oc.dot(oc) - s.w * s.w
+            disc = b * b - a * c
+
+            def inside():
+                t = (-b - disc.sqrt()) / a
+                k.if_(t.ge(ray.extract(1)) & t.lt(ray.extract(3)), lambda: k.call(Func.RayQueryCommitProcedural, [rq, t], k.void))
+            k.if_(disc.ge(0.0), inside)
+        k.ray_query(rq, on_surface_hit, on_procedural_hit)
+        out.write(i, k.call(Func.RayQueryCommittedHit, [rq], committed_ty))
+    k.body(body)
+    k.finish()
+    return k

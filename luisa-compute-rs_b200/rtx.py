@@ -141,6 +141,37 @@ class Mesh:
         self._alive = False
 
 
+class ProceduralPrimitive:
+    """`Device::create_procedural_primitive(aabb_view, option)` (runtime.rs:702-720; rtx.rs:65-95): a BLAS over user AABBs
+    ({min: [f32; 3], max: [f32; 3]}, 24 B).  Hits come from the `on_procedural_hit` block of a RayQuery."""
+
+    def __init__(self, device, aabb_view, option=None):
+        self.device = device
+        self.option = option or AccelOption()
+        self.aabb_view = aabb_view
+        if aabb_view.buffer.stride != 24:
+            raise LuisaError("procedural primitives need a buffer of Aabb {min, max} records (24 bytes)")
+        info = device.iface.create_procedural_primitive(device.handle, C.byref(self.option))
+        self.handle = abi.Handle(info.handle)
+        self._alive = True
+
+    def build_async(self, request=AccelBuildRequest.FORCE_BUILD):
+        cmd = abi.Command()
+        cmd.tag = abi.CMD_PROCEDURAL_BUILD
+        cmd.u.procedural_build = abi.CmdProceduralBuild(self.handle, request, self.aabb_view.buffer.handle, self.aabb_view.offset, self.aabb_view.size // 24)
+        return HostCommand(cmd, keep=[self, self.aabb_view.buffer])
+
+    def build(self, request=AccelBuildRequest.FORCE_BUILD):
+        s = self.device.default_stream()
+        s.submit([self.build_async(request)])
+        s.synchronize()
+
+    def destroy(self):
+        if self._alive and not self.device._closed:
+            self.device.iface.destroy_procedural_primitive(self.device.handle, self.handle)
+        self._alive = False
+
+
 class Accel:
     """`Device::create_accel(option)` (runtime.rs:690-701) and `rtx::Accel` (rtx.rs:154-311)."""
 
@@ -173,6 +204,10 @@ class Accel:
 
     def push_mesh(self, mesh, transform=None, ray_mask=0xFF, opaque=True):
         self._push_handle(mesh, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, opaque)
+
+    def push_procedural_primitive(self, prim, transform=None, ray_mask=0xFF):
+        """rtx.rs:236-247: procedural instances are never opaque (every candidate goes through the callback)."""
+        self._push_handle(prim, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, False)
 
     def set_mesh(self, index, mesh, transform=None, ray_mask=0xFF, opaque=True):
         self._set_handle(index, mesh, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, opaque)
