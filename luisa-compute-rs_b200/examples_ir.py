@@ -284,7 +284,7 @@ def ray_query_kernel(radius, any_hit=False):
     return k
 
 
-def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64):
+def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64, block=16):
     """BASELINE config C5: the path tracer of examples/path_tracer.rs generalised to an instanced scene and to tile sharding
     (SURVEY.md §8d / §8e).  One thread per pixel of a 64x64 tile; `tiles[k]` names the global tile a rank's k-th local tile is
     (Morton round-robin, sharding.tiles_of_rank), results accumulate in a packed per-rank tile buffer that ONE all-gather
@@ -293,8 +293,8 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
     tan_half_fov), object-space vertices go through RayTracingInstanceTransform, normals face the viewer, a constant sky, one
     emissive quad `light` = (position, u, v, emission, instance index), albedo by instance.
     Args: tiles Buffer<u32>, out Buffer<Float4>, accel, params {resolution: Uint2, frame: u32, n_local_tiles: u32},
-    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s)."""
-    k = ir.KernelBuilder(block_size=(16, 16, 1))
+    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s).  `block`: edge of the square thread block."""
+    k = ir.KernelBuilder(block_size=(block, block, 1))
     f3, ray_ty, hit_ty = common_types(k)
     index_ty = k.array(k.u32, 3)
     params_ty = k.struct([k.u322, k.u32, k.u32])

@@ -29,6 +29,10 @@ def main():
     ap.add_argument("--spp-per-dispatch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=5)
     ap.add_argument("--nx", type=int, default=1582, help="terrain vertices per side (1582 -> 5.0M triangles per mesh, 50M instanced)")
+    ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
+    ap.add_argument("--streams", type=int, default=2, help="the rank's tiles are split over this many streams so that the tail of one dispatch overlaps the next")
+    ap.add_argument("--chunk", type=int, default=1, help="tiles per round-robin run along the Morton curve (sharding.tiles_of_rank)")
+    ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's tiles in this single process (tuning aid; no gather)")
     ap.add_argument("--save", default="")
     a = ap.parse_args()
     import torch
@@ -77,14 +81,18 @@ def main():
     u = np.cross(r, f)
     camera = (tuple(map(float, cam_o)), tuple(map(float, f)), tuple(map(float, r)), tuple(map(float, u)), float(np.tan(np.radians(45.0) / 2)))
     light = (l_pos, l_u, l_v, (60.0, 54.0, 45.0), 10)
-    kb = examples_ir.tiled_path_tracer_kernel(vheap.handle.id, iheap.handle.id, camera, light, n_inst, a.spp_per_dispatch, a.depth)
+    kb = examples_ir.tiled_path_tracer_kernel(vheap.handle.id, iheap.handle.id, camera, light, n_inst, a.spp_per_dispatch, a.depth, block=a.block)
     shader = dev.create_shader(C.addressof(kb.km), keep=kb)
 
     # ---- this rank's tiles ----------------------------------------------------------------------------------------------
     tile = sharding.TILE
-    tx, ty = sharding.tiles_of_rank(a.width, a.height, rank, world)
+    if a.emulate:
+        erank, eworld = (int(v) for v in a.emulate.split("/"))
+        tx, ty = sharding.tiles_of_rank(a.width, a.height, erank, eworld, chunk=a.chunk)
+    else:
+        tx, ty = sharding.tiles_of_rank(a.width, a.height, rank, world, chunk=a.chunk)
     tiles_x = (a.width + tile - 1) // tile
-    per_rank = sharding.padded_tile_count(a.width, a.height, world)
+    per_rank = max(sharding.padded_tile_count(a.width, a.height, world, chunk=a.chunk), tx.shape[0])
     tile_ids = dev.create_buffer_from_array((ty * tiles_x + tx).astype(np.uint32))
     out_t = torch.zeros((per_rank * tile * tile, 4), dtype=torch.float32, device="cuda")
     out = dev.wrap_device_memory(out_t.data_ptr(), per_rank * tile * tile, 16, 16)
@@ -95,10 +103,27 @@ def main():
     def params(frame):
         return np.array([a.width, a.height, frame, tx.shape[0]], np.uint32)
 
+    # the rank's tiles in `--streams` contiguous groups, one stream each: a dispatch's tail (a few long paths) overlaps the other
+    # group's work instead of idling the GPU; the groups touch disjoint slices of the tile buffer
+    lanes = [s] + [dev.create_stream() for _ in range(max(1, a.streams) - 1)]
+    bounds = np.linspace(0, tx.shape[0], len(lanes) + 1).astype(int)
+    done = dev.create_event()
+
     def render(first_frame):
-        s.submit([shader.dispatch_async((tile, tile * tx.shape[0]), tile_ids, out, accel, params(first_frame + i), counters) for i in range(n_dispatch)])
+        for li, lane in enumerate(lanes):
+            b0, b1 = int(bounds[li]), int(bounds[li + 1])
+            if b1 == b0:
+                continue
+            lane.submit([shader.dispatch_async((tile, tile * (b1 - b0)), tile_ids.view(b0, b1 - b0), out.view(b0 * tile * tile, (b1 - b0) * tile * tile), accel,
+                                               np.array([a.width, a.height, first_frame + i, b1 - b0], np.uint32), counters) for i in range(n_dispatch)])
+        render.serial += 1
+        for lane in lanes[1:]:   # join the side lanes into the timed stream
+            done.signal(lane, render.serial * 16 + lanes.index(lane)); done.wait(s, render.serial * 16 + lanes.index(lane))
+    render.serial = 0
 
     render(1000); s.synchronize()   # warm-up (different frames), then reset
+    for lane in lanes:
+        lane.synchronize()
     out_t.zero_(); counters_t.zero_(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -113,16 +138,20 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         g0.record(); dist.all_gather_into_tensor(gathered.view(-1), out_t.view(-1)); g1.record(); torch.cuda.synchronize()
         gms = torch.tensor([g0.elapsed_time(g1)], device="cuda")
+        per_rank_ms = torch.empty(world, device="cuda"); dist.all_gather_into_tensor(per_rank_ms, ms)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX); dist.all_reduce(gms, op=dist.ReduceOp.MAX); dist.all_reduce(rays, op=dist.ReduceOp.SUM)
     else:
-        gathered = out_t[None]; gms = torch.zeros(1)
-    if rank == 0:
-        img = sharding.untile(gathered.cpu().numpy(), a.width, a.height, world)
+        gathered = out_t[None]; gms = torch.zeros(1); per_rank_ms = ms.clone()
+    if rank == 0 and a.emulate:
+        os.write(real_stdout, (json.dumps({"emulate": a.emulate, "tiles": int(tx.shape[0]), "render_ms": round(float(ms.item()), 3), "spp_per_dispatch": a.spp_per_dispatch,
+                                           "block": a.block, "streams": len(lanes), "rays": int(rays.sum().item())}) + "\n").encode())
+    elif rank == 0:
+        img = sharding.untile(gathered.cpu().numpy(), a.width, a.height, world, chunk=a.chunk)
         rgb = img[..., :3] / np.maximum(img[..., 3:4], 1)
         total_rays = int(rays.sum().item())
         res = {"config": "c5_path_trace", "n_gpus": world, "width": a.width, "height": a.height, "spp": n_dispatch * a.spp_per_dispatch, "depth": a.depth,
                "triangles": int(tris.shape[0]) * 10 + 2, "instances": n_inst, "blas_build_ms": round(blas_ms, 3), "tlas_build_ms": round(accel.stats()["build_ms"], 3),
-               "render_ms": round(float(ms.item()), 3), "rays": total_rays, "closest_rays": int(rays[0].item()), "any_rays": int(rays[1].item()),
+               "render_ms": round(float(ms.item()), 3), "render_ms_per_rank": [round(float(x), 2) for x in per_rank_ms.tolist()], "block": a.block, "streams": len(lanes), "chunk": a.chunk, "rays": total_rays, "closest_rays": int(rays[0].item()), "any_rays": int(rays[1].item()),
                "mrays_per_s": round(total_rays / float(ms.item()) / 1e3, 1), "msamples_per_s": round(a.width * a.height * n_dispatch * a.spp_per_dispatch / float(ms.item()) / 1e3, 1),
                "gather_ms": round(float(gms.item()), 3), "gather_bytes": int(gathered.numel() * 4), "mean_radiance": round(float(rgb.mean()), 5),
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": hashlib.sha256(img.tobytes()).hexdigest()}
