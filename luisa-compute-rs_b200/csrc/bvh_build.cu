@@ -306,9 +306,11 @@ __global__ void __launch_bounds__(kPlocTile) k_ploc_step(const float4 *__restric
     __shared__ int s_nn[kPlocTile + 2 * kPlocMaxRadius];
     __shared__ uint32_t s_warp[kPlocTile / 32], s_node_base;
     const uint32_t n = st->n_clusters;
-    const int base = (int)(blockIdx.x * kPlocTile);
-    if (n <= 1 || (uint32_t)base >= n) return;
+    if (n <= 1) return;
+    // persistent tiles: the grid is sized once per build, the live cluster count is read on the device
+    for (int base = (int)(blockIdx.x * kPlocTile); (uint32_t)base < n; base += (int)(gridDim.x * kPlocTile)) {
     const int r = radius, span = kPlocTile + 4 * r, first = base - 2 * r;
+    const uint32_t tile_index = (uint32_t)base / kPlocTile;
     for (int t = threadIdx.x; t < span; t += kPlocTile) {
         const int i = first + t;
         if (i >= 0 && (uint32_t)i < n) { s_lo[t] = in[2 * (size_t)i]; s_hi[t] = in[2 * (size_t)i + 1]; }
@@ -378,7 +380,9 @@ __global__ void __launch_bounds__(kPlocTile) k_ploc_step(const float4 *__restric
     if (threadIdx.x == 0) {
         uint32_t tot = 0;
         for (int w = 0; w < kPlocTile / 32; w++) tot += s_warp[w];
-        block_counts[blockIdx.x] = tot;
+        block_counts[tile_index] = tot;
+    }
+    __syncthreads();  // shared arrays are reused by the next tile
     }
 }
 
@@ -417,17 +421,20 @@ __global__ void __launch_bounds__(kPlocTile) k_ploc_compact(const float4 *__rest
                                                             float4 *__restrict__ out, const PlocState *st) {
     __shared__ uint32_t s_warp[kPlocTile / 32];
     const uint32_t n_before = st->pad;
-    const uint32_t i = blockIdx.x * kPlocTile + threadIdx.x;
-    if (n_before <= 1 || blockIdx.x * kPlocTile >= n_before) return;
+    if (n_before <= 1) return;
+    for (uint32_t tile = blockIdx.x; tile * kPlocTile < n_before; tile += gridDim.x) {
+    const uint32_t i = tile * kPlocTile + threadIdx.x;
     const bool k = i < n_before && keep[i] != 0u;
     const uint32_t ballot = __ballot_sync(0xffffffffu, k), lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
-    uint32_t off = block_offsets[blockIdx.x];
+    uint32_t off = block_offsets[tile];
     for (uint32_t w = 0; w < warp; w++) off += s_warp[w];
     if (k) {
         const uint32_t dst = off + __popc(ballot & ((1u << lane) - 1u));
         out[2 * (size_t)dst] = in[2 * (size_t)i]; out[2 * (size_t)dst + 1] = in[2 * (size_t)i + 1];
+    }
+    __syncthreads();
     }
 }
 
@@ -718,20 +725,28 @@ void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc
         float4 *a = sc.ploc_a, *b = sc.ploc_b;
         uint32_t *keep = reinterpret_cast<uint32_t *>(sc.flags);
         k_ploc_init<<<(n + 255) / 256, 256, 0, s>>>(vals, sc.boxes, n, a, sc.ploc_state); lc.count++;
-        // Mutual nearest neighbours always exist, so every iteration merges; in practice the cluster count shrinks by a third to a
-        // half per iteration.  Iterations are launched in chunks with the whole-array grid (tiles past the live count exit at
-        // once) and the live count is read back between chunks; the grid follows it.
-        // Adversarial inputs (distances growing monotonically along the order) can leave one mutual pair per iteration: after 60
+        // Mutual nearest neighbours always exist, so every iteration merges; in practice the cluster count shrinks by 20-45 % per
+        // iteration.  The kernels are persistent over tiles and read the live count on the device, so iterations are launched in
+        // chunks without the host knowing it; it is read back once per chunk (usually once per build).
+        // Adversarial inputs (distances growing monotonically along the order) can leave one mutual pair per iteration: after 72
         // iterations the remaining clusters are paired by position, which halves their number per iteration.
+        static int resident = 0;
+        if (!resident) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ploc_step, kPlocTile, 0);
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        const uint32_t grid = tiles < (uint32_t)resident ? tiles : (uint32_t)resident;
         uint32_t live = n;
         for (int chunk = 0; live > 1; chunk++) {
-            const int iters = chunk == 0 ? 12 : 8;
-            const int forced = chunk >= 7 ? 1 : 0;
-            const uint32_t live_tiles = (live + kPlocTile - 1) / kPlocTile;
+            const int iters = chunk == 0 ? 40 : 16;
+            const int forced = chunk >= 3 ? 1 : 0;  // after 72 iterations
             for (int it = 0; it < iters; it++) {
-                k_ploc_step<<<live_tiles, kPlocTile, 0, s>>>(a, b, keep, sc.ploc_counts, sc.bin, sc.ploc_state, radius, forced);
+                k_ploc_step<<<grid, kPlocTile, 0, s>>>(a, b, keep, sc.ploc_counts, sc.bin, sc.ploc_state, radius, forced);
                 k_ploc_scan<<<1, 1024, 0, s>>>(sc.ploc_counts, sc.ploc_state);
-                k_ploc_compact<<<live_tiles, kPlocTile, 0, s>>>(b, keep, sc.ploc_counts, a, sc.ploc_state);
+                k_ploc_compact<<<grid, kPlocTile, 0, s>>>(b, keep, sc.ploc_counts, a, sc.ploc_state);
                 lc.count += 3;
             }
             PlocState st;

@@ -36,7 +36,10 @@ constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
 #define LCB_TRACE_MIN_BLOCKS 7
 #endif
-constexpr int kSmemStack = 16;                               // stack levels held in shared memory ([level][thread])
+#ifndef LCB_SMEM_STACK
+#define LCB_SMEM_STACK 16
+#endif
+constexpr int kSmemStack = LCB_SMEM_STACK;                               // stack levels held in shared memory ([level][thread])
 constexpr int kLocalStack = kTraversalStack - kSmemStack;    // deeper levels spill to local memory (never on the bench scenes)
 
 // Scheduling knob of the traversal loop (LC_B200_TRACE_TUNE = "fetch_min").
