@@ -164,6 +164,48 @@ def ncu_traffic():
         return None
 
 
+def dsl_path_tracer_leg(dev, lc, scenes, torch, _ext):
+    """Cornell box 1024 x 1024, 32 spp per dispatch, depth 10 (BASELINE configs[1]) with the example's kernel built as an
+    ir::KernelModule and lowered by the device; rays counted by the hand-lowered twin on the same seeds (bit-identical walks)."""
+    import ctypes as C
+    import luisa_compute_rs_b200.examples as ex
+    from luisa_compute_rs_b200 import examples_ir
+    w = h = 1024
+    desc = scenes.c2_cornell()
+    pt = ex.PathTracer(dev, desc.meshes, w, h)
+    for _ in range(2):
+        pt.dispatch(32, 10, count_rays=True)
+    rays_per_dispatch = sum(pt.rays) / 2
+    n = len(desc.meshes)
+    vheap, iheap = dev.create_bindless_array(n), dev.create_bindless_array(n)
+    for i, (vb, ib) in enumerate(zip(pt.vbuffers, pt.ibuffers)):
+        vheap.emplace_buffer_async(i, vb); iheap.emplace_buffer_async(i, ib)
+    s = dev.default_stream()
+    s.submit([vheap.update_async(), iheap.update_async()])
+    image = dev.create_tex2d("Rgba32f", w, h); seeds = dev.create_tex2d("R32Uint", w, h)
+    seeds.copy_from(ex.seed_image(w, h).reshape(h, w))
+    t0 = time.perf_counter()
+    k = examples_ir.path_tracer_kernel(vheap.handle.id, iheap.handle.id, 32, 10, polynomial_sincos=True)
+    shader = dev.create_shader(C.addressof(k.km), keep=k)
+    create_s = time.perf_counter() - t0
+    res = np.array([w, h], np.uint32)
+    shader.dispatch((w, h), image, seeds, pt.accel, res)   # warm-up; same seeds as the counted dispatches above
+    sext = torch.cuda.ExternalStream(s.cuda_stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    e0.record(sext)
+    s.submit([shader.dispatch_async((w, h), image, seeds, pt.accel, res) for _ in range(reps)])
+    e1.record(sext); s.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"workload": "C2: Cornell box 1024x1024, 32 spp per dispatch, depth 10, examples/path_tracer.rs as IR through create_shader",
+           "ms_per_dispatch": ms, "mrays_per_s": rays_per_dispatch / ms / 1e3, "rays_per_dispatch": rays_per_dispatch, "create_shader_s": create_s,
+           "note": "ray count of the first two dispatches of the hand-lowered twin; later dispatches trace a similar number"}
+    for r in (shader, image, seeds, vheap, iheap):
+        r.destroy()
+    pt.destroy()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -270,7 +312,8 @@ def main():
                    "l2": "ray + hit buffers (896 MiB) exceed the 126 MB L2; the BVH (~60 MB) is L2-resident by nature of the workload"},
         "gpu_launches": int(launches), "clocks": clocks,
         "build": {"blas_ms": float(min(build_ms)), "blas_ms_all": [float(x) for x in build_ms], "tlas_ms": float(tlas_ms),
-                  "wide_nodes": int(mstats["wide_node_count"]), "bvh_bytes": int(mstats["bvh_bytes"]), "max_depth": int(mstats["max_depth"])},
+                  "wide_nodes": int(mstats["wide_node_count"]), "bvh_bytes": int(mstats["bvh_bytes"]), "max_depth": int(mstats["max_depth"]),
+                  "builder": ["lbvh", "ploc"][int(mstats["builder"])] + " (chosen per mesh under AccelUsageHint::FastTrace)"},
     }
 
     if rank == 0 and not args.profile:
@@ -323,6 +366,10 @@ def main():
         stream.synchronize()
         hb.view().copy_to(chk)
         assert got.tobytes() == chk.tobytes(), "host and device entry points disagree"
+
+    if rank == 0 and not args.profile:
+        # ---- config C2 beside the headline: examples/path_tracer.rs as an IR kernel through create_shader (IR -> CUDA lowering + NVRTC) ----
+        out["dsl_path_tracer"] = dsl_path_tracer_leg(dev, lc, scenes, torch, ext)
 
     if world > 1 and not args.profile:
         # the one collective of the path: gather of a 4K Float4 framebuffer's tiles over NCCL

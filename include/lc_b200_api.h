@@ -370,7 +370,7 @@ typedef struct lcb_build_stats {
     uint32_t max_depth;        /* wide-tree depth */
     uint32_t was_refit;        /* 1 if PreferUpdate took the refit path */
     float build_ms;            /* device time of the last build (CUDA events) */
-    float _pad;
+    uint32_t builder;          /* binary tree of the last full build: 0 LBVH split rule, 1 PLOC (see lc_b200_set_builder) */
 } lcb_build_stats;
 LCB_EXPORT void lc_b200_mesh_stats(lcb_device, lcb_mesh, lcb_build_stats *out);
 LCB_EXPORT void lc_b200_accel_stats(lcb_device, lcb_accel, lcb_build_stats *out);

@@ -257,7 +257,7 @@ class LibInterface(C.Structure):
 
 class BuildStats(C.Structure):
     _fields_ = [("primitive_count", C.c_uint64), ("wide_node_count", C.c_uint64), ("packed_tri_count", C.c_uint64), ("bvh_bytes", C.c_uint64),
-                ("max_depth", C.c_uint32), ("was_refit", C.c_uint32), ("build_ms", C.c_float), ("_pad", C.c_float)]
+                ("max_depth", C.c_uint32), ("was_refit", C.c_uint32), ("build_ms", C.c_float), ("builder", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

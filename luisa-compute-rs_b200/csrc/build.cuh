@@ -43,7 +43,8 @@ BuildScratch build_scratch_layout(void *base, uint32_t n);
 // builder: how the binary tree over the Morton-sorted primitives is formed — the LBVH split rule (k_hierarchy), PLOC (agglomerative
 // clustering, k_ploc_*), or chosen per mesh from the primitives' overlap (kBuilderAuto).
 enum { kBuilderLbvh = 0, kBuilderPloc = 1, kBuilderAuto = 2 };
-void build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder);
+// returns the builder that ran (kBuilderLbvh / kBuilderPloc)
+int build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder);
 // Procedural primitives: a BLAS over user AABBs (24-byte {min, max} records); leaf slots hold the box and the primitive id.
 void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc);
 void build_tlas(cudaStream_t s, uint32_t n_active, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc,

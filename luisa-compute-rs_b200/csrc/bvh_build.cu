@@ -806,7 +806,7 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
     return sc;
 }
 
-void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder) {
+int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
@@ -826,6 +826,7 @@ void build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const Build
     LeafSinkTriangles sink{tris};
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, use_ploc);
     k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
+    return use_ploc && n > 1 ? kBuilderPloc : kBuilderLbvh;
 }
 
 void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc) {

@@ -376,8 +376,9 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
     // LC_B200_BUILDER=lbvh|ploc|auto overrides.
     const int forced = g_builder_override.load();
     const int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
+    int built_with = kBuilderLbvh;
     if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
-    else build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
+    else built_with = build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
     BuildHeader hdr;
     CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
@@ -399,7 +400,7 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     m->stats.wide_node_count = hdr.node_count; m->stats.packed_tri_count = hdr.prim_count;
     m->stats.bvh_bytes = (uint64_t)m->node_capacity * sizeof(WideNode) + (uint64_t)n * sizeof(PackedTri);
-    m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.build_ms = ms;
+    m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.build_ms = ms; m->stats.builder = (uint32_t)built_with;
 }
 
 // ---- accel build (AccelImpl::update, cpu/accel.rs:324-447) ---------------------------------------
