@@ -193,7 +193,7 @@ __device__ __forceinline__ uint64_t expand21(uint32_t x) {
 }
 
 __global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxes, uint32_t n, const BuildHeader *__restrict__ h,
-                                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int drop_bits) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)i];
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxe
         t = fminf(fmaxf(t, 0.f), 1.f);
         q[k] = min((uint32_t)(t * 2097152.0f), 2097151u);
     }
-    // the top 48 bits of the 63-bit code (16 bits per axis): six 8-bit sort passes; equal keys are split by position
-    keys[i] = (expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2)) >> 15;
+    // the top 8 * passes bits of the 63-bit code, one 8-bit sort pass each; equal keys are split by position
+    keys[i] = (expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2)) >> drop_bits;
     vals[i] = i;
 }
 
@@ -715,8 +715,18 @@ __global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) { 
 
 template <class Sink>
 void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc, bool ploc) {
-    k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals); lc.count++;
-    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, 6, lc);
+    // Morton resolution follows the primitive count: log2(n) bits only enumerate the primitives, the rest resolves non-uniform
+    // density — 12 extra bits measured as good as 28 on the bench scenes (profiles/r01r_sort_passes.txt); each pass saved is one
+    // sweep over the pairs (24 B per pair).  LC_B200_SORT_PASSES overrides (3..6).
+    static const int forced_passes = [] { const char *e = getenv("LC_B200_SORT_PASSES"); int v = e ? atoi(e) : 0; return v >= 3 && v <= 6 ? v : 0; }();
+    int passes = forced_passes;
+    if (!passes) {
+        int lg = 0; while ((1ull << lg) < n) lg++;
+        passes = (lg + 12 + 7) / 8;
+        passes = passes < 3 ? 3 : (passes > 6 ? 6 : passes);
+    }
+    k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals, 63 - 8 * passes); lc.count++;
+    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, passes, lc);
     const uint64_t *keys = in_alt ? sc.keys_alt : sc.keys;
     const uint32_t *vals = in_alt ? sc.vals_alt : sc.vals;
     if (ploc && n > 1) {

@@ -128,6 +128,7 @@ struct BufferObj { uint8_t *ptr = nullptr; size_t size = 0; bool owned = true; }
 struct MeshObj {
     lcb_accel_option option{};
     bool built = false;
+    int auto_builder = -1; uint32_t auto_builder_n = 0;  // what the per-mesh builder choice picked last time, and for how many triangles
     bool procedural = false;  // created by create_procedural_primitive: leaves are user AABBs, hits come from the RayQuery callback
     uint32_t n_tris = 0;
     uint64_t generation = 0;  // bumped whenever nodes/tris are re-allocated
@@ -375,10 +376,15 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
     // lets the builder choose between PLOC and the LBVH split rule per mesh, FastBuild always takes the LBVH.
     // LC_B200_BUILDER=lbvh|ploc|auto overrides.
     const int forced = g_builder_override.load();
-    const int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
+    int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
+    // the per-mesh choice reads a statistic back from the device (one stream synchronisation); a rebuild of the same mesh with the
+    // same triangle count reuses the previous answer
+    const bool was_auto = builder == kBuilderAuto;
+    if (was_auto && m->auto_builder >= 0 && m->auto_builder_n == n) builder = m->auto_builder;
     int built_with = kBuilderLbvh;
     if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
     else built_with = build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
+    if (was_auto) { m->auto_builder = built_with; m->auto_builder_n = n; }
     BuildHeader hdr;
     CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
