@@ -221,20 +221,85 @@ __device__ __forceinline__ uint64_t split_delta(const uint64_t *__restrict__ key
     return x ? (x | (1ull << 63)) : (uint64_t)(i ^ (i + 1));
 }
 
+// Two phases.  (1) Warp-local: the 32 consecutive sorted leaves of a warp are merged with shuffles only — every lane owns the
+// cluster that starts at its leaf; per step a cluster whose parent lies to its right merges with the next active cluster when
+// that one's parent lies to its left (then both are children of internal node `right`); a cluster whose sibling is outside the
+// warp's span leaves for phase 2.  31 of 32 internal nodes are emitted here without atomics, fences or L2 round trips.
+// (2) Global: the classic bottom-up climb with one atomic exchange per arrival (Apetrei 2014): the first child to arrive at an
+// internal node leaves its box there and stops, the second merges and continues.
 __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ prim, const PrimBox *__restrict__ boxes,
                                                    uint32_t n, BinNode *bin, int *flags, BuildHeader *h) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t p = prim[i];
-    float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p];
-    float4 hi = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p + 1];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp_base = i - lane;
+    if (warp_base >= n) return;  // whole warp out of range
+    const bool in_range = i < n;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (in_range) {
+        const uint32_t p = prim[i];
+        lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p];
+        hi = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)p + 1];
+    }
     uint32_t left = i, right = i, cur = i | kLeafBit;
     if (n == 1) {
-        h->root = cur;
-        h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
-        h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+        if (i == 0) {
+            h->root = cur;
+            h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
+            h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+        }
         return;
     }
+    // delta of the split after leaf i (between i and i + 1), and of the split before the warp's first leaf
+    const uint64_t d_mine = (in_range && i + 1 < n) ? split_delta(keys, i) : ~0ull;
+    const uint64_t d_before = warp_base > 0 ? split_delta(keys, warp_base - 1) : ~0ull;
+    bool local = in_range;    // still owned by phase 1
+    bool climbing = false;    // left phase 1 for phase 2
+    bool done = false;
+    for (;;) {
+        const uint32_t active = __ballot_sync(0xffffffffu, local);
+        if (active == 0u) break;
+        // my decision: is my parent the split to my right?
+        const uint64_t d_right = __shfl_sync(0xffffffffu, d_mine, (right - warp_base) & 31u);
+        const uint64_t d_left_in = __shfl_sync(0xffffffffu, d_mine, (left - 1u - warp_base) & 31u);
+        const uint64_t d_left = left == warp_base ? d_before : d_left_in;
+        const bool want_right = local && ((left == 0) || (right != n - 1 && d_right < d_left));
+        const bool want_left = local && !want_right;
+        const uint32_t next = (active & ~((2u << lane) - 1u)) ? (uint32_t)__ffs(active & ~((2u << lane) - 1u)) - 1u : 32u;
+        const uint32_t next_wants_left = __ballot_sync(0xffffffffu, want_left);
+        const bool merge = want_right && next < 32u && (next_wants_left >> next & 1u);
+        const uint32_t merge_ballot = __ballot_sync(0xffffffffu, merge);
+        // the cluster right before me merges with me this step: I am absorbed
+        const uint32_t prev = (active & ((1u << lane) - 1u)) ? 31u - (uint32_t)__clz(active & ((1u << lane) - 1u)) : 32u;
+        const bool absorbed = local && prev < 32u && (merge_ballot >> prev & 1u);
+        // sibling data travels from lane `next` to me
+        const uint32_t src = next & 31u;
+        const float4 slo = make_float4(__shfl_sync(0xffffffffu, lo.x, src), __shfl_sync(0xffffffffu, lo.y, src), __shfl_sync(0xffffffffu, lo.z, src), 0.f);
+        const float4 shi = make_float4(__shfl_sync(0xffffffffu, hi.x, src), __shfl_sync(0xffffffffu, hi.y, src), __shfl_sync(0xffffffffu, hi.z, src), 0.f);
+        const uint32_t s_cur = __shfl_sync(0xffffffffu, cur, src), s_right = __shfl_sync(0xffffffffu, right, src);
+        if (merge) {
+            const uint32_t parent = right;
+            float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
+            pn[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
+            pn[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(right - left + 1u));
+            pn[2] = make_float4(slo.x, slo.y, slo.z, __uint_as_float(s_cur));
+            pn[3] = make_float4(shi.x, shi.y, shi.z, __uint_as_float(s_right - right));
+            lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
+            hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
+            right = s_right; cur = parent;
+            if (left == 0 && right == n - 1) {
+                h->root = parent;
+                h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
+                h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
+                local = false; done = true;
+            }
+        } else if (absorbed) {
+            local = false; done = true;
+        } else if ((want_right && next == 32u) || (want_left && prev == 32u)) {
+            // no phase-1 cluster on the side my sibling will come from: it lives in (or will be formed by clusters of) another warp.
+            // Only the outermost clusters can leave, so the remaining ones stay contiguous.
+            local = false; climbing = true;
+        }
+    }
+    if (!climbing || done) return;
     while (true) {
         const uint32_t count = right - left + 1;
         const bool parent_on_right = (left == 0) || (right != n - 1 && split_delta(keys, right) < split_delta(keys, left - 1));
