@@ -563,8 +563,11 @@ __device__ __forceinline__ void quantise_axis(float clo, float chi, float org, f
 constexpr int kCollapseThreads = 256;
 constexpr int kCollapseGroups = kCollapseThreads / 8;
 
+#ifndef LCB_COLLAPSE_MIN_BLOCKS
+#define LCB_COLLAPSE_MIN_BLOCKS 5
+#endif
 template <class Sink>
-__global__ void __launch_bounds__(kCollapseThreads) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
+__global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
                                                                unsigned long long *queue, WideNode *nodes, uint32_t capacity, Sink sink) {
     __shared__ WideNode s_node[kCollapseGroups];
     __shared__ uint32_t s_int[kCollapseGroups], s_prm[kCollapseGroups];
