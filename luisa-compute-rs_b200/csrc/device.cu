@@ -1019,7 +1019,12 @@ void lc_b200_trace_closest_counted(lcb_device dev, lcb_stream sh, lcb_accel ah, 
 // two alternating streams (each with its own ray-pool counter) so that the tail of one persistent launch overlaps the
 // start of the next.
 static uint64_t host_chunk_rays() {
-    static uint64_t c = [] { uint64_t v = 1ull << 20; if (const char *e = getenv("LC_B200_HOST_CHUNK")) v = strtoull(e, nullptr, 10); return v < 1024 ? 1024 : v; }();
+    static uint64_t c = [] { uint64_t v = 1ull << 18; if (const char *e = getenv("LC_B200_HOST_CHUNK")) v = strtoull(e, nullptr, 10); return v < 1024 ? 1024 : v; }();
+    return c;
+}
+
+static uint64_t host_chunk_max_rays() {
+    static uint64_t c = [] { uint64_t v = 1ull << 20; if (const char *e = getenv("LC_B200_HOST_CHUNK_MAX")) v = strtoull(e, nullptr, 10); return v; }();
     return c;
 }
 
@@ -1027,14 +1032,30 @@ static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays,
     std::lock_guard<std::mutex> lk(d->mu);
     ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
     ensure_stage(d->stage_out, d->stage_out_cap, count * out_stride);
-    const uint64_t chunk = host_chunk_rays();
-    const size_t n_chunks = (size_t)((count + chunk - 1) / chunk);
+    // Chunk schedule: small chunks at both ends (the first kernel cannot start before its rays arrived, the last download cannot start
+    // before its kernel ended), doubling towards the middle where large chunks keep the number of persistent launches down.
+    // LC_B200_HOST_CHUNK = size of the end chunks, LC_B200_HOST_CHUNK_MAX = cap in the middle (equal values: uniform chunks).
+    const uint64_t c_min = host_chunk_rays(), c_max = std::max(c_min, host_chunk_max_rays());
+    std::vector<uint64_t> sizes;
+    {
+        std::vector<uint64_t> head, tail;
+        uint64_t left = count, ch = c_min, ct = c_min;
+        while (left > 0) {
+            uint64_t n = std::min(ch, left); head.push_back(n); left -= n; ch = std::min(ch * 2, c_max);
+            if (left == 0) break;
+            n = std::min(ct, left); tail.push_back(n); left -= n; ct = std::min(ct * 2, c_max);
+        }
+        sizes = head;
+        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+    }
+    const size_t n_chunks = sizes.size();
     std::vector<cudaEvent_t> ev(2 * n_chunks);
     for (auto &e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     StreamObj *lanes[2] = {d->internal, d->internal2};
     const AccelView view = view_of(a);
+    uint64_t first = 0;
     for (size_t c = 0; c < n_chunks; c++) {
-        const uint64_t first = c * chunk, n = std::min(chunk, count - first);
+        const uint64_t n = sizes[c];
         StreamObj *k = lanes[c & 1];
         CUDA_CHECK(cudaMemcpyAsync(d->stage_rays + first * 32, rays + first, n * 32, cudaMemcpyHostToDevice, d->copy_in));
         CUDA_CHECK(cudaEventRecord(ev[2 * c], d->copy_in));
@@ -1044,6 +1065,7 @@ static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays,
         CUDA_CHECK(cudaEventRecord(ev[2 * c + 1], k->stream));
         CUDA_CHECK(cudaStreamWaitEvent(d->copy_out, ev[2 * c + 1], 0));
         CUDA_CHECK(cudaMemcpyAsync((uint8_t *)out + first * out_stride, d->stage_out + first * out_stride, n * out_stride, cudaMemcpyDeviceToHost, d->copy_out));
+        first += n;
     }
     CUDA_CHECK(cudaStreamSynchronize(d->copy_out));
     CUDA_CHECK(cudaStreamSynchronize(lanes[0]->stream));
