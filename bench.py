@@ -146,7 +146,7 @@ def run_reference(args, rank):
     }))
 
 
-NCU_SUMMARY = "profiles/r01g_k_trace_ncu_full_summary.csv"
+NCU_SUMMARY = "profiles/r01t_k_trace_ncu_full_summary.csv"
 
 
 def ncu_traffic():
