@@ -267,6 +267,7 @@ struct FunctionEmitter {
     int indent = 1;
     bool in_generic_loop = false;
     bool is_callable = false;
+    int nest = 0;  // depth of enclosing If / Switch / loop / RayQuery blocks
 
     explicit FunctionEmitter(Globals &gl) : g(gl) {}
 
@@ -401,6 +402,12 @@ struct FunctionEmitter {
         auto bin = [&](const char *op) { need(2); value(a[0] + " " + op + " " + a[1]); };
         auto fn = [&](const char *name) { value(std::string(name) + "(" + join(a) + ")"); };
         if (f.tag < 0 || f.tag >= Func::COUNT) fail("unknown Func discriminant " + std::to_string(f.tag));
+        // Warp operations act on the lanes that reach them.  At the top level of the kernel body that is every live lane of the warp
+        // (lc_warp_mask, taken at kernel entry) and the *_sync primitives wait for exactly those lanes, so the result does not depend
+        // on whether the hardware has reconverged after divergent code (an If, the CAS loop inside a float atomic); inside divergent
+        // constructs and callables it is the lanes present (__activemask()).
+        const bool is_warp_op = f.tag >= Func::WarpIsFirstActiveLane && f.tag <= Func::WarpReadFirstLane;
+        if (is_warp_op) a.insert(a.begin(), nest == 0 && !is_callable ? "lc_warp_mask" : "__activemask()");
         switch (f.tag) {
             case Func::Add: bin("+"); break;
             case Func::Sub: bin("-"); break;
@@ -488,8 +495,8 @@ struct FunctionEmitter {
             case Func::Transpose: fn("lc_transpose"); break;
             case Func::Inverse: fn("lc_inverse"); break;
             case Func::SynchronizeBlock: line("__syncthreads();"); break;
-            case Func::WarpIsFirstActiveLane: value("lc_warp_is_first_active_lane()"); break;
-            case Func::WarpFirstActiveLane: value("lc_warp_first_active_lane()"); break;
+            case Func::WarpIsFirstActiveLane: fn("lc_warp_is_first_active_lane"); break;
+            case Func::WarpFirstActiveLane: fn("lc_warp_first_active_lane"); break;
             case Func::WarpActiveAllEqual: fn("lc_warp_active_all_equal"); break;
             case Func::WarpActiveBitAnd: fn("lc_warp_active_bit_and"); break;
             case Func::WarpActiveBitOr: fn("lc_warp_active_bit_or"); break;
@@ -633,9 +640,9 @@ struct FunctionEmitter {
     }
     void emit_block(const BasicBlock *bb) {
         line("{");
-        indent++;
+        indent++; nest++;
         emit_block_content(bb);
-        indent--;
+        indent--; nest--;
         line("}");
     }
 
@@ -659,10 +666,10 @@ struct FunctionEmitter {
             case Instruction::Loop: {  // do { body } while (cond)  — cpp.rs:1683-1699
                 const bool old = in_generic_loop; in_generic_loop = false;
                 line("for (;;) {");
-                indent++;
+                indent++; nest++;
                 emit_block_content(ins->loop.body.ptr);
                 line("if (!(" + ref(ins->loop.cond) + ")) break;");
-                indent--;
+                indent--; nest--;
                 line("}");
                 in_generic_loop = old;
                 break;
@@ -670,7 +677,7 @@ struct FunctionEmitter {
             case Instruction::GenericLoop: {
                 const bool old = in_generic_loop; in_generic_loop = true;
                 line("for (;;) {");
-                indent++;
+                indent++; nest++;
                 line("bool loop_break = false;");
                 emit_block_content(ins->generic_loop.prepare.ptr);
                 line("if (!(" + ref(ins->generic_loop.cond) + ")) break;");
@@ -679,7 +686,7 @@ struct FunctionEmitter {
                 line("while (false);");
                 line("if (loop_break) break;");
                 emit_block(ins->generic_loop.update.ptr);
-                indent--;
+                indent--; nest--;
                 line("}");
                 in_generic_loop = old;
                 break;
@@ -864,10 +871,11 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
         << g.callable_defs
         << "extern \"C\" __global__ void __launch_bounds__(" << (out.block_size[0] * out.block_size[1] * out.block_size[2]) << ") lc_kernel(const lc_params p) {\n"
         << g.shared_decls
-        << "    {   // partial edge blocks are clipped to dispatch_size (cpu/stream.rs:384-404)\n"
-        << "        const lc_uint3 id = lc_dispatch_id();\n"
-        << "        if (id.x >= p.launch.dispatch_size[0] || id.y >= p.launch.dispatch_size[1] || id.z >= p.launch.dispatch_size[2]) return;\n"
-        << "    }\n"
+        << "    // partial edge blocks are clipped to dispatch_size (cpu/stream.rs:384-404); lc_warp_mask = this warp's live lanes\n"
+        << "    const lc_uint3 lc_id = lc_dispatch_id();\n"
+        << "    const bool lc_live = lc_id.x < p.launch.dispatch_size[0] && lc_id.y < p.launch.dispatch_size[1] && lc_id.z < p.launch.dispatch_size[2];\n"
+        << "    const uint32_t lc_warp_mask = __ballot_sync(0xffffffffu, lc_live);\n"
+        << "    if (!lc_live) return;\n"
         << fe.decls << fe.body << "}\n";
     out.source = src.str();
     out.messages = g.messages;

@@ -315,25 +315,28 @@ __device__ inline float lc_atomic_fetch_max(float *p, float v) {
     for (;;) { const float seen = lc_atomic_compare_exchange(p, old, fmaxf(old, v)); if (__float_as_uint(seen) == __float_as_uint(old)) return old; old = seen; }
 }
 
-// ---- warp intrinsics over the active lanes ----------------------------------------------------------------------------------
+// ---- warp intrinsics -----------------------------------------------------------------------------------------------------
+// Every operation takes the mask `m` of the lanes taking part.  At the top level of a kernel body the lowering passes the mask of
+// the warp's live lanes, computed once at kernel entry (lc_warp_mask): the *_sync primitives then wait for exactly those lanes, so
+// the result does not depend on whether the hardware has reconverged after earlier divergent code (an If, the CAS loop of a float
+// atomic).  Inside divergent constructs it passes __activemask(): the lanes that are there.
 __device__ inline uint32_t lc_lane_id() { return (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u; }
-__device__ inline bool lc_warp_is_first_active_lane() { return lc_lane_id() == (uint32_t)(__ffs(__activemask()) - 1); }
-__device__ inline uint32_t lc_warp_first_active_lane() { return (uint32_t)(__ffs(__activemask()) - 1); }
-__device__ inline bool lc_warp_active_all(bool v) { return __all_sync(__activemask(), v); }
-__device__ inline bool lc_warp_active_any(bool v) { return __any_sync(__activemask(), v); }
-__device__ inline lc_uint4 lc_warp_active_bit_mask(bool v) { return lc_uint4(__ballot_sync(__activemask(), v), 0u, 0u, 0u); }
-__device__ inline uint32_t lc_warp_active_count_bits(bool v) { return __popc(__ballot_sync(__activemask(), v)); }
-__device__ inline uint32_t lc_warp_prefix_count_bits(bool v) { return __popc(__ballot_sync(__activemask(), v) & ((1u << lc_lane_id()) - 1u)); }
-template <class T> __device__ inline T lc_warp_read_lane_at(T v, uint32_t lane) { return __shfl_sync(__activemask(), v, lane); }
-template <class T> __device__ inline T lc_warp_read_first_lane(T v) { return __shfl_sync(__activemask(), v, __ffs(__activemask()) - 1); }
-template <class T, class Op> __device__ inline T lc_warp_reduce(T v, Op op) {
-    const uint32_t m = __activemask();
+__device__ inline bool lc_warp_is_first_active_lane(uint32_t m) { return lc_lane_id() == (uint32_t)(__ffs(m) - 1); }
+__device__ inline uint32_t lc_warp_first_active_lane(uint32_t m) { return (uint32_t)(__ffs(m) - 1); }
+__device__ inline bool lc_warp_active_all(uint32_t m, bool v) { return __all_sync(m, v); }
+__device__ inline bool lc_warp_active_any(uint32_t m, bool v) { return __any_sync(m, v); }
+__device__ inline lc_uint4 lc_warp_active_bit_mask(uint32_t m, bool v) { return lc_uint4(__ballot_sync(m, v), 0u, 0u, 0u); }
+__device__ inline uint32_t lc_warp_active_count_bits(uint32_t m, bool v) { return __popc(__ballot_sync(m, v)); }
+__device__ inline uint32_t lc_warp_prefix_count_bits(uint32_t m, bool v) { return __popc(__ballot_sync(m, v) & ((1u << lc_lane_id()) - 1u)); }
+template <class T> __device__ inline T lc_warp_read_lane_at(uint32_t m, T v, uint32_t lane) { return __shfl_sync(m, v, lane); }
+template <class T> __device__ inline T lc_warp_read_first_lane(uint32_t m, T v) { return __shfl_sync(m, v, __ffs(m) - 1); }
+template <class T, class Op> __device__ inline T lc_warp_reduce(uint32_t m, T v, Op op) {
     T r = v; bool have = false;
     for (uint32_t lanes = m; lanes; lanes &= lanes - 1) { const T o = __shfl_sync(m, v, __ffs(lanes) - 1); r = have ? op(r, o) : o; have = true; }
     return r;
 }
-template <class T, class Op> __device__ inline T lc_warp_prefix(T v, T identity, Op op) {
-    const uint32_t m = __activemask(), me = lc_lane_id();
+template <class T, class Op> __device__ inline T lc_warp_prefix(uint32_t m, T v, T identity, Op op) {
+    const uint32_t me = lc_lane_id();
     T r = identity;
     for (uint32_t lanes = m; lanes; lanes &= lanes - 1) { const uint32_t l = __ffs(lanes) - 1; const T o = __shfl_sync(m, v, l); if (l < me) r = op(r, o); }
     return r;
@@ -345,16 +348,16 @@ struct lc_op_max { template <class T> __device__ T operator()(T a, T b) const { 
 struct lc_op_and { template <class T> __device__ T operator()(T a, T b) const { return a & b; } };
 struct lc_op_or { template <class T> __device__ T operator()(T a, T b) const { return a | b; } };
 struct lc_op_xor { template <class T> __device__ T operator()(T a, T b) const { return a ^ b; } };
-template <class T> __device__ inline T lc_warp_active_sum(T v) { return lc_warp_reduce(v, lc_op_add()); }
-template <class T> __device__ inline T lc_warp_active_product(T v) { return lc_warp_reduce(v, lc_op_mul()); }
-template <class T> __device__ inline T lc_warp_active_min(T v) { return lc_warp_reduce(v, lc_op_min()); }
-template <class T> __device__ inline T lc_warp_active_max(T v) { return lc_warp_reduce(v, lc_op_max()); }
-template <class T> __device__ inline T lc_warp_active_bit_and(T v) { return lc_warp_reduce(v, lc_op_and()); }
-template <class T> __device__ inline T lc_warp_active_bit_or(T v) { return lc_warp_reduce(v, lc_op_or()); }
-template <class T> __device__ inline T lc_warp_active_bit_xor(T v) { return lc_warp_reduce(v, lc_op_xor()); }
-template <class T> __device__ inline bool lc_warp_active_all_equal(T v) { return __all_sync(__activemask(), v == lc_warp_read_first_lane(v)); }
-template <class T> __device__ inline T lc_warp_prefix_sum(T v) { return lc_warp_prefix(v, T(0), lc_op_add()); }
-template <class T> __device__ inline T lc_warp_prefix_product(T v) { return lc_warp_prefix(v, T(1), lc_op_mul()); }
+template <class T> __device__ inline T lc_warp_active_sum(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_add()); }
+template <class T> __device__ inline T lc_warp_active_product(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_mul()); }
+template <class T> __device__ inline T lc_warp_active_min(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_min()); }
+template <class T> __device__ inline T lc_warp_active_max(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_max()); }
+template <class T> __device__ inline T lc_warp_active_bit_and(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_and()); }
+template <class T> __device__ inline T lc_warp_active_bit_or(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_or()); }
+template <class T> __device__ inline T lc_warp_active_bit_xor(uint32_t m, T v) { return lc_warp_reduce(m, v, lc_op_xor()); }
+template <class T> __device__ inline bool lc_warp_active_all_equal(uint32_t m, T v) { return __all_sync(m, v == lc_warp_read_first_lane(m, v)); }
+template <class T> __device__ inline T lc_warp_prefix_sum(uint32_t m, T v) { return lc_warp_prefix(m, v, T(0), lc_op_add()); }
+template <class T> __device__ inline T lc_warp_prefix_product(uint32_t m, T v) { return lc_warp_prefix(m, v, T(1), lc_op_mul()); }
 
 // casts between vectors (Func::Cast on vectors, cpp.rs:1218-1226)
 template <class D, class S, int N> __device__ inline lc_vec<D, N> lc_vec_cast(lc_vec<S, N> v) { lc_vec<D, N> r; LC_LOOP r[i] = static_cast<D>(v[i]); return r; }
