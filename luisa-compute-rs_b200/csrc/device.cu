@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -855,15 +856,56 @@ void destroy_device(lcb_device_interface iface) {
     delete d;
 }
 
+// Device names this library does not own are forwarded to the stock backend library when one is installed next to it: the frontend
+// dlopens a fixed file name (liblc-api.so, luisa_compute_backend/src/lib.rs:102-117), so a drop-in that keeps "cpu" / "cuda" working is
+// this library under that name plus the original renamed to liblc-api-orig.so (or named by LC_B200_FORWARD_LIB).  SURVEY.md §8b.
+struct Forward { void *handle = nullptr; lcb_lib_interface iface{}; lcb_context ctx{0}; bool tried = false; std::mutex mu; };
+Forward g_forward;
+
+bool forward_ready(const char *runtime_dir) {
+    std::lock_guard<std::mutex> lk(g_forward.mu);
+    if (g_forward.tried) return g_forward.handle != nullptr;
+    g_forward.tried = true;
+    std::vector<std::string> candidates;
+    if (const char *env = getenv("LC_B200_FORWARD_LIB")) candidates.push_back(env);
+    Dl_info info;
+    if (dladdr((const void *)&forward_ready, &info) && info.dli_fname) {
+        std::string dir = info.dli_fname;
+        const size_t slash = dir.rfind('/');
+        dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+        candidates.push_back(dir + "/liblc-api-orig.so");
+    }
+    for (const std::string &c : candidates) {
+        void *h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) continue;
+        auto entry = (lcb_lib_interface(*)(void))dlsym(h, "luisa_compute_lib_interface");
+        if (!entry) { dlclose(h); continue; }
+        g_forward.handle = h;
+        g_forward.iface = entry();
+        if (g_forward.iface.set_logger_callback && g_logger.load()) g_forward.iface.set_logger_callback(g_logger.load());
+        g_forward.ctx = g_forward.iface.create_context(runtime_dir ? runtime_dir : ".");
+        log_msg("I", "device names other than \"b200\" are forwarded to %s", c.c_str());
+        return true;
+    }
+    return false;
+}
+
 // ---- library interface -----------------------------------------------------------------------------
-void set_logger_callback(void (*cb)(lcb_logger_message)) { g_logger.store(cb); }
+void set_logger_callback(void (*cb)(lcb_logger_message)) {
+    g_logger.store(cb);
+    std::lock_guard<std::mutex> lk(g_forward.mu);
+    if (g_forward.handle && g_forward.iface.set_logger_callback) g_forward.iface.set_logger_callback(cb);
+}
 lcb_context create_context(const char *) { return lcb_context{1}; }
 void destroy_context(lcb_context) {}
 void free_string(char *s) { free(s); }
 
 lcb_device_interface create_device(lcb_context, const char *name, const char *json) {
-    if (!name || (strcmp(name, "b200") != 0 && strcmp(name, "cuda-b200") != 0))
-        fatal("device \"%s\" is not served by this library (only \"b200\"); there is no CPU fallback", name ? name : "(null)");
+    if (!name || (strcmp(name, "b200") != 0 && strcmp(name, "cuda-b200") != 0)) {
+        if (name && forward_ready(nullptr)) return g_forward.iface.create_device(g_forward.ctx, name, json);
+        fatal("device \"%s\" is not served by this library (only \"b200\") and no stock backend library (liblc-api-orig.so / LC_B200_FORWARD_LIB) "
+              "is installed to forward to; there is no CPU fallback", name ? name : "(null)");
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) fatal("no CUDA device available (%s); the b200 device has no CPU fallback", cudaGetErrorString(e));

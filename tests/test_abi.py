@@ -59,3 +59,52 @@ def test_affine_packing_matches_into_affine3x4():
     import numpy as np
     m = np.arange(16, dtype=np.float32).reshape(4, 4)
     assert lc.affine_from_mat4(m).tolist() == list(range(12))
+
+
+def test_foreign_device_names_are_forwarded_to_the_stock_library(tmp_path):
+    """Drop-in under the frontend's fixed file name (liblc-api.so): device names other than "b200" go to the original backend library
+    (liblc-api-orig.so next to ours, or LC_B200_FORWARD_LIB).  A stand-in library records the call; runs in a subprocess because the
+    forwarding target is resolved once per process."""
+    import subprocess, sys, textwrap
+    src = tmp_path / "fake_backend.c"
+    src.write_text(textwrap.dedent('''
+        #include <stdint.h>
+        #include <string.h>
+        #include "lc_b200_api.h"
+        static char seen[64];
+        static lcb_context create_context(const char *dir) { lcb_context c = {42}; return c; }
+        static void destroy_context(lcb_context c) {}
+        static void set_logger(void (*cb)(lcb_logger_message)) {}
+        static void free_string(char *s) {}
+        static uint32_t warp(lcb_device d) { return 7; }
+        static char *query(lcb_device d, const char *name) { return seen; }
+        static lcb_device_interface create_device(lcb_context c, const char *name, const char *json) {
+            lcb_device_interface t; memset(&t, 0, sizeof(t));
+            t.device.id = c.id * 100 + 1; t.compute_warp_size = warp; t.query = query;
+            strncpy(seen, name, sizeof(seen) - 1);
+            return t;
+        }
+        lcb_lib_interface luisa_compute_lib_interface(void) {
+            lcb_lib_interface l; memset(&l, 0, sizeof(l));
+            l.set_logger_callback = set_logger; l.create_context = create_context; l.destroy_context = destroy_context; l.create_device = create_device; l.free_string = free_string;
+            return l;
+        }
+    '''))
+    so = tmp_path / "libfake.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", str(so), str(src)], check=True)
+    code = textwrap.dedent(f'''
+        import ctypes as C, sys
+        sys.path.insert(0, {ROOT!r})
+        import luisa_compute_rs_b200 as lc
+        abi = lc._abi
+        iface = abi.load_library().luisa_compute_lib_interface()
+        ctx = iface.create_context(b".")
+        dev = iface.create_device(ctx, b"cpu", None)
+        assert dev.device.id == 4201, dev.device.id
+        assert dev.compute_warp_size(dev.device) == 7
+        assert C.string_at(dev.query(dev.device, b"device_name")) == b"cpu"
+        print("forwarded")
+    ''')
+    env = dict(os.environ, LC_B200_FORWARD_LIB=str(so))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "forwarded" in r.stdout, r.stdout + r.stderr
