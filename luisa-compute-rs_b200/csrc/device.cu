@@ -714,7 +714,7 @@ size_t texture_region_bytes(const TextureObj *t, int32_t storage, uint32_t level
     if (size[0] != t->width || size[1] != t->height || (t->dim == 3 && size[2] != t->depth)) fatal("%s: region %ux%ux%u is not the whole level (%ux%ux%u)", what, size[0], size[1], size[2], t->width, t->height, t->depth);
     return t->bytes;
 }
-HostTextureArg texture_arg(const TextureObj *t) { return HostTextureArg{t->ptr, t->width, t->height, t->depth, (uint32_t)t->storage}; }
+HostTextureArg texture_arg(const TextureObj *t, uint32_t sampler = 0) { return HostTextureArg{t->ptr, t->width, t->height, t->depth, (uint32_t)t->storage, sampler, 0u}; }
 
 // ---- bindless arrays -------------------------------------------------------------------------------------------------------
 lcb_created create_bindless_array(lcb_device dev, size_t size) {
@@ -739,8 +739,8 @@ void bindless_update(StreamObj *s, const lcb_cmd_bindless_update &c) {  // Bindl
             if (m.buffer.offset > buf->size) fatal("BindlessArrayUpdate: buffer offset beyond the buffer");
             slot.buffer = buf->ptr + m.buffer.offset; slot.buffer_size = buf->size - m.buffer.offset;
         } else if (m.buffer.op == 2) { slot.buffer = nullptr; slot.buffer_size = 0; }
-        if (m.tex2d.op == 1) slot.tex2d = texture_arg(as<TextureObj>(m.tex2d.handle.id)); else if (m.tex2d.op == 2) slot.tex2d = HostTextureArg{};
-        if (m.tex3d.op == 1) slot.tex3d = texture_arg(as<TextureObj>(m.tex3d.handle.id)); else if (m.tex3d.op == 2) slot.tex3d = HostTextureArg{};
+        if (m.tex2d.op == 1) slot.tex2d = texture_arg(as<TextureObj>(m.tex2d.handle.id), (uint32_t)(m.tex2d.sampler.filter & 3) | ((uint32_t)(m.tex2d.sampler.address & 3) << 2)); else if (m.tex2d.op == 2) slot.tex2d = HostTextureArg{};
+        if (m.tex3d.op == 1) slot.tex3d = texture_arg(as<TextureObj>(m.tex3d.handle.id), (uint32_t)(m.tex3d.sampler.filter & 3) | ((uint32_t)(m.tex3d.sampler.address & 3) << 2)); else if (m.tex3d.op == 2) slot.tex3d = HostTextureArg{};
         lo = std::min(lo, m.slot); hi = std::max(hi, m.slot + 1);
     }
     if (lo < hi)  // pageable source: staged before the call returns, the host table may change right after

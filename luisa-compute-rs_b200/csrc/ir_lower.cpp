@@ -580,6 +580,17 @@ struct FunctionEmitter {
             case Func::BindlessBufferAddress: need(2); value("lc_bindless_buffer_address(" + a[0] + ", " + a[1] + ")"); break;
             case Func::BindlessTexture2dRead: need(3); value("lc_bindless_texture2d_read(" + join(a) + ")"); break;
             case Func::BindlessTexture3dRead: need(3); value("lc_bindless_texture3d_read(" + join(a) + ")"); break;
+            // filtered sampling; a texture of this device has one level, so the level / gradient operands of the other forms select nothing
+            case Func::BindlessTexture2dSample: need(3); value("lc_bindless_texture2d_sample(" + join(a) + ")"); break;
+            case Func::BindlessTexture3dSample: need(3); value("lc_bindless_texture3d_sample(" + join(a) + ")"); break;
+            case Func::BindlessTexture2dSampleLevel: case Func::BindlessTexture2dSampleGrad: case Func::BindlessTexture2dSampleGradLevel:
+                value("lc_bindless_texture2d_sample(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessTexture3dSampleLevel: case Func::BindlessTexture3dSampleGrad: case Func::BindlessTexture3dSampleGradLevel:
+                value("lc_bindless_texture3d_sample(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessTexture2dReadLevel: value("lc_bindless_texture2d_read(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessTexture3dReadLevel: value("lc_bindless_texture3d_read(" + a[0] + ", " + a[1] + ", " + a[2] + ")"); break;
+            case Func::BindlessTexture2dSizeLevel: value("lc_bindless_texture2d_size(" + a[0] + ", " + a[1] + ")"); break;
+            case Func::BindlessTexture3dSizeLevel: value("lc_bindless_texture3d_size(" + a[0] + ", " + a[1] + ")"); break;
             case Func::BindlessTexture2dSize: need(2); value("lc_bindless_texture2d_size(" + join(a) + ")"); break;
             case Func::BindlessTexture3dSize: need(2); value("lc_bindless_texture3d_size(" + join(a) + ")"); break;
 

@@ -374,7 +374,7 @@ __device__ inline void lc_assert(bool c, int id) { if (!c) lc_trap("assertion fa
 // ---- resources -------------------------------------------------------------------------------------------------------------
 // Kernel parameter records written by the host at every ShaderDispatch (shader.cu: pack_arguments).
 struct lc_buffer { uint8_t *ptr; uint64_t size; };                                     // BufferView of cpu_kernel_defs (data + byte size)
-struct lc_texture { uint8_t *data; uint32_t width, height, depth; uint32_t storage; }; // level-0 view, row-major texels
+struct lc_texture { uint8_t *data; uint32_t width, height, depth; uint32_t storage; uint32_t sampler; uint32_t pad; }; // level-0 view, row-major texels; sampler = filter | address << 2
 struct lc_bindless_slot { uint8_t *buffer; uint64_t buffer_size; lc_texture tex2d; lc_texture tex3d; };
 struct lc_bindless { const lc_bindless_slot *slots; uint64_t count; };
 struct lc_accel { lcb::AccelView view; lcb::InstanceRec *instances_rw; };
@@ -441,15 +441,58 @@ template <class V> __device__ inline void lc_texel_write(const lc_texture &t, ui
         else lc_uint_to_channel(p + k * cb, cb, (uint32_t)c[k]);
     }
 }
-template <class V> __device__ inline V lc_texture2d_read(const lc_texture &t, lc_uint2 uv) { return lc_texel_read<V>(t, (uint64_t)uv.y * t.width + uv.x); }
-template <class V> __device__ inline void lc_texture2d_write(const lc_texture &t, lc_uint2 uv, const V &v) { lc_texel_write<V>(t, (uint64_t)uv.y * t.width + uv.x, v); }
-template <class V> __device__ inline V lc_texture3d_read(const lc_texture &t, lc_uint3 p) { return lc_texel_read<V>(t, ((uint64_t)p.z * t.height + p.y) * t.width + p.x); }
-template <class V> __device__ inline void lc_texture3d_write(const lc_texture &t, lc_uint3 p, const V &v) { lc_texel_write<V>(t, ((uint64_t)p.z * t.height + p.y) * t.width + p.x, v); }
+// out-of-range coordinates read as zero and are not written (TextureView::read2d / write2d, cpu_texture.h:369-390)
+template <class V> __device__ inline V lc_texture2d_read(const lc_texture &t, lc_uint2 uv) { return uv.x < t.width && uv.y < t.height ? lc_texel_read<V>(t, (uint64_t)uv.y * t.width + uv.x) : V(); }
+template <class V> __device__ inline void lc_texture2d_write(const lc_texture &t, lc_uint2 uv, const V &v) { if (uv.x < t.width && uv.y < t.height) lc_texel_write<V>(t, (uint64_t)uv.y * t.width + uv.x, v); }
+template <class V> __device__ inline V lc_texture3d_read(const lc_texture &t, lc_uint3 p) { return p.x < t.width && p.y < t.height && p.z < t.depth ? lc_texel_read<V>(t, ((uint64_t)p.z * t.height + p.y) * t.width + p.x) : V(); }
+template <class V> __device__ inline void lc_texture3d_write(const lc_texture &t, lc_uint3 p, const V &v) { if (p.x < t.width && p.y < t.height && p.z < t.depth) lc_texel_write<V>(t, ((uint64_t)p.z * t.height + p.y) * t.width + p.x, v); }
 __device__ inline lc_uint2 lc_texture2d_size(const lc_texture &t) { return lc_uint2(t.width, t.height); }
 __device__ inline lc_uint3 lc_texture3d_size(const lc_texture &t) { return lc_uint3(t.width, t.height, t.depth); }
 __device__ inline lc_float4 lc_bindless_texture2d_read(const lc_bindless &a, uint32_t slot, lc_uint2 uv) { return lc_texture2d_read<lc_float4>(a.slots[slot].tex2d, uv); }
 __device__ inline lc_float4 lc_bindless_texture3d_read(const lc_bindless &a, uint32_t slot, lc_uint3 p) { return lc_texture3d_read<lc_float4>(a.slots[slot].tex3d, p); }
 __device__ inline lc_uint2 lc_bindless_texture2d_size(const lc_bindless &a, uint32_t slot) { return lc_texture2d_size(a.slots[slot].tex2d); }
+// Filtered sampling of bindless textures (texture_coord_point / texture_sample_point / texture_sample_linear, cpu_texture.h:417-500):
+// address modes EDGE / REPEAT / MIRROR / ZERO, filters POINT and LINEAR_* (bilinear / trilinear in the texture's one level; the
+// level / gradient arguments of the *Level / *Grad forms select nothing on a single-level texture).
+__device__ inline float lc_sample_coord(uint32_t address, float uv, float s) {
+    const float one_minus_epsilon = __uint_as_float(0x3f7fffffu);
+    switch (address) {
+        case 0: return lc_clamp(uv, 0.0f, one_minus_epsilon) * s;
+        case 1: return lc_fract(uv) * s;
+        case 2: { float m = fmodf(fabsf(uv), 2.0f); m = m < 1.0f ? m : 2.0f - m; return fminf(m, one_minus_epsilon) * s; }
+        default: return (uv < 0.0f || uv >= 1.0f) ? 65536.0f : uv * s;
+    }
+}
+__device__ inline lc_float4 lc_texture2d_sample(const lc_texture &t, lc_float2 uv) {
+    const uint32_t filter = t.sampler & 3u, address = (t.sampler >> 2) & 3u;
+    const float sx = (float)t.width, sy = (float)t.height;
+    if (filter == 0u) return lc_texture2d_read<lc_float4>(t, lc_uint2((uint32_t)lc_sample_coord(address, uv.x, sx), (uint32_t)lc_sample_coord(address, uv.y, sy)));
+    const float ax = lc_sample_coord(address, uv.x - 0.5f * (1.0f / sx), sx), bx = lc_sample_coord(address, uv.x + 0.5f * (1.0f / sx), sx);
+    const float ay = lc_sample_coord(address, uv.y - 0.5f * (1.0f / sy), sy), by = lc_sample_coord(address, uv.y + 0.5f * (1.0f / sy), sy);
+    const float x0 = fminf(ax, bx), x1 = fmaxf(ax, bx), y0 = fminf(ay, by), y1 = fmaxf(ay, by);
+    const float tx = lc_fract(x1), ty = lc_fract(y1);
+    const lc_uint2 c0((uint32_t)x0, (uint32_t)y0), c1((uint32_t)x1, (uint32_t)y1);
+    const lc_float4 v00 = lc_texture2d_read<lc_float4>(t, c0), v01 = lc_texture2d_read<lc_float4>(t, lc_uint2(c1.x, c0.y));
+    const lc_float4 v10 = lc_texture2d_read<lc_float4>(t, lc_uint2(c0.x, c1.y)), v11 = lc_texture2d_read<lc_float4>(t, c1);
+    return lc_lerp(lc_lerp(v00, v01, tx), lc_lerp(v10, v11, tx), ty);
+}
+__device__ inline lc_float4 lc_texture3d_sample(const lc_texture &t, lc_float3 uvw) {
+    const uint32_t filter = t.sampler & 3u, address = (t.sampler >> 2) & 3u;
+    const float s[3] = {(float)t.width, (float)t.height, (float)t.depth}, u[3] = {uvw.x, uvw.y, uvw.z};
+    if (filter == 0u) return lc_texture3d_read<lc_float4>(t, lc_uint3((uint32_t)lc_sample_coord(address, u[0], s[0]), (uint32_t)lc_sample_coord(address, u[1], s[1]), (uint32_t)lc_sample_coord(address, u[2], s[2])));
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        const float a = lc_sample_coord(address, u[k] - 0.5f * (1.0f / s[k]), s[k]), b = lc_sample_coord(address, u[k] + 0.5f * (1.0f / s[k]), s[k]);
+        lo[k] = fminf(a, b); hi[k] = fmaxf(a, b);
+    }
+    const float tx = lc_fract(hi[0]), ty = lc_fract(hi[1]), tz = lc_fract(hi[2]);
+    const uint32_t x0 = (uint32_t)lo[0], y0 = (uint32_t)lo[1], z0 = (uint32_t)lo[2], x1 = (uint32_t)hi[0], y1 = (uint32_t)hi[1], z1 = (uint32_t)hi[2];
+    auto rd = [&](uint32_t x, uint32_t y, uint32_t z) { return lc_texture3d_read<lc_float4>(t, lc_uint3(x, y, z)); };
+    return lc_lerp(lc_lerp(lc_lerp(rd(x0, y0, z0), rd(x1, y0, z0), tx), lc_lerp(rd(x0, y1, z0), rd(x1, y1, z0), tx), ty),
+                   lc_lerp(lc_lerp(rd(x0, y0, z1), rd(x1, y0, z1), tx), lc_lerp(rd(x0, y1, z1), rd(x1, y1, z1), tx), ty), tz);
+}
+__device__ inline lc_float4 lc_bindless_texture2d_sample(const lc_bindless &a, uint32_t slot, lc_float2 uv) { return lc_texture2d_sample(a.slots[slot].tex2d, uv); }
+__device__ inline lc_float4 lc_bindless_texture3d_sample(const lc_bindless &a, uint32_t slot, lc_float3 uvw) { return lc_texture3d_sample(a.slots[slot].tex3d, uvw); }
 __device__ inline lc_uint3 lc_bindless_texture3d_size(const lc_bindless &a, uint32_t slot) { return lc_texture3d_size(a.slots[slot].tex3d); }
 
 // ---- ray tracing (rows 5-8 of SURVEY.md §8a) ------------------------------------------------------------------------------

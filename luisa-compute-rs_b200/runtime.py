@@ -306,10 +306,16 @@ class BindlessArray:
         m.buffer = abi.BindlessBufferUpdate(abi.BINDLESS_EMPLACE, buffer.handle, offset)
         self._keep[("b", slot)] = buffer
 
-    def emplace_tex2d_async(self, slot, texture):
+    def emplace_tex2d_async(self, slot, texture, filter=0, address=0):
+        """`emplace_tex2d_async(slot, tex, Sampler{filter, address})`: filter 0 point / 1-3 linear, address 0 edge / 1 repeat / 2 mirror / 3 zero."""
         m = self._mod(slot)
-        m.tex2d = abi.BindlessTextureUpdate(abi.BINDLESS_EMPLACE, texture.handle, abi.Sampler(0, 0))
+        m.tex2d = abi.BindlessTextureUpdate(abi.BINDLESS_EMPLACE, texture.handle, abi.Sampler(filter, address))
         self._keep[("t2", slot)] = texture
+
+    def emplace_tex3d_async(self, slot, texture, filter=0, address=0):
+        m = self._mod(slot)
+        m.tex3d = abi.BindlessTextureUpdate(abi.BINDLESS_EMPLACE, texture.handle, abi.Sampler(filter, address))
+        self._keep[("t3", slot)] = texture
 
     def remove_buffer_async(self, slot):
         self._mod(slot).buffer = abi.BindlessBufferUpdate(abi.BINDLESS_REMOVE, abi.Handle(0xFFFFFFFFFFFFFFFF), 0)
