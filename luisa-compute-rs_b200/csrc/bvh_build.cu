@@ -611,14 +611,13 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
             for (int phase = 0; phase < 2; phase++) {
                 const uint32_t limit = phase == 0 ? (uint32_t)kLeafMax : 1u;
                 while (nc < 8) {
-                    float a = (sub < nc && mine.count > limit) ? half_area(mine) : -1.f;
-                    uint32_t who = sub;
-#pragma unroll
-                    for (int m = 1; m < 8; m <<= 1) {  // argmax, ties -> lowest lane
-                        const float oa = GXOR(a, m); const uint32_t ow = GXOR(who, m);
-                        if (oa > a || (oa == a && ow < who)) { a = oa; who = ow; }
-                    }
-                    if (a < 0.f) break;
+                    // argmax of the half-area over the group in ONE redux: non-negative floats order like their bit patterns; the low
+                    // three mantissa bits carry 7 - lane (ties and near-ties go to the lowest lane)
+                    const float a = (sub < nc && mine.count > limit) ? half_area(mine) : -1.f;
+                    const uint32_t akey = a >= 0.f ? (((__float_as_uint(a) & ~7u) + 8u) | (7u - sub)) : 0u;
+                    const uint32_t abest = __reduce_max_sync(gmask, akey);
+                    if (abest == 0u) break;
+                    const uint32_t who = 7u - (abest & 7u);
                     Child p, l, r;
                     p.id = GSHFL(mine.id, who);
                     split_child(bin, p, l, r);
@@ -631,9 +630,11 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
             float nhi[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                nlo[k] = mine.lo[k]; nhi[k] = mine.hi[k];  // invalid lanes hold (+max, -max)
-#pragma unroll
-                for (int m = 1; m < 8; m <<= 1) { nlo[k] = fminf(nlo[k], GXOR(nlo[k], m)); nhi[k] = fmaxf(nhi[k], GXOR(nhi[k], m)); }
+                // group min / max through the order-preserving integer image of the floats (one redux each); invalid lanes hold
+                // (+max, -max), NaN is treated the same way (fminf / fmaxf would skip it too)
+                const float vlo = mine.lo[k] == mine.lo[k] ? mine.lo[k] : FLT_MAX, vhi = mine.hi[k] == mine.hi[k] ? mine.hi[k] : -FLT_MAX;
+                nlo[k] = ordered_to_float(__reduce_min_sync(gmask, float_to_ordered(vlo)));
+                nhi[k] = ordered_to_float(__reduce_max_sync(gmask, float_to_ordered(vhi)));
                 const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
                 const uint32_t bits = __float_as_uint(sc);
                 uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
@@ -658,12 +659,13 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
                         if (cost < best) { best = cost; bs = sl; }
                     }
                 }
-                uint32_t who = (valid && my_slot == 8 && bs != 8) ? sub : 8u;
-#pragma unroll
-                for (int m = 1; m < 8; m <<= 1) {
-                    const float ob = GXOR(best, m); const uint32_t ow = GXOR(who, m), os = GXOR(bs, m);
-                    if (ow != 8u && (who == 8u || ob < best || (ob == best && ow < who))) { best = ob; who = ow; bs = os; }
-                }
+                // group argmin in ONE redux: order-preserving image of the cost with its low six bits replaced by (child, slot)
+                const uint32_t cbits = __float_as_uint(best);
+                const uint32_t cord = cbits ^ ((cbits >> 31) ? 0xffffffffu : 0x80000000u);
+                const uint32_t ckey = (valid && my_slot == 8 && bs != 8) ? ((cord & ~63u) | (sub << 3) | bs) : 0xffffffffu;
+                const uint32_t cbest = __reduce_min_sync(gmask, ckey);
+                uint32_t who = cbest == 0xffffffffu ? 8u : ((cbest >> 3) & 7u);
+                if (who != 8u) bs = cbest & 7u;
                 if (who == 8u) {  // only NaN costs left: lowest unassigned child takes the lowest free slot
                     who = __ffs(__ballot_sync(gmask, valid && my_slot == 8) >> (lane & 24u)) - 1;
                     bs = __ffs(~slot_used & 0xffu) - 1;
