@@ -1156,7 +1156,7 @@ void *lc_b200_stream_native(lcb_device, lcb_stream h) { return (void *)as<Stream
 void *lc_b200_buffer_native(lcb_device, lcb_buffer h) { return as<BufferObj>(h.id)->ptr; }
 int lc_b200_device_ordinal(lcb_device dev) { return dev_of(dev)->ordinal; }
 uint64_t lc_b200_kernel_launch_count(void) { return g_launches.load(); }
-const char *lc_b200_version(void) { return "lc_b200 0.1 (sm_100a; LBVH + 8-wide quantised BVH; canonical fp32 watertight)"; }
+const char *lc_b200_version(void) { return "lc_b200 0.2 (sm_100a; LBVH / PLOC + 8-wide quantised BVH; canonical fp32 watertight traversal; IR -> CUDA lowering via NVRTC)"; }
 
 // The CUDA source the lowering produces for a KernelModule (malloc'd; release with free_string).  No GPU needed.
 char *lc_b200_ir_lower_source(const void *kernel_module) {
