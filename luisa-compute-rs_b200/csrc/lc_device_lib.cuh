@@ -17,7 +17,7 @@ template <class T, int N> struct lc_vec;
 #define LC_VEC_ALIGN(T, N) (sizeof(T) * (N) < 16 ? sizeof(T) * (N) : 16)
 template <class T> struct alignas(LC_VEC_ALIGN(T, 2)) lc_vec<T, 2> {
     T x, y;
-    __device__ lc_vec() : x(), y() {}
+    lc_vec() = default;  // trivial: vectors may live in __shared__ arrays; T() / T{} still zero-initialise
     __device__ explicit lc_vec(T s) : x(s), y(s) {}
     __device__ lc_vec(T a, T b) : x(a), y(b) {}
     __device__ T &operator[](unsigned i) { return (&x)[i]; }
@@ -25,7 +25,7 @@ template <class T> struct alignas(LC_VEC_ALIGN(T, 2)) lc_vec<T, 2> {
 };
 template <class T> struct alignas(LC_VEC_ALIGN(T, 4)) lc_vec<T, 3> {
     T x, y, z;
-    __device__ lc_vec() : x(), y(), z() {}
+    lc_vec() = default;
     __device__ explicit lc_vec(T s) : x(s), y(s), z(s) {}
     __device__ lc_vec(T a, T b, T c) : x(a), y(b), z(c) {}
     __device__ lc_vec(lc_vec<T, 2> a, T c) : x(a.x), y(a.y), z(c) {}
@@ -35,7 +35,7 @@ template <class T> struct alignas(LC_VEC_ALIGN(T, 4)) lc_vec<T, 3> {
 };
 template <class T> struct alignas(LC_VEC_ALIGN(T, 4)) lc_vec<T, 4> {
     T x, y, z, w;
-    __device__ lc_vec() : x(), y(), z(), w() {}
+    lc_vec() = default;
     __device__ explicit lc_vec(T s) : x(s), y(s), z(s), w(s) {}
     __device__ lc_vec(T a, T b, T c, T d) : x(a), y(b), z(c), w(d) {}
     __device__ lc_vec(lc_vec<T, 3> a, T d) : x(a.x), y(a.y), z(a.z), w(d) {}
@@ -73,7 +73,7 @@ template <class T, size_t N> struct lc_array {
 
 template <int N> struct lc_mat {
     lc_vec<float, N> cols[N];
-    __device__ lc_mat() {}
+    lc_mat() = default;
     __device__ lc_vec<float, N> &operator[](unsigned i) { return cols[i]; }
     __device__ const lc_vec<float, N> &operator[](unsigned i) const { return cols[i]; }
     __device__ static lc_mat full(float s) { lc_mat m; for (int i = 0; i < N; i++) m.cols[i] = lc_vec<float, N>(s); return m; }
