@@ -155,6 +155,7 @@ struct AccelObj {
     WideNode *tlas_nodes = nullptr; uint32_t *tlas_prims = nullptr; uint32_t *active_ids = nullptr; uint32_t tlas_capacity = 0;
     uint32_t n_active = 0;
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
+    uint32_t *dirty = nullptr;  // device flag raised by kernels that edit the instance table (lc_set_instance_*)
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of modification records + active ids (grow-only; every build ends synchronised)
     lcb_build_stats stats{};
     std::mutex mu;
@@ -433,6 +434,26 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, st));
+    // Kernels may have edited the instance table (RayTracingSetInstance*): fold those edits into the host mirror first, so that this
+    // build (and its TLAS) sees them and later modifications apply on top.
+    if (a->dirty && a->table) {
+        uint32_t flag = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&flag, a->dirty, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (flag) {
+            const size_t live = std::min<size_t>(a->instances.size(), a->table_capacity);
+            std::vector<InstanceRec> recs(live);
+            CUDA_CHECK(cudaMemcpyAsync(recs.data(), a->table, live * sizeof(InstanceRec), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemsetAsync(a->dirty, 0, 4, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < live; i++) {
+                InstanceHost &in = a->instances[i];
+                if (!in.valid) continue;
+                memcpy(in.affine, recs[i].affine, sizeof(in.affine));
+                in.visible = recs[i].visibility; in.user_id = recs[i].user_id; in.opaque = (recs[i].flags & 2u) != 0;
+            }
+        }
+    }
     const uint32_t n = c.instance_count;
     a->instances.resize(n);  // grow with default (invalid) slots / pop from the back (accel.rs:345-353)
     std::vector<uint8_t> touched(n, 0);
@@ -681,6 +702,7 @@ void destroy_accel(lcb_device dev, lcb_accel h) {
     if (a->table) cudaFree(a->table);
     if (a->tlas_nodes) { cudaFree(a->tlas_nodes); cudaFree(a->tlas_prims); cudaFree(a->active_ids); }
     if (a->h_stage) cudaFreeHost(a->h_stage);
+    if (a->dirty) cudaFree(a->dirty);
     delete a;
 }
 
@@ -786,7 +808,8 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
     };
     auto put_accel = [&](const ParamSlot &p, uint64_t handle) {
         AccelObj *ao = as<AccelObj>(handle);
-        HostAccelArg a{view_of(ao), ao->table}; memcpy(block.data() + p.offset, &a, sizeof(a));
+        if (!ao->dirty) { CUDA_CHECK(cudaMalloc((void **)&ao->dirty, 256)); CUDA_CHECK(cudaMemset(ao->dirty, 0, 256)); }
+        HostAccelArg a{view_of(ao), ao->table, ao->dirty}; memcpy(block.data() + p.offset, &a, sizeof(a));
     };
     for (const ParamSlot &p : k.captures) {  // bound at create_shader time (KernelModule.captures, cpu/mod.rs:296-301)
         switch (p.kind) {

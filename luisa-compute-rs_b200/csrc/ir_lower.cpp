@@ -612,6 +612,8 @@ struct FunctionEmitter {
             case Func::RayTracingInstanceUserId: need(2); value("lc_accel_instance_user_id(" + a[0] + ", " + a[1] + ")"); break;
             case Func::RayTracingSetInstanceVisibility: need(3); line("lc_set_instance_visibility(" + join(a) + ");"); break;
             case Func::RayTracingSetInstanceUserId: need(3); line("lc_set_instance_user_id(" + join(a) + ");"); break;
+            case Func::RayTracingSetInstanceTransform: need(3); line("lc_set_instance_transform(" + join(a) + ");"); break;
+            case Func::RayTracingSetInstanceOpacity: need(3); line("lc_set_instance_opacity(" + join(a) + ");"); break;
             // row 7: RayQuery objects (cpp.rs:1401-1472).  The object is a mutable local; Instruction::RayQuery runs the traversal.
             case Func::RayTracingQueryAll: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_all(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
             case Func::RayTracingQueryAny: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;

@@ -377,7 +377,7 @@ struct lc_buffer { uint8_t *ptr; uint64_t size; };                              
 struct lc_texture { uint8_t *data; uint32_t width, height, depth; uint32_t storage; uint32_t sampler; uint32_t pad; }; // level-0 view, row-major texels; sampler = filter | address << 2
 struct lc_bindless_slot { uint8_t *buffer; uint64_t buffer_size; lc_texture tex2d; lc_texture tex3d; };
 struct lc_bindless { const lc_bindless_slot *slots; uint64_t count; };
-struct lc_accel { lcb::AccelView view; lcb::InstanceRec *instances_rw; };
+struct lc_accel { lcb::AccelView view; lcb::InstanceRec *instances_rw; uint32_t *dirty; };
 
 template <class T> __device__ inline T lc_buffer_read(const lc_buffer &b, uint64_t i) { return reinterpret_cast<const T *>(b.ptr)[i]; }
 template <class T> __device__ inline void lc_buffer_write(const lc_buffer &b, uint64_t i, const T &v) { reinterpret_cast<T *>(b.ptr)[i] = v; }
@@ -564,5 +564,31 @@ __device__ inline lc_float4x4 lc_accel_instance_transform(const lc_accel &a, uin
 }
 __device__ inline uint32_t lc_accel_instance_visibility_mask(const lc_accel &a, uint32_t i) { return a.view.instances[i].visibility; }
 __device__ inline uint32_t lc_accel_instance_user_id(const lc_accel &a, uint32_t i) { return a.view.instances[i].user_id; }
-__device__ inline void lc_set_instance_visibility(const lc_accel &a, uint32_t i, uint32_t m) { a.instances_rw[i].visibility = m; }
-__device__ inline void lc_set_instance_user_id(const lc_accel &a, uint32_t i, uint32_t id) { a.instances_rw[i].user_id = id; }
+// Setters (cpu/accel.rs:560-579, stream.rs:596-658) edit the device's instance table and raise the accel's dirty flag: the next
+// AccelBuild reads the edited slots back into the host mirror before it rebuilds the TLAS.  Visibility, opacity and user id take
+// effect for traversals at once; a new transform moves the instance's box only at that next AccelBuild, as on the CPU backend.
+__device__ inline void lc_set_instance_visibility(const lc_accel &a, uint32_t i, uint32_t m) { a.instances_rw[i].visibility = m; *a.dirty = 1u; }
+__device__ inline void lc_set_instance_user_id(const lc_accel &a, uint32_t i, uint32_t id) { a.instances_rw[i].user_id = id; *a.dirty = 1u; }
+__device__ inline void lc_set_instance_opacity(const lc_accel &a, uint32_t i, bool opaque) {
+    const uint32_t f = a.instances_rw[i].flags;
+    a.instances_rw[i].flags = opaque ? (f | 2u) : (f & ~2u);
+    *a.dirty = 1u;
+}
+__device__ inline void lc_set_instance_transform(const lc_accel &a, uint32_t i, const lc_float4x4 &m) {
+    lcb::InstanceRec &r = a.instances_rw[i];
+    float aff[12];
+    for (int row = 0; row < 3; row++) for (int col = 0; col < 4; col++) aff[4 * row + col] = m[col][row];  // column-major Mat4 -> row-major 3x4
+    for (int k = 0; k < 12; k++) r.affine[k] = aff[k];
+    // world -> object: double-precision adjugate inverse rounded once to fp32, the same formula the host uses (device.cu invert_affine)
+    const double A = aff[0], B = aff[1], Cc = aff[2], D = aff[4], E = aff[5], F = aff[6], G = aff[8], H = aff[9], I = aff[10];
+    const double tx = aff[3], ty = aff[7], tz = aff[11];
+    const double c00 = E * I - F * H, c01 = Cc * H - B * I, c02 = B * F - Cc * E;
+    const double c10 = F * G - D * I, c11 = A * I - Cc * G, c12 = Cc * D - A * F;
+    const double c20 = D * H - E * G, c21 = B * G - A * H, c22 = A * E - B * D;
+    const double rdet = 1.0 / (A * c00 + B * c10 + Cc * c20);
+    const double n00 = c00 * rdet, n01 = c01 * rdet, n02 = c02 * rdet, n10 = c10 * rdet, n11 = c11 * rdet, n12 = c12 * rdet, n20 = c20 * rdet, n21 = c21 * rdet, n22 = c22 * rdet;
+    r.inv[0] = (float)n00; r.inv[1] = (float)n01; r.inv[2] = (float)n02; r.inv[3] = (float)(-(n00 * tx + n01 * ty + n02 * tz));
+    r.inv[4] = (float)n10; r.inv[5] = (float)n11; r.inv[6] = (float)n12; r.inv[7] = (float)(-(n10 * tx + n11 * ty + n12 * tz));
+    r.inv[8] = (float)n20; r.inv[9] = (float)n21; r.inv[10] = (float)n22; r.inv[11] = (float)(-(n20 * tx + n21 * ty + n22 * tz));
+    *a.dirty = 1u;
+}

@@ -36,10 +36,10 @@ struct HostBufferArg { void *ptr; uint64_t size; };
 struct HostTextureArg { void *data; uint32_t width, height, depth; uint32_t storage; uint32_t sampler; uint32_t pad; };  // sampler = filter | address << 2 (Sampler::encode, api_types:448-452)
 struct HostBindlessSlot { void *buffer; uint64_t buffer_size; HostTextureArg tex2d, tex3d; };
 struct HostBindlessArg { const HostBindlessSlot *slots; uint64_t count; };
-struct HostAccelArg { AccelView view; InstanceRec *instances_rw; };
+struct HostAccelArg { AccelView view; InstanceRec *instances_rw; uint32_t *dirty; };  // dirty: set by kernels that edit the instance table
 struct HostLaunch { uint32_t dispatch_size[3]; uint32_t pad; };
 static_assert(sizeof(HostBufferArg) == 16 && sizeof(HostTextureArg) == 32 && sizeof(HostBindlessSlot) == 80 && sizeof(HostBindlessArg) == 16 &&
-                  sizeof(HostAccelArg) == 64 && sizeof(HostLaunch) == 16,
+                  sizeof(HostAccelArg) == 72 && sizeof(HostLaunch) == 16,
               "parameter records are mirrored byte for byte in lc_device_lib.cuh");
 
 // NVRTC + module loading (shader.cu).  compile_only: stop after NVRTC (usable without a GPU; create_shader's compile_only option).
