@@ -13,6 +13,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 
 namespace lcb {
 
@@ -88,6 +89,17 @@ ShaderObj *shader_create(const ir::KernelModule *km, bool fast_math, bool compil
             char path[512]; snprintf(path, sizeof(path), "%s/lc_kernel_%d.cu", dump, serial++);
             if (FILE *f = fopen(path, "w")) { fputs(s->lowered.source.c_str(), f); fclose(f); }
         }
+        // identical source + options -> identical cubin: kernels re-created in a process (the frontend's enable_cache) skip NVRTC
+        static std::mutex cache_mu;
+        static std::unordered_map<std::string, std::vector<char>> cache;
+        const std::string cache_key = (fast_math ? "F" : "P") + s->lowered.source;
+        bool cached = false;
+        {
+            std::lock_guard<std::mutex> lk(cache_mu);
+            auto it = cache.find(cache_key);
+            if (it != cache.end()) { s->cubin = it->second; cached = true; }
+        }
+        if (!cached) {
         const Nvrtc &rt = nvrtc();
         const size_t n_headers = sizeof(kEmbeddedHeaders) / sizeof(kEmbeddedHeaders[0]);
         std::vector<const char *> names, texts;
@@ -113,6 +125,9 @@ ShaderObj *shader_create(const ir::KernelModule *km, bool fast_math, bool compil
         s->cubin.resize(sz);
         rt.GetCUBIN(prog, s->cubin.data());
         rt.DestroyProgram(&prog);
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (cache.size() < 256) cache[cache_key] = s->cubin;
+        }
         if (!compile_only) {
             cudaError_t e = cudaLibraryLoadData(&s->library, s->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
             if (e != cudaSuccess) throw std::runtime_error(std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
