@@ -284,7 +284,7 @@ def ray_query_kernel(radius, any_hit=False):
     return k
 
 
-def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64, block=16):
+def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64, block=16, regenerate=False):
     """BASELINE config C5: the path tracer of examples/path_tracer.rs generalised to an instanced scene and to tile sharding
     (SURVEY.md §8d / §8e).  One thread per pixel of a 64x64 tile; `tiles[k]` names the global tile a rank's k-th local tile is
     (Morton round-robin, sharding.tiles_of_rank), results accumulate in a packed per-rank tile buffer that ONE all-gather
@@ -293,7 +293,12 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
     tan_half_fov), object-space vertices go through RayTracingInstanceTransform, normals face the viewer, a constant sky, one
     emissive quad `light` = (position, u, v, emission, instance index), albedo by instance.
     Args: tiles Buffer<u32>, out Buffer<Float4>, accel, params {resolution: Uint2, frame: u32, n_local_tiles: u32},
-    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s).  `block`: edge of the square thread block."""
+    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s).  `block`: edge of the square thread block.
+    `regenerate`: one loop whose iteration is ONE bounce — a lane whose path ended starts its next sample at once instead of idling
+    until the longest path of the warp's current sample is done (the nested sample / bounce loops of the example leave 3 of 4 lanes
+    idle on C2, profiles/r01u_*).  Each pixel still consumes its random stream in the same order, so the image is bit-identical either
+    way.  Off by default: on C5 paths average 1.13 rays per sample, so there is little idling to recover and the loss of ray coherence
+    inside a warp costs more (300.9 vs 284.1 ms, profiles/r01v_c5_regeneration.txt)."""
     k = ir.KernelBuilder(block_size=(block, block, 1))
     f3, ray_ty, hit_ty = common_types(k)
     index_ty = k.array(k.u32, 3)
@@ -358,19 +363,31 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
         light_normal = light_u.cross(light_v).normalize()
         aspect = res.x.cast(k.f32) / res.y.cast(k.f32)
 
-        def sample_body():
+        ray = k.local_zero(ray_ty)
+        beta = k.local_zero(k.f323)
+        pdf_bsdf = k.local_zero(k.f32)
+        depth = k.local_zero(k.u32)
+        alive = k.local(k.b(False))
+
+        def end_path():
+            if regenerate:
+                alive.store(k.b(False))
+                k.continue_()
+            else:
+                k.break_()
+
+        def start_path():
             jx, jy = lcg(state), lcg(state)
             sx = ((px.cast(k.f32) + jx) / res.x.cast(k.f32) * 2.0 - 1.0) * k.f(tan_half) * aspect
             sy = (k.f(1.0) - (py.cast(k.f32) + jy) / res.y.cast(k.f32) * 2.0) * k.f(tan_half)
             origin = k.vec(k.f323, *cam_o)
             direction = (k.vec(k.f323, *cam_f) + sx * k.vec(k.f323, *cam_r) + sy * k.vec(k.f323, *cam_u)).normalize()
-            ray = k.local_zero(ray_ty)
             ray.store(make_ray(k, ray_ty, f3, origin, direction, 1e-4, F32_MAX))
-            beta = k.local_zero(k.f323)
             beta.store(k.vec(k.f323, 1.0, 1.0, 1.0))
-            pdf_bsdf = k.local_zero(k.f32)
-            depth = k.local_zero(k.u32)
+            pdf_bsdf.store(k.f(0.0))
+            depth.store(k.u(0))
 
+        if True:
             def bounce():
                 hit = accel.trace_closest(ray.load(), 0xFF, hit_ty)
                 n_closest.store(n_closest.load() + k.u(1))
@@ -378,7 +395,7 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
 
                 def missed():
                     radiance.store(radiance.load() + beta.load() * sky)
-                    k.break_()
+                    end_path()
                 k.if_(inst.eq(0xFFFFFFFF), missed)
                 tri = index_heap.bindless_buffer_read(inst, prim, index_ty)
                 xf = k.call(Func.RayTracingInstanceTransform, [accel, inst], k.matrix(4))
@@ -393,7 +410,7 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
                 direction_w = _to_float3(k, ray.gep(2).load())
                 n = direction_w.dot(ng).gt(0.0).select(-ng, ng)
                 cos_wi = -direction_w.dot(n)
-                k.if_(cos_wi.lt(1e-4), lambda: k.break_())
+                k.if_(cos_wi.lt(1e-4), end_path)
                 pp = offset_ray_origin(k, pnt, n)
                 albedo = materials.extract(inst)
 
@@ -406,7 +423,7 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
                         mis_weight = pdf_bsdf.load() / k.max(pdf_bsdf.load() + pdf_light, k.f(1e-4))
                         radiance.store(radiance.load() + mis_weight * beta.load() * light_emission)
                     k.if_(depth.load().eq(0), first, later)
-                    k.break_()
+                    end_path()
 
                 def sample_light():
                     p_light = light_position + lcg(state) * light_u + lcg(state) * light_v
@@ -438,13 +455,28 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
                 beta.store(beta.load() * albedo)
                 pdf_bsdf.store(cos_wi * k.f(FRAC_1_PI))
                 lum = k.vec(k.f323, 0.212671, 0.715160, 0.072169).dot(beta.load())
-                k.if_(lum.eq(0.0), lambda: k.break_())
+                k.if_(lum.eq(0.0), end_path)
                 q = k.max(lum, k.f(0.05))
-                k.if_(lcg(state).gt(q), lambda: k.break_())
+                k.if_(lcg(state).gt(q), end_path)
                 beta.store(beta.load() / q)
                 depth.store(depth.load() + k.u(1))
-            k.generic_loop(lambda: depth.load().lt(max_depth), bounce)
-        k.generic_loop(lambda: sample.load().lt(spp_per_dispatch), sample_body, lambda: sample.store(sample.load() + k.u(1)))
+                if regenerate:
+                    k.if_(depth.load().ge(max_depth), lambda: alive.store(k.b(False)))
+
+        if regenerate:
+            def iteration():
+                def begin():
+                    start_path()
+                    sample.store(sample.load() + k.u(1))
+                    alive.store(k.b(True))
+                k.if_(alive.load().not_(), begin)
+                bounce()
+            k.generic_loop(lambda: sample.load().lt(spp_per_dispatch) | alive.load(), iteration)
+        else:
+            def sample_body():
+                start_path()
+                k.generic_loop(lambda: depth.load().lt(max_depth), bounce)
+            k.generic_loop(lambda: sample.load().lt(spp_per_dispatch), sample_body, lambda: sample.store(sample.load() + k.u(1)))
         rad = radiance.load() / k.f(float(spp_per_dispatch))
         rad = rad.is_nan().any().select(k.vec(k.f323, 0.0, 0.0, 0.0), rad).clamp(k.vec(k.f323, k.f(0.0)), k.vec(k.f323, k.f(30.0)))
         old = out.read(slot)

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--streams", type=int, default=2, help="the rank's tiles are split over this many streams so that the tail of one dispatch overlaps the next")
     ap.add_argument("--chunk", type=int, default=1, help="tiles per round-robin run along the Morton curve (sharding.tiles_of_rank)")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's tiles in this single process (tuning aid; no gather)")
+    ap.add_argument("--regenerate", action="store_true", help="path regeneration instead of the example's nested sample / bounce loops (same image; measured slower, profiles/r01v)")
     ap.add_argument("--save", default="")
     a = ap.parse_args()
     import torch
@@ -81,7 +82,7 @@ def main():
     u = np.cross(r, f)
     camera = (tuple(map(float, cam_o)), tuple(map(float, f)), tuple(map(float, r)), tuple(map(float, u)), float(np.tan(np.radians(45.0) / 2)))
     light = (l_pos, l_u, l_v, (60.0, 54.0, 45.0), 10)
-    kb = examples_ir.tiled_path_tracer_kernel(vheap.handle.id, iheap.handle.id, camera, light, n_inst, a.spp_per_dispatch, a.depth, block=a.block)
+    kb = examples_ir.tiled_path_tracer_kernel(vheap.handle.id, iheap.handle.id, camera, light, n_inst, a.spp_per_dispatch, a.depth, block=a.block, regenerate=a.regenerate)
     shader = dev.create_shader(C.addressof(kb.km), keep=kb)
 
     # ---- this rank's tiles ----------------------------------------------------------------------------------------------
