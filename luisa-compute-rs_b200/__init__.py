@@ -7,9 +7,9 @@ top-level shim `luisa_compute_rs_b200`.
 from . import _abi
 from . import ir
 from .runtime import BindlessArray, Buffer, BufferView, Context, Device, Event, LuisaError, Shader, Stream, Texture
-from .rtx import (Accel, AccelBuildRequest, AccelOption, AccelUsageHint, CommittedHit, HitType, Index, Mesh, ProceduralPrimitive, Ray, SurfaceCandidateFilter, SurfaceHit, INVALID,
+from .rtx import (Accel, AccelBuildRequest, AccelOption, AccelUsageHint, CommittedHit, Curve, CurveBasis, HitType, Index, Mesh, ProceduralPrimitive, Ray, SurfaceCandidateFilter, SurfaceHit, INVALID,
                   affine_from_mat4, hit_valid, make_rays, offset_ray_origin)
 
 __all__ = ["Accel", "AccelBuildRequest", "AccelOption", "AccelUsageHint", "CommittedHit", "HitType", "SurfaceCandidateFilter", "Buffer", "BufferView", "Context", "Device", "Event",
            "Index", "INVALID", "LuisaError", "Mesh", "Ray", "Stream", "SurfaceHit", "affine_from_mat4", "hit_valid", "make_rays",
-           "offset_ray_origin", "_abi", "ir", "ProceduralPrimitive", "BindlessArray", "Shader", "Texture"]
+           "offset_ray_origin", "_abi", "ir", "ProceduralPrimitive", "Curve", "CurveBasis", "BindlessArray", "Shader", "Texture"]

@@ -73,6 +73,12 @@ class CmdProceduralBuild(C.Structure):
     _fields_ = [("handle", Handle), ("request", C.c_int32), ("aabb_buffer", Handle), ("aabb_offset", C.c_size_t), ("aabb_count", C.c_size_t)]
 
 
+class CmdCurveBuild(C.Structure):
+    """CurveBuildCommand (api_types:618-631); basis = CurveBasis (api_types:196-202)"""
+    _fields_ = [("curve", Handle), ("request", C.c_int32), ("basis", C.c_int32), ("cp_count", C.c_size_t), ("seg_count", C.c_size_t),
+                ("cp_buffer", Handle), ("cp_offset", C.c_size_t), ("cp_stride", C.c_size_t), ("seg_buffer", Handle), ("seg_offset", C.c_size_t)]
+
+
 class CmdAccelBuild(C.Structure):
     _fields_ = [("accel", Handle), ("request", C.c_int32), ("instance_count", C.c_uint32),
                 ("modifications", C.POINTER(AccelModification)), ("modifications_count", C.c_size_t),
@@ -155,7 +161,7 @@ class _CmdUnion(C.Union):
     _fields_ = [("buffer_upload", CmdBufferUpload), ("buffer_download", CmdBufferDownload), ("buffer_copy", CmdBufferCopy),
                 ("buffer_to_texture", CmdBufferTexture), ("texture_to_buffer", CmdBufferTexture), ("texture_upload", CmdTextureTransfer),
                 ("texture_download", CmdTextureTransfer), ("texture_copy", CmdTextureCopy), ("shader_dispatch", CmdShaderDispatch),
-                ("bindless_update", CmdBindlessUpdate), ("procedural_build", CmdProceduralBuild),
+                ("bindless_update", CmdBindlessUpdate), ("procedural_build", CmdProceduralBuild), ("curve_build", CmdCurveBuild),
                 ("mesh_build", CmdMeshBuild), ("accel_build", CmdAccelBuild), ("_raw", C.c_uint8 * 80)]
 
 

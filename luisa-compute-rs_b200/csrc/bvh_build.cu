@@ -6,6 +6,7 @@
 // Replaces what the reference delegates to rtcCommitScene (cpu/accel.rs:258,439) /
 // optixAccelBuild (cuda_primitive.cpp:57-60).  No reference source exists for any of it.
 #include "build.cuh"
+#include "trace_device.cuh"
 #include <cfloat>
 #include <cstdlib>
 
@@ -136,6 +137,49 @@ __global__ void __launch_bounds__(256) k_pack_aabbs(const uint8_t *__restrict__ 
     o[0] = make_float4(fminf(a[0], a[3]), fminf(a[1], a[4]), fminf(a[2], a[5]), __uint_as_float(prim));
     o[1] = make_float4(fmaxf(a[0], a[3]), fmaxf(a[1], a[4]), fmaxf(a[2], a[5]), 0.f);
     o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Curve pieces (CurveBuild): box of the two end spheres, rounded outward.
+__global__ void __launch_bounds__(256) k_curve_boxes(CurveInput in, uint32_t n, PrimBox *boxes, BuildHeader *h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cen[3] = {0, 0, 0};
+    float area = 0.f;
+    bool valid = i < n;
+    if (valid) {
+        float4 A, B;
+        curve_piece(in.cps, in.cp_stride, in.segs, in.basis, i / in.pieces, i % in.pieces, A, B);
+        const float ra = fabsf(A.w), rb = fabsf(B.w);
+        const float pa[3] = {A.x, A.y, A.z}, pb[3] = {B.x, B.y, B.z};
+        float lo[3], hi[3];
+#pragma unroll
+        // the canonical cone test decides in fp32: pad by a fraction of the radius and of the piece's extent so that a ray it
+        // accepts never misses the box
+        const float pad = fmaxf(ra, rb) * (1.0f / 256.0f) + fmaxf(fmaxf(fabsf(pb[0] - pa[0]), fabsf(pb[1] - pa[1])), fabsf(pb[2] - pa[2])) * (1.0f / 4096.0f);
+        for (int k = 0; k < 3; k++) {
+            lo[k] = __fsub_rd(fminf(__fsub_rd(pa[k], ra), __fsub_rd(pb[k], rb)), pad);
+            hi[k] = __fadd_ru(fmaxf(__fadd_ru(pa[k], ra), __fadd_ru(pb[k], rb)), pad);
+            cen[k] = 0.5f * lo[k] + 0.5f * hi[k];
+        }
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        area = dx * dy + dy * dz + dz * dx;
+    }
+    reduce_centroid_bounds(cen, valid, h, area);
+}
+
+// leaf records of a curve BLAS: the piece's two spheres, its segment and its parameter range (CurveSeg)
+__global__ void __launch_bounds__(256) k_pack_curves(CurveInput in, PackedTri *slots, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = slots[i].prim, seg = j / in.pieces, k = j % in.pieces;
+    float4 A, B;
+    curve_piece(in.cps, in.cp_stride, in.segs, in.basis, seg, k, A, B);
+    const float du = 1.0f / (float)in.pieces;
+    float4 *o = reinterpret_cast<float4 *>(&slots[i]);
+    o[0] = make_float4(A.x, A.y, A.z, __uint_as_float(seg));
+    o[1] = make_float4(B.x, B.y, B.z, A.w);
+    o[2] = make_float4(B.w, (float)k * du, du, 0.f);
 }
 
 // World-space box of an instance: union of the BLAS root's (conservatively decoded) child
@@ -916,6 +960,15 @@ void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const Bu
     LeafSinkTriangles sink{slots};
     run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);
     k_pack_aabbs<<<(n + 255) / 256, 256, 0, s>>>(aabbs, slots, n); lc.count++;
+}
+
+void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc) {
+    uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_curve_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
+    LeafSinkTriangles sink{slots};
+    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);
+    k_pack_curves<<<(n + 255) / 256, 256, 0, s>>>(in, slots, n); lc.count++;
 }
 
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,

@@ -131,6 +131,7 @@ struct MeshObj {
     bool built = false;
     int auto_builder = -1; uint32_t auto_builder_n = 0;  // what the per-mesh builder choice picked last time, and for how many triangles
     bool procedural = false;  // created by create_procedural_primitive: leaves are user AABBs, hits come from the RayQuery callback
+    bool curve = false;       // created by create_curve: leaves are the rounded-cone pieces of the segments (trace_device.cuh "curves")
     uint32_t n_tris = 0;
     uint64_t generation = 0;  // bumped whenever nodes/tris are re-allocated
     WideNode *nodes = nullptr; PackedTri *tris = nullptr;
@@ -291,11 +292,11 @@ void free_stream(StreamObj *s) {
 void destroy_stream(lcb_device dev, lcb_stream h) { DeviceObj *d = dev_of(dev); bind(d); free_stream(as<StreamObj>(h.id)); }
 
 // ---- mesh build (GeometryImpl::build_mesh, cpu/accel.rs:205-260) ---------------------------------
-void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs);
+void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs, const CurveInput *curve = nullptr);
 
 void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     MeshObj *m = as<MeshObj>(c.mesh.id);
-    if (m->procedural) fatal("MeshBuild on a procedural primitive handle");
+    if (m->procedural || m->curve) fatal("MeshBuild on a %s handle", m->curve ? "curve" : "procedural primitive");
     std::lock_guard<std::mutex> lk(m->mu);
     if (c.index_stride != 12) fatal("Index stride must be 12 (got %zu).", c.index_stride);  // api/runtime.cpp:191-193
     if (c.vertex_stride < 12) fatal("vertex stride must be >= 12 (got %zu)", c.vertex_stride);
@@ -317,7 +318,34 @@ void procedural_build(DeviceObj *d, StreamObj *s, const lcb_cmd_procedural_build
     blas_build(d, s, m, (uint32_t)c.aabb_count, LCB_REQUEST_FORCE_BUILD, TriangleInput{nullptr, 0, nullptr}, ab->ptr + c.aabb_offset);
 }
 
-void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs) {
+// CurveBuild (GeometryImpl::build_curve, cpu/accel.rs:142-203): control points are read as float4 {x, y, z, radius} at cp_stride
+// (>= 16, asserted there), segments are u32 first-control-point indices.  The reference refits on PreferUpdate (rtcUpdateGeometryBuffer);
+// a curve BLAS is small next to a mesh, so every CurveBuild here is a full build — same result.
+void curve_build(DeviceObj *d, StreamObj *s, const lcb_cmd_curve_build &c) {
+    MeshObj *m = as<MeshObj>(c.curve.id);
+    if (!m->curve) fatal("CurveBuild on a handle that is not a curve");
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (c.basis < 0 || c.basis > 3) fatal("CurveBuild: unknown basis %d", c.basis);
+    if (c.cp_stride < 16) fatal("cp buffer stride must be >= 16 (got %zu)", c.cp_stride);  // cpu/accel.rs:159
+    if (c.cp_stride % 16 != 0) fatal("CurveBuild: cp buffer stride must be a multiple of 16 (got %zu)", c.cp_stride);
+    BufferObj *cb = as<BufferObj>(c.cp_buffer.id), *sb = as<BufferObj>(c.seg_buffer.id);
+    if (c.cp_offset % 16 != 0) fatal("CurveBuild: cp buffer offset must be a multiple of 16");
+    if (c.cp_count && c.cp_offset + (c.cp_count - 1) * c.cp_stride + 16 > cb->size) fatal("CurveBuild: control point range exceeds buffer");
+    if (c.seg_offset % 4 != 0 || c.seg_offset + c.seg_count * 4 > sb->size) fatal("CurveBuild: segment range exceeds buffer");
+    const uint32_t pieces = c.basis == 0 ? 1u : kCurveSubdiv, per_seg = c.basis == 0 ? 2u : 4u;
+    if (c.seg_count * pieces > 0x7fffffffull) fatal("CurveBuild: too many segments");
+    if (c.seg_count) {  // every segment must stay inside the control points (Embree reads them unchecked)
+        std::vector<uint32_t> segs(c.seg_count);
+        CUDA_CHECK(cudaMemcpyAsync(segs.data(), sb->ptr + c.seg_offset, c.seg_count * 4, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        for (size_t i = 0; i < c.seg_count; i++)
+            if ((size_t)segs[i] + per_seg > c.cp_count) fatal("CurveBuild: segment %zu starts at control point %u of %zu", i, segs[i], c.cp_count);
+    }
+    CurveInput in{cb->ptr + c.cp_offset, c.cp_stride, reinterpret_cast<const uint32_t *>(sb->ptr + c.seg_offset), (uint32_t)c.basis, pieces};
+    blas_build(d, s, m, (uint32_t)(c.seg_count * pieces), LCB_REQUEST_FORCE_BUILD, TriangleInput{nullptr, 0, nullptr}, nullptr, &in);
+}
+
+void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs, const CurveInput *curve) {
     struct { int32_t request; } c{request};
     cudaStream_t st = s->stream;
     cudaEvent_t e0, e1;
@@ -384,7 +412,8 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
     const bool was_auto = builder == kBuilderAuto;
     if (was_auto && m->auto_builder >= 0 && m->auto_builder_n == n) builder = m->auto_builder;
     int built_with = kBuilderLbvh;
-    if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
+    if (curve) build_curves(st, n, *curve, sc, target, m->tris, d->lc);
+    else if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
     else built_with = build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
     if (was_auto) { m->auto_builder = built_with; m->auto_builder_n = n; }
     BuildHeader hdr;
@@ -497,7 +526,7 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         if (!touched[i]) continue;
         InstanceModRec r{};
         r.index = i; r.visibility = in.visible; r.user_id = in.user_id;
-        r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u) | (in.valid && in.mesh->procedural ? 4u : 0u);
+        r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u) | (in.valid && in.mesh->procedural ? 4u : 0u) | (in.valid && in.mesh->curve ? 8u : 0u);
         memcpy(r.affine, in.affine, sizeof(r.affine));
         invert_affine(in.affine, r.inv);
         if (in.valid) { r.nodes = in.mesh->nodes; r.tris = in.mesh->tris; in.mesh_generation = in.mesh->generation; }
@@ -568,6 +597,7 @@ AccelView view_of(AccelObj *a) {
     v.tlas_nodes = a->n_active ? a->tlas_nodes : nullptr;
     v.tlas_prims = a->tlas_prims; v.instances = a->table; v.instance_count = (uint32_t)a->instances.size();
     for (int k = 0; k < 3; k++) { v.world_lo[k] = a->world_lo[k]; v.world_hi[k] = a->world_hi[k]; }
+    for (const InstanceHost &in : a->instances) if (in.valid && in.mesh->curve) { v.flags |= 1u; break; }
     return v;
 }
 
@@ -637,9 +667,10 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
             case LCB_CMD_BINDLESS_UPDATE: bindless_update(s, c.u.bindless_update); break;
             case LCB_CMD_MESH_BUILD: mesh_build(d, s, c.u.mesh_build); break;
             case LCB_CMD_PROCEDURAL_BUILD: procedural_build(d, s, c.u.procedural_build); break;
+            case LCB_CMD_CURVE_BUILD: curve_build(d, s, c.u.curve_build); break;
             case LCB_CMD_ACCEL_BUILD: accel_build(d, s, c.u.accel_build); break;
             default:
-                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8f: curves are a \"next\" row)", c.tag);
+                fatal("command tag %d is outside the B200 ray-tracing device's scope (SURVEY.md §8)", c.tag);
         }
     }
     flush_launches(d);
@@ -845,8 +876,12 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
 lcb_created_swapchain create_swapchain(lcb_device, const lcb_swapchain_option *, lcb_stream) { UNSUPPORTED("create_swapchain"); }
 void present_display_in_stream(lcb_device, lcb_stream, lcb_swapchain, lcb_texture) { UNSUPPORTED("present_display_in_stream"); }
 void destroy_swapchain(lcb_device, lcb_swapchain) { UNSUPPORTED("destroy_swapchain"); }
-lcb_created create_curve(lcb_device, const lcb_accel_option *) { UNSUPPORTED("create_curve"); }
-void destroy_curve(lcb_device, lcb_curve) { UNSUPPORTED("destroy_curve"); }
+lcb_created create_curve(lcb_device dev, const lcb_accel_option *opt) {
+    lcb_created c = create_mesh(dev, opt);
+    as<MeshObj>(c.handle)->curve = true;
+    return c;
+}
+void destroy_curve(lcb_device dev, lcb_curve h) { destroy_mesh(dev, lcb_mesh{h.id}); }
 lcb_created create_procedural_primitive(lcb_device dev, const lcb_accel_option *opt) {
     bind(dev_of(dev));
     auto *m = new MeshObj; if (opt) m->option = *opt;

@@ -221,6 +221,7 @@ struct Globals {
     std::unordered_map<NodeRef, std::string> resources;  // kernel captures + arguments -> expression valid in every function
     std::unordered_map<const void *, std::string> callables;
     std::string callable_defs;
+    uint32_t curve_bases = 0;  // Module.curve_basis_set of the kernel and of every callable it reaches
     std::string shared_decls;
 };
 
@@ -775,6 +776,7 @@ struct FunctionEmitter {
 
 std::string FunctionEmitter::callable_name(const Arc<CallableModule> &arc) {
     const CallableModule *cm = arc.get();
+    g.curve_bases |= cm->module.curve_basis_set;
     if (!cm) fail("null callable");
     auto it = g.callables.find(arc.inner);
     if (it != g.callables.end()) return it->second;
@@ -878,7 +880,10 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
     fe.emit_block_content(km->module.entry.ptr);
 
     std::ostringstream src;
-    src << "// generated by lc_b200 (ir_lower.cpp) — do not edit\n#include \"lc_device_lib.cuh\"\n\n"
+    // traversal with curve support only where the frontend recorded a curve basis for some trace call (AccelTraceOptions::curve_bases,
+    // lc/src/rtx.rs:780-806) — what the OptiX backend keys its curve modules on; curve instances are skipped otherwise
+    g.curve_bases |= km->module.curve_basis_set;
+    src << "// generated by lc_b200 (ir_lower.cpp) — do not edit\n" << (g.curve_bases ? "#define LCB_CURVES 1\n" : "") << "#include \"lc_device_lib.cuh\"\n\n"
         << g.types.defs << "\n" << params.str() << asserts.str()
         << "static_assert(sizeof(lc_params) == " << align_up(off, max_align) << ", \"parameter block size\");\n\n"
         << g.callable_defs

@@ -60,7 +60,7 @@ struct alignas(16) InstanceRec {
     const PackedTri *tris;    // BLAS packed triangles
     uint32_t visibility;
     uint32_t user_id;
-    uint32_t flags;           // bit0 valid, bit1 opaque
+    uint32_t flags;           // bit0 valid, bit1 opaque, bit2 procedural primitive, bit3 curve
     uint32_t pad;
     float affine[12];         // object -> world as given by the frontend (for instance_transform)
 };
@@ -106,8 +106,11 @@ struct AccelView {
     const InstanceRec *instances;
     uint32_t instance_count;
     float world_lo[3], world_hi[3];  // bounds of the TLAS root (ray reordering quantises origins against them)
+    uint32_t flags;                  // bit 0: some instance is a curve (the batch entry points then take the per-thread kernel)
 };
+static_assert(sizeof(AccelView) == 56, "AccelView is mirrored in lc_accel / HostAccelArg");
 
+constexpr uint32_t kCurveSubdiv = 8;  // pieces per cubic curve segment (trace_device.cuh "curves")
 constexpr int kMaxWideDepth = 40;   // builder fails loudly beyond this; traversal stack is sized for it
 constexpr int kTraversalStack = 96; // >= TLAS depth + 3 + BLAS depth
 

@@ -259,6 +259,31 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
     }
 }
 
+// Accels that hold curve instances: one ray per thread through trace_one_impl<…, CURVES = true> (the persistent kernel above keeps
+// its register budget for triangles).  Same records as k_trace + k_refine write.
+struct FilterHook {
+    CandidateFilter f;
+    __device__ __forceinline__ int triangle(uint32_t inst, uint32_t prim, float u, float v, float) const { return candidate_commits(f, inst, prim, u, v) ? 1 : 0; }
+    __device__ __forceinline__ int procedural(uint32_t, uint32_t, float, float &) const { return 0; }
+};
+template <int MODE>
+__global__ void __launch_bounds__(128) k_trace_curves(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out, unsigned long long count, uint32_t mask,
+                                                      CandidateFilter filter) {
+    constexpr bool ANY = MODE == kAny;
+    constexpr bool QUERY = MODE == kQueryAll || MODE == kQueryAny;
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
+    FilterHook hook{filter};
+    const DeviceHit h = trace_one_impl<ANY, QUERY, FilterHook, true>(acc, ra, rb, mask, MODE == kQueryAny, hook);
+    if (ANY) { reinterpret_cast<uint32_t *>(out)[i] = h.inst != kNone ? 1u : 0u; return; }
+    uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * i;
+    o[0] = make_uint2(h.inst, h.prim);
+    o[1] = make_uint2(__float_as_uint(h.u), __float_as_uint(h.v));
+    if (QUERY) o[2] = h.inst != kNone ? make_uint2(1u, __float_as_uint(h.t)) : make_uint2(0u, 0u);
+    else o[2] = make_uint2(__float_as_uint(h.t), 0u);
+}
+
 // Second pass of closest-hit queries: barycentrics of every hit, one thread per ray, fully converged.  The f64
 // evaluation is the reported value (oracle.c refine_bary); if its determinant vanishes the canonical fp32 ones stand.
 // COMMITTED selects the record layout: SurfaceHit {inst, prim, u, v, t, pad} or CommittedHit {inst, prim, u, v, hit_type, t}.
@@ -362,6 +387,12 @@ template <int MODE, bool COUNTERS>
 void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uint64_t count, uint32_t mask, unsigned long long *work_counter,
             TraceCounters *ctr, LaunchCounter &lc, const CandidateFilter &filter = CandidateFilter{0, 0.f, nullptr, nullptr}) {
     constexpr bool ANY = MODE == kAny;
+    if (a.flags & 1u) {  // curve instances present
+        if (count == 0) return;
+        k_trace_curves<MODE><<<(unsigned)((count + 127) / 128), 128, 0, s>>>(a, reinterpret_cast<const float4 *>(rays), out, count, mask, filter);
+        lc.count++;
+        return;
+    }
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
         int dev = 0; cudaGetDevice(&dev);

@@ -203,6 +203,116 @@ __device__ __forceinline__ bool refine_bary(const RaySetup &r, const float4 v0, 
     return true;
 }
 
+// ---- curves (CurveBuild, api_types:620-631; GeometryImpl::build_curve, cpu/accel.rs:142-203) -------------------------------
+// Control points are float4 (x, y, z, radius); segment i starts at control point seg[i] and uses 2 (PiecewiseLinear) or 4 of them.
+// The surface is the sweep of a sphere of radius r(u) along c(u) — the union of those spheres.  A segment is put into the power
+// basis with the frontend's own matrices (CubicCurve::{bspline, catmull_rom, bezier}, lc/src/rtx/curve.rs:88-139, so `u` means what
+// CurveEvaluator expects), cubic segments are cut at u = k/8 into kCurveSubdiv pieces, and every piece is a rounded cone between
+// the spheres at its ends — one BLAS leaf (CurveSeg below, in the PackedTri slot) with its own box.  The reference's round curves
+// (Embree RTC_GEOMETRY_TYPE_ROUND_*_CURVE) are intersected iteratively to a tolerance instead; parity unpinned, as for triangles.
+// A hit reports prim = segment index, bary = (u, -1) (cpu/accel.rs:491-494) and the entry t.  oracle.c: curve_basis / canon_cone.
+constexpr uint32_t kCurveLinear = 0, kCurveBSpline = 1, kCurveCatmullRom = 2, kCurveBezier = 3;  // CurveBasis, api_types:196-202
+
+struct alignas(64) CurveSeg {   // one piece, in the 64-byte PackedTri slot
+    float pa[3]; uint32_t prim;  // sphere at the piece's start; prim = segment index
+    float pb[3]; float ra;       // sphere at its end; radius at the start
+    float rb, u0, du; uint32_t pad;
+    uint32_t spare[4];
+};
+static_assert(sizeof(CurveSeg) == 64, "CurveSeg shares the PackedTri slot");
+
+__device__ __forceinline__ float4 curve_lin4(const float m0, const float m1, const float m2, const float m3, const float div,
+                                             const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
+#define LCB_L4(C) __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0, q0.C), __fmul_rn(m1, q1.C)), __fmul_rn(m2, q2.C)), __fmul_rn(m3, q3.C)), div)
+    return make_float4(LCB_L4(x), LCB_L4(y), LCB_L4(z), LCB_L4(w));
+#undef LCB_L4
+}
+// power basis c(u) = ((a[0] u + a[1]) u + a[2]) u + a[3]
+__device__ __forceinline__ void curve_power_basis(uint32_t basis, const float4 q0, const float4 q1, const float4 q2, const float4 q3, float4 a[4]) {
+    if (basis == kCurveBSpline) {
+        a[0] = curve_lin4(-1.f, 3.f, -3.f, 1.f, 6.f, q0, q1, q2, q3); a[1] = curve_lin4(3.f, -6.f, 3.f, 0.f, 6.f, q0, q1, q2, q3);
+        a[2] = curve_lin4(-3.f, 0.f, 3.f, 0.f, 6.f, q0, q1, q2, q3);  a[3] = curve_lin4(1.f, 4.f, 1.f, 0.f, 6.f, q0, q1, q2, q3);
+    } else if (basis == kCurveCatmullRom) {
+        a[0] = curve_lin4(-1.f, 3.f, -3.f, 1.f, 2.f, q0, q1, q2, q3); a[1] = curve_lin4(2.f, -5.f, 4.f, -1.f, 2.f, q0, q1, q2, q3);
+        a[2] = curve_lin4(-1.f, 0.f, 1.f, 0.f, 2.f, q0, q1, q2, q3);  a[3] = curve_lin4(0.f, 2.f, 0.f, 0.f, 2.f, q0, q1, q2, q3);
+    } else {
+        a[0] = curve_lin4(-1.f, 3.f, -3.f, 1.f, 1.f, q0, q1, q2, q3); a[1] = curve_lin4(3.f, -6.f, 3.f, 0.f, 1.f, q0, q1, q2, q3);
+        a[2] = curve_lin4(-3.f, 3.f, 0.f, 0.f, 1.f, q0, q1, q2, q3);  a[3] = curve_lin4(1.f, 0.f, 0.f, 0.f, 1.f, q0, q1, q2, q3);
+    }
+}
+__device__ __forceinline__ float4 curve_point(const float4 a[4], float u) {
+#define LCB_H(C) __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(a[0].C, u), a[1].C), u), a[2].C), u), a[3].C)
+    return make_float4(LCB_H(x), LCB_H(y), LCB_H(z), LCB_H(w));
+#undef LCB_H
+}
+// the two end spheres (xyz, radius) of piece k of segment `seg`
+__device__ __forceinline__ void curve_piece(const uint8_t *cps, size_t cp_stride, const uint32_t *segs, uint32_t basis, uint32_t seg, uint32_t k,
+                                            float4 &A, float4 &B) {
+    const uint32_t first = segs[seg];
+    const float4 q0 = *reinterpret_cast<const float4 *>(cps + (size_t)first * cp_stride);
+    const float4 q1 = *reinterpret_cast<const float4 *>(cps + (size_t)(first + 1) * cp_stride);
+    if (basis == kCurveLinear) { A = q0; B = q1; return; }
+    const float4 q2 = *reinterpret_cast<const float4 *>(cps + (size_t)(first + 2) * cp_stride);
+    const float4 q3 = *reinterpret_cast<const float4 *>(cps + (size_t)(first + 3) * cp_stride);
+    float4 a[4];
+    curve_power_basis(basis, q0, q1, q2, q3, a);
+    A = curve_point(a, (float)k * (1.0f / kCurveSubdiv));
+    B = curve_point(a, (float)(k + 1) * (1.0f / kCurveSubdiv));
+}
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, __fmul_rn(az, bz)));
+}
+// Canonical ray / rounded cone: the smallest t in (tmin, tmax] among the roots of the lateral surface that lie between the two
+// tangent circles and the entries into the two end spheres (after I. Quilez' rounded-cone intersector, extended to unnormalised
+// directions and both lateral roots).  The quadratics are formed about the point of the ray nearest to sphere A, so that their
+// cancellation error scales with the piece and not with the distance the ray has travelled.  s = axis parameter of the sphere of
+// the sweep that the hit point lies on.
+__device__ __forceinline__ bool canonical_cone(const RaySetup &r, float tmin, float tmax, const float4 A, const float4 B, float &t_out, float &s_out) {
+    const float ra = A.w, rb = B.w;
+    const float dd = dot3_rn(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    const float t0 = __fdiv_rn(dot3_rn(__fsub_rn(A.x, r.ox), __fsub_rn(A.y, r.oy), __fsub_rn(A.z, r.oz), r.dx, r.dy, r.dz), dd);
+    const float ox = __fmaf_rn(t0, r.dx, r.ox), oy = __fmaf_rn(t0, r.dy, r.oy), oz = __fmaf_rn(t0, r.dz, r.oz);
+    const float bax = __fsub_rn(B.x, A.x), bay = __fsub_rn(B.y, A.y), baz = __fsub_rn(B.z, A.z);
+    const float oax = __fsub_rn(ox, A.x), oay = __fsub_rn(oy, A.y), oaz = __fsub_rn(oz, A.z);
+    const float obx = __fsub_rn(ox, B.x), oby = __fsub_rn(oy, B.y), obz = __fsub_rn(oz, B.z);
+    const float rr = __fsub_rn(ra, rb);
+    const float m0 = dot3_rn(bax, bay, baz, bax, bay, baz), m1 = dot3_rn(bax, bay, baz, oax, oay, oaz), m2 = dot3_rn(bax, bay, baz, r.dx, r.dy, r.dz);
+    const float m3 = dot3_rn(r.dx, r.dy, r.dz, oax, oay, oaz), m5 = dot3_rn(oax, oay, oaz, oax, oay, oaz);
+    const float m6 = dot3_rn(obx, oby, obz, r.dx, r.dy, r.dz), m7 = dot3_rn(obx, oby, obz, obx, oby, obz);
+    const float d2 = __fmaf_rn(-rr, rr, m0);
+    bool found = false;
+    float tb = 0.f, sb = 0.f;
+    if (d2 > 0.0f) {
+        const float k2 = __fmaf_rn(d2, dd, -__fmul_rn(m2, m2));
+        const float k1 = __fmaf_rn(d2, m3, __fmaf_rn(-m1, m2, __fmul_rn(__fmul_rn(m2, rr), ra)));
+        const float k0 = __fmaf_rn(d2, m5, __fmaf_rn(-m1, m1, __fmaf_rn(__fmul_rn(m1, rr), __fmul_rn(ra, 2.0f), -__fmul_rn(m0, __fmul_rn(ra, ra)))));
+        const float h = __fmaf_rn(k1, k1, -__fmul_rn(k0, k2));
+        if (h >= 0.0f && k2 != 0.0f) {
+            const float sq = __fsqrt_rn(h);
+#pragma unroll
+            for (int root = 0; root < 2; root++) {
+                const float tl = __fdiv_rn(root == 0 ? __fsub_rn(-sq, k1) : __fsub_rn(sq, k1), k2);
+                const float y = __fmaf_rn(tl, m2, __fmaf_rn(-ra, rr, m1));
+                const float t = __fadd_rn(tl, t0);
+                if (t > tmin && t <= tmax && y > 0.0f && y < d2 && (!found || t < tb)) { found = true; tb = t; sb = __fdiv_rn(y, d2); }
+            }
+        }
+    }
+    const float h1 = __fmaf_rn(m3, m3, -__fmul_rn(dd, __fmaf_rn(-ra, ra, m5)));
+    if (h1 >= 0.0f) {
+        const float t = __fadd_rn(__fdiv_rn(__fsub_rn(-m3, __fsqrt_rn(h1)), dd), t0);
+        if (t > tmin && t <= tmax && (!found || t < tb)) { found = true; tb = t; sb = 0.0f; }
+    }
+    const float h2 = __fmaf_rn(m6, m6, -__fmul_rn(dd, __fmaf_rn(-rb, rb, m7)));
+    if (h2 >= 0.0f) {
+        const float t = __fadd_rn(__fdiv_rn(__fsub_rn(-m6, __fsqrt_rn(h2)), dd), t0);
+        if (t > tmin && t <= tmax && (!found || t < tb)) { found = true; tb = t; sb = 1.0f; }
+    }
+    t_out = tb; s_out = sb;
+    return found;
+}
+
 // ---- one ray, traced by the calling thread ---------------------------------------------------------------------------
 // lc_trace_closest / lc_trace_any for device code: the same node test, the same canonical triangle arithmetic and the
 // same tie rule as the batch kernel, as a plain per-thread loop with a local-memory stack.  Returns the hit in the
@@ -221,7 +331,14 @@ struct NoCandidateHook {
     __device__ __forceinline__ int procedural(uint32_t, uint32_t, float, float &) const { return 0; }
 };
 
-template <bool ANY, bool QUERY, class Hook>
+// CURVES: curve instances (flags bit 3) are entered and their leaves tested with canonical_cone; a curve hit goes through the same
+// commit rules as a triangle (opaque: commits; otherwise hook.triangle with bary = (u, -1): the reference routes curve candidates of
+// a RayQuery to on_surface_hit as well, cpu/accel.rs:650-684).  Without CURVES those instances are skipped.  Lowered kernels get it
+// from the module's curve_basis_set (the frontend records it per trace call, rtx.rs:780-806), like the OptiX backend does.
+#ifndef LCB_CURVES
+#define LCB_CURVES 0
+#endif
+template <bool ANY, bool QUERY, class Hook, bool CURVES = (LCB_CURVES != 0)>
 __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask, bool first, Hook &hook) {
     DeviceHit h{kNone, kNone, 0.f, 0.f, rb.w, 0u};
     if (!acc.tlas_nodes) return h;
@@ -232,7 +349,8 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
     const float tmin = ra.w, ray_tmax = rb.w;
     float tbest = rb.w;
     uint32_t cur_inst = kNone, hit_slot = 0;
-    bool cur_opaque = true, cur_procedural = false, stop = false;
+    bool hit_curve = false;
+    bool cur_opaque = true, cur_procedural = false, cur_curve = false, stop = false;
     const WideNode *nodes = acc.tlas_nodes;
     const PackedTri *tris = nullptr;
     uint2 G = make_uint2(0u, 0x80000000u), Gt = make_uint2(0u, 0u);
@@ -262,6 +380,28 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                     if (first) stop = true;
                 }
                 if (stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
+            } else if (CURVES && cur_curve) {
+                const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
+                const float4 c0 = __ldg(tp), c1 = __ldg(tp + 1), c2 = __ldg(tp + 2);
+                float t, sl;
+                if (canonical_cone(r, tmin, ray_tmax, make_float4(c0.x, c0.y, c0.z, c1.w), make_float4(c1.x, c1.y, c1.z, c2.x), t, sl)) {
+                    const uint32_t prim = __float_as_uint(c0.w);
+                    const float u = __fmaf_rn(sl, c2.z, c2.y);
+                    bool commit = true;
+                    if (QUERY && !cur_opaque) {
+                        const int verdict = hook.triangle(cur_inst, prim, u, -1.0f, t);
+                        commit = (verdict & 1) != 0; stop = (verdict & 2) != 0;
+                    }
+                    if (commit) {
+                        if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; h.kind = 1u; return h; }
+                        // ties: lowest (inst, prim), then lowest u (two pieces of one segment meeting in a shared sphere)
+                        const bool better = t < tbest || h.inst == kNone ||
+                                            (t == tbest && (cur_inst < h.inst || (cur_inst == h.inst && (prim < h.prim || (prim == h.prim && hit_curve && u < h.u)))));
+                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; h.kind = 1u; h.u = u; h.v = -1.0f; hit_curve = true; }
+                        if (QUERY && first) stop = true;
+                    }
+                    if (QUERY && stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
+                }
             } else if (cur_inst != kNone) {
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
@@ -277,7 +417,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                     if (commit) {
                         if (ANY) { h.inst = cur_inst; h.prim = prim; h.t = t; h.kind = 1u; return h; }
                         const bool better = t < tbest || h.inst == kNone || (t == tbest && (cur_inst < h.inst || (cur_inst == h.inst && prim < h.prim)));
-                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; h.kind = 1u; hit_slot = Gt.x + bit; }
+                        if (better) { tbest = t; h.inst = cur_inst; h.prim = prim; h.kind = 1u; hit_slot = Gt.x + bit; hit_curve = false; }
                         if (QUERY && first) stop = true;
                     }
                     if (QUERY && stop) { Gt.y = 0u; G.y = 0u; sp = 0; break; }
@@ -286,7 +426,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 const uint32_t inst = __ldg(acc.tlas_prims + Gt.x + bit);
                 const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
                 const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);
-                if ((meta.x & mask) != 0u && (QUERY || (meta.z & 4u) == 0u)) {
+                if ((meta.x & mask) != 0u && (QUERY || (meta.z & 4u) == 0u) && (CURVES || (meta.z & 8u) == 0u)) {
                     if (Gt.y) stack[sp++] = Gt;
                     if (G.y & 0xff000000u) stack[sp++] = G;
                     stack[sp++] = make_uint2(0u, 0u);  // sentinel: below it lies world space
@@ -297,6 +437,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                     setup_object(r, ra, rb, m0, m1, m2);
                     cur_inst = inst;
                     if (QUERY) { cur_opaque = (meta.z & 2u) != 0u; cur_procedural = (meta.z & 4u) != 0u; }
+                    if (CURVES) cur_curve = (meta.z & 8u) != 0u;
                     G = make_uint2(0u, 0x80000000u);
                     Gt = make_uint2(0u, 0u);
                     break;
@@ -310,7 +451,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 const uint2 e = stack[--sp];
                 if (e.y & 0xff000000u) { G = e; break; }
                 if (e.y != 0u) { Gt = e; break; }
-                cur_inst = kNone; cur_procedural = false; nodes = acc.tlas_nodes; tris = nullptr;
+                cur_inst = kNone; cur_procedural = false; cur_curve = false; nodes = acc.tlas_nodes; tris = nullptr;
                 if (sp == 0) { done = true; break; }
                 setup_world(r, ra, rb);
             }
@@ -318,7 +459,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
         }
     }
     if (!ANY && h.inst != kNone) h.t = tbest;
-    if (!ANY && h.inst != kNone && h.kind == 1u) {
+    if (!ANY && h.inst != kNone && h.kind == 1u && !hit_curve) {
         const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h.inst);
         const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
         const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);

@@ -749,9 +749,10 @@ class KernelBuilder(Module):
         km = k.finish()              # address of the KernelModule (LCKernelModule.ptr)
     """
 
-    def __init__(self, block_size=(64, 1, 1)):
+    def __init__(self, block_size=(64, 1, 1), curve_bases=0):
         super().__init__()
         self.block_size = block_size
+        self.curve_bases = curve_bases  # CurveBasisSet bits (AccelTraceOptions::curve_bases, rtx.rs:659-670): 1 linear, 2 B-spline, 4 Catmull-Rom, 8 Bezier
         self._args, self._captures, self._shared = [], [], []
         self._entry = None
 
@@ -806,6 +807,7 @@ class KernelBuilder(Module):
         km.module.kind = 2
         km.module.entry = self._entry
         km.module.flags = 0
+        km.module.curve_basis_set = self.curve_bases
         km.captures = self.slice(Capture, self._captures)
         km.args = self.slice(sz, self._args)
         km.shared = self.slice(sz, self._shared)

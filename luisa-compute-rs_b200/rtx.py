@@ -172,6 +172,49 @@ class ProceduralPrimitive:
         self._alive = False
 
 
+class CurveBasis:
+    """api::CurveBasis (api_types:196-202)"""
+    PIECEWISE_LINEAR, CUBIC_BSPLINE, CATMULL_ROM, BEZIER = 0, 1, 2, 3
+
+
+class Curve:
+    """A curve geometry behind `create_curve` / `CurveBuildCommand` (api_types:618-631; backend: GeometryImpl::build_curve,
+    cpu/accel.rs:142-203).  The Rust frontend of the reference has the device-side half only (SurfaceHit::is_curve / curve_parameter,
+    rtx/curve.rs evaluators); the host type follows the C++ runtime's `Device::create_curve(basis, control_points, segments)`.
+    control points: a buffer of float4 {x, y, z, radius} (stride >= 16); segments: a buffer of u32 first-control-point indices."""
+
+    def __init__(self, device, basis, cp_view, seg_view, option=None):
+        self.device = device
+        self.option = option or AccelOption()
+        self.basis = int(basis)
+        self.cp_view, self.seg_view = cp_view, seg_view
+        if cp_view.buffer.stride < 16:
+            raise LuisaError("cp buffer stride must be >= 16")
+        if seg_view.buffer.stride != 4:
+            raise LuisaError("curve segments are u32 control point indices")
+        info = device.iface.create_curve(device.handle, C.byref(self.option))
+        self.handle = abi.Handle(info.handle)
+        self._alive = True
+
+    def build_async(self, request=AccelBuildRequest.FORCE_BUILD):
+        cmd = abi.Command()
+        cmd.tag = abi.CMD_CURVE_BUILD
+        cp, sg = self.cp_view, self.seg_view
+        cmd.u.curve_build = abi.CmdCurveBuild(self.handle, request, self.basis, cp.size // cp.buffer.stride, sg.size // 4,
+                                              cp.buffer.handle, cp.offset, cp.buffer.stride, sg.buffer.handle, sg.offset)
+        return HostCommand(cmd, keep=[self, cp.buffer, sg.buffer])
+
+    def build(self, request=AccelBuildRequest.FORCE_BUILD):
+        s = self.device.default_stream()
+        s.submit([self.build_async(request)])
+        s.synchronize()
+
+    def destroy(self):
+        if self._alive and not self.device._closed:
+            self.device.iface.destroy_curve(self.device.handle, self.handle)
+        self._alive = False
+
+
 class Accel:
     """`Device::create_accel(option)` (runtime.rs:690-701) and `rtx::Accel` (rtx.rs:154-311)."""
 
@@ -208,6 +251,9 @@ class Accel:
     def push_procedural_primitive(self, prim, transform=None, ray_mask=0xFF):
         """rtx.rs:236-247: procedural instances are never opaque (every candidate goes through the callback)."""
         self._push_handle(prim, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, False)
+
+    def push_curve(self, curve, transform=None, ray_mask=0xFF, opaque=True):
+        self._push_handle(curve, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, opaque)
 
     def set_mesh(self, index, mesh, transform=None, ray_mask=0xFF, opaque=True):
         self._set_handle(index, mesh, np.eye(4, dtype=np.float32) if transform is None else transform, ray_mask, opaque)

@@ -99,6 +99,10 @@ class Device:
         from .rtx import Accel
         return Accel(self, option)
 
+    def create_curve(self, basis, cp_view, seg_view, option=None):
+        from .rtx import Curve
+        return Curve(self, basis, cp_view, seg_view, option)
+
     def create_procedural_primitive(self, aabb_view, option=None):
         from .rtx import ProceduralPrimitive
         return ProceduralPrimitive(self, aabb_view, option)

@@ -42,6 +42,10 @@ typedef struct mesh {
     bvh_node *nodes;
     uint32_t n_nodes;
     uint32_t *prims;
+    /* curves (build_curve, accel.rs:142-203): float4 control points {x, y, z, radius}, u32 first-control-point index per segment */
+    int is_curve, basis;
+    const uint8_t *cps; size_t cp_stride, cp_count;
+    const uint32_t *segs; size_t nsegs;
 } mesh;
 
 /* accel.rs:270-296 */
@@ -91,6 +95,15 @@ void oracle_mesh_set(oracle_scene *s, uint64_t id, const void *vertices, size_t 
     mesh *m = &s->meshes[id];
     m->verts = (const uint8_t *)vertices; m->vstride = vstride; m->nverts = nverts;
     m->indices = (const uint8_t *)indices; m->istride = istride; m->ntris = ntris;
+}
+
+void oracle_curve_set(oracle_scene *s, uint64_t id, int basis, const void *cps, size_t cp_stride, size_t cp_count, const uint32_t *segs, size_t nsegs) {
+    if (id >= s->n_meshes) die("bad curve id");
+    if (cp_stride < 16) die("cp buffer stride must be >= 16 (cpu/accel.rs:159)");
+    if (basis < 0 || basis > 3) die("bad curve basis");
+    mesh *m = &s->meshes[id];
+    m->is_curve = 1; m->basis = basis; m->cps = (const uint8_t *)cps; m->cp_stride = cp_stride; m->cp_count = cp_count; m->segs = segs; m->nsegs = nsegs;
+    m->built = 1;
 }
 
 static inline void tri_verts(const mesh *m, uint32_t prim, const float **a, const float **b, const float **c) {
@@ -321,14 +334,115 @@ int oracle_canonical_triangle(const float o[3], const float d[3], float tmin, fl
     return canon_tri(&f, tmin, tmax, v0, v1, v2, t, u, v);
 }
 
-typedef struct best_hit { float t, u, v; uint32_t inst, prim; int found; } best_hit;
+typedef struct best_hit { float t, u, v; uint32_t inst, prim; int found; int curve; } best_hit;
 
 static inline void consider(best_hit *b, float t, float u, float v, uint32_t inst, uint32_t prim) {
     /* closest; ties -> lowest (inst, prim) */
     if (!b->found || t < b->t || (t == b->t && (inst < b->inst || (inst == b->inst && prim < b->prim)))) {
-        b->found = 1; b->t = t; b->u = u; b->v = v; b->inst = inst; b->prim = prim;
+        b->found = 1; b->t = t; b->u = u; b->v = v; b->inst = inst; b->prim = prim; b->curve = 0;
     }
 }
+
+/* ---- curves ------------------------------------------------------------------------------------
+ * The surface is the sweep of a sphere of radius r(u) along c(u).  A segment is put into the power basis with the frontend's own
+ * matrices (lc/src/rtx/curve.rs:88-139), cubic segments are cut at u = k/8 into 8 pieces, every piece is a rounded cone between
+ * the spheres at its ends (linear segments are one piece).  Embree's round curves (the reference) are intersected iteratively to a
+ * tolerance instead: PARITY UNPINNED.  A hit reports prim = segment, bary = (u, -1) (accel.rs:491-494), entry t. */
+#define CURVE_PIECES 8
+static inline int filter_accept(const oracle_filter *flt, uint32_t inst, uint32_t prim, float u, float v);
+static inline void lin4(const float m[4], float div, const float *q0, const float *q1, const float *q2, const float *q3, float out[4]) {
+    for (int c = 0; c < 4; c++) out[c] = (((m[0] * q0[c] + m[1] * q1[c]) + m[2] * q2[c]) + m[3] * q3[c]) / div;
+}
+static void curve_basis(int basis, const float *q0, const float *q1, const float *q2, const float *q3, float a[4][4]) {
+    static const float BS[4][4] = {{-1, 3, -3, 1}, {3, -6, 3, 0}, {-3, 0, 3, 0}, {1, 4, 1, 0}};
+    static const float CR[4][4] = {{-1, 3, -3, 1}, {2, -5, 4, -1}, {-1, 0, 1, 0}, {0, 2, 0, 0}};
+    static const float BZ[4][4] = {{-1, 3, -3, 1}, {3, -6, 3, 0}, {-3, 3, 0, 0}, {1, 0, 0, 0}};
+    const float (*M)[4] = basis == 1 ? BS : (basis == 2 ? CR : BZ);
+    const float div = basis == 1 ? 6.0f : (basis == 2 ? 2.0f : 1.0f);
+    for (int r = 0; r < 4; r++) lin4(M[r], div, q0, q1, q2, q3, a[r]);
+}
+static inline void curve_point(float a[4][4], float u, float out[4]) {
+    for (int c = 0; c < 4; c++) out[c] = ((a[0][c] * u + a[1][c]) * u + a[2][c]) * u + a[3][c];
+}
+static void curve_piece(const mesh *m, uint32_t seg, uint32_t k, float A[4], float B[4]) {
+    const uint32_t first = m->segs[seg];
+    const float *q0 = (const float *)(m->cps + (size_t)first * m->cp_stride), *q1 = (const float *)(m->cps + (size_t)(first + 1) * m->cp_stride);
+    if (m->basis == 0) { memcpy(A, q0, 16); memcpy(B, q1, 16); return; }
+    const float *q2 = (const float *)(m->cps + (size_t)(first + 2) * m->cp_stride), *q3 = (const float *)(m->cps + (size_t)(first + 3) * m->cp_stride);
+    float a[4][4];
+    curve_basis(m->basis, q0, q1, q2, q3, a);
+    curve_point(a, (float)k * (1.0f / CURVE_PIECES), A);
+    curve_point(a, (float)(k + 1) * (1.0f / CURVE_PIECES), B);
+}
+static inline float dot3f(const float *a, const float *b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
+/* canonical ray / rounded cone (after I. Quilez' intersector; both lateral roots, unnormalised direction, formed about the point
+ * of the ray nearest to sphere A).  Same operation order as trace_device.cuh canonical_cone. */
+static int canon_cone(const ray_frame *f, float tmin, float tmax, const float A[4], const float B[4], float *t_out, float *s_out) {
+    const float ra = A[3], rb = B[3];
+    const float *d = f->d;
+    const float dd = dot3f(d, d);
+    const float ao[3] = {A[0] - f->o[0], A[1] - f->o[1], A[2] - f->o[2]};
+    const float t0 = dot3f(ao, d) / dd;
+    const float o[3] = {fmaf(t0, d[0], f->o[0]), fmaf(t0, d[1], f->o[1]), fmaf(t0, d[2], f->o[2])};
+    const float ba[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+    const float oa[3] = {o[0] - A[0], o[1] - A[1], o[2] - A[2]};
+    const float ob[3] = {o[0] - B[0], o[1] - B[1], o[2] - B[2]};
+    const float rr = ra - rb;
+    const float m0 = dot3f(ba, ba), m1 = dot3f(ba, oa), m2 = dot3f(ba, d), m3 = dot3f(d, oa), m5 = dot3f(oa, oa), m6 = dot3f(ob, d), m7 = dot3f(ob, ob);
+    const float d2 = fmaf(-rr, rr, m0);
+    int found = 0; float tb = 0.f, sb = 0.f;
+    if (d2 > 0.0f) {
+        const float k2 = fmaf(d2, dd, -(m2 * m2));
+        const float k1 = fmaf(d2, m3, fmaf(-m1, m2, (m2 * rr) * ra));
+        const float k0 = fmaf(d2, m5, fmaf(-m1, m1, fmaf(m1 * rr, ra * 2.0f, -(m0 * (ra * ra)))));
+        const float h = fmaf(k1, k1, -(k0 * k2));
+        if (h >= 0.0f && k2 != 0.0f) {
+            const float sq = sqrtf(h);
+            for (int root = 0; root < 2; root++) {
+                const float tl = (root == 0 ? -sq - k1 : sq - k1) / k2;
+                const float y = fmaf(tl, m2, fmaf(-ra, rr, m1));
+                const float t = tl + t0;
+                if (t > tmin && t <= tmax && y > 0.0f && y < d2 && (!found || t < tb)) { found = 1; tb = t; sb = y / d2; }
+            }
+        }
+    }
+    const float h1 = fmaf(m3, m3, -(dd * fmaf(-ra, ra, m5)));
+    if (h1 >= 0.0f) {
+        const float t = (-m3 - sqrtf(h1)) / dd + t0;
+        if (t > tmin && t <= tmax && (!found || t < tb)) { found = 1; tb = t; sb = 0.0f; }
+    }
+    const float h2 = fmaf(m6, m6, -(dd * fmaf(-rb, rb, m7)));
+    if (h2 >= 0.0f) {
+        const float t = (-m6 - sqrtf(h2)) / dd + t0;
+        if (t > tmin && t <= tmax && (!found || t < tb)) { found = 1; tb = t; sb = 1.0f; }
+    }
+    *t_out = tb; *s_out = sb;
+    return found;
+}
+int oracle_canonical_cone(const float o[3], const float d[3], float tmin, float tmax, const float A[4], const float B[4], float *t, float *s) {
+    ray_frame f; memset(&f, 0, sizeof(f));
+    memcpy(f.o, o, 12); memcpy(f.d, d, 12);
+    return canon_cone(&f, tmin, tmax, A, B, t, s);
+}
+/* every piece of every segment, brute force; ties: lowest (inst, prim), then lowest u */
+static void curve_closest(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, const oracle_filter *flt, int first) {
+    const uint32_t pieces = m->basis == 0 ? 1 : CURVE_PIECES;
+    const float du = 1.0f / (float)pieces;
+    for (uint32_t seg = 0; seg < m->nsegs; seg++)
+        for (uint32_t k = 0; k < pieces; k++) {
+            float A[4], B[4], t, sl;
+            curve_piece(m, seg, k, A, B);
+            if (!canon_cone(f, tmin, tmax, A, B, &t, &sl)) continue;
+            const float u = fmaf(sl, du, (float)k * du);
+            if (flt && !filter_accept(flt, inst, seg, u, -1.0f)) continue;
+            best_hit *b = best;
+            if (!b->found || t < b->t || (t == b->t && (inst < b->inst || (inst == b->inst && (seg < b->prim || (seg == b->prim && b->curve && u < b->u)))))) {
+                b->found = 1; b->t = t; b->u = u; b->v = -1.0f; b->inst = inst; b->prim = seg; b->curve = 1;
+            }
+            if (first) return;
+        }
+}
+
 
 /* Reported barycentrics: the winning triangle is re-evaluated once in double (Moeller-Trumbore on the
  * canonical object-space ray, fixed operation order, no contraction) and rounded to fp32.  The fp32 edge
@@ -498,9 +612,11 @@ static void closest_one(const oracle_scene *s, const oracle_ray *r, uint32_t mas
         const instance *in = &s->insts[i];
         if (!in->valid || (in->visible & mask) == 0) continue;
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
-        mesh_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode);
+        if (s->meshes[in->mesh].is_curve) curve_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, NULL, 0);
+        else mesh_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode);
     }
-    if (best.found) {
+    if (best.found && best.curve) { h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->t = best.t; }
+    else if (best.found) {
         const instance *in = &s->insts[best.inst];
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
         const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best.prim, &a, &b, &c);
@@ -517,6 +633,12 @@ static uint32_t any_one(const oracle_scene *s, const oracle_ray *r, uint32_t mas
         const instance *in = &s->insts[i];
         if (!in->valid || (in->visible & mask) == 0) continue;
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        if (s->meshes[in->mesh].is_curve) {
+            best_hit b; memset(&b, 0, sizeof(b));
+            curve_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &b, NULL, 1);
+            if (b.found) return 1;
+            continue;
+        }
         if (mesh_any(&s->meshes[in->mesh], &f, r->tmin, r->tmax, mode)) return 1;
     }
     return 0;
@@ -529,9 +651,11 @@ static void query_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask,
         const instance *in = &s->insts[i];
         if (!in->valid || (in->visible & mask) == 0) continue;
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
-        mesh_closest_filtered(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode, in->opaque ? NULL : flt, first);
+        if (s->meshes[in->mesh].is_curve) curve_closest(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, in->opaque ? NULL : flt, first);
+        else mesh_closest_filtered(&s->meshes[in->mesh], &f, r->tmin, r->tmax, i, &best, mode, in->opaque ? NULL : flt, first);
     }
-    if (best.found) {
+    if (best.found && best.curve) { h->inst = best.inst; h->prim = best.prim; h->u = best.u; h->v = best.v; h->hit_type = 1; h->t = best.t; }
+    else if (best.found) {
         const instance *in = &s->insts[best.inst];
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
         const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best.prim, &a, &b, &c);

@@ -57,6 +57,10 @@ void oracle_mesh_set(oracle_scene *, uint64_t mesh, const void *vertices, size_t
                      const void *indices, size_t index_stride, size_t triangle_count);
 /* (Re)build the per-mesh CPU BVH after the vertex data changed. */
 void oracle_mesh_commit(oracle_scene *, uint64_t mesh);
+/* cpu/accel.rs:142-203 GeometryImpl::build_curve: a curve geometry on a handle from oracle_mesh_new(); basis = api::CurveBasis
+ * (0 PiecewiseLinear, 1 CubicBSpline, 2 CatmullRom, 3 Bezier); control points float4 {x, y, z, radius} at cp_stride; buffers are aliased. */
+void oracle_curve_set(oracle_scene *, uint64_t mesh, int basis, const void *cps, size_t cp_stride, size_t cp_count, const uint32_t *segs, size_t seg_count);
+int oracle_canonical_cone(const float o[3], const float d[3], float tmin, float tmax, const float A[4], const float B[4], float *t, float *s);
 
 /* AccelImpl::update (accel.rs:324-447). */
 void oracle_accel_update(oracle_scene *, uint32_t instance_count, const oracle_mod *mods, size_t n_mods);

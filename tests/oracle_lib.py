@@ -51,9 +51,20 @@ def lib():
         L.oracle_canonical_triangle.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float] + [C.POINTER(C.c_float)] * 6
         L.oracle_canonical_triangle.restype = C.c_int
         L.oracle_invert_affine.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_curve_set.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.oracle_canonical_cone.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float] + [C.POINTER(C.c_float)] * 4
+        L.oracle_canonical_cone.restype = C.c_int
         L.oracle_hw_threads.restype = C.c_int
         _lib = L
     return _lib
+
+
+def canonical_cone(o, d, tmin, tmax, A, B):
+    """oracle canon_cone on one ray and one rounded cone (A, B = (x, y, z, radius)): (hit, t, s)"""
+    f = lambda a: (C.c_float * len(a))(*[float(x) for x in a])
+    t, s = C.c_float(), C.c_float()
+    hit = lib().oracle_canonical_cone(f(o), f(d), tmin, tmax, f(A), f(B), C.byref(t), C.byref(s))
+    return bool(hit), t.value, s.value
 
 
 HIT = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("committed_ray_t", "<f4"), ("_pad", "<u4")])
@@ -74,6 +85,15 @@ class OracleScene:
         m = self.L.oracle_mesh_new(self.s)
         self.L.oracle_mesh_set(self.s, m, verts.ctypes.data, stride or verts.strides[0], verts.shape[0], tris.ctypes.data, 12, tris.shape[0])
         self.L.oracle_mesh_commit(self.s, m)
+        return m
+
+    def add_curve(self, basis, cps, segs):
+        """control points (n, 4) float32 {x, y, z, radius}; segs (m,) uint32 first-control-point indices"""
+        cps = np.ascontiguousarray(cps, dtype=np.float32)
+        segs = np.ascontiguousarray(segs, dtype=np.uint32)
+        self.keep += [cps, segs]
+        m = self.L.oracle_mesh_new(self.s)
+        self.L.oracle_curve_set(self.s, m, int(basis), cps.ctypes.data, cps.strides[0], cps.shape[0], segs.ctypes.data, segs.shape[0])
         return m
 
     def commit_mesh(self, m):
