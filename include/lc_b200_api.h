@@ -176,6 +176,9 @@ typedef struct lcb_cmd_mesh_build { /* api_types:603-616 */
 } lcb_cmd_mesh_build;
 LCB_STATIC_ASSERT(sizeof(lcb_cmd_mesh_build) == 80, "MeshBuildCommand is 80 bytes");
 
+/* CurveBuildCommand (api_types:618-631; backend: GeometryImpl::build_curve, cpu/accel.rs:142-203).  basis = api::CurveBasis
+ * (0 PiecewiseLinear, 1 CubicBSpline, 2 CatmullRom, 3 Bezier); control points are float4 {x, y, z, radius} at cp_stride (>= 16,
+ * multiple of 16); segments are u32 indices of each segment's first control point.  Always a full build. */
 typedef struct lcb_cmd_curve_build { lcb_curve curve; int32_t request; int32_t basis; size_t cp_count, seg_count; lcb_buffer cp_buffer; size_t cp_offset, cp_stride; lcb_buffer seg_buffer; size_t seg_offset; } lcb_cmd_curve_build;
 typedef struct lcb_cmd_procedural_build { lcb_procedural handle; int32_t request; lcb_buffer aabb_buffer; size_t aabb_offset, aabb_count; } lcb_cmd_procedural_build;
 

@@ -123,6 +123,14 @@ size_t ir_type_size(const IrType *t) {  // ir.rs:325-335
     }
 }
 
+// Zero-fill of a fresh allocation.  cudaMemset runs on the legacy default stream and returns before it has executed; the
+// device's streams are non-blocking (they do not order against that stream), so an upload submitted right after creation
+// could be overtaken by the fill.  Waiting for the fill here closes that window.
+static void zero_fill(void *p, size_t bytes) {
+    CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, cudaStreamLegacy));
+    CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+}
+
 // ---- backend objects ---------------------------------------------------------------------------
 struct BufferObj { uint8_t *ptr = nullptr; size_t size = 0; bool owned = true; };
 
@@ -246,7 +254,7 @@ lcb_created_buffer create_buffer(lcb_device dev, const void *ir_type, size_t cou
     if (ext_mem) { b->ptr = (uint8_t *)ext_mem; b->owned = false; }
     else {
         CUDA_CHECK(cudaMalloc(&b->ptr, total ? total : 16));
-        CUDA_CHECK(cudaMemset(b->ptr, 0, total ? total : 16));  // BufferImpl::new zero-initialises (cpu/resource.rs:126-133)
+        zero_fill(b->ptr, total ? total : 16);  // BufferImpl::new zero-initialises (cpu/resource.rs:126-133)
     }
     lcb_created_buffer out{};
     out.resource.handle = (uint64_t)b; out.resource.native_handle = b->ptr;
@@ -757,7 +765,7 @@ lcb_created create_texture(lcb_device dev, int32_t format, uint32_t dim, uint32_
     t->storage = format_to_storage(format); t->pixel_bytes = storage_pixel_bytes(t->storage);
     t->bytes = (size_t)t->width * t->height * t->depth * t->pixel_bytes;
     CUDA_CHECK(cudaMalloc(&t->ptr, t->bytes ? t->bytes : 16));
-    CUDA_CHECK(cudaMemset(t->ptr, 0, t->bytes ? t->bytes : 16));
+    zero_fill(t->ptr, t->bytes ? t->bytes : 16);
     return lcb_created{(uint64_t)t, t->ptr};
 }
 void destroy_texture(lcb_device dev, lcb_texture h) { bind(dev_of(dev)); TextureObj *t = as<TextureObj>(h.id); cudaFree(t->ptr); delete t; }
@@ -775,7 +783,7 @@ lcb_created create_bindless_array(lcb_device dev, size_t size) {
     auto *b = new BindlessObj;
     b->host.assign(size, HostBindlessSlot{});
     CUDA_CHECK(cudaMalloc((void **)&b->device, (size ? size : 1) * sizeof(HostBindlessSlot)));
-    CUDA_CHECK(cudaMemset(b->device, 0, (size ? size : 1) * sizeof(HostBindlessSlot)));
+    zero_fill(b->device, (size ? size : 1) * sizeof(HostBindlessSlot));
     return lcb_created{(uint64_t)b, b->device};
 }
 void destroy_bindless_array(lcb_device dev, lcb_bindless h) { bind(dev_of(dev)); BindlessObj *b = as<BindlessObj>(h.id); cudaFree(b->device); delete b; }
@@ -839,7 +847,7 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
     };
     auto put_accel = [&](const ParamSlot &p, uint64_t handle) {
         AccelObj *ao = as<AccelObj>(handle);
-        if (!ao->dirty) { CUDA_CHECK(cudaMalloc((void **)&ao->dirty, 256)); CUDA_CHECK(cudaMemset(ao->dirty, 0, 256)); }
+        if (!ao->dirty) { CUDA_CHECK(cudaMalloc((void **)&ao->dirty, 256)); zero_fill(ao->dirty, 256); }
         HostAccelArg a{view_of(ao), ao->table, ao->dirty}; memcpy(block.data() + p.offset, &a, sizeof(a));
     };
     for (const ParamSlot &p : k.captures) {  // bound at create_shader time (KernelModule.captures, cpu/mod.rs:296-301)

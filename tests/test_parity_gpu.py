@@ -555,3 +555,20 @@ def test_full_size_properties_c5_instanced(device):
     pick = np.random.default_rng(6).integers(0, rays.shape[0], 30000)
     assert_hits_equal(h1[pick], o.trace_closest(rays[pick]), "50M-triangle instanced sample")
     d.destroy(); o.close()
+
+
+@pytest.mark.gpu
+def test_upload_right_after_create_buffer_survives_the_zero_fill(device):
+    """create_buffer zero-fills (BufferImpl::new, cpu/resource.rs:126-133) on the legacy stream; the device's streams are
+    non-blocking, so the fill of a large buffer must be over before create_buffer returns or it overtakes the first upload."""
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        big = device.create_buffer(64 << 20, 4, 4)  # 256 MiB: a fill that takes a while
+        head = rng.integers(0, 2**32, 4096, dtype=np.uint32)
+        big.view(0, head.shape[0]).copy_from(head)
+        small = device.create_buffer_from_array(head)
+        back = np.zeros_like(head); big.view(0, head.shape[0]).copy_to(back)
+        back2 = np.zeros_like(head); small.view().copy_to(back2)
+        tail = np.ones(16, np.uint32); big.view((64 << 20) - 16, 16).copy_to(tail)
+        assert np.array_equal(back, head) and np.array_equal(back2, head) and not tail.any()
+        big.destroy(); small.destroy()
