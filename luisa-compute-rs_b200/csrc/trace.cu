@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
             uint32_t child_base, prim_base, imask;
             const uint32_t hits = intersect_node(node, r, tmin, tbest, child_base, prim_base, imask);
             if (COUNTERS) n_nodes++;
+#ifdef LCB_COUNT_HOT
+            if (COUNTERS && cur_inst != kNone && (uint32_t)(node - nodes) < (uint32_t)LCB_COUNT_HOT) n_inst++;
+#endif
             G = make_uint2(child_base, (hits & 0xff000000u) | imask);
             Gt = make_uint2(prim_base, hits & 0x00ffffffu);
         }
