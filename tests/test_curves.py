@@ -322,3 +322,29 @@ def test_curve_kernel_compiles_with_curve_support():
         assert ("#define LCB_CURVES 1" in text) == bool(bases)
         log = C.c_void_p()
         assert L.lc_b200_shader_compile_check(C.addressof(k.km), False, C.byref(log)) == 0, C.string_at(log).decode()
+
+
+@pytest.mark.gpu
+def test_curve_rebuild_follows_the_control_points(device):
+    """CurveBuild reads the control points where they lie (shared buffers, cpu/accel.rs:160-181): after the buffer changes, a
+    rebuild (PreferUpdate is served by a full build) and an AccelBuild give the oracle's hits for the new curve."""
+    import luisa_compute_rs_b200 as lc
+    from harness import assert_hits_equal
+    cps, segs = strands(BEZIER, 30, 10, 900)
+    cpb, sgb = device.create_buffer_from_array(cps), device.create_buffer_from_array(segs)
+    curve = device.create_curve(lc.CurveBasis.BEZIER, cpb.view(), sgb.view(), lc.AccelOption(allow_update=True))
+    curve.build()
+    accel = device.create_accel()
+    accel.push_curve(curve)
+    accel.build()
+    rays = random_rays(20000, 901)
+    for step in range(2):
+        o = ol.OracleScene()
+        m = o.add_curve(BEZIER, cps, segs)
+        o.update(1, [{"index": 0, "flags": 1 | 2 | 4 | 16, "visibility": 0xFF, "mesh": m}])
+        assert_hits_equal(batch_closest(device, lc, accel, rays), o.trace_closest(rays, mode=ol.BRUTE), f"curve rebuild step {step}")
+        o.close()
+        cps = cps.copy(); cps[:, :3] += np.float32(0.05) * np.sin(np.arange(cps.shape[0], dtype=np.float32))[:, None]; cps[:, 3] *= np.float32(1.5)
+        cpb.view().copy_from(cps)
+        curve.build(lc.AccelBuildRequest.PREFER_UPDATE)
+        accel.build()
