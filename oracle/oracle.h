@@ -12,6 +12,8 @@
  * the *semantics* the reference wraps around Embree, file by file:
  *
  *   cpu/accel.rs:205-260   GeometryImpl::build_mesh       -> oracle_mesh_set()
+ *   cpu/accel.rs:142-203   GeometryImpl::build_curve      -> oracle_curve_set()  (round curves as rounded-cone pieces cut in the
+ *                          frontend's power basis, lc/src/rtx/curve.rs:88-139; `oracle_canonical_cone()`; hits (u, -1): accel.rs:491-494)
  *   cpu/accel.rs:324-447   AccelImpl::update              -> oracle_accel_update()
  *   cpu/accel.rs:449-509   AccelImpl::trace_closest       -> oracle_trace_closest()
  *   cpu/accel.rs:511-535   AccelImpl::trace_any           -> oracle_trace_any()
