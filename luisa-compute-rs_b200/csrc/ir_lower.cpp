@@ -47,14 +47,13 @@ size_t prim_size(int32_t p) {
     return sz[p];
 }
 const char *prim_c(int32_t p) {
-    static const char *n[12] = {"bool", "int8_t", "uint8_t", "int16_t", "uint16_t", "int32_t", "uint32_t", "int64_t", "uint64_t", nullptr, "float", "double"};
+    static const char *n[12] = {"bool", "int8_t", "uint8_t", "int16_t", "uint16_t", "int32_t", "uint32_t", "int64_t", "uint64_t", "lc_half", "float", "double"};
     if (p < 0 || p >= 12) fail("bad primitive tag");
-    if (!n[p]) fail("Float16 values are not supported by the B200 lowering");
     return n[p];
 }
 const char *prim_vec(int32_t p) {
-    static const char *n[12] = {"bool", "char", "uchar", "short", "ushort", "int", "uint", "long", "ulong", nullptr, "float", "double"};
-    if (!n[p]) fail("Float16 vectors are not supported by the B200 lowering");
+    static const char *n[12] = {"bool", "char", "uchar", "short", "ushort", "int", "uint", "long", "ulong", "half", "float", "double"};
+    if (p < 0 || p >= 12) fail("bad primitive tag");
     return n[p];
 }
 bool prim_is_float(int32_t p) { return p == P_Float16 || p == P_Float32 || p == P_Float64; }
@@ -169,7 +168,8 @@ std::string prim_literal(int32_t p, const uint8_t *d) {
         case P_Uint64: { uint64_t v; memcpy(&v, d, 8); snprintf(buf, sizeof(buf), "%lluull", (unsigned long long)v); return buf; }
         case P_Float32: { float v; memcpy(&v, d, 4); return float_literal(v); }
         case P_Float64: { double v; memcpy(&v, d, 8); return double_literal(v); }
-        default: fail("Float16 constants are not supported");
+        case P_Float16: { uint16_t v; memcpy(&v, d, 2); snprintf(buf, sizeof(buf), "lc_half::from_bits(0x%04xu)", (unsigned)v); return buf; }
+        default: fail("bad primitive tag");
     }
 }
 
@@ -364,7 +364,8 @@ struct FunctionEmitter {
             case Const::Float32: e = float_literal(c.f32); break;
             case Const::Float64: e = double_literal(c.f64); break;
             case Const::Generic: e = decode_const(g.types, c.generic.type.get(), c.generic.bytes.ptr, c.generic.bytes.len); break;
-            default: fail("Float16 constants are not supported");
+            case Const::Float16: e = prim_literal(P_Float16, (const uint8_t *)&c.f16_bits); break;
+            default: fail("unknown constant tag " + std::to_string(c.tag));
         }
         line("const " + ts + " " + v + " = " + e + ";");
     }

@@ -61,6 +61,18 @@ LC_VEC_TYPEDEFS(int64_t, long)
 LC_VEC_TYPEDEFS(uint64_t, ulong)
 LC_VEC_TYPEDEFS(float, float)
 LC_VEC_TYPEDEFS(double, double)
+// Float16 (ir.rs Primitive::Float16; the CPU backend's `half`, device_math.h): storage is IEEE binary16, arithmetic happens in fp32
+// and every SSA value of the type is rounded back (round-to-nearest-even) when it is formed — for + - * / and sqrt that is the
+// correctly rounded binary16 result.  Only the two conversions are defined: operators and math builtins reach it through float.
+struct alignas(2) lc_f16 {
+    unsigned short bits;
+    lc_f16() = default;
+    __device__ lc_f16(float f) { asm("cvt.rn.f16.f32 %0, %1;" : "=h"(bits) : "f"(f)); }
+    __device__ operator float() const { float f; asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(bits)); return f; }
+    __device__ static lc_f16 from_bits(unsigned short b) { lc_f16 h; h.bits = b; return h; }
+};
+LC_VEC_TYPEDEFS(lc_f16, half)
+static_assert(sizeof(lc_half) == 2 && sizeof(lc_half2) == 4 && sizeof(lc_half3) == 8 && sizeof(lc_half4) == 8 && alignof(lc_half4) == 8, "IR vector layout rules for f16");
 static_assert(sizeof(lc_float3) == 16 && alignof(lc_float3) == 16 && sizeof(lc_float2) == 8 && sizeof(lc_bool3) == 4 && sizeof(lc_double3) == 32 &&
                   alignof(lc_double3) == 16 && sizeof(lc_uint4) == 16,
               "IR vector layout rules (ir.rs:234-263)");

@@ -344,7 +344,7 @@ class Module:
 
     # shorthand for the common vector types
     def __getattr__(self, name):
-        m = _re.fullmatch(r"(bool|i8|u8|i16|u16|i32|u32|i64|u64|f32|f64)([234])", name)
+        m = _re.fullmatch(r"(bool|i8|u8|i16|u16|i32|u32|i64|u64|f16|f32|f64)([234])", name)
         if m:
             return self.vector(getattr(self, m.group(1)), int(m.group(2)))
         raise AttributeError(name)
