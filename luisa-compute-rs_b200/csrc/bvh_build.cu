@@ -28,8 +28,9 @@ __global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags) {
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
         h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->bar_count = 0; h->bar_release = 0; h->max_depth = 0; h->error = 0;
-        h->prim_area_sum = 0.f;
+        h->prim_area_sum = 0.f; h->pad2 = 0.f;
     }
+    if (i < 48) h->level_end[i] = 0;  // the host reads the header back whole (builder choice, compaction)
     for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
 }
 
