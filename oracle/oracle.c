@@ -463,7 +463,9 @@ static inline void refine_bary(const ray_frame *f, const float *a, const float *
 }
 
 /* conservative slab test in double against the box padded by 2^-18 * Linf(ray origin, box) */
-static inline int box_cull(const float lo[3], const float hi[3], const float o[3], const float d[3], double tmin, double tbest,
+static inline void ray_inverse(const float d[3], double inv[3]) { for (int k = 0; k < 3; k++) inv[k] = d[k] == 0.0f ? 0.0 : 1.0 / (double)d[k]; }
+/* inv = ray_inverse(d), hoisted out of the node loop (the same double values as dividing per node) */
+static inline int box_cull(const float lo[3], const float hi[3], const float o[3], const float d[3], const double rinv[3], double tmin, double tbest,
                            double *tnear_out) {
     double R = 0.0;
     for (int k = 0; k < 3; k++) { double a = fabs((double)lo[k] - o[k]), b = fabs((double)hi[k] - o[k]); if (a > R) R = a; if (b > R) R = b; }
@@ -472,7 +474,7 @@ static inline int box_cull(const float lo[3], const float hi[3], const float o[3
     for (int k = 0; k < 3; k++) {
         double l = (double)lo[k] - pad - o[k], h = (double)hi[k] + pad - o[k];
         if (d[k] == 0.0f) { if (l > 0.0 || h < 0.0) return 1; continue; }
-        double inv = 1.0 / (double)d[k];
+        double inv = rinv[k];
         double t0 = l * inv, t1 = h * inv;
         if (t0 > t1) { double s = t0; t0 = t1; t1 = s; }
         if (t0 > tn) tn = t0;
@@ -517,11 +519,12 @@ static void mesh_closest_filtered(const mesh *m, const ray_frame *f, float tmin,
         return;
     }
     uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    double rinv[3]; ray_inverse(f->d, rinv);
     while (top) {
         const bvh_node *nd = &m->nodes[stack[--top]];
         double tn;
         double tb = best->found ? (double)best->t : (double)tmax;
-        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tb, &tn)) continue;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, rinv, tmin, tb, &tn)) continue;
         if (nd->count) {
             for (uint32_t i = 0; i < nd->count; i++) {
                 uint32_t p = m->prims[nd->left + i];
@@ -550,11 +553,12 @@ static void mesh_closest(const mesh *m, const ray_frame *f, float tmin, float tm
         return;
     }
     uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    double rinv[3]; ray_inverse(f->d, rinv);
     while (top) {
         const bvh_node *nd = &m->nodes[stack[--top]];
         double tn;
         double tb = best->found ? (double)best->t : (double)tmax;
-        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tb, &tn)) continue;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, rinv, tmin, tb, &tn)) continue;
         if (nd->count) {
             for (uint32_t i = 0; i < nd->count; i++) {
                 uint32_t p = m->prims[nd->left + i];
@@ -588,10 +592,11 @@ static int mesh_any(const mesh *m, const ray_frame *f, float tmin, float tmax, i
         return 0;
     }
     uint32_t stack[128]; int top = 0; stack[top++] = 0;
+    double rinv[3]; ray_inverse(f->d, rinv);
     while (top) {
         const bvh_node *nd = &m->nodes[stack[--top]];
         double tn;
-        if (box_cull(nd->lo, nd->hi, f->o, f->d, tmin, tmax, &tn)) continue;
+        if (box_cull(nd->lo, nd->hi, f->o, f->d, rinv, tmin, tmax, &tn)) continue;
         if (nd->count) {
             for (uint32_t i = 0; i < nd->count; i++) {
                 const float *a, *b, *c; tri_verts(m, m->prims[nd->left + i], &a, &b, &c);
@@ -720,10 +725,11 @@ static void truth_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask,
             for (uint32_t p = 0; p < m->ntris; p++) { const float *a, *b, *c; tri_verts(m, p, &a, &b, &c); truth_tri(o, d, r->tmin, r->tmax, a, b, c, i, p, &st); }
         } else {
             uint32_t stack[128]; int top = 0; stack[top++] = 0;
+            double rinv[3]; ray_inverse(df, rinv);
             while (top) {
                 const bvh_node *nd = &m->nodes[stack[--top]];
                 double tn, tb = st.found ? st.t_best * (1.0 + 1e-4) + 1e-30 : (double)r->tmax * (1.0 + 1e-4);
-                if (box_cull(nd->lo, nd->hi, of, df, (double)r->tmin * (1.0 - 1e-4) - 1e-30, tb, &tn)) continue;
+                if (box_cull(nd->lo, nd->hi, of, df, rinv, (double)r->tmin * (1.0 - 1e-4) - 1e-30, tb, &tn)) continue;
                 if (nd->count) {
                     for (uint32_t j = 0; j < nd->count; j++) { uint32_t p = m->prims[nd->left + j]; const float *a, *b, *c; tri_verts(m, p, &a, &b, &c); truth_tri(o, d, r->tmin, r->tmax, a, b, c, i, p, &st); }
                 } else { if (top + 2 > 128) die("oracle BVH stack overflow"); stack[top++] = nd->left; stack[top++] = nd->left + 1; }
