@@ -187,3 +187,26 @@ extern "C" int ref_texture2d_sample(const float *img, uint32_t w, uint32_t h, co
     delete[] store;
     return 0;
 }
+
+// cpu_texture.h pixel conversions: lc_texture2d_write<float4> followed by lc_texture2d_read<float4> on a w x 1 image of the given
+// LCPixelStorage.  raw = the stored pixel (pixel_bytes each, in x order, read at the reference's own _pixel2d address), back = what a
+// float read returns.  Covers the float -> unorm8 / unorm16 / half rounding and clamping rules (cpu_texture.h:58-135).
+extern "C" int ref_texture2d_write_read(uint32_t storage, uint32_t pixel_shift, const float *values, uint32_t w, uint8_t *raw, float *back) {
+    const size_t blocks = (size_t)((w + 3) / 4);
+    uint8_t *store = new uint8_t[(blocks * 16) << pixel_shift]();
+    Texture tex{};
+    tex.data = store; tex.width = w; tex.height = 1; tex.depth = 1;
+    tex.storage = (uint8_t)storage; tex.dimension = 2; tex.mip_levels = 1; tex.pixel_stride_shift = (uint8_t)pixel_shift;
+    tex.mip_offsets[0] = 0;
+    Texture2D arg{tex, 0};
+    KernelFnArgs *k_args = nullptr;
+    for (uint32_t x = 0; x < w; x++) lc_texture2d_write<lc_float4>(k_args, arg, lc_make_uint2(x, 0u), ld4(values, x));
+    TextureView view = lc_texture_view(&tex, 0u);
+    for (uint32_t x = 0; x < w; x++) {
+        const uint8_t *p = view._pixel2d(lc_make_uint2(x, 0u));
+        for (uint32_t b = 0; b < (1u << pixel_shift); b++) raw[((size_t)x << pixel_shift) + b] = p[b];
+        st4(back, x, lc_texture2d_read<lc_float4>(k_args, arg, lc_make_uint2(x, 0u)));
+    }
+    delete[] store;
+    return 0;
+}

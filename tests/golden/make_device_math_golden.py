@@ -77,7 +77,37 @@ def compute_texture(lib_path=REF_LIB):
     return res
 
 
+# format name (luisa-compute-rs_b200/runtime.py PIXEL_FORMATS) -> (LCPixelStorage, log2 bytes per pixel, numpy dtype, channels)
+PIXEL_CASES = {"Rgba8Unorm": (2, 2, np.uint8, 4), "R8Unorm": (0, 0, np.uint8, 1), "Rgba16Unorm": (5, 3, np.uint16, 4), "Rgba16f": (11, 3, np.float16, 4),
+               "R32f": (12, 2, np.float32, 1), "Rgba32f": (14, 4, np.float32, 4)}
+PIXEL_W = 96
+
+
+def pixel_values():
+    rng = np.random.default_rng(0xF1E1D)
+    v = rng.uniform(-0.2, 1.2, (PIXEL_W, 4)).astype(np.float32)
+    ties = np.array([0.0, -0.0, 1.0, -0.5, 1.5, 0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 0.5 / 65535, 1.5 / 65535, 65534.5 / 65535,
+                     0.49999 / 255, 0.50001 / 255, 70000.0, -70000.0, 6.0e-8, 1.0e-5, 0.333333, 0.1, 2049.0 / 2048.0, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 100.0], np.float32)
+    v.reshape(-1)[:ties.size] = ties
+    return v
+
+
+def compute_pixels(lib_path=REF_LIB):
+    """cpu_texture.h write -> stored pixel -> read for the storages of PIXEL_CASES: px_<format>_raw (stored texels), px_<format>_back."""
+    lib = C.CDLL(lib_path)
+    v = pixel_values()
+    res = {}
+    for name, (storage, shift, dtype, ch) in PIXEL_CASES.items():
+        raw = np.zeros(PIXEL_W << shift, np.uint8)
+        back = np.zeros((PIXEL_W, 4), np.float32)
+        lib.ref_texture2d_write_read(storage, shift, v.ctypes.data_as(C.c_void_p), PIXEL_W, raw.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p))
+        res["px_%s_raw" % name] = raw.view(dtype).reshape(PIXEL_W, ch) if ch > 1 else raw.view(dtype).reshape(PIXEL_W)
+        res["px_%s_back" % name] = back
+    return res
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "pixel_conversion_reference.npz"), **compute_pixels())
     np.savez_compressed(os.path.join(HERE, "texture_sample_reference.npz"), **compute_texture())
     res = compute()
     np.savez_compressed(os.path.join(HERE, "device_math_reference.npz"), **res)

@@ -250,3 +250,55 @@ def test_reverse_is_bit_reversal(device):
     bits = np.array([int(format(int(x), "032b")[::-1], 2) for x in d["ua"].reshape(-1)], np.uint32).reshape(-1, 4)
     assert np.array_equal(got, bits)
     assert np.array_equal(g["u4_Reverse"], d["ua"].byteswap())
+
+
+# ---- texel conversions ------------------------------------------------------------------------------------------------------------------
+def test_pixel_conversion_vectors_are_what_the_compiled_reference_returns():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_device_math_golden as mk
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "pixel_conversion_reference.npz"))
+    assert sorted(g.files) == sorted(["px_%s_%s" % (n, k) for n in mk.PIXEL_CASES for k in ("raw", "back")])
+    v = mk.pixel_values()
+    # by hand: unorm8 is roundf(x * 255) clamped (cpu_texture.h:74-86): halves round away from zero, out-of-range values clamp
+    raw = g["px_Rgba8Unorm_raw"].reshape(-1)
+    flat = v.reshape(-1)
+    for x, want in ((0.5 / 255, 1), (1.5 / 255, 2), (2.5 / 255, 3), (-0.5, 0), (1.5, 255), (1.0, 255)):
+        i = int(np.argwhere(flat == np.float32(x))[0, 0])
+        assert raw[i] == want, (x, raw[i])
+    if os.path.exists(REF_LIB):
+        fresh = mk.compute_pixels(REF_LIB)
+        for k in g.files:
+            assert np.array_equal(fresh[k].view(np.uint8), g[k].view(np.uint8)), k
+
+
+@pytest.mark.gpu
+def test_texel_write_and_read_conversions_are_bit_identical(device):
+    """Texture2dWrite of a float4 then Texture2dRead, per storage: the stored texels (downloaded) and the values read back equal what the
+    reference `cpu` device's cpu_texture.h stores and returns — unorm8 / unorm16 rounding and clamping, binary16 rounding and overflow."""
+    from luisa_compute_rs_b200 import ir
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_device_math_golden as mk
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "pixel_conversion_reference.npz"))
+    v = mk.pixel_values()
+    k = ir.KernelBuilder(block_size=(32, 1, 1))
+    img, vals, out = k.arg_tex2d(k.f324), k.arg_buffer(k.f324), k.arg_buffer(k.f324)
+
+    def body():
+        i = k.dispatch_id().x
+        c = k.vec(k.u322, i, k.u(0))
+        img.tex_write(c, vals.read(i))
+        out.write(i, img.tex_read(c))
+    k.body(body)
+    k.finish()
+    sh = device.create_shader(C.addressof(k.km), keep=k)
+    vb = device.create_buffer_from_array(v)
+    for name in mk.PIXEL_CASES:
+        tex = device.create_tex2d(name, mk.PIXEL_W, 1)
+        ob = device.create_buffer(mk.PIXEL_W, 16, 16)
+        sh.dispatch((mk.PIXEL_W,), tex, vb, ob)
+        back = ob.view().to_numpy(np.float32).reshape(-1, 4)
+        raw = tex.to_numpy().reshape(g["px_%s_raw" % name].shape)
+        assert np.array_equal(raw.view(np.uint8), g["px_%s_raw" % name].view(np.uint8)), "%s: stored texels differ at %r" % (name, np.argwhere(raw != g["px_%s_raw" % name])[:4])
+        assert np.array_equal(back.view(np.uint32), g["px_%s_back" % name].view(np.uint32)), "%s: values read back differ" % name
+        tex.destroy(); ob.destroy()
+    vb.destroy(); sh.destroy()
