@@ -22,8 +22,9 @@ def seed_image(width, height, seed=0xC0FFEE):
 
 
 class PathTracer:
-    def __init__(self, device, meshes, width, height, seed=0xC0FFEE):
-        """meshes: list of (vertices float32 (nv,3), triangles uint32 (nt,3)), one instance each with identity transform."""
+    def __init__(self, device, meshes, width, height, seed=0xC0FFEE, opaque=True):
+        """meshes: list of (vertices float32 (nv,3), triangles uint32 (nt,3)), one instance each with identity transform;
+        opaque=False is path_tracer_cutout.rs:250 (candidates of every instance reach the ray-query callback)."""
         self.device, self.width, self.height = device, width, height
         self.vbuffers, self.ibuffers, self.meshes = [], [], []
         self.accel = device.create_accel(AccelOption())
@@ -32,7 +33,7 @@ class PathTracer:
             ib = device.create_buffer_from_array(np.ascontiguousarray(tris, np.uint32))
             m = device.create_mesh(vb.view(), ib.view(), AccelOption())
             m.build(AccelBuildRequest.FORCE_BUILD)
-            self.accel.push_mesh(m, np.eye(4, dtype=np.float32), 255, True)
+            self.accel.push_mesh(m, np.eye(4, dtype=np.float32), 255, opaque)
             self.vbuffers.append(vb); self.ibuffers.append(ib); self.meshes.append(m)
         self.accel.build(AccelBuildRequest.FORCE_BUILD)
         self.image = device.create_buffer(width * height, 16, 16)       # Tex2d<Float4>, zero-initialised

@@ -92,8 +92,15 @@ F32_MAX = float(np.finfo(np.float32).max)
 TAN_HALF_FOV = float(np.float32(np.tan(np.float32(0.5) * (np.float32(27.8) * np.float32(np.pi) / np.float32(180.0)))))
 
 
-def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=SPP_PER_DISPATCH, max_depth=10, polynomial_sincos=False):
+CUTOUT_STRIPES = {5: (6.0, 0.6), 6: (5.0, 0.5)}   # path_tracer_cutout.rs:364-373: instance -> (frequency, kept fraction) of bary.y stripes
+
+
+def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=SPP_PER_DISPATCH, max_depth=10, polynomial_sincos=False, cutout=False):
     """examples/path_tracer.rs:247-455 — `Kernel::<fn(Tex2d<Float4>, Tex2d<u32>, Accel, Uint2)>`; the two bindless heaps are captures.
+
+    cutout=True is examples/path_tracer_cutout.rs: `accel.traverse(ray).on_surface_hit(|c| if filter(&c) { c.commit() }).trace()` replaces
+    intersect, `traverse_any` replaces intersect_any (:379-389, :435-445); the filter cuts bary.y stripes out of the two boxes (:364-373).
+    The instances must then be pushed non-opaque (:250) — opaque instances never reach the callback.
 
     polynomial_sincos=False emits Func::Sin / Func::Cos for the hemisphere sample like the example.  True replaces them by a
     callable evaluating the fixed polynomial of csrc/path_tracer.cu / oracle.c (sincos_2pi), so that the random walks are
@@ -133,6 +140,23 @@ def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=S
         k.return_()
     sincos = k.callable([(k.f32, True), (k.f32, False), (k.f32, False)], k.void, sincos_body) if polynomial_sincos else None
 
+    committed_ty = k.struct([k.u32, k.u32, k.f322, k.u32, k.f32], align=8)
+
+    def cutout_query(ray_value, any_hit):
+        """RayQueryAll / RayQueryAny with the example's filter as the on_surface_hit block; returns the CommittedHit."""
+        rq = accel.query(ray_value, k.u(0xFF), any_hit)
+
+        def on_surface_hit():
+            cand = k.call(Func.RayQueryTriangleCandidateHit, [rq], hit_ty)
+            c_inst, v = cand.extract(0), cand.extract(2).y
+            valid = None
+            for inst_id, (freq, keep) in sorted(CUTOUT_STRIPES.items()):
+                ok = c_inst.ne(inst_id) | (v * k.f(freq)).unary(Func.Fract).lt(keep)
+                valid = ok if valid is None else (valid & ok)
+            k.if_(valid, lambda: k.call(Func.RayQueryCommitTriangle, [rq], k.void))
+        k.ray_query(rq, on_surface_hit, None)
+        return k.call(Func.RayQueryCommittedHit, [rq], committed_ty)
+
     def body():
         materials = k.const(k.array(k.f323, 8), CBOX_MATERIALS)
         coord = k.dispatch_id().permute(0, 1)
@@ -166,8 +190,8 @@ def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=S
             depth = k.local_zero(k.u32)
 
             def bounce():
-                hit = accel.trace_closest(ray.load(), 0xFF, hit_ty)
-                inst, prim, bary = hit.extract(0), hit.extract(1), hit.extract(2)
+                hit = cutout_query(ray.load(), False) if cutout else accel.trace_closest(ray.load(), 0xFF, hit_ty)
+                inst, prim, bary = hit.extract(0), hit.extract(1), hit.extract(2)   # CommittedHit and SurfaceHit agree on these fields
                 k.if_(inst.ne(0xFFFFFFFF).not_(), lambda: k.break_())
                 tri = index_heap.bindless_buffer_read(inst, prim, index_ty)
                 p0 = _to_float3(k, vertex_heap.bindless_buffer_read(inst, tri.extract(0), f3))
@@ -201,7 +225,7 @@ def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=S
                     d_light = (pp - pp_light).length()
                     wi_light = (pp_light - pp).normalize()
                     shadow_ray = make_ray(k, ray_ty, f3, offset_ray_origin(k, pp, n), wi_light, 0.0, d_light)
-                    occluded = accel.trace_any(shadow_ray, 0xFF)
+                    occluded = cutout_query(shadow_ray, True).extract(3).ne(0) if cutout else accel.trace_any(shadow_ray, 0xFF)
                     cos_wi_light = wi_light.dot(n)
                     cos_light = -light_normal.dot(wi_light)
 

@@ -498,6 +498,12 @@ static inline int filter_accept(const oracle_filter *flt, uint32_t inst, uint32_
             return xy < r2 && yz < r2 && xz < r2;
         }
         case 2: { uint32_t b = flt->first_bit[inst] + prim; return (flt->bits[b >> 5] >> (b & 31u)) & 1u; }
+        case 4: {
+            const float fr = flt->stripe_freq[inst];
+            if (fr == 0.0f) return 1;
+            const float x = v * fr;
+            return (x - floorf(x)) < flt->stripe_keep[inst];
+        }
         default: return 0;
     }
 }
@@ -802,7 +808,7 @@ void oracle_trace_closest_f64(const oracle_scene *s, const oracle_ray *rays, uin
 }
 void oracle_ray_query(const oracle_scene *s, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
                       oracle_committed_hit *out, int mode, int threads) {
-    static const oracle_filter commit_all = {0, 0.f, NULL, NULL};
+    static const oracle_filter commit_all = {0, 0.f, NULL, NULL, NULL, NULL};
     job j = {s, rays, n, mask, mode, 3, NULL, NULL, NULL, 0, filter ? filter : &commit_all, out, terminate_on_first, NULL}; run(&j, threads);
 }
 
@@ -866,6 +872,7 @@ struct pt_job {
     const float *const *vertex_heap; const uint32_t *const *index_heap; float *image; uint32_t *seeds;
     uint32_t width, height, spp, max_depth; float tan_half_fov; int mode;
     uint64_t n_closest, n_any;
+    const oracle_filter *flt;  /* non-NULL: path_tracer_cutout.rs (ray queries with a candidate filter) */
 };
 
 static void pt_pixel(const struct pt_job *ptc, const oracle_scene *s, uint64_t pixel) {
@@ -896,7 +903,11 @@ static void pt_pixel(const struct pt_job *ptc, const oracle_scene *s, uint64_t p
         while (depth < pt->max_depth) {
             oracle_ray r = {{ray_o.x, ray_o.y, ray_o.z}, ray_tmin, {ray_d.x, ray_d.y, ray_d.z}, ray_tmax};
             oracle_hit hit;
-            closest_one(s, &r, 0xffu, &hit, pt->mode);
+            if (pt->flt) {
+                oracle_committed_hit ch;
+                query_one(s, &r, 0xffu, 0, pt->flt, &ch, pt->mode);
+                hit.inst = ch.inst; hit.prim = ch.prim; hit.u = ch.u; hit.v = ch.v; hit.t = ch.t;
+            } else closest_one(s, &r, 0xffu, &hit, pt->mode);
             n_closest++;
             if (hit.inst == UINT32_MAX) break;
             const float *vb = pt->vertex_heap[hit.inst];
@@ -927,7 +938,9 @@ static void pt_pixel(const struct pt_job *ptc, const oracle_scene *s, uint64_t p
                 const v3 wi_light = vnormalize(vsub(pp_light, pp));
                 const v3 so = voffset(pp, n);
                 oracle_ray sr = {{so.x, so.y, so.z}, 0.0f, {wi_light.x, wi_light.y, wi_light.z}, d_light};
-                const int occluded = (int)any_one(s, &sr, 0xffu, pt->mode);
+                int occluded;
+                if (pt->flt) { oracle_committed_hit ch; query_one(s, &sr, 0xffu, 1, pt->flt, &ch, pt->mode); occluded = ch.hit_type != 0u; }
+                else occluded = (int)any_one(s, &sr, 0xffu, pt->mode);
                 n_any++;
                 const float cos_wi_light = vdot(wi_light, n);
                 const float cos_light = -vdot(light_normal, wi_light);
@@ -972,7 +985,13 @@ static void pt_pixel(const struct pt_job *ptc, const oracle_scene *s, uint64_t p
 void oracle_path_tracer(const oracle_scene *s, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
                         uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, int threads,
                         uint64_t ray_counts_out[2]) {
-    struct pt_job pt = {vertex_heap, index_heap, image_rgba, seed_image, width, height, spp_per_dispatch, max_depth, tan_half_fov, 1, 0, 0};
+    oracle_path_tracer_cutout(s, vertex_heap, index_heap, image_rgba, seed_image, width, height, spp_per_dispatch, max_depth, tan_half_fov, NULL, threads, ray_counts_out);
+}
+
+void oracle_path_tracer_cutout(const oracle_scene *s, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
+                               uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, const oracle_filter *filter,
+                               int threads, uint64_t ray_counts_out[2]) {
+    struct pt_job pt = {vertex_heap, index_heap, image_rgba, seed_image, width, height, spp_per_dispatch, max_depth, tan_half_fov, 1, 0, 0, filter};
     job j = {s, NULL, (uint64_t)width * height, 0xff, 1, 4, NULL, NULL, NULL, 0, NULL, NULL, 0, &pt};
     run(&j, threads);
     if (ray_counts_out) { ray_counts_out[0] = pt.n_closest; ray_counts_out[1] = pt.n_any; }

@@ -88,7 +88,10 @@ void oracle_trace_any(const oracle_scene *, const oracle_ray *rays, uint64_t n, 
  * terminate_on_first = RayTracingQueryAny (rtcOccluded1): WHICH hit is reported is then traversal-order dependent.
  * Nothing committed -> {~0, ~0, (0,0), hit_type 0, t 0} (the zero-initialised RayQuery of cpu_resource.h:320-331). */
 typedef struct __attribute__((aligned(8))) oracle_committed_hit { uint32_t inst, prim; float u, v; uint32_t hit_type; float t; } oracle_committed_hit;
-typedef struct oracle_filter { int kind; float radius; const uint32_t *bits; const uint32_t *first_bit; } oracle_filter;
+/* kind 0 commit all, 1 barycentric disc (examples/ray_query.rs:148-162), 2 per-primitive bit table, 3 reject all,
+ * 4 stripes (examples/path_tracer_cutout.rs:364-373): on instance i with stripe_freq[i] != 0 a candidate commits iff
+ * fract(bary.y * stripe_freq[i]) < stripe_keep[i], fract(x) = x - floorf(x) (device_math.h lc_fract). */
+typedef struct oracle_filter { int kind; float radius; const uint32_t *bits; const uint32_t *first_bit; const float *stripe_freq; const float *stripe_keep; } oracle_filter;
 void oracle_ray_query(const oracle_scene *, const oracle_ray *rays, uint64_t n, uint32_t mask, int terminate_on_first, const oracle_filter *filter,
                       oracle_committed_hit *out, int mode, int threads);
 
@@ -99,6 +102,13 @@ void oracle_ray_query(const oracle_scene *, const oracle_ray *rays, uint64_t n, 
 void oracle_path_tracer(const oracle_scene *, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
                         uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, int threads,
                         uint64_t ray_counts_out[2]);
+
+/* examples/path_tracer_cutout.rs: the same kernel with `accel.traverse(ray).on_surface_hit(|c| if filter(&c) { c.commit() }).trace()` in
+ * place of intersect and `traverse_any` in place of intersect_any (:379-389, :435-445); every instance is pushed non-opaque (:250), so every
+ * triangle candidate passes through `filter` (an oracle_filter, kind 4 for the example's stripes on the two boxes). */
+void oracle_path_tracer_cutout(const oracle_scene *, const float *const *vertex_heap, const uint32_t *const *index_heap, float *image_rgba, uint32_t *seed_image,
+                               uint32_t width, uint32_t height, uint32_t spp_per_dispatch, uint32_t max_depth, float tan_half_fov, const oracle_filter *filter,
+                               int threads, uint64_t ray_counts_out[2]);
 
 /* Double-precision ground truth.  ambiguous[i] (may be NULL) is set to 1 when the fp32
  * answer is not forced: a second candidate lies within rel 1e-6 of the closest t, or some

@@ -12,7 +12,7 @@ _lib = None
 
 
 class Filter(C.Structure):
-    _fields_ = [("kind", C.c_int), ("radius", C.c_float), ("bits", C.c_void_p), ("first_bit", C.c_void_p)]
+    _fields_ = [("kind", C.c_int), ("radius", C.c_float), ("bits", C.c_void_p), ("first_bit", C.c_void_p), ("stripe_freq", C.c_void_p), ("stripe_keep", C.c_void_p)]
 
 
 class Mod(C.Structure):
@@ -172,6 +172,23 @@ def path_tracer_dispatch(oracle_scene, meshes, image, seeds, width, height, spp,
     ih = (C.c_void_p * len(ts))(*[t.ctypes.data for t in ts])
     counts = (C.c_uint64 * 2)()
     lib().oracle_path_tracer(oracle_scene.s, vh, ih, image.ctypes.data, seeds.ctypes.data, width, height, spp, max_depth, float(tan_half_fov), threads, counts)
+    return counts[0], counts[1]
+
+
+def path_tracer_cutout_dispatch(oracle_scene, meshes, image, seeds, width, height, spp, max_depth, tan_half_fov, stripe_freq, stripe_keep, threads=0):
+    """One dispatch of the CPU restatement of examples/path_tracer_cutout.rs: ray queries whose candidates pass the stripes filter
+    (stripe_freq / stripe_keep: one float per instance, freq 0 = no cut-out)."""
+    vs = [np.ascontiguousarray(v, np.float32) for v, _ in meshes]
+    ts = [np.ascontiguousarray(t, np.uint32) for _, t in meshes]
+    vh = (C.c_void_p * len(vs))(*[v.ctypes.data for v in vs])
+    ih = (C.c_void_p * len(ts))(*[t.ctypes.data for t in ts])
+    fr, kp = np.ascontiguousarray(stripe_freq, np.float32), np.ascontiguousarray(stripe_keep, np.float32)
+    flt = Filter(4, 0.0, None, None, fr.ctypes.data, kp.ctypes.data)
+    counts = (C.c_uint64 * 2)()
+    L = lib()
+    L.oracle_path_tracer_cutout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
+                                            C.POINTER(Filter), C.c_int, C.c_void_p]
+    L.oracle_path_tracer_cutout(oracle_scene.s, vh, ih, image.ctypes.data, seeds.ctypes.data, width, height, spp, max_depth, float(tan_half_fov), C.byref(flt), threads, counts)
     return counts[0], counts[1]
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--spp", type=int, default=32)
     ap.add_argument("--dispatches", type=int, default=8)
     ap.add_argument("--depth", type=int, default=10)
+    ap.add_argument("--cutout", action="store_true", help="also time examples/path_tracer_cutout.rs (ray queries with a candidate filter)")
     a = ap.parse_args()
     import torch
     import luisa_compute_rs_b200 as lc
@@ -79,6 +80,26 @@ def main():
             out["mean_radiance_hand"] = m0; out["mean_radiance_lowered"] = m1
         print(json.dumps(out))
         sh.destroy(); image.destroy(); seeds.destroy()
+    if a.cutout:
+        # examples/path_tracer_cutout.rs: every ray a RayQuery with the stripes filter inlined as the candidate callback, instances non-opaque
+        ptc = ex.PathTracer(dev, desc.meshes, w, h, opaque=False)
+        vh2, ih2 = dev.create_bindless_array(n), dev.create_bindless_array(n)
+        for i, (vb, ib) in enumerate(zip(ptc.vbuffers, ptc.ibuffers)):
+            vh2.emplace_buffer_async(i, vb); ih2.emplace_buffer_async(i, ib)
+        s.submit([vh2.update_async(), ih2.update_async()])
+        image = dev.create_tex2d("Rgba32f", w, h); seeds = dev.create_tex2d("R32Uint", w, h)
+        k = examples_ir.path_tracer_kernel(vh2.handle.id, ih2.handle.id, a.spp, a.depth, polynomial_sincos=True, cutout=True)
+        t0 = time.perf_counter()
+        sh = dev.create_shader(C.addressof(k.km), keep=k)
+        compile_s = time.perf_counter() - t0
+        res = np.array([w, h], np.uint32)
+        seeds.copy_from(ex.seed_image(w, h).reshape(h, w))
+        sh.dispatch((w, h), image, seeds, ptc.accel, res)   # warm-up
+        image.copy_from(np.zeros((h, w, 4), np.float32)); seeds.copy_from(ex.seed_image(w, h).reshape(h, w))
+        ms = timed(lambda: s.submit([sh.dispatch_async((w, h), image, seeds, ptc.accel, res) for _ in range(a.dispatches)]))
+        print(json.dumps({"variant": "lowered_cutout_ray_query", "size": w, "spp": a.spp * a.dispatches, "depth": a.depth, "ms_per_dispatch": ms / a.dispatches,
+                          "create_shader_s": compile_s, "note": "path_tracer_cutout.rs; rays not counted (paths differ from the opaque scene)"}))
+        sh.destroy(); image.destroy(); seeds.destroy(); vh2.destroy(); ih2.destroy(); ptc.destroy()
     pt.destroy(); dev.close()
 
 
