@@ -210,3 +210,23 @@ extern "C" int ref_texture2d_write_read(uint32_t storage, uint32_t pixel_shift, 
     delete[] store;
     return 0;
 }
+
+// cpu_texture.h: lc_texture_3d_sample (point / trilinear x edge / repeat / mirror / zero) on a one-level FLOAT4 volume stored in the
+// reference's 4 x 4 x 4 blocks.  vol = d x h x w x 4 floats, uvw = n x 4 (xyz used), out = n x 4.
+extern "C" int ref_texture3d_sample(const float *vol, uint32_t w, uint32_t h, uint32_t d, const float *uvw, size_t n, uint32_t filter, uint32_t address, float *out) {
+    const size_t blocks = (size_t)((w + 3) / 4) * ((h + 3) / 4) * ((d + 3) / 4);
+    lc_float4 *store = new lc_float4[blocks * 64]();
+    Texture tex{};
+    tex.data = reinterpret_cast<uint8_t *>(store);
+    tex.width = w; tex.height = h; tex.depth = d;
+    tex.storage = LC_PIXEL_STORAGE_FLOAT4; tex.dimension = 3; tex.mip_levels = 1; tex.pixel_stride_shift = 4;
+    tex.mip_offsets[0] = 0;
+    TextureView view = lc_texture_view(&tex, 0u);
+    for (uint32_t z = 0; z < d; z++)
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) view.write3d<lc_float4, float>(lc_make_uint3(x, y, z), ld4(vol, ((size_t)z * h + y) * w + x));
+    LCSampler s{static_cast<LCSamplerAddress>(address), static_cast<LCSamplerFilter>(filter)};
+    for (size_t i = 0; i < n; i++) st4(out, i, lc_texture_3d_sample(nullptr, &tex, s, ld3(uvw, i)));
+    delete[] store;
+    return 0;
+}

@@ -77,6 +77,30 @@ def compute_texture(lib_path=REF_LIB):
     return res
 
 
+def texture3d_inputs():
+    rng = np.random.default_rng(46)
+    w, h, d, n = 7, 5, 6, 768
+    vol = rng.uniform(0, 1, (d, h, w, 4)).astype(np.float32)
+    uvw = rng.uniform(-1.5, 2.5, (n, 4)).astype(np.float32)
+    uvw[:6, :3] = [[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [-1, 2, 0.25], [0.999999, 0.000001, 1.0], [2.0, -2.0, 0.75]]
+    uvw[:, 3] = 0
+    return vol, uvw
+
+
+def compute_texture3d(lib_path=REF_LIB):
+    """cpu_texture.h's lc_texture_3d_sample for 2 filters x 4 address modes: key tex3d_<filter>_<address>."""
+    lib = C.CDLL(lib_path)
+    vol, uvw = texture3d_inputs()
+    res = {}
+    for filt in (0, 1):
+        for address in range(4):
+            out = np.zeros((uvw.shape[0], 4), np.float32)
+            lib.ref_texture3d_sample(vol.ctypes.data_as(C.c_void_p), vol.shape[2], vol.shape[1], vol.shape[0], uvw.ctypes.data_as(C.c_void_p), C.c_size_t(uvw.shape[0]),
+                                     filt, address, out.ctypes.data_as(C.c_void_p))
+            res["tex3d_%d_%d" % (filt, address)] = out
+    return res
+
+
 # format name (luisa-compute-rs_b200/runtime.py PIXEL_FORMATS) -> (LCPixelStorage, log2 bytes per pixel, numpy dtype, channels)
 PIXEL_CASES = {"Rgba8Unorm": (2, 2, np.uint8, 4), "R8Unorm": (0, 0, np.uint8, 1), "Rgba16Unorm": (5, 3, np.uint16, 4), "Rgba16f": (11, 3, np.float16, 4),
                "R32f": (12, 2, np.float32, 1), "Rgba32f": (14, 4, np.float32, 4)}
@@ -108,7 +132,7 @@ def compute_pixels(lib_path=REF_LIB):
 
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "pixel_conversion_reference.npz"), **compute_pixels())
-    np.savez_compressed(os.path.join(HERE, "texture_sample_reference.npz"), **compute_texture())
+    np.savez_compressed(os.path.join(HERE, "texture_sample_reference.npz"), **compute_texture(), **compute_texture3d())
     res = compute()
     np.savez_compressed(os.path.join(HERE, "device_math_reference.npz"), **res)
     print("wrote %d arrays" % len(res))

@@ -58,7 +58,8 @@ def test_texture_sampling_restatement_equals_the_reference_vectors():
             got = til.np_sample2d(img, uv, filt, address).astype(np.float32)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (filt, address)
     if os.path.exists(REF_LIB):
-        fresh = mk.compute_texture(REF_LIB)
+        fresh = dict(mk.compute_texture(REF_LIB), **mk.compute_texture3d(REF_LIB))
+        assert sorted(fresh) == sorted(g.files)
         for k in g.files:
             assert np.array_equal(fresh[k].view(np.uint32), g[k].view(np.uint32)), k
 
@@ -302,3 +303,42 @@ def test_texel_write_and_read_conversions_are_bit_identical(device):
         assert np.array_equal(back.view(np.uint32), g["px_%s_back" % name].view(np.uint32)), "%s: values read back differ" % name
         tex.destroy(); ob.destroy()
     vb.destroy(); sh.destroy()
+
+
+@pytest.mark.gpu
+def test_bindless_texture3d_sampling_is_bit_identical_to_the_reference_header(device):
+    """BindlessTexture3dSample over 8 slots = point / trilinear x edge / repeat / mirror / zero of one Float4 volume against
+    lc_texture_3d_sample of the compiled cpu_texture.h (tests/golden/texture_sample_reference.npz, keys tex3d_*)."""
+    from luisa_compute_rs_b200 import ir
+    from luisa_compute_rs_b200.ir import Func
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_device_math_golden as mk
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "texture_sample_reference.npz"))
+    vol, uvw = mk.texture3d_inputs()
+    n = uvw.shape[0]
+    k = ir.KernelBuilder(block_size=(64, 1, 1))
+    heap, coords, out = k.arg_bindless(), k.arg_buffer(k.f324), k.arg_buffer(k.f324)
+
+    def body():
+        i = k.dispatch_id().x
+        c = coords.read(i / k.u(8))
+        out.write(i, k.call(Func.BindlessTexture3dSample, [heap, i % k.u(8), k.vec(k.f323, c.x, c.y, c.z)], k.f324))
+    k.body(body)
+    k.finish()
+    tex = device.create_tex3d("Rgba32f", vol.shape[2], vol.shape[1], vol.shape[0]); tex.copy_from(vol)
+    heap_arr = device.create_bindless_array(8)
+    for filt in (0, 1):
+        for address in range(4):
+            heap_arr.emplace_tex3d_async(filt * 4 + address, tex, filt, address)
+    heap_arr.update()
+    cb = device.create_buffer_from_array(uvw); ob = device.create_buffer(n * 8, 16, 16)
+    sh = device.create_shader(C.addressof(k.km), keep=k)
+    sh.dispatch((n * 8,), heap_arr, cb, ob)
+    got = ob.view().to_numpy(np.float32).reshape(n, 8, 4)
+    for filt in (0, 1):
+        for address in range(4):
+            want = g["tex3d_%d_%d" % (filt, address)]
+            x = got[:, filt * 4 + address]
+            assert np.array_equal(x.view(np.uint32), want.view(np.uint32)), "filter %d address %d: %d of %d differ, max %g" % (filt, address, (x != want).any(1).sum(), n, np.abs(x - want).max())
+    for r in (sh, cb, ob, heap_arr, tex):
+        r.destroy()
