@@ -91,9 +91,9 @@ struct CandidateFilter {
 };
 
 void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-                   TraceCounters *counters /* device, nullable */, LaunchCounter &lc);
+                   TraceCounters *counters /* device, nullable */, LaunchCounter &lc, unsigned grid_limit = 0 /* CTAs; 0 = every resident slot */);
 void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-               LaunchCounter &lc);
+               LaunchCounter &lc, unsigned grid_limit = 0);
 
 void ray_query(cudaStream_t s, const AccelView &a, const void *rays, void *committed_hits, uint64_t count, uint32_t mask, bool terminate_on_first,
                const CandidateFilter &filter, unsigned long long *work_counter, LaunchCounter &lc);

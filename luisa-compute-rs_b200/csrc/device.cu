@@ -1136,6 +1136,11 @@ static uint64_t host_chunk_max_rays() {
     return c;
 }
 
+static unsigned host_grid_limit() {  // LC_B200_HOST_GRID: CTAs per chunk launch of the host pipeline (0 = all resident slots)
+    static unsigned c = [] { const char *e = getenv("LC_B200_HOST_GRID"); return e ? (unsigned)strtoul(e, nullptr, 10) : 0u; }();
+    return c;
+}
+
 static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays, void *out, size_t out_stride, uint64_t count, uint32_t mask, bool any) {
     std::lock_guard<std::mutex> lk(d->mu);
     ensure_stage(d->stage_rays, d->stage_rays_cap, count * 32);
@@ -1172,8 +1177,8 @@ static void trace_host_pipelined(DeviceObj *d, AccelObj *a, const lcb_ray *rays,
         if (!(probe & 1)) CUDA_CHECK(cudaMemcpyAsync(d->stage_rays + first * 32, rays + first, n * 32, cudaMemcpyHostToDevice, d->copy_in));
         CUDA_CHECK(cudaEventRecord(ev[2 * c], d->copy_in));
         CUDA_CHECK(cudaStreamWaitEvent(k->stream, ev[2 * c], 0));
-        if (any) trace_any(k->stream, view, d->stage_rays + first * 32, (uint32_t *)(d->stage_out + first * out_stride), n, mask, k->work_counter, d->lc);
-        else trace_closest(k->stream, view, d->stage_rays + first * 32, d->stage_out + first * out_stride, n, mask, k->work_counter, nullptr, d->lc);
+        if (any) trace_any(k->stream, view, d->stage_rays + first * 32, (uint32_t *)(d->stage_out + first * out_stride), n, mask, k->work_counter, d->lc, host_grid_limit());
+        else trace_closest(k->stream, view, d->stage_rays + first * 32, d->stage_out + first * out_stride, n, mask, k->work_counter, nullptr, d->lc, host_grid_limit());
         CUDA_CHECK(cudaEventRecord(ev[2 * c + 1], k->stream));
         CUDA_CHECK(cudaStreamWaitEvent(d->copy_out, ev[2 * c + 1], 0));
         if (!(probe & 2)) CUDA_CHECK(cudaMemcpyAsync((uint8_t *)out + first * out_stride, d->stage_out + first * out_stride, n * out_stride, cudaMemcpyDeviceToHost, d->copy_out));

@@ -388,7 +388,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <int MODE, bool COUNTERS>
 void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-            TraceCounters *ctr, LaunchCounter &lc, const CandidateFilter &filter = CandidateFilter{0, 0.f, nullptr, nullptr}) {
+            TraceCounters *ctr, LaunchCounter &lc, const CandidateFilter &filter = CandidateFilter{0, 0.f, nullptr, nullptr}, unsigned grid_limit = 0) {
     constexpr bool ANY = MODE == kAny;
     if (a.flags & 1u) {  // curve instances present
         if (count == 0) return;
@@ -406,6 +406,7 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
     unsigned long long want = (count + kTraceThreads - 1) / kTraceThreads;
     unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
     if (grid > want) grid = want;
+    if (grid_limit && grid > grid_limit) grid = grid_limit;  // chunked host pipeline: leave CTA slots to the neighbouring chunk's launch
     if (grid == 0) return;
     // ray reordering for large batches
     const RaySortConfig rs = ray_sort_config();
@@ -445,14 +446,16 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
 }  // namespace
 
 void trace_closest(cudaStream_t s, const AccelView &a, const void *rays, void *hits, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-                   TraceCounters *counters, LaunchCounter &lc) {
-    if (counters) launch<kClosest, true>(s, a, rays, hits, count, mask, work_counter, counters, lc);
-    else launch<kClosest, false>(s, a, rays, hits, count, mask, work_counter, nullptr, lc);
+                   TraceCounters *counters, LaunchCounter &lc, unsigned grid_limit) {
+    const CandidateFilter none{0, 0.f, nullptr, nullptr};
+    if (counters) launch<kClosest, true>(s, a, rays, hits, count, mask, work_counter, counters, lc, none, grid_limit);
+    else launch<kClosest, false>(s, a, rays, hits, count, mask, work_counter, nullptr, lc, none, grid_limit);
 }
 
 void trace_any(cudaStream_t s, const AccelView &a, const void *rays, uint32_t *occluded, uint64_t count, uint32_t mask, unsigned long long *work_counter,
-               LaunchCounter &lc) {
-    launch<kAny, false>(s, a, rays, occluded, count, mask, work_counter, nullptr, lc);
+               LaunchCounter &lc, unsigned grid_limit) {
+    const CandidateFilter none{0, 0.f, nullptr, nullptr};
+    launch<kAny, false>(s, a, rays, occluded, count, mask, work_counter, nullptr, lc, none, grid_limit);
 }
 
 void ray_query(cudaStream_t s, const AccelView &a, const void *rays, void *committed_hits, uint64_t count, uint32_t mask, bool terminate_on_first,
