@@ -31,7 +31,10 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kTraceThreads = 128;
+#ifndef LCB_TRACE_THREADS
+#define LCB_TRACE_THREADS 128
+#endif
+constexpr int kTraceThreads = LCB_TRACE_THREADS;  // warps are independent (warp-local ray pools, no block barrier): any multiple of 32
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
 #define LCB_TRACE_MIN_BLOCKS 7
