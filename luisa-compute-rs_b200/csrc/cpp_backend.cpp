@@ -12,9 +12,8 @@
 // container only — the headers are not copied into this repository) and resolves `luisa::detail::allocator_*`,
 // `luisa::log_*`, `AST2IR::*`, `DeviceInterface::DeviceInterface` from the host program's lc-core / lc-runtime / lc-ir
 // at load time, exactly like every other LuisaCompute backend module.
-#include <atomic>
 #include <cstring>
-#include <mutex>
+#include <limits>
 
 #include <luisa/core/logging.h>
 #include <luisa/core/stl/vector.h>
