@@ -26,11 +26,11 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--spp", type=int, default=64, help="total samples per pixel (BASELINE: 1024)")
-    ap.add_argument("--spp-per-dispatch", type=int, default=32)
+    ap.add_argument("--spp-per-dispatch", type=int, default=16, help="16 x 4 streams: 7.16x at N = 8; 32 x 2 streams is 2 %% faster on one GPU (profiles/r01z_c5_path_trace_16x4.jsonl)")
     ap.add_argument("--depth", type=int, default=5)
     ap.add_argument("--nx", type=int, default=1582, help="terrain vertices per side (1582 -> 5.0M triangles per mesh, 50M instanced)")
     ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
-    ap.add_argument("--streams", type=int, default=2, help="the rank's tiles are split over this many streams so that the tail of one dispatch overlaps the next")
+    ap.add_argument("--streams", type=int, default=4, help="the rank's tiles are split over this many streams so that the tail of one dispatch overlaps the next")
     ap.add_argument("--chunk", type=int, default=1, help="tiles per round-robin run along the Morton curve (sharding.tiles_of_rank)")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's tiles in this single process (tuning aid; no gather)")
     ap.add_argument("--regenerate", action="store_true", help="path regeneration instead of the example's nested sample / bounce loops (same image; measured slower, profiles/r01v)")
