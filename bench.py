@@ -326,7 +326,8 @@ def main():
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                            "traffic_source": NCU_SUMMARY, "peak_source": how, "kernel": "k_trace<closest>", "algorithmic_bytes_per_launch": int(algo_bytes),
                            "nodes_per_ray": ctr["nodes_visited"] / n, "tris_per_ray": ctr["tris_tested"] / n,
-                           "note": "logical (L1/L2-inclusive) bytes per SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test",
+                           "note": "logical (L1/L2-inclusive) bytes per SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test; divided by the whole step "
+                                   "(k_trace + its k_refine pass, 14.06 + 0.34 ms in profiles/r01z_launches_summary.csv), so the fraction is a lower bound for k_trace alone",
                            "build_achieved_gbs": build_bytes / (min(build_ms) * 1e-3) / 1e9, "build_frac": build_bytes / (min(build_ms) * 1e-3) / 1e9 / peak}
         # ---- any-hit on the same batch (C3's shadow set), reported beside the headline ----
         hits_np = np.empty(n, dtype=lc.SurfaceHit)
