@@ -5,7 +5,7 @@
 // the backend module the Context finds and loads from its runtime directory is csrc/cpp_backend.cpp + liblc_b200.so.  The program
 // drives the path exactly as LC's C++ runtime would — Context::create_device("b200"), buffers, one CommandList carrying uploads +
 // MeshBuildCommand + AccelBuildCommand (+ a host callback), a second list after a PREFER_UPDATE vertex edit and an instance
-// modification — traces a ray grid through the batch entry point, downloads the hits with a BufferDownloadCommand and compares
+// modification, then a DSL kernel (create_shader from an ir::KernelModule + ShaderDispatchCommand) — traces a ray grid through the batch entry point, downloads the hits with a BufferDownloadCommand and compares
 // them bit for bit with the CPU oracle (liboracle.so) on the same scene.  Exit code 0 and a final "ok" line = pass.
 #include <atomic>
 #include <cstdio>
@@ -18,7 +18,10 @@
 #include <luisa/runtime/rhi/device_interface.h>
 #include <luisa/runtime/rhi/command.h>
 #include <luisa/runtime/command_list.h>
+#include <luisa/runtime/rhi/command_encoder.h>
 #include <luisa/rust/ir.hpp>
+
+#include "../ir_ref_build.hpp"
 
 #include "../../include/lc_b200_api.h"
 extern "C" {
@@ -167,6 +170,39 @@ int main(int argc, char **argv) {
         CHECK(n_hit > N / 4);
         CHECK(round == 0 ? n_inst1 > 0 : n_inst1 == 0);
         std::printf("round %d: %u rays, %u hits (%u on instance 1), closest + any identical to the oracle\n", round, N, n_hit, n_inst1);
+    }
+
+    // a DSL kernel through the C++ interface: an ir::KernelModule made of the reference's own IR records (ir_ref_build.hpp) ->
+    // DeviceInterface::create_shader(option, const ir::KernelModule *) -> the reference's ComputeDispatchCmdEncoder packs {buffer, uniform}
+    // into a ShaderDispatchCommand -> the adapter turns the argument buffer into lcb_argument records (uniform bytes handed out in place)
+    {
+        ShaderOption so{};
+        so.enable_fast_math = false;
+        auto shader = d->create_shader(so, ir_ref::build_axpy_module());
+        CHECK(shader.valid() && shader.block_size.x == 128u && shader.block_size.y == 1u);
+        constexpr uint32_t M = 1000, LIMIT = 777;
+        std::vector<float> xs(M), ys(M, -1.f);
+        for (uint32_t i = 0; i < M; i++) xs[i] = 0.25f * (float)i - 3.f;
+        auto fb = d->create_buffer(&bytes, M * 4, nullptr);
+        uint32_t limit = LIMIT;
+        ComputeDispatchCmdEncoder enc{shader.handle, 2, 16};
+        enc.encode_buffer(fb.handle, 0, M * 4);
+        enc.encode_uniform(&limit, sizeof(limit));
+        enc.set_dispatch_size(make_uint3(M, 1u, 1u));
+        auto list = CommandList::create();
+        list << luisa::make_unique<BufferUploadCommand>(fb.handle, 0, M * 4, xs.data())
+             << std::move(enc).build()
+             << luisa::make_unique<BufferDownloadCommand>(fb.handle, 0, M * 4, ys.data());
+        limit = 0;   // the command owns a copy of the uniform bytes: changing the source after encoding must not matter
+        d->dispatch(stream.handle, std::move(list));
+        d->synchronize_stream(stream.handle);
+        for (uint32_t i = 0; i < M; i++) {
+            const float want = i < LIMIT ? xs[i] * 2.0f + 1.0f : xs[i];
+            if (ys[i] != want) { std::fprintf(stderr, "shader dispatch: a[%u] = %a, expected %a\n", i, ys[i], want); return 1; }
+        }
+        d->destroy_shader(shader.handle);
+        d->destroy_buffer(fb.handle);
+        std::printf("shader: reference-built ir::KernelModule -> create_shader -> ShaderDispatchCommand{buffer, uniform}: %u of %u elements updated, rest untouched\n", LIMIT, M);
     }
 
     // events through the C++ interface

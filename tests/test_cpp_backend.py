@@ -56,9 +56,11 @@ def test_reference_context_loads_the_module_and_there_is_no_cpu_fallback():
 @needs_host
 def test_cpp_host_program_matches_the_oracle_on_b200():
     """Context::create_device("b200") -> DeviceInterface virtuals -> CommandList{uploads, MeshBuildCommand, AccelBuildCommand, callback}
-    -> batch trace -> BufferDownloadCommand, twice (FORCE_BUILD, then PREFER_UPDATE + instance made invisible): closest hits (inst, prim,
+    -> batch trace -> BufferDownloadCommand (then a DSL kernel: create_shader + ShaderDispatchCommand), twice (FORCE_BUILD, then PREFER_UPDATE + instance made invisible): closest hits (inst, prim,
     bary, t) and any-hit flags bit-identical to the CPU oracle."""
     r = subprocess.run([HOST], cwd=HOST_DIR, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "cpp_host_check ok" in r.stdout
     assert "round 1:" in r.stdout and "(0 on instance 1)" in r.stdout
+    # create_shader(const ir::KernelModule *) + ShaderDispatchCommand{buffer, uniform} packed by the reference's own ComputeDispatchCmdEncoder
+    assert "shader: reference-built ir::KernelModule" in r.stdout and "777 of 1000 elements updated" in r.stdout
