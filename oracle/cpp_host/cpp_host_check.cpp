@@ -19,6 +19,8 @@
 #include <luisa/runtime/rhi/command.h>
 #include <luisa/runtime/command_list.h>
 #include <luisa/runtime/rhi/command_encoder.h>
+#include <luisa/runtime/rhi/sampler.h>
+#include <luisa/runtime/rhi/pixel.h>
 #include <luisa/rust/ir.hpp>
 
 #include "../ir_ref_build.hpp"
@@ -203,6 +205,39 @@ int main(int argc, char **argv) {
         d->destroy_shader(shader.handle);
         d->destroy_buffer(fb.handle);
         std::printf("shader: reference-built ir::KernelModule -> create_shader -> ShaderDispatchCommand{buffer, uniform}: %u of %u elements updated, rest untouched\n", LIMIT, M);
+    }
+
+    // textures and bindless arrays through the C++ commands: upload -> device -> download of a Float4 image and of an RGBA8 image,
+    // a BindlessArrayUpdateCommand that emplaces a buffer + a sampled texture and removes them again
+    {
+        constexpr uint32_t TW = 8, TH = 4;
+        auto tex = d->create_texture(PixelFormat::RGBA32F, 2u, TW, TH, 1u, 1u, false, false);
+        auto tex8 = d->create_texture(PixelFormat::RGBA8UNorm, 2u, TW, TH, 1u, 1u, false, false);
+        CHECK(tex.valid() && tex8.valid());
+        std::vector<float> src(TW * TH * 4), dst(TW * TH * 4, -1.f);
+        std::vector<uint8_t> src8(TW * TH * 4), dst8(TW * TH * 4, 0xEE);
+        for (size_t i = 0; i < src.size(); i++) { src[i] = 0.5f * (float)i - 7.f; src8[i] = (uint8_t)(i * 37u + 11u); }
+        auto heap = d->create_bindless_array(4);
+        CHECK(heap.valid());
+        using Mod = BindlessArrayUpdateCommand::Modification;
+        luisa::vector<Mod> emplace, remove;
+        emplace.emplace_back(2u, Mod::Buffer::emplace(vbuf.handle, 0u), Mod::Texture::emplace(tex.handle, Sampler{Sampler::Filter::LINEAR_POINT, Sampler::Address::REPEAT}), Mod::Texture{});
+        remove.emplace_back(2u, Mod::Buffer::remove(), Mod::Texture::remove(), Mod::Texture{});
+        auto list = CommandList::create();
+        list << luisa::make_unique<TextureUploadCommand>(tex.handle, PixelStorage::FLOAT4, 0u, make_uint3(TW, TH, 1u), src.data())
+             << luisa::make_unique<TextureUploadCommand>(tex8.handle, PixelStorage::BYTE4, 0u, make_uint3(TW, TH, 1u), src8.data())
+             << luisa::make_unique<BindlessArrayUpdateCommand>(heap.handle, std::move(emplace))
+             << luisa::make_unique<TextureDownloadCommand>(tex.handle, PixelStorage::FLOAT4, 0u, make_uint3(TW, TH, 1u), dst.data())
+             << luisa::make_unique<TextureDownloadCommand>(tex8.handle, PixelStorage::BYTE4, 0u, make_uint3(TW, TH, 1u), dst8.data())
+             << luisa::make_unique<BindlessArrayUpdateCommand>(heap.handle, std::move(remove));
+        d->dispatch(stream.handle, std::move(list));
+        d->synchronize_stream(stream.handle);
+        CHECK(std::memcmp(src.data(), dst.data(), src.size() * 4) == 0);
+        CHECK(std::memcmp(src8.data(), dst8.data(), src8.size()) == 0);
+        d->destroy_bindless_array(heap.handle);
+        d->destroy_texture(tex.handle);
+        d->destroy_texture(tex8.handle);
+        std::printf("textures: Float4 and RGBA8 images round-trip through TextureUpload / TextureDownload; bindless emplace + remove accepted\n");
     }
 
     // events through the C++ interface

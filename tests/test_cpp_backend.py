@@ -64,3 +64,4 @@ def test_cpp_host_program_matches_the_oracle_on_b200():
     assert "round 1:" in r.stdout and "(0 on instance 1)" in r.stdout
     # create_shader(const ir::KernelModule *) + ShaderDispatchCommand{buffer, uniform} packed by the reference's own ComputeDispatchCmdEncoder
     assert "shader: reference-built ir::KernelModule" in r.stdout and "777 of 1000 elements updated" in r.stdout
+    assert "textures: Float4 and RGBA8 images round-trip" in r.stdout   # TextureUpload / TextureDownload / BindlessArrayUpdate commands
