@@ -1,6 +1,7 @@
 #!/bin/bash
-# full verification on one B200: GPU parity tests, smoke, default bench
+# full verification on one B200: GPU parity tests (incl. the C++ host program and the reference-pinned builtin vectors), smoke, default bench, reference arm
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-300
