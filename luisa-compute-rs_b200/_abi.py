@@ -279,7 +279,7 @@ EXPORTED_SYMBOLS = [
     "lc_b200_trace_any_host", "lc_b200_instance_transform", "lc_b200_instance_user_id", "lc_b200_instance_visibility_mask",
     "lc_b200_mesh_stats", "lc_b200_accel_stats", "lc_b200_trace_closest_counted", "lc_b200_stream_native",
     "lc_b200_buffer_native", "lc_b200_device_ordinal", "lc_b200_kernel_launch_count", "lc_b200_version", "lc_b200_make_ir_type",
-    "lc_b200_ray_query", "lc_b200_example_path_tracer", "lc_b200_ir_lower_source", "lc_b200_shader_compile_check", "lc_b200_ir_layout_json", "lc_b200_set_builder",
+    "lc_b200_ray_query", "lc_b200_example_path_tracer", "lc_b200_ir_lower_source", "lc_b200_shader_compile_check", "lc_b200_ir_layout_json", "lc_b200_set_builder", "lc_b200_set_lowering",
 ]
 
 
@@ -356,6 +356,8 @@ def load_library(path=None):
     lib.lc_b200_shader_compile_check.restype = C.c_int
     lib.lc_b200_set_builder.argtypes = [C.c_int]
     lib.lc_b200_set_builder.restype = C.c_int
+    lib.lc_b200_set_lowering.argtypes = [C.c_int]
+    lib.lc_b200_set_lowering.restype = C.c_int
     lib.lc_b200_ir_layout_json.argtypes = []
     lib.lc_b200_ir_layout_json.restype = C.c_char_p
     if path is None:

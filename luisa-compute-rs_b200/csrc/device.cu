@@ -830,7 +830,7 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
     const LoweredKernel &k = shader_lowered(sh);
     if (c.args_count != k.args.size()) fatal("ShaderDispatch: %zu arguments given, the kernel takes %zu (runtime.rs:1517)", c.args_count, k.args.size());
     std::vector<uint8_t> block(k.param_bytes, 0);
-    HostLaunch launch{{c.dispatch_size[0], c.dispatch_size[1], c.dispatch_size[2]}, 0};
+    HostLaunch launch{{c.dispatch_size[0], c.dispatch_size[1], c.dispatch_size[2]}, 0, nullptr, 0};
     memcpy(block.data(), &launch, sizeof(launch));
     auto put_buffer = [&](const ParamSlot &p, uint64_t handle, size_t offset, size_t size) {
         BufferObj *b = as<BufferObj>(handle);
@@ -875,8 +875,7 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
                 break;
         }
     }
-    try { shader_launch(sh, s->stream, block.data(), c.dispatch_size); } catch (const std::exception &e) { fatal("ShaderDispatch: %s", e.what()); }
-    d->lc.count++;
+    try { d->lc.count += shader_launch(sh, s->stream, block.data(), c.dispatch_size, s->work_counter); } catch (const std::exception &e) { fatal("ShaderDispatch: %s", e.what()); }
 }
 
 // ---- out-of-scope slots: loud failure -------------------------------------------------------------

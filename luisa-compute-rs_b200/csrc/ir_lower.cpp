@@ -14,9 +14,25 @@
 //   * captures are kernel parameters bound at create_shader time, arguments are bound per dispatch (cpp.rs:1928-1990).
 // Differences by design: kernel parameters travel as one by-value struct (lc_params) whose layout is computed here AND
 // static_assert-ed inside the generated source; Switch lowers to an if-chain so that Break keeps its loop meaning.
+//
+// Wavefront lowering (the default for kernels that call RayTracingTraceClosest / TraceAny from their own body): the kernel becomes a
+// persistent-thread state machine.  Every thread slot of the grid loops { take a work item (= one dispatch id) from a warp-local pool;
+// run the kernel body until it needs a ray traced; park the ray and yield }, and between those user phases the warp runs the shared
+// if-if traversal loop of trace_device.cuh (wave_traverse — the same loop as the batch kernel k_trace) over all parked lanes together.
+// A trace call is therefore a suspension point: `wave_begin(...); lc_pc = K; goto lc_yield; case K: value = result;` inside one
+// `switch (lc_pc)` that encloses the whole body (case labels inside the loops and ifs of the body, Duff's-device style), which is why
+// in this mode every SSA value is declared at function scope without an initialiser and assigned where it is defined, GetElementPtr
+// nodes are substituted textually, and Return is `goto lc_done`.  Lanes that reach the end of the body take the next dispatch id at
+// once, so a path tracer's lanes never idle while their neighbours finish longer paths, and the traversal — the dominant cost — always
+// runs with every parked lane of the warp converged.  Kernels that use block-level features whose meaning depends on the CUDA thread
+// mapping (shared memory, SynchronizeBlock, warp intrinsics), several accels, curve bases, or that only trace from callables / RayQuery
+// callbacks keep the direct lowering (one dispatch id per CUDA thread, trace_one per call).  LC_B200_LOWERING=direct|wavefront overrides.
 #include "shader.h"
+#include "trace_device.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -27,6 +43,8 @@
 #include <unordered_set>
 
 namespace lcb {
+// 0 = decide per kernel, 1 = always direct, 2 = wavefront wherever it is legal (LC_B200_LOWERING, lc_b200_set_lowering)
+std::atomic<int> g_lowering{[] { const char *e = getenv("LC_B200_LOWERING"); return !e ? 0 : (strcmp(e, "direct") == 0 ? 1 : (strcmp(e, "wavefront") == 0 ? 2 : 0)); }()};
 namespace {
 
 using namespace ir;
@@ -225,6 +243,15 @@ struct Globals {
     std::string shared_decls;
 };
 
+// What decides between the direct and the wavefront lowering (header comment): gathered over the kernel body and every callable it reaches.
+struct ModuleScan {
+    int trace_sites = 0;         // RayTracingTraceClosest / TraceAny calls in the kernel's own body, outside RayQuery callbacks
+    bool block_features = false; // SynchronizeBlock, warp intrinsics
+    uint32_t curve_bases = 0;
+    std::unordered_set<NodeRef> accels;  // accel operands of those trace sites
+    std::unordered_set<const void *> seen_callables;
+};
+
 struct PhiMap {
     std::vector<NodeRef> phis;
     std::unordered_map<const BasicBlock *, std::vector<NodeRef>> per_block;
@@ -269,6 +296,11 @@ struct FunctionEmitter {
     bool in_generic_loop = false;
     bool is_callable = false;
     int nest = 0;  // depth of enclosing If / Switch / loop / RayQuery blocks
+    bool wave = false;        // wavefront lowering of the kernel body (header comment)
+    int lambda_depth = 0;     // inside RayQuery callbacks (C++ lambdas): no suspension points there
+    int wave_sites = 0;       // suspension points emitted so far (case labels 1..)
+    int break_serial = 0;
+    std::string break_flag = "loop_break";
 
     explicit FunctionEmitter(Globals &gl) : g(gl) {}
 
@@ -367,7 +399,18 @@ struct FunctionEmitter {
             case Const::Float16: e = prim_literal(P_Float16, (const uint8_t *)&c.f16_bits); break;
             default: fail("unknown constant tag " + std::to_string(c.tag));
         }
-        line("const " + ts + " " + v + " = " + e + ";");
+        if (wave) decls += "    const " + ts + " " + v + " = " + e + ";\n";  // function scope: visible from every resume point
+        else line("const " + ts + " " + v + " = " + e + ";");
+    }
+
+    // one SSA value: `const T v = e;` where it is defined — or, in a wavefront-lowered body, a function-scope variable assigned there
+    void define(NodeRef n, const std::string &ts, const std::string &e) {
+        if (wave) { decls += "    " + ts + " " + ref(n) + ";\n"; line(ref(n) + " = " + e + ";"); }
+        else line("const " + ts + " " + ref(n) + " = " + e + ";");
+    }
+    void declare_mutable(NodeRef n, const std::string &ts, const std::string &e) {
+        if (wave) { decls += "    " + ts + " " + ref(n) + ";\n"; line(ref(n) + " = " + e + ";"); }
+        else line(ts + " " + ref(n) + " = " + e + ";");
     }
 
     std::string join(const std::vector<std::string> &a, size_t from = 0) {
@@ -400,7 +443,7 @@ struct FunctionEmitter {
         std::vector<std::string> a;
         for (NodeRef r : args) a.push_back(ref(r));
         auto need = [&](size_t k) { if (a.size() != k) fail(std::string(kFuncNames[f.tag]) + " expects " + std::to_string(k) + " operands, got " + std::to_string(a.size())); };
-        auto value = [&](const std::string &e) { if (is_void) line(e + ";"); else line("const " + ts + " " + ref(n) + " = " + e + ";"); };
+        auto value = [&](const std::string &e) { if (is_void) line(e + ";"); else define(n, ts, e); };
         auto bin = [&](const char *op) { need(2); value(a[0] + " " + op + " " + a[1]); };
         auto fn = [&](const char *name) { value(std::string(name) + "(" + join(a) + ")"); };
         if (f.tag < 0 || f.tag >= Func::COUNT) fail("unknown Func discriminant " + std::to_string(f.tag));
@@ -524,12 +567,12 @@ struct FunctionEmitter {
             case Func::Assert: need(1); g.messages.push_back(slice_to_string(f.message)); line("lc_assert(" + a[0] + ", " + std::to_string(g.messages.size() - 1) + ");"); break;
             case Func::Unreachable:
                 g.messages.push_back(slice_to_string(f.message));
-                if (!is_void) line(ts + " " + ref(n) + "{};");
+                if (!is_void) declare_mutable(n, ts, ts + "{}");
                 line("lc_trap(\"unreachable\", " + std::to_string(g.messages.size() - 1) + ");");
                 break;
-            case Func::ThreadId: value("lc_thread_id()"); break;
-            case Func::BlockId: value("lc_block_id()"); break;
-            case Func::DispatchId: value("lc_dispatch_id()"); break;
+            case Func::ThreadId: value("lc_ids.thread"); break;
+            case Func::BlockId: value("lc_ids.block"); break;
+            case Func::DispatchId: value("lc_ids.dispatch"); break;
             case Func::DispatchSize: value("lc_uint3(p.launch.dispatch_size[0], p.launch.dispatch_size[1], p.launch.dispatch_size[2])"); break;
 
             case Func::Load: need(1); value(a[0]); break;
@@ -543,12 +586,23 @@ struct FunctionEmitter {
             case Func::ExtractElement: value(access_chain(a[0], ntype(args[0]), args, 1)); break;
             case Func::InsertElement: {  // (aggregate, value, indices...)
                 const std::string v = ref(n);
+                if (wave) {
+                    decls += "    " + ts + " " + v + ";\n";
+                    line(v + " = " + a[0] + ";");
+                    line(access_chain(v, ntype(args[0]), args, 2) + " = " + a[1] + ";");
+                    break;
+                }
                 line(ts + " " + v + "_m = " + a[0] + ";");
                 line(access_chain(v + "_m", ntype(args[0]), args, 2) + " = " + a[1] + ";");
                 line("const " + ts + " &" + v + " = " + v + "_m;");
                 break;
             }
-            case Func::GetElementPtr: line(ts + " &" + ref(n) + " = " + access_chain(a[0], ntype(args[0]), args, 1) + ";"); break;
+            case Func::GetElementPtr:
+                // a C++ reference where it is defined; in a wavefront-lowered body references cannot be declared ahead, so the access
+                // expression itself stands for the node (its index operands are SSA values: it means the same wherever it is used)
+                if (wave) names[n] = access_chain(a[0], ntype(args[0]), args, 1);
+                else line(ts + " &" + ref(n) + " = " + access_chain(a[0], ntype(args[0]), args, 1) + ";");
+                break;
             case Func::Struct: value(ts + "{" + join(a) + "}"); break;
             case Func::Array: value(ts + "{{" + join(a) + "}}"); break;
             case Func::Vec: case Func::Vec2: case Func::Vec3: case Func::Vec4: value(ts + "(" + join(a) + ")"); break;
@@ -607,8 +661,20 @@ struct FunctionEmitter {
             case Func::AtomicFetchMax: value("lc_atomic_fetch_max(&" + atomic_target(args, 1) + ", " + a[a.size() - 1] + ")"); break;
 
             // rows 5, 6, 8 of SURVEY.md §8a — cpp.rs:1334-1400
-            case Func::RayTracingTraceClosest: need(3); value("lc_bit_cast<" + ts + ">(lc_trace_closest(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + "))"); break;
-            case Func::RayTracingTraceAny: need(3); value("lc_trace_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ")"); break;
+            case Func::RayTracingTraceClosest: case Func::RayTracingTraceAny: {
+                need(3);
+                const bool any = f.tag == Func::RayTracingTraceAny;
+                if (wave && lambda_depth == 0) {
+                    // suspension point: park the ray, yield to the warp's traversal loop, resume at `case K` with the result in lc_w
+                    const std::string K = std::to_string(++wave_sites);
+                    line("if (lc_wave_begin(lc_w, lc_s, " + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ", " + (any ? "true" : "false") + ")) { lc_pc = " + K + "u; goto lc_yield; }");
+                    line("case " + K + "u:;");
+                    if (any) value("lc_wave_any(lc_w)");
+                    else value("lc_bit_cast<" + ts + ">(lc_wave_closest(lc_w, lc_s, " + a[0] + "))");
+                } else if (any) value("lc_trace_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ")");
+                else value("lc_bit_cast<" + ts + ">(lc_trace_closest(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + "))");
+                break;
+            }
             case Func::RayTracingInstanceTransform: need(2); value("lc_accel_instance_transform(" + a[0] + ", " + a[1] + ")"); break;
             case Func::RayTracingInstanceVisibilityMask: need(2); value("lc_accel_instance_visibility_mask(" + a[0] + ", " + a[1] + ")"); break;
             case Func::RayTracingInstanceUserId: need(2); value("lc_accel_instance_user_id(" + a[0] + ", " + a[1] + ")"); break;
@@ -617,8 +683,8 @@ struct FunctionEmitter {
             case Func::RayTracingSetInstanceTransform: need(3); line("lc_set_instance_transform(" + join(a) + ");"); break;
             case Func::RayTracingSetInstanceOpacity: need(3); line("lc_set_instance_opacity(" + join(a) + ");"); break;
             // row 7: RayQuery objects (cpp.rs:1401-1472).  The object is a mutable local; Instruction::RayQuery runs the traversal.
-            case Func::RayTracingQueryAll: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_all(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
-            case Func::RayTracingQueryAny: need(3); line("lc_ray_query_state " + ref(n) + " = lc_ray_query_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ");"); break;
+            case Func::RayTracingQueryAll: need(3); declare_mutable(n, "lc_ray_query_state", "lc_ray_query_all(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ")"); break;
+            case Func::RayTracingQueryAny: need(3); declare_mutable(n, "lc_ray_query_state", "lc_ray_query_any(" + a[0] + ", lc_bit_cast<lc_ray_rec>(" + a[1] + "), " + a[2] + ")"); break;
             case Func::RayQueryWorldSpaceRay: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".ray)"); break;
             case Func::RayQueryTriangleCandidateHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".cur_triangle)"); break;
             case Func::RayQueryProceduralCandidateHit: need(1); value("lc_bit_cast<" + ts + ">(" + a[0] + ".cur_procedural)"); break;
@@ -629,7 +695,7 @@ struct FunctionEmitter {
 
             case Func::Callable: {
                 const std::string name = callable_name(f.callable);
-                std::string call = name + "(p";
+                std::string call = name + "(p, lc_ids";
                 for (const auto &s : a) call += ", " + s;
                 value(call + ")");
                 break;
@@ -670,13 +736,14 @@ struct FunctionEmitter {
             case Instruction::Uniform: case Instruction::Shared: case Instruction::Argument: case Instruction::UserData: case Instruction::Comment:
                 break;
             case Instruction::Invalid: fail("Instruction::Invalid inside a block");
-            case Instruction::Local: line(tname(ntype(n)) + " " + ref(n) + " = " + ref(ins->local.init) + ";"); break;
+            case Instruction::Local: declare_mutable(n, tname(ntype(n)), ref(ins->local.init)); break;
             case Instruction::Const: emit_const(n); break;
             case Instruction::Update: line(ref(ins->update.var) + " = " + ref(ins->update.value) + ";"); break;
             case Instruction::Call: emit_call(n); break;
             case Instruction::Phi: decls += "    " + tname(ntype(n)) + " " + ref(n) + "{};\n"; break;
             case Instruction::Return:
-                if (ins->return_) line("return " + ref(ins->return_) + ";"); else line("return;");
+                if (wave && lambda_depth == 0) line("goto lc_done;");  // this dispatch id is finished; the lane takes the next one
+                else if (ins->return_) line("return " + ref(ins->return_) + ";"); else line("return;");
                 break;
             case Instruction::Loop: {  // do { body } while (cond)  — cpp.rs:1683-1699
                 const bool old = in_generic_loop; in_generic_loop = false;
@@ -691,23 +758,28 @@ struct FunctionEmitter {
             }
             case Instruction::GenericLoop: {
                 const bool old = in_generic_loop; in_generic_loop = true;
+                const std::string old_flag = break_flag;
                 line("for (;;) {");
                 indent++; nest++;
-                line("bool loop_break = false;");
+                if (wave) {  // function scope: a resume point inside the loop body must not jump past an initialised declaration
+                    break_flag = "lc_brk" + std::to_string(break_serial++);
+                    decls += "    bool " + break_flag + ";\n";
+                    line(break_flag + " = false;");
+                } else line("bool loop_break = false;");
                 emit_block_content(ins->generic_loop.prepare.ptr);
                 line("if (!(" + ref(ins->generic_loop.cond) + ")) break;");
                 line("do");
                 emit_block(ins->generic_loop.body.ptr);
                 line("while (false);");
-                line("if (loop_break) break;");
+                line("if (" + break_flag + ") break;");
                 emit_block(ins->generic_loop.update.ptr);
                 indent--; nest--;
                 line("}");
-                in_generic_loop = old;
+                in_generic_loop = old; break_flag = old_flag;
                 break;
             }
             case Instruction::Break:
-                if (in_generic_loop) line("loop_break = true;");
+                if (in_generic_loop) line(break_flag + " = true;");
                 line("break;");
                 break;
             case Instruction::Continue: line(in_generic_loop ? "break;" : "continue;"); break;
@@ -762,11 +834,13 @@ struct FunctionEmitter {
                 fail("autodiff scopes must be removed by the frontend's transform pipeline before create_shader");
             case Instruction::RayQuery: {  // cpp.rs:1807-1830: the two candidate blocks become callbacks of the traversal
                 const bool old = in_generic_loop; in_generic_loop = false;
+                lambda_depth++;
                 line("lc_ray_query(" + ref(ins->ray_query.ray_query) + ", [&]()");
                 emit_block(ins->ray_query.on_triangle_hit.ptr);
                 line(", [&]()");
                 emit_block(ins->ray_query.on_procedural_hit.ptr);
                 line(");");
+                lambda_depth--;
                 in_generic_loop = old;
                 break;
             }
@@ -784,7 +858,7 @@ std::string FunctionEmitter::callable_name(const Arc<CallableModule> &arc) {
     if (cm->cpu_custom_ops.len) fail("CpuCustomOp callables cannot run on the GPU");
     FunctionEmitter ce(g);
     ce.is_callable = true;
-    std::string params = "const lc_params &p";
+    std::string params = "const lc_params &p, const lc_ids_t &lc_ids";
     for (size_t i = 0; i < cm->args.len; i++) {
         const NodeRef an = cm->args[i];
         const Instruction *ai = node(an)->instruction.get();
@@ -810,6 +884,46 @@ std::string FunctionEmitter::callable_name(const Arc<CallableModule> &arc) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void scan_block(const BasicBlock *bb, ModuleScan &sc, bool kernel_level) {
+    for_each_node(bb, [&](NodeRef n) {
+        const Instruction *ins = node(n)->instruction.get();
+        if (!ins) return;
+        switch (ins->tag) {
+            case Instruction::Call: {
+                const Func &f = ins->call.func;
+                if (f.tag == Func::RayTracingTraceClosest || f.tag == Func::RayTracingTraceAny) {
+                    if (kernel_level && ins->call.args.len == 3) { sc.trace_sites++; sc.accels.insert(ins->call.args[0]); }
+                } else if (f.tag == Func::SynchronizeBlock || f.tag == Func::WarpLaneId || (f.tag >= Func::WarpIsFirstActiveLane && f.tag <= Func::WarpReadFirstLane)) {
+                    sc.block_features = true;
+                } else if (f.tag == Func::Callable) {
+                    const CallableModule *cm = f.callable.get();
+                    if (cm && sc.seen_callables.insert(f.callable.inner).second) {
+                        sc.curve_bases |= cm->module.curve_basis_set;
+                        scan_block(cm->module.entry.ptr, sc, false);
+                    }
+                }
+                break;
+            }
+            case Instruction::If: scan_block(ins->if_.true_branch.ptr, sc, kernel_level); scan_block(ins->if_.false_branch.ptr, sc, kernel_level); break;
+            case Instruction::Loop: scan_block(ins->loop.body.ptr, sc, kernel_level); break;
+            case Instruction::GenericLoop:
+                scan_block(ins->generic_loop.prepare.ptr, sc, kernel_level); scan_block(ins->generic_loop.body.ptr, sc, kernel_level);
+                scan_block(ins->generic_loop.update.ptr, sc, kernel_level);
+                break;
+            case Instruction::Switch:
+                scan_block(ins->switch_.default_.ptr, sc, kernel_level);
+                for (const auto &c : ins->switch_.cases) scan_block(c.block.ptr, sc, kernel_level);
+                break;
+            case Instruction::RayQuery:  // callbacks are C++ lambdas: traces inside them are direct calls
+                scan_block(ins->ray_query.on_triangle_hit.ptr, sc, false); scan_block(ins->ray_query.on_procedural_hit.ptr, sc, false);
+                break;
+            default: break;
+        }
+    });
+}
+
+int lowering_override() { return g_lowering.load(); }
 
 }  // namespace
 
@@ -877,7 +991,17 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
         g.shared_decls += "    __shared__ " + g.types.name(node(s)->type_.get()) + " " + nm + ";\n";
     }
 
+    // direct or wavefront lowering (header comment)
+    ModuleScan scan;
+    scan.curve_bases = km->module.curve_basis_set;
+    scan_block(km->module.entry.ptr, scan, true);
+    const bool wave = lowering_override() != 1 && scan.trace_sites > 0 && !scan.block_features && km->shared.len == 0 && scan.accels.size() == 1 &&
+                      scan.curve_bases == 0;
+    fe.wave = wave;
+    out.wave = wave;
+
     collect_phis(km->module.entry.ptr, fe.phis);
+    if (wave) fe.indent = 4;
     fe.emit_block_content(km->module.entry.ptr);
 
     std::ostringstream src;
@@ -887,15 +1011,56 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
     src << "// generated by lc_b200 (ir_lower.cpp) — do not edit\n" << (g.curve_bases ? "#define LCB_CURVES 1\n" : "") << "#include \"lc_device_lib.cuh\"\n\n"
         << g.types.defs << "\n" << params.str() << asserts.str()
         << "static_assert(sizeof(lc_params) == " << align_up(off, max_align) << ", \"parameter block size\");\n\n"
-        << g.callable_defs
-        << "extern \"C\" __global__ void __launch_bounds__(" << (out.block_size[0] * out.block_size[1] * out.block_size[2]) << ") lc_kernel(const lc_params p) {\n"
-        << g.shared_decls
-        << "    // partial edge blocks are clipped to dispatch_size (cpu/stream.rs:384-404); lc_warp_mask = this warp's live lanes\n"
-        << "    const lc_uint3 lc_id = lc_dispatch_id();\n"
-        << "    const bool lc_live = lc_id.x < p.launch.dispatch_size[0] && lc_id.y < p.launch.dispatch_size[1] && lc_id.z < p.launch.dispatch_size[2];\n"
-        << "    const uint32_t lc_warp_mask = __ballot_sync(0xffffffffu, lc_live);\n"
-        << "    if (!lc_live) return;\n"
-        << fe.decls << fe.body << "}\n";
+        << g.callable_defs;
+    if (!wave) {
+        src << "extern \"C\" __global__ void __launch_bounds__(" << (out.block_size[0] * out.block_size[1] * out.block_size[2]) << ") lc_kernel(const lc_params p) {\n"
+            << g.shared_decls
+            << "    // partial edge blocks are clipped to dispatch_size (cpu/stream.rs:384-404); lc_warp_mask = this warp's live lanes\n"
+            << "    const lc_ids_t lc_ids{lc_thread_id(), lc_block_id(), lc_dispatch_id()};\n"
+            << "    const lc_uint3 lc_id = lc_ids.dispatch;\n"
+            << "    const bool lc_live = lc_id.x < p.launch.dispatch_size[0] && lc_id.y < p.launch.dispatch_size[1] && lc_id.z < p.launch.dispatch_size[2];\n"
+            << "    const uint32_t lc_warp_mask = __ballot_sync(0xffffffffu, lc_live);\n"
+            << "    if (!lc_live) return;\n"
+            << fe.decls << fe.body << "}\n";
+    } else {
+        // persistent-thread state machine (header comment).  A work item is one CUDA-thread position of the grid the direct lowering
+        // would launch (block-major, then x-fastest inside the block), so that the items of a warp's pool are neighbours in the
+        // dispatch exactly as the threads of a block are; positions outside dispatch_size are skipped (cpu/stream.rs:384-404).
+        const char *min_blocks = getenv("LC_B200_WAVE_MIN_BLOCKS");
+        src << "extern \"C\" __global__ void __launch_bounds__(" << kWaveThreads << ", " << (min_blocks ? atoi(min_blocks) : 4) << ") lc_kernel(const lc_params p) {\n"
+            << "    __shared__ lcb::WaveShared lc_s;\n"
+            << "    uint2 lc_deep_stack[lcb::kWaveLocalStack];\n"
+            << "    lcb::WaveLane lc_w;\n"
+            << "    lcb::WavePool lc_pool{0ull, 0ull, false};\n"
+            << "    lc_ids_t lc_ids;\n"
+            << "    unsigned long long lc_item = 0ull;\n"
+            << "    uint32_t lc_pc = 0u;\n"
+            << "    int lc_state = lcb::kWaveNeedsWork;\n"
+            << fe.decls
+            << "    for (;;) {\n"
+            << "        lcb::wave_fetch(lc_pool, lc_state, lc_item, p.launch.work_items, p.launch.work_counter);\n"
+            << "        if (lc_state == lcb::kWaveNeedsWork) { lc_pc = 0u; }\n"
+            << "        const uint32_t lc_dead = __ballot_sync(0xffffffffu, lc_state == lcb::kWaveDead);\n"
+            << "        if (lc_dead == 0xffffffffu) break;\n"
+            << "        if (lc_state == lcb::kWaveReady) {\n"
+            << "            switch (lc_pc) {\n"
+            << "            case 0u:\n"
+            << "                if (!lc_wave_ids<" << out.block_size[0] << ", " << out.block_size[1] << ", " << out.block_size[2] << ">(p.launch, lc_item, lc_ids)) goto lc_done;\n"
+            << fe.body
+            << "            }\n"
+            << "        lc_done:\n"
+            << "            lc_state = lcb::kWaveNeedsWork; lc_pc = 0u;\n"
+            << "            goto lc_resume;\n"
+            << "        lc_yield:\n"
+            << "            lc_state = lcb::kWaveTraversing;\n"
+            << "        lc_resume:;\n"
+            << "        }\n"
+            << "        // lanes that finished their dispatch id take the next one before the warp goes back to traversing\n"
+            << "        if (!lc_pool.exhausted && __any_sync(0xffffffffu, lc_state == lcb::kWaveNeedsWork)) continue;\n"
+            << "        lcb::wave_traverse(lc_w, lc_state, " << g.resources[*scan.accels.begin()] << ".view, lc_s, lc_deep_stack, lc_dead | __ballot_sync(0xffffffffu, lc_state == lcb::kWaveNeedsWork), (int)p.launch.yield_min);\n"
+            << "    }\n"
+            << "}\n";
+    }
     out.source = src.str();
     out.messages = g.messages;
 }
@@ -903,6 +1068,11 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
 }  // namespace lcb
 
 // ---- layout self-description (compared with tests/golden/ir_layout_reference.json) ---------------------------------------------
+extern "C" __attribute__((visibility("default"))) int lc_b200_set_lowering(int mode) {
+    if (mode < 0 || mode > 2) mode = 0;
+    return lcb::g_lowering.exchange(mode);
+}
+
 extern "C" __attribute__((visibility("default"))) const char *lc_b200_ir_layout_json(void) {
     namespace M = lcb::ir;
     static std::string s = [] {

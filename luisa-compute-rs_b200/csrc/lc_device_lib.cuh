@@ -375,10 +375,28 @@ template <class T> __device__ inline T lc_warp_prefix_product(uint32_t m, T v) {
 template <class D, class S, int N> __device__ inline lc_vec<D, N> lc_vec_cast(lc_vec<S, N> v) { lc_vec<D, N> r; LC_LOOP r[i] = static_cast<D>(v[i]); return r; }
 
 // ---- dispatch geometry ---------------------------------------------------------------------------------------------------
-struct lc_launch { uint32_t dispatch_size[3]; uint32_t pad; };
+struct lc_launch { uint32_t dispatch_size[3]; uint32_t yield_min; unsigned long long *work_counter; unsigned long long work_items; };  // shader.h HostLaunch
+static_assert(sizeof(lc_launch) == 32, "launch record is mirrored in shader.h");
 __device__ inline lc_uint3 lc_thread_id() { return lc_uint3(threadIdx.x, threadIdx.y, threadIdx.z); }
 __device__ inline lc_uint3 lc_block_id() { return lc_uint3(blockIdx.x, blockIdx.y, blockIdx.z); }
 __device__ inline lc_uint3 lc_dispatch_id() { return lc_uint3(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y, blockIdx.z * blockDim.z + threadIdx.z); }
+// thread_id / block_id / dispatch_id of the DSL as the kernel body and its callables see them.  Direct lowering: the CUDA thread's own;
+// wavefront lowering: those of the work item the lane is running (lc_wave_ids).
+struct lc_ids_t { lc_uint3 thread, block, dispatch; };
+// work item -> ids: items enumerate the grid the direct lowering would launch, block-major and x-fastest inside a block (the order of
+// a CUDA block's threads), so consecutive items are neighbours in the dispatch.  false: the position lies outside dispatch_size.
+template <uint32_t BX, uint32_t BY, uint32_t BZ> __device__ inline bool lc_wave_ids(const lc_launch &l, unsigned long long item, lc_ids_t &ids) {
+    constexpr uint32_t kBlock = BX * BY * BZ;
+    const unsigned long long b = item / kBlock;
+    const uint32_t t = (uint32_t)(item - b * kBlock);
+    const uint32_t gx = (l.dispatch_size[0] + BX - 1) / BX, gy = (l.dispatch_size[1] + BY - 1) / BY;
+    const unsigned long long bz = b / ((unsigned long long)gx * gy);
+    const uint32_t bxy = (uint32_t)(b - bz * ((unsigned long long)gx * gy));
+    ids.block = lc_uint3(bxy % gx, bxy / gx, (uint32_t)bz);
+    ids.thread = lc_uint3(t % BX, (t / BX) % BY, t / (BX * BY));
+    ids.dispatch = lc_uint3(ids.block.x * BX + ids.thread.x, ids.block.y * BY + ids.thread.y, ids.block.z * BZ + ids.thread.z);
+    return ids.dispatch.x < l.dispatch_size[0] && ids.dispatch.y < l.dispatch_size[1] && ids.dispatch.z < l.dispatch_size[2];
+}
 __device__ inline void lc_assume(bool) {}
 __device__ inline void lc_trap(const char *what, int id) { printf("[lc_b200 kernel] %s (message %d) at block (%u,%u,%u) thread (%u,%u,%u)\n", what, id, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y, threadIdx.z); __trap(); }
 __device__ inline void lc_assert(bool c, int id) { if (!c) lc_trap("assertion failed", id); }
@@ -520,6 +538,18 @@ __device__ inline lc_hit_rec lc_trace_closest(const lc_accel &a, const lc_ray_re
 }
 __device__ inline bool lc_trace_any(const lc_accel &a, const lc_ray_rec &r, uint32_t mask) {
     return lcb::trace_one<true>(a.view, make_float4(r.o[0], r.o[1], r.o[2], r.tmin), make_float4(r.d[0], r.d[1], r.d[2], r.tmax), mask).inst != lcb::kNone;
+}
+// Wavefront lowering (ir_lower.cpp header): a trace call parks its ray in the lane's traversal state and yields; the result is read
+// back where the body resumes.  Same records, same arithmetic and the same barycentrics as lc_trace_closest / lc_trace_any above.
+__device__ inline bool lc_wave_begin(lcb::WaveLane &w, lcb::WaveShared &s, const lc_accel &a, const lc_ray_rec &r, uint32_t mask, bool any) {
+    return lcb::wave_begin(w, s, a.view, make_float4(r.o[0], r.o[1], r.o[2], r.tmin), make_float4(r.d[0], r.d[1], r.d[2], r.tmax), mask, any);
+}
+__device__ inline bool lc_wave_any(const lcb::WaveLane &w) { return w.hit_inst != lcb::kNone; }
+__device__ inline lc_hit_rec lc_wave_closest(const lcb::WaveLane &w, const lcb::WaveShared &s, const lc_accel &a) {
+    const lcb::DeviceHit h = lcb::wave_closest_result(w, s, a.view);
+    lc_hit_rec out;
+    out.inst = h.inst; out.prim = h.prim; out.u = h.u; out.v = h.v; out.t = h.t; out.pad = 0u;
+    return out;
 }
 // RayQuery objects (defs::RayQuery, cpu_kernel_defs/src/lib.rs:127-141; accessors cpu_resource.h:318-396).  CommittedHit is
 // {inst, prim, bary, hit_type (0 miss / 1 triangle / 2 procedural), committed_ray_t} (defs:68-77); a query that commits nothing

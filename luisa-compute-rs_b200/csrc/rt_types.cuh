@@ -112,7 +112,10 @@ static_assert(sizeof(AccelView) == 56, "AccelView is mirrored in lc_accel / Host
 
 constexpr uint32_t kCurveSubdiv = 8;  // pieces per cubic curve segment (trace_device.cuh "curves")
 constexpr int kMaxWideDepth = 40;   // builder fails loudly beyond this; traversal stack is sized for it
-constexpr int kTraversalStack = 96; // >= TLAS depth + 3 + BLAS depth
+// Entries of a traversal stack.  Mandatory pushes: one node group per level + three per instance entry (<= 2 * kMaxWideDepth + 3 = 83);
+// the if-if loop may also postpone one primitive group per level, and stops doing so at kPostponeLimit (trace_device.cuh) so that the two
+// together never exceed the stack.
+constexpr int kTraversalStack = 128;
 
 __host__ __device__ inline int float_to_ordered(float f) {
     int i;

@@ -5,6 +5,7 @@
 // dispatch_size clipped per thread (cpu/stream.rs:330-440).  NVRTC is loaded lazily with dlopen so that the library itself
 // has no link-time dependency on it; a missing libnvrtc fails loudly at the first create_shader.
 #include "shader.h"
+#include "trace_device.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +77,7 @@ struct ShaderObj {
     std::vector<char> cubin;
     cudaLibrary_t library = nullptr;
     cudaKernel_t kernel = nullptr;
+    unsigned resident_ctas = 0;  // wavefront-lowered kernels: SMs x CTAs per SM (occupancy query at the first launch)
     std::string name;
 };
 
@@ -149,15 +151,42 @@ void shader_destroy(ShaderObj *s) {
 
 const LoweredKernel &shader_lowered(const ShaderObj *s) { return s->lowered; }
 
-void shader_launch(ShaderObj *s, cudaStream_t stream, const void *params, const uint32_t dispatch_size[3]) {
+// LC_B200_WAVE_YIELD: how many lanes of a warp must be able to continue in user code before the traversal loop hands control back
+static int wave_yield_min() {
+    const char *e = getenv("LC_B200_WAVE_YIELD");  // read per launch: a tuning knob for sweeps
+    const int y = e ? atoi(e) : 8;
+    return y < 1 ? 1 : (y > 32 ? 32 : y);
+}
+
+int shader_launch(ShaderObj *s, cudaStream_t stream, void *params, const uint32_t dispatch_size[3], unsigned long long *work_counter) {
     if (!s->kernel) throw std::runtime_error("shader was created with compile_only and cannot be dispatched");
     const uint32_t *b = s->lowered.block_size;
-    if (dispatch_size[0] == 0 || dispatch_size[1] == 0 || dispatch_size[2] == 0) return;
+    if (dispatch_size[0] == 0 || dispatch_size[1] == 0 || dispatch_size[2] == 0) return 0;
     dim3 grid((dispatch_size[0] + b[0] - 1) / b[0], (dispatch_size[1] + b[1] - 1) / b[1], (dispatch_size[2] + b[2] - 1) / b[2]);
     dim3 block(b[0], b[1], b[2]);
-    void *args[1] = {const_cast<void *>(params)};
+    if (s->lowered.wave) {
+        // persistent grid: every resident thread slot pulls dispatch ids (in the block-major order of the grid above) from the counter
+        if (s->resident_ctas == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)s->kernel, kWaveThreads, 0) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+            s->resident_ctas = (unsigned)(sms * per_sm);
+        }
+        HostLaunch *launch = reinterpret_cast<HostLaunch *>(params);
+        launch->work_items = (unsigned long long)grid.x * grid.y * grid.z * b[0] * b[1] * b[2];
+        launch->work_counter = work_counter;
+        launch->yield_min = (uint32_t)wave_yield_min();
+        const unsigned long long want = (launch->work_items + kWaveThreads - 1) / kWaveThreads;
+        grid = dim3((unsigned)(want < s->resident_ctas ? want : s->resident_ctas), 1, 1);
+        block = dim3(kWaveThreads, 1, 1);
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("work counter reset failed: ") + cudaGetErrorString(e));
+    }
+    void *args[1] = {params};
     cudaError_t e = cudaLaunchKernel((const void *)s->kernel, grid, block, args, 0, stream);
     if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+    return 1;
 }
 
 }  // namespace lcb

@@ -25,6 +25,7 @@ struct LoweredKernel {
     std::vector<ParamSlot> args;      // in KernelModule.args order
     size_t param_bytes = 0;           // sizeof(lc_params)
     uint32_t block_size[3] = {1, 1, 1};
+    bool wave = false;                // wavefront lowering: persistent grid of kWaveThreads-thread CTAs pulling dispatch ids from a work counter
     std::vector<std::string> messages;  // assert / unreachable texts, indexed by the id the kernel prints
 };
 
@@ -37,9 +38,10 @@ struct HostTextureArg { void *data; uint32_t width, height, depth; uint32_t stor
 struct HostBindlessSlot { void *buffer; uint64_t buffer_size; HostTextureArg tex2d, tex3d; };
 struct HostBindlessArg { const HostBindlessSlot *slots; uint64_t count; };
 struct HostAccelArg { AccelView view; InstanceRec *instances_rw; uint32_t *dirty; };  // dirty: set by kernels that edit the instance table
-struct HostLaunch { uint32_t dispatch_size[3]; uint32_t pad; };
+// yield_min / work_counter / work_items: wavefront-lowered kernels only (ir_lower.cpp header; trace_device.cuh wave_fetch / wave_traverse)
+struct HostLaunch { uint32_t dispatch_size[3]; uint32_t yield_min; unsigned long long *work_counter; unsigned long long work_items; };
 static_assert(sizeof(HostBufferArg) == 16 && sizeof(HostTextureArg) == 32 && sizeof(HostBindlessSlot) == 80 && sizeof(HostBindlessArg) == 16 &&
-                  sizeof(HostAccelArg) == 72 && sizeof(HostLaunch) == 16,
+                  sizeof(HostAccelArg) == 72 && sizeof(HostLaunch) == 32,
               "parameter records are mirrored byte for byte in lc_device_lib.cuh");
 
 // NVRTC + module loading (shader.cu).  compile_only: stop after NVRTC (usable without a GPU; create_shader's compile_only option).
@@ -48,6 +50,8 @@ ShaderObj *shader_create(const ir::KernelModule *km, bool fast_math, bool compil
 void shader_destroy(ShaderObj *);
 const LoweredKernel &shader_lowered(const ShaderObj *);
 // params: a filled lc_params image of shader_lowered().param_bytes bytes
-void shader_launch(ShaderObj *, cudaStream_t stream, const void *params, const uint32_t dispatch_size[3]);
+// work_counter: an 8-byte device word owned by the stream (zeroed in stream order before a wavefront-lowered kernel starts).
+// Returns the number of kernels launched.
+int shader_launch(ShaderObj *, cudaStream_t stream, void *params, const uint32_t dispatch_size[3], unsigned long long *work_counter);
 
 }  // namespace lcb

@@ -74,6 +74,17 @@ __device__ __forceinline__ bool candidate_commits(const CandidateFilter &f, uint
     }
 }
 
+// Rays and hits stream through once per launch while the BVH is re-read by every ray: their loads and stores carry the streaming
+// (evict-first) cache operator so that they do not push nodes and triangles out of L2 (round-1 capture: 7.5 GB of DRAM traffic per
+// launch against 1 GB compulsory).  -DLCB_NO_STREAM_HINTS restores plain accesses for A/B runs.
+#ifdef LCB_NO_STREAM_HINTS
+#define LCB_LD_STREAM(P) __ldg(P)
+#define LCB_ST_STREAM(P, V) (*(P) = (V))
+#else
+#define LCB_LD_STREAM(P) __ldcs(P)
+#define LCB_ST_STREAM(P, V) __stcs(P, V)
+#endif
+
 template <int MODE, bool COUNTERS>
 __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(AccelView acc, const float4 *__restrict__ rays, void *__restrict__ out,
                                                                                unsigned long long count, uint32_t mask, unsigned long long *work_counter,
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     const unsigned long long mine = pool_next + __popc(m_idle & lt_mask);
                     if (!has_ray && mine < pool_end) {
                         ray_idx = order ? (unsigned long long)__ldg(order + mine) : mine;
-                        const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                        const float4 ra = LCB_LD_STREAM(rays + 2 * ray_idx), rb = LCB_LD_STREAM(rays + 2 * ray_idx + 1);
                         setup_world(r, ra, rb);
                         tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
                         hit_inst = kNone; hit_prim = kNone; hit_slot = 0;
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
             // A lane whose group is not exhausted by this one test postpones the rest (pushes it) when it still has
             // node work: on incoherent rays, returning to the wide node step with the whole warp beats draining the
             // group with a few stragglers (tune sweep in profiles/r01_trace_tune_sweep.txt).
-            if (Gt.y != 0u && (G.y & 0xff000000u) != 0u) { LCB_PUSH(Gt) Gt.y = 0u; }
+            if (Gt.y != 0u && (G.y & 0xff000000u) != 0u && sp < kPostponeLimit) { LCB_PUSH(Gt) Gt.y = 0u; }
         }
 
         // ---- tail: lanes that ran out of work pop the next group, or retire ------------------------------------------
@@ -245,12 +256,12 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
             }
             if (retire) {
                 if (ANY) {
-                    reinterpret_cast<uint32_t *>(out)[ray_idx] = hit_inst != kNone ? 1u : 0u;
+                    LCB_ST_STREAM(reinterpret_cast<uint32_t *>(out) + ray_idx, hit_inst != kNone ? 1u : 0u);
                 } else {
                     uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
-                    o[0] = make_uint2(hit_inst, hit_prim);
+                    LCB_ST_STREAM(o, make_uint2(hit_inst, hit_prim));
                     // barycentrics are formed by k_refine; the pad word carries the winning PackedTri slot to it
-                    o[2] = make_uint2(__float_as_uint(hit_inst != kNone ? tbest : ray_tmax), hit_slot);
+                    LCB_ST_STREAM(o + 2, make_uint2(__float_as_uint(hit_inst != kNone ? tbest : ray_tmax), hit_slot));
                 }
                 has_ray = false;
             }
@@ -297,18 +308,18 @@ template <bool COMMITTED>
 __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__restrict__ rays, uint2 *__restrict__ hits, unsigned long long count) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const uint2 h0 = hits[3 * i], h2 = hits[3 * i + 2];
+    const uint2 h0 = LCB_LD_STREAM(hits + 3 * i), h2 = LCB_LD_STREAM(hits + 3 * i + 2);
     if (h0.x == kNone) {
-        hits[3 * i + 1] = make_uint2(0u, 0u);
+        LCB_ST_STREAM(hits + 3 * i + 1, make_uint2(0u, 0u));
         // a RayQuery that commits nothing leaves its zero-initialised CommittedHit (cpu_resource.h:320-331): hit_type Miss, t = 0
-        hits[3 * i + 2] = COMMITTED ? make_uint2(0u /* HitType::Miss */, 0u) : make_uint2(h2.x, 0u);
+        LCB_ST_STREAM(hits + 3 * i + 2, COMMITTED ? make_uint2(0u /* HitType::Miss */, 0u) : make_uint2(h2.x, 0u));
         return;
     }
     const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + h0.x);
     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
     const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + h2.y);
-    const float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
+    const float4 ra = LCB_LD_STREAM(rays + 2 * i), rb = LCB_LD_STREAM(rays + 2 * i + 1);
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     RaySetup r;
     transform_ray(r, ra, rb, m0, m1, m2);
@@ -321,8 +332,8 @@ __global__ void __launch_bounds__(256) k_refine(AccelView acc, const float4 *__r
             u = __fmul_rn(V, rdet); v = __fmul_rn(W, rdet);
         }
     }
-    hits[3 * i + 1] = make_uint2(__float_as_uint(u), __float_as_uint(v));
-    hits[3 * i + 2] = COMMITTED ? make_uint2(1u /* HitType::Triangle */, h2.x) : make_uint2(h2.x, 0u);
+    LCB_ST_STREAM(hits + 3 * i + 1, make_uint2(__float_as_uint(u), __float_as_uint(v)));
+    LCB_ST_STREAM(hits + 3 * i + 2, COMMITTED ? make_uint2(1u /* HitType::Triangle */, h2.x) : make_uint2(h2.x, 0u));
 }
 
 // ---- ray reordering ---------------------------------------------------------------------------------------------------

@@ -484,4 +484,189 @@ __device__ __forceinline__ DeviceHit trace_one(const AccelView &acc, const float
     return trace_one_impl<ANY, false>(acc, ra, rb, mask, false, hook);
 }
 
+
+// ---- wavefront traversal for kernels that trace from their own threads -----------------------------------------------------------
+// The persistent-thread form of a lowered DSL kernel (ir_lower.cpp "wavefront lowering"): the kernel body is a resumable state machine,
+// a trace call parks the lane's ray here (wave_begin) and yields, and the warp then runs the SAME if-if loop with postponing as the batch
+// kernel k_trace (trace.cu) over the lanes that are parked — all of them converged in the wide node step, whatever point of the user
+// code each came from.  The loop hands control back (wave_traverse returns) as soon as `yield_min` lanes could make progress in user
+// code (their traversal ended, or they are waiting for a new work item), so finished lanes are refilled with new rays while the others
+// keep their traversal state in registers — the work refill of k_trace, with the kernel body in the place of the ray fetch.
+// Stack: kWaveSmemStack levels per thread in shared memory laid out [level][thread], deeper levels in the caller's local array.
+// The world-space ray is parked in shared memory too (it is needed again when an instance is left and for the barycentrics).
+constexpr int kWaveThreads = 128;     // CTA size of a wavefront-lowered kernel (4 independent warps)
+constexpr int kWaveSmemStack = 16;
+constexpr int kWaveLocalStack = kTraversalStack - kWaveSmemStack;
+constexpr int kWaveChunk = 128;       // work items taken per global atomic
+// Postponed primitive groups are optional pushes; the mandatory ones are one node group per level plus three per instance entry
+// (<= 2 * kMaxWideDepth + 3).  Postponing stops where the two together could exceed the stack.
+constexpr int kPostponeLimit = kTraversalStack - (2 * kMaxWideDepth + 3) - 1;
+static_assert(kPostponeLimit >= 24, "traversal stack too small for postponing");
+
+struct WaveShared {
+    uint2 stack[kWaveSmemStack * kWaveThreads];
+    float4 ray[2 * kWaveThreads];  // [0..T): origin | tmin, [T..2T): direction | tmax
+};
+
+struct WaveLane {
+    RaySetup r;
+    float tmin, tbest, ray_tmax;
+    uint32_t hit_inst, hit_prim, hit_slot, cur_inst, mask;
+    const WideNode *nodes;
+    const PackedTri *tris;
+    uint2 G, Gt;
+    int sp;
+    bool any;
+};
+
+// park one ray: returns false when there is nothing to traverse (empty accel) — the lane's result is then already a miss
+__device__ __forceinline__ bool wave_begin(WaveLane &w, WaveShared &S, const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask, bool any) {
+    S.ray[threadIdx.x] = ra; S.ray[kWaveThreads + threadIdx.x] = rb;
+    setup_world(w.r, ra, rb);
+    w.tmin = ra.w; w.tbest = rb.w; w.ray_tmax = rb.w;
+    w.hit_inst = kNone; w.hit_prim = kNone; w.hit_slot = 0u;
+    w.cur_inst = kNone; w.nodes = acc.tlas_nodes; w.tris = nullptr;
+    w.sp = 0; w.mask = mask; w.any = any;
+    w.G = make_uint2(0u, acc.tlas_nodes ? 0x80000000u : 0u);
+    w.Gt = make_uint2(0u, 0u);
+    return acc.tlas_nodes != nullptr;
+}
+
+// `state` per lane: kWaveTraversing lanes take part; a lane whose ray is finished becomes kWaveReady.  `m_dead`: lanes that will never
+// have anything to do again (warp-uniform).  Returns when no lane traverses any more or when yield_min lanes are ready.
+constexpr int kWaveNeedsWork = 0, kWaveReady = 1, kWaveTraversing = 2, kWaveDead = 3;
+__device__ __forceinline__ void wave_traverse(WaveLane &w, int &state, const AccelView &acc, WaveShared &S, uint2 *l_stack, uint32_t m_dead, int yield_min) {
+    uint2 *const my_stack = S.stack + threadIdx.x;
+#define LCW_PUSH(E)                                                          \
+    {                                                                        \
+        if (w.sp < kWaveSmemStack) my_stack[w.sp * kWaveThreads] = (E);      \
+        else l_stack[w.sp - kWaveSmemStack] = (E);                           \
+        w.sp++;                                                              \
+    }
+    for (;;) {
+        const uint32_t m_trav = __ballot_sync(0xffffffffu, state == kWaveTraversing);
+        if (m_trav == 0u) break;
+        if (32 - __popc(m_trav | m_dead) >= yield_min) break;
+        const bool has_ray = state == kWaveTraversing;
+        // ---- node step ----------------------------------------------------------------------------------------------------------
+        if (has_ray && w.Gt.y == 0u && (w.G.y & 0xff000000u) != 0u) {
+            const uint32_t bit = 31u - __clz(w.G.y);
+            w.G.y &= ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ w.r.octinv;
+            const uint32_t rel = __popc(w.G.y & 0xffu & ((1u << slot) - 1u));
+            const WideNode *node = w.nodes + (w.G.x + rel);
+            if (w.G.y & 0xff000000u) LCW_PUSH(w.G)
+            uint32_t child_base, prim_base, imask;
+            const uint32_t hits = intersect_node(node, w.r, w.tmin, w.tbest, child_base, prim_base, imask);
+            w.G = make_uint2(child_base, (hits & 0xff000000u) | imask);
+            w.Gt = make_uint2(prim_base, hits & 0x00ffffffu);
+        }
+        // ---- primitive step: one triangle (or one instance entry) -------------------------------------------------------------------
+        if (has_ray && w.Gt.y != 0u) {
+            const uint32_t bit = __ffs(w.Gt.y) - 1;
+            w.Gt.y &= w.Gt.y - 1;
+            if (w.cur_inst != kNone) {
+                const float4 *tp = reinterpret_cast<const float4 *>(w.tris + (w.Gt.x + bit));
+                const U8 t01 = ldg256(tp);
+                const float4 v2 = __ldg(tp + 2);
+                const float4 v0 = make_float4(__uint_as_float(t01.v[0]), __uint_as_float(t01.v[1]), __uint_as_float(t01.v[2]), __uint_as_float(t01.v[3]));
+                const float4 v1 = make_float4(__uint_as_float(t01.v[4]), __uint_as_float(t01.v[5]), __uint_as_float(t01.v[6]), 0.f);
+                float t, V, W, det;
+                if (canonical_triangle(w.r, w.tmin, w.ray_tmax, v0, v1, v2, t, V, W, det)) {
+                    const uint32_t prim = __float_as_uint(v0.w);
+                    if (w.any) {
+                        w.hit_inst = w.cur_inst; w.Gt.y = 0u; w.G.y = 0u; w.sp = 0;  // retires in the tail below
+                    } else {
+                        const bool better = t < w.tbest || w.hit_inst == kNone ||
+                                            (t == w.tbest && (w.cur_inst < w.hit_inst || (w.cur_inst == w.hit_inst && prim < w.hit_prim)));
+                        if (better) { w.tbest = t; w.hit_inst = w.cur_inst; w.hit_prim = prim; w.hit_slot = w.Gt.x + bit; }
+                    }
+                }
+            } else {
+                const uint32_t inst = __ldg(acc.tlas_prims + w.Gt.x + bit);
+                const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + inst);
+                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rec) + 4);  // visibility, user_id, flags, pad
+                // procedural (bit 2) and curve (bit 3) instances are not entered: trace_closest / trace_any without a RayQuery and
+                // without a curve basis skip them (trace_one_impl<ANY, false, ..., false>)
+                if ((meta.x & w.mask) != 0u && (meta.z & 12u) == 0u) {
+                    if (w.Gt.y) LCW_PUSH(w.Gt)
+                    if (w.G.y & 0xff000000u) LCW_PUSH(w.G)
+                    LCW_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
+                    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+                    const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+                    w.nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+                    w.tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                    const float4 wo = make_float4(w.r.ox, w.r.oy, w.r.oz, 0.f), wd = make_float4(w.r.dx, w.r.dy, w.r.dz, 0.f);
+                    setup_object(w.r, wo, wd, m0, m1, m2);
+                    w.cur_inst = inst;
+                    w.G = make_uint2(0u, 0x80000000u);
+                    w.Gt = make_uint2(0u, 0u);
+                }
+            }
+            if (w.Gt.y != 0u && (w.G.y & 0xff000000u) != 0u && w.sp < kPostponeLimit) { LCW_PUSH(w.Gt) w.Gt.y = 0u; }
+        }
+        // ---- tail: pop the next group, or finish ---------------------------------------------------------------------------------------
+        if (has_ray && w.Gt.y == 0u && (w.G.y & 0xff000000u) == 0u) {
+            for (;;) {
+                if (w.sp == 0) { state = kWaveReady; break; }
+                --w.sp;
+                const uint2 e = w.sp < kWaveSmemStack ? my_stack[w.sp * kWaveThreads] : l_stack[w.sp - kWaveSmemStack];
+                if (e.y & 0xff000000u) { w.G = e; break; }
+                if (e.y != 0u) { w.Gt = e; break; }
+                w.cur_inst = kNone; w.nodes = acc.tlas_nodes; w.tris = nullptr;  // sentinel: the instance is exhausted
+                if (w.sp == 0) { state = kWaveReady; break; }
+                setup_world(w.r, S.ray[threadIdx.x], S.ray[kWaveThreads + threadIdx.x]);
+            }
+        }
+    }
+#undef LCW_PUSH
+}
+
+// result of a finished closest-hit traversal in the SurfaceHit convention, barycentrics as trace_one_impl reports them (refine_bary)
+__device__ __forceinline__ DeviceHit wave_closest_result(const WaveLane &w, const WaveShared &S, const AccelView &acc) {
+    const float4 ra = S.ray[threadIdx.x], rb = S.ray[kWaveThreads + threadIdx.x];
+    DeviceHit h{w.hit_inst, w.hit_prim, 0.f, 0.f, rb.w, 0u};
+    if (w.hit_inst == kNone) return h;
+    h.t = w.tbest; h.kind = 1u;
+    const float4 *rec = reinterpret_cast<const float4 *>(acc.instances + w.hit_inst);
+    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+    const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
+    const float4 *tp = reinterpret_cast<const float4 *>(reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z) + w.hit_slot);
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    RaySetup r;
+    transform_ray(r, ra, rb, m0, m1, m2);
+    if (!refine_bary(r, v0, v1, v2, h.u, h.v)) {
+        finish_setup(r);
+        float t, V, W, det;
+        if (canonical_triangle(r, -INFINITY, INFINITY, v0, v1, v2, t, V, W, det)) {
+            const float rdet = __frcp_rn(det);
+            h.u = __fmul_rn(V, rdet); h.v = __fmul_rn(W, rdet);
+        }
+    }
+    return h;
+}
+
+// Warp-local pool of work items (the ray pool of k_trace): lanes in state kWaveNeedsWork receive consecutive items, topped up with one
+// global atomic per kWaveChunk items; when the dispatch is exhausted they become kWaveDead.
+struct WavePool { unsigned long long next, end; bool exhausted; };
+__device__ __forceinline__ void wave_fetch(WavePool &pool, int &state, unsigned long long &item, unsigned long long total, unsigned long long *counter) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        const uint32_t m_need = __ballot_sync(0xffffffffu, state == kWaveNeedsWork);
+        if (m_need == 0u) return;
+        if (pool.next == pool.end) {
+            if (pool.exhausted) { if (state == kWaveNeedsWork) state = kWaveDead; return; }
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)kWaveChunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total) { pool.exhausted = true; continue; }
+            pool.next = base; pool.end = base + kWaveChunk < total ? base + kWaveChunk : total;
+        }
+        const unsigned long long mine = pool.next + __popc(m_need & ((1u << lane) - 1u));
+        if (state == kWaveNeedsWork && mine < pool.end) { item = mine; state = kWaveReady; }
+        const unsigned long long adv = pool.next + __popc(m_need);
+        pool.next = adv < pool.end ? adv : pool.end;
+    }
+}
+
 }  // namespace lcb

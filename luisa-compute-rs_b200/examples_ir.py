@@ -85,6 +85,34 @@ def raytracing_rays(width, height):
     return rays
 
 
+def trace_buffer_kernel(any_hit=False, mask=0xFF, block_size=(64, 1, 1)):
+    """The smallest DSL kernel on the hot path — what a luisa-compute-rs user writes to trace a buffer of rays (config C3):
+
+        Kernel::<fn(Buffer<Ray>, Buffer<SurfaceHit>, Accel)>::new(&device, &track!(|rays, hits, accel| {
+            let i = dispatch_id().x;
+            hits.write(i, accel.intersect(rays.read(i), mask));      // rtx.rs:774-795 -> Func::RayTracingTraceClosest
+        }))
+
+    (`any_hit`: Buffer<bool> stored as u32, accel.intersect_any -> Func::RayTracingTraceAny, rtx.rs:796-817).  Block size: the frontend's
+    default for kernels that do not call set_block_size (runtime/kernel.rs:506)."""
+    k = ir.KernelBuilder(block_size=block_size)
+    _, ray_ty, hit_ty = common_types(k)
+    rays = k.arg_buffer(ray_ty)
+    out = k.arg_buffer(k.u32 if any_hit else hit_ty)
+    accel = k.arg_accel()
+
+    def body():
+        i = k.dispatch_id().x
+        ray = rays.read(i)
+        if any_hit:
+            out.write(i, accel.trace_any(ray, mask).select(k.u(1), k.u(0)))
+        else:
+            out.write(i, accel.trace_closest(ray, mask, hit_ty))
+    k.body(body)
+    k.finish()
+    return k
+
+
 CBOX_MATERIALS = [(0.725, 0.710, 0.680)] * 3 + [(0.140, 0.450, 0.091), (0.630, 0.065, 0.050)] + [(0.725, 0.710, 0.680)] * 2 + [(0.0, 0.0, 0.0)]
 SPP_PER_DISPATCH = 32
 FRAC_1_PI = float(np.float32(0.318309886183790671537767526745028724))

@@ -563,6 +563,12 @@ class Module:
     def dispatch_id(self):
         return self.call(Func.DispatchId, [], self.u323)
 
+    def thread_id(self):
+        return self.call(Func.ThreadId, [], self.u323)
+
+    def block_id(self):
+        return self.call(Func.BlockId, [], self.u323)
+
     def dispatch_size(self):
         return self.call(Func.DispatchSize, [], self.u323)
 

@@ -56,6 +56,24 @@ class DeviceScene:
         rb.destroy(); ob.destroy()
         return occ
 
+    def trace_dsl(self, rays, any_hit=False, mask=0xFF, block_size=(64, 1, 1)):
+        """the reference call path: a DSL kernel `hits.write(i, accel.intersect(rays.read(i), mask))` as an ir::KernelModule through
+        create_shader + ShaderDispatch (examples_ir.trace_buffer_kernel)"""
+        import ctypes as C
+        from luisa_compute_rs_b200 import examples_ir
+        n = rays.shape[0]
+        rb = self.device.create_buffer(max(n, 1), 32, 16)
+        ob = self.device.create_buffer(max(n, 1), 4, 4) if any_hit else self.device.create_buffer(max(n, 1), 24, 8)
+        out = np.zeros(n, dtype=np.uint32 if any_hit else lc.SurfaceHit)
+        k = examples_ir.trace_buffer_kernel(any_hit=any_hit, mask=mask, block_size=block_size)
+        sh = self.device.create_shader(C.addressof(k.km), keep=k)
+        if n:
+            rb.view(0, n).copy_from(rays)
+            sh.dispatch((n, 1, 1), rb, ob, self.accel)
+            ob.view(0, n).copy_to(out)
+        sh.destroy(); rb.destroy(); ob.destroy()
+        return out
+
     def destroy(self):
         self.accel.destroy()
         for m in self.meshes:
