@@ -3,8 +3,14 @@
 
 Metric (BASELINE.json): Mrays/s closest-hit on incoherent rays, with BVH build ms beside it, as absolute numbers and as a
 fraction of the measured HBM roofline.  Workload at every N: C3 of BASELINE.json — a 1 000 000-triangle random soup and
-16 777 216 incoherent rays per GPU (`configs[2]`, the configuration the metric is quoted on; configs[1], the Cornell path
-tracer, needs the IR->CUDA lowering that SURVEY.md §8f ranks "next").  A step = one trace_closest pass over the ray batch.
+16 777 216 incoherent rays per GPU (`configs[2]`, the configuration the metric is quoted on).  A step = one pass of the reference
+call path over the ray batch: the DSL kernel `hits.write(i, accel.intersect(rays.read(i), mask))` (rtx.rs:774-795) as an
+ir::KernelModule through DeviceInterface.create_shader + dispatch(ShaderDispatch) — lowered by the device to its persistent
+wavefront form (csrc/ir_lower.cpp).  `value` times that with rays resident in HBM; `e2e` times the same kernel with pinned HOST
+buffers, BufferUpload / ShaderDispatch / BufferDownload commands pipelined over three streams with timeline events — only
+DeviceInterface calls.  The batch entry points (lc_b200_trace_closest, ..._host) are reported beside them as extra keys, and so are
+config C2 (Cornell path tracer through create_shader) and config C5 (4K path tracing over the 10-instance 50 M-triangle scene,
+tiles sharded over the ranks, render + NCCL framebuffer gather in one timed region).
 
   python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N > 1)
   python bench.py --impl reference ...                   the CPU arm: the oracle port on all host cores, bounded sample
@@ -31,7 +37,7 @@ N_TRIS = 1_000_000
 N_RAYS = 1 << 24
 METRIC = "closest_hit_incoherent_mrays_per_s"
 UNIT = "Mrays/s"
-WORKLOAD = "C3: 1M-triangle random soup (seed 0x5EED0001), 16Mi incoherent rays per GPU (seed 0x5EED0002+rank), trace_closest"
+WORKLOAD = "C3: 1M-triangle random soup (seed 0x5EED0001), 16Mi incoherent rays per GPU (seed 0x5EED0002+rank), closest hit through create_shader + ShaderDispatch"
 
 
 def measured_peaks():
@@ -146,12 +152,12 @@ def run_reference(args, rank):
     }))
 
 
-NCU_SUMMARY = "profiles/r01t_k_trace_ncu_full_summary.csv"
+NCU_SUMMARY = "profiles/r02_c3_lc_kernel_ncu_full_summary.csv"
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_trace<closest> per launch on this workload, from the committed
-    `ncu --set full` capture of `bench.py --profile` (bytes); None if the summary is not there."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the timed kernel (the wavefront-lowered DSL kernel, `lc_kernel`) per launch on
+    this workload, from the committed `ncu --set full` capture of `bench.py --profile` (bytes); None if the summary is not there."""
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         tot = 0.0
@@ -206,6 +212,89 @@ def dsl_path_tracer_leg(dev, lc, scenes, torch, _ext):
     return out
 
 
+def e2e_reference_api(dev, shader, accel, rb, hb, rays_np, hits_np, n, lanes, chunk_rays):
+    """One end-to-end pass with HOST buffers through DeviceInterface calls only: per chunk a BufferUpload on the upload stream, the
+    ShaderDispatch over that chunk's buffer views on the compute stream, a BufferDownload on the download stream, ordered by two
+    timeline events — what a luisa-compute-rs program does with three Streams and two Events."""
+    up, run, down, ev_up, ev_run = lanes
+    base = e2e_reference_api.serial
+    c = 0
+    for b0 in range(0, n, chunk_rays):
+        cnt = min(chunk_rays, n - b0)
+        c += 1
+        up.submit([rb.view(b0, cnt).copy_from_async(rays_np[b0:b0 + cnt])])
+        ev_up.signal(up, base + c); ev_up.wait(run, base + c)
+        run.submit([shader.dispatch_async((cnt, 1, 1), rb.view(b0, cnt), hb.view(b0, cnt), accel)])
+        ev_run.signal(run, base + c); ev_run.wait(down, base + c)
+        down.submit([hb.view(b0, cnt).copy_to_async(hits_np[b0:b0 + cnt])])
+    e2e_reference_api.serial = base + c
+    down.synchronize()
+
+
+e2e_reference_api.serial = 0
+
+
+def parity_sample_leg(dev, lc, shader_factory, n_sample=1 << 20):
+    """north_star's tolerance statement made driver-visible: on the first 1 Mi rays of the batch against the full 1 M-triangle scene,
+    hits of the DSL call path vs the oracle's float64 ground truth — inst / prim must agree wherever the f64 answer is unambiguous,
+    t and barycentrics within 1e-5; the rate of ambiguous rays (a second candidate within 1e-5 relative, or an edge within rounding)
+    is the tie rate."""
+    import oracle_lib as ol
+    import scenes
+    from harness import DeviceScene, compare_with_truth
+    desc = scenes.c3_soup(N_TRIS)
+    rays = scenes.incoherent_rays(n_sample, seed=0x5EED0002)
+    d = DeviceScene(dev, desc)
+    got = d.trace_dsl(rays)
+    o = ol.scene_from_desc(desc)
+    t0 = time.perf_counter()
+    truth, amb = o.truth(rays)
+    truth_s = time.perf_counter() - t0
+    r = compare_with_truth(got, truth, amb)
+    canon = o.trace_closest(rays[: 1 << 16])
+    bit_equal = bool(got[: 1 << 16].tobytes() == canon.tobytes())
+    d.destroy(); o.close()
+    return {"rays": n_sample, "tie_rate": r["tie_rate"], "f64_mismatches": r["mismatches"], "disagree_inside_ties": r["disagree_in_ties"], "t_rel_err_max": r["t_rel_err"],
+            "bary_abs_err_max": r["bary_abs_err"], "bit_identical_to_oracle_on_64k": bit_equal, "truth_seconds": round(truth_s, 2),
+            "note": "DSL call path (create_shader + ShaderDispatch) vs oracle float64 ground truth; mismatches counted outside flagged ties"}
+
+
+def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, balance_passes):
+    """BASELINE config C5 (4K, depth 5, `spp` samples per pixel, 10 x 5 M-triangle instances + light): render AND the NCCL framebuffer
+    gather inside one timed region on the device, strong scaling (the frame is fixed, ranks split it)."""
+    from luisa_compute_rs_b200.tiled_render import TiledPathTracer
+    t0 = time.perf_counter()
+    pt = TiledPathTracer(dev, lc, scenes, spp_per_dispatch=spp_per_dispatch, rank=rank, world=world, dist=dist)
+    setup_s = time.perf_counter() - t0
+    pt.frame(spp_per_dispatch, first_frame=50000)                  # warm-up: kernels, NCCL communicator, allocator
+    history = pt.balance(balance_passes) if world > 1 else []
+    ms, gathered, n_dispatch = pt.frame(spp, first_frame=0)
+    times = pt.all_times(ms)
+    render_only = pt.all_times(pt.timed(lambda: pt.render(1, 70000)))   # one pass without the gather, for the per-rank picture
+    rays = pt.counters_t.clone()
+    if world > 1:
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        img = pt.image(gathered)
+        total = max(times)
+        imbalance = max(render_only) / (sum(render_only) / len(render_only))
+        out = {"workload": "C5: 10 instances of a 5.0M-triangle terrain + emissive quad (50.0M triangles), 3840x2160, depth 5, path tracer as IR through create_shader; "
+                           "tiles sharded over the ranks, Accel replicated, ONE ncclAllGather of the framebuffer inside the timed region",
+               "n_gpus": world, "spp": n_dispatch * spp_per_dispatch, "spp_per_dispatch": spp_per_dispatch, "triangles": pt.triangles,
+               "frame_ms": total, "frame_ms_per_rank": [round(t, 2) for t in times], "scaling": "strong",
+               "mrays_per_s": float(rays.sum().item()) / total / 1e3 * (n_dispatch / (n_dispatch + 1)),   # the counters also hold the extra pass above
+               "msamples_per_s": pt.width * pt.height * n_dispatch * spp_per_dispatch / total / 1e3,
+               "partition": "contiguous ranges of the Morton-ordered 64x64 tiles, cut to equal measured cost" if world > 1 else "all tiles on one GPU",
+               "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes_imbalance": [round(h, 3) for h in history],
+               "one_pass_ms_per_rank": [round(t, 3) for t in render_only], "imbalance_max_over_mean": round(imbalance, 4),
+               "limiter": ("load imbalance between ranks" if imbalance > 1.05 else "per-rank efficiency: 1/N of the image is few work items per SM (dispatch tails) and reuses less of the 430 MB BLAS in L2"),
+               "gather_bytes": int(gathered.numel() * 4) if world > 1 else 0, "blas_build_ms": round(pt.blas_ms, 3), "tlas_build_ms": round(pt.tlas_ms, 3),
+               "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img), "setup_s": round(setup_s, 1)}
+    pt.destroy()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,7 +304,10 @@ def main():
     ap.add_argument("--tris", type=int, default=N_TRIS)
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / cpu legs")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: only the headline steps")
+    ap.add_argument("--c5-spp", type=int, default=1024, help="samples per pixel of the C5 leg (BASELINE: 1024); 0 skips the leg")
+    ap.add_argument("--c5-spp-per-dispatch", type=int, default=16)
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="rays per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,10 +317,12 @@ def main():
         return
     warmup = max(args.warmup, 3) if not args.profile else args.warmup
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import luisa_compute_rs_b200 as lc
     import scenes
+    from luisa_compute_rs_b200 import examples_ir
 
     torch.cuda.set_device(local_rank)
     os.environ["LC_B200_DEVICE"] = str(local_rank)
@@ -257,14 +351,21 @@ def main():
         tlas_all.append(accel.stats()["build_ms"])
     tlas_ms = min(tlas_all)
 
+    # ---- the DSL kernel of the reference call path, lowered + compiled by the device ------------------------------------
+    t0 = time.perf_counter()
+    kernel = examples_ir.trace_buffer_kernel()
+    shader = dev.create_shader(C.addressof(kernel.km), keep=kernel)
+    create_shader_s = time.perf_counter() - t0
+
     # ---- rays: resident in HBM before the timed region -------------------------------------------------------------
     n = args.rays
     rays_h = torch.from_numpy(scenes.incoherent_rays(n, seed=0x5EED0002 + rank).view(np.uint8).reshape(-1)).pin_memory()
     hits_h = torch.empty(n * 24, dtype=torch.uint8).pin_memory()
+    rays_np, hits_np = rays_h.numpy().view(lc.Ray), hits_h.numpy().view(lc.SurfaceHit)
     rb = dev.create_buffer(n, 32, 16)
     hb = dev.create_buffer(n, 24, 8)
     ob = dev.create_buffer(n, 4, 4)
-    rb.view().copy_from(rays_h.numpy().view(lc.Ray))
+    rb.view().copy_from(rays_np)
     stream = dev.create_stream()
     ext = torch.cuda.ExternalStream(stream.cuda_stream(), device=torch.device("cuda", local_rank))
 
@@ -274,11 +375,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step():
+        stream.submit([shader.dispatch_async((n, 1, 1), rb, hb, accel)])
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_first()
     for _ in range(warmup):
-        accel.intersect(rb, hb, n, 0xFF, stream)
+        step()
     stream.synchronize()
 
     barrier()
@@ -287,7 +391,7 @@ def main():
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(ext)
     for k in range(args.steps):
-        accel.intersect(rb, hb, n, 0xFF, stream)
+        step()
         evs[k + 1].record(ext)
     stream.synchronize()
     barrier()
@@ -309,50 +413,77 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD if (args.tris, args.rays) == (N_TRIS, N_RAYS) else f"C3-shaped: {args.tris} triangles, {args.rays} rays per GPU",
                    "triangles": args.tris, "rays_per_gpu": n, "parallelism": f"rays sharded x{world}, accel replicated",
-                   "l2": "ray + hit buffers (896 MiB) exceed the 126 MB L2; the BVH (~60 MB) is L2-resident by nature of the workload"},
-        "gpu_launches": int(launches), "clocks": clocks,
+                   "api": "DeviceInterface.create_shader(ir::KernelModule of `hits.write(i, accel.intersect(rays.read(i), 0xff))`) + dispatch(ShaderDispatch)",
+                   "lowering": "wavefront (persistent threads, trace calls are suspension points of the warp-synchronous traversal loop)",
+                   "l2": "ray + hit buffers (896 MiB) exceed the 126 MB L2; the BVH (~80 MB) is L2-resident by nature of the workload"},
+        "gpu_launches": int(launches), "clocks": clocks, "create_shader_s": create_shader_s,
         "build": {"blas_ms": float(min(build_ms)), "blas_ms_all": [float(x) for x in build_ms], "tlas_ms": float(tlas_ms),
                   "wide_nodes": int(mstats["wide_node_count"]), "bvh_bytes": int(mstats["bvh_bytes"]), "max_depth": int(mstats["max_depth"]),
                   "builder": ["lbvh", "ploc"][int(mstats["builder"])] + " (chosen per mesh under AccelUsageHint::FastTrace)"},
     }
 
+    # the batch entry point on the same buffers (the native extension symbol, not the reference call path): every rank, device-timed
+    for _ in range(2):
+        accel.intersect(rb, hb, n, 0xFF, stream)
+    stream.synchronize()
+    dsl_hits = None
     if rank == 0 and not args.profile:
-        # ---- roofline of the dominant kernel (k_trace): algorithmic bytes from the instrumented kernel on the same inputs ----
+        step(); stream.synchronize()
+        dsl_hits = np.empty(n, dtype=lc.SurfaceHit); hb.view().copy_to(dsl_hits)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(5):
+        accel.intersect(rb, hb, n, 0xFF, stream)
+    e1.record(ext); stream.synchronize()
+    batch_ms = e0.elapsed_time(e1) / 5
+    out["batch_entry"] = {"value": n / batch_ms / 1e3, "unit": UNIT, "ms": batch_ms, "api": "lc_b200_trace_closest (k_trace + k_refine); per GPU", "dsl_over_batch": batch_ms / kernel_ms}
+
+    if rank == 0 and not args.profile:
+        batch_hits = np.empty(n, dtype=lc.SurfaceHit); hb.view().copy_to(batch_hits)
+        assert dsl_hits.tobytes() == batch_hits.tobytes(), "the DSL call path and the batch entry point disagree"
+        # ---- roofline of the timed kernel: algorithmic bytes from the instrumented traversal on the same inputs (the per-ray walk is
+        #      the same in the batch kernel and in the lowered kernel: it depends on the ray and the tree only) ----
         ctr = accel.intersect_counted(rb, hb, n, 0xFF, stream)
         algo_bytes = n * (32 + 24) + 128 * ctr["nodes_visited"] + 48 * ctr["tris_tested"]
         peak, how = measured_peaks()
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         build_bytes = 12 * args.tris + 12 * verts.shape[0] + mstats["bvh_bytes"]
-        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                           "traffic_source": NCU_SUMMARY, "peak_source": how, "kernel": "k_trace<closest>", "algorithmic_bytes_per_launch": int(algo_bytes),
-                           "nodes_per_ray": ctr["nodes_visited"] / n, "tris_per_ray": ctr["tris_tested"] / n,
-                           "note": "logical (L1/L2-inclusive) bytes per SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test; divided by the whole step "
-                                   "(k_trace + its k_refine pass, 14.06 + 0.34 ms in profiles/r01z_launches_summary.csv), so the fraction is a lower bound for k_trace alone",
+        traffic = ncu_traffic()
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                           "traffic_source": NCU_SUMMARY, "peak_source": how, "kernel": "lc_kernel (wavefront-lowered DSL kernel: traversal + barycentrics in one launch)",
+                           "algorithmic_bytes_per_launch": int(algo_bytes), "nodes_per_ray": ctr["nodes_visited"] / n, "tris_per_ray": ctr["tris_tested"] / n,
+                           "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                           "compulsory_dram_bytes": int(n * 56 + mstats["bvh_bytes"]),
+                           "note": "frac is the LOGICAL (L1/L2-inclusive) fraction of SURVEY.md §8(d): 56 B/ray I/O + 128 B per node visit + 48 B per triangle test; it grows with nodes_per_ray, "
+                                   "so Mrays/s and nodes_per_ray are the co-metrics.  dram_frac is measured DRAM traffic (ncu) over the same time: the kernel is bound by L1TEX wavefronts of divergent "
+                                   "32-byte gathers + issue slots, not by HBM",
                            "build_achieved_gbs": build_bytes / (min(build_ms) * 1e-3) / 1e9, "build_frac": build_bytes / (min(build_ms) * 1e-3) / 1e9 / peak}
-        # ---- any-hit on the same batch (C3's shadow set), reported beside the headline ----
-        hits_np = np.empty(n, dtype=lc.SurfaceHit)
-        hb.view().copy_to(hits_np)
-        shadow = scenes.shadow_rays_from_hits(rays_h.numpy().view(lc.Ray), hits_np)
+        # ---- any-hit on the same batch (C3's shadow set), both call paths ----
+        shadow = scenes.shadow_rays_from_hits(rays_np, dsl_hits)
         rb2 = dev.create_buffer_from_array(shadow)
-        for _ in range(2):
-            accel.intersect_any(rb2, ob, n, 0xFF, stream)
-        stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
-        for _ in range(5):
-            accel.intersect_any(rb2, ob, n, 0xFF, stream)
-        e1.record(ext)
-        stream.synchronize()
-        out["any_hit"] = {"value": n * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": UNIT, "hit_rate": float((hits_np["inst"] != lc.INVALID).mean())}
-        rb2.destroy()
+        ka = examples_ir.trace_buffer_kernel(any_hit=True)
+        sha = dev.create_shader(C.addressof(ka.km), keep=ka)
+        res = {}
+        for name, fn in (("dsl", lambda: stream.submit([sha.dispatch_async((n, 1, 1), rb2, ob, accel)])), ("batch", lambda: accel.intersect_any(rb2, ob, n, 0xFF, stream))):
+            for _ in range(2):
+                fn()
+            stream.synchronize()
+            e0.record(ext)
+            for _ in range(5):
+                fn()
+            e1.record(ext); stream.synchronize()
+            res[name] = n * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e6
+        out["any_hit"] = {"value": res["dsl"], "unit": UNIT, "batch_entry": res["batch"], "hit_rate": float((dsl_hits["inst"] != lc.INVALID).mean())}
+        sha.destroy(); rb2.destroy()
 
     if not args.profile:
-        # ---- end to end through the C ABI host entry point: pinned host rays in, pinned host hits out, every step ----
-        accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+        # ---- end to end with HOST buffers through DeviceInterface calls only (docstring) ----
+        lanes = (dev.create_stream(), dev.create_stream(), dev.create_stream(), dev.create_event(), dev.create_event())
+        e2e_reference_api(dev, shader, accel, rb, hb, rays_np, hits_np, n, lanes, args.e2e_chunk)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+            e2e_reference_api(dev, shader, accel, rb, hb, rays_np, hits_np, n, lanes, args.e2e_chunk)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -360,33 +491,34 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         out["e2e"] = {"value": world * n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * n * 24,
-                      "api": "lc_b200_trace_closest_host (chunked H2D / trace / D2H pipeline)"}
-        got = hits_h.numpy().view(lc.SurfaceHit)
-        chk = np.empty(n, dtype=lc.SurfaceHit)
-        accel.intersect(rb, hb, n, 0xFF, stream)
-        stream.synchronize()
-        hb.view().copy_to(chk)
-        assert got.tobytes() == chk.tobytes(), "host and device entry points disagree"
+                      "api": f"DeviceInterface only: per {args.e2e_chunk}-ray chunk BufferUpload | ShaderDispatch | BufferDownload on three streams ordered by timeline events; pinned host buffers"}
+        if dsl_hits is not None:
+            assert hits_np.tobytes() == dsl_hits.tobytes(), "host-buffer pipeline and device-resident dispatch disagree"
+        # the batch-form host entry point beside it
+        accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(args.steps // 2, 1)):
+            accel.intersect_host_ptr(rays_h.data_ptr(), hits_h.data_ptr(), n)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out["e2e_batch_entry"] = {"value": world * n * max(args.steps // 2, 1) / dt / 1e6, "unit": UNIT, "api": "lc_b200_trace_closest_host (chunked H2D / k_trace / D2H pipeline inside the library)"}
+        for r in lanes:
+            r.destroy()
 
     if rank == 0 and not args.profile:
-        # ---- config C2 beside the headline: examples/path_tracer.rs as an IR kernel through create_shader (IR -> CUDA lowering + NVRTC) ----
+        out["parity_sample"] = parity_sample_leg(dev, lc, None)
+        # ---- config C2 beside the headline: examples/path_tracer.rs as an IR kernel through create_shader ----
         out["dsl_path_tracer"] = dsl_path_tracer_leg(dev, lc, scenes, torch, ext)
 
-    if world > 1 and not args.profile:
-        # the one collective of the path: gather of a 4K Float4 framebuffer's tiles over NCCL
-        import luisa_compute_rs_b200.sharding as sh
-        per_rank = sh.padded_tile_count(3840, 2160, world) * sh.TILE * sh.TILE
-        local = torch.zeros(per_rank, 4, device="cuda")
-        sh.gather_tiles(local, dist, world)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            sh.gather_tiles(local, dist, world)
-        e1.record(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / 10], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out["framebuffer_gather"] = {"ms": float(t.item()), "bytes_total": int(per_rank * 16 * world), "collective": "ncclAllGather 4K Float4 tiles"}
+    if not args.profile and args.c5_spp > 0:
+        c5 = c5_leg(dev, lc, scenes, torch, dist if world > 1 else None, rank, world, args.c5_spp, args.c5_spp_per_dispatch, 4)
+        if rank == 0:
+            out["c5_path_trace"] = c5
 
     if rank == 0 and world == 1 and not args.no_cpu and not args.profile:
         import oracle_lib as ol
@@ -398,7 +530,7 @@ def main():
 
     if rank == 0:
         emit(json.dumps(out))
-    for b in (rb, hb, ob, vb, ib):
+    for b in (shader, rb, hb, ob, vb, ib):
         b.destroy()
     accel.destroy(); mesh.destroy(); stream.destroy(); dev.close()
     if world > 1:

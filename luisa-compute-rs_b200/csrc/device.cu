@@ -20,6 +20,7 @@
 #include <cstring>
 #include <deque>
 #include <dlfcn.h>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -177,18 +178,69 @@ struct TextureObj { uint8_t *ptr = nullptr; uint32_t dim = 2, width = 1, height 
 // Bindless arrays (cpu/resource.rs:60-124): a slot table mirrored on the host; BindlessArrayUpdate uploads touched slots.
 struct BindlessObj { std::vector<HostBindlessSlot> host; HostBindlessSlot *device = nullptr; std::mutex mu; };
 
+// Timeline event (cpu/resource.rs:10-44): one monotone 64-bit counter in device memory.  signal = a one-thread kernel doing atomicMax
+// on the signalling stream (EventImpl::signal is fetch_max), wait = cuStreamWaitValue64(>=) enqueued on the waiting stream — the host
+// never blocks, so wait-before-signal works as on the reference's stream threads (cpu/mod.rs:367-402) — synchronize / is_completed
+// read the counter back through a private copy stream.  `seen` caches the largest value the host has observed.
 struct EventObj {
-    std::mutex mu; std::condition_variable cv;
-    std::map<uint64_t, cudaEvent_t> signalled;  // value -> event recorded at the signal point
+    unsigned long long *counter = nullptr;
+    std::atomic<uint64_t> seen{0};
 };
 
 struct DeviceObj;
+
+// Upload snapshots.  BufferUpload / TextureUpload sources are only borrowed until dispatch() returns (the frontend's copy_from_async
+// borrows for the life of the Command; the CPU backend memcpy's them into staging buffers inside dispatch, cpu/stream.rs:33-64), so the
+// bytes are copied into pinned staging blocks before dispatch returns — whatever the source is (pageable, pinned, registered: a pinned
+// source would otherwise be read by the copy engine long after the caller may have reused it) — and the H2D copy runs from the staging
+// block.  Blocks are pooled by size class (cudaHostAlloc costs milliseconds) and large snapshots are taken by several host threads.
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    size_t pooled_bytes = 0;
+    static size_t size_class(size_t n) { size_t c = 64 << 10; while (c < n) c <<= 1; return c; }
+    void *take(size_t n, size_t &cap) {
+        cap = size_class(n);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_blocks.find(cap);
+            if (it != free_blocks.end()) { void *p = it->second; free_blocks.erase(it); pooled_bytes -= cap; return p; }
+        }
+        void *p = nullptr;
+        CUDA_CHECK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+        return p;
+    }
+    void give(void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (pooled_bytes + cap <= (size_t(4) << 30)) { free_blocks.emplace(cap, p); pooled_bytes += cap; return; }
+        }
+        cudaFreeHost(p);
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &kv : free_blocks) cudaFreeHost(kv.second);
+        free_blocks.clear(); pooled_bytes = 0;
+    }
+};
+PinnedPool g_pinned;
+void release_staged(std::vector<std::pair<void *, size_t>> &v) { for (auto &b : v) g_pinned.give(b.first, b.second); v.clear(); }
+
+void parallel_copy(void *dst, const void *src, size_t n) {
+    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (n < (size_t(8) << 20) || hw == 1) { memcpy(dst, src, n); return; }
+    const size_t slice = ((n + hw - 1) / hw + 4095) & ~size_t(4095);
+    std::vector<std::thread> workers;
+    for (size_t off = slice; off < n; off += slice) workers.emplace_back([=] { memcpy((uint8_t *)dst + off, (const uint8_t *)src + off, std::min(slice, n - off)); });
+    memcpy(dst, src, std::min(slice, n));
+    for (auto &w : workers) w.join();
+}
 
 struct StreamObj {
     DeviceObj *dev = nullptr;
     cudaStream_t stream = nullptr;
     unsigned long long *work_counter = nullptr;   // device: ray-pool counter for trace launches on this stream
-    struct Pending { cudaEvent_t ev; lcb_dispatch_callback cb; uint8_t *ctx; std::vector<void *> host_frees; };
+    struct Pending { cudaEvent_t ev; lcb_dispatch_callback cb; uint8_t *ctx; std::vector<std::pair<void *, size_t>> staged; /* pinned upload snapshots, back to the pool on completion */ };
     std::mutex mu; std::condition_variable cv, drained;
     std::deque<Pending> pending;
     bool stop = false; size_t in_flight = 0;
@@ -206,7 +258,7 @@ struct StreamObj {
             cudaError_t e = cudaEventSynchronize(p.ev);
             if (e != cudaSuccess) fatal("stream failed: %s", cudaGetErrorString(e));
             cudaEventDestroy(p.ev);
-            for (void *h : p.host_frees) cudaFreeHost(h);
+            release_staged(p.staged);
             if (p.cb) p.cb(p.ctx);
             { std::lock_guard<std::mutex> lk(mu); in_flight--; }
             drained.notify_all();
@@ -233,6 +285,8 @@ struct DeviceObj {
     // multi-GB blocks made a rebuild after a few refits cost 15-30 ms instead of 8 (tools/micro/rebuild_probe.py).
     uint8_t *build_arena = nullptr; size_t build_arena_cap = 0;
     std::mutex build_mu;
+    // event counters are read back on their own stream (never behind the user's work)
+    cudaStream_t poll_stream = nullptr; unsigned long long *poll_word = nullptr; std::mutex poll_mu;
 };
 
 template <class T> T *as(uint64_t h) { if (h == 0 || h == LCB_INVALID_HANDLE) fatal("invalid resource handle"); return reinterpret_cast<T *>(h); }
@@ -618,15 +672,36 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
     DeviceObj *d = dev_of(dev); bind(d);
     StreamObj *s = as<StreamObj>(sh.id);
     cudaStream_t st = s->stream;
+    std::vector<std::pair<void *, size_t>> staged;
+    std::vector<cudaEvent_t> direct_copies;
+    // Snapshot the source before returning (PinnedPool comment).  Two ways: (1) large pinned sources on an idle stream are copied by the
+    // copy engine straight from the caller's memory and dispatch() waits for exactly that copy before it returns — the device buffer is
+    // the snapshot, no second pass over host memory; (2) everything else goes through a pinned staging block.
+    auto upload = [&](void *dst, const void *src, size_t n) {
+        cudaPointerAttributes attr{};
+        const bool pinned = n >= (size_t(1) << 20) && cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) (void)cudaGetLastError();
+        if (pinned && (!direct_copies.empty() || cudaStreamQuery(st) == cudaSuccess)) {
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st));
+            cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+            CUDA_CHECK(cudaEventRecord(ev, st));
+            direct_copies.push_back(ev);
+            return;
+        }
+        (void)cudaGetLastError();  // cudaStreamQuery: cudaErrorNotReady is not an error
+        size_t cap = 0;
+        void *stage = g_pinned.take(n, cap);
+        parallel_copy(stage, src, n);
+        staged.emplace_back(stage, cap);
+        CUDA_CHECK(cudaMemcpyAsync(dst, stage, n, cudaMemcpyHostToDevice, st));
+    };
     for (size_t i = 0; i < list.commands_count; i++) {
         const lcb_command &c = list.commands[i];
         switch (c.tag) {
             case LCB_CMD_BUFFER_UPLOAD: {
-                // pageable-source cudaMemcpyAsync returns once the source has been staged, which is the
-                // "snapshot upload payloads before returning" contract of stream.rs:47-64
                 BufferObj *b = as<BufferObj>(c.u.buffer_upload.buffer.id);
                 if (c.u.buffer_upload.offset + c.u.buffer_upload.size > b->size) fatal("BufferUpload out of range");
-                if (c.u.buffer_upload.size) CUDA_CHECK(cudaMemcpyAsync(b->ptr + c.u.buffer_upload.offset, c.u.buffer_upload.data, c.u.buffer_upload.size, cudaMemcpyHostToDevice, st));
+                if (c.u.buffer_upload.size) upload(b->ptr + c.u.buffer_upload.offset, c.u.buffer_upload.data, c.u.buffer_upload.size);
                 break;
             }
             case LCB_CMD_BUFFER_DOWNLOAD: {
@@ -644,7 +719,7 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
             case LCB_CMD_TEXTURE_UPLOAD: {
                 TextureObj *t = as<TextureObj>(c.u.texture_upload.texture.id);
                 const size_t n = texture_region_bytes(t, c.u.texture_upload.storage, c.u.texture_upload.level, c.u.texture_upload.size, "TextureUpload");
-                if (n) CUDA_CHECK(cudaMemcpyAsync(t->ptr, c.u.texture_upload.data, n, cudaMemcpyHostToDevice, st));
+                if (n) upload(t->ptr, c.u.texture_upload.data, n);
                 break;
             }
             case LCB_CMD_TEXTURE_DOWNLOAD: {
@@ -685,43 +760,78 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
     StreamObj::Pending p{};
     CUDA_CHECK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventRecord(p.ev, st));
-    p.cb = cb; p.ctx = ctx;
+    p.cb = cb; p.ctx = ctx; p.staged = std::move(staged);
     s->push(std::move(p));
+    for (cudaEvent_t ev : direct_copies) { CUDA_CHECK(cudaEventSynchronize(ev)); cudaEventDestroy(ev); }  // the borrow of those sources ends here
 }
 
 // ---- events (timeline semantics, cpu/resource.rs:10-44, cpu/mod.rs:367-402) -----------------------
-lcb_created create_event(lcb_device dev) { bind(dev_of(dev)); auto *e = new EventObj; return lcb_created{(uint64_t)e, e}; }
+__global__ void k_event_signal(unsigned long long *counter, unsigned long long value) { atomicMax(counter, value); }
+
+typedef int (*StreamWaitValue64Fn)(cudaStream_t, unsigned long long /* CUdeviceptr */, unsigned long long, unsigned int);
+StreamWaitValue64Fn stream_wait_value64() {
+    static StreamWaitValue64Fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &status) != cudaSuccess || status != cudaDriverEntryPointSuccess || !p)
+            fatal("the driver does not export cuStreamWaitValue64: timeline events need stream memory operations");
+        return (StreamWaitValue64Fn)p;
+    }();
+    return fn;
+}
+
+lcb_created create_event(lcb_device dev) {
+    bind(dev_of(dev));
+    auto *e = new EventObj;
+    CUDA_CHECK(cudaMalloc((void **)&e->counter, 256));
+    zero_fill(e->counter, 256);
+    return lcb_created{(uint64_t)e, e};
+}
 void destroy_event(lcb_device dev, lcb_event h) {
     bind(dev_of(dev));
     EventObj *e = as<EventObj>(h.id);
-    for (auto &kv : e->signalled) cudaEventDestroy(kv.second);
+    cudaFree(e->counter);  // synchronises with every stream that still signals or waits on it
     delete e;
 }
 void signal_event(lcb_device dev, lcb_event h, lcb_stream sh, uint64_t value) {
-    bind(dev_of(dev));
+    DeviceObj *d = dev_of(dev); bind(d);
     EventObj *e = as<EventObj>(h.id); StreamObj *s = as<StreamObj>(sh.id);
-    cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventRecord(ev, s->stream));
-    { std::lock_guard<std::mutex> lk(e->mu); auto it = e->signalled.find(value); if (it != e->signalled.end()) { cudaEventDestroy(it->second); } e->signalled[value] = ev; }
-    e->cv.notify_all();
+    k_event_signal<<<1, 1, 0, s->stream>>>(e->counter, (unsigned long long)value);
+    CUDA_CHECK(cudaGetLastError());
+    g_launches++;
 }
-cudaEvent_t event_for(EventObj *e, uint64_t value) {  // first signal with value >= requested; blocks until one was issued
-    std::unique_lock<std::mutex> lk(e->mu);
-    e->cv.wait(lk, [&] { return e->signalled.lower_bound(value) != e->signalled.end(); });
-    return e->signalled.lower_bound(value)->second;
-}
-void synchronize_event(lcb_device dev, lcb_event h, uint64_t value) { bind(dev_of(dev)); CUDA_CHECK(cudaEventSynchronize(event_for(as<EventObj>(h.id), value))); }
-void wait_event(lcb_device dev, lcb_event h, lcb_stream sh, uint64_t value) {
-    bind(dev_of(dev));
-    CUDA_CHECK(cudaStreamWaitEvent(as<StreamObj>(sh.id)->stream, event_for(as<EventObj>(h.id), value), 0));
+uint64_t event_value(DeviceObj *d, EventObj *e) {  // the counter as the device holds it now
+    std::lock_guard<std::mutex> lk(d->poll_mu);
+    if (!d->poll_stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&d->poll_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaHostAlloc((void **)&d->poll_word, 64, cudaHostAllocDefault));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d->poll_word, e->counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->poll_stream));
+    CUDA_CHECK(cudaStreamSynchronize(d->poll_stream));
+    const uint64_t v = *d->poll_word;
+    uint64_t prev = e->seen.load();
+    while (prev < v && !e->seen.compare_exchange_weak(prev, v)) {}
+    return v;
 }
 bool is_event_completed(lcb_device dev, lcb_event h, uint64_t value) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    EventObj *e = as<EventObj>(h.id);
+    return e->seen.load() >= value || event_value(d, e) >= value;
+}
+void synchronize_event(lcb_device dev, lcb_event h, uint64_t value) {
+    DeviceObj *d = dev_of(dev); bind(d);
+    EventObj *e = as<EventObj>(h.id);
+    if (e->seen.load() >= value) return;
+    for (unsigned spins = 0; event_value(d, e) < value; spins++) {
+        if (spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(spins > 1024 ? 200 : 20));
+    }
+}
+void wait_event(lcb_device dev, lcb_event h, lcb_stream sh, uint64_t value) {
     bind(dev_of(dev));
     EventObj *e = as<EventObj>(h.id);
-    std::lock_guard<std::mutex> lk(e->mu);
-    auto it = e->signalled.lower_bound(value);
-    if (it == e->signalled.end()) return false;
-    return cudaEventQuery(it->second) == cudaSuccess;
+    if (e->seen.load() >= value) return;  // already completed: nothing to order against
+    const int rc = stream_wait_value64()(as<StreamObj>(sh.id)->stream, (unsigned long long)e->counter, (unsigned long long)value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) fatal("cuStreamWaitValue64 failed (%d)", rc);
 }
 
 // ---- mesh / accel objects ------------------------------------------------------------------------
@@ -917,6 +1027,9 @@ void destroy_device(lcb_device_interface iface) {
     if (d->stage_rays) cudaFree(d->stage_rays);
     if (d->stage_out) cudaFree(d->stage_out);
     if (d->build_arena) cudaFree(d->build_arena);
+    if (d->poll_stream) cudaStreamDestroy(d->poll_stream);
+    if (d->poll_word) cudaFreeHost(d->poll_word);
+    g_pinned.clear();
     flush_launches(d);
     delete d;
 }

@@ -247,6 +247,7 @@ struct Globals {
 struct ModuleScan {
     int trace_sites = 0;         // RayTracingTraceClosest / TraceAny calls in the kernel's own body, outside RayQuery callbacks
     bool block_features = false; // SynchronizeBlock, warp intrinsics
+    size_t body_nodes = 0;       // IR nodes of the kernel body and of the callables it reaches: the size of the user phases
     uint32_t curve_bases = 0;
     std::unordered_set<NodeRef> accels;  // accel operands of those trace sites
     std::unordered_set<const void *> seen_callables;
@@ -889,6 +890,7 @@ void scan_block(const BasicBlock *bb, ModuleScan &sc, bool kernel_level) {
     for_each_node(bb, [&](NodeRef n) {
         const Instruction *ins = node(n)->instruction.get();
         if (!ins) return;
+        sc.body_nodes++;
         switch (ins->tag) {
             case Instruction::Call: {
                 const Func &f = ins->call.func;
@@ -999,6 +1001,12 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
                       scan.curve_bases == 0;
     fe.wave = wave;
     out.wave = wave;
+    // Two knobs of the wavefront form, both set by how much user code runs between two trace calls (B200 sweeps,
+    // profiles/r02a_dsl_c*_sweep.jsonl): a kernel that only moves rays and hits (config C3) wants its finished lanes refilled early
+    // (yield at 8 ready lanes) and 5 CTAs per SM; a path tracer's user phases are long enough that running them for a few lanes at a
+    // time costs more than the idle traversal lanes (yield at 32 = when the whole warp has finished) and need 4 CTAs' worth of registers.
+    out.wave_yield_min = scan.body_nodes < 64 ? 8 : (scan.body_nodes >= 256 ? 32 : 16);
+    const int wave_min_blocks = scan.body_nodes < 128 ? 5 : 4;
 
     collect_phis(km->module.entry.ptr, fe.phis);
     if (wave) fe.indent = 4;
@@ -1027,7 +1035,7 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
         // would launch (block-major, then x-fastest inside the block), so that the items of a warp's pool are neighbours in the
         // dispatch exactly as the threads of a block are; positions outside dispatch_size are skipped (cpu/stream.rs:384-404).
         const char *min_blocks = getenv("LC_B200_WAVE_MIN_BLOCKS");
-        src << "extern \"C\" __global__ void __launch_bounds__(" << kWaveThreads << ", " << (min_blocks ? atoi(min_blocks) : 4) << ") lc_kernel(const lc_params p) {\n"
+        src << "extern \"C\" __global__ void __launch_bounds__(" << kWaveThreads << ", " << (min_blocks ? atoi(min_blocks) : wave_min_blocks) << ") lc_kernel(const lc_params p) {\n"
             << "    __shared__ lcb::WaveShared lc_s;\n"
             << "    uint2 lc_deep_stack[lcb::kWaveLocalStack];\n"
             << "    lcb::WaveLane lc_w;\n"
@@ -1039,7 +1047,6 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
             << fe.decls
             << "    for (;;) {\n"
             << "        lcb::wave_fetch(lc_pool, lc_state, lc_item, p.launch.work_items, p.launch.work_counter);\n"
-            << "        if (lc_state == lcb::kWaveNeedsWork) { lc_pc = 0u; }\n"
             << "        const uint32_t lc_dead = __ballot_sync(0xffffffffu, lc_state == lcb::kWaveDead);\n"
             << "        if (lc_dead == 0xffffffffu) break;\n"
             << "        if (lc_state == lcb::kWaveReady) {\n"

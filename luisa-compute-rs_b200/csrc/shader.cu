@@ -151,10 +151,10 @@ void shader_destroy(ShaderObj *s) {
 
 const LoweredKernel &shader_lowered(const ShaderObj *s) { return s->lowered; }
 
-// LC_B200_WAVE_YIELD: how many lanes of a warp must be able to continue in user code before the traversal loop hands control back
-static int wave_yield_min() {
-    const char *e = getenv("LC_B200_WAVE_YIELD");  // read per launch: a tuning knob for sweeps
-    const int y = e ? atoi(e) : 8;
+// LC_B200_WAVE_YIELD overrides the per-kernel choice of ir_lower.cpp (read per launch: a tuning knob for sweeps)
+static int wave_yield_min(int chosen) {
+    const char *e = getenv("LC_B200_WAVE_YIELD");
+    const int y = e ? atoi(e) : chosen;
     return y < 1 ? 1 : (y > 32 ? 32 : y);
 }
 
@@ -176,7 +176,7 @@ int shader_launch(ShaderObj *s, cudaStream_t stream, void *params, const uint32_
         HostLaunch *launch = reinterpret_cast<HostLaunch *>(params);
         launch->work_items = (unsigned long long)grid.x * grid.y * grid.z * b[0] * b[1] * b[2];
         launch->work_counter = work_counter;
-        launch->yield_min = (uint32_t)wave_yield_min();
+        launch->yield_min = (uint32_t)wave_yield_min(s->lowered.wave_yield_min);
         const unsigned long long want = (launch->work_items + kWaveThreads - 1) / kWaveThreads;
         grid = dim3((unsigned)(want < s->resident_ctas ? want : s->resident_ctas), 1, 1);
         block = dim3(kWaveThreads, 1, 1);

@@ -218,13 +218,11 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     if ((meta.x & mask) != 0u && (meta.z & 4u) == 0u) {
                         if (Gt.y) LCB_PUSH(Gt)
                         if (G.y & 0xff000000u) LCB_PUSH(G)
-                        LCB_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
                         const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                         const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                         nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                         tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                        const float4 wo = make_float4(r.ox, r.oy, r.oz, 0.f), wd = make_float4(r.dx, r.dy, r.dz, 0.f);
-                        setup_object(r, wo, wd, m0, m1, m2);
+                        LCB_PUSH(make_uint2(enter_instance(r, m0, m1, m2) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
                         cur_inst = inst;
                         if (QUERY) cur_opaque = (meta.z & 2u) != 0u;
                         G = make_uint2(0u, 0x80000000u);
@@ -251,8 +249,10 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                 // sentinel: the instance is exhausted, back to world space
                 cur_inst = kNone; nodes = acc.tlas_nodes; tris = nullptr;
                 if (sp == 0) { retire = true; break; }  // nothing left in the TLAS either: skip the re-setup
-                const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
-                setup_world(r, ra, rb);
+                if (e.x == 0u) {
+                    const float4 ra = __ldg(rays + 2 * ray_idx), rb = __ldg(rays + 2 * ray_idx + 1);
+                    setup_world(r, ra, rb);
+                }
             }
             if (retire) {
                 if (ANY) {

@@ -63,6 +63,22 @@ __device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const
     finish_setup(r);
 }
 
+// Entering an instance from world space, where `r` holds the world-space setup: the canonical transform is always evaluated, but when
+// the object-space ray comes out bit-identical to the world-space one (identity transforms — single-instance scenes, the Cornell box's
+// eight meshes) the derived constants are the same pure function of the same bits and are kept.  Returns true in that case; the
+// caller records it in the stack sentinel so that leaving the instance skips the world-space re-setup too.
+__device__ __forceinline__ bool enter_instance(RaySetup &r, const float4 m0, const float4 m1, const float4 m2) {
+    RaySetup t;
+    transform_ray(t, make_float4(r.ox, r.oy, r.oz, 0.f), make_float4(r.dx, r.dy, r.dz, 0.f), m0, m1, m2);
+    const bool same = __float_as_uint(t.ox) == __float_as_uint(r.ox) && __float_as_uint(t.oy) == __float_as_uint(r.oy) && __float_as_uint(t.oz) == __float_as_uint(r.oz) &&
+                      __float_as_uint(t.dx) == __float_as_uint(r.dx) && __float_as_uint(t.dy) == __float_as_uint(r.dy) && __float_as_uint(t.dz) == __float_as_uint(r.dz);
+    if (!same) {
+        r.ox = t.ox; r.oy = t.oy; r.oz = t.oz; r.dx = t.dx; r.dy = t.dy; r.dz = t.dz;
+        finish_setup(r);
+    }
+    return same;
+}
+
 // 16-bit plane index -> float 2^23 + q in ONE byte-permute (no int->float conversion, no subtraction): the 2^23
 // bias is folded into the per-node plane offsets below, at the price of half a quantisation step of rounding
 // slop that the padding absorbs (one extra step, 2^-16 of the node extent).  The constant sits in the first
@@ -429,12 +445,11 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 if ((meta.x & mask) != 0u && (QUERY || (meta.z & 4u) == 0u) && (CURVES || (meta.z & 8u) == 0u)) {
                     if (Gt.y) stack[sp++] = Gt;
                     if (G.y & 0xff000000u) stack[sp++] = G;
-                    stack[sp++] = make_uint2(0u, 0u);  // sentinel: below it lies world space
                     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                     nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                     tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                    setup_object(r, ra, rb, m0, m1, m2);
+                    stack[sp++] = make_uint2(enter_instance(r, m0, m1, m2) ? 1u : 0u, 0u);  // sentinel: below it lies world space (x = 1: same ray setup)
                     cur_inst = inst;
                     if (QUERY) { cur_opaque = (meta.z & 2u) != 0u; cur_procedural = (meta.z & 4u) != 0u; }
                     if (CURVES) cur_curve = (meta.z & 8u) != 0u;
@@ -453,7 +468,7 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 if (e.y != 0u) { Gt = e; break; }
                 cur_inst = kNone; cur_procedural = false; cur_curve = false; nodes = acc.tlas_nodes; tris = nullptr;
                 if (sp == 0) { done = true; break; }
-                setup_world(r, ra, rb);
+                if (e.x == 0u) setup_world(r, ra, rb);
             }
             if (done) break;
         }
@@ -591,13 +606,11 @@ __device__ __forceinline__ void wave_traverse(WaveLane &w, int &state, const Acc
                 if ((meta.x & w.mask) != 0u && (meta.z & 12u) == 0u) {
                     if (w.Gt.y) LCW_PUSH(w.Gt)
                     if (w.G.y & 0xff000000u) LCW_PUSH(w.G)
-                    LCW_PUSH(make_uint2(0u, 0u))  // sentinel: below it lies world space
                     const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                     w.nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                     w.tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                    const float4 wo = make_float4(w.r.ox, w.r.oy, w.r.oz, 0.f), wd = make_float4(w.r.dx, w.r.dy, w.r.dz, 0.f);
-                    setup_object(w.r, wo, wd, m0, m1, m2);
+                    LCW_PUSH(make_uint2(enter_instance(w.r, m0, m1, m2) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
                     w.cur_inst = inst;
                     w.G = make_uint2(0u, 0x80000000u);
                     w.Gt = make_uint2(0u, 0u);
@@ -615,7 +628,7 @@ __device__ __forceinline__ void wave_traverse(WaveLane &w, int &state, const Acc
                 if (e.y != 0u) { w.Gt = e; break; }
                 w.cur_inst = kNone; w.nodes = acc.tlas_nodes; w.tris = nullptr;  // sentinel: the instance is exhausted
                 if (w.sp == 0) { state = kWaveReady; break; }
-                setup_world(w.r, S.ray[threadIdx.x], S.ray[kWaveThreads + threadIdx.x]);
+                if (e.x == 0u) setup_world(w.r, S.ray[threadIdx.x], S.ray[kWaveThreads + threadIdx.x]);
             }
         }
     }

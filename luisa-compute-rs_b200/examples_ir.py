@@ -307,6 +307,26 @@ def path_tracer_kernel(vertex_heap_handle, index_heap_handle, spp_per_dispatch=S
     return k
 
 
+def display_kernel():
+    """examples/path_tracer.rs:465-479 — `Kernel::<fn(Tex2d<Float4>, Tex2d<Float4>)>`: accumulated radiance / spp through the sRGB transfer
+    curve into the display image (whose storage is the swapchain's, Byte4: the texel conversion rounds to 8 bits, cpu_texture.h)."""
+    k = ir.KernelBuilder(block_size=(16, 16, 1))
+    acc = k.arg_tex2d(k.f324)
+    display = k.arg_tex2d(k.f324)
+
+    def body():
+        coord = k.dispatch_id().permute(0, 1)
+        texel = acc.tex_read(coord)
+        radiance = texel.permute(0, 1, 2) / texel.w
+        e = 1.0 / 2.4
+        r = k.f(1.055) * k.call(Func.Powf, [radiance, k.vec(k.f323, e, e, e)], k.f323) - 0.055   # the scalar exponent is spread to the vector (ops/spread.rs:367)
+        srgb = radiance.lt(0.0031308).select(radiance * 12.92, r)
+        display.tex_write(coord, k.vec(k.f324, srgb.x, srgb.y, srgb.z, 1.0))
+    k.body(body)
+    k.finish()
+    return k
+
+
 def ray_query_kernel(radius, any_hit=False):
     """The query of examples/ray_query.rs:135-170 over a ray buffer: `accel.traverse(ray).on_surface_hit(|c| if disc(c.bary) { c.commit() })`,
     one ray per thread, CommittedHit written per ray.  Args: rays Buffer<Ray>, committed Buffer<CommittedHit>, accel, mask: u32."""

@@ -81,3 +81,60 @@ def untile(gathered, width, height, world, tile=TILE, chunk=1):
         img[idx[valid]] = buf[valid]
         assert tx.shape[0] <= per_rank
     return img.reshape(height, width, channels)
+
+
+# ---- cost-balanced contiguous partition of the Morton curve -------------------------------------------------------------------------
+# Round-robin single tiles balance a path tracer's load but scatter every rank's rays over the whole scene (a rank re-reads the whole
+# BVH through its L2); contiguous runs keep a rank in one part of the scene but are unbalanced, because cost per tile varies with what
+# the tile sees.  The partition below has both: rank r renders the contiguous range [bounds[r], bounds[r + 1]) of the Morton-ordered
+# tiles, and the bounds are cut so that every range carries the same estimated cost.  The estimate is refined from what a progressive
+# renderer already has — the time each rank took for its range in the previous pass: the per-tile estimate is rescaled inside every
+# range so that the range sums to the measured time, then the bounds are re-cut.  Pixels never depend on the partition (random streams
+# are keyed by the global pixel index), so the image is the same bits for every cut.
+
+def balanced_bounds(cost, world):
+    """cost: per-tile estimates along the Morton curve (positive).  Returns world + 1 tile indices; range r = [b[r], b[r + 1]).  Every
+    range is non-empty when there are at least `world` tiles."""
+    cost = np.maximum(np.asarray(cost, np.float64), 1e-30)
+    n = cost.shape[0]
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    targets = cum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cum, targets, side="left")
+    # the cut goes to whichever side of the crossing tile leaves the smaller error
+    inner = np.where((inner > 0) & (np.abs(cum[np.maximum(inner - 1, 0)] - targets) < np.abs(cum[np.minimum(inner, n)] - targets)), inner - 1, inner)
+    bounds = np.concatenate([[0], inner, [n]]).astype(np.int64)
+    if n >= world:   # keep every range non-empty
+        for r in range(1, world):
+            bounds[r] = max(bounds[r], bounds[r - 1] + 1)
+        for r in range(world - 1, 0, -1):
+            bounds[r] = min(bounds[r], bounds[r + 1] - 1)
+    return bounds
+
+
+def refine_cost(cost, bounds, times):
+    """Rescale the per-tile estimates inside every range so that the range sums to the time measured for it."""
+    cost = np.array(cost, np.float64)
+    for r, t in enumerate(times):
+        b0, b1 = int(bounds[r]), int(bounds[r + 1])
+        if b1 > b0 and t > 0:
+            total = cost[b0:b1].sum()
+            cost[b0:b1] = cost[b0:b1] * (t / total) if total > 0 else t / (b1 - b0)
+    return cost
+
+
+def tiles_of_range(width, height, begin, end, tile=TILE):
+    tx, ty = tile_order(width, height, tile)
+    return tx[begin:end], ty[begin:end]
+
+
+def untile_ranges(gathered, width, height, bounds, tile=TILE):
+    """untile() for the contiguous partition: gathered[r] holds the tiles [bounds[r], bounds[r + 1]) of the Morton order, padded to the
+    longest range."""
+    channels = gathered.shape[-1]
+    img = np.zeros((height * width, channels), dtype=gathered.dtype)
+    tx, ty = tile_order(width, height, tile)
+    for r in range(len(bounds) - 1):
+        b0, b1 = int(bounds[r]), int(bounds[r + 1])
+        idx, valid = pixels_of_tiles(tx[b0:b1], ty[b0:b1], width, height, tile)
+        img[idx[valid]] = gathered[r, : (b1 - b0) * tile * tile][valid]
+    return img.reshape(height, width, channels)

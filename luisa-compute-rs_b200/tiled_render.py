@@ -1,0 +1,174 @@
+"""BASELINE config C5 as a host program: tile-sharded path tracing over a replicated Accel, one process per GPU.
+
+What a luisa-compute-rs user would write on top of the device for SURVEY.md §8e: every rank builds the same meshes + Accel itself
+(the build is deterministic, so nothing is broadcast), renders its share of the 64 x 64 tiles with the path tracer as an
+ir::KernelModule through create_shader + ShaderDispatch (examples_ir.tiled_path_tracer_kernel — the wavefront lowering of
+csrc/ir_lower.cpp), and ONE NCCL all-gather assembles the framebuffer: the only collective of the path.
+
+Partition (sharding.py): rank r owns a contiguous range of the Morton-ordered tiles, cut so that every range costs the same.  The cost
+map is what a progressive renderer gets for free — each pass's per-rank time, exchanged with one tiny all-gather — and is refined over
+a few short balancing passes before the frame starts (their samples are discarded; they are part of the warm-up, not of the frame).
+Random streams are keyed by the global pixel index and the frame number, so the image is the same bits whatever the cut and whatever N.
+
+torch is plumbing here: device memory for the tile buffer, CUDA events, torch.distributed for NCCL.
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+from . import sharding
+
+
+class TiledPathTracer:
+    def __init__(self, dev, lc, scenes, width=3840, height=2160, nx=1582, spp_per_dispatch=16, depth=5, block=8, streams=2, rank=0, world=1, dist=None):
+        import torch
+        from . import examples_ir
+        self.torch, self.dist, self.dev, self.lc = torch, dist, dev, lc
+        self.width, self.height, self.rank, self.world = width, height, rank, world
+        self.spp_per_dispatch, self.depth = spp_per_dispatch, depth
+        self.s = dev.default_stream()
+        self.ext = torch.cuda.ExternalStream(self.s.cuda_stream())
+        # ---- scene: 10 terrain instances on a 5 x 2 grid (yaw 36 deg * k) + one emissive quad above ----
+        verts, tris = scenes.terrain(nx)
+        quad_v = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 1], [0, 0, 1]], np.float32)
+        quad_t = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+        self.vb, self.ib = dev.create_buffer_from_array(verts), dev.create_buffer_from_array(tris)
+        self.qvb, self.qib = dev.create_buffer_from_array(quad_v), dev.create_buffer_from_array(quad_t)
+        self.mesh = dev.create_mesh(self.vb.view(), self.ib.view(), lc.AccelOption())
+        self.quad = dev.create_mesh(self.qvb.view(), self.qib.view(), lc.AccelOption())
+        self.mesh.build(lc.AccelBuildRequest.FORCE_BUILD); self.quad.build(lc.AccelBuildRequest.FORCE_BUILD)
+        self.mesh.build(lc.AccelBuildRequest.FORCE_BUILD)
+        self.blas_ms = self.mesh.stats()["build_ms"]
+        self.triangles = int(tris.shape[0]) * 10 + 2
+        self.accel = dev.create_accel(lc.AccelOption())
+        for k in range(10):
+            t = np.eye(4, dtype=np.float32); t[:3, :] = scenes.rotation_y(36.0 * k)
+            t[:3, 3] = [1.2 * (k % 5), 0.0, 1.2 * (k // 5)]
+            self.accel.push_mesh(self.mesh, t)
+        l_pos, l_u, l_v = (2.0, 1.6, 0.2), (2.0, 0.0, 0.0), (0.0, 0.0, 1.6)
+        t = np.eye(4, dtype=np.float32); t[0, 0], t[2, 2] = l_u[0], l_v[2]; t[:3, 3] = l_pos
+        self.accel.push_mesh(self.quad, t)
+        self.accel.build(lc.AccelBuildRequest.FORCE_BUILD)
+        self.tlas_ms = self.accel.stats()["build_ms"]
+        n_inst = 11
+        self.vheap, self.iheap = dev.create_bindless_array(n_inst), dev.create_bindless_array(n_inst)
+        for i in range(n_inst):
+            self.vheap.emplace_buffer_async(i, self.vb if i < 10 else self.qvb); self.iheap.emplace_buffer_async(i, self.ib if i < 10 else self.qib)
+        self.s.submit([self.vheap.update_async(), self.iheap.update_async()])
+        cam_o, cam_at = np.float32([3.0, 2.5, -3.0]), np.float32([3.0, 0.0, 1.0])
+        f = cam_at - cam_o; f /= np.linalg.norm(f)
+        r = np.cross(f, np.float32([0, 1, 0])); r /= np.linalg.norm(r)
+        u = np.cross(r, f)
+        camera = (tuple(map(float, cam_o)), tuple(map(float, f)), tuple(map(float, r)), tuple(map(float, u)), float(np.tan(np.radians(45.0) / 2)))
+        light = (l_pos, l_u, l_v, (60.0, 54.0, 45.0), 10)
+        self.kernel = examples_ir.tiled_path_tracer_kernel(self.vheap.handle.id, self.iheap.handle.id, camera, light, n_inst, spp_per_dispatch, depth, block=block)
+        self.shader = dev.create_shader(C.addressof(self.kernel.km), keep=self.kernel)
+        # ---- tiles ----
+        self.tile = sharding.TILE
+        self.order_tx, self.order_ty = sharding.tile_order(width, height)
+        self.n_tiles = int(self.order_tx.shape[0])
+        self.tiles_x = (width + self.tile - 1) // self.tile
+        self.all_tile_ids = dev.create_buffer_from_array((self.order_ty * self.tiles_x + self.order_tx).astype(np.uint32))   # Morton order
+        self.cost = np.ones(self.n_tiles)
+        self.lanes = [self.s] + [dev.create_stream() for _ in range(max(1, streams) - 1)]
+        self.join = dev.create_event()
+        self.serial = 0
+        self.counters_t = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self.counters = dev.wrap_device_memory(self.counters_t.data_ptr(), 2, 8, 8)
+        self.out_t = self.out = None
+        self.set_bounds(sharding.balanced_bounds(self.cost, world))
+
+    def set_bounds(self, bounds):
+        """this rank renders tiles [bounds[rank], bounds[rank + 1]) of the Morton order; tile buffers are padded to the longest range"""
+        torch = self.torch
+        self.bounds = np.asarray(bounds, np.int64)
+        self.b0, self.b1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        cap = int(np.max(np.diff(self.bounds))) * self.tile * self.tile
+        if self.out_t is None or self.out_t.shape[0] != cap:
+            if self.out is not None:
+                self.out.destroy()
+            self.out_t = torch.zeros((cap, 4), dtype=torch.float32, device="cuda")
+            self.out = self.dev.wrap_device_memory(self.out_t.data_ptr(), cap, 16, 16)
+        else:
+            self.out_t.zero_()
+        torch.cuda.synchronize()
+
+    def render(self, n_dispatch, first_frame):
+        """enqueue n_dispatch passes of spp_per_dispatch samples over this rank's range; the range is split over the lanes (streams) so
+        that the tail of one dispatch overlaps the other lane's work; all lanes are joined into the default stream"""
+        tile, n = self.tile, self.b1 - self.b0
+        edges = np.linspace(0, n, len(self.lanes) + 1).astype(int)
+        for li, lane in enumerate(self.lanes):
+            a, b = int(edges[li]), int(edges[li + 1])
+            if b == a:
+                continue
+            lane.submit([self.shader.dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view(a * tile * tile, (b - a) * tile * tile), self.accel,
+                                                    np.array([self.width, self.height, first_frame + i, b - a], np.uint32), self.counters) for i in range(n_dispatch)])
+        self.serial += 1
+        for li, lane in enumerate(self.lanes[1:], 1):
+            self.join.signal(lane, self.serial * 16 + li); self.join.wait(self.s, self.serial * 16 + li)
+
+    def timed(self, fn):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.ext); fn(); e1.record(self.ext); self.s.synchronize()
+        return e0.elapsed_time(e1)
+
+    def all_times(self, ms):
+        torch = self.torch
+        if self.world == 1:
+            return [ms]
+        t = torch.tensor([ms], device="cuda"); out = torch.empty(self.world, device="cuda")
+        self.dist.all_gather_into_tensor(out, t)
+        return [float(x) for x in out.tolist()]
+
+    def balance(self, passes=4, frame0=100000):
+        """refine the cost map from per-rank times of short passes and re-cut the ranges (samples discarded)"""
+        history = []
+        for p in range(passes):
+            ms = self.timed(lambda: self.render(1, frame0 + p))
+            times = self.all_times(ms)
+            history.append(max(times) / (sum(times) / len(times)))
+            self.cost = sharding.refine_cost(self.cost, self.bounds, times)
+            self.set_bounds(sharding.balanced_bounds(self.cost, self.world))
+        return history
+
+    def gather(self):
+        """the one collective: all-gather of the padded per-rank tile buffers (stream-ordered after the render on the default stream)"""
+        torch = self.torch
+        if self.world == 1:
+            return self.out_t[None]
+        if getattr(self, "_gathered", None) is None or self._gathered.shape[1] != self.out_t.shape[0]:
+            self._gathered = torch.empty((self.world,) + tuple(self.out_t.shape), dtype=self.out_t.dtype, device="cuda")
+        with torch.cuda.stream(self.ext):
+            self.dist.all_gather_into_tensor(self._gathered.view(-1), self.out_t.view(-1))
+        return self._gathered
+
+    def frame(self, spp, first_frame=0):
+        """one frame: render spp samples per pixel AND gather the framebuffer, timed as one region on the device; returns (ms, gathered)"""
+        n_dispatch = max(1, spp // self.spp_per_dispatch)
+        self.out_t.zero_(); self.counters_t.zero_(); self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        box = {}
+
+        def work():
+            self.render(n_dispatch, first_frame)
+            box["g"] = self.gather()
+        ms = self.timed(work)
+        self.torch.cuda.synchronize()
+        return ms, box["g"], n_dispatch
+
+    def image(self, gathered):
+        return sharding.untile_ranges(gathered.cpu().numpy(), self.width, self.height, self.bounds)
+
+    @staticmethod
+    def sha(img):
+        return hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
+
+    def destroy(self):
+        for r in (self.shader, self.vheap, self.iheap, self.all_tile_ids, self.out, self.counters, self.accel, self.mesh, self.quad, self.vb, self.ib, self.qvb, self.qib):
+            r.destroy()
+        for lane in self.lanes[1:]:
+            lane.destroy()

@@ -391,6 +391,56 @@ def test_stream_ordering_events_and_callbacks(device):
     s1.destroy(); s2.destroy(); ev.destroy(); a.destroy(); b.destroy()
 
 
+def test_timeline_events_wait_before_signal_and_monotone_counter(device):
+    """EventImpl semantics (cpu/resource.rs:10-44, cpu/mod.rs:367-402): wait is enqueued, never blocks the caller, so a wait issued
+    before its signal — from the same host thread — completes once the signal arrives; the counter is a fetch_max; value 0 of a fresh
+    event is complete; thousands of signals on one event leave nothing behind."""
+    s1, s2 = device.create_stream(), device.create_stream()
+    ev = device.create_event()
+    assert ev.is_completed(0) and not ev.is_completed(1)
+    ev.synchronize(0)                                   # returns at once on a fresh event
+    a = device.create_buffer(1 << 20, 4); b = device.create_buffer(1 << 20, 4)
+    src = np.arange(1 << 20, dtype=np.uint32); dst = np.zeros_like(src)
+    ev.wait(s2, 5)                                      # wait first ...
+    s2.submit([b.view().copy_to_async(dst)])
+    assert not ev.is_completed(5)
+    s1.submit([a.view().copy_from_async(src), a.view().copy_to_buffer_async(b.view())])
+    ev.signal(s1, 5)                                    # ... signal afterwards, same host thread
+    s2.synchronize()
+    assert np.array_equal(src, dst) and ev.is_completed(5) and ev.is_completed(3) and not ev.is_completed(6)
+    ev.signal(s1, 2)                                    # a smaller value never lowers the counter
+    s1.synchronize()
+    assert ev.is_completed(5)
+    for v in range(6, 3006):                            # per-frame signalling: one counter, no per-signal objects
+        ev.signal(s1, v)
+        if v % 500 == 0:
+            ev.wait(s2, v)
+    ev.synchronize(3005)
+    assert ev.is_completed(3005) and not ev.is_completed(3006)
+    s1.synchronize(); s2.synchronize()
+    s1.destroy(); s2.destroy(); ev.destroy(); a.destroy(); b.destroy()
+
+
+def test_upload_sources_are_snapshotted_before_dispatch_returns(device):
+    """BufferUpload only borrows its source until dispatch() returns (cpu/stream.rs:33-64 copies it into staging buffers): the caller may
+    overwrite or free it right after submit — also when it is pinned memory, which a plain cudaMemcpyAsync would still be reading."""
+    import torch
+    n = 1 << 24                                             # 64 MiB: long enough for a late DMA read to be caught
+    stream = device.create_stream()
+    buf = device.create_buffer(n, 4)
+    for pinned in (True, False):
+        host = torch.arange(n, dtype=torch.int32)
+        if pinned:
+            host = host.pin_memory()
+        src = host.numpy().view(np.uint32)
+        stream.submit([buf.view().copy_from_async(src)])
+        src[:] = 0xDEADBEEF                                 # the borrow has ended
+        stream.synchronize()
+        got = buf.view().to_numpy(np.uint32)
+        assert np.array_equal(got, np.arange(n, dtype=np.uint32)), f"pinned={pinned}: {(got != np.arange(n, dtype=np.uint32)).sum()} words changed under the copy"
+    buf.destroy(); stream.destroy()
+
+
 def test_counted_traversal_matches_and_reports_work(device):
     desc = scenes.c3_soup(20000, seed=61)
     rays = scenes.incoherent_rays(50000, seed=62)

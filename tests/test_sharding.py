@@ -79,3 +79,65 @@ def test_gloo_world2_gather_reassembles_the_framebuffer(tmp_path):
     want = np.stack([px, px * 2, px % 7, np.ones_like(px)], 1).astype(np.float32).reshape(h, w, 4)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"img{r}.npy"), want)
+
+
+# ---- cost-balanced contiguous partition (sharding.balanced_bounds / refine_cost / untile_ranges) ---------------------------------------
+def test_balanced_bounds_cut_equal_cost_and_keep_ranges_non_empty():
+    rng = np.random.default_rng(0)
+    cost = np.exp(rng.normal(size=2040) * 0.5) * (1 + 2 * np.sin(np.arange(2040) / 300) ** 2)
+    for world in (1, 2, 3, 4, 8):
+        b = sh.balanced_bounds(cost, world)
+        assert b[0] == 0 and b[-1] == 2040 and np.all(np.diff(b) > 0) and b.shape[0] == world + 1
+        sums = np.array([cost[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert sums.max() / sums.mean() < 1.01            # one tile is ~0.05 % of the total
+    # degenerate inputs: all cost in one tile, fewer tiles than ranks is not asked for, exactly `world` tiles
+    spike = np.full(16, 1e-9); spike[5] = 1.0
+    b = sh.balanced_bounds(spike, 4)
+    assert np.all(np.diff(b) > 0) and b[-1] == 16
+    assert np.array_equal(sh.balanced_bounds(np.ones(8), 8), np.arange(9))
+
+
+def test_cost_map_refinement_converges_from_per_rank_times_only():
+    """what the renderer does between passes: only ONE number per rank is measured, yet the cut converges to balance"""
+    rng = np.random.default_rng(1)
+    true = np.exp(rng.normal(size=2040) * 0.5) * (1 + 3 * (np.arange(2040) > 1400))
+    for world in (2, 4, 8):
+        cost = np.ones(2040)
+        imbalance = []
+        for _ in range(5):
+            b = sh.balanced_bounds(cost, world)
+            times = [true[b[r]:b[r + 1]].sum() for r in range(world)]
+            imbalance.append(max(times) / np.mean(times))
+            cost = sh.refine_cost(cost, b, times)
+        assert imbalance[0] > 1.2 and imbalance[-1] < 1.03, imbalance
+
+
+def _range_worker(rank, world, port, w, h, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_tiles = sh.tile_order(w, h)[0].shape[0]
+    cost = 1.0 + np.arange(n_tiles) % 5                      # every rank holds the same map (it is built from all-gathered times)
+    bounds = sh.balanced_bounds(cost, world)
+    tx, ty = sh.tiles_of_range(w, h, int(bounds[rank]), int(bounds[rank + 1]))
+    idx, valid = sh.pixels_of_tiles(tx, ty, w, h)
+    per_rank = int(np.max(np.diff(bounds))) * sh.TILE * sh.TILE   # ranks pad to the longest range: one all-gather of equal counts
+    local = torch.zeros(per_rank, 4)
+    vals = torch.from_numpy(np.stack([idx, idx * 2, idx % 7, np.ones_like(idx)], 1).astype(np.float32))
+    vals[~torch.from_numpy(valid)] = 0
+    local[: idx.shape[0]] = vals
+    g = sh.gather_tiles(local, dist, world)
+    np.save(os.path.join(out_dir, f"img{rank}.npy"), sh.untile_ranges(g.numpy(), w, h, bounds))
+    # the per-rank times travel the same way: one value per rank
+    t = sh.gather_tiles(torch.tensor([float(rank + 1)]), dist, world)
+    assert t.reshape(-1).tolist() == [float(r + 1) for r in range(world)]
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_of_unequal_contiguous_ranges(tmp_path):
+    w, h, world = 200, 136, 2
+    mp.spawn(_range_worker, args=(world, _free_port(), w, h, str(tmp_path)), nprocs=world, join=True)
+    px = np.arange(w * h)
+    want = np.stack([px, px * 2, px % 7, np.ones_like(px)], 1).astype(np.float32).reshape(h, w, 4)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"img{r}.npy"), want)
