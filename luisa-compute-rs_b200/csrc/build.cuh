@@ -39,17 +39,17 @@ struct BuildScratch {
 BuildScratch build_scratch_layout(void *base, uint32_t n);
 
 // Full build: prim boxes -> Morton -> sort -> fused hierarchy+refit -> collapse to WideNode + leaves.
-// `nodes` has capacity `n` nodes; `tris` capacity `n` (BLAS) / `prim_ids` capacity n (TLAS).
+// `nodes` has room for `capacity` wide nodes (the builder raises its error flag beyond that); `tris` capacity `n` (BLAS) / `prim_ids` capacity n (TLAS).
 // builder: how the binary tree over the Morton-sorted primitives is formed — the LBVH split rule (k_hierarchy), PLOC (agglomerative
 // clustering, k_ploc_*), or chosen per mesh from the primitives' overlap (kBuilderAuto).
 enum { kBuilderLbvh = 0, kBuilderPloc = 1, kBuilderAuto = 2 };
 // returns the builder that ran (kBuilderLbvh / kBuilderPloc)
-int build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder);
+int build_blas(cudaStream_t s, uint32_t n_tris, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *tris, LaunchCounter &lc, int builder);
 // Procedural primitives: a BLAS over user AABBs (24-byte {min, max} records); leaf slots hold the box and the primitive id.
-void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc);
+void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc);
 // Curves: a BLAS over the rounded-cone pieces of the segments (trace_device.cuh "curves"); n = seg_count * pieces per segment.
 struct CurveInput { const uint8_t *cps; size_t cp_stride; const uint32_t *segs; uint32_t basis; uint32_t pieces; };
-void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc);
+void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc);
 void build_tlas(cudaStream_t s, uint32_t n_active, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc,
                 WideNode *nodes, uint32_t *prim_ids, LaunchCounter &lc);
 

@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, PackedTri *
 __global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) { queue[0] = (unsigned long long)h->root; }
 
 template <class Sink>
-void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, const Sink &sink, LaunchCounter &lc, bool ploc) {
+void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, const Sink &sink, LaunchCounter &lc, bool ploc) {
     // Morton resolution follows the primitive count: log2(n) bits only enumerate the primitives, the rest resolves non-uniform
     // density — 12 extra bits measured as good as 28 on the bench scenes (profiles/r01r_sort_passes.txt); each pass saved is one
     // sweep over the pairs (24 B per pair).  LC_B200_SORT_PASSES overrides (3..6).
@@ -897,7 +897,7 @@ void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc
     }
     uint32_t blocks = (n / 6 + kCollapseGroups - 1) / kCollapseGroups + 1;
     if (blocks > (uint32_t)max_blocks) blocks = (uint32_t)max_blocks;
-    const BinNode *a_bin = sc.bin; const uint32_t *a_vals = vals; uint32_t a_n = n, a_cap = n; BuildHeader *a_h = sc.header;
+    const BinNode *a_bin = sc.bin; const uint32_t *a_vals = vals; uint32_t a_n = n, a_cap = capacity; BuildHeader *a_h = sc.header;
     unsigned long long *a_queue = sc.queue; WideNode *a_nodes = nodes; Sink a_sink = sink;
     void *args[] = {&a_bin, &a_vals, &a_n, &a_h, &a_queue, &a_nodes, &a_cap, &a_sink};
     cudaLaunchCooperativeKernel((const void *)k_collapse<Sink>, dim3(blocks), dim3(kCollapseThreads), args, 0, s); lc.count++;
@@ -931,7 +931,7 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
     return sc;
 }
 
-int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *tris, LaunchCounter &lc, int builder) {
+int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *tris, LaunchCounter &lc, int builder) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
@@ -949,26 +949,26 @@ int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildS
         use_ploc = scene > 0.f && hdr.prim_area_sum < 4.0f * scene;
     }
     LeafSinkTriangles sink{tris};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, use_ploc);
+    run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, use_ploc);
     k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
     return use_ploc && n > 1 ? kBuilderPloc : kBuilderLbvh;
 }
 
-void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc) {
+void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_aabb_boxes<<<(n + 255) / 256, 256, 0, s>>>(aabbs, n, sc.boxes, sc.header); lc.count++;
     LeafSinkTriangles sink{slots};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);
+    run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
     k_pack_aabbs<<<(n + 255) / 256, 256, 0, s>>>(aabbs, slots, n); lc.count++;
 }
 
-void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, PackedTri *slots, LaunchCounter &lc) {
+void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_curve_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
     LeafSinkTriangles sink{slots};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);
+    run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
     k_pack_curves<<<(n + 255) / 256, 256, 0, s>>>(in, slots, n); lc.count++;
 }
 
@@ -978,7 +978,7 @@ void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const In
     k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
     k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
     LeafSinkInstances sink{active_ids, prim_ids};
-    run_pipeline_after_boxes(s, n, sc, nodes, sink, lc, false);  // a handful of instances: the LBVH order is as good as any
+    run_pipeline_after_boxes(s, n, sc, nodes, n, sink, lc, false);  // a handful of instances: the LBVH order is as good as any; the node array holds n
 }
 
 // ---- refit (MeshBuild with PreferUpdate on an updatable mesh; GeometryImpl::build_mesh, cpu/accel.rs:251-258) ----

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <deque>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -31,6 +32,13 @@
 using namespace lcb;
 
 namespace {
+
+// NVTX ranges around build stages and dispatches (what the reference's CUDA backend marks in cuda_primitive.cpp:22,53,84,113): visible to
+// nsys / ncu --nvtx, free when no tool is attached (nvtx3 is header-only and resolves the injection library lazily).
+struct nvtx_range {
+    explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
 
 // ---- logging / errors ------------------------------------------------------------------------
 std::atomic<void (*)(lcb_logger_message)> g_logger{nullptr};
@@ -135,6 +143,38 @@ static void zero_fill(void *p, size_t bytes) {
 // ---- backend objects ---------------------------------------------------------------------------
 struct BufferObj { uint8_t *ptr = nullptr; size_t size = 0; bool owned = true; };
 
+// A build command is enqueued and dispatch() returns (cpu/mod.rs:168-180 enqueues and returns; cuda_primitive.cpp:20-110 builds on the
+// stream): what the host wants to know about the finished build — node count, depth, the builder's error flag, the device time — is
+// copied into pinned memory behind the build and picked up lazily, when somebody asks (stats, the next build of the same object, a
+// refit that needs the node count, destroy).
+struct PendingBuild {
+    bool active = false;
+    BuildHeader *h_hdr = nullptr;   // pinned
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    void begin(cudaStream_t st) {
+        if (!h_hdr) {
+            CUDA_CHECK(cudaHostAlloc((void **)&h_hdr, sizeof(BuildHeader), cudaHostAllocDefault));
+            CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        }
+        memset(h_hdr, 0, sizeof(BuildHeader));
+        CUDA_CHECK(cudaEventRecord(e0, st));
+    }
+    void end(cudaStream_t st, const BuildHeader *device_header) {
+        if (device_header) CUDA_CHECK(cudaMemcpyAsync(h_hdr, device_header, sizeof(BuildHeader), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        active = true;
+    }
+    float wait_ms() {  // blocks until the build has finished on the device
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        active = false;
+        return ms;
+    }
+    void destroy() {
+        if (h_hdr) { cudaFreeHost(h_hdr); cudaEventDestroy(e0); cudaEventDestroy(e1); h_hdr = nullptr; }
+    }
+};
+
 struct MeshObj {
     lcb_accel_option option{};
     bool built = false;
@@ -147,6 +187,8 @@ struct MeshObj {
     uint32_t n_nodes = 0, n_packed = 0, node_capacity = 0;
     RefitArrays refit{nullptr, nullptr, nullptr};  // side arrays of the refit path, allocated at the first PreferUpdate
     lcb_build_stats stats{};
+    PendingBuild pend;                             // the last MeshBuild as the stream will finish it (mesh_finalize folds it in)
+    bool pend_refit = false; int pend_builder = 0;
     std::mutex mu;
 };
 
@@ -166,8 +208,11 @@ struct AccelObj {
     uint32_t n_active = 0;
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     uint32_t *dirty = nullptr;  // device flag raised by kernels that edit the instance table (lc_set_instance_*)
-    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of modification records + active ids (grow-only; every build ends synchronised)
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of modification records + active ids (grow-only; reused once the previous build has finished)
     lcb_build_stats stats{};
+    PendingBuild pend;          // the last AccelBuild as the stream will finish it (accel_finalize folds it in)
+    uint32_t pend_instances = 0, pend_active = 0; bool pend_table_only = false;
+    bool maybe_dirty = false;   // a kernel that can edit the instance table (RayTracingSetInstance*) was dispatched with this accel since the last build
     std::mutex mu;
 };
 
@@ -240,7 +285,9 @@ struct StreamObj {
     DeviceObj *dev = nullptr;
     cudaStream_t stream = nullptr;
     unsigned long long *work_counter = nullptr;   // device: ray-pool counter for trace launches on this stream
-    struct Pending { cudaEvent_t ev; lcb_dispatch_callback cb; uint8_t *ctx; std::vector<std::pair<void *, size_t>> staged; /* pinned upload snapshots, back to the pool on completion */ };
+    struct CopyOut { void *dst; void *stage; size_t bytes, cap; };  // a download into pageable memory: pinned staging -> destination, by the stream's worker
+    struct Pending { cudaEvent_t ev; lcb_dispatch_callback cb; uint8_t *ctx; std::vector<std::pair<void *, size_t>> staged; /* pinned upload snapshots, back to the pool on completion */
+                     std::vector<CopyOut> copy_out; };
     std::mutex mu; std::condition_variable cv, drained;
     std::deque<Pending> pending;
     bool stop = false; size_t in_flight = 0;
@@ -258,6 +305,7 @@ struct StreamObj {
             cudaError_t e = cudaEventSynchronize(p.ev);
             if (e != cudaSuccess) fatal("stream failed: %s", cudaGetErrorString(e));
             cudaEventDestroy(p.ev);
+            for (auto &c : p.copy_out) { parallel_copy(c.dst, c.stage, c.bytes); g_pinned.give(c.stage, c.cap); }
             release_staged(p.staged);
             if (p.cb) p.cb(p.ctx);
             { std::lock_guard<std::mutex> lk(mu); in_flight--; }
@@ -284,6 +332,7 @@ struct DeviceObj {
     // rebuilding the same scene every frame (C4) then touches no allocator at all.  Stream-ordered pool allocations of these
     // multi-GB blocks made a rebuild after a few refits cost 15-30 ms instead of 8 (tools/micro/rebuild_probe.py).
     uint8_t *build_arena = nullptr; size_t build_arena_cap = 0;
+    cudaEvent_t arena_event = nullptr;   // recorded behind the last build that used the arena: the next build (any stream) waits for it on the device
     std::mutex build_mu;
     // event counters are read back on their own stream (never behind the user's work)
     cudaStream_t poll_stream = nullptr; unsigned long long *poll_word = nullptr; std::mutex poll_mu;
@@ -355,6 +404,7 @@ void destroy_stream(lcb_device dev, lcb_stream h) { DeviceObj *d = dev_of(dev); 
 
 // ---- mesh build (GeometryImpl::build_mesh, cpu/accel.rs:205-260) ---------------------------------
 void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs, const CurveInput *curve = nullptr);
+void accel_finalize(AccelObj *a);
 
 void mesh_build(DeviceObj *d, StreamObj *s, const lcb_cmd_mesh_build &c) {
     MeshObj *m = as<MeshObj>(c.mesh.id);
@@ -407,16 +457,37 @@ void curve_build(DeviceObj *d, StreamObj *s, const lcb_cmd_curve_build &c) {
     blas_build(d, s, m, (uint32_t)(c.seg_count * pieces), LCB_REQUEST_FORCE_BUILD, TriangleInput{nullptr, 0, nullptr}, nullptr, &in);
 }
 
+// Fold a finished MeshBuild into the host-side record (PendingBuild comment).  Caller holds m->mu.
+void mesh_finalize(MeshObj *m) {
+    if (!m->pend.active) return;
+    const float ms = m->pend.wait_ms();
+    m->stats.build_ms = ms;
+    if (m->pend_refit) { m->stats.was_refit = 1; return; }
+    const BuildHeader &hdr = *m->pend.h_hdr;
+    const uint32_t n = m->n_tris;
+    if (hdr.error) fatal("BVH build failed (code %u: %s)", hdr.error, hdr.error == 1 ? "tree deeper than the traversal stack" : "node capacity exceeded");
+    if (hdr.emitted != n || hdr.prim_count != n) fatal("BVH build inconsistent: emitted %u of %u primitives", hdr.emitted, n);
+    m->n_nodes = hdr.node_count; m->n_packed = hdr.prim_count;
+    m->stats.wide_node_count = hdr.node_count; m->stats.packed_tri_count = hdr.prim_count;
+    m->stats.bvh_bytes = (uint64_t)hdr.node_count * sizeof(WideNode) + (uint64_t)n * sizeof(PackedTri);
+    m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.builder = (uint32_t)m->pend_builder;
+}
+
+// Wide nodes a tree over n primitives can have.  Every wide node absorbs at least min(7, kLeafMax) = 2 internal nodes of the binary
+// tree (k_collapse opens children until eight, or until every child is a single primitive; a subtree of <= kLeafMax primitives is a
+// leaf child, not a node), and the binary tree has n - 1 of them: at most (n - 1) / 2 wide nodes, the root included.  The node block is
+// allocated for that bound up front, which is what lets the build run without the host (no count to wait for, no compaction copy).
+static uint32_t wide_node_bound(uint32_t n) { return n / 2 + 2; }
+
 void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t request, const TriangleInput &in, const uint8_t *aabbs, const CurveInput *curve) {
-    struct { int32_t request; } c{request};
     cudaStream_t st = s->stream;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    CUDA_CHECK(cudaEventRecord(e0, st));
+    mesh_finalize(m);  // the previous build of this mesh (usually long finished): its node count is needed below, its record is reused
     // PreferUpdate on a built, updatable mesh is a vertex-update refit (accel.rs:251-257; the OptiX backend's rule —
     // rebuild when updates are not allowed, the mesh was never built or its size changed — is cuda_mesh.cpp:42-68).
     // The BVH aliases the user buffers like Embree's shared geometry buffers (accel.rs:217-237): vertices are re-read now.
-    if (c.request == LCB_REQUEST_PREFER_UPDATE && m->built && m->option.allow_update && n == m->n_tris && n > 0 && m->nodes) {
+    if (request == LCB_REQUEST_PREFER_UPDATE && m->built && m->option.allow_update && n == m->n_tris && n > 0 && m->nodes) {
+        nvtx_range range("lc_b200 MeshBuild (refit)");
+        m->pend.begin(st);
         if (!m->refit.parent) {
             CUDA_CHECK(cudaMallocAsync((void **)&m->refit.parent, (size_t)m->n_nodes * 4, st));
             CUDA_CHECK(cudaMallocAsync((void **)&m->refit.boxes, (size_t)m->n_nodes * 24, st));
@@ -424,82 +495,57 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
             build_refit_arrays(st, m->n_nodes, m->nodes, m->refit, d->lc);
         }
         refit_blas(st, m->n_nodes, n, in, m->nodes, m->tris, m->refit, nullptr, d->lc);
-        CUDA_CHECK(cudaEventRecord(e1, st));
-        CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        m->stats.was_refit = 1; m->stats.build_ms = ms;
+        m->pend_refit = true;
+        m->pend.end(st, nullptr);
         return;
     }
+    nvtx_range range("lc_b200 MeshBuild (build)");
     if (m->refit.parent) {
         CUDA_CHECK(cudaFreeAsync(m->refit.parent, st)); CUDA_CHECK(cudaFreeAsync(m->refit.boxes, st)); CUDA_CHECK(cudaFreeAsync(m->refit.counters, st));
         m->refit = RefitArrays{nullptr, nullptr, nullptr};
     }
-    // The mesh keeps its triangle block when the triangle count is unchanged and its node block when the new tree fits;
-    // everything transient lives in the device's build arena.
+    // The mesh keeps its triangle and node blocks when the triangle count is unchanged; everything transient lives in the device's
+    // build arena.
     if (m->tris && n != m->n_tris) { CUDA_CHECK(cudaFreeAsync(m->tris, st)); m->tris = nullptr; }
-    if (n == 0 && m->nodes) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; m->node_capacity = 0; }
+    const uint32_t capacity = n ? wide_node_bound(n) : 0;
+    if (m->nodes && m->node_capacity != capacity) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; m->node_capacity = 0; }
     m->built = true; m->n_tris = n; m->generation++;
     m->n_nodes = m->n_packed = 0;
     memset(&m->stats, 0, sizeof(m->stats));
     m->stats.primitive_count = n;
-    if (n == 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return; }
-    std::lock_guard<std::mutex> arena_lock(d->build_mu);
+    if (n == 0) return;
+    std::lock_guard<std::mutex> arena_lock(d->build_mu);  // held while the build is enqueued, not while it runs
     const BuildScratch layout = build_scratch_layout(nullptr, n);
-    const size_t staging_off = (layout.total_bytes + 255) / 256 * 256, staging_bytes = (size_t)n * sizeof(WideNode);
-    const bool compact = m->option.allow_compaction;
-    const size_t arena_need = staging_off + (compact ? staging_bytes : 0);
-    if (arena_need > d->build_arena_cap) {
-        CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!d->arena_event) CUDA_CHECK(cudaEventCreateWithFlags(&d->arena_event, cudaEventDisableTiming));
+    else CUDA_CHECK(cudaStreamWaitEvent(st, d->arena_event, 0));  // the arena's previous user may be running on another stream
+    if (layout.total_bytes > d->build_arena_cap) {
+        CUDA_CHECK(cudaDeviceSynchronize());  // growing the arena: rare (sizes only grow), and nothing may still be using the old block
         if (d->build_arena) CUDA_CHECK(cudaFree(d->build_arena));
-        d->build_arena_cap = arena_need + arena_need / 8;
+        d->build_arena_cap = layout.total_bytes + layout.total_bytes / 8;
         CUDA_CHECK(cudaMalloc((void **)&d->build_arena, d->build_arena_cap));
     }
     BuildScratch sc = build_scratch_layout(d->build_arena, n);
     if (!m->tris) CUDA_CHECK(cudaMallocAsync((void **)&m->tris, (size_t)n * sizeof(PackedTri), st));
-    WideNode *target = nullptr;
-    if (compact) target = reinterpret_cast<WideNode *>(d->build_arena + staging_off);
-    else {
-        if (m->nodes && m->node_capacity != n) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
-        if (!m->nodes) { CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, staging_bytes, st)); m->node_capacity = n; }
-        target = m->nodes;
-    }
+    if (!m->nodes) { CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, (size_t)capacity * sizeof(WideNode), st)); m->node_capacity = capacity; }
     // AccelUsageHint (api_types:204-212; the CPU backend maps it to Embree build quality, cpu/accel.rs:49-63): FastTrace (the default)
     // lets the builder choose between PLOC and the LBVH split rule per mesh, FastBuild always takes the LBVH.
     // LC_B200_BUILDER=lbvh|ploc|auto overrides.
     const int forced = g_builder_override.load();
     int builder = forced >= 0 ? forced : (m->option.hint == LCB_HINT_FAST_TRACE ? kBuilderAuto : kBuilderLbvh);
-    // the per-mesh choice reads a statistic back from the device (one stream synchronisation); a rebuild of the same mesh with the
-    // same triangle count reuses the previous answer
+    // the per-mesh choice reads a statistic back from the device (one stream synchronisation, and PLOC reads its live cluster count
+    // back between chunks of iterations); a rebuild of the same mesh with the same triangle count reuses the previous answer, and the
+    // LBVH pipeline never touches the host
     const bool was_auto = builder == kBuilderAuto;
     if (was_auto && m->auto_builder >= 0 && m->auto_builder_n == n) builder = m->auto_builder;
+    m->pend.begin(st);
     int built_with = kBuilderLbvh;
-    if (curve) build_curves(st, n, *curve, sc, target, m->tris, d->lc);
-    else if (aabbs) build_procedural(st, n, aabbs, sc, target, m->tris, d->lc);
-    else built_with = build_blas(st, n, in, sc, target, m->tris, d->lc, builder);
+    if (curve) build_curves(st, n, *curve, sc, m->nodes, capacity, m->tris, d->lc);
+    else if (aabbs) build_procedural(st, n, aabbs, sc, m->nodes, capacity, m->tris, d->lc);
+    else built_with = build_blas(st, n, in, sc, m->nodes, capacity, m->tris, d->lc, builder);
     if (was_auto) { m->auto_builder = built_with; m->auto_builder_n = n; }
-    BuildHeader hdr;
-    CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));  // compaction needs the counts (the OptiX backend syncs here too: cuda_primitive.cpp:74-80)
-    if (hdr.error) fatal("BVH build failed (code %u: %s)", hdr.error, hdr.error == 1 ? "tree deeper than the traversal stack" : "node capacity exceeded");
-    if (hdr.emitted != n || hdr.prim_count != n) fatal("BVH build inconsistent: emitted %u of %u primitives", hdr.emitted, n);
-    m->n_nodes = hdr.node_count; m->n_packed = hdr.prim_count;
-    if (compact) {
-        // keep the old block if the new tree fits without wasting more than a quarter of it
-        if (m->nodes && (m->node_capacity < hdr.node_count || (size_t)m->node_capacity * 3 > (size_t)hdr.node_count * 4 + 1024)) { CUDA_CHECK(cudaFreeAsync(m->nodes, st)); m->nodes = nullptr; }
-        if (!m->nodes) {
-            m->node_capacity = hdr.node_count + hdr.node_count / 16;
-            CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, (size_t)m->node_capacity * sizeof(WideNode), st));
-        }
-        CUDA_CHECK(cudaMemcpyAsync(m->nodes, target, (size_t)hdr.node_count * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
-    }
-    CUDA_CHECK(cudaEventRecord(e1, st));
-    CUDA_CHECK(cudaEventSynchronize(e1));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    m->stats.wide_node_count = hdr.node_count; m->stats.packed_tri_count = hdr.prim_count;
-    m->stats.bvh_bytes = (uint64_t)m->node_capacity * sizeof(WideNode) + (uint64_t)n * sizeof(PackedTri);
-    m->stats.max_depth = hdr.max_depth; m->stats.was_refit = 0; m->stats.build_ms = ms; m->stats.builder = (uint32_t)built_with;
+    m->pend_refit = false; m->pend_builder = built_with;
+    m->pend.end(st, sc.header);
+    CUDA_CHECK(cudaEventRecord(d->arena_event, st));
 }
 
 // ---- accel build (AccelImpl::update, cpu/accel.rs:324-447) ---------------------------------------
@@ -521,13 +567,14 @@ void invert_affine(const float m[12], float inv[12]) {
 void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
     AccelObj *a = as<AccelObj>(c.accel.id);
     std::lock_guard<std::mutex> lk(a->mu);
+    nvtx_range range("lc_b200 AccelBuild");
     cudaStream_t st = s->stream;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    CUDA_CHECK(cudaEventRecord(e0, st));
+    accel_finalize(a);  // the previous build of this accel (its pinned staging block and record are reused)
     // Kernels may have edited the instance table (RayTracingSetInstance*): fold those edits into the host mirror first, so that this
-    // build (and its TLAS) sees them and later modifications apply on top.
-    if (a->dirty && a->table) {
+    // build (and its TLAS) sees them and later modifications apply on top.  Only kernels that contain such a call raise maybe_dirty
+    // (shader_dispatch), so ordinary frames — path tracers, ray queries — never wait for the stream here.
+    if (a->maybe_dirty && a->dirty && a->table) {
+        a->maybe_dirty = false;
         uint32_t flag = 0;
         CUDA_CHECK(cudaMemcpyAsync(&flag, a->dirty, 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
@@ -545,6 +592,7 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
             }
         }
     }
+    a->pend.begin(st);
     const uint32_t n = c.instance_count;
     a->instances.resize(n);  // grow with default (invalid) slots / pop from the back (accel.rs:345-353)
     std::vector<uint8_t> touched(n, 0);
@@ -591,6 +639,9 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         r.flags = (in.valid ? 1u : 0u) | (in.opaque ? 2u : 0u) | (in.valid && in.mesh->procedural ? 4u : 0u) | (in.valid && in.mesh->curve ? 8u : 0u);
         memcpy(r.affine, in.affine, sizeof(r.affine));
         invert_affine(in.affine, r.inv);
+        bool identity = true;  // bit 4: the inverse is exactly the identity, zeros of either sign (trace_device.cuh enter_instance)
+        for (int k = 0; k < 12; k++) identity = identity && r.inv[k] == ((k == 0 || k == 5 || k == 10) ? 1.0f : 0.0f);
+        if (identity) r.flags |= 16u;
         if (in.valid) { r.nodes = in.mesh->nodes; r.tris = in.mesh->tris; in.mesh_generation = in.mesh->generation; }
         recs.push_back(r);
     }
@@ -611,8 +662,8 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
     }
     a->stats.primitive_count = n;
     if (c.update_instance_buffer_only) {  // accel.rs:428-430
-        CUDA_CHECK(cudaStreamSynchronize(st));  // the staging block is reused by the next build
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        a->pend_table_only = true;
+        a->pend.end(st, nullptr);
         return;
     }
     // TLAS over the active instances (request is ignored, as on the CPU backend: stream.rs:418-428)
@@ -634,27 +685,36 @@ void accel_build(DeviceObj *d, StreamObj *s, const lcb_cmd_accel_build &c) {
         CUDA_CHECK(cudaMallocAsync(&scratch, layout.total_bytes, st));
         BuildScratch sc = build_scratch_layout(scratch, na);
         build_tlas(st, na, a->active_ids, a->table, sc, a->tlas_nodes, a->tlas_prims, d->lc);
-        BuildHeader hdr;
-        CUDA_CHECK(cudaMemcpyAsync(&hdr, sc.header, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+        a->pend_instances = n; a->pend_active = na; a->pend_table_only = false;
+        a->pend.end(st, sc.header);
         CUDA_CHECK(cudaFreeAsync(scratch, st));
-        CUDA_CHECK(cudaEventRecord(e1, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+    } else {
+        a->pend_instances = n; a->pend_active = 0; a->pend_table_only = false;
+        a->pend.end(st, nullptr);
+    }
+}
+
+// Fold a finished AccelBuild into the host-side record.  Caller holds a->mu.
+void accel_finalize(AccelObj *a) {
+    if (!a->pend.active) return;
+    const float ms = a->pend.wait_ms();
+    if (a->pend_table_only) return;
+    const BuildHeader &hdr = *a->pend.h_hdr;
+    if (a->pend_active) {
         if (hdr.error) fatal("TLAS build failed (code %u)", hdr.error);
-        if (hdr.emitted != na) fatal("TLAS build inconsistent: emitted %u of %u instances", hdr.emitted, na);
+        if (hdr.emitted != a->pend_active) fatal("TLAS build inconsistent: emitted %u of %u instances", hdr.emitted, a->pend_active);
         for (int k = 0; k < 3; k++) { a->world_lo[k] = hdr.root_lo[k]; a->world_hi[k] = hdr.root_hi[k]; }
         a->stats.wide_node_count = hdr.node_count; a->stats.packed_tri_count = hdr.prim_count; a->stats.max_depth = hdr.max_depth;
-        a->stats.bvh_bytes = (uint64_t)hdr.node_count * sizeof(WideNode) + (uint64_t)n * sizeof(InstanceRec);
+        a->stats.bvh_bytes = (uint64_t)hdr.node_count * sizeof(WideNode) + (uint64_t)a->pend_instances * sizeof(InstanceRec);
     } else {
-        CUDA_CHECK(cudaEventRecord(e1, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
         a->stats.wide_node_count = 0; a->stats.packed_tri_count = 0; a->stats.max_depth = 0; a->stats.bvh_bytes = 0;
     }
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     a->stats.build_ms = ms; a->stats.was_refit = 0;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 AccelView view_of(AccelObj *a) {
+    if (a->pend.active && cudaEventQuery(a->pend.e1) == cudaSuccess) { std::lock_guard<std::mutex> lk(a->mu); accel_finalize(a); }  // world bounds, never blocks
+    else (void)cudaGetLastError();
     AccelView v{};
     v.tlas_nodes = a->n_active ? a->tlas_nodes : nullptr;
     v.tlas_prims = a->tlas_prims; v.instances = a->table; v.instance_count = (uint32_t)a->instances.size();
@@ -695,6 +755,21 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
         staged.emplace_back(stage, cap);
         CUDA_CHECK(cudaMemcpyAsync(dst, stage, n, cudaMemcpyHostToDevice, st));
     };
+    // Downloads never block the caller either: cudaMemcpyAsync into pageable memory would wait on the host until the copy has run — behind
+    // everything queued on the stream, an event wait included (the reference only enqueues, cpu/mod.rs:168-180).  Pinned destinations are
+    // written by the copy engine; pageable ones receive the bytes from a pinned staging block, copied by the stream's worker thread before
+    // the completion callback fires (the frontend keeps download destinations alive until then, runtime.rs:1019-1027).
+    std::vector<StreamObj::CopyOut> copy_out;
+    auto download = [&](void *dst, const void *src, size_t n) {
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (pinned) { CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st)); return; }
+        (void)cudaGetLastError();
+        size_t cap = 0;
+        void *stage = g_pinned.take(n, cap);
+        CUDA_CHECK(cudaMemcpyAsync(stage, src, n, cudaMemcpyDeviceToHost, st));
+        copy_out.push_back(StreamObj::CopyOut{dst, stage, n, cap});
+    };
     for (size_t i = 0; i < list.commands_count; i++) {
         const lcb_command &c = list.commands[i];
         switch (c.tag) {
@@ -707,7 +782,7 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
             case LCB_CMD_BUFFER_DOWNLOAD: {
                 BufferObj *b = as<BufferObj>(c.u.buffer_download.buffer.id);
                 if (c.u.buffer_download.offset + c.u.buffer_download.size > b->size) fatal("BufferDownload out of range");
-                if (c.u.buffer_download.size) CUDA_CHECK(cudaMemcpyAsync(c.u.buffer_download.data, b->ptr + c.u.buffer_download.offset, c.u.buffer_download.size, cudaMemcpyDeviceToHost, st));
+                if (c.u.buffer_download.size) download(c.u.buffer_download.data, b->ptr + c.u.buffer_download.offset, c.u.buffer_download.size);
                 break;
             }
             case LCB_CMD_BUFFER_COPY: {
@@ -725,7 +800,7 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
             case LCB_CMD_TEXTURE_DOWNLOAD: {
                 TextureObj *t = as<TextureObj>(c.u.texture_download.texture.id);
                 const size_t n = texture_region_bytes(t, c.u.texture_download.storage, c.u.texture_download.level, c.u.texture_download.size, "TextureDownload");
-                if (n) CUDA_CHECK(cudaMemcpyAsync(c.u.texture_download.data, t->ptr, n, cudaMemcpyDeviceToHost, st));
+                if (n) download(c.u.texture_download.data, t->ptr, n);
                 break;
             }
             case LCB_CMD_TEXTURE_COPY: {
@@ -760,7 +835,7 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
     StreamObj::Pending p{};
     CUDA_CHECK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventRecord(p.ev, st));
-    p.cb = cb; p.ctx = ctx; p.staged = std::move(staged);
+    p.cb = cb; p.ctx = ctx; p.staged = std::move(staged); p.copy_out = std::move(copy_out);
     s->push(std::move(p));
     for (cudaEvent_t ev : direct_copies) { CUDA_CHECK(cudaEventSynchronize(ev)); cudaEventDestroy(ev); }  // the borrow of those sources ends here
 }
@@ -839,6 +914,8 @@ lcb_created create_mesh(lcb_device dev, const lcb_accel_option *opt) { bind(dev_
 void destroy_mesh(lcb_device dev, lcb_mesh h) {
     bind(dev_of(dev));
     MeshObj *m = as<MeshObj>(h.id);
+    if (m->pend.active) m->pend.wait_ms();
+    m->pend.destroy();
     if (m->nodes) cudaFree(m->nodes);
     if (m->tris) cudaFree(m->tris);
     if (m->refit.parent) { cudaFree(m->refit.parent); cudaFree(m->refit.boxes); cudaFree(m->refit.counters); }
@@ -848,6 +925,8 @@ lcb_created create_accel(lcb_device dev, const lcb_accel_option *opt) { bind(dev
 void destroy_accel(lcb_device dev, lcb_accel h) {
     bind(dev_of(dev));
     AccelObj *a = as<AccelObj>(h.id);
+    if (a->pend.active) a->pend.wait_ms();
+    a->pend.destroy();
     if (a->table) cudaFree(a->table);
     if (a->tlas_nodes) { cudaFree(a->tlas_nodes); cudaFree(a->tlas_prims); cudaFree(a->active_ids); }
     if (a->h_stage) cudaFreeHost(a->h_stage);
@@ -958,6 +1037,7 @@ void shader_dispatch(DeviceObj *d, StreamObj *s, const lcb_cmd_shader_dispatch &
     auto put_accel = [&](const ParamSlot &p, uint64_t handle) {
         AccelObj *ao = as<AccelObj>(handle);
         if (!ao->dirty) { CUDA_CHECK(cudaMalloc((void **)&ao->dirty, 256)); zero_fill(ao->dirty, 256); }
+        if (k.writes_accel) ao->maybe_dirty = true;
         HostAccelArg a{view_of(ao), ao->table, ao->dirty}; memcpy(block.data() + p.offset, &a, sizeof(a));
     };
     for (const ParamSlot &p : k.captures) {  // bound at create_shader time (KernelModule.captures, cpu/mod.rs:296-301)
@@ -1332,8 +1412,8 @@ uint32_t lc_b200_instance_visibility_mask(lcb_device, lcb_accel ah, uint32_t i) 
     return a->instances[i].visible;
 }
 
-void lc_b200_mesh_stats(lcb_device, lcb_mesh h, lcb_build_stats *out) { MeshObj *m = as<MeshObj>(h.id); std::lock_guard<std::mutex> lk(m->mu); *out = m->stats; }
-void lc_b200_accel_stats(lcb_device, lcb_accel h, lcb_build_stats *out) { AccelObj *a = as<AccelObj>(h.id); std::lock_guard<std::mutex> lk(a->mu); *out = a->stats; }
+void lc_b200_mesh_stats(lcb_device dev, lcb_mesh h, lcb_build_stats *out) { bind(dev_of(dev)); MeshObj *m = as<MeshObj>(h.id); std::lock_guard<std::mutex> lk(m->mu); mesh_finalize(m); *out = m->stats; }
+void lc_b200_accel_stats(lcb_device dev, lcb_accel h, lcb_build_stats *out) { bind(dev_of(dev)); AccelObj *a = as<AccelObj>(h.id); std::lock_guard<std::mutex> lk(a->mu); accel_finalize(a); *out = a->stats; }
 
 void *lc_b200_stream_native(lcb_device, lcb_stream h) { return (void *)as<StreamObj>(h.id)->stream; }
 void *lc_b200_buffer_native(lcb_device, lcb_buffer h) { return as<BufferObj>(h.id)->ptr; }

@@ -247,6 +247,7 @@ struct Globals {
 struct ModuleScan {
     int trace_sites = 0;         // RayTracingTraceClosest / TraceAny calls in the kernel's own body, outside RayQuery callbacks
     bool block_features = false; // SynchronizeBlock, warp intrinsics
+    bool writes_accel = false;   // RayTracingSetInstance*: the kernel may edit an instance table
     size_t body_nodes = 0;       // IR nodes of the kernel body and of the callables it reaches: the size of the user phases
     uint32_t curve_bases = 0;
     std::unordered_set<NodeRef> accels;  // accel operands of those trace sites
@@ -896,6 +897,9 @@ void scan_block(const BasicBlock *bb, ModuleScan &sc, bool kernel_level) {
                 const Func &f = ins->call.func;
                 if (f.tag == Func::RayTracingTraceClosest || f.tag == Func::RayTracingTraceAny) {
                     if (kernel_level && ins->call.args.len == 3) { sc.trace_sites++; sc.accels.insert(ins->call.args[0]); }
+                } else if (f.tag == Func::RayTracingSetInstanceTransform || f.tag == Func::RayTracingSetInstanceVisibility || f.tag == Func::RayTracingSetInstanceOpacity ||
+                           f.tag == Func::RayTracingSetInstanceUserId) {
+                    sc.writes_accel = true;
                 } else if (f.tag == Func::SynchronizeBlock || f.tag == Func::WarpLaneId || (f.tag >= Func::WarpIsFirstActiveLane && f.tag <= Func::WarpReadFirstLane)) {
                     sc.block_features = true;
                 } else if (f.tag == Func::Callable) {
@@ -1001,6 +1005,7 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
                       scan.curve_bases == 0;
     fe.wave = wave;
     out.wave = wave;
+    out.writes_accel = scan.writes_accel;
     // Two knobs of the wavefront form, both set by how much user code runs between two trace calls (B200 sweeps,
     // profiles/r02a_dsl_c*_sweep.jsonl): a kernel that only moves rays and hits (config C3) wants its finished lanes refilled early
     // (yield at 8 ready lanes) and 5 CTAs per SM; a path tracer's user phases are long enough that running them for a few lanes at a

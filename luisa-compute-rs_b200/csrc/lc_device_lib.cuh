@@ -632,5 +632,8 @@ __device__ inline void lc_set_instance_transform(const lc_accel &a, uint32_t i, 
     r.inv[0] = (float)n00; r.inv[1] = (float)n01; r.inv[2] = (float)n02; r.inv[3] = (float)(-(n00 * tx + n01 * ty + n02 * tz));
     r.inv[4] = (float)n10; r.inv[5] = (float)n11; r.inv[6] = (float)n12; r.inv[7] = (float)(-(n10 * tx + n11 * ty + n12 * tz));
     r.inv[8] = (float)n20; r.inv[9] = (float)n21; r.inv[10] = (float)n22; r.inv[11] = (float)(-(n20 * tx + n21 * ty + n22 * tz));
+    bool identity = true;  // flag bit 4: exactly the identity, zeros of either sign (the host does the same in AccelBuild)
+    for (int k = 0; k < 12; k++) identity = identity && r.inv[k] == ((k == 0 || k == 5 || k == 10) ? 1.0f : 0.0f);
+    r.flags = identity ? (r.flags | lcb::kInstIdentity) : (r.flags & ~lcb::kInstIdentity);
     *a.dirty = 1u;
 }

@@ -60,7 +60,7 @@ struct alignas(16) InstanceRec {
     const PackedTri *tris;    // BLAS packed triangles
     uint32_t visibility;
     uint32_t user_id;
-    uint32_t flags;           // bit0 valid, bit1 opaque, bit2 procedural primitive, bit3 curve
+    uint32_t flags;           // bit0 valid, bit1 opaque, bit2 procedural primitive, bit3 curve, bit4 `inv` is exactly the identity (trace_device.cuh enter_instance)
     uint32_t pad;
     float affine[12];         // object -> world as given by the frontend (for instance_transform)
 };

@@ -26,6 +26,7 @@ struct LoweredKernel {
     size_t param_bytes = 0;           // sizeof(lc_params)
     uint32_t block_size[3] = {1, 1, 1};
     bool wave = false;                // wavefront lowering: persistent grid of kWaveThreads-thread CTAs pulling dispatch ids from a work counter
+    bool writes_accel = false;        // contains RayTracingSetInstance*: AccelBuild must read the instance table back before it applies modifications
     int wave_yield_min = 8;           // ready lanes per warp at which the traversal loop hands control back to the kernel body
     std::vector<std::string> messages;  // assert / unreachable texts, indexed by the id the kernel prints
 };

@@ -218,11 +218,10 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     if ((meta.x & mask) != 0u && (meta.z & 4u) == 0u) {
                         if (Gt.y) LCB_PUSH(Gt)
                         if (G.y & 0xff000000u) LCB_PUSH(G)
-                        const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                         const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                         nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                         tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                        LCB_PUSH(make_uint2(enter_instance(r, m0, m1, m2) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
+                        LCB_PUSH(make_uint2(enter_instance(r, meta.z, rec) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
                         cur_inst = inst;
                         if (QUERY) cur_opaque = (meta.z & 2u) != 0u;
                         G = make_uint2(0u, 0x80000000u);

@@ -63,20 +63,24 @@ __device__ __forceinline__ void setup_object(RaySetup &r, const float4 wo, const
     finish_setup(r);
 }
 
-// Entering an instance from world space, where `r` holds the world-space setup: the canonical transform is always evaluated, but when
-// the object-space ray comes out bit-identical to the world-space one (identity transforms — single-instance scenes, the Cornell box's
-// eight meshes) the derived constants are the same pure function of the same bits and are kept.  Returns true in that case; the
-// caller records it in the stack sentinel so that leaving the instance skips the world-space re-setup too.
-__device__ __forceinline__ bool enter_instance(RaySetup &r, const float4 m0, const float4 m1, const float4 m2) {
-    RaySetup t;
-    transform_ray(t, make_float4(r.ox, r.oy, r.oz, 0.f), make_float4(r.dx, r.dy, r.dz, 0.f), m0, m1, m2);
-    const bool same = __float_as_uint(t.ox) == __float_as_uint(r.ox) && __float_as_uint(t.oy) == __float_as_uint(r.oy) && __float_as_uint(t.oz) == __float_as_uint(r.oz) &&
-                      __float_as_uint(t.dx) == __float_as_uint(r.dx) && __float_as_uint(t.dy) == __float_as_uint(r.dy) && __float_as_uint(t.dz) == __float_as_uint(r.dz);
-    if (!same) {
-        r.ox = t.ox; r.oy = t.oy; r.oz = t.oz; r.dx = t.dx; r.dy = t.dy; r.dz = t.dz;
-        finish_setup(r);
-    }
-    return same;
+// Entering an instance from world space, where `r` holds the world-space setup.  Instances whose world -> object matrix is exactly the
+// identity (zeros of either sign) carry flag bit 4 (set by the host in AccelBuild, kept by lc_set_instance_transform): for them the canonical transform
+// fma(1, x, fma(0, y, fma(0, z, 0))) reproduces every component bit for bit as long as none of the six is zero or non-finite (a zero
+// could change sign, 0 * inf is NaN), so the object-space setup — a pure function of those bits — is the world-space one and nothing is
+// recomputed: no matrix load, no divisions.  Single-instance scenes and the Cornell box's eight meshes take this path for practically
+// every ray.  Returns true in that case; the caller records it in the stack sentinel so that leaving the instance skips the
+// world-space re-setup too.
+constexpr uint32_t kInstIdentity = 16u;
+__device__ __forceinline__ bool nonzero_finite(float x) { return ((__float_as_uint(x) & 0x7fffffffu) - 1u) < 0x7f7fffffu; }
+__device__ __forceinline__ bool enter_instance(RaySetup &r, uint32_t inst_flags, const float4 *__restrict__ rec) {
+#ifndef LCB_NO_IDENTITY_SHORTCUT  // A/B switch for kernel sweeps
+    if ((inst_flags & kInstIdentity) && nonzero_finite(r.ox) && nonzero_finite(r.oy) && nonzero_finite(r.oz) && nonzero_finite(r.dx) && nonzero_finite(r.dy) &&
+        nonzero_finite(r.dz))
+        return true;
+#endif
+    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+    setup_object(r, make_float4(r.ox, r.oy, r.oz, 0.f), make_float4(r.dx, r.dy, r.dz, 0.f), m0, m1, m2);
+    return false;
 }
 
 // 16-bit plane index -> float 2^23 + q in ONE byte-permute (no int->float conversion, no subtraction): the 2^23
@@ -445,11 +449,10 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 if ((meta.x & mask) != 0u && (QUERY || (meta.z & 4u) == 0u) && (CURVES || (meta.z & 8u) == 0u)) {
                     if (Gt.y) stack[sp++] = Gt;
                     if (G.y & 0xff000000u) stack[sp++] = G;
-                    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                     nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                     tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                    stack[sp++] = make_uint2(enter_instance(r, m0, m1, m2) ? 1u : 0u, 0u);  // sentinel: below it lies world space (x = 1: same ray setup)
+                    stack[sp++] = make_uint2(enter_instance(r, meta.z, rec) ? 1u : 0u, 0u);  // sentinel: below it lies world space (x = 1: same ray setup)
                     cur_inst = inst;
                     if (QUERY) { cur_opaque = (meta.z & 2u) != 0u; cur_procedural = (meta.z & 4u) != 0u; }
                     if (CURVES) cur_curve = (meta.z & 8u) != 0u;
@@ -606,11 +609,10 @@ __device__ __forceinline__ void wave_traverse(WaveLane &w, int &state, const Acc
                 if ((meta.x & w.mask) != 0u && (meta.z & 12u) == 0u) {
                     if (w.Gt.y) LCW_PUSH(w.Gt)
                     if (w.G.y & 0xff000000u) LCW_PUSH(w.G)
-                    const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4 *>(rec) + 3);
                     w.nodes = reinterpret_cast<const WideNode *>(((unsigned long long)ptrs.y << 32) | ptrs.x);
                     w.tris = reinterpret_cast<const PackedTri *>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-                    LCW_PUSH(make_uint2(enter_instance(w.r, m0, m1, m2) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
+                    LCW_PUSH(make_uint2(enter_instance(w.r, meta.z, rec) ? 1u : 0u, 0u))  // sentinel: below it lies world space (x = 1: same ray setup)
                     w.cur_inst = inst;
                     w.G = make_uint2(0u, 0x80000000u);
                     w.Gt = make_uint2(0u, 0u);

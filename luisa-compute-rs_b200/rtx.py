@@ -281,18 +281,21 @@ class Accel:
     def set_user_id_on_update(self, index, user_id):
         self._modify(index, abi.MOD_USER_ID, user_id=user_id)
 
-    def build_async(self, request=AccelBuildRequest.FORCE_BUILD):
+    def build_async(self, request=AccelBuildRequest.FORCE_BUILD, instance_buffer_only=False):
+        """`Accel::build_async` (rtx.rs:287-311; the Rust frontend always passes update_instance_buffer_only = false, the C++ one
+        exposes it as Accel::update_instance_buffer, runtime/rtx/accel.cpp:47-63): apply the pending modifications to the instance
+        table and — unless instance_buffer_only — rebuild the TLAS."""
         mods = list(self.modifications.values())  # drained, like HashMap::drain (rtx.rs:295)
         self.modifications = {}
         arr = (abi.AccelModification * max(len(mods), 1))(*mods)
         cmd = abi.Command()
         cmd.tag = abi.CMD_ACCEL_BUILD
-        cmd.u.accel_build = abi.CmdAccelBuild(self.handle, request, len(self.instance_handles), arr, len(mods), False)
+        cmd.u.accel_build = abi.CmdAccelBuild(self.handle, request, len(self.instance_handles), arr, len(mods), bool(instance_buffer_only))
         return HostCommand(cmd, keep=[self, arr] + list(self.instance_handles))
 
-    def build(self, request=AccelBuildRequest.FORCE_BUILD):
+    def build(self, request=AccelBuildRequest.FORCE_BUILD, instance_buffer_only=False):
         s = self.device.default_stream()
-        s.submit([self.build_async(request)])
+        s.submit([self.build_async(request, instance_buffer_only)])
         s.synchronize()
 
     # ---- ray queries: batch form of AccelVar::intersect / intersect_any --------------------------

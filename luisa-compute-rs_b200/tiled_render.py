@@ -21,7 +21,7 @@ from . import sharding
 
 
 class TiledPathTracer:
-    def __init__(self, dev, lc, scenes, width=3840, height=2160, nx=1582, spp_per_dispatch=16, depth=5, block=8, streams=2, rank=0, world=1, dist=None):
+    def __init__(self, dev, lc, scenes, width=3840, height=2160, nx=1582, spp_per_dispatch=16, depth=5, block=8, streams=2, rank=0, world=1, dist=None, fast_math=True):
         import torch
         from . import examples_ir
         self.torch, self.dist, self.dev, self.lc = torch, dist, dev, lc
@@ -63,7 +63,8 @@ class TiledPathTracer:
         camera = (tuple(map(float, cam_o)), tuple(map(float, f)), tuple(map(float, r)), tuple(map(float, u)), float(np.tan(np.radians(45.0) / 2)))
         light = (l_pos, l_u, l_v, (60.0, 54.0, 45.0), 10)
         self.kernel = examples_ir.tiled_path_tracer_kernel(self.vheap.handle.id, self.iheap.handle.id, camera, light, n_inst, spp_per_dispatch, depth, block=block)
-        self.shader = dev.create_shader(C.addressof(self.kernel.km), keep=self.kernel)
+        # enable_fast_math is the frontend's default (KernelBuildOptions, runtime/kernel.rs:556-570); hits do not depend on it (csrc/shader.cu)
+        self.shader = dev.create_shader(C.addressof(self.kernel.km), fast_math=fast_math, keep=self.kernel)
         # ---- tiles ----
         self.tile = sharding.TILE
         self.order_tx, self.order_ty = sharding.tile_order(width, height)
@@ -72,7 +73,7 @@ class TiledPathTracer:
         self.all_tile_ids = dev.create_buffer_from_array((self.order_ty * self.tiles_x + self.order_tx).astype(np.uint32))   # Morton order
         self.cost = np.ones(self.n_tiles)
         self.lanes = [self.s] + [dev.create_stream() for _ in range(max(1, streams) - 1)]
-        self.join = dev.create_event()
+        self.joins = [dev.create_event() for _ in self.lanes[1:]]   # one timeline per side lane (a timeline event is a max counter)
         self.serial = 0
         self.counters_t = torch.zeros(2, dtype=torch.int64, device="cuda")
         self.counters = dev.wrap_device_memory(self.counters_t.data_ptr(), 2, 8, 8)
@@ -106,8 +107,8 @@ class TiledPathTracer:
             lane.submit([self.shader.dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view(a * tile * tile, (b - a) * tile * tile), self.accel,
                                                     np.array([self.width, self.height, first_frame + i, b - a], np.uint32), self.counters) for i in range(n_dispatch)])
         self.serial += 1
-        for li, lane in enumerate(self.lanes[1:], 1):
-            self.join.signal(lane, self.serial * 16 + li); self.join.wait(self.s, self.serial * 16 + li)
+        for lane, join in zip(self.lanes[1:], self.joins):
+            join.signal(lane, self.serial); join.wait(self.s, self.serial)
 
     def timed(self, fn):
         torch = self.torch
@@ -172,3 +173,5 @@ class TiledPathTracer:
             r.destroy()
         for lane in self.lanes[1:]:
             lane.destroy()
+        for j in self.joins:
+            j.destroy()

@@ -9,6 +9,7 @@
 #define _GNU_SOURCE
 #include "oracle.h"
 #include <float.h>
+#include <immintrin.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdio.h>
@@ -33,6 +34,14 @@ typedef struct bvh_node {
     uint32_t count; /* 0 = internal */
 } bvh_node;
 
+typedef struct __attribute__((aligned(32))) wnode {
+    float lo[3][8], hi[3][8];
+    uint32_t child[8];  /* internal child: wnode index; leaf child: first packed triangle */
+    uint32_t count[8];  /* 0 = internal child, 1..4 = triangles of a leaf child, WIDE_EMPTY = unused slot (its box is inverted) */
+} wnode;
+#define WIDE_EMPTY 0xffffffffu
+typedef struct ptri { float v0[3], v1[3], v2[3]; uint32_t prim; } ptri;
+
 typedef struct mesh {
     const uint8_t *verts;
     size_t vstride, nverts;
@@ -42,6 +51,9 @@ typedef struct mesh {
     bvh_node *nodes;
     uint32_t n_nodes;
     uint32_t *prims;
+    /* mode 2 (the CPU baseline's fast path): the binary tree collapsed to 8-wide nodes tested with AVX2, leaves packed in tree order */
+    struct wnode *wide; uint32_t n_wide;
+    struct ptri *packed;
     /* curves (build_curve, accel.rs:142-203): float4 control points {x, y, z, radius}, u32 first-control-point index per segment */
     int is_curve, basis;
     const uint8_t *cps; size_t cp_stride, cp_count;
@@ -73,7 +85,7 @@ oracle_scene *oracle_scene_new(void) { return (oracle_scene *)calloc(1, sizeof(o
 
 void oracle_scene_free(oracle_scene *s) {
     if (!s) return;
-    for (size_t i = 0; i < s->n_meshes; i++) { free(s->meshes[i].nodes); free(s->meshes[i].prims); }
+    for (size_t i = 0; i < s->n_meshes; i++) { free(s->meshes[i].nodes); free(s->meshes[i].prims); free(s->meshes[i].wide); free(s->meshes[i].packed); }
     free(s->meshes);
     free(s->insts);
     free(s);
@@ -128,11 +140,118 @@ static inline float box_area(const box3 *b) {
 }
 
 typedef struct { uint32_t node, first, count; } build_task;
+int oracle_hw_threads(void);
+
+/* Binned-SAH binary BVH, built by a pool of threads: a task is one node with its primitive range; large tasks put their two halves
+ * back on the shared stack, small ones are finished by the thread that holds them.  Splits depend on the range only, so the tree is the
+ * same whatever the schedule (node numbering aside; hits never depend on the tree anyway). */
+typedef struct build_ctx {
+    mesh *m; const box3 *tb; const float *cen;
+    uint32_t n_nodes;                 /* atomic */
+    build_task *stack; size_t top, cap; long pending; int waiting, threads;
+    pthread_mutex_t mu; pthread_cond_t cv;
+} build_ctx;
+
+/* processes one node; returns 1 and the two child tasks when it was split */
+static int build_node(build_ctx *c, build_task t, build_task out[2]) {
+    mesh *m = c->m; const box3 *tb = c->tb; const float *cen = c->cen;
+    bvh_node *nd = &m->nodes[t.node];
+    box3 nb, cb; box_empty(&nb); box_empty(&cb);
+    for (uint32_t i = t.first; i < t.first + t.count; i++) {
+        uint32_t p = m->prims[i];
+        box_grow(&nb, &tb[p]);
+        for (int k = 0; k < 3; k++) { float v = cen[3 * p + k]; if (v < cb.lo[k]) cb.lo[k] = v; if (v > cb.hi[k]) cb.hi[k] = v; }
+    }
+    memcpy(nd->lo, nb.lo, 12); memcpy(nd->hi, nb.hi, 12);
+    if (t.count <= 4) { nd->left = t.first; nd->count = t.count; return 0; }
+    /* binned SAH over the 3 axes */
+    int best_axis = -1, best_bin = -1; float best_cost = FLT_MAX;
+    for (int ax = 0; ax < 3; ax++) {
+        float ext = cb.hi[ax] - cb.lo[ax];
+        if (!(ext > 0)) continue;
+        box3 bb[NBINS]; uint32_t bc[NBINS];
+        for (int j = 0; j < NBINS; j++) { box_empty(&bb[j]); bc[j] = 0; }
+        float scale = NBINS / ext;
+        for (uint32_t i = t.first; i < t.first + t.count; i++) {
+            uint32_t p = m->prims[i];
+            int j = (int)((cen[3 * p + ax] - cb.lo[ax]) * scale); if (j >= NBINS) j = NBINS - 1; if (j < 0) j = 0;
+            bc[j]++; box_grow(&bb[j], &tb[p]);
+        }
+        float la[NBINS], ra[NBINS]; uint32_t lc[NBINS], rc[NBINS];
+        box3 acc; box_empty(&acc); uint32_t cnt = 0;
+        for (int j = 0; j < NBINS - 1; j++) { box_grow(&acc, &bb[j]); cnt += bc[j]; la[j] = box_area(&acc); lc[j] = cnt; }
+        box_empty(&acc); cnt = 0;
+        for (int j = NBINS - 1; j > 0; j--) { box_grow(&acc, &bb[j]); cnt += bc[j]; ra[j - 1] = box_area(&acc); rc[j - 1] = cnt; }
+        for (int j = 0; j < NBINS - 1; j++) {
+            if (lc[j] == 0 || rc[j] == 0) continue;
+            float cost = la[j] * lc[j] + ra[j] * rc[j];
+            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = j; }
+        }
+    }
+    uint32_t mid;
+    if (best_axis < 0) {
+        mid = t.first + t.count / 2; /* all centroids coincide: split by position in list */
+    } else {
+        float ext = cb.hi[best_axis] - cb.lo[best_axis], scale = NBINS / ext;
+        uint32_t i = t.first, j = t.first + t.count;
+        while (i < j) {
+            uint32_t p = m->prims[i];
+            int b = (int)((cen[3 * p + best_axis] - cb.lo[best_axis]) * scale); if (b >= NBINS) b = NBINS - 1; if (b < 0) b = 0;
+            if (b <= best_bin) i++; else { j--; m->prims[i] = m->prims[j]; m->prims[j] = p; }
+        }
+        mid = i;
+        if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
+    }
+    nd->left = __atomic_fetch_add(&c->n_nodes, 2u, __ATOMIC_RELAXED); nd->count = 0;
+    out[0] = (build_task){nd->left, t.first, mid - t.first};
+    out[1] = (build_task){nd->left + 1, mid, t.first + t.count - mid};
+    return 1;
+}
+
+static void build_subtree(build_ctx *c, build_task root) {  /* finishes a small task on a local stack */
+    build_task local[128]; int top = 0; local[top++] = root;
+    while (top) {
+        build_task kids[2];
+        if (build_node(c, local[--top], kids)) { if (top + 2 > 128) die("oracle build stack overflow"); local[top++] = kids[0]; local[top++] = kids[1]; }
+    }
+}
+
+static void *build_worker(void *arg) {
+    build_ctx *c = (build_ctx *)arg;
+    for (;;) {
+        pthread_mutex_lock(&c->mu);
+        while (c->top == 0 && c->pending > 0) pthread_cond_wait(&c->cv, &c->mu);
+        if (c->top == 0) { pthread_mutex_unlock(&c->mu); return NULL; }   /* nothing queued, nothing running */
+        build_task t = c->stack[--c->top];
+        pthread_mutex_unlock(&c->mu);
+        long delta = -1;
+        if (t.count <= 8192) build_subtree(c, t);
+        else {
+            build_task kids[2];
+            if (build_node(c, t, kids)) {
+                pthread_mutex_lock(&c->mu);
+                if (c->top + 2 > c->cap) { c->cap *= 2; c->stack = (build_task *)realloc(c->stack, c->cap * sizeof(build_task)); }
+                c->stack[c->top++] = kids[0]; c->stack[c->top++] = kids[1];
+                c->pending += 2;
+                pthread_mutex_unlock(&c->mu);
+                pthread_cond_broadcast(&c->cv);
+            }
+        }
+        pthread_mutex_lock(&c->mu);
+        c->pending += delta;
+        const int done = c->pending == 0;
+        pthread_mutex_unlock(&c->mu);
+        if (done) pthread_cond_broadcast(&c->cv);
+    }
+}
+
+static void build_wide(mesh *m);
 
 void oracle_mesh_commit(oracle_scene *s, uint64_t id) {
     if (id >= s->n_meshes) die("bad mesh id");
     mesh *m = &s->meshes[id];
-    free(m->nodes); free(m->prims); m->nodes = NULL; m->prims = NULL; m->n_nodes = 0;
+    free(m->nodes); free(m->prims); free(m->wide); free(m->packed);
+    m->nodes = NULL; m->prims = NULL; m->n_nodes = 0; m->wide = NULL; m->packed = NULL; m->n_wide = 0;
     m->built = 1;
     size_t n = m->ntris;
     if (n == 0) return;
@@ -148,72 +267,82 @@ void oracle_mesh_commit(oracle_scene *s, uint64_t id) {
         }
         m->prims[i] = (uint32_t)i;
     }
-    size_t cap = 64, top = 0;
-    build_task *stack = (build_task *)malloc(cap * sizeof(build_task));
-    uint32_t n_nodes = 1;
-    stack[top++] = (build_task){0, 0, (uint32_t)n};
-    while (top) {
-        build_task t = stack[--top];
-        bvh_node *nd = &m->nodes[t.node];
-        box3 nb, cb; box_empty(&nb); box_empty(&cb);
-        for (uint32_t i = t.first; i < t.first + t.count; i++) {
-            uint32_t p = m->prims[i];
-            box_grow(&nb, &tb[p]);
-            for (int k = 0; k < 3; k++) { float c = cen[3 * p + k]; if (c < cb.lo[k]) cb.lo[k] = c; if (c > cb.hi[k]) cb.hi[k] = c; }
-        }
-        memcpy(nd->lo, nb.lo, 12); memcpy(nd->hi, nb.hi, 12);
-        if (t.count <= 4) { nd->left = t.first; nd->count = t.count; continue; }
-        /* binned SAH over the 3 axes */
-        int best_axis = -1, best_bin = -1; float best_cost = FLT_MAX;
-        for (int ax = 0; ax < 3; ax++) {
-            float ext = cb.hi[ax] - cb.lo[ax];
-            if (!(ext > 0)) continue;
-            box3 bb[NBINS]; uint32_t bc[NBINS];
-            for (int j = 0; j < NBINS; j++) { box_empty(&bb[j]); bc[j] = 0; }
-            float scale = NBINS / ext;
-            for (uint32_t i = t.first; i < t.first + t.count; i++) {
-                uint32_t p = m->prims[i];
-                int j = (int)((cen[3 * p + ax] - cb.lo[ax]) * scale); if (j >= NBINS) j = NBINS - 1; if (j < 0) j = 0;
-                bc[j]++; box_grow(&bb[j], &tb[p]);
-            }
-            float la[NBINS], ra[NBINS]; uint32_t lc[NBINS], rc[NBINS];
-            box3 acc; box_empty(&acc); uint32_t c = 0;
-            for (int j = 0; j < NBINS - 1; j++) { box_grow(&acc, &bb[j]); c += bc[j]; la[j] = box_area(&acc); lc[j] = c; }
-            box_empty(&acc); c = 0;
-            for (int j = NBINS - 1; j > 0; j--) { box_grow(&acc, &bb[j]); c += bc[j]; ra[j - 1] = box_area(&acc); rc[j - 1] = c; }
-            for (int j = 0; j < NBINS - 1; j++) {
-                if (lc[j] == 0 || rc[j] == 0) continue;
-                float cost = la[j] * lc[j] + ra[j] * rc[j];
-                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = j; }
-            }
-        }
-        uint32_t mid;
-        if (best_axis < 0) {
-            mid = t.first + t.count / 2; /* all centroids coincide: split by position in list */
-        } else {
-            float ext = cb.hi[best_axis] - cb.lo[best_axis], scale = NBINS / ext;
-            uint32_t i = t.first, j = t.first + t.count;
-            while (i < j) {
-                uint32_t p = m->prims[i];
-                int b = (int)((cen[3 * p + best_axis] - cb.lo[best_axis]) * scale); if (b >= NBINS) b = NBINS - 1; if (b < 0) b = 0;
-                if (b <= best_bin) i++; else { j--; m->prims[i] = m->prims[j]; m->prims[j] = p; }
-            }
-            mid = i;
-            if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
-        }
-        nd->left = n_nodes; nd->count = 0;
-        n_nodes += 2;
-        if (top + 2 > cap) { cap *= 2; stack = (build_task *)realloc(stack, cap * sizeof(build_task)); }
-        stack[top++] = (build_task){nd->left, t.first, mid - t.first};
-        stack[top++] = (build_task){nd->left + 1, mid, t.first + t.count - mid};
+    build_ctx c; memset(&c, 0, sizeof(c));
+    c.m = m; c.tb = tb; c.cen = cen; c.n_nodes = 1;
+    c.cap = 256; c.stack = (build_task *)malloc(c.cap * sizeof(build_task));
+    c.stack[c.top++] = (build_task){0, 0, (uint32_t)n}; c.pending = 1;
+    pthread_mutex_init(&c.mu, NULL); pthread_cond_init(&c.cv, NULL);
+    int threads = n < 65536 ? 1 : oracle_hw_threads();
+    if (threads > 64) threads = 64;
+    if (threads == 1) build_worker(&c);
+    else {
+        pthread_t th[64];
+        for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, build_worker, &c);
+        for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     }
-    m->n_nodes = n_nodes;
-    free(stack); free(tb); free(cen);
+    pthread_mutex_destroy(&c.mu); pthread_cond_destroy(&c.cv);
+    m->n_nodes = c.n_nodes;
+    free(c.stack); free(tb); free(cen);
+    build_wide(m);
 }
 
-/* ------------------------------------------------------------------------------------ */
-/* AccelImpl::update — accel.rs:324-447                                                  */
-/* ------------------------------------------------------------------------------------ */
+/* ---- 8-wide collapse for mode 2 --------------------------------------------------------------------------------------------------- */
+static uint32_t collapse_node(mesh *m, uint32_t bnode, uint32_t *n_wide, uint32_t *n_packed) {
+    const uint32_t w = (*n_wide)++;
+    uint32_t kids[8]; int nk = 0;
+    if (m->nodes[bnode].count) kids[nk++] = bnode;   /* a tree that is one leaf */
+    else { kids[nk++] = m->nodes[bnode].left; kids[nk++] = m->nodes[bnode].left + 1; }
+    while (nk < 8) {   /* open the internal child with the largest surface until the node is full */
+        int best = -1; float ba = -1.f;
+        for (int i = 0; i < nk; i++) {
+            const bvh_node *k = &m->nodes[kids[i]];
+            if (k->count) continue;
+            box3 b; memcpy(b.lo, k->lo, 12); memcpy(b.hi, k->hi, 12);
+            const float a = box_area(&b);
+            if (a > ba) { ba = a; best = i; }
+        }
+        if (best < 0) break;
+        const uint32_t l = m->nodes[kids[best]].left;
+        kids[best] = l; kids[nk++] = l + 1;
+    }
+    /* children first (their subtrees number themselves), then fill this node: the array may have moved */
+    uint32_t child[8], count[8];
+    for (int i = 0; i < nk; i++) {
+        const bvh_node *k = &m->nodes[kids[i]];
+        if (k->count) {
+            child[i] = *n_packed; count[i] = k->count;
+            for (uint32_t j = 0; j < k->count; j++) {
+                const uint32_t p = m->prims[k->left + j];
+                const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
+                ptri *t = &m->packed[(*n_packed)++];
+                memcpy(t->v0, a, 12); memcpy(t->v1, b, 12); memcpy(t->v2, c, 12); t->prim = p;
+            }
+        } else { count[i] = 0; child[i] = collapse_node(m, kids[i], n_wide, n_packed); }
+    }
+    wnode *nd = &m->wide[w];
+    for (int i = 0; i < 8; i++) {
+        if (i < nk) {
+            const bvh_node *k = &m->nodes[kids[i]];
+            for (int a = 0; a < 3; a++) { nd->lo[a][i] = k->lo[a]; nd->hi[a][i] = k->hi[a]; }
+            nd->child[i] = child[i]; nd->count[i] = count[i];
+        } else {
+            for (int a = 0; a < 3; a++) { nd->lo[a][i] = INFINITY; nd->hi[a][i] = -INFINITY; }
+            nd->child[i] = 0; nd->count[i] = WIDE_EMPTY;
+        }
+    }
+    return w;
+}
+
+static void build_wide(mesh *m) {
+    if (m->ntris == 0 || m->is_curve) return;
+    if (posix_memalign((void **)&m->wide, 32, (size_t)m->n_nodes * sizeof(wnode)) != 0) die("out of memory");
+    m->packed = (ptri *)malloc(m->ntris * sizeof(ptri));
+    uint32_t nw = 0, np = 0;
+    collapse_node(m, 0, &nw, &np);
+    m->n_wide = nw;
+    wnode *shrunk = NULL;
+    if (posix_memalign((void **)&shrunk, 32, (size_t)nw * sizeof(wnode)) == 0) { memcpy(shrunk, m->wide, (size_t)nw * sizeof(wnode)); free(m->wide); m->wide = shrunk; }
+}
 
 void oracle_invert_affine(const float m[12], float inv[12]) {
     /* double adjugate inverse of the 3x3 part, translation = -inv*t, one rounding to fp32 */
@@ -548,8 +677,12 @@ static void mesh_closest_filtered(const mesh *m, const ray_frame *f, float tmin,
     }
 }
 
+static void mesh_closest_wide(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best);
+static int mesh_any_wide(const mesh *m, const ray_frame *f, float tmin, float tmax);
+static int have_avx2(void);
 static void mesh_closest(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, int mode) {
     if (m->ntris == 0) return;
+    if (mode == 2 && m->wide && have_avx2()) { mesh_closest_wide(m, f, tmin, tmax, inst, best); return; }
     if (mode == 0) {
         for (uint32_t p = 0; p < m->ntris; p++) {
             const float *a, *b, *c; tri_verts(m, p, &a, &b, &c);
@@ -589,6 +722,7 @@ static void mesh_closest(const mesh *m, const ray_frame *f, float tmin, float tm
 
 static int mesh_any(const mesh *m, const ray_frame *f, float tmin, float tmax, int mode) {
     if (m->ntris == 0) return 0;
+    if (mode == 2 && m->wide && have_avx2()) return mesh_any_wide(m, f, tmin, tmax);
     float t, u, v;
     if (mode == 0) {
         for (uint32_t p = 0; p < m->ntris; p++) {
@@ -611,6 +745,111 @@ static int mesh_any(const mesh *m, const ray_frame *f, float tmin, float tmax, i
         } else {
             if (top + 2 > 128) die("oracle BVH stack overflow");
             stack[top++] = nd->left; stack[top++] = nd->left + 1;
+        }
+    }
+    return 0;
+}
+
+
+/* ---- mode 2: the 8-wide tree, box tests eight at a time (AVX2) -----------------------------------------------------------------------
+ * The CPU baseline's fast path: same canonical triangle arithmetic (canon_tri), same tie rule (consider), so the hits are the same
+ * bits as modes 0 and 1; only the culling differs — single-precision slabs for the eight children of a node at once, each child box
+ * padded by 2^-18 of its L-inf distance from the ray origin (32 times the rounding of the fp32 slab arithmetic, so no box that the
+ * exact arithmetic would enter is ever skipped), children visited near to far. */
+static int g_has_avx2 = -1;
+static int have_avx2(void) {
+    if (g_has_avx2 < 0) g_has_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma") ? 1 : 0;
+    return g_has_avx2;
+}
+
+typedef struct wide_ray { __m256 o[3], inv[3]; } wide_ray;
+
+__attribute__((target("avx2,fma"))) static inline void wide_ray_setup(const ray_frame *f, wide_ray *w) {
+    for (int k = 0; k < 3; k++) {
+        w->o[k] = _mm256_set1_ps(f->o[k]);
+        /* a zero direction component: a huge finite reciprocal keeps 0 * inv = 0 (no NaN) and sends every other plane to +-1e30 */
+        w->inv[k] = _mm256_set1_ps(f->d[k] == 0.0f ? 1e30f : 1.0f / f->d[k]);
+    }
+}
+
+/* entry distances of the children of `nd` that [tmin, tbest] may hit; returns the lane mask */
+__attribute__((target("avx2,fma"))) static inline unsigned wide_node_test(const wnode *nd, const wide_ray *w, float tmin, float tbest, float tn_out[8]) {
+    const __m256 sign = _mm256_set1_ps(-0.0f);
+    __m256 l[3], h[3], R = _mm256_setzero_ps();
+    for (int k = 0; k < 3; k++) {
+        l[k] = _mm256_sub_ps(_mm256_load_ps(nd->lo[k]), w->o[k]);
+        h[k] = _mm256_sub_ps(_mm256_load_ps(nd->hi[k]), w->o[k]);
+        R = _mm256_max_ps(R, _mm256_max_ps(_mm256_andnot_ps(sign, l[k]), _mm256_andnot_ps(sign, h[k])));
+    }
+    const __m256 pad = _mm256_add_ps(_mm256_mul_ps(R, _mm256_set1_ps(1.0f / 262144.0f)), _mm256_set1_ps(1e-30f));
+    __m256 tn = _mm256_set1_ps(tmin), tf = _mm256_set1_ps(tbest);
+    for (int k = 0; k < 3; k++) {
+        const __m256 t0 = _mm256_mul_ps(_mm256_sub_ps(l[k], pad), w->inv[k]), t1 = _mm256_mul_ps(_mm256_add_ps(h[k], pad), w->inv[k]);
+        tn = _mm256_max_ps(tn, _mm256_min_ps(t0, t1));
+        tf = _mm256_min_ps(tf, _mm256_max_ps(t0, t1));
+    }
+    /* widen the comparison by the rounding of the products themselves (a relative 2^-22 of the larger magnitude) */
+    const __m256 slack = _mm256_mul_ps(_mm256_max_ps(_mm256_andnot_ps(sign, tn), _mm256_andnot_ps(sign, tf)), _mm256_set1_ps(1.0f / 4194304.0f));
+    _mm256_storeu_ps(tn_out, tn);
+    return (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(tn, _mm256_add_ps(tf, slack), _CMP_LE_OQ));
+}
+
+typedef struct wide_entry { uint32_t node; float tn; } wide_entry;
+
+__attribute__((target("avx2,fma"))) static void mesh_closest_wide(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best) {
+    wide_ray w; wide_ray_setup(f, &w);
+    wide_entry stack[512]; int top = 0;
+    stack[top++] = (wide_entry){0, -INFINITY};
+    while (top) {
+        const wide_entry e = stack[--top];
+        const float tb = best->found ? best->t : tmax;
+        if (e.tn > tb) continue;
+        const wnode *nd = &m->wide[e.node];
+        float tn[8];
+        unsigned mask = wide_node_test(nd, &w, tmin, tb, tn);
+        const int base = top;
+        while (mask) {
+            const int i = __builtin_ctz(mask); mask &= mask - 1;
+            if (nd->count[i] == WIDE_EMPTY) continue;
+            if (nd->count[i]) {
+                const ptri *t = &m->packed[nd->child[i]];
+                for (uint32_t j = 0; j < nd->count[i]; j++) {
+                    float tt, u, v;
+                    if (canon_tri(f, tmin, tmax, t[j].v0, t[j].v1, t[j].v2, &tt, &u, &v)) consider(best, tt, u, v, inst, t[j].prim);
+                }
+            } else {
+                if (top + 1 > 512) die("oracle wide BVH stack overflow");
+                /* insertion keeps the new entries far-to-near, so the nearest child is popped first */
+                int k = top++;
+                while (k > base && stack[k - 1].tn < tn[i]) { stack[k] = stack[k - 1]; k--; }
+                stack[k] = (wide_entry){nd->child[i], tn[i]};
+                { const char *pf = (const char *)&m->wide[nd->child[i]]; _mm_prefetch(pf, _MM_HINT_T0); _mm_prefetch(pf + 64, _MM_HINT_T0); _mm_prefetch(pf + 128, _MM_HINT_T0); _mm_prefetch(pf + 192, _MM_HINT_T0); }
+            }
+        }
+    }
+}
+
+__attribute__((target("avx2,fma"))) static int mesh_any_wide(const mesh *m, const ray_frame *f, float tmin, float tmax) {
+    wide_ray w; wide_ray_setup(f, &w);
+    uint32_t stack[512]; int top = 0;
+    stack[top++] = 0;
+    while (top) {
+        const wnode *nd = &m->wide[stack[--top]];
+        float tn[8];
+        unsigned mask = wide_node_test(nd, &w, tmin, tmax, tn);
+        while (mask) {
+            const int i = __builtin_ctz(mask); mask &= mask - 1;
+            if (nd->count[i] == WIDE_EMPTY) continue;
+            if (nd->count[i]) {
+                const ptri *t = &m->packed[nd->child[i]];
+                for (uint32_t j = 0; j < nd->count[i]; j++) {
+                    float tt, u, v;
+                    if (canon_tri(f, tmin, tmax, t[j].v0, t[j].v1, t[j].v2, &tt, &u, &v)) return 1;
+                }
+            } else {
+                if (top + 1 > 512) die("oracle wide BVH stack overflow");
+                stack[top++] = nd->child[i];
+            }
         }
     }
     return 0;

@@ -69,7 +69,7 @@ def canonical_cone(o, d, tmin, tmax, A, B):
 
 HIT = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("committed_ray_t", "<f4"), ("_pad", "<u4")])
 COMMITTED = np.dtype([("inst", "<u4"), ("prim", "<u4"), ("bary", "<f4", (2,)), ("hit_type", "<u4"), ("committed_ray_t", "<f4")])
-BRUTE, BVH = 0, 1
+BRUTE, BVH, WIDE = 0, 1, 2   # WIDE: the 8-wide AVX2 traversal (CPU baseline); same canonical hits
 
 
 class OracleScene:

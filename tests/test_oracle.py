@@ -54,9 +54,10 @@ def test_golden_regression_vectors():
 def test_bvh_equals_brute_force(n_tris, n_rays):
     o = ol.scene_from_desc(scenes.c3_soup(n_tris, seed=n_tris))
     rays = scenes.incoherent_rays(n_rays, seed=n_rays, tmin=0.0)
-    a, b = o.trace_closest(rays, mode=ol.BRUTE), o.trace_closest(rays, mode=ol.BVH)
-    assert a.tobytes() == b.tobytes()
+    a, b, c = o.trace_closest(rays, mode=ol.BRUTE), o.trace_closest(rays, mode=ol.BVH), o.trace_closest(rays, mode=ol.WIDE)
+    assert a.tobytes() == b.tobytes() == c.tobytes()      # brute force = binary BVH = 8-wide AVX2 traversal (the CPU baseline's fast path)
     assert np.array_equal(o.trace_any(rays, mode=ol.BRUTE), o.trace_any(rays, mode=ol.BVH))
+    assert np.array_equal(o.trace_any(rays, mode=ol.BRUTE), o.trace_any(rays, mode=ol.WIDE))
     assert np.array_equal(o.trace_any(rays, mode=ol.BRUTE) != 0, a["inst"] != 0xFFFFFFFF)
 
 
@@ -66,7 +67,7 @@ def test_instanced_bvh_equals_brute_and_masks():
     rays = scenes.incoherent_rays(5000, lo=-1.0, hi=8.0, seed=11)
     for mask in (0xFF, 0xF0, 0x01, 0):
         a, b = o.trace_closest(rays, mask, ol.BRUTE), o.trace_closest(rays, mask, ol.BVH)
-        assert a.tobytes() == b.tobytes()
+        assert a.tobytes() == b.tobytes() == o.trace_closest(rays, mask, ol.WIDE).tobytes()
         hit = a["inst"] != 0xFFFFFFFF
         vis = np.array([i["mask"] for i in desc.instances], np.uint32)
         assert np.all((vis[a["inst"][hit]] & mask) != 0)
@@ -192,3 +193,19 @@ def test_ray_query_semantics():
         anyq = o.ray_query(rays, terminate_on_first=True, kind=kind, **kw)
         assert np.array_equal(anyq["hit_type"], a["hit_type"])   # which hit is order dependent, whether one exists is not
     o.close(); o2.close()
+
+
+def test_wide_mode_and_parallel_build_on_a_larger_scene():
+    """mode 2 (8-wide tree, AVX2 box tests; what `bench.py --impl reference` times) returns the canonical hits of the scalar modes on a
+    scene large enough for the multi-threaded SAH build, on grazing / axis-aligned rays and with a zero direction component."""
+    verts, tris = scenes.terrain(200)
+    s = scenes.SceneDesc(); s.add_instance(s.add_mesh(verts, tris), np.eye(4, dtype=np.float32)[:3])
+    o = ol.scene_from_desc(s)
+    rays = scenes.incoherent_rays(60000, seed=77)
+    rays["orig"][:, 1] = rays["orig"][:, 1] * 0.3 + 0.05
+    rays["dir"][:20000, 1] = 0.0                     # exactly horizontal: a zero direction component in the slab test
+    rays["dir"][20000:30000] = (0.0, -1.0, 0.0)      # straight down
+    a, b = o.trace_closest(rays, mode=ol.BVH), o.trace_closest(rays, mode=ol.WIDE)
+    assert a.tobytes() == b.tobytes() and (a["inst"] != 0xFFFFFFFF).mean() > 0.3
+    assert np.array_equal(o.trace_any(rays, mode=ol.BVH), o.trace_any(rays, mode=ol.WIDE))
+    o.close()

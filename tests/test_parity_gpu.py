@@ -441,6 +441,77 @@ def test_upload_sources_are_snapshotted_before_dispatch_returns(device):
     buf.destroy(); stream.destroy()
 
 
+def test_builds_are_enqueued_and_do_not_block_the_submitting_thread(device):
+    """MeshBuild / AccelBuild are stream work: dispatch() returns while the build is still running (the reference enqueues and returns,
+    cpu/mod.rs:168-180; cuda_primitive.cpp:20-110 builds on the stream).  Measured with a host timestamp against the device time of
+    the same build; the LBVH pipeline (AccelUsageHint::FastBuild) never reads anything back."""
+    import time
+    verts, tris = scenes.random_soup(4_000_000, 77)
+    vb, ib = device.create_buffer_from_array(verts), device.create_buffer_from_array(tris)
+    opt = lc.AccelOption(hint=lc.AccelUsageHint.FAST_BUILD)
+    mesh = device.create_mesh(vb.view(), ib.view(), opt)
+    accel = device.create_accel(opt)
+    accel.push_mesh(mesh)
+    s = device.create_stream()
+    s.submit([mesh.build_async(), accel.build_async()]); s.synchronize()      # first build: allocations, arena growth
+    first_nodes = mesh.stats()["wide_node_count"]
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        s.submit([mesh.build_async(), accel.build_async()])
+        times.append(time.perf_counter() - t0)
+        s.synchronize()
+    st = mesh.stats()
+    assert st["wide_node_count"] == first_nodes and st["primitive_count"] == 4_000_000 and st["was_refit"] == 0
+    assert min(times) * 1e3 < 0.5 * st["build_ms"], f"submit took {min(times) * 1e3:.3f} ms, the build {st['build_ms']:.3f} ms on the device"
+    # a refit is enqueued the same way
+    mesh2 = device.create_mesh(vb.view(), ib.view(), lc.AccelOption(hint=lc.AccelUsageHint.FAST_BUILD, allow_update=True))
+    s.submit([mesh2.build_async()]); s.synchronize(); mesh2.stats()
+    s.submit([mesh2.build_async(lc.AccelBuildRequest.PREFER_UPDATE)]); s.synchronize(); mesh2.stats()   # first refit allocates its side arrays
+    t0 = time.perf_counter(); s.submit([mesh2.build_async(lc.AccelBuildRequest.PREFER_UPDATE)]); dt = time.perf_counter() - t0
+    s.synchronize()
+    st2 = mesh2.stats()
+    assert st2["was_refit"] == 1 and dt * 1e3 < 0.5 * st2["build_ms"], (dt * 1e3, st2["build_ms"])
+    # results of an asynchronously built scene: the usual parity check on a sample
+    rays = scenes.incoherent_rays(20000, seed=5)
+    rb, hb = device.create_buffer_from_array(rays), device.create_buffer(20000, 24, 8)
+    accel.intersect(rb, hb, 20000, 0xFF, s); s.synchronize()
+    o = ol.OracleScene(); o.update(1, [{"index": 0, "flags": 1 | 2 | 4 | 16, "visibility": 0xFF, "mesh": o.add_mesh(verts, tris)}])
+    assert_hits_equal(hb.view().to_numpy(lc.SurfaceHit), o.trace_closest(rays), "async build")
+    o.close()
+    for r in (rb, hb, accel, mesh, mesh2, vb, ib, s):
+        r.destroy()
+
+
+def test_update_instance_buffer_only_edits_the_table_and_keeps_the_tlas(device):
+    """AccelBuildCommand.update_instance_buffer_only (api_types:643-652; AccelImpl::update returns before the scene commit,
+    cpu/accel.rs:428-430; cuda_accel.cpp:277 skips the BVH build): the instance table takes the modifications — visibility, user id and
+    opacity are read from it per instance entry, so they hold for the next traversal — while the TLAS keeps its boxes until the next
+    full AccelBuild."""
+    desc = scenes.instanced_scene(500, 4)
+    d = DeviceScene(device, desc)
+    o = ol.scene_from_desc(desc)
+    rays = scenes.incoherent_rays(50000, lo=-1.0, hi=8.0, seed=13)
+    tlas_before = d.accel.stats()
+    assert_hits_equal(d.trace_closest(rays), o.trace_closest(rays), "before")
+    d.accel.set_visibility_on_update(1, 0x0)
+    d.accel.set_user_id_on_update(2, 4242)
+    d.accel.build(instance_buffer_only=True)
+    o.update(4, [{"index": 1, "flags": 16, "visibility": 0x0}, {"index": 2, "flags": 32, "user_id": 4242}])
+    got = d.trace_closest(rays)
+    assert_hits_equal(got, o.trace_closest(rays), "after update_instance_buffer_only")
+    assert not (got["inst"] == 1).any() and d.accel.instance_user_id(2) == 4242 and d.accel.instance_visibility_mask(1) == 0
+    assert d.accel.stats()["wide_node_count"] == tlas_before["wide_node_count"]      # the TLAS was not rebuilt
+    # a transform edited the same way moves the instance's rays at once but its TLAS box only at the next full build
+    t = np.eye(4, dtype=np.float32); t[:3, :] = desc.instances[3]["transform"]; t[1, 3] += 0.25
+    d.accel.set_transform_on_update(3, t)
+    d.accel.build(instance_buffer_only=True)
+    d.accel.build()
+    o.update(4, [{"index": 3, "flags": 2, "affine": t[:3, :].reshape(-1)}])
+    assert_hits_equal(d.trace_closest(rays), o.trace_closest(rays), "after the full build")
+    d.destroy(); o.close()
+
+
 def test_counted_traversal_matches_and_reports_work(device):
     desc = scenes.c3_soup(20000, seed=61)
     rays = scenes.incoherent_rays(50000, seed=62)

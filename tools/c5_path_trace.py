@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--balance-passes", type=int, default=4, help="0: equal tile counts per rank")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's equal-count range in this single process (tuning aid)")
+    ap.add_argument("--precise", action="store_true", help="compile the kernel without enable_fast_math (the frontend default is on)")
+    ap.add_argument("--lowering", default="auto", choices=["auto", "direct"])
     ap.add_argument("--save", default="")
     a = ap.parse_args()
     import torch
@@ -42,8 +44,9 @@ def main():
     from luisa_compute_rs_b200 import sharding
     from luisa_compute_rs_b200.tiled_render import TiledPathTracer
     dev = lc.Context().create_device("b200")
+    lc._abi.load_library().lc_b200_set_lowering(1 if a.lowering == "direct" else 0)
     erank, eworld = (int(v) for v in a.emulate.split("/")) if a.emulate else (rank, world)
-    pt = TiledPathTracer(dev, lc, scenes, a.width, a.height, a.nx, a.spp_per_dispatch, a.depth, a.block, a.streams, erank, eworld, dist if world > 1 else None)
+    pt = TiledPathTracer(dev, lc, scenes, a.width, a.height, a.nx, a.spp_per_dispatch, a.depth, a.block, a.streams, erank, eworld, dist if world > 1 else None, fast_math=not a.precise)
     if a.emulate:
         pt.world = 1   # no collective: time this rank's share alone
         pt.frame(a.spp_per_dispatch, 50000)
@@ -63,7 +66,7 @@ def main():
         total_rays = int(rays.sum().item())
         rgb = img[..., :3] / np.maximum(img[..., 3:4], 1)
         res = {"config": "c5_path_trace", "n_gpus": world, "width": a.width, "height": a.height, "spp": n_dispatch * a.spp_per_dispatch, "depth": a.depth, "triangles": pt.triangles,
-               "frame_ms": round(max(times), 3), "frame_ms_per_rank": [round(t, 2) for t in times], "streams": len(pt.lanes), "block": a.block,
+               "frame_ms": round(max(times), 3), "frame_ms_per_rank": [round(t, 2) for t in times], "streams": len(pt.lanes), "block": a.block, "fast_math": not a.precise, "lowering": a.lowering,
                "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes_imbalance": [round(h, 3) for h in history], "rays": total_rays,
                "mrays_per_s": round(total_rays / max(times) / 1e3, 1), "mean_radiance": round(float(rgb.mean()), 5),
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img)}

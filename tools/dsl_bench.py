@@ -41,7 +41,8 @@ def c3(dev, n_rays, configs):
     ms = timed(stream, ext, lambda: accel.intersect(rb, hb2, n_rays, 0xFF, stream), 5)
     print(json.dumps({"c3": "batch k_trace", "ms": ms, "mrays": n_rays / ms / 1e3}), flush=True)
     ref = hb2.view().to_numpy(lc.SurfaceHit).tobytes()
-    for mode, minb, yld in configs:
+    for cfg in configs:
+        mode, minb, yld = cfg[:3]
         lib.lc_b200_set_lowering(mode)
         os.environ["LC_B200_WAVE_MIN_BLOCKS"] = str(minb); os.environ["LC_B200_WAVE_YIELD"] = str(yld)
         k = examples_ir.trace_buffer_kernel()
@@ -73,13 +74,15 @@ def c2(dev, configs):
     sext = torch.cuda.ExternalStream(s.cuda_stream())
     res = np.array([w, h], np.uint32)
     ref = None
-    for mode, minb, yld in configs:
+    for cfg in configs:
+        mode, minb, yld = cfg[:3]
+        fast = bool(cfg[3]) if len(cfg) > 3 else False
         lib.lc_b200_set_lowering(mode)
         os.environ["LC_B200_WAVE_MIN_BLOCKS"] = str(minb); os.environ["LC_B200_WAVE_YIELD"] = str(yld)
         image = dev.create_tex2d("Rgba32f", w, h); seeds = dev.create_tex2d("R32Uint", w, h)
         seeds.copy_from(ex.seed_image(w, h).reshape(h, w))
-        k = examples_ir.path_tracer_kernel(vheap.handle.id, iheap.handle.id, 32, 10, polynomial_sincos=True)
-        sh = dev.create_shader(C.addressof(k.km), keep=k)
+        k = examples_ir.path_tracer_kernel(vheap.handle.id, iheap.handle.id, 32, 10, polynomial_sincos=not fast)
+        sh = dev.create_shader(C.addressof(k.km), fast_math=fast, keep=k)
         sh.dispatch((w, h), image, seeds, pt.accel, res)
         img = image.to_numpy().tobytes()
         if ref is None:
@@ -89,7 +92,7 @@ def c2(dev, configs):
         s.submit([sh.dispatch_async((w, h), image, seeds, pt.accel, res) for _ in range(3)])
         e1.record(sext); s.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        print(json.dumps({"c2": "dsl path tracer", "lowering": ["wavefront", "direct"][mode == 1], "min_blocks": minb, "yield": yld, "ms_per_dispatch": ms,
+        print(json.dumps({"c2": "dsl path tracer", "lowering": ["wavefront", "direct"][mode == 1], "fast_math": fast, "min_blocks": minb, "yield": yld, "ms_per_dispatch": ms,
                           "mrays": rays_per_dispatch / ms / 1e3, "first_dispatch_identical": img == ref}), flush=True)
         for r in (sh, image, seeds):
             r.destroy()
