@@ -407,8 +407,8 @@ LCB_EXPORT const void *lc_b200_make_ir_type(size_t size, size_t alignment);
 LCB_EXPORT int lc_b200_set_builder(int builder);
 
 /* How create_shader lowers kernels that call RayTracingTraceClosest / TraceAny from their own body (csrc/ir_lower.cpp header):
- * 0 decide per kernel (wavefront lowering wherever it is legal), 1 always the direct lowering (one dispatch id per CUDA thread,
- * per-thread traversal), 2 same as 0.  Returns the previous setting.  Results never depend on it (same arithmetic per ray); only
+ * 0 decide per kernel (wavefront lowering where it is legal and the body is short), 1 always the direct lowering (one dispatch id per
+ * CUDA thread, per-thread traversal), 2 wavefront lowering wherever it is legal.  Returns the previous setting.  Results never depend on it (same arithmetic per ray); only
  * throughput does.  Initial value: environment LC_B200_LOWERING = direct | wavefront.  Applies to shaders created afterwards. */
 LCB_EXPORT int lc_b200_set_lowering(int mode);
 

@@ -26,7 +26,8 @@
 // once, so a path tracer's lanes never idle while their neighbours finish longer paths, and the traversal — the dominant cost — always
 // runs with every parked lane of the warp converged.  Kernels that use block-level features whose meaning depends on the CUDA thread
 // mapping (shared memory, SynchronizeBlock, warp intrinsics), several accels, curve bases, or that only trace from callables / RayQuery
-// callbacks keep the direct lowering (one dispatch id per CUDA thread, trace_one per call).  LC_B200_LOWERING=direct|wavefront overrides.
+// callbacks keep the direct lowering (one dispatch id per CUDA thread, trace_one per call) — and so do, by default, kernels with long
+// bodies (path tracers), for which it measured slower (lower_kernel).  LC_B200_LOWERING=direct|wavefront / lc_b200_set_lowering override.
 #include "shader.h"
 #include "trace_device.cuh"
 
@@ -1001,8 +1002,12 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
     ModuleScan scan;
     scan.curve_bases = km->module.curve_basis_set;
     scan_block(km->module.entry.ptr, scan, true);
-    const bool wave = lowering_override() != 1 && scan.trace_sites > 0 && !scan.block_features && km->shared.len == 0 && scan.accels.size() == 1 &&
-                      scan.curve_bases == 0;
+    // ... and, unless forced, only where it pays: kernels whose body is little more than the trace call (ray generation, buffer-to-buffer
+    // queries — config C3: 504 -> 1109 Mrays/s).  Path tracers spend enough instructions between two trace calls that the state machine's
+    // extra registers and the partially filled user phases cost what the converged traversal gains: measured on B200 with the
+    // frontend's default fast math, C2 direct 33.5 ms per dispatch vs wavefront 37.2, C5 288 vs 291 ms (profiles/r02d_*).
+    const bool wave_legal = scan.trace_sites > 0 && !scan.block_features && km->shared.len == 0 && scan.accels.size() == 1 && scan.curve_bases == 0;
+    const bool wave = wave_legal && lowering_override() != 1 && (lowering_override() == 2 || scan.body_nodes < 128);
     fe.wave = wave;
     out.wave = wave;
     out.writes_accel = scan.writes_accel;

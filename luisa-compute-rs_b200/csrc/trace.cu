@@ -37,7 +37,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kTraceThreads = LCB_TRACE_THREADS;  // warps are independent (warp-local ray pools, no block barrier): any multiple of 32
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
-#define LCB_TRACE_MIN_BLOCKS 7
+#define LCB_TRACE_MIN_BLOCKS 6  // 80 registers, 4 bytes of spills; 7 CTAs (72 registers, 28 bytes) measured 2-4 % slower (profiles/r02a_, r02d_k_trace_variants.txt)
 #endif
 #ifndef LCB_SMEM_STACK
 #define LCB_SMEM_STACK 16
