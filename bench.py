@@ -289,7 +289,7 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
                "mrays_per_s": float(rays.sum().item()) / total / 1e3,
                "msamples_per_s": pt.width * pt.height * n_dispatch * spp_per_dispatch / total / 1e3,
                "partition": "contiguous ranges of the Morton-ordered 64x64 tiles, cut to equal measured cost" if world > 1 else "all tiles on one GPU",
-               "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes_imbalance": [round(h, 3) for h in history],
+               "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes": [{"imbalance": round(h[0], 3), "tiles_per_rank": h[1], "ms_per_rank": h[2]} for h in history],
                "one_pass_ms_per_rank": [round(t, 3) for t in render_only], "imbalance_max_over_mean": round(imbalance, 4),
                "limiter": ("load imbalance between ranks" if imbalance > 1.05 else "per-rank efficiency: 1/N of the image is few work items per SM (dispatch tails) and reuses less of the 430 MB BLAS in L2"),
                "gather_bytes": int(gathered.numel() * 4) if world > 1 else 0, "blas_build_ms": round(pt.blas_ms, 3), "tlas_build_ms": round(pt.tlas_ms, 3),
@@ -441,6 +441,12 @@ def main():
     batch_ms = e0.elapsed_time(e1) / 5
     out["batch_entry"] = {"value": n / batch_ms / 1e3, "unit": UNIT, "ms": batch_ms, "api": "lc_b200_trace_closest (k_trace + k_refine); per GPU", "dsl_over_batch": batch_ms / kernel_ms}
 
+    # ---- config C5 on all ranks, before the legs only rank 0 runs (they would leave its GPU warmer than the others) ----
+    if not args.profile and args.c5_spp > 0:
+        c5 = c5_leg(dev, lc, scenes, torch, dist if world > 1 else None, rank, world, args.c5_spp, args.c5_spp_per_dispatch, 4)
+        if rank == 0:
+            out["c5_path_trace"] = c5
+
     if rank == 0 and not args.profile:
         batch_hits = np.empty(n, dtype=lc.SurfaceHit); hb.view().copy_to(batch_hits)
         assert dsl_hits.tobytes() == batch_hits.tobytes(), "the DSL call path and the batch entry point disagree"
@@ -517,11 +523,6 @@ def main():
         out["parity_sample"] = parity_sample_leg(dev, lc, None)
         # ---- config C2 beside the headline: examples/path_tracer.rs as an IR kernel through create_shader ----
         out["dsl_path_tracer"] = dsl_path_tracer_leg(dev, lc, scenes, torch, ext)
-
-    if not args.profile and args.c5_spp > 0:
-        c5 = c5_leg(dev, lc, scenes, torch, dist if world > 1 else None, rank, world, args.c5_spp, args.c5_spp_per_dispatch, 4)
-        if rank == 0:
-            out["c5_path_trace"] = c5
 
     if rank == 0 and world == 1 and not args.no_cpu and not args.profile:
         import oracle_lib as ol

@@ -180,7 +180,17 @@ __global__ void __launch_bounds__(256) k_pack_curves(CurveInput in, PackedTri *s
     float4 *o = reinterpret_cast<float4 *>(&slots[i]);
     o[0] = make_float4(A.x, A.y, A.z, __uint_as_float(seg));
     o[1] = make_float4(B.x, B.y, B.z, A.w);
-    o[2] = make_float4(B.w, (float)k * du, du, 0.f);
+    o[2] = make_float4(B.w, (float)k * du, du, __uint_as_float(n + seg));  // coefficient slot of the segment (k_curve_coefs)
+}
+
+// power-basis coefficients of every cubic segment, one 64-byte slot each, behind the n leaf slots (read by refine_curve_hit)
+__global__ void __launch_bounds__(256) k_curve_coefs(CurveInput in, PackedTri *slots, uint32_t n, uint32_t n_segs) {
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_segs) return;
+    float4 a[4];
+    curve_coefficients(in.cps, in.cp_stride, in.segs, in.basis, seg, a);
+    float4 *o = reinterpret_cast<float4 *>(&slots[n + seg]);
+    o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
 }
 
 // World-space box of an instance: union of the BLAS root's (conservatively decoded) child
@@ -970,6 +980,7 @@ void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildS
     LeafSinkTriangles sink{slots};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
     k_pack_curves<<<(n + 255) / 256, 256, 0, s>>>(in, slots, n); lc.count++;
+    if (in.basis != kCurveLinear) { const uint32_t n_segs = n / in.pieces; k_curve_coefs<<<(n_segs + 255) / 256, 256, 0, s>>>(in, slots, n, n_segs); lc.count++; }
 }
 
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,

@@ -525,7 +525,9 @@ void blas_build(DeviceObj *d, StreamObj *s, MeshObj *m, uint32_t n, int32_t requ
         CUDA_CHECK(cudaMalloc((void **)&d->build_arena, d->build_arena_cap));
     }
     BuildScratch sc = build_scratch_layout(d->build_arena, n);
-    if (!m->tris) CUDA_CHECK(cudaMallocAsync((void **)&m->tris, (size_t)n * sizeof(PackedTri), st));
+    // cubic curve BLASes keep the segments' power-basis coefficients behind the leaves, one 64-byte slot per segment (k_curve_coefs)
+    const size_t leaf_slots = (size_t)n + (curve && curve->pieces > 1 ? n / curve->pieces : 0);
+    if (!m->tris) CUDA_CHECK(cudaMallocAsync((void **)&m->tris, leaf_slots * sizeof(PackedTri), st));
     if (!m->nodes) { CUDA_CHECK(cudaMallocAsync((void **)&m->nodes, (size_t)capacity * sizeof(WideNode), st)); m->node_capacity = capacity; }
     // AccelUsageHint (api_types:204-212; the CPU backend maps it to Embree build quality, cpu/accel.rs:49-63): FastTrace (the default)
     // lets the builder choose between PLOC and the LBVH split rule per mesh, FastBuild always takes the LBVH.

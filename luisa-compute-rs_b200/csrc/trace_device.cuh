@@ -235,8 +235,8 @@ constexpr uint32_t kCurveLinear = 0, kCurveBSpline = 1, kCurveCatmullRom = 2, kC
 
 struct alignas(64) CurveSeg {   // one piece, in the 64-byte PackedTri slot
     float pa[3]; uint32_t prim;  // sphere at the piece's start; prim = segment index
-    float pb[3]; float ra;       // sphere at its end; radius at the start
-    float rb, u0, du; uint32_t pad;
+    float pb[3]; float ra;       // sphere at its end; radius at the start (both radii inflated by the piece's sag bound, curve_piece)
+    float rb, u0, du; uint32_t coef;  // coef: slot (in the same 64-byte array) of the segment's power-basis coefficients a0..a3, cubic bases only
     uint32_t spare[4];
 };
 static_assert(sizeof(CurveSeg) == 64, "CurveSeg shares the PackedTri slot");
@@ -276,8 +276,96 @@ __device__ __forceinline__ void curve_piece(const uint8_t *cps, size_t cp_stride
     const float4 q3 = *reinterpret_cast<const float4 *>(cps + (size_t)(first + 3) * cp_stride);
     float4 a[4];
     curve_power_basis(basis, q0, q1, q2, q3, a);
-    A = curve_point(a, (float)k * (1.0f / kCurveSubdiv));
-    B = curve_point(a, (float)(k + 1) * (1.0f / kCurveSubdiv));
+    const float u0 = (float)k * (1.0f / kCurveSubdiv), u1 = (float)(k + 1) * (1.0f / kCurveSubdiv);
+    A = curve_point(a, u0);
+    B = curve_point(a, u1);
+    // The cone only locates the hit (refine_curve_hit decides): its radii are inflated by a bound on how far the cubic leaves its chord
+    // over the piece — du^2 / 8 * max |c''| per component, c'' linear in u — so that every ray that enters the true sweep here also enters
+    // the cone and becomes a candidate (oracle.c curve_piece, same operations).
+    float sag = 0.0f;
+#define LCB_SAG(C) sag = __fadd_rn(sag, fmaxf(fabsf(__fadd_rn(__fmul_rn(__fmul_rn(6.0f, a[0].C), u0), __fmul_rn(2.0f, a[1].C))), fabsf(__fadd_rn(__fmul_rn(__fmul_rn(6.0f, a[0].C), u1), __fmul_rn(2.0f, a[1].C)))));
+    LCB_SAG(x) LCB_SAG(y) LCB_SAG(z) LCB_SAG(w)
+#undef LCB_SAG
+    sag = __fmul_rn(__fmul_rn(sag, 1.0f / (8.0f * kCurveSubdiv * kCurveSubdiv)), 1.0625f);
+    A.w = __fadd_rn(fabsf(A.w), sag); B.w = __fadd_rn(fabsf(B.w), sag);
+}
+
+// The segment's power-basis coefficients (what refine_curve_hit evaluates), written behind the leaves of a cubic curve BLAS.
+__device__ __forceinline__ void curve_coefficients(const uint8_t *cps, size_t cp_stride, const uint32_t *segs, uint32_t basis, uint32_t seg, float4 a[4]) {
+    const uint32_t first = segs[seg];
+    curve_power_basis(basis, *reinterpret_cast<const float4 *>(cps + (size_t)first * cp_stride), *reinterpret_cast<const float4 *>(cps + (size_t)(first + 1) * cp_stride),
+                      *reinterpret_cast<const float4 *>(cps + (size_t)(first + 2) * cp_stride), *reinterpret_cast<const float4 *>(cps + (size_t)(first + 3) * cp_stride), a);
+}
+
+// Refinement of a cone hit against the true swept surface: Newton on F1 = |p - c(u)|^2 - r(u)^2 = 0, F2 = (p - c(u)).c'(u) + r(u) r'(u) = 0
+// (the envelope condition), p = o + t d, in double precision with a fixed operation order — oracle.c refine_curve_hit is the same
+// sequence, so both sides report the same bits.  end: -1 the piece starts the segment, +1 it ends it.  Candidates: the envelope point
+// the iteration settled on (inside the segment, entry side) and, on a first / last piece, the sphere that closes the segment (exact);
+// the earlier one is the hit.  Neither: the (inflated) cone only bulged out of the sweep, or the ray grazes — the piece reports nothing.
+__device__ __forceinline__ bool curve_end_sphere(const double o[3], const double d[3], const float4 a[4], double ue, float &t_out, float &u_out) {
+#define LCB_CE(C) __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn((double)a[0].C, ue), (double)a[1].C), ue), (double)a[2].C), ue), (double)a[3].C)
+    const double c0 = LCB_CE(x), c1 = LCB_CE(y), c2 = LCB_CE(z), c3 = LCB_CE(w);
+#undef LCB_CE
+    const double oc0 = __dsub_rn(c0, o[0]), oc1 = __dsub_rn(c1, o[1]), oc2 = __dsub_rn(c2, o[2]);
+    const double dd = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+    const double b = __dadd_rn(__dadd_rn(__dmul_rn(oc0, d[0]), __dmul_rn(oc1, d[1])), __dmul_rn(oc2, d[2]));
+    const double ococ = __dadd_rn(__dadd_rn(__dmul_rn(oc0, oc0), __dmul_rn(oc1, oc1)), __dmul_rn(oc2, oc2));
+    const double disc = __dsub_rn(__dmul_rn(b, b), __dmul_rn(dd, __dsub_rn(ococ, __dmul_rn(c3, c3))));
+    if (!(disc >= 0.0)) return false;
+    t_out = __double2float_rn(__ddiv_rn(__dsub_rn(b, __dsqrt_rn(disc)), dd)); u_out = __double2float_rn(ue);
+    return true;
+}
+__device__ __forceinline__ bool refine_curve_hit(const RaySetup &r, const float4 *__restrict__ coef, int end, float &t_io, float &u_io) {
+    float4 a[4] = {__ldg(coef), __ldg(coef + 1), __ldg(coef + 2), __ldg(coef + 3)};
+    double t = (double)t_io, u = (double)u_io;
+    const double o[3] = {(double)r.ox, (double)r.oy, (double)r.oz}, d[3] = {(double)r.dx, (double)r.dy, (double)r.dz};
+    double step_t = INFINITY, step_u = INFINITY, qd = 0.0;
+    bool settled = true;
+    for (int it = 0; it < 6; it++) {
+        double c[4], c1[4], c2[4];
+#define LCB_EV(K, C)                                                                                                                           \
+        {                                                                                                                                      \
+            const double a0 = (double)a[0].C, a1 = (double)a[1].C, a2 = (double)a[2].C, a3 = (double)a[3].C;                                     \
+            c[K] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(a0, u), a1), u), a2), u), a3);                                   \
+            c1[K] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(3.0, a0), u), __dmul_rn(2.0, a1)), u), a2);                               \
+            c2[K] = __dadd_rn(__dmul_rn(__dmul_rn(6.0, a0), u), __dmul_rn(2.0, a1));                                                             \
+        }
+        LCB_EV(0, x) LCB_EV(1, y) LCB_EV(2, z) LCB_EV(3, w)
+#undef LCB_EV
+        const double q0 = __dsub_rn(__dadd_rn(o[0], __dmul_rn(t, d[0])), c[0]), q1 = __dsub_rn(__dadd_rn(o[1], __dmul_rn(t, d[1])), c[1]),
+                     q2 = __dsub_rn(__dadd_rn(o[2], __dmul_rn(t, d[2])), c[2]);
+#define LCB_DOT3(X0, X1, X2, Y0, Y1, Y2) __dadd_rn(__dadd_rn(__dmul_rn(X0, Y0), __dmul_rn(X1, Y1)), __dmul_rn(X2, Y2))
+        const double qq = LCB_DOT3(q0, q1, q2, q0, q1, q2);
+        qd = LCB_DOT3(q0, q1, q2, d[0], d[1], d[2]);
+        const double qc1 = LCB_DOT3(q0, q1, q2, c1[0], c1[1], c1[2]);
+        const double qc2 = LCB_DOT3(q0, q1, q2, c2[0], c2[1], c2[2]);
+        const double dc1 = LCB_DOT3(d[0], d[1], d[2], c1[0], c1[1], c1[2]);
+        const double c1c1 = LCB_DOT3(c1[0], c1[1], c1[2], c1[0], c1[1], c1[2]);
+#undef LCB_DOT3
+        const double F1 = __dsub_rn(qq, __dmul_rn(c[3], c[3]));
+        const double F2 = __dadd_rn(qc1, __dmul_rn(c[3], c1[3]));
+        const double J11 = __dmul_rn(2.0, qd), J12 = __dmul_rn(-2.0, F2), J21 = dc1;
+        const double J22 = __dadd_rn(__dadd_rn(__dsub_rn(qc2, c1c1), __dmul_rn(c1[3], c1[3])), __dmul_rn(c[3], c2[3]));
+        const double det = __dsub_rn(__dmul_rn(J11, J22), __dmul_rn(J12, J21));
+        if (det == 0.0) { settled = false; break; }
+        step_t = __ddiv_rn(__dsub_rn(__dmul_rn(F1, J22), __dmul_rn(J12, F2)), det);
+        step_u = __ddiv_rn(__dsub_rn(__dmul_rn(J11, F2), __dmul_rn(J21, F1)), det);
+        t = __dsub_rn(t, step_t);
+        u = __dsub_rn(u, step_u);
+        if (!(fabs(u) <= 4.0)) { settled = false; break; }
+        if (fabs(step_t) <= __dmul_rn(1e-13, __dadd_rn(fabs(t), 1.0)) && fabs(step_u) <= 1e-13) break;
+    }
+    if (settled && !(fabs(step_t) <= __dmul_rn(1e-7, __dadd_rn(fabs(t), 1.0)) && fabs(step_u) <= 1e-7)) settled = false;
+    bool found = false;
+    float tb = 0.f, ub = 0.f;
+    if (settled && u >= 0.0 && u <= 1.0 && qd < 0.0) { found = true; tb = __double2float_rn(t); ub = __double2float_rn(u); }
+    if (end != 0) {
+        float te, ue;
+        if (curve_end_sphere(o, d, a, end < 0 ? 0.0 : 1.0, te, ue) && (!found || te < tb)) { found = true; tb = te; ub = ue; }
+    }
+    if (!found) return false;
+    t_io = tb; u_io = ub;
+    return true;
 }
 
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
@@ -404,9 +492,14 @@ __device__ __forceinline__ DeviceHit trace_one_impl(const AccelView &acc, const 
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + (Gt.x + bit));
                 const float4 c0 = __ldg(tp), c1 = __ldg(tp + 1), c2 = __ldg(tp + 2);
                 float t, sl;
-                if (canonical_cone(r, tmin, ray_tmax, make_float4(c0.x, c0.y, c0.z, c1.w), make_float4(c1.x, c1.y, c1.z, c2.x), t, sl)) {
+                bool cone_hit = canonical_cone(r, tmin, ray_tmax, make_float4(c0.x, c0.y, c0.z, c1.w), make_float4(c1.x, c1.y, c1.z, c2.x), t, sl);
+                float u = __fmaf_rn(sl, c2.z, c2.y);
+                if (cone_hit && c2.z != 1.0f) {  // a piece of a cubic segment: the cone located the hit, the swept surface decides (refine_curve_hit)
+                    const int end = c2.y == 0.0f ? -1 : (__fadd_rn(c2.y, c2.z) == 1.0f ? 1 : 0);
+                    cone_hit = refine_curve_hit(r, reinterpret_cast<const float4 *>(tris + __float_as_uint(c2.w)), end, t, u) && t > tmin && t <= ray_tmax;
+                }
+                if (cone_hit) {
                     const uint32_t prim = __float_as_uint(c0.w);
-                    const float u = __fmaf_rn(sl, c2.z, c2.y);
                     bool commit = true;
                     if (QUERY && !cur_opaque) {
                         const int verdict = hook.triangle(cur_inst, prim, u, -1.0f, t);

@@ -124,13 +124,14 @@ class TiledPathTracer:
         self.dist.all_gather_into_tensor(out, t)
         return [float(x) for x in out.tolist()]
 
-    def balance(self, passes=4, frame0=100000):
-        """refine the cost map from per-rank times of short passes and re-cut the ranges (samples discarded)"""
+    def balance(self, passes=4, dispatches=4, frame0=100000):
+        """refine the cost map from per-rank times of short passes (`dispatches` dispatches each, samples discarded) and re-cut the
+        ranges; returns the history [(imbalance = max / mean of the per-rank times, tiles per rank)]"""
         history = []
         for p in range(passes):
-            ms = self.timed(lambda: self.render(1, frame0 + p))
+            ms = self.timed(lambda: self.render(dispatches, frame0 + p * dispatches))
             times = self.all_times(ms)
-            history.append(max(times) / (sum(times) / len(times)))
+            history.append((max(times) / (sum(times) / len(times)), [int(x) for x in np.diff(self.bounds)], [round(t, 2) for t in times]))
             self.cost = sharding.refine_cost(self.cost, self.bounds, times)
             self.set_bounds(sharding.balanced_bounds(self.cost, self.world))
         return history

@@ -500,8 +500,19 @@ static void curve_piece(const mesh *m, uint32_t seg, uint32_t k, float A[4], flo
     const float *q2 = (const float *)(m->cps + (size_t)(first + 2) * m->cp_stride), *q3 = (const float *)(m->cps + (size_t)(first + 3) * m->cp_stride);
     float a[4][4];
     curve_basis(m->basis, q0, q1, q2, q3, a);
-    curve_point(a, (float)k * (1.0f / CURVE_PIECES), A);
-    curve_point(a, (float)(k + 1) * (1.0f / CURVE_PIECES), B);
+    const float u0 = (float)k * (1.0f / CURVE_PIECES), u1 = (float)(k + 1) * (1.0f / CURVE_PIECES);
+    curve_point(a, u0, A);
+    curve_point(a, u1, B);
+    /* The cone only locates the hit (refine_curve_hit decides): its radii are inflated by a bound on how far the cubic leaves its chord
+     * over the piece — du^2 / 8 * max |c''| per component, c'' linear in u — so that every ray that enters the true sweep here also enters
+     * the cone and becomes a candidate. */
+    float sag = 0.0f;
+    for (int c = 0; c < 4; c++) {
+        const float s0 = fabsf(6.0f * a[0][c] * u0 + 2.0f * a[1][c]), s1 = fabsf(6.0f * a[0][c] * u1 + 2.0f * a[1][c]);
+        sag += fmaxf(s0, s1);
+    }
+    sag = sag * (1.0f / (8.0f * CURVE_PIECES * CURVE_PIECES)) * 1.0625f;
+    A[3] = fabsf(A[3]) + sag; B[3] = fabsf(B[3]) + sag;
 }
 static inline float dot3f(const float *a, const float *b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
 /* canonical ray / rounded cone (after I. Quilez' intersector; both lateral roots, unnormalised direction, formed about the point
@@ -553,6 +564,73 @@ int oracle_canonical_cone(const float o[3], const float d[3], float tmin, float 
     memcpy(f.o, o, 12); memcpy(f.d, d, 12);
     return canon_cone(&f, tmin, tmax, A, B, t, s);
 }
+/* The cone pieces only locate the hit: a cubic segment's surface is the sweep of the sphere (c(u), r(u)), and the hit a piece reports is
+ * refined against it — Newton on  F1 = |p - c(u)|^2 - r(u)^2 = 0,  F2 = (p - c(u)).c'(u) + r(u) r'(u) = 0  (the envelope condition), p = o + t d,
+ * in double precision with a fixed operation order (trace_device.cuh refine_curve_hit is the same sequence), at most six iterations from
+ * the cone hit.  When the iteration does not settle inside the segment, the first / last piece answers with the sphere that closes the
+ * segment (exact, in double) if the ray hits it; otherwise — and when the iteration settles on the far side of the sweep — the piece reports
+ * no hit (returns 0).  The cone hit itself is never reported for a cubic segment. */
+static int curve_end_sphere(const double o[3], const double d[3], float a[4][4], double ue, float *t_io, float *u_io) {
+    double c[4];
+    for (int k = 0; k < 4; k++) c[k] = (((double)a[0][k] * ue + (double)a[1][k]) * ue + (double)a[2][k]) * ue + (double)a[3][k];
+    const double oc[3] = {c[0] - o[0], c[1] - o[1], c[2] - o[2]};
+    const double dd = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+    const double b = (oc[0] * d[0] + oc[1] * d[1]) + oc[2] * d[2];
+    const double disc = b * b - dd * (((oc[0] * oc[0] + oc[1] * oc[1]) + oc[2] * oc[2]) - c[3] * c[3]);
+    if (!(disc >= 0.0)) return 0;
+    *t_io = (float)((b - sqrt(disc)) / dd); *u_io = (float)ue;
+    return 1;
+}
+/* end: -1 the piece starts the segment, +1 it ends it, 0 neither (a one-piece segment cannot occur: cubic segments have 8 pieces) */
+static int refine_curve_hit(const ray_frame *f, float a[4][4], int end, float *t_io, float *u_io) {
+    double t = (double)*t_io, u = (double)*u_io;
+    const double o[3] = {f->o[0], f->o[1], f->o[2]}, d[3] = {f->d[0], f->d[1], f->d[2]};
+    double step_t = INFINITY, step_u = INFINITY, qd = 0.0;
+    int settled = 1;
+    for (int it = 0; it < 6; it++) {
+        double c[4], c1[4], c2[4];
+        for (int k = 0; k < 4; k++) {
+            const double a0 = a[0][k], a1 = a[1][k], a2 = a[2][k], a3 = a[3][k];
+            c[k] = ((a0 * u + a1) * u + a2) * u + a3;
+            c1[k] = ((3.0 * a0) * u + (2.0 * a1)) * u + a2;
+            c2[k] = (6.0 * a0) * u + (2.0 * a1);
+        }
+        const double q[3] = {(o[0] + t * d[0]) - c[0], (o[1] + t * d[1]) - c[1], (o[2] + t * d[2]) - c[2]};
+        const double qq = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+        qd = (q[0] * d[0] + q[1] * d[1]) + q[2] * d[2];
+        const double qc1 = (q[0] * c1[0] + q[1] * c1[1]) + q[2] * c1[2];
+        const double qc2 = (q[0] * c2[0] + q[1] * c2[1]) + q[2] * c2[2];
+        const double dc1 = (d[0] * c1[0] + d[1] * c1[1]) + d[2] * c1[2];
+        const double c1c1 = (c1[0] * c1[0] + c1[1] * c1[1]) + c1[2] * c1[2];
+        const double F1 = qq - c[3] * c[3];
+        const double F2 = qc1 + c[3] * c1[3];
+        const double J11 = 2.0 * qd, J12 = -2.0 * F2, J21 = dc1;
+        const double J22 = ((qc2 - c1c1) + c1[3] * c1[3]) + c[3] * c2[3];
+        const double det = J11 * J22 - J12 * J21;
+        if (det == 0.0) { settled = 0; break; }
+        step_t = (F1 * J22 - J12 * F2) / det;
+        step_u = (J11 * F2 - J21 * F1) / det;
+        t = t - step_t;
+        u = u - step_u;
+        if (!(fabs(u) <= 4.0)) { settled = 0; break; }   /* diverging (also catches NaN) */
+        if (fabs(step_t) <= 1e-13 * (fabs(t) + 1.0) && fabs(step_u) <= 1e-13) break;
+    }
+    if (settled && !(fabs(step_t) <= 1e-7 * (fabs(t) + 1.0) && fabs(step_u) <= 1e-7)) settled = 0;
+    /* candidates: the envelope point the iteration settled on (inside the segment, entry side) and — on the segment's first / last piece —
+     * the sphere that closes the segment (exact, in double), which the ray may enter before it reaches the envelope; the earlier one is
+     * the hit.  Neither: the cone's surface only bulged out of the sweep, or the ray grazes. */
+    int found = 0;
+    float tb = 0.f, ub = 0.f;
+    if (settled && u >= 0.0 && u <= 1.0 && qd < 0.0) { found = 1; tb = (float)t; ub = (float)u; }
+    if (end != 0) {
+        float te, ue;
+        if (curve_end_sphere(o, d, a, end < 0 ? 0.0 : 1.0, &te, &ue) && (!found || te < tb)) { found = 1; tb = te; ub = ue; }
+    }
+    if (!found) return 0;
+    *t_io = tb; *u_io = ub;
+    return 1;
+}
+
 /* every piece of every segment, brute force; ties: lowest (inst, prim), then lowest u */
 static void curve_closest(const mesh *m, const ray_frame *f, float tmin, float tmax, uint32_t inst, best_hit *best, const oracle_filter *flt, int first) {
     const uint32_t pieces = m->basis == 0 ? 1 : CURVE_PIECES;
@@ -562,7 +640,15 @@ static void curve_closest(const mesh *m, const ray_frame *f, float tmin, float t
             float A[4], B[4], t, sl;
             curve_piece(m, seg, k, A, B);
             if (!canon_cone(f, tmin, tmax, A, B, &t, &sl)) continue;
-            const float u = fmaf(sl, du, (float)k * du);
+            float u = fmaf(sl, du, (float)k * du);
+            if (m->basis != 0) {
+                const uint32_t first = m->segs[seg];
+                float a[4][4];
+                curve_basis(m->basis, (const float *)(m->cps + (size_t)first * m->cp_stride), (const float *)(m->cps + (size_t)(first + 1) * m->cp_stride),
+                            (const float *)(m->cps + (size_t)(first + 2) * m->cp_stride), (const float *)(m->cps + (size_t)(first + 3) * m->cp_stride), a);
+                if (!refine_curve_hit(f, a, k == 0 ? -1 : (k + 1 == pieces ? 1 : 0), &t, &u)) continue;
+                if (!(t > tmin && t <= tmax)) continue;
+            }
             if (flt && !filter_accept(flt, inst, seg, u, -1.0f)) continue;
             best_hit *b = best;
             if (!b->found || t < b->t || (t == b->t && (inst < b->inst || (inst == b->inst && (seg < b->prim || (seg == b->prim && b->curve && u < b->u)))))) {

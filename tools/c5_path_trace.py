@@ -67,7 +67,7 @@ def main():
         rgb = img[..., :3] / np.maximum(img[..., 3:4], 1)
         res = {"config": "c5_path_trace", "n_gpus": world, "width": a.width, "height": a.height, "spp": n_dispatch * a.spp_per_dispatch, "depth": a.depth, "triangles": pt.triangles,
                "frame_ms": round(max(times), 3), "frame_ms_per_rank": [round(t, 2) for t in times], "streams": len(pt.lanes), "block": a.block, "fast_math": not a.precise, "lowering": a.lowering,
-               "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes_imbalance": [round(h, 3) for h in history], "rays": total_rays,
+               "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes": [{"imbalance": round(h[0], 3), "tiles_per_rank": h[1], "ms_per_rank": h[2]} for h in history], "rays": total_rays,
                "mrays_per_s": round(total_rays / max(times) / 1e3, 1), "mean_radiance": round(float(rgb.mean()), 5),
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img)}
         os.write(real_stdout, (json.dumps(res) + "\n").encode())
