@@ -215,6 +215,68 @@ def dsl_path_tracer_leg(dev, lc, scenes, torch, _ext):
     return out
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank — and allocate its pinned staging — on the host cores next to its GPU: with 8 ranks the e2e legs move 56 B per ray
+    through host memory, and a rank whose pinned buffers sit on the other socket crosses the socket interconnect twice.  No-op when the
+    platform reports no NUMA node for the device (single-socket hosts, containers that hide /sys)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so.12")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, local_rank) == 0:
+                bdf = buf.value.decode()
+        if not bdf:
+            return info
+        path = f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as e:  # binding is an optimisation: never fail the bench for it
+        info["error"] = str(e)[:80]
+    return info
+
+
+def pcie_probe(torch, dist, world, mib=512, reps=3):
+    """What the host link gives THIS run: every rank copies `mib` MiB pinned -> device and device -> pinned at the same time, all ranks
+    together; returns per-rank GB/s (min over ranks) and the sum — the ceiling of any host-buffer (e2e) number at this N."""
+    n = mib << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = float("inf")
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    gbs = torch.tensor([2 * n / best / 1e9], device="cuda", dtype=torch.float64)
+    lo, total = gbs.clone(), gbs.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return {"h2d_plus_d2h_gbs_per_rank_min": float(lo.item()), "h2d_plus_d2h_gbs_sum": float(total.item()),
+            "e2e_ceiling_mrays_per_s": float(total.item()) * 1e9 / 56 / 1e6, "note": f"{mib} MiB each way per rank, concurrently on all {world} ranks, pinned memory"}
+
+
+
 def e2e_reference_api(dev, shader, accel, rb, hb, rays_np, hits_np, n, lanes, chunk_rays):
     """One end-to-end pass with HOST buffers through DeviceInterface calls only: per chunk a BufferUpload on the upload stream, the
     ShaderDispatch over that chunk's buffer views on the compute stream, a BufferDownload on the download stream, ordered by two
@@ -310,7 +372,7 @@ def main():
     ap.add_argument("--profile", action="store_true", help="short run for ncu: only the headline steps")
     ap.add_argument("--c5-spp", type=int, default=1024, help="samples per pixel of the C5 leg (BASELINE: 1024); 0 skips the leg")
     ap.add_argument("--c5-spp-per-dispatch", type=int, default=16)
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="rays per chunk of the host-buffer pipeline")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 21, help="rays per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -329,6 +391,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     os.environ["LC_B200_DEVICE"] = str(local_rank)
+    host_binding = bind_to_gpu_numa_node(torch, local_rank)   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -518,6 +581,8 @@ def main():
         out["e2e_batch_entry"] = {"value": world * n * max(args.steps // 2, 1) / dt / 1e6, "unit": UNIT, "api": "lc_b200_trace_closest_host (chunked H2D / k_trace / D2H pipeline inside the library)"}
         for r in lanes:
             r.destroy()
+        out["host_link"] = pcie_probe(torch, dist if world > 1 else None, world)
+        out["host_link"]["rank0_binding"] = host_binding
 
     if rank == 0 and not args.profile:
         out["parity_sample"] = parity_sample_leg(dev, lc, None)

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, 
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             float scale = __uint_as_float((uint32_t)root.e[k] << 23);
-            uint32_t qmin = 0xffff, qmax = 0;
+            uint32_t qmin = kQMax, qmax = 0;
             for (int c = 0; c < 8; c++) {
                 if (root.meta[c] == 0) continue;
                 qmin = min(qmin, (uint32_t)root.q[k][0][c]);
@@ -600,12 +600,12 @@ struct LeafSinkInstances {
 };
 
 // Quantise [lo,hi] of one child against the node frame, conservatively (directed rounding).
-__device__ __forceinline__ void quantise_axis(float clo, float chi, float org, float inv_scale, uint16_t &qlo, uint16_t &qhi) {
+__device__ __forceinline__ void quantise_axis(float clo, float chi, float org, float inv_scale, qplane_t &qlo, qplane_t &qhi) {
     float l = floorf(__fmul_rd(__fsub_rd(clo, org), inv_scale));
     float u = ceilf(__fmul_ru(__fsub_ru(chi, org), inv_scale));
-    l = fminf(fmaxf(l, 0.f), 65535.f);
-    u = fminf(fmaxf(u, 0.f), 65535.f);
-    qlo = (uint16_t)l; qhi = (uint16_t)u;
+    l = fminf(fmaxf(l, 0.f), (float)kQMax);
+    u = fminf(fmaxf(u, 0.f), (float)kQMax);
+    qlo = (qplane_t)l; qhi = (qplane_t)u;
 }
 
 // One 8-lane group per wide node, lane j holding child j in registers: the split search, the node frame, the greedy
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
                 const float vlo = mine.lo[k] == mine.lo[k] ? mine.lo[k] : FLT_MAX, vhi = mine.hi[k] == mine.hi[k] ? mine.hi[k] : -FLT_MAX;
                 nlo[k] = ordered_to_float(__reduce_min_sync(gmask, float_to_ordered(vlo)));
                 nhi[k] = ordered_to_float(__reduce_max_sync(gmask, float_to_ordered(vhi)));
-                const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
+                const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
                 const uint32_t bits = __float_as_uint(sc);
                 uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
                 e = max(e, 1u); e = min(e, 253u);
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
         }
         if (!occupied) {
             out.meta[sub] = 0;
-            for (int k = 0; k < 3; k++) { out.q[k][0][sub] = 0xffff; out.q[k][1][sub] = 0; }
+            for (int k = 0; k < 3; k++) { out.q[k][0][sub] = (qplane_t)kQMax; out.q[k][1][sub] = 0; }
         } else {
             for (int k = 0; k < 3; k++) quantise_axis(c.lo[k], c.hi[k], nlo[k], inv_scale[k], out.q[k][0][sub], out.q[k][1][sub]);
             if (is_int) {
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
             }
         }
         __syncwarp(gmask);
-        reinterpret_cast<uint4 *>(&nodes[t])[sub] = reinterpret_cast<const uint4 *>(&out)[sub];
+        if (sub < (uint32_t)kNodeQuads) reinterpret_cast<uint4 *>(&nodes[t])[sub] = reinterpret_cast<const uint4 *>(&out)[sub];
         __syncwarp(gmask);
       }
       // ---- grid barrier; the last CTA to arrive publishes the end of the next level -------------------------------
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(128) k_refit(WideNode *nodes, const PackedTri 
         }
         float inv_scale[3];
         for (int k = 0; k < 3; k++) {
-            float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), 65535.0f);
+            float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
             uint32_t bits = __float_as_uint(sc);
             uint32_t ex = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
             ex = max(ex, 1u); ex = min(ex, 253u);
@@ -1058,7 +1058,7 @@ __global__ void __launch_bounds__(128) k_refit(WideNode *nodes, const PackedTri 
         const uint4 *src = reinterpret_cast<const uint4 *>(&node);
         uint4 *dst = reinterpret_cast<uint4 *>(&nodes[i]);
 #pragma unroll
-        for (int q = 0; q < 8; q++) dst[q] = src[q];
+        for (int q = 0; q < kNodeQuads; q++) dst[q] = src[q];
         float *b = boxes + 6 * (size_t)i;
         for (int k = 0; k < 3; k++) { __stcg(b + k, nlo[k]); __stcg(b + 3 + k, nhi[k]); }
         const uint32_t p = parent[i];

@@ -3,8 +3,8 @@
 // Everything the traversal kernels touch is laid out for full-sector access with sm_100's 256-bit loads
 // (LDG.E.ENL2.256: one 32-byte sector per lane and instruction — on divergent addresses the L1TEX data pipe
 // charges per lane and instruction, so wider loads are what relieves it; tools/micro/gather256.cu):
-//   WideNode    128 B, 128-byte aligned : one L2 line = four sectors, fetched as 4 x LDG.256
-//                                         (header | x planes lo,hi | y planes lo,hi | z planes lo,hi)
+//   WideNode     96 B,  32-byte aligned : three sectors, fetched as 3 x LDG.256 (header | x, y planes lo,hi | z planes lo,hi + spare);
+//                                         with 16-bit planes (LCB_NODE_BITS=16) 128 B = four sectors (header | x | y | z planes lo,hi)
 //   PackedTri    64 B,  64-byte aligned : LDG.256 (v0|prim, v1) + LDG.128 (v2); 16 B spare
 //   InstanceRec 128 B,  16-byte aligned : eight float4
 #pragma once
@@ -34,16 +34,35 @@ namespace lcb {
 //   imask   : bit i set <=> slot i is an internal child; internal children are stored
 //             contiguously from child_base in ascending slot order
 //   prim_base : first PackedTri (BLAS) / first entry of the instance-id list (TLAS)
-struct alignas(128) WideNode {
+// Plane resolution (compile-time): 8 bits -> a 96-byte node = THREE 32-byte sectors per visit, 16 bits -> 128 bytes = four.  The traversal
+// is bound by the L1TEX wavefronts of exactly these divergent sector fetches, so the narrower node is the default; its boxes are looser by
+// at most 1/255 of the parent's extent per plane (a few per cent more node visits), which the sector count more than pays for
+// (profiles/r02g_node_bits.txt).  -DLCB_NODE_BITS=16 builds the round-1 layout for A/B runs.
+#ifndef LCB_NODE_BITS
+#define LCB_NODE_BITS 8
+#endif
+#if LCB_NODE_BITS == 16
+typedef uint16_t qplane_t;
+#define LCB_NODE_ALIGN 128
+#else
+typedef uint8_t qplane_t;
+#define LCB_NODE_ALIGN 32
+#endif
+constexpr uint32_t kQMax = (1u << LCB_NODE_BITS) - 1u;  // largest plane index
+struct alignas(LCB_NODE_ALIGN) WideNode {
     float org[3];
     uint8_t e[3];
     uint8_t imask;
     uint32_t child_base;
     uint32_t prim_base;
     uint8_t meta[8];
-    uint16_t q[3][2][8];  // [axis][0 = lower plane, 1 = upper plane][slot]
+    qplane_t q[3][2][8];  // [axis][0 = lower plane, 1 = upper plane][slot]
+#if LCB_NODE_BITS == 8
+    uint8_t spare[16];    // the node is three whole sectors: header | x, y planes | z planes + spare
+#endif
 };
-static_assert(sizeof(WideNode) == 128, "WideNode must be one 128-byte line");
+static_assert(sizeof(WideNode) == (LCB_NODE_BITS == 16 ? 128 : 96), "WideNode is a whole number of 32-byte sectors");
+constexpr int kNodeQuads = sizeof(WideNode) / 16;  // 16-byte pieces of a node (node stores)
 
 struct alignas(64) PackedTri {
     float v0[3]; uint32_t prim;

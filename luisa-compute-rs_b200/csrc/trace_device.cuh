@@ -107,14 +107,19 @@ __device__ __forceinline__ uint32_t sign_extend_bytes(uint32_t x) {
     return d;
 }
 
+// 8-bit plane index (byte B of word W) -> float 1 + q * 2^-15 in ONE byte-permute: the byte lands in bits 8..15 of the mantissa of 1.0f.
+// Folding the 1 into the per-node constants then costs an ulp of 2^15 * step = 2^-9 of a quantisation step (the 16-bit form above pays
+// half a step, because 2^23 + q leaves no mantissa below q), so the slop the padding has to absorb shrinks from a whole step to 1/64.
+#define LCB_Q8(W, B) __uint_as_float(__byte_perm(0x3F800000u, W, 0x3240 + ((B) << 4)))
+
 // Tests the 8 children of one node.  Returns the hit mask: bits 24..31 internal children in
 // traversal priority order for this ray's octant, bits 0..23 leaf primitives.
 __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ node, const RaySetup &r, float tmin, float tmax,
                                                    uint32_t &child_base, uint32_t &prim_base, uint32_t &imask) {
     const uint4 *p = reinterpret_cast<const uint4 *>(node);
-    const U8 H = ldg256(p), X = ldg256(p + 2), Y = ldg256(p + 4), Z = ldg256(p + 6);
-    const uint4 n0 = make_uint4(H.v[0], H.v[1], H.v[2], H.v[3]), n1 = make_uint4(H.v[4], H.v[5], H.v[6], H.v[7]);
     const bool neg_x = (r.octinv & 1u) == 0, neg_y = (r.octinv & 2u) == 0, neg_z = (r.octinv & 4u) == 0;
+#if LCB_NODE_BITS == 16
+    const U8 H = ldg256(p), X = ldg256(p + 2), Y = ldg256(p + 4), Z = ldg256(p + 6);
     // near/far plane vectors by direction sign (words 0..3 = lower planes, 4..7 = upper planes of the 8 slots)
 #define LCB_NEAR(V, NEG) make_uint4(NEG ? V.v[4] : V.v[0], NEG ? V.v[5] : V.v[1], NEG ? V.v[6] : V.v[2], NEG ? V.v[7] : V.v[3])
 #define LCB_FAR(V, NEG) make_uint4(NEG ? V.v[0] : V.v[4], NEG ? V.v[1] : V.v[5], NEG ? V.v[2] : V.v[6], NEG ? V.v[3] : V.v[7])
@@ -123,18 +128,37 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
     const uint4 qnz = LCB_NEAR(Z, neg_z), qfz = LCB_FAR(Z, neg_z);
 #undef LCB_NEAR
 #undef LCB_FAR
+#else
+    // three sectors: header | x lo, x hi, y lo, y hi (8 bytes each) | z lo, z hi, spare
+    const U8 H = ldg256(p), XY = ldg256(p + 2);
+    const uint4 Zq = __ldg(p + 4);
+    const uint2 qnx = neg_x ? make_uint2(XY.v[2], XY.v[3]) : make_uint2(XY.v[0], XY.v[1]), qfx = neg_x ? make_uint2(XY.v[0], XY.v[1]) : make_uint2(XY.v[2], XY.v[3]);
+    const uint2 qny = neg_y ? make_uint2(XY.v[6], XY.v[7]) : make_uint2(XY.v[4], XY.v[5]), qfy = neg_y ? make_uint2(XY.v[4], XY.v[5]) : make_uint2(XY.v[6], XY.v[7]);
+    const uint2 qnz = neg_z ? make_uint2(Zq.z, Zq.w) : make_uint2(Zq.x, Zq.y), qfz = neg_z ? make_uint2(Zq.x, Zq.y) : make_uint2(Zq.z, Zq.w);
+#endif
+    const uint4 n0 = make_uint4(H.v[0], H.v[1], H.v[2], H.v[3]), n1 = make_uint4(H.v[4], H.v[5], H.v[6], H.v[7]);
     child_base = n1.x; prim_base = n1.y; imask = n0.w >> 24;
     const float sclx = __uint_as_float((n0.w & 0xffu) << 23), scly = __uint_as_float((n0.w & 0xff00u) << 15), sclz = __uint_as_float((n0.w & 0xff0000u) << 7);
     const float rx = __uint_as_float(n0.x) - r.ox, ry = __uint_as_float(n0.y) - r.oy, rz = __uint_as_float(n0.z) - r.oz;
     // conservative padding: 2^-20 of the L-inf distance from the ray origin to the far side of the node frame
-    const float R = fmaxf(fmaxf(fabsf(rx) + 65535.0f * sclx, fabsf(ry) + 65535.0f * scly), fabsf(rz) + 65535.0f * sclz);
+    constexpr float kSpan = (float)kQMax;
+    const float R = fmaxf(fmaxf(fabsf(rx) + kSpan * sclx, fabsf(ry) + kSpan * scly), fabsf(rz) + kSpan * sclz);
     const float pad = R * (1.0f / 1048576.0f);
     const float ax = sclx * r.ix, ay = scly * r.iy, az = sclz * r.iz;
     const float cx = rx * r.ix, cy = ry * r.iy, cz = rz * r.iz;
+#if LCB_NODE_BITS == 16
     const float px = fmaf(pad, fabsf(r.ix), fabsf(ax)), py = fmaf(pad, fabsf(r.iy), fabsf(ay)), pz = fmaf(pad, fabsf(r.iz), fabsf(az));
     const float bnx = fmaf(-8388608.0f, ax, cx - px), bfx = fmaf(-8388608.0f, ax, cx + px);
     const float bny = fmaf(-8388608.0f, ay, cy - py), bfy = fmaf(-8388608.0f, ay, cy + py);
     const float bnz = fmaf(-8388608.0f, az, cz - pz), bfz = fmaf(-8388608.0f, az, cz + pz);
+    const float mx = ax, my = ay, mz = az;
+#else
+    const float px = fmaf(pad, fabsf(r.ix), fabsf(ax) * (1.0f / 64.0f)), py = fmaf(pad, fabsf(r.iy), fabsf(ay) * (1.0f / 64.0f)), pz = fmaf(pad, fabsf(r.iz), fabsf(az) * (1.0f / 64.0f));
+    const float mx = ax * 32768.0f, my = ay * 32768.0f, mz = az * 32768.0f;  // plane index arrives as 1 + q * 2^-15
+    const float bnx = (cx - px) - mx, bfx = (cx + px) - mx;
+    const float bny = (cy - py) - my, bfy = (cy + py) - my;
+    const float bnz = (cz - pz) - mz, bfz = (cz + pz) - mz;
+#endif
     // hit-mask construction on 4 meta bytes at a time (after Ylitie et al. 2017): per child only a byte extract,
     // a shift and a select remain.  Internal children (low 5 bits >= 24) get their bit index XORed with the
     // ray octant so that __clz order is front-to-back order.
@@ -144,15 +168,15 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
     const uint32_t idx_lo = (n1.z ^ (oct4 & inner_lo)) & 0x1f1f1f1fu, idx_hi = (n1.w ^ (oct4 & inner_hi)) & 0x1f1f1f1fu;
     const uint32_t bits_lo = (n1.z >> 5) & 0x07070707u, bits_hi = (n1.w >> 5) & 0x07070707u;
     uint32_t hits = 0;
-#define LCB_CHILD(WORD, CONV, BITS, IDX, SHIFT)                                                              \
+#define LCB_CHILD_T(NX, NY, NZ, FX, FY, FZ, BITS, IDX, SHIFT)                                                \
     {                                                                                                        \
-        const float tn = fmaxf(fmaxf(fmaf(CONV(qnx.WORD), ax, bnx), fmaf(CONV(qny.WORD), ay, bny)),          \
-                               fmaxf(fmaf(CONV(qnz.WORD), az, bnz), tmin));                                  \
-        const float tf = fminf(fminf(fmaf(CONV(qfx.WORD), ax, bfx), fmaf(CONV(qfy.WORD), ay, bfy)),          \
-                               fminf(fmaf(CONV(qfz.WORD), az, bfz), tmax));                                  \
+        const float tn = fmaxf(fmaxf(fmaf(NX, mx, bnx), fmaf(NY, my, bny)), fmaxf(fmaf(NZ, mz, bnz), tmin));   \
+        const float tf = fminf(fminf(fmaf(FX, mx, bfx), fmaf(FY, my, bfy)), fminf(fmaf(FZ, mz, bfz), tmax));   \
         const uint32_t b = ((BITS >> SHIFT) & 0xffu) << ((IDX >> SHIFT) & 31u);                              \
         hits |= tn <= tf ? b : 0u;                                                                           \
     }
+#if LCB_NODE_BITS == 16
+#define LCB_CHILD(WORD, CONV, BITS, IDX, SHIFT) LCB_CHILD_T(CONV(qnx.WORD), CONV(qny.WORD), CONV(qnz.WORD), CONV(qfx.WORD), CONV(qfy.WORD), CONV(qfz.WORD), BITS, IDX, SHIFT)
     LCB_CHILD(x, q16_lo, bits_lo, idx_lo, 0)
     LCB_CHILD(x, q16_hi, bits_lo, idx_lo, 8)
     LCB_CHILD(y, q16_lo, bits_lo, idx_lo, 16)
@@ -161,7 +185,19 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode *__restrict__ 
     LCB_CHILD(z, q16_hi, bits_hi, idx_hi, 8)
     LCB_CHILD(w, q16_lo, bits_hi, idx_hi, 16)
     LCB_CHILD(w, q16_hi, bits_hi, idx_hi, 24)
+#else
+#define LCB_CHILD(WORD, B, BITS, IDX, SHIFT) LCB_CHILD_T(LCB_Q8(qnx.WORD, B), LCB_Q8(qny.WORD, B), LCB_Q8(qnz.WORD, B), LCB_Q8(qfx.WORD, B), LCB_Q8(qfy.WORD, B), LCB_Q8(qfz.WORD, B), BITS, IDX, SHIFT)
+    LCB_CHILD(x, 0, bits_lo, idx_lo, 0)
+    LCB_CHILD(x, 1, bits_lo, idx_lo, 8)
+    LCB_CHILD(x, 2, bits_lo, idx_lo, 16)
+    LCB_CHILD(x, 3, bits_lo, idx_lo, 24)
+    LCB_CHILD(y, 0, bits_hi, idx_hi, 0)
+    LCB_CHILD(y, 1, bits_hi, idx_hi, 8)
+    LCB_CHILD(y, 2, bits_hi, idx_hi, 16)
+    LCB_CHILD(y, 3, bits_hi, idx_hi, 24)
+#endif
 #undef LCB_CHILD
+#undef LCB_CHILD_T
     return hits;
 }
 
