@@ -745,7 +745,7 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
         if (!pinned) (void)cudaGetLastError();
         if (pinned && (!direct_copies.empty() || cudaStreamQuery(st) == cudaSuccess)) {
             CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st));
-            cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+            cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));  // spin-wait: a blocking-sync wake-up cost ~0.4 ms per 64 MB chunk (profiles/r02j_e2e_probe.txt)
             CUDA_CHECK(cudaEventRecord(ev, st));
             direct_copies.push_back(ev);
             return;

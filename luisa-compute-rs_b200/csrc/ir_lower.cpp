@@ -1016,7 +1016,7 @@ void lower_kernel(const KernelModule *km, LoweredKernel &out) {
     // (yield at 8 ready lanes) and 5 CTAs per SM; a path tracer's user phases are long enough that running them for a few lanes at a
     // time costs more than the idle traversal lanes (yield at 32 = when the whole warp has finished) and need 4 CTAs' worth of registers.
     out.wave_yield_min = scan.body_nodes < 64 ? 8 : (scan.body_nodes >= 256 ? 32 : 16);
-    const int wave_min_blocks = scan.body_nodes < 128 ? 5 : 4;
+    const int wave_min_blocks = scan.body_nodes < 128 ? 7 : 4;   // 72 registers: the spilled state machine still wins on occupancy (profiles/r02h_dsl_c3.jsonl)
 
     collect_phis(km->module.entry.ptr, fe.phis);
     if (wave) fe.indent = 4;

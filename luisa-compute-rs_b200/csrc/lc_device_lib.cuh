@@ -387,12 +387,29 @@ struct lc_ids_t { lc_uint3 thread, block, dispatch; };
 // a CUDA block's threads), so consecutive items are neighbours in the dispatch.  false: the position lies outside dispatch_size.
 template <uint32_t BX, uint32_t BY, uint32_t BZ> __device__ inline bool lc_wave_ids(const lc_launch &l, unsigned long long item, lc_ids_t &ids) {
     constexpr uint32_t kBlock = BX * BY * BZ;
-    const unsigned long long b = item / kBlock;
-    const uint32_t t = (uint32_t)(item - b * kBlock);
+    if (BY == 1 && BZ == 1 && l.dispatch_size[1] == 1 && l.dispatch_size[2] == 1 && l.work_items <= 0xffffffffull) {
+        // one-dimensional dispatch (buffer-to-buffer kernels): the work item IS the dispatch id — no divisions on the per-ray path
+        const uint32_t x = (uint32_t)item;
+        ids.block = lc_uint3(x / BX, 0u, 0u);
+        ids.thread = lc_uint3(x % BX, 0u, 0u);
+        ids.dispatch = lc_uint3(x, 0u, 0u);
+        return x < l.dispatch_size[0];
+    }
     const uint32_t gx = (l.dispatch_size[0] + BX - 1) / BX, gy = (l.dispatch_size[1] + BY - 1) / BY;
-    const unsigned long long bz = b / ((unsigned long long)gx * gy);
-    const uint32_t bxy = (uint32_t)(b - bz * ((unsigned long long)gx * gy));
-    ids.block = lc_uint3(bxy % gx, bxy / gx, (uint32_t)bz);
+    uint32_t t, bxy, bz;
+    if (l.work_items <= 0xffffffffull) {  // 32-bit arithmetic whenever the padded grid fits (a 64-bit division costs ~100 instructions)
+        const uint32_t b = (uint32_t)item / kBlock;
+        t = (uint32_t)item - b * kBlock;
+        bz = b / (gx * gy);
+        bxy = b - bz * (gx * gy);
+    } else {
+        const unsigned long long b = item / kBlock;
+        t = (uint32_t)(item - b * kBlock);
+        const unsigned long long z = b / ((unsigned long long)gx * gy);
+        bz = (uint32_t)z;
+        bxy = (uint32_t)(b - z * ((unsigned long long)gx * gy));
+    }
+    ids.block = lc_uint3(bxy % gx, bxy / gx, bz);
     ids.thread = lc_uint3(t % BX, (t / BX) % BY, t / (BX * BY));
     ids.dispatch = lc_uint3(ids.block.x * BX + ids.thread.x, ids.block.y * BY + ids.thread.y, ids.block.z * BZ + ids.thread.z);
     return ids.dispatch.x < l.dispatch_size[0] && ids.dispatch.y < l.dispatch_size[1] && ids.dispatch.z < l.dispatch_size[2];

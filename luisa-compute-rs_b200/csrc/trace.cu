@@ -37,7 +37,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kTraceThreads = LCB_TRACE_THREADS;  // warps are independent (warp-local ray pools, no block barrier): any multiple of 32
 constexpr int kChunk = 128;  // ray indices fetched per global atomic
 #ifndef LCB_TRACE_MIN_BLOCKS
-#define LCB_TRACE_MIN_BLOCKS 6  // 80 registers, 4 bytes of spills; 7 CTAs (72 registers, 28 bytes) measured 2-4 % slower (profiles/r02a_, r02d_k_trace_variants.txt)
+#define LCB_TRACE_MIN_BLOCKS 7  // 72 registers, no spills with the 96-byte node: 1410 Mrays/s on C3 against 1342 at 6 CTAs and 1202 at 5 (profiles/r02h_occupancy.txt)
 #endif
 #ifndef LCB_SMEM_STACK
 #define LCB_SMEM_STACK 16
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
     bool has_ray = false;
     unsigned long long ray_idx = 0;
     RaySetup r;
-    float tmin = 0.f, tbest = 0.f, ray_tmax = 0.f;
+    float tmin = 0.f, tbest = 0.f;  // tbest starts as the ray's tmax and only shrinks: also the upper end of the interval triangles are tested against
     uint32_t hit_inst = kNone, hit_prim = kNone, hit_slot = 0;  // hit_slot: index of the winning PackedTri
     uint32_t cur_inst = kNone;
     const WideNode *nodes = acc.tlas_nodes;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                         ray_idx = order ? (unsigned long long)__ldg(order + mine) : mine;
                         const float4 ra = LCB_LD_STREAM(rays + 2 * ray_idx), rb = LCB_LD_STREAM(rays + 2 * ray_idx + 1);
                         setup_world(r, ra, rb);
-                        tmin = ra.w; tbest = rb.w; ray_tmax = rb.w;
+                        tmin = ra.w; tbest = rb.w;
                         hit_inst = kNone; hit_prim = kNone; hit_slot = 0;
                         cur_inst = kNone; nodes = acc.tlas_nodes; tris = nullptr;
                         sp = 0;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     const float4 v1 = make_float4(__uint_as_float(t01.v[4]), __uint_as_float(t01.v[5]), __uint_as_float(t01.v[6]), 0.f);
                     if (COUNTERS) n_tris++;
                     float t, V, W, det;
-                    if (canonical_triangle(r, tmin, ray_tmax, v0, v1, v2, t, V, W, det)) {
+                    if (canonical_triangle(r, tmin, tbest, v0, v1, v2, t, V, W, det)) {
                         const uint32_t prim = __float_as_uint(v0.w);
                         bool commit = true;
                         if (QUERY && !cur_opaque) {  // candidate hook sees the canonical fp32 barycentrics
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kTraceThreads, LCB_TRACE_MIN_BLOCKS) k_trace(A
                     uint2 *o = reinterpret_cast<uint2 *>(out) + 3 * ray_idx;
                     LCB_ST_STREAM(o, make_uint2(hit_inst, hit_prim));
                     // barycentrics are formed by k_refine; the pad word carries the winning PackedTri slot to it
-                    LCB_ST_STREAM(o + 2, make_uint2(__float_as_uint(hit_inst != kNone ? tbest : ray_tmax), hit_slot));
+                    LCB_ST_STREAM(o + 2, make_uint2(__float_as_uint(tbest), hit_slot));  // a miss still holds the ray's tmax
                 }
                 has_ray = false;
             }

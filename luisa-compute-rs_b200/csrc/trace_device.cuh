@@ -657,7 +657,7 @@ struct WaveShared {
 
 struct WaveLane {
     RaySetup r;
-    float tmin, tbest, ray_tmax;
+    float tmin, tbest;  // tbest starts as the ray's tmax and only shrinks: it is also the upper end of the interval every triangle is tested against
     uint32_t hit_inst, hit_prim, hit_slot, cur_inst, mask;
     const WideNode *nodes;
     const PackedTri *tris;
@@ -670,7 +670,7 @@ struct WaveLane {
 __device__ __forceinline__ bool wave_begin(WaveLane &w, WaveShared &S, const AccelView &acc, const float4 ra, const float4 rb, uint32_t mask, bool any) {
     S.ray[threadIdx.x] = ra; S.ray[kWaveThreads + threadIdx.x] = rb;
     setup_world(w.r, ra, rb);
-    w.tmin = ra.w; w.tbest = rb.w; w.ray_tmax = rb.w;
+    w.tmin = ra.w; w.tbest = rb.w;
     w.hit_inst = kNone; w.hit_prim = kNone; w.hit_slot = 0u;
     w.cur_inst = kNone; w.nodes = acc.tlas_nodes; w.tris = nullptr;
     w.sp = 0; w.mask = mask; w.any = any;
@@ -719,7 +719,8 @@ __device__ __forceinline__ void wave_traverse(WaveLane &w, int &state, const Acc
                 const float4 v0 = make_float4(__uint_as_float(t01.v[0]), __uint_as_float(t01.v[1]), __uint_as_float(t01.v[2]), __uint_as_float(t01.v[3]));
                 const float4 v1 = make_float4(__uint_as_float(t01.v[4]), __uint_as_float(t01.v[5]), __uint_as_float(t01.v[6]), 0.f);
                 float t, V, W, det;
-                if (canonical_triangle(w.r, w.tmin, w.ray_tmax, v0, v1, v2, t, V, W, det)) {
+                // (tmin, tbest]: a hit beyond the best one so far would lose anyway; ties at tbest still reach the (inst, prim) rule below
+                if (canonical_triangle(w.r, w.tmin, w.tbest, v0, v1, v2, t, V, W, det)) {
                     const uint32_t prim = __float_as_uint(v0.w);
                     if (w.any) {
                         w.hit_inst = w.cur_inst; w.Gt.y = 0u; w.G.y = 0u; w.sp = 0;  // retires in the tail below

@@ -1,7 +1,8 @@
 /*
  * oracle.c — CPU restatement of the reference ray-tracing hot path.  See oracle.h for the
  * reference file:line map.  TEST INFRASTRUCTURE ONLY (checker + CPU baseline), never the
- * product path.  PARITY UNPINNED (Embree, the reference's arithmetic, is absent).
+ * product path.  PARITY UNPINNED per hit (Embree, the reference's arithmetic, is absent); pinned statistically against the reference's
+ * own cbox.png (oracle.h).
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -shared -fPIC (see oracle/Makefile).  -ffp-contract=off
  * is REQUIRED: the canonical arithmetic below is defined operation by operation.
@@ -474,9 +475,11 @@ static inline void consider(best_hit *b, float t, float u, float v, uint32_t ins
 
 /* ---- curves ------------------------------------------------------------------------------------
  * The surface is the sweep of a sphere of radius r(u) along c(u).  A segment is put into the power basis with the frontend's own
- * matrices (lc/src/rtx/curve.rs:88-139), cubic segments are cut at u = k/8 into 8 pieces, every piece is a rounded cone between
- * the spheres at its ends (linear segments are one piece).  Embree's round curves (the reference) are intersected iteratively to a
- * tolerance instead: PARITY UNPINNED.  A hit reports prim = segment, bary = (u, -1) (accel.rs:491-494), entry t. */
+ * matrices (lc/src/rtx/curve.rs:88-139).  Linear segments ARE rounded cones (exact).  Cubic segments are cut at u = k/8 into 8 pieces
+ * whose rounded cones (radii inflated by the chord-sag bound) only LOCATE a hit; refine_curve_hit() then solves for the point of the
+ * true sweep (Newton, double): t agrees with a dense float64 sweep to 1e-5 (tests/test_curves.py).  Embree's round curves (the
+ * reference) are intersected iteratively to their own tolerance: PARITY UNPINNED bit for bit, within tolerance by construction.
+ * A hit reports prim = segment, bary = (u, -1) (accel.rs:491-494), entry t. */
 #define CURVE_PIECES 8
 static inline int filter_accept(const oracle_filter *flt, uint32_t inst, uint32_t prim, float u, float v);
 static inline void lin4(const float m[4], float div, const float *q0, const float *q1, const float *q2, const float *q3, float out[4]) {
