@@ -332,6 +332,8 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
     pt = TiledPathTracer(dev, lc, scenes, spp_per_dispatch=spp_per_dispatch, rank=rank, world=world, dist=dist)
     setup_s = time.perf_counter() - t0
     pt.frame(spp_per_dispatch, first_frame=50000)                  # warm-up: kernels, NCCL communicator, allocator
+    if world > 1:
+        pt.probe_cost()
     history = pt.balance(balance_passes) if world > 1 else []
     ms, gathered, n_dispatch = pt.frame(spp, first_frame=0)
     times = pt.all_times(ms)
@@ -353,7 +355,7 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
                "partition": "contiguous ranges of the Morton-ordered 64x64 tiles, cut to equal measured cost" if world > 1 else "all tiles on one GPU",
                "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes": [{"imbalance": round(h[0], 3), "tiles_per_rank": h[1], "ms_per_rank": h[2]} for h in history],
                "one_pass_ms_per_rank": [round(t, 3) for t in render_only], "imbalance_max_over_mean": round(imbalance, 4),
-               "limiter": ("load imbalance between ranks" if imbalance > 1.05 else "per-rank efficiency: 1/N of the image is few work items per SM (dispatch tails) and reuses less of the 430 MB BLAS in L2"),
+               "limiter": ("load imbalance between ranks" if imbalance > 1.08 else "per-rank efficiency: the ranks that own the expensive tiles own few of them (70-160 tiles = 3-6 waves of resident threads per dispatch), so dispatch tails weigh more than on one GPU"),
                "gather_bytes": int(gathered.numel() * 4) if world > 1 else 0, "blas_build_ms": round(pt.blas_ms, 3), "tlas_build_ms": round(pt.tlas_ms, 3),
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img), "setup_s": round(setup_s, 1)}
     pt.destroy()
@@ -371,7 +373,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: only the headline steps")
     ap.add_argument("--c5-spp", type=int, default=1024, help="samples per pixel of the C5 leg (BASELINE: 1024); 0 skips the leg")
-    ap.add_argument("--c5-spp-per-dispatch", type=int, default=16)
+    ap.add_argument("--c5-spp-per-dispatch", type=int, default=32, help="the example's own SPP_PER_DISPATCH (path_tracer.rs:179)")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 21, help="rays per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -506,7 +508,7 @@ def main():
 
     # ---- config C5 on all ranks, before the legs only rank 0 runs (they would leave its GPU warmer than the others) ----
     if not args.profile and args.c5_spp > 0:
-        c5 = c5_leg(dev, lc, scenes, torch, dist if world > 1 else None, rank, world, args.c5_spp, args.c5_spp_per_dispatch, 4)
+        c5 = c5_leg(dev, lc, scenes, torch, dist if world > 1 else None, rank, world, args.c5_spp, args.c5_spp_per_dispatch, 6)
         if rank == 0:
             out["c5_path_trace"] = c5
 

@@ -21,7 +21,7 @@ from . import sharding
 
 
 class TiledPathTracer:
-    def __init__(self, dev, lc, scenes, width=3840, height=2160, nx=1582, spp_per_dispatch=16, depth=5, block=8, streams=2, rank=0, world=1, dist=None, fast_math=True):
+    def __init__(self, dev, lc, scenes, width=3840, height=2160, nx=1582, spp_per_dispatch=32, depth=5, block=8, streams=2, rank=0, world=1, dist=None, fast_math=True):
         import torch
         from . import examples_ir
         self.torch, self.dist, self.dev, self.lc = torch, dist, dev, lc
@@ -124,9 +124,42 @@ class TiledPathTracer:
         self.dist.all_gather_into_tensor(out, t)
         return [float(x) for x in out.tolist()]
 
-    def balance(self, passes=4, dispatches=4, frame0=100000):
+    def probe_cost(self, pieces_per_rank=8, frame0=90000):
+        """first estimate of the cost map: the Morton curve is cut into world * pieces_per_rank equal pieces dealt round-robin, every
+        rank times each of its pieces on its own (one small dispatch each, samples discarded) and the piece costs are exchanged — a
+        piecewise-constant map with world * pieces_per_rank steps, which already sees that sky tiles cost a fifth of terrain tiles"""
+        torch = self.torch
+        n_pieces = self.world * pieces_per_rank
+        edges = np.linspace(0, self.n_tiles, n_pieces + 1).astype(np.int64)
+        saved = (self.bounds, self.b0, self.b1)
+        mine = []
+        for j in range(pieces_per_rank):
+            piece = j * self.world + self.rank
+            self.b0, self.b1 = int(edges[piece]), int(edges[piece + 1])
+            cap_needed = (self.b1 - self.b0) * self.tile * self.tile
+            if self.out_t.shape[0] < cap_needed:
+                self.bounds, self.b0, self.b1 = saved
+                return False   # tile buffer too small for a probe piece (cannot happen with equal initial ranges)
+            mine.append(self.timed(lambda: self.render(1, frame0 + j)) if self.b1 > self.b0 else 0.0)
+        self.bounds, self.b0, self.b1 = saved
+        t = torch.tensor(mine, device="cuda", dtype=torch.float32)
+        if self.world > 1:
+            allt = torch.empty(self.world * pieces_per_rank, device="cuda", dtype=torch.float32)
+            self.dist.all_gather_into_tensor(allt, t)
+            allt = allt.view(self.world, pieces_per_rank).cpu().numpy()
+        else:
+            allt = t.view(1, -1).cpu().numpy()
+        for piece in range(n_pieces):
+            r, j = piece % self.world, piece // self.world
+            b0, b1 = int(edges[piece]), int(edges[piece + 1])
+            if b1 > b0:
+                self.cost[b0:b1] = max(float(allt[r, j]), 1e-6) / (b1 - b0)
+        self.set_bounds(sharding.balanced_bounds(self.cost, self.world))
+        return True
+
+    def balance(self, passes=4, dispatches=2, frame0=100000):
         """refine the cost map from per-rank times of short passes (`dispatches` dispatches each, samples discarded) and re-cut the
-        ranges; returns the history [(imbalance = max / mean of the per-rank times, tiles per rank)]"""
+        ranges; returns the history [(imbalance = max / mean of the per-rank times, tiles per rank, ms per rank)]"""
         history = []
         for p in range(passes):
             ms = self.timed(lambda: self.render(dispatches, frame0 + p * dispatches))

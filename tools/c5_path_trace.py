@@ -20,15 +20,15 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--spp", type=int, default=64, help="total samples per pixel (BASELINE: 1024)")
-    ap.add_argument("--spp-per-dispatch", type=int, default=16)
+    ap.add_argument("--spp-per-dispatch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=5)
     ap.add_argument("--nx", type=int, default=1582, help="terrain vertices per side (1582 -> 5.0M triangles per mesh, 50M instanced)")
     ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
     ap.add_argument("--streams", type=int, default=2)
-    ap.add_argument("--balance-passes", type=int, default=4, help="0: equal tile counts per rank")
+    ap.add_argument("--balance-passes", type=int, default=6, help="0: equal tile counts per rank")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's equal-count range in this single process (tuning aid)")
     ap.add_argument("--precise", action="store_true", help="compile the kernel without enable_fast_math (the frontend default is on)")
-    ap.add_argument("--lowering", default="auto", choices=["auto", "direct"])
+    ap.add_argument("--lowering", default="auto", choices=["auto", "direct", "wavefront"])
     ap.add_argument("--save", default="")
     a = ap.parse_args()
     import torch
@@ -44,7 +44,7 @@ def main():
     from luisa_compute_rs_b200 import sharding
     from luisa_compute_rs_b200.tiled_render import TiledPathTracer
     dev = lc.Context().create_device("b200")
-    lc._abi.load_library().lc_b200_set_lowering(1 if a.lowering == "direct" else 0)
+    lc._abi.load_library().lc_b200_set_lowering({"auto": 0, "direct": 1, "wavefront": 2}[a.lowering])
     erank, eworld = (int(v) for v in a.emulate.split("/")) if a.emulate else (rank, world)
     pt = TiledPathTracer(dev, lc, scenes, a.width, a.height, a.nx, a.spp_per_dispatch, a.depth, a.block, a.streams, erank, eworld, dist if world > 1 else None, fast_math=not a.precise)
     if a.emulate:
@@ -55,6 +55,8 @@ def main():
         dev.close()
         return
     pt.frame(a.spp_per_dispatch, 50000)
+    if world > 1 and a.balance_passes:
+        pt.probe_cost()
     history = pt.balance(a.balance_passes) if world > 1 and a.balance_passes else []
     ms, gathered, n_dispatch = pt.frame(a.spp, 0)
     times = pt.all_times(ms)
