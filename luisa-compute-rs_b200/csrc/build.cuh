@@ -10,8 +10,8 @@ struct LaunchCounter { unsigned long long count = 0; };
 
 // ---- radix_sort.cu -------------------------------------------------------------------------
 size_t sort_scratch_bytes(uint32_t n, int passes);
-bool sort_pairs(cudaStream_t s, uint32_t n, uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, void *scratch,
-                int begin_bit, int passes, LaunchCounter &lc);
+bool sort_pairs(cudaStream_t s, uint32_t n, void *keys, uint32_t *vals, void *keys_alt, uint32_t *vals_alt, void *scratch,
+                int begin_bit, int passes, int key_bytes /* 4: uint32_t keys, 8: uint64_t */, LaunchCounter &lc);
 
 // ---- bvh_build.cu --------------------------------------------------------------------------
 struct TriangleInput {

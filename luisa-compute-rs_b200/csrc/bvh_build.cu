@@ -15,6 +15,7 @@ namespace lcb {
 namespace {
 
 constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr unsigned long long kQueueRoot = 1ull << 32;  // collapse work item of the root: (wide depth + 1) << 32 | binary root (written by whoever forms the root)
 #ifndef LCB_LEAF_MAX
 #define LCB_LEAF_MAX 2
 #endif
@@ -23,15 +24,17 @@ constexpr int kLeafMax = LCB_LEAF_MAX;  // primitives per leaf child (unary coun
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
 
-__global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags) {
+__global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags, unsigned long long *queue) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
-        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->bar_count = 0; h->bar_release = 0; h->max_depth = 0; h->error = 0;
+        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->tickets = 0; h->processed = 0; h->max_depth = 0; h->error = 0;
         h->prim_area_sum = 0.f; h->pad2 = 0.f;
     }
-    if (i < 48) h->level_end[i] = 0;  // the host reads the header back whole (builder choice, compaction)
-    for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) flags[j] = -1;
+    if (i < 24) h->pad_line[i] = 0;  // the host reads the header back whole
+    if (i < 23) h->reserved[i] = 0;
+    if (i == 0) h->collapse_done = 0;
+    for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) { flags[j] = -1; queue[j] = 0ull; }  // collapse work items: 0 = not published yet
 }
 
 // block-reduce the centroid (shuffles, then one shared-memory round) and fold it into the header's ordered-int
@@ -129,10 +132,10 @@ __global__ void __launch_bounds__(256) k_aabb_boxes(const uint8_t *__restrict__ 
 }
 
 // leaf records of a procedural BLAS: the primitive's box and id in the PackedTri slot the collapse assigned
-__global__ void __launch_bounds__(256) k_pack_aabbs(const uint8_t *__restrict__ aabbs, PackedTri *tris, uint32_t n) {
+__global__ void __launch_bounds__(256) k_pack_aabbs(const uint8_t *__restrict__ aabbs, const uint32_t *__restrict__ slot_prim, PackedTri *tris, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t prim = tris[i].prim;
+    const uint32_t prim = slot_prim[i];
     const float *a = reinterpret_cast<const float *>(aabbs + (size_t)prim * 24);
     float4 *o = reinterpret_cast<float4 *>(&tris[i]);
     o[0] = make_float4(fminf(a[0], a[3]), fminf(a[1], a[4]), fminf(a[2], a[5]), __uint_as_float(prim));
@@ -170,10 +173,10 @@ __global__ void __launch_bounds__(256) k_curve_boxes(CurveInput in, uint32_t n, 
 }
 
 // leaf records of a curve BLAS: the piece's two spheres, its segment and its parameter range (CurveSeg)
-__global__ void __launch_bounds__(256) k_pack_curves(CurveInput in, PackedTri *slots, uint32_t n) {
+__global__ void __launch_bounds__(256) k_pack_curves(CurveInput in, const uint32_t *__restrict__ slot_prim, PackedTri *slots, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t j = slots[i].prim, seg = j / in.pieces, k = j % in.pieces;
+    const uint32_t j = slot_prim[i], seg = j / in.pieces, k = j % in.pieces;
     float4 A, B;
     curve_piece(in.cps, in.cp_stride, in.segs, in.basis, seg, k, A, B);
     const float du = 1.0f / (float)in.pieces;
@@ -237,6 +240,10 @@ __global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, 
     reduce_centroid_bounds(cen, valid, h);
 }
 
+// orders this thread's earlier stores before its next atomic at GPU scope; what __threadfence() gives beyond that (sequential
+// consistency: MEMBAR.SC) is not needed by the arrival protocols here, whose readers go to L2 (__ldcg)
+__device__ __forceinline__ void release_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t expand21(uint32_t x) {
     uint64_t v = x & 0x1fffffull;
     v = (v | v << 32) & 0x1f00000000ffffull;
@@ -247,8 +254,9 @@ __device__ __forceinline__ uint64_t expand21(uint32_t x) {
     return v;
 }
 
+template <typename K>
 __global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxes, uint32_t n, const BuildHeader *__restrict__ h,
-                                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int drop_bits) {
+                                                K *__restrict__ keys, uint32_t *__restrict__ vals, int drop_bits) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 lo = reinterpret_cast<const float4 *>(boxes)[2 * (size_t)i];
@@ -264,14 +272,15 @@ __global__ void __launch_bounds__(256) k_morton(const PrimBox *__restrict__ boxe
         q[k] = min((uint32_t)(t * 2097152.0f), 2097151u);
     }
     // the top 8 * passes bits of the 63-bit code, one 8-bit sort pass each; equal keys are split by position
-    keys[i] = (expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2)) >> drop_bits;
+    keys[i] = (K)((expand21(q[0]) | (expand21(q[1]) << 1) | (expand21(q[2]) << 2)) >> drop_bits);
     vals[i] = i;
 }
 
 // ---- fused hierarchy + refit ---------------------------------------------------------------
 // Internal node i separates sorted leaves i and i+1.  delta(i) orders the splits: the XOR of
 // adjacent keys, with runs of equal keys split by position bits.
-__device__ __forceinline__ uint64_t split_delta(const uint64_t *__restrict__ keys, uint32_t i) {
+template <typename K>
+__device__ __forceinline__ uint64_t split_delta(const K *__restrict__ keys, uint32_t i) {
     uint64_t x = keys[i] ^ keys[i + 1];
     return x ? (x | (1ull << 63)) : (uint64_t)(i ^ (i + 1));
 }
@@ -282,8 +291,9 @@ __device__ __forceinline__ uint64_t split_delta(const uint64_t *__restrict__ key
 // warp's span leaves for phase 2.  31 of 32 internal nodes are emitted here without atomics, fences or L2 round trips.
 // (2) Global: the classic bottom-up climb with one atomic exchange per arrival (Apetrei 2014): the first child to arrive at an
 // internal node leaves its box there and stops, the second merges and continues.
-__global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ prim, const PrimBox *__restrict__ boxes,
-                                                   uint32_t n, BinNode *bin, int *flags, BuildHeader *h) {
+template <typename K>
+__global__ void __launch_bounds__(128) k_hierarchy(const K *__restrict__ keys, const uint32_t *__restrict__ prim, const PrimBox *__restrict__ boxes,
+                                                   uint32_t n, BinNode *bin, int *flags, BuildHeader *h, unsigned long long *queue) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp_base = i - lane;
     if (warp_base >= n) return;  // whole warp out of range
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
     uint32_t left = i, right = i, cur = i | kLeafBit;
     if (n == 1) {
         if (i == 0) {
-            h->root = cur;
+            h->root = cur; queue[0] = kQueueRoot | cur;
             h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
             h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
         }
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
             hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
             right = s_right; cur = parent;
             if (left == 0 && right == n - 1) {
-                h->root = parent;
+                h->root = parent; queue[0] = kQueueRoot | parent;
                 h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
                 h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
                 local = false; done = true;
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
             float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
             pn[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
             pn[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
-            __threadfence();
+            release_fence();
             int other = atomicExch(&flags[parent], (int)left);
             if (other == -1) return;
             right = (uint32_t)other;  // the sibling fenced before its exchange; its box is read at L2 (__ldcg) below
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
             float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
             pn[2] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
             pn[3] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
-            __threadfence();
+            release_fence();
             int other = atomicExch(&flags[parent], (int)right);
             if (other == -1) return;
             left = (uint32_t)other;
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(128) k_hierarchy(const uint64_t *__restrict__ 
         hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
         cur = parent;
         if (left == 0 && right == n - 1) {
-            h->root = parent;
+            h->root = parent; queue[0] = kQueueRoot | parent;
             h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
             h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
             return;
@@ -558,10 +568,10 @@ __global__ void __launch_bounds__(kPlocTile) k_ploc_compact(const float4 *__rest
     }
 }
 
-__global__ void k_ploc_finish(const float4 *clusters, const PlocState *st, BuildHeader *h) {
+__global__ void k_ploc_finish(const float4 *clusters, const PlocState *st, BuildHeader *h, unsigned long long *queue) {
     if (st->n_clusters != 1) { h->error = 3u; return; }
     const float4 lo = clusters[0], hi = clusters[1];
-    h->root = __float_as_uint(lo.w);
+    h->root = __float_as_uint(lo.w); queue[0] = kQueueRoot | __float_as_uint(lo.w);
     h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
     h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
 }
@@ -591,8 +601,8 @@ __device__ __forceinline__ void split_child(const BinNode *__restrict__ bin, con
 // all slots at once (one thread per slot: the index -> vertex gather is a chain of dependent DRAM reads that must not
 // sit on the collapse's per-node critical path).
 struct LeafSinkTriangles {
-    PackedTri *tris;
-    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const { tris[dst].prim = prim; }
+    uint32_t *slot_prim;  // compact (4 bytes per slot, not one word of every 64-byte record: that is a sector read-modify-write per slot)
+    __device__ __forceinline__ void emit(uint32_t dst, uint32_t prim) const { slot_prim[dst] = prim; }
 };
 struct LeafSinkInstances {
     const uint32_t *active; uint32_t *prim_ids;
@@ -610,45 +620,91 @@ __device__ __forceinline__ void quantise_axis(float clo, float chi, float org, f
 
 // One 8-lane group per wide node, lane j holding child j in registers: the split search, the node frame, the greedy
 // octant slot assignment and the quantisation are 3-step shuffle reductions inside the group instead of serial loops
-// over local-memory arrays; the finished node is assembled in shared memory and leaves as one coalesced 128-byte
-// store.  The kernel is launched cooperatively (all CTAs co-resident) and walks the wide tree level by level: the
-// nodes of a level are a contiguous id range handed out CTA-strided, children and leaf slots are allocated with ONE
-// 64-bit atomic per CTA and step (same-address atomics serialise at L2: one per node was the bottleneck), and a grid
-// barrier whose last arriver snapshots node_count separates the levels — no polling.
-constexpr int kCollapseThreads = 256;
+// over local-memory arrays; the finished node is assembled in shared memory and leaves as coalesced 16-byte stores.
+//
+// Barrier-free work queue (round 1 walked the wide tree level by level with a grid barrier per level).  queue[t] is the
+// work item of wide node t: (wide depth + 1) << 32 | binary subtree root — zero until the parent has written it.  Warps are
+// autonomous, four groups each: a group takes node ids as TICKETS and polls its entry; a parent allocates its internal
+// children as a contiguous id range and writes their entries (two atomics per warp and step: nodes + leaf slots in one
+// 64-bit word, tickets).  Tickets are only held by running groups and a node's parent always has a smaller ticket, so the
+// queue drains without co-residency requirements.  The walk is over when every primitive has a leaf slot: the allocation
+// that places the last one publishes the final node count in `collapse_done` (its own cache line: thousands of idle warps
+// poll it, and must not queue up in front of the allocation atomics).
+//
+// What a wide node costs is a chain of dependent loads from a 64 MB array in DRAM, so the chain is kept short:
+//  * every lane PRELOADS the binary node of the child it holds: the opened child's two children arrive by shuffles and only
+//    the two lanes that received them issue new loads — the chain is the depth of the opening tree (3-4), not six opens;
+//  * SMALL SUBTREES IN ONE ROUND TRIP: in the LBVH numbering an internal node's id is the position of its split, so the
+//    subtree over sorted leaves [l, r] owns exactly the ids l .. r-1.  A root with <= 16 leaves (every bottom node, 4 of 5
+//    nodes) fetches all of them, and its primitive ids, with independent loads into shared memory / registers and opens
+//    from there; PLOC numbers nodes in merge order and takes the general path;
+//  * a parent prefetches into L2 what each internal child will touch first (its subtree block, or its children's nodes).
+#ifndef LCB_COLLAPSE_THREADS
+#define LCB_COLLAPSE_THREADS 128
+#endif
+constexpr int kCollapseThreads = LCB_COLLAPSE_THREADS;
 constexpr int kCollapseGroups = kCollapseThreads / 8;
+constexpr uint32_t kSmallSubtree = 16;  // leaves; 15 binary nodes = 960 bytes of shared memory per group
+static_assert(kLeafMax <= 2, "k_collapse reads the primitives of a leaf child from the child's preloaded binary node");
+
+// reductions over the 8-lane group of a lane: xor butterflies on the FULL warp mask (the four groups of a warp run in lockstep — a
+// redux.sync or shfl.sync on a partial, lane-dependent mask compiles to a MATCH.ANY loop over the distinct masks, ~50 instructions each)
+#define GSHFL(V, SRC) __shfl_sync(0xffffffffu, V, SRC, 8)
+#define GXOR(V, M) __shfl_xor_sync(0xffffffffu, V, M, 8)
+__device__ __forceinline__ uint32_t group_max(uint32_t v) { v = max(v, GXOR(v, 1)); v = max(v, GXOR(v, 2)); return max(v, GXOR(v, 4)); }
+__device__ __forceinline__ uint32_t group_min(uint32_t v) { v = min(v, GXOR(v, 1)); v = min(v, GXOR(v, 2)); return min(v, GXOR(v, 4)); }
+__device__ __forceinline__ int group_min(int v) { v = min(v, GXOR(v, 1)); v = min(v, GXOR(v, 2)); return min(v, GXOR(v, 4)); }
+__device__ __forceinline__ int group_max(int v) { v = max(v, GXOR(v, 1)); v = max(v, GXOR(v, 2)); return max(v, GXOR(v, 4)); }
+__device__ __forceinline__ uint32_t group_or(uint32_t v) { v |= GXOR(v, 1); v |= GXOR(v, 2); return v | GXOR(v, 4); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 #ifndef LCB_COLLAPSE_MIN_BLOCKS
-#define LCB_COLLAPSE_MIN_BLOCKS 5
+#define LCB_COLLAPSE_MIN_BLOCKS (1024 / LCB_COLLAPSE_THREADS)
 #endif
-template <class Sink>
+template <class Sink, bool kContiguous>
 __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_collapse(const BinNode *__restrict__ bin, const uint32_t *__restrict__ prim_sorted, uint32_t n, BuildHeader *h,
                                                                unsigned long long *queue, WideNode *nodes, uint32_t capacity, Sink sink) {
     __shared__ WideNode s_node[kCollapseGroups];
-    __shared__ uint32_t s_int[kCollapseGroups], s_prm[kCollapseGroups];
-    __shared__ unsigned long long s_base;
-    const uint32_t lane = threadIdx.x & 31, sub = lane & 7u, grp = threadIdx.x >> 3;
+    __shared__ float4 s_bin[kContiguous ? kCollapseGroups : 1][(kSmallSubtree - 1) * 4];
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7u, grp = threadIdx.x >> 3, wgrp = lane >> 3;
     const uint32_t gmask = 0xffu << (lane & 24u);
-    const uint32_t below = gmask & ((1u << lane) - 1u);  // lanes of this group below me
     WideNode &out = s_node[grp];
-#define GSHFL(V, SRC) __shfl_sync(gmask, V, SRC, 8)
-#define GXOR(V, M) __shfl_xor_sync(gmask, V, M, 8)
-    uint32_t level_begin = 0, level_end = 1;
-    for (uint32_t depth = 0; level_begin < level_end; depth++) {
-      const uint32_t level_n = level_end - level_begin;
-      for (uint32_t base = blockIdx.x * kCollapseGroups; base < level_n; base += gridDim.x * kCollapseGroups) {
-        const bool active = base + grp < level_n;
-        const uint32_t t = level_begin + base + grp;
+    float4 *blk = s_bin[kContiguous ? grp : 0];
+    // warps are autonomous (no CTA barrier anywhere): four groups, four tickets
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&h->tickets, 4u);
+    t = __shfl_sync(0xffffffffu, t, 0) + wgrp;  // my ticket = the wide node this group emits next
+    bool exhausted = false;                     // no node will ever appear at my ticket
+    uint32_t my_depth = 0, my_emitted = 0, idle_streak = 0;
+    for (;;) {
+        // ================= take the work item, if its parent has published it =================
+        unsigned long long item = 0ull;
+        if (!exhausted && sub == 0 && t < n) item = __ldcg(queue + t);  // the queue holds n entries; a tree over n primitives has fewer wide nodes
+        item = GSHFL(item, 0);
+        const bool active = item != 0ull;
+        const uint32_t bnode = (uint32_t)item, depth = (uint32_t)(item >> 32) - 1u;
+        if (!__any_sync(0xffffffffu, active)) {
+            // nothing published for this warp: is the walk over?  collapse_done = final node count + 1 (1 after an error: everybody leaves)
+            uint32_t done = 0u;
+            if (lane == 0) done = *reinterpret_cast<volatile uint32_t *>(&h->collapse_done);
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done != 0u && t >= done - 1u) exhausted = true;
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            __nanosleep(128u << min(idle_streak, 3u));
+            idle_streak++;
+            continue;
+        }
+        idle_streak = 0;
         // ================= phase A: choose the (up to) 8 children and their slots =================
-        Child c;  // after phase A: the child of slot `sub`
-        for (int k = 0; k < 3; k++) { c.lo[k] = FLT_MAX; c.hi[k] = -FLT_MAX; }
-        c.id = 0; c.count = 0;
-        bool occupied = false;
-        float nlo[3] = {0.f, 0.f, 0.f}; uint32_t ex[3] = {1u, 1u, 1u}; float inv_scale[3] = {0.f, 0.f, 0.f};
+        Child mine;  // the child this lane holds (children are NOT brought into slot order: the lane writes to its slot's place)
+        for (int k = 0; k < 3; k++) { mine.lo[k] = FLT_MAX; mine.hi[k] = -FLT_MAX; }
+        mine.id = 0; mine.count = 0;
+        uint32_t nc = 0;
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa, pd = pa;  // preloaded binary node of `mine`
+        bool small = false;              // the whole subtree sits in `blk` (uniform over the group)
+        uint32_t first = 0;              // small: first sorted leaf = first binary node id of the subtree
+        uint32_t prims_lo = 0, prims_hi = 0;  // small: primitive ids of sorted leaves first + sub, first + 8 + sub
         if (active) {
-            const uint32_t bnode = (uint32_t)__ldcg(queue + t);  // written by another CTA in the previous level: read at L2
-            Child mine = c;
-            uint32_t nc;
             if (bnode & kLeafBit) {  // single-primitive tree
                 nc = 1;
                 if (sub == 0) {
@@ -660,174 +716,205 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
                 split_child(bin, self, l, r);
                 nc = 2;
                 if (sub == 0) mine = l; else if (sub == 1) mine = r;
-            }
-            // phase 0: open the largest subtree that cannot be a leaf; phase 1: use spare slots to split multi-primitive
-            // leaves (tighter boxes at no traversal cost: all 8 slots are tested anyway)
-            for (int phase = 0; phase < 2; phase++) {
-                const uint32_t limit = phase == 0 ? (uint32_t)kLeafMax : 1u;
-                while (nc < 8) {
-                    // argmax of the half-area over the group in ONE redux: non-negative floats order like their bit patterns; the low
-                    // three mantissa bits carry 7 - lane (ties and near-ties go to the lowest lane)
-                    const float a = (sub < nc && mine.count > limit) ? half_area(mine) : -1.f;
-                    const uint32_t akey = a >= 0.f ? (((__float_as_uint(a) & ~7u) + 8u) | (7u - sub)) : 0u;
-                    const uint32_t abest = __reduce_max_sync(gmask, akey);
-                    if (abest == 0u) break;
-                    const uint32_t who = 7u - (abest & 7u);
-                    Child p, l, r;
-                    p.id = GSHFL(mine.id, who);
-                    split_child(bin, p, l, r);
-                    if (sub == who) mine = l; else if (sub == nc) mine = r;
-                    nc++;
+                const uint32_t total = l.count + r.count;
+                if (kContiguous && total <= kSmallSubtree) {
+                    small = true;
+                    first = bnode + 1u - l.count;
+                    const float4 *srcq = reinterpret_cast<const float4 *>(&bin[first]);
+                    const uint32_t quads = (total - 1u) * 4u;
+#pragma unroll
+                    for (uint32_t q = 0; q < (kSmallSubtree - 1) * 4 / 8 + 1; q++) { const uint32_t qi = q * 8u + sub; if (qi < quads) blk[qi] = srcq[qi]; }
+                    if (sub < total) prims_lo = prim_sorted[first + sub];
+                    if (8u + sub < total) prims_hi = prim_sorted[first + 8u + sub];
                 }
             }
-            const bool valid = sub < nc;
-            // ---- node frame ----
-            float nhi[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                // group min / max through the order-preserving integer image of the floats (one redux each); invalid lanes hold
-                // (+max, -max), NaN is treated the same way (fminf / fmaxf would skip it too)
-                const float vlo = mine.lo[k] == mine.lo[k] ? mine.lo[k] : FLT_MAX, vhi = mine.hi[k] == mine.hi[k] ? mine.hi[k] : -FLT_MAX;
-                nlo[k] = ordered_to_float(__reduce_min_sync(gmask, float_to_ordered(vlo)));
-                nhi[k] = ordered_to_float(__reduce_max_sync(gmask, float_to_ordered(vhi)));
-                const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
-                const uint32_t bits = __float_as_uint(sc);
-                uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
-                e = max(e, 1u); e = min(e, 253u);
-                ex[k] = e;
-                inv_scale[k] = __uint_as_float((254u - e) << 23);
+        }
+        __syncwarp();  // blk is read by other lanes of the group
+        auto fetch = [&](uint32_t id) {
+            const float4 *pn = (kContiguous && small) ? blk + (size_t)(id - first) * 4 : reinterpret_cast<const float4 *>(&bin[id]);
+            pa = pn[0]; pb = pn[1]; pc = pn[2]; pd = pn[3];
+        };
+        if (active && sub < nc && !(mine.id & kLeafBit)) fetch(mine.id);
+        // Open the largest subtree that cannot be a leaf until there are 8 children; then use spare slots to split two-primitive
+        // leaves (tighter boxes at no traversal cost: all 8 slots are tested anyway).  One loop: bit 31 of the key ranks the first
+        // kind above the second.  argmax of the half-area: non-negative floats order like their bit patterns; the low three
+        // mantissa bits carry 7 - lane (ties and near-ties go to the lowest lane).
+        for (;;) {
+            uint32_t akey = 0u;
+            if (sub < nc && mine.count > 1u) {
+                const float a = half_area(mine);
+                if (a >= 0.f) akey = (((__float_as_uint(a) & 0x7ffffff8u) + 8u) | (7u - sub)) | (mine.count > (uint32_t)kLeafMax ? 0x80000000u : 0u);  // a NaN box is never opened
             }
-            // ---- octant slot assignment: slot s is visited first by rays whose direction signs are s (bit k set =
-            // negative along axis k); greedy global minimum of dot(child centre - node centre, sign_s), ties -> lowest
-            // child, then lowest slot ----
-            const float cx = 0.5f * (mine.lo[0] + mine.hi[0]) - 0.5f * (nlo[0] + nhi[0]);
-            const float cy = 0.5f * (mine.lo[1] + mine.hi[1]) - 0.5f * (nlo[1] + nhi[1]);
-            const float cz = 0.5f * (mine.lo[2] + mine.hi[2]) - 0.5f * (nlo[2] + nhi[2]);
-            uint32_t slot_used = 0, my_slot = 8;
-            for (uint32_t it = 0; it < nc; it++) {
-                float best = FLT_MAX; uint32_t bs = 8;
-                if (valid && my_slot == 8) {
-#pragma unroll
-                    for (uint32_t sl = 0; sl < 8; sl++) {
-                        if (slot_used >> sl & 1u) continue;
-                        const float cost = ((sl & 1) ? -cx : cx) + ((sl & 2) ? -cy : cy) + ((sl & 4) ? -cz : cz);
-                        if (cost < best) { best = cost; bs = sl; }
-                    }
-                }
-                // group argmin in ONE redux: order-preserving image of the cost with its low six bits replaced by (child, slot)
-                const uint32_t cbits = __float_as_uint(best);
-                const uint32_t cord = cbits ^ ((cbits >> 31) ? 0xffffffffu : 0x80000000u);
-                const uint32_t ckey = (valid && my_slot == 8 && bs != 8) ? ((cord & ~63u) | (sub << 3) | bs) : 0xffffffffu;
-                const uint32_t cbest = __reduce_min_sync(gmask, ckey);
-                uint32_t who = cbest == 0xffffffffu ? 8u : ((cbest >> 3) & 7u);
-                if (who != 8u) bs = cbest & 7u;
-                if (who == 8u) {  // only NaN costs left: lowest unassigned child takes the lowest free slot
-                    who = __ffs(__ballot_sync(gmask, valid && my_slot == 8) >> (lane & 24u)) - 1;
-                    bs = __ffs(~slot_used & 0xffu) - 1;
-                }
-                if (sub == who) my_slot = bs;
-                slot_used |= 1u << bs;
+            const uint32_t abest = group_max(akey);
+            const bool open = nc < 8u && abest != 0u;  // uniform over the group (nc = 0 in a group without work)
+            if (!__any_sync(0xffffffffu, open)) break;
+            const uint32_t who = 7u - (abest & 7u);
+            // the opened child's left child stays in lane `who` (own registers), its right child goes to lane nc
+            const float4 qc = make_float4(GSHFL(pc.x, who), GSHFL(pc.y, who), GSHFL(pc.z, who), GSHFL(pc.w, who));
+            const float4 qd = make_float4(GSHFL(pd.x, who), GSHFL(pd.y, who), GSHFL(pd.z, who), GSHFL(pd.w, who));
+            if (open) {
+                const bool take_l = sub == who, take_r = sub == nc;
+                if (take_l) { mine.lo[0] = pa.x; mine.lo[1] = pa.y; mine.lo[2] = pa.z; mine.id = __float_as_uint(pa.w); mine.hi[0] = pb.x; mine.hi[1] = pb.y; mine.hi[2] = pb.z; mine.count = __float_as_uint(pb.w); }
+                if (take_r) { mine.lo[0] = qc.x; mine.lo[1] = qc.y; mine.lo[2] = qc.z; mine.id = __float_as_uint(qc.w); mine.hi[0] = qd.x; mine.hi[1] = qd.y; mine.hi[2] = qd.z; mine.count = __float_as_uint(qd.w); }
+                if ((take_l || take_r) && !(mine.id & kLeafBit)) fetch(mine.id);
+                nc++;
             }
-            // ---- bring the children into slot order: lane s now holds the child of slot s ----
-            uint32_t src = 8;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) { const uint32_t sj = GSHFL(my_slot, j); if (sj == sub) src = j; }
-            const uint32_t from = src & 7u;
-#pragma unroll
-            for (int k = 0; k < 3; k++) { c.lo[k] = GSHFL(mine.lo[k], from); c.hi[k] = GSHFL(mine.hi[k], from); }
-            c.id = GSHFL(mine.id, from); c.count = GSHFL(mine.count, from);
-            occupied = src != 8;
         }
-        const bool is_int = occupied && c.count > (uint32_t)kLeafMax;
-        const bool is_leaf = occupied && !is_int;
-        const uint32_t int_ballot = __ballot_sync(gmask, is_int);
-        const uint32_t n_internal = __popc(int_ballot), int_rank = __popc(int_ballot & below);
-        uint32_t leaf_count = is_leaf ? c.count : 0u, prim_off = leaf_count;
-#pragma unroll
-        for (int m = 1; m < 8; m <<= 1) { const uint32_t o = __shfl_up_sync(gmask, prim_off, m, 8); if (sub >= (uint32_t)m) prim_off += o; }
-        const uint32_t n_prims = GSHFL(prim_off, 7);
-        prim_off -= leaf_count;  // exclusive
-        // ================= allocation: one 64-bit atomic per CTA and step =================
-        if (sub == 0) { s_int[grp] = n_internal; s_prm[grp] = n_prims; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t ti = 0, tp = 0;
-            for (int g = 0; g < kCollapseGroups; g++) { const uint32_t a = s_int[g], b = s_prm[g]; s_int[g] = ti; s_prm[g] = tp; ti += a; tp += b; }
-            s_base = (ti | tp) ? atomicAdd(reinterpret_cast<unsigned long long *>(&h->node_count), (unsigned long long)ti | ((unsigned long long)tp << 32)) : 0ull;
+        const bool valid = sub < nc;
+        const bool is_int = valid && mine.count > (uint32_t)kLeafMax, is_leaf = valid && !is_int;
+        // the primitives of a leaf child (a two-primitive child is a binary node over two leaves: preloaded)
+        uint32_t pos_a = 0, pos_b = 0, prim_a = 0, prim_b = 0;
+        if (is_leaf) {
+            if (mine.id & kLeafBit) pos_a = mine.id & ~kLeafBit;
+            else { pos_a = __float_as_uint(pa.w) & ~kLeafBit; pos_b = __float_as_uint(pc.w) & ~kLeafBit; }
         }
-        __syncthreads();
-        const uint32_t child_base = (uint32_t)s_base + s_int[grp], prim_base = (uint32_t)(s_base >> 32) + s_prm[grp];
-        __syncthreads();  // s_int / s_prm / s_base are rewritten by the next step
-        if (!active) continue;
-        if (child_base + n_internal > capacity || depth + 1 > (uint32_t)kMaxWideDepth) {
-            if (sub == 0) atomicExch(&h->error, child_base + n_internal > capacity ? 2u : 1u);
-            continue;  // every CTA still has to reach the barrier; the level loop ends on the error flag
+        if (kContiguous && __any_sync(0xffffffffu, small)) {  // small subtrees: the ids are in the group's registers
+            const uint32_t ia = (pos_a - first) & 15u, ib = (pos_b - first) & 15u;
+            const uint32_t a_lo = GSHFL(prims_lo, ia & 7u), a_hi = GSHFL(prims_hi, ia & 7u), b_lo = GSHFL(prims_lo, ib & 7u), b_hi = GSHFL(prims_hi, ib & 7u);
+            if (small) { prim_a = (ia & 8u) ? a_hi : a_lo; prim_b = (ib & 8u) ? b_hi : b_lo; }
         }
-        // ================= phase B: assemble the node in shared memory, store it as one 128-byte line =================
-        if (sub == 0) {
-            for (int k = 0; k < 3; k++) { out.org[k] = nlo[k]; out.e[k] = (uint8_t)ex[k]; }
-            out.imask = (uint8_t)(int_ballot >> (lane & 24u));
-            out.child_base = child_base; out.prim_base = prim_base;
-        }
-        if (!occupied) {
-            out.meta[sub] = 0;
-            for (int k = 0; k < 3; k++) { out.q[k][0][sub] = (qplane_t)kQMax; out.q[k][1][sub] = 0; }
-        } else {
-            for (int k = 0; k < 3; k++) quantise_axis(c.lo[k], c.hi[k], nlo[k], inv_scale[k], out.q[k][0][sub], out.q[k][1][sub]);
-            if (is_int) {
-                out.meta[sub] = (uint8_t)(0x20u | (24u + sub));
-                __stcg(queue + child_base + int_rank, (unsigned long long)c.id);
+        if (is_leaf && !small) { prim_a = prim_sorted[pos_a]; if (mine.count > 1u) prim_b = prim_sorted[pos_b]; }
+        // what an internal child's group will touch first, on its way into L2 while this node is being finished
+        if (is_int) {
+            if (kContiguous && mine.count <= kSmallSubtree) {
+                const uint32_t cfirst = mine.id + 1u - __float_as_uint(pb.w);
+                const char *p0 = reinterpret_cast<const char *>(&bin[cfirst]), *p1 = reinterpret_cast<const char *>(&bin[cfirst + mine.count - 1u]);
+                for (const char *p = p0; p < p1; p += 128) prefetch_l2(p);
+                prefetch_l2(p1 - 1);
+                prefetch_l2(prim_sorted + cfirst); prefetch_l2(prim_sorted + cfirst + mine.count - 1u);
             } else {
-                out.meta[sub] = (uint8_t)((((1u << c.count) - 1u) << 5) | prim_off);
-                // the (at most kLeafMax) leaves below this child, left to right; valid for any binary tree (LBVH or PLOC)
-                uint32_t todo[4], sp = 0, q = 0;
-                todo[sp++] = c.id;
-                while (sp) {
-                    const uint32_t id = todo[--sp];
-                    if (id & kLeafBit) sink.emit(prim_base + prim_off + q++, prim_sorted[id & ~kLeafBit]);
-                    else {
-                        const float4 *pn = reinterpret_cast<const float4 *>(&bin[id]);
-                        todo[sp++] = __float_as_uint(pn[2].w); todo[sp++] = __float_as_uint(pn[0].w);
-                    }
-                }
+                if (!(__float_as_uint(pa.w) & kLeafBit)) prefetch_l2(&bin[__float_as_uint(pa.w)]);
+                if (!(__float_as_uint(pc.w) & kLeafBit)) prefetch_l2(&bin[__float_as_uint(pc.w)]);
             }
         }
-        __syncwarp(gmask);
-        if (sub < (uint32_t)kNodeQuads) reinterpret_cast<uint4 *>(&nodes[t])[sub] = reinterpret_cast<const uint4 *>(&out)[sub];
-        __syncwarp(gmask);
-      }
-      // ---- grid barrier; the last CTA to arrive publishes the end of the next level -------------------------------
-      __syncthreads();
-      if (threadIdx.x == 0) {
-          __threadfence();
-          const uint32_t arrived = atomicAdd(&h->bar_count, 1u) + 1u;
-          if (arrived == gridDim.x * (depth + 1)) {
-              const uint32_t err = *reinterpret_cast<volatile uint32_t *>(&h->error);
-              const uint32_t end = *reinterpret_cast<volatile uint32_t *>(&h->node_count);
-              h->level_end[depth + 1] = err ? level_end : end;  // an error ends the walk: the next level is empty
-              h->max_depth = depth + 1;
-              h->emitted = *reinterpret_cast<volatile uint32_t *>(&h->prim_count);
-              __threadfence();
-              atomicExch(&h->bar_release, depth + 1);
-          } else {
-              while (*reinterpret_cast<volatile uint32_t *>(&h->bar_release) < depth + 1) __nanosleep(64);
-          }
-          __threadfence();
-      }
-      __syncthreads();
-      level_begin = level_end;
-      level_end = *reinterpret_cast<volatile uint32_t *>(&h->level_end[depth + 1]);
+        // ---- node frame ----
+        float nlo[3], nhi[3], inv_scale[3]; uint32_t ex[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // group min / max through the order-preserving integer image of the floats; invalid lanes hold (+max, -max), NaN is
+            // treated the same way (fminf / fmaxf would skip it too)
+            const float vlo = mine.lo[k] == mine.lo[k] ? mine.lo[k] : FLT_MAX, vhi = mine.hi[k] == mine.hi[k] ? mine.hi[k] : -FLT_MAX;
+            nlo[k] = ordered_to_float(group_min(float_to_ordered(vlo)));
+            nhi[k] = ordered_to_float(group_max(float_to_ordered(vhi)));
+            const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
+            const uint32_t bits = __float_as_uint(sc);
+            uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+            e = max(e, 1u); e = min(e, 253u);
+            ex[k] = e;
+            inv_scale[k] = __uint_as_float((254u - e) << 23);
+        }
+        // ---- octant slot assignment: slot s is visited first by rays whose direction signs are s (bit k set =
+        // negative along axis k); greedy global minimum of dot(child centre - node centre, sign_s), ties -> lowest
+        // child, then lowest slot ----
+        const float cx = 0.5f * (mine.lo[0] + mine.hi[0]) - 0.5f * (nlo[0] + nhi[0]);
+        const float cy = 0.5f * (mine.lo[1] + mine.hi[1]) - 0.5f * (nlo[1] + nhi[1]);
+        const float cz = 0.5f * (mine.lo[2] + mine.hi[2]) - 0.5f * (nlo[2] + nhi[2]);
+        float cost[8];
+#pragma unroll
+        for (uint32_t sl = 0; sl < 8; sl++) cost[sl] = ((sl & 1) ? -cx : cx) + ((sl & 2) ? -cy : cy) + ((sl & 4) ? -cz : cz);
+        uint32_t slot_used = 0, my_slot = 8;
+        for (uint32_t it = 0; it < 8u; it++) {
+            float best = FLT_MAX; uint32_t bs = 8;
+            const bool waiting = valid && my_slot == 8;
+            if (waiting) {
+#pragma unroll
+                for (uint32_t sl = 0; sl < 8; sl++) if (!(slot_used >> sl & 1u) && cost[sl] < best) { best = cost[sl]; bs = sl; }
+            }
+            const uint32_t unassigned = (__ballot_sync(0xffffffffu, waiting) >> (lane & 24u)) & 0xffu;  // uniform over the group
+            if (!__any_sync(0xffffffffu, unassigned != 0u)) break;
+            // Shortcut: when the waiting children all prefer different free slots (and none is left with NaN costs only), the greedy
+            // hands each of them exactly that slot whatever the order — taking one never removes another's favourite — so they are all
+            // assigned at once.  Children spread over the octants of their parent: this ends most nodes after one or two rounds.
+            const uint32_t wanted = group_or(waiting && bs != 8 ? 1u << bs : 0u);
+            const bool all_distinct = (uint32_t)__popc(wanted) == (uint32_t)__popc(unassigned);
+            // group argmin: order-preserving image of the cost with its low six bits replaced by (child, slot)
+            const uint32_t cbits = __float_as_uint(best);
+            const uint32_t cord = cbits ^ ((cbits >> 31) ? 0xffffffffu : 0x80000000u);
+            const uint32_t ckey = (waiting && bs != 8) ? ((cord & ~63u) | (sub << 3) | bs) : 0xffffffffu;
+            const uint32_t cbest = group_min(ckey);
+            if (all_distinct) {
+                if (waiting) my_slot = bs;
+                slot_used |= wanted;
+            } else if (unassigned != 0u) {
+                uint32_t who = (cbest >> 3) & 7u, ws = cbest & 7u;
+                if (cbest == 0xffffffffu) {  // only NaN costs left: lowest unassigned child takes the lowest free slot
+                    who = __ffs(unassigned) - 1;
+                    ws = __ffs(~slot_used & 0xffu) - 1;
+                }
+                if (sub == who) my_slot = ws;
+                slot_used |= 1u << ws;
+            }
+        }
+        // ---- per-slot summaries: which slots hold internal children, how many primitives each leaf slot holds (2 bits per slot) ----
+        const uint32_t imask = group_or(is_int ? 1u << my_slot : 0u);
+        const uint32_t counts = group_or(is_leaf ? mine.count << (2u * my_slot) : 0u);
+        const uint32_t lower = (1u << (2u * (my_slot & 7u))) - 1u;
+        const uint32_t n_internal = __popc(imask), int_rank = __popc(imask & ((1u << (my_slot & 7u)) - 1u));
+        const uint32_t n_prims = __popc(counts & 0x5555u) + 2u * __popc(counts & 0xaaaau);
+        const uint32_t prim_off = __popc(counts & lower & 0x5555u) + 2u * __popc(counts & lower & 0xaaaau);
+        // ================= allocation + next tickets: two atomics per warp and step =================
+        const uint32_t mine_cnt = active ? (1u | (n_internal << 8) | (n_prims << 18)) : 0u;  // uniform over the group
+        const uint32_t c0 = __shfl_sync(0xffffffffu, mine_cnt, 0), c1 = __shfl_sync(0xffffffffu, mine_cnt, 8), c2 = __shfl_sync(0xffffffffu, mine_cnt, 16), c3 = __shfl_sync(0xffffffffu, mine_cnt, 24);
+        const uint32_t total = c0 + c1 + c2 + c3, excl = (wgrp > 0 ? c0 : 0u) + (wgrp > 1 ? c1 : 0u) + (wgrp > 2 ? c2 : 0u);
+        unsigned long long base = 0ull; uint32_t ticket = 0u;
+        if (lane == 0) {
+            const uint32_t ti = (total >> 8) & 0x3ffu, tp = total >> 18;
+            base = atomicAdd(reinterpret_cast<unsigned long long *>(&h->node_count), (unsigned long long)ti | ((unsigned long long)tp << 32));
+            ticket = atomicAdd(&h->tickets, total & 0xffu);
+            // the allocation that places the last primitive ends the walk: nothing allocated before it is unprocessed (an unprocessed
+            // node still holds unplaced primitives), so the node count it sees is final
+            if ((uint32_t)(base >> 32) + tp == n) *reinterpret_cast<volatile uint32_t *>(&h->collapse_done) = (uint32_t)base + ti + 1u;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0); ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const uint32_t child_base = (uint32_t)base + ((excl >> 8) & 0x3ffu), prim_base = (uint32_t)(base >> 32) + (excl >> 18);
+        const uint32_t next_ticket = ticket + (excl & 0xffu);
+        if (active) {
+            if (child_base + n_internal > capacity || depth + 1 > (uint32_t)kMaxWideDepth) {
+                if (sub == 0) {  // every group leaves at its next idle step
+                    atomicExch(&h->error, child_base + n_internal > capacity ? 2u : 1u);
+                    *reinterpret_cast<volatile uint32_t *>(&h->collapse_done) = 1u;
+                }
+            } else {
+                // ================= phase B: assemble the node in shared memory, store it in 16-byte pieces =================
+                out.meta[sub] = 0;  // every slot empty; the lanes that hold a child then fill theirs
+                for (int k = 0; k < 3; k++) { out.q[k][0][sub] = (qplane_t)kQMax; out.q[k][1][sub] = 0; }
+                if (sub == 0) {
+                    for (int k = 0; k < 3; k++) { out.org[k] = nlo[k]; out.e[k] = (uint8_t)ex[k]; }
+                    out.imask = (uint8_t)imask;
+                    out.child_base = child_base; out.prim_base = prim_base;
+                }
+                __syncwarp(gmask);
+                if (valid) {
+                    for (int k = 0; k < 3; k++) quantise_axis(mine.lo[k], mine.hi[k], nlo[k], inv_scale[k], out.q[k][0][my_slot], out.q[k][1][my_slot]);
+                    if (is_int) {
+                        out.meta[my_slot] = (uint8_t)(0x20u | (24u + my_slot));
+                        __stcg(queue + child_base + int_rank, ((unsigned long long)(depth + 2u) << 32) | (unsigned long long)mine.id);
+                    } else {
+                        out.meta[my_slot] = (uint8_t)((((1u << mine.count) - 1u) << 5) | prim_off);
+                        sink.emit(prim_base + prim_off, prim_a);
+                        if (mine.count > 1u) sink.emit(prim_base + prim_off + 1u, prim_b);
+                        my_emitted += mine.count;
+                    }
+                }
+                __syncwarp(gmask);
+                if (sub < (uint32_t)kNodeQuads) reinterpret_cast<uint4 *>(&nodes[t])[sub] = reinterpret_cast<const uint4 *>(&out)[sub];
+                __syncwarp(gmask);
+                my_depth = max(my_depth, depth + 1u);
+            }
+            t = next_ticket;
+        }
     }
-#undef GSHFL
-#undef GXOR
+    // ---- per-warp totals: deepest node, primitives emitted ----
+    for (int off = 16; off > 0; off >>= 1) { my_depth = max(my_depth, __shfl_xor_sync(0xffffffffu, my_depth, off)); my_emitted += __shfl_xor_sync(0xffffffffu, my_emitted, off); }
+    if (lane == 0) { if (my_depth) atomicMax(&h->max_depth, my_depth); if (my_emitted) atomicAdd(&h->emitted, my_emitted); }
 }
 
 // One thread per packed slot: gather the slot's triangle (id recorded by the collapse, or kept from the last build when
 // refitting) through the index buffer and write the 48 used bytes of the record.
-__global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, PackedTri *tris, uint32_t n) {
+__global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, const uint32_t *__restrict__ slot_prim, PackedTri *tris, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t prim = tris[i].prim;
+    const uint32_t prim = slot_prim ? slot_prim[i] : tris[i].prim;  // build: the collapse's slot -> primitive list; refit: kept in the record
     float a[3], b[3], c[3];
     load_triangle(in, prim, a, b, c);
     float4 *o = reinterpret_cast<float4 *>(&tris[i]);
@@ -836,7 +923,6 @@ __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, PackedTri *
     o[2] = make_float4(c[0], c[1], c[2], 0.f);
 }
 
-__global__ void k_seed_queue(const BuildHeader *h, unsigned long long *queue) { queue[0] = (unsigned long long)h->root; }
 
 template <class Sink>
 void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, const Sink &sink, LaunchCounter &lc, bool ploc) {
@@ -850,8 +936,14 @@ void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc
         passes = (lg + 12 + 7) / 8;
         passes = passes < 3 ? 3 : (passes > 6 ? 6 : passes);
     }
-    k_morton<<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals, 63 - 8 * passes); lc.count++;
-    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, passes, lc);
+    // up to 2^25 primitives the sort keys are 32 bits (at least 7 bits beyond log2 n: measured as good as 40 on the 20 M-triangle terrain,
+    // profiles/r01r_sort_passes.txt): two thirds of the sort's traffic, half its registers and shared memory
+    if (!forced_passes && n <= (1u << 25) && passes > 4) passes = 4;
+    const bool narrow = passes <= 4;
+    if (narrow) k_morton<uint32_t><<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, reinterpret_cast<uint32_t *>(sc.keys), sc.vals, 63 - 8 * passes);
+    else k_morton<uint64_t><<<(n + 255) / 256, 256, 0, s>>>(sc.boxes, n, sc.header, sc.keys, sc.vals, 63 - 8 * passes);
+    lc.count++;
+    bool in_alt = sort_pairs(s, n, sc.keys, sc.vals, sc.keys_alt, sc.vals_alt, sc.sort_scratch, 0, passes, narrow ? 4 : 8, lc);
     const uint64_t *keys = in_alt ? sc.keys_alt : sc.keys;
     const uint32_t *vals = in_alt ? sc.vals_alt : sc.vals;
     if (ploc && n > 1) {
@@ -890,27 +982,27 @@ void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc
             live = st.n_clusters;
         }
         (void)tiles;
-        k_ploc_finish<<<1, 1, 0, s>>>(a, sc.ploc_state, sc.header); lc.count++;
+        k_ploc_finish<<<1, 1, 0, s>>>(a, sc.ploc_state, sc.header, sc.queue); lc.count++;
     } else {
-        k_hierarchy<<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header); lc.count++;
+        if (narrow) k_hierarchy<uint32_t><<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const uint32_t *>(keys), vals, sc.boxes, n, sc.bin, sc.flags, sc.header, sc.queue);
+        else k_hierarchy<uint64_t><<<(n + 127) / 128, 128, 0, s>>>(keys, vals, sc.boxes, n, sc.bin, sc.flags, sc.header, sc.queue);
+        lc.count++;
     }
-    // seed the collapse queue with the binary root (device-side, no host round trip)
-    k_seed_queue<<<1, 1, 0, s>>>(sc.header, sc.queue); lc.count++;
-    // one 8-lane group per wide node of the widest level; cooperative launch: the grid must be co-resident for the barrier
-    static int max_blocks = 0;
-    if (!max_blocks) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse<Sink>, kCollapseThreads, 0);
-        max_blocks = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    uint32_t blocks = (n / 6 + kCollapseGroups - 1) / kCollapseGroups + 1;
-    if (blocks > (uint32_t)max_blocks) blocks = (uint32_t)max_blocks;
-    const BinNode *a_bin = sc.bin; const uint32_t *a_vals = vals; uint32_t a_n = n, a_cap = capacity; BuildHeader *a_h = sc.header;
-    unsigned long long *a_queue = sc.queue; WideNode *a_nodes = nodes; Sink a_sink = sink;
-    void *args[] = {&a_bin, &a_vals, &a_n, &a_h, &a_queue, &a_nodes, &a_cap, &a_sink};
-    cudaLaunchCooperativeKernel((const void *)k_collapse<Sink>, dim3(blocks), dim3(kCollapseThreads), args, 0, s); lc.count++;
+    // one 8-lane group per wide node in flight; every resident slot when the tree is large enough (the queue needs no co-residency)
+    auto launch = [&](auto kernel) {
+        static int max_blocks = 0;
+        if (!max_blocks) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCollapseThreads, 0);
+            max_blocks = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        uint32_t blocks = (n / 6 + kCollapseGroups - 1) / kCollapseGroups + 1;
+        if (blocks > (uint32_t)max_blocks) blocks = (uint32_t)max_blocks;
+        kernel<<<blocks, kCollapseThreads, 0, s>>>(sc.bin, vals, n, sc.header, sc.queue, nodes, capacity, sink); lc.count++;
+    };
+    if (ploc && n > 1) launch(k_collapse<Sink, false>); else launch(k_collapse<Sink, true>);  // LBVH ids are split positions (contiguous subtrees)
 }
 
 }  // namespace
@@ -943,7 +1035,7 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
 
 int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *tris, LaunchCounter &lc, int builder) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
     k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
     bool use_ploc = builder == kBuilderPloc;
     if (builder == kBuilderAuto && n > 1) {
@@ -958,35 +1050,38 @@ int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildS
         const float scene = ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0];
         use_ploc = scene > 0.f && hdr.prim_area_sum < 4.0f * scene;
     }
-    LeafSinkTriangles sink{tris};
+    uint32_t *slot_prim = reinterpret_cast<uint32_t *>(sc.flags);  // the arrival flags are dead once the binary tree exists
+    LeafSinkTriangles sink{slot_prim};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, use_ploc);
-    k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, tris, n); lc.count++;
+    k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(in, slot_prim, tris, n); lc.count++;
     return use_ploc && n > 1 ? kBuilderPloc : kBuilderLbvh;
 }
 
 void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
     k_aabb_boxes<<<(n + 255) / 256, 256, 0, s>>>(aabbs, n, sc.boxes, sc.header); lc.count++;
-    LeafSinkTriangles sink{slots};
+    uint32_t *slot_prim = reinterpret_cast<uint32_t *>(sc.flags);
+    LeafSinkTriangles sink{slot_prim};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
-    k_pack_aabbs<<<(n + 255) / 256, 256, 0, s>>>(aabbs, slots, n); lc.count++;
+    k_pack_aabbs<<<(n + 255) / 256, 256, 0, s>>>(aabbs, slot_prim, slots, n); lc.count++;
 }
 
 void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
     k_curve_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
-    LeafSinkTriangles sink{slots};
+    uint32_t *slot_prim = reinterpret_cast<uint32_t *>(sc.flags);
+    LeafSinkTriangles sink{slot_prim};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
-    k_pack_curves<<<(n + 255) / 256, 256, 0, s>>>(in, slots, n); lc.count++;
+    k_pack_curves<<<(n + 255) / 256, 256, 0, s>>>(in, slot_prim, slots, n); lc.count++;
     if (in.basis != kCurveLinear) { const uint32_t n_segs = n / in.pieces; k_curve_coefs<<<(n_segs + 255) / 256, 256, 0, s>>>(in, slots, n, n_segs); lc.count++; }
 }
 
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,
                 uint32_t *prim_ids, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
     k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
     LeafSinkInstances sink{active_ids, prim_ids};
     run_pipeline_after_boxes(s, n, sc, nodes, n, sink, lc, false);  // a handful of instances: the LBVH order is as good as any; the node array holds n
@@ -1012,64 +1107,82 @@ __global__ void __launch_bounds__(256) k_refit_reset(uint32_t *counters, uint32_
     if (i < n_nodes) counters[i] = 0;
 }
 
-__global__ void __launch_bounds__(128) k_refit(WideNode *nodes, const PackedTri *tris, uint32_t n_nodes, const uint32_t *__restrict__ parent,
+// One 8-lane group per node, lane s = slot s (the layout of k_collapse): every lane fetches its own child — the box of an internal child,
+// the one or two triangles of a leaf child — so a node costs one round of loads, not eight in sequence, and nothing lives in local
+// memory; node frame by group butterflies, the lane quantises its own slot into the node's copy in shared memory.
+constexpr int kRefitThreads = 256;
+__global__ void __launch_bounds__(kRefitThreads) k_refit(WideNode *nodes, const PackedTri *tris, uint32_t n_nodes, const uint32_t *__restrict__ parent,
                                                float *boxes, uint32_t *counters) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    if (nodes[i].imask != 0) return;  // reached later through its children
-    while (true) {
-        WideNode node = nodes[i];
-        float clo[8][3], chi[8][3];
-        float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        uint32_t int_rank = 0;
-        for (int s = 0; s < 8; s++) {
-            const uint32_t meta = node.meta[s];
-            if (meta == 0) continue;
-            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-            if (node.imask >> s & 1) {
-                const float *b = boxes + 6 * (size_t)(node.child_base + int_rank);
-                for (int k = 0; k < 3; k++) { lo[k] = __ldcg(b + k); hi[k] = __ldcg(b + 3 + k); }
-                int_rank++;
-            } else {
-                const uint32_t count = __popc(meta >> 5), first = node.prim_base + (meta & 31u);
-                for (uint32_t q = 0; q < count; q++) {
-                    const float4 *pt = reinterpret_cast<const float4 *>(&tris[first + q]);  // refreshed by k_pack_tris just before
-                    const float4 a = pt[0], b = pt[1], c = pt[2];
-                    lo[0] = fminf(lo[0], fmin3(a.x, b.x, c.x)); hi[0] = fmaxf(hi[0], fmax3(a.x, b.x, c.x));
-                    lo[1] = fminf(lo[1], fmin3(a.y, b.y, c.y)); hi[1] = fmaxf(hi[1], fmax3(a.y, b.y, c.y));
-                    lo[2] = fminf(lo[2], fmin3(a.z, b.z, c.z)); hi[2] = fmaxf(hi[2], fmax3(a.z, b.z, c.z));
+    __shared__ WideNode s_node[kRefitThreads / 8];
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 7u;
+    WideNode &node = s_node[threadIdx.x >> 3];
+    uint32_t i = (blockIdx.x * kRefitThreads + threadIdx.x) >> 3;
+    bool live = i < n_nodes && nodes[i].imask == 0;  // nodes with internal children are reached later through them
+    while (__any_sync(0xffffffffu, live)) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        uint32_t meta = 0;
+        if (live) {
+            if (sub < (uint32_t)kNodeQuads) reinterpret_cast<uint4 *>(&node)[sub] = reinterpret_cast<const uint4 *>(&nodes[i])[sub];
+        }
+        __syncwarp();
+        if (live) {
+            meta = node.meta[sub];
+            const uint32_t imask = node.imask;
+            if (meta != 0) {
+                if (imask >> sub & 1u) {
+                    const float *b = boxes + 6 * (size_t)(node.child_base + __popc(imask & ((1u << sub) - 1u)));
+                    for (int k = 0; k < 3; k++) { lo[k] = __ldcg(b + k); hi[k] = __ldcg(b + 3 + k); }
+                } else {
+                    const uint32_t count = __popc(meta >> 5), first = node.prim_base + (meta & 31u);
+                    for (uint32_t q = 0; q < count; q++) {
+                        const float4 *pt = reinterpret_cast<const float4 *>(&tris[first + q]);  // refreshed by k_pack_tris just before
+                        const float4 a = pt[0], b = pt[1], c = pt[2];
+                        lo[0] = fminf(lo[0], fmin3(a.x, b.x, c.x)); hi[0] = fmaxf(hi[0], fmax3(a.x, b.x, c.x));
+                        lo[1] = fminf(lo[1], fmin3(a.y, b.y, c.y)); hi[1] = fmaxf(hi[1], fmax3(a.y, b.y, c.y));
+                        lo[2] = fminf(lo[2], fmin3(a.z, b.z, c.z)); hi[2] = fmaxf(hi[2], fmax3(a.z, b.z, c.z));
+                    }
                 }
             }
-            for (int k = 0; k < 3; k++) { clo[s][k] = lo[k]; chi[s][k] = hi[k]; nlo[k] = fminf(nlo[k], lo[k]); nhi[k] = fmaxf(nhi[k], hi[k]); }
         }
-        float inv_scale[3];
-        for (int k = 0; k < 3; k++) {
-            float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
-            uint32_t bits = __float_as_uint(sc);
-            uint32_t ex = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
-            ex = max(ex, 1u); ex = min(ex, 253u);
-            node.e[k] = (uint8_t)ex; node.org[k] = nlo[k];
-            inv_scale[k] = __uint_as_float((254u - ex) << 23);
-        }
-        for (int s = 0; s < 8; s++) {
-            if (node.meta[s] == 0) continue;
-            for (int k = 0; k < 3; k++) quantise_axis(clo[s][k], chi[s][k], nlo[k], inv_scale[k], node.q[k][0][s], node.q[k][1][s]);
-        }
-        const uint4 *src = reinterpret_cast<const uint4 *>(&node);
-        uint4 *dst = reinterpret_cast<uint4 *>(&nodes[i]);
+        float nlo[3], nhi[3], inv_scale[3]; uint32_t ex[3];
 #pragma unroll
-        for (int q = 0; q < kNodeQuads; q++) dst[q] = src[q];
-        float *b = boxes + 6 * (size_t)i;
-        for (int k = 0; k < 3; k++) { __stcg(b + k, nlo[k]); __stcg(b + 3 + k, nhi[k]); }
-        const uint32_t p = parent[i];
-        if (p == 0xffffffffu) return;
-        __threadfence();
-        const uint32_t arrived = atomicAdd(&counters[p], 1u) + 1u;
-        if (arrived != (uint32_t)__popc(nodes[p].imask)) return;
-        __threadfence();
-        i = p;
+        for (int k = 0; k < 3; k++) {
+            nlo[k] = ordered_to_float(group_min(float_to_ordered(lo[k])));
+            nhi[k] = ordered_to_float(group_max(float_to_ordered(hi[k])));
+            const float sc = __fdiv_ru(__fsub_ru(nhi[k], nlo[k]), (float)kQMax);
+            const uint32_t bits = __float_as_uint(sc);
+            uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+            e = max(e, 1u); e = min(e, 253u);
+            ex[k] = e;
+            inv_scale[k] = __uint_as_float((254u - e) << 23);
+        }
+        uint32_t next = 0xffffffffu;
+        if (live) {
+            if (meta != 0) for (int k = 0; k < 3; k++) quantise_axis(lo[k], hi[k], nlo[k], inv_scale[k], node.q[k][0][sub], node.q[k][1][sub]);
+            if (sub < 3) { node.org[sub] = nlo[sub]; node.e[sub] = (uint8_t)ex[sub]; }
+            if (sub < 6) __stcg(boxes + 6 * (size_t)i + sub, sub < 3 ? nlo[sub] : nhi[sub - 3]);
+            release_fence();  // the node's box before the arrival below
+        }
+        __syncwarp();
+        if (live) {
+            if (sub < (uint32_t)kNodeQuads) reinterpret_cast<uint4 *>(&nodes[i])[sub] = reinterpret_cast<const uint4 *>(&node)[sub];
+            if (sub == 0) {
+                const uint32_t p = parent[i];
+                if (p != 0xffffffffu) {
+                    const uint32_t arrived = atomicAdd(&counters[p], 1u) + 1u;
+                    if (arrived == (uint32_t)__popc(nodes[p].imask)) next = p;  // the last internal child to arrive takes the parent
+                }
+            }
+        }
+        next = GSHFL(next, 0);
+        __syncwarp();  // the shared copy is rewritten by the next round
+        live = live && next != 0xffffffffu;
+        i = next;
     }
 }
+
+#undef GSHFL
+#undef GXOR
 
 void build_refit_arrays(cudaStream_t s, uint32_t n_nodes, const WideNode *nodes, const RefitArrays &ra, LaunchCounter &lc) {
     if (!n_nodes) return;
@@ -1080,8 +1193,8 @@ void refit_blas(cudaStream_t s, uint32_t n_nodes, uint32_t n_tris, const Triangl
                 BuildHeader *, LaunchCounter &lc) {
     if (!n_nodes || !n_tris) return;
     k_refit_reset<<<(n_nodes + 255) / 256, 256, 0, s>>>(ra.counters, n_nodes); lc.count++;
-    k_pack_tris<<<(n_tris + 255) / 256, 256, 0, s>>>(in, tris, n_tris); lc.count++;
-    k_refit<<<(n_nodes + 127) / 128, 128, 0, s>>>(nodes, tris, n_nodes, ra.parent, ra.boxes, ra.counters); lc.count++;
+    k_pack_tris<<<(n_tris + 255) / 256, 256, 0, s>>>(in, nullptr, tris, n_tris); lc.count++;
+    k_refit<<<(unsigned)(((size_t)n_nodes * 8 + kRefitThreads - 1) / kRefitThreads), kRefitThreads, 0, s>>>(nodes, tris, n_nodes, ra.parent, ra.boxes, ra.counters); lc.count++;
 }
 
 // ---- instance table scatter ----------------------------------------------------------------

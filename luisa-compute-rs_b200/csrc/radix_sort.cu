@@ -17,22 +17,27 @@ namespace {
 constexpr int kRadix = 256;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItems = 16;
-constexpr int kTile = kSortThreads * kItems;  // 4096 pairs per tile
+#ifndef LCB_SORT_ITEMS_SMALL
+#define LCB_SORT_ITEMS_SMALL 16
+#endif
+constexpr int kItemsLarge = 16, kItemsSmall = LCB_SORT_ITEMS_SMALL;   // keys per thread: tiles of 4096 pairs (8 and 12 per thread measured slower at 1 M pairs: profiles/r02n_variants.txt)
+constexpr uint32_t kSmallTileMax = 4u << 20;      // sorts up to this size take the small tile
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagPrefix = 2u << 30, kValueMask = (1u << 30) - 1;
 constexpr int kSmallSortMax = 2048;
+constexpr int kLookBatch = 8;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
 // Histogram of every 8-bit digit of every pass in one read of the keys.
-__global__ void __launch_bounds__(256) k_sort_histogram(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ ghist,
+template <typename K>
+__global__ void __launch_bounds__(256) k_sort_histogram(const K *__restrict__ keys, uint32_t n, uint32_t *__restrict__ ghist,
                                                          int begin_bit, int passes) {
     __shared__ uint32_t sh[8 * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint64_t k = keys[i] >> begin_bit;
+        K k = keys[i] >> begin_bit;
         for (int p = 0; p < passes; p++) {
             atomicAdd(&sh[p * kRadix + (uint32_t)(k & 0xff)], 1u);
             k >>= 8;
@@ -61,13 +66,20 @@ __global__ void __launch_bounds__(256) k_sort_scan(uint32_t *ghist) {
     h[threadIdx.x] = sh[threadIdx.x] - v;
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-                                                                uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n, int shift,
+// K: key type (uint32_t when the Morton code fits — up to 2^25 primitives — else uint64_t); kItems: keys per thread.  Small sorts take
+// smaller tiles: with 16 keys per thread a 1 M-pair pass is 245 tiles on 148 SMs, one serial chain of load / rank / look-back / scatter
+// per tile with little to overlap it; the small tile is sized so that a 1 M-pair pass still fits one wave of resident CTAs.
+template <typename K, int kItems>
+__global__ void __launch_bounds__(kSortThreads, kItems * sizeof(K) <= 64 ? 3 : 2) k_sort_onesweep(const K *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                K *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n, int shift,
                                                                 const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *ticket) {
+    constexpr int kTile = kSortThreads * kItems;
+    constexpr int kEntry = sizeof(K) > 5 ? sizeof(K) : 5;   // the exchange buffer holds the keys, then values (4 B) + their digits (1 B)
     __shared__ uint32_t warp_hist[kSortWarps][kRadix];
     __shared__ uint32_t tile_start[kRadix];   // first position of digit d inside the (digit-sorted) tile
     __shared__ int digit_delta[kRadix];       // global position of digit d's run minus its position inside the tile
-    __shared__ uint64_t exch[kTile];          // tile in digit order: keys, then (reused) values -> coalesced runs per digit
+    __shared__ __align__(8) uint8_t exch_raw[kTile * kEntry];  // tile in digit order: keys, then (reused) values -> coalesced runs per digit
+    K *exch = reinterpret_cast<K *>(exch_raw);
     __shared__ uint32_t tile_s;
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
@@ -78,12 +90,12 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *
     const uint32_t base = tile * kTile + warp * (32 * kItems);
     const uint32_t tile_count = min((uint32_t)kTile, n - tile * kTile);
 
-    uint64_t key[kItems];
+    K key[kItems];
     uint16_t rank[kItems];
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
         uint32_t idx = base + j * 32 + lane;
-        key[j] = idx < n ? kin[idx] : ~0ull;
+        key[j] = idx < n ? kin[idx] : (K)~(K)0;
     }
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
@@ -127,14 +139,24 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *
             st_volatile_u32(mine, kFlagPrefix | total);
         } else {
             st_volatile_u32(mine, kFlagAgg | total);
+            // look-back, kLookBatch predecessors per L2 round trip: when every tile of a pass is resident at once (1 M pairs = 245 tiles
+            // on 148 SMs) nobody has an inclusive prefix to offer at first, and a one-at-a-time walk is a chain of ~sqrt(2 * tiles)
+            // dependent loads per pass; the batch is consumed in order and stops at the first prefix or the first unpublished entry
             int look = (int)tile - 1;
-            while (true) {
-                uint32_t v = ld_volatile_u32(status + (size_t)look * kRadix + d);
-                uint32_t f = v >> 30;
-                if (f == 0) continue;
-                excl += v & kValueMask;
-                if (f == 2) break;
-                look--;
+            bool found = false;
+            while (!found) {
+                uint32_t v[kLookBatch];
+#pragma unroll
+                for (int b = 0; b < kLookBatch; b++) v[b] = look - b >= 0 ? ld_volatile_u32(status + (size_t)(look - b) * kRadix + d) : 0u;
+#pragma unroll
+                for (int b = 0; b < kLookBatch; b++) {
+                    if (found) break;
+                    const uint32_t f = v[b] >> 30;
+                    if (f == 0) break;            // not published yet: poll again from here
+                    excl += v[b] & kValueMask;
+                    look--;
+                    if (f == 2) found = true;
+                }
             }
             st_volatile_u32(mine, kFlagPrefix | (excl + total));
         }
@@ -152,14 +174,14 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *
     }
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < tile_count; p += kSortThreads) {
-        const uint64_t k = exch[p];
+        const K k = exch[p];
         const uint32_t d = (uint32_t)(k >> shift) & 0xff;
         kout[(int)p + digit_delta[d]] = k;
     }
     __syncthreads();
     // values: same route through the (reused) exchange buffer; the digit of position p is recovered from the key pass
-    uint32_t *exv = reinterpret_cast<uint32_t *>(exch);
-    uint8_t *exd = reinterpret_cast<uint8_t *>(exch) + kTile * 4;
+    uint32_t *exv = reinterpret_cast<uint32_t *>(exch_raw);
+    uint8_t *exd = exch_raw + kTile * 4;
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
         uint32_t idx = base + j * 32 + lane;
@@ -171,11 +193,12 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(const uint64_t *
 
 // n <= 2048: one block, bitonic sort of (key, value) in shared memory; (key, value) compared
 // lexicographically so the result equals the stable sort when values are the input positions.
-__global__ void __launch_bounds__(1024) k_sort_small(uint64_t *keys, uint32_t *vals, uint32_t n) {
-    __shared__ uint64_t sk[kSmallSortMax];
+template <typename K>
+__global__ void __launch_bounds__(1024) k_sort_small(K *keys, uint32_t *vals, uint32_t n) {
+    __shared__ K sk[kSmallSortMax];
     __shared__ uint32_t sv[kSmallSortMax];
     for (uint32_t i = threadIdx.x; i < kSmallSortMax; i += blockDim.x) {
-        sk[i] = i < n ? keys[i] : ~0ull;
+        sk[i] = i < n ? keys[i] : (K)~(K)0;
         sv[i] = i < n ? vals[i] : 0xffffffffu;
     }
     __syncthreads();
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint64_t *keys, uint32_t *v
                 uint32_t ixj = i ^ j;
                 if (ixj > i) {
                     bool up = (i & k) == 0;
-                    uint64_t a = sk[i], b = sk[ixj];
+                    K a = sk[i], b = sk[ixj];
                     uint32_t va = sv[i], vb = sv[ixj];
                     bool gt = a > b || (a == b && va > vb);
                     if (gt == up) { sk[i] = b; sk[ixj] = a; sv[i] = vb; sv[ixj] = va; }
@@ -199,39 +222,50 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint64_t *keys, uint32_t *v
 
 }  // namespace
 
+static int tile_pairs(uint32_t n) { return kSortThreads * (n <= kSmallTileMax ? kItemsSmall : kItemsLarge); }
+
 size_t sort_scratch_bytes(uint32_t n, int passes) {
     if (n <= (uint32_t)kSmallSortMax) return 256;
-    size_t tiles = (n + kTile - 1) / kTile;
+    size_t tiles = (n + tile_pairs(n) - 1) / tile_pairs(n);
     return (size_t)8 * kRadix * 4 + 256 + (size_t)passes * tiles * kRadix * 4;
 }
 
-// Sorts by bits [begin_bit, begin_bit + 8*passes).  Returns true if the result is in (keys_alt, vals_alt).
-bool sort_pairs(cudaStream_t s, uint32_t n, uint64_t *keys, uint32_t *vals, uint64_t *keys_alt, uint32_t *vals_alt, void *scratch,
-                int begin_bit, int passes, LaunchCounter &lc) {
-    if (n <= 1) return false;
+template <typename K>
+static bool sort_pairs_t(cudaStream_t s, uint32_t n, K *keys, uint32_t *vals, K *keys_alt, uint32_t *vals_alt, void *scratch,
+                         int begin_bit, int passes, LaunchCounter &lc) {
     if (n <= (uint32_t)kSmallSortMax) {
-        k_sort_small<<<1, 1024, 0, s>>>(keys, vals, n); lc.count++;
+        k_sort_small<K><<<1, 1024, 0, s>>>(keys, vals, n); lc.count++;
         return false;
     }
-    const size_t tiles = (n + kTile - 1) / kTile;
+    const bool small = n <= kSmallTileMax;
+    const size_t tiles = (n + tile_pairs(n) - 1) / tile_pairs(n);
     uint32_t *ghist = (uint32_t *)scratch;
     uint32_t *tickets = ghist + 8 * kRadix;
     uint32_t *status = tickets + 64;
     cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n, passes), s);
     int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    k_sort_histogram<<<hist_blocks, 256, 0, s>>>(keys, n, ghist, begin_bit, passes); lc.count++;
+    k_sort_histogram<K><<<hist_blocks, 256, 0, s>>>(keys, n, ghist, begin_bit, passes); lc.count++;
     k_sort_scan<<<passes, kRadix, 0, s>>>(ghist); lc.count++;
-    uint64_t *ki = keys, *ko = keys_alt;
+    K *ki = keys, *ko = keys_alt;
     uint32_t *vi = vals, *vo = vals_alt;
     for (int p = 0; p < passes; p++) {
-        k_sort_onesweep<<<(unsigned)tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, begin_bit + 8 * p, ghist + p * kRadix,
-                                                                  status + (size_t)p * tiles * kRadix, tickets + p);
+        if (small) k_sort_onesweep<K, kItemsSmall><<<(unsigned)tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, begin_bit + 8 * p, ghist + p * kRadix, status + (size_t)p * tiles * kRadix, tickets + p);
+        else k_sort_onesweep<K, kItemsLarge><<<(unsigned)tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, n, begin_bit + 8 * p, ghist + p * kRadix, status + (size_t)p * tiles * kRadix, tickets + p);
         lc.count++;
-        uint64_t *tk = ki; ki = ko; ko = tk;
+        K *tk = ki; ki = ko; ko = tk;
         uint32_t *tv = vi; vi = vo; vo = tv;
     }
     return (passes & 1) != 0;
+}
+
+// Sorts by bits [begin_bit, begin_bit + 8*passes).  Returns true if the result is in (keys_alt, vals_alt).  key_bytes = 4: the key
+// arrays hold uint32_t (the caller's Morton codes fit 32 bits), 8: uint64_t.
+bool sort_pairs(cudaStream_t s, uint32_t n, void *keys, uint32_t *vals, void *keys_alt, uint32_t *vals_alt, void *scratch,
+                int begin_bit, int passes, int key_bytes, LaunchCounter &lc) {
+    if (n <= 1) return false;
+    if (key_bytes == 4) return sort_pairs_t<uint32_t>(s, n, (uint32_t *)keys, vals, (uint32_t *)keys_alt, vals_alt, scratch, begin_bit, passes, lc);
+    return sort_pairs_t<uint64_t>(s, n, (uint64_t *)keys, vals, (uint64_t *)keys_alt, vals_alt, scratch, begin_bit, passes, lc);
 }
 
 }  // namespace lcb

@@ -106,16 +106,19 @@ struct BuildHeader {
     uint32_t emitted;       // primitives emitted into leaves (= prim_count after a complete collapse)
     uint32_t node_count;    // wide nodes allocated   } one 8-byte aligned pair: the collapse allocates both
     uint32_t prim_count;    // packed prims allocated } with a single 64-bit atomic per CTA and step
-    uint32_t bar_count;     // collapse: grid barrier arrivals
+    uint32_t tickets;       // collapse: next wide-node id to hand out as a work ticket
     uint32_t max_depth;
     uint32_t error;         // nonzero: builder failure code
-    uint32_t bar_release;   // collapse: last released level
+    uint32_t processed;     // collapse: wide nodes whose children have been allocated (== node_count: the walk is over)
     float root_lo[3]; float prim_area_sum;  // sum of the primitives' box half-areas (builder choice, bvh_build.cu)
     float root_hi[3]; float pad2;
-    uint32_t level_end[48]; // collapse: node_count snapshot taken by the last arriver of each level's barrier
+    uint32_t pad_line[24];  // keeps collapse_done out of the cache line of the allocation atomics
+    uint32_t collapse_done; // collapse: final wide-node count + 1 once every primitive has a leaf slot (1 after an error); polled by idle warps
+    uint32_t reserved[23];
 };
 #ifndef __CUDACC_RTC__
 static_assert(offsetof(BuildHeader, node_count) % 8 == 0, "node_count/prim_count must form an aligned 64-bit word");
+static_assert(offsetof(BuildHeader, collapse_done) / 128 != offsetof(BuildHeader, tickets) / 128 && offsetof(BuildHeader, collapse_done) / 128 != offsetof(BuildHeader, node_count) / 128, "collapse_done has its own cache line");
 #endif
 
 // What a traversal needs to know about one acceleration structure (by value in kernel parameters).

@@ -439,7 +439,7 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
             inv.z = a.world_hi[2] > a.world_lo[2] ? 1.f / (a.world_hi[2] - a.world_lo[2]) : 0.f;
             k_ray_keys<<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4 *>(rays), n, lo, inv, rs.origin_bits, rs.dir_bits, keys, vals);
             lc.count++;
-            const bool in_alt = sort_pairs(s, n, keys, vals, keys_alt, vals_alt, p + 2 * kb + 2 * vb, 0, passes, lc);
+            const bool in_alt = sort_pairs(s, n, keys, vals, keys_alt, vals_alt, p + 2 * kb + 2 * vb, 0, passes, 8, lc);
             order = in_alt ? vals_alt : vals;
         } else {
             (void)cudaGetLastError();  // no memory for the permutation: trace in submission order

@@ -1,0 +1,192 @@
+/* treelab.c — development aid (not product, not oracle): CPU model of the device's BVH pipeline used to compare BINARY-TREE builders
+ * by what matters to k_trace: wide nodes visited and triangles tested per incoherent closest-hit ray, after the same 8-wide collapse
+ * (open the largest-area child until 8, spare slots split small leaves; bvh_build.cu k_collapse) and an ordered traversal.
+ *   gcc -O2 -march=native -o /tmp/treelab tools/treelab/treelab.c -lm && /tmp/treelab [n_tris] [n_rays] [leaf_max]
+ * Builders: lbvh (Morton order, split at the highest differing bit = the device's k_hierarchy), sah (binned top-down, the oracle's
+ * kind of tree), ploc (radius 8, the device's k_ploc_*), and lbvh+X experiments. */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float lo[3], hi[3]; } box_t;
+typedef struct { box_t b; int left, right; int count; int first; } bnode_t; /* left/right: >= 0 internal node, < 0 leaf ~prim_pos; */
+
+static uint64_t rng_s = 0x9E3779B97F4A7C15ull;
+static inline uint64_t rnd64(void) { rng_s ^= rng_s << 13; rng_s ^= rng_s >> 7; rng_s ^= rng_s << 17; return rng_s; }
+static inline float rndf(void) { return (float)((rnd64() >> 40) * (1.0 / 16777216.0)); }
+
+static int n_tris;
+static float (*V)[3][3]; /* triangle vertices */
+static box_t *pbox;      /* primitive boxes */
+
+static inline box_t box_empty(void) { box_t b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}}; return b; }
+static inline void box_grow(box_t *a, const box_t *b) { for (int k = 0; k < 3; k++) { if (b->lo[k] < a->lo[k]) a->lo[k] = b->lo[k]; if (b->hi[k] > a->hi[k]) a->hi[k] = b->hi[k]; } }
+static inline float box_area(const box_t *b) { float dx = b->hi[0] - b->lo[0], dy = b->hi[1] - b->lo[1], dz = b->hi[2] - b->lo[2]; return dx * dy + dy * dz + dz * dx; }
+
+/* ---- binary tree storage: nodes[0..n_nodes), order[] = primitive at sorted position ---- */
+static bnode_t *nodes; static int n_nodes; static int *order; static int root;
+
+static uint64_t expand21(uint32_t x) { uint64_t v = x & 0x1fffff; v = (v | v << 32) & 0x1f00000000ffffull; v = (v | v << 16) & 0x1f0000ff0000ffull; v = (v | v << 8) & 0x100f00f00f00f00full; v = (v | v << 4) & 0x10c30c30c30c30c3ull; v = (v | v << 2) & 0x1249249249249249ull; return v; }
+typedef struct { uint64_t key; int prim; } kv_t;
+static int kv_cmp(const void *a, const void *b) { const kv_t *x = a, *y = b; return x->key < y->key ? -1 : x->key > y->key ? 1 : (x->prim - y->prim); }
+static kv_t *kv;
+
+static void morton_sort(int bits_total, int extended) {
+    box_t cb = box_empty();
+    for (int i = 0; i < n_tris; i++) { float c[3]; for (int k = 0; k < 3; k++) c[k] = 0.5f * pbox[i].lo[k] + 0.5f * pbox[i].hi[k]; box_t p = {{c[0], c[1], c[2]}, {c[0], c[1], c[2]}}; box_grow(&cb, &p); }
+    float maxdiag = 0.f;
+    if (extended) for (int i = 0; i < n_tris; i++) { float d = 0; for (int k = 0; k < 3; k++) { float e = pbox[i].hi[k] - pbox[i].lo[k]; d += e * e; } d = sqrtf(d); if (d > maxdiag) maxdiag = d; }
+    for (int i = 0; i < n_tris; i++) {
+        uint32_t q[3];
+        for (int k = 0; k < 3; k++) { float c = 0.5f * pbox[i].lo[k] + 0.5f * pbox[i].hi[k]; float t = (c - cb.lo[k]) / (cb.hi[k] - cb.lo[k]); t = t < 0 ? 0 : t > 1 ? 1 : t; uint32_t v = (uint32_t)(t * 2097152.0f); q[k] = v > 2097151u ? 2097151u : v; }
+        uint64_t code = expand21(q[0]) | expand21(q[1]) << 1 | expand21(q[2]) << 2;
+        if (extended) { /* Vinkler et al. 2017: interleave a size bit after every `extended` spatial triplets */
+            float d = 0; for (int k = 0; k < 3; k++) { float e = pbox[i].hi[k] - pbox[i].lo[k]; d += e * e; } d = sqrtf(d) / maxdiag;
+            uint32_t sz = (uint32_t)(d * 1023.0f); uint64_t out = 0; int ob = 0, sb = 9;
+            for (int b = 62; b >= 0 && ob < 63; b -= 3) { for (int j = 0; j < 3 && ob < 63; j++) { out = out << 1 | (code >> (b - j) & 1); ob++; } if (((62 - b) / 3 + 1) % extended == 0 && sb >= 0 && ob < 63) { out = out << 1 | (sz >> sb & 1); sb--; ob++; } }
+            code = out << (63 - ob);
+        }
+        kv[i].key = code >> (63 - bits_total); kv[i].prim = i;
+    }
+    qsort(kv, n_tris, sizeof(kv_t), kv_cmp);
+    for (int i = 0; i < n_tris; i++) order[i] = kv[i].prim;
+}
+
+static inline uint64_t delta(int i) { uint64_t x = kv[i].key ^ kv[i + 1].key; return x ? (x | 1ull << 63) : (uint64_t)(i ^ (i + 1)); }
+
+/* returns child ref: >= 0 internal node id, < 0 leaf ~pos */
+static int lbvh_rec(int lo, int hi) {
+    if (lo == hi) return ~lo;
+    int split = lo; uint64_t best = 0;
+    for (int i = lo; i < hi; i++) { uint64_t d = delta(i); if (d > best) { best = d; split = i; } }
+    int id = n_nodes++;
+    int l = lbvh_rec(lo, split), r = lbvh_rec(split + 1, hi);
+    nodes[id].left = l; nodes[id].right = r; nodes[id].count = hi - lo + 1; nodes[id].first = lo;
+    return id;
+}
+static box_t ref_box(int ref) { return ref < 0 ? pbox[order[~ref]] : nodes[ref].b; }
+static void fit_boxes(int ref) { if (ref < 0) return; fit_boxes(nodes[ref].left); fit_boxes(nodes[ref].right); box_t b = ref_box(nodes[ref].left), c = ref_box(nodes[ref].right); box_grow(&b, &c); nodes[ref].b = b; }
+static int ref_count(int ref) { return ref < 0 ? 1 : nodes[ref].count; }
+
+/* highest-differing-bit split found by binary search would be equivalent; the linear scan keeps the code obvious (n log n total) */
+static void build_lbvh(int bits, int extended) { morton_sort(bits, extended); n_nodes = 0; root = lbvh_rec(0, n_tris - 1); fit_boxes(root); }
+
+/* ---- binned SAH over the Morton order's primitives (order[] is permuted in place) ---- */
+static int sah_rec(int lo, int hi) {
+    if (lo == hi) return ~lo;
+    box_t cb = box_empty(), bb = box_empty();
+    for (int i = lo; i <= hi; i++) { const box_t *p = &pbox[order[i]]; box_grow(&bb, p); float c[3]; for (int k = 0; k < 3; k++) c[k] = 0.5f * (p->lo[k] + p->hi[k]); box_t q = {{c[0], c[1], c[2]}, {c[0], c[1], c[2]}}; box_grow(&cb, &q); }
+    int n = hi - lo + 1, best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
+    enum { NB = 32 };
+    for (int ax = 0; ax < 3; ax++) {
+        float ext = cb.hi[ax] - cb.lo[ax]; if (!(ext > 0)) continue;
+        box_t bins[NB]; int cnt[NB]; for (int b = 0; b < NB; b++) { bins[b] = box_empty(); cnt[b] = 0; }
+        for (int i = lo; i <= hi; i++) { const box_t *p = &pbox[order[i]]; float c = 0.5f * (p->lo[ax] + p->hi[ax]); int b = (int)((c - cb.lo[ax]) / ext * NB); if (b >= NB) b = NB - 1; box_grow(&bins[b], p); cnt[b]++; }
+        float ra[NB]; box_t acc = box_empty(); int rc[NB], c2 = 0;
+        for (int b = NB - 1; b > 0; b--) { box_grow(&acc, &bins[b]); c2 += cnt[b]; ra[b] = c2 ? box_area(&acc) : 0; rc[b] = c2; }
+        acc = box_empty(); int c1 = 0;
+        for (int b = 0; b < NB - 1; b++) { box_grow(&acc, &bins[b]); c1 += cnt[b]; if (!c1 || !rc[b + 1]) continue; float cost = box_area(&acc) * c1 + ra[b + 1] * rc[b + 1]; if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; } }
+    }
+    int mid;
+    if (best_axis < 0) mid = lo + n / 2 - 1 + (n == 1);
+    else {
+        float ext = cb.hi[best_axis] - cb.lo[best_axis]; int i = lo, j = hi;
+        while (i <= j) { const box_t *p = &pbox[order[i]]; float c = 0.5f * (p->lo[best_axis] + p->hi[best_axis]); int b = (int)((c - cb.lo[best_axis]) / ext * NB); if (b >= NB) b = NB - 1; if (b <= best_bin) i++; else { int t = order[i]; order[i] = order[j]; order[j] = t; j--; } }
+        mid = i - 1; if (mid < lo || mid >= hi) mid = lo + n / 2 - 1;
+    }
+    int id = n_nodes++;
+    int l = sah_rec(lo, mid), r = sah_rec(mid + 1, hi);
+    nodes[id].left = l; nodes[id].right = r; nodes[id].count = n; nodes[id].first = lo;
+    return id;
+}
+static void build_sah(void) { for (int i = 0; i < n_tris; i++) order[i] = i; n_nodes = 0; root = sah_rec(0, n_tris - 1); fit_boxes(root); }
+
+/* ---- PLOC (Meister & Bittner 2018), radius r, over the Morton order ---- */
+static void build_ploc(int bits, int radius) {
+    morton_sort(bits, 0); n_nodes = 0;
+    int n = n_tris; int *ref = malloc(sizeof(int) * n), *ref2 = malloc(sizeof(int) * n), *nn = malloc(sizeof(int) * n); box_t *cb = malloc(sizeof(box_t) * n), *cb2 = malloc(sizeof(box_t) * n);
+    for (int i = 0; i < n; i++) { ref[i] = ~i; cb[i] = pbox[order[i]]; }
+    while (n > 1) {
+        for (int i = 0; i < n; i++) { float best = FLT_MAX; int bj = -1; for (int j = i - radius; j <= i + radius; j++) { if (j == i || j < 0 || j >= n) continue; box_t u = cb[i]; box_grow(&u, &cb[j]); float a = box_area(&u); if (a < best) { best = a; bj = j; } } nn[i] = bj; }
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            int j = nn[i];
+            if (j >= 0 && nn[j] == i) { if (i < j) { int id = n_nodes++; nodes[id].left = ref[i]; nodes[id].right = ref[j]; nodes[id].count = ref_count(ref[i]) + ref_count(ref[j]); nodes[id].first = -1; box_t u = cb[i]; box_grow(&u, &cb[j]); nodes[id].b = u; ref2[m] = id; cb2[m] = u; m++; } }
+            else { ref2[m] = ref[i]; cb2[m] = cb[i]; m++; }
+        }
+        int *t = ref; ref = ref2; ref2 = t; box_t *tb = cb; cb = cb2; cb2 = tb; n = m;
+    }
+    root = ref[0]; free(ref); free(ref2); free(nn); free(cb); free(cb2);
+}
+
+/* ---- bottom-up treelet-style improvement experiments go here ---- */
+static double sah_cost_binary(void) { double c = 0; double ra = box_area(&nodes[root].b); for (int i = 0; i < n_nodes; i++) c += box_area(&nodes[i].b) / ra; return c; }
+
+/* ---- 8-wide collapse (k_collapse's rule) ---- */
+typedef struct { box_t cb[8]; int child[8]; /* >= 0 wide node, -1 empty, <= -2: leaf, first packed prim = -(v + 2) */ int cnt[8]; } wnode_t;
+static wnode_t *wn; static int n_wide; static int *packed; static int n_packed; static int leaf_max = 2;
+static void emit_leaves(int ref) { if (ref < 0) { packed[n_packed++] = order[~ref]; return; } emit_leaves(nodes[ref].left); emit_leaves(nodes[ref].right); }
+static int collapse(int ref) {
+    int id = n_wide++; int c[8], nc;
+    if (ref < 0) { c[0] = ref; nc = 1; } else { c[0] = nodes[ref].left; c[1] = nodes[ref].right; nc = 2; }
+    for (int phase = 0; phase < 2; phase++) { int limit = phase == 0 ? leaf_max : 1;
+        while (nc < 8) { int who = -1; float best = -1; for (int i = 0; i < nc; i++) if (ref_count(c[i]) > limit) { box_t b = ref_box(c[i]); float a = box_area(&b); if (a > best) { best = a; who = i; } } if (who < 0) break; int r = c[who]; c[who] = nodes[r].left; c[nc++] = nodes[r].right; } }
+    for (int i = 0; i < 8; i++) { wn[id].child[i] = -1; wn[id].cnt[i] = 0; }
+    for (int i = 0; i < nc; i++) { wn[id].cb[i] = ref_box(c[i]); if (ref_count(c[i]) > leaf_max) { int ch = collapse(c[i]); wn[id].child[i] = ch; } else { wn[id].child[i] = -(n_packed + 2); wn[id].cnt[i] = ref_count(c[i]); emit_leaves(c[i]); } }
+    return id;
+}
+
+/* ---- traversal: closest hit, children visited near to far ---- */
+static inline int tri_hit(const float o[3], const float d[3], int prim, float *t) {
+    const float *a = V[prim][0], *b = V[prim][1], *c = V[prim][2];
+    float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    float p[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    float det = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2]; if (det == 0) return 0; float inv = 1 / det;
+    float s[3] = {o[0] - a[0], o[1] - a[1], o[2] - a[2]}; float u = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inv; if (u < 0 || u > 1) return 0;
+    float q[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+    float v = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) * inv; if (v < 0 || u + v > 1) return 0;
+    float tt = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv; if (tt > 1e-4f && tt < *t) { *t = tt; return 1; } return 0;
+}
+static double nodes_visited, tris_tested;
+static void trace(const float o[3], const float d[3]) {
+    float inv[3] = {1 / d[0], 1 / d[1], 1 / d[2]}; float tbest = 1e30f;
+    struct { int node; float t; } stack[256]; int sp = 0; stack[sp].node = 0; stack[sp].t = 0; sp++;
+    while (sp) { sp--; if (stack[sp].t > tbest) continue; const wnode_t *w = &wn[stack[sp].node]; nodes_visited++;
+        int idx[8]; float te[8]; int nh = 0;
+        for (int i = 0; i < 8; i++) { if (w->child[i] == -1) continue; float t0 = 1e-4f, t1 = tbest; for (int k = 0; k < 3; k++) { float a = (w->cb[i].lo[k] - o[k]) * inv[k], b = (w->cb[i].hi[k] - o[k]) * inv[k]; if (a > b) { float x = a; a = b; b = x; } if (a > t0) t0 = a; if (b < t1) t1 = b; } if (t0 <= t1) { idx[nh] = i; te[nh] = t0; nh++; } }
+        for (int a = 1; a < nh; a++) { int ii = idx[a]; float tt = te[a]; int b = a - 1; while (b >= 0 && te[b] < tt) { idx[b + 1] = idx[b]; te[b + 1] = te[b]; b--; } idx[b + 1] = ii; te[b + 1] = tt; } /* descending: nearest last */
+        /* leaves first (they may shorten the ray), then push internal children far to near */
+        for (int a = nh - 1; a >= 0; a--) { int i = idx[a]; if (w->child[i] <= -2) { int first = -(w->child[i] + 2); for (int q = 0; q < w->cnt[i]; q++) { tris_tested++; tri_hit(o, d, packed[first + q], &tbest); } } }
+        for (int a = 0; a < nh; a++) { int i = idx[a]; if (w->child[i] >= 0 && te[a] <= tbest) { stack[sp].node = w->child[i]; stack[sp].t = te[a]; sp++; } }
+    }
+}
+
+static int n_rays; static float (*RO)[3], (*RD)[3];
+static void evaluate(const char *name) {
+    n_wide = 0; n_packed = 0; collapse(root);
+    nodes_visited = tris_tested = 0;
+    for (int i = 0; i < n_rays; i++) trace(RO[i], RD[i]);
+    printf("%-28s binary SAH %.1f | wide nodes %d | nodes/ray %.2f tris/ray %.2f | est. cost (250 n + 70 t) %.0f\n", name, sah_cost_binary(), n_wide, nodes_visited / n_rays, tris_tested / n_rays, (250 * nodes_visited + 70 * tris_tested) / n_rays);
+    fflush(stdout);
+}
+
+int main(int argc, char **argv) {
+    n_tris = argc > 1 ? atoi(argv[1]) : 1000000; n_rays = argc > 2 ? atoi(argv[2]) : 100000; leaf_max = argc > 3 ? atoi(argv[3]) : 2;
+    const char *only = argc > 4 ? argv[4] : "";
+    V = malloc(sizeof(*V) * n_tris); pbox = malloc(sizeof(box_t) * n_tris); kv = malloc(sizeof(kv_t) * n_tris); order = malloc(sizeof(int) * n_tris);
+    nodes = malloc(sizeof(bnode_t) * n_tris); wn = malloc(sizeof(wnode_t) * n_tris); packed = malloc(sizeof(int) * n_tris);
+    const float extent = 0.01f;
+    for (int i = 0; i < n_tris; i++) { float c[3], e1[3], e2[3]; for (int k = 0; k < 3; k++) { c[k] = rndf(); e1[k] = (rndf() * 2 - 1) * extent; e2[k] = (rndf() * 2 - 1) * extent; }
+        box_t b = box_empty(); for (int k = 0; k < 3; k++) { V[i][0][k] = c[k] - (e1[k] + e2[k]) / 3; V[i][1][k] = V[i][0][k] + e1[k]; V[i][2][k] = V[i][0][k] + e2[k]; for (int v = 0; v < 3; v++) { if (V[i][v][k] < b.lo[k]) b.lo[k] = V[i][v][k]; if (V[i][v][k] > b.hi[k]) b.hi[k] = V[i][v][k]; } } pbox[i] = b; }
+    RO = malloc(sizeof(*RO) * n_rays); RD = malloc(sizeof(*RD) * n_rays);
+    for (int i = 0; i < n_rays; i++) { for (int k = 0; k < 3; k++) RO[i][k] = rndf(); float z = rndf() * 2 - 1, phi = rndf() * 6.2831853f, r = sqrtf(fmaxf(0, 1 - z * z)); RD[i][0] = r * cosf(phi); RD[i][1] = r * sinf(phi); RD[i][2] = z; }
+    printf("soup %d triangles, %d rays, leaf_max %d\n", n_tris, n_rays, leaf_max);
+    if (!*only || strstr(only, "lbvh")) { build_lbvh(32, 0); evaluate("lbvh 32-bit"); }
+    if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
+    if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
+    if (!*only || strstr(only, "ploc")) { build_ploc(32, 8); evaluate("ploc r8"); }
+    return 0;
+}
