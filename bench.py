@@ -26,6 +26,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context exists (luisa-compute-rs_b200/__init__.py says why)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
@@ -221,13 +223,12 @@ def bind_to_gpu_numa_node(torch, local_rank):
     platform reports no NUMA node for the device (single-socket hosts, containers that hide /sys)."""
     info = {"numa_node": None, "cpus": None}
     try:
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bdf is None:
-            import ctypes
-            buf = ctypes.create_string_buffer(32)
-            rt = ctypes.CDLL("libcudart.so.12")
-            if rt.cudaDeviceGetPCIBusId(buf, 32, local_rank) == 0:
-                bdf = buf.value.decode()
+        import ctypes
+        bdf = None
+        buf = ctypes.create_string_buffer(32)
+        rt = ctypes.CDLL("libcudart.so.12")
+        if rt.cudaDeviceGetPCIBusId(buf, 32, local_rank) == 0:
+            bdf = buf.value.decode()   # "0000:1b:00.0" (torch's pci_bus_id property is the bus number alone)
         if not bdf:
             return info
         path = f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node"
@@ -280,7 +281,10 @@ def pcie_probe(torch, dist, world, mib=512, reps=3):
 def e2e_reference_api(dev, shader, accel, rb, hb, rays_np, hits_np, n, lanes, chunk_rays):
     """One end-to-end pass with HOST buffers through DeviceInterface calls only: per chunk a BufferUpload on the upload stream, the
     ShaderDispatch over that chunk's buffer views on the compute stream, a BufferDownload on the download stream, ordered by two
-    timeline events — what a luisa-compute-rs program does with three Streams and two Events."""
+    timeline events — what a luisa-compute-rs program does with three Streams and two Events.  One host thread: a BufferUpload only
+    returns once its source has been read (the snapshot contract, cpu/stream.rs:33-64), so the link idles for the ~0.25 ms the other
+    five calls of a chunk take.  (A second Python thread for those calls was measured and is slower — 543 Mrays/s against 750-910: the
+    GIL changes hands at millisecond granularity; profiles/r02s_bench.json.)"""
     up, run, down, ev_up, ev_run = lanes
     base = e2e_reference_api.serial
     c = 0
@@ -335,7 +339,8 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
     if world > 1:
         pt.probe_cost()
     history = pt.balance(balance_passes) if world > 1 else []
-    ms, gathered, n_dispatch = pt.frame(spp, first_frame=0)
+    recuts = 6 if world > 1 else 0
+    ms, gathered, n_dispatch = pt.frame(spp, first_frame=0, recuts=recuts)
     times = pt.all_times(ms)
     rays = pt.counters_t.clone()
     if world > 1:
@@ -352,7 +357,8 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
                "frame_ms": total, "frame_ms_per_rank": [round(t, 2) for t in times], "scaling": "strong",
                "mrays_per_s": float(rays.sum().item()) / total / 1e3,
                "msamples_per_s": pt.width * pt.height * n_dispatch * spp_per_dispatch / total / 1e3,
-               "partition": "contiguous ranges of the Morton-ordered 64x64 tiles, cut to equal measured cost" if world > 1 else "all tiles on one GPU",
+               "partition": "contiguous ranges of the Morton-ordered 64x64 tiles, cut to equal measured cost and re-cut inside the frame (tiles that change owner take their accumulators along)" if world > 1 else "all tiles on one GPU",
+               "recuts_in_frame": [{"imbalance_before": r[0], "tiles_moved_by_rank0": r[1]} for r in getattr(pt, "recut_log", [])],
                "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes": [{"imbalance": round(h[0], 3), "tiles_per_rank": h[1], "ms_per_rank": h[2]} for h in history],
                "one_pass_ms_per_rank": [round(t, 3) for t in render_only], "imbalance_max_over_mean": round(imbalance, 4),
                "limiter": ("load imbalance between ranks" if imbalance > 1.08 else "per-rank efficiency: the ranks that own the expensive tiles own few of them (70-160 tiles = 3-6 waves of resident threads per dispatch), so dispatch tails weigh more than on one GPU"),
@@ -393,7 +399,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     os.environ["LC_B200_DEVICE"] = str(local_rank)
-    host_binding = bind_to_gpu_numa_node(torch, local_rank)   # before any pinned allocation
+    # before any pinned allocation; only when several ranks share the host (at N = 1 the CPU legs keep every core the box gives)
+    host_binding = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else {"numa_node": None, "cpus": None, "note": "not bound at N = 1"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

@@ -2,11 +2,12 @@
 // kernel translation units (radix_sort.cu, bvh_build.cu, trace.cu).
 #pragma once
 #include "rt_types.cuh"
+#include <atomic>
 #include <cstddef>
 
 namespace lcb {
 
-struct LaunchCounter { unsigned long long count = 0; };
+struct LaunchCounter { std::atomic<unsigned long long> count{0}; };  // streams of one device dispatch from several host threads
 
 // ---- radix_sort.cu -------------------------------------------------------------------------
 size_t sort_scratch_bytes(uint32_t n, int passes);

@@ -341,7 +341,7 @@ struct DeviceObj {
 template <class T> T *as(uint64_t h) { if (h == 0 || h == LCB_INVALID_HANDLE) fatal("invalid resource handle"); return reinterpret_cast<T *>(h); }
 DeviceObj *dev_of(lcb_device d) { return as<DeviceObj>(d.id); }
 void bind(DeviceObj *d) { CUDA_CHECK(cudaSetDevice(d->ordinal)); }
-void flush_launches(DeviceObj *d) { g_launches += d->lc.count; d->lc.count = 0; }
+void flush_launches(DeviceObj *d) { g_launches += d->lc.count.exchange(0); }
 
 // ---- buffers -----------------------------------------------------------------------------------
 lcb_created_buffer create_buffer(lcb_device dev, const void *ir_type, size_t count, void *ext_mem) {
@@ -743,7 +743,15 @@ void dispatch(lcb_device dev, lcb_stream sh, lcb_command_list list, lcb_dispatch
         cudaPointerAttributes attr{};
         const bool pinned = n >= (size_t(1) << 20) && cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) (void)cudaGetLastError();
-        if (pinned && (!direct_copies.empty() || cudaStreamQuery(st) == cudaSuccess)) {
+        // "idle" tolerates what drains in microseconds (the signal kernel of the previous chunk's timeline event): a short poll, not one query
+        auto idle_soon = [&] {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (;;) {
+                if (cudaStreamQuery(st) == cudaSuccess) return true;
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(100)) return false;
+            }
+        };
+        if (pinned && (!direct_copies.empty() || idle_soon())) {
             CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st));
             cudaEvent_t ev; CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));  // spin-wait: a blocking-sync wake-up cost ~0.4 ms per 64 MB chunk (profiles/r02j_e2e_probe.txt)
             CUDA_CHECK(cudaEventRecord(ev, st));

@@ -138,3 +138,40 @@ def untile_ranges(gathered, width, height, bounds, tile=TILE):
         idx, valid = pixels_of_tiles(tx[b0:b1], ty[b0:b1], width, height, tile)
         img[idx[valid]] = gathered[r, : (b1 - b0) * tile * tile][valid]
     return img.reshape(height, width, channels)
+
+
+# ---- re-cutting the ranges while a frame accumulates ---------------------------------------------------------------------------------
+# A frame of many dispatches need not live with the cut it started with: every few dispatches the ranks exchange their times, the cost
+# map is refined and the ranges are re-cut.  A tile that changes owner takes its accumulator along (one point-to-point copy from the old
+# owner to the new one), so every pixel still receives its samples one after the other on top of the same running sum — the image stays
+# the same bits.  Every rank keeps a buffer for the WHOLE Morton-ordered frame and is authoritative for its own range only.
+
+def migration_plan(old_bounds, new_bounds):
+    """[(src_rank, dst_rank, first_tile, end_tile)]: the tiles of [first, end) belonged to src under old_bounds and belong to dst under
+    new_bounds (src != dst).  Every rank computes the same plan."""
+    plan = []
+    world = len(old_bounds) - 1
+    for src in range(world):
+        for dst in range(world):
+            if src == dst:
+                continue
+            a = max(int(old_bounds[src]), int(new_bounds[dst])); b = min(int(old_bounds[src + 1]), int(new_bounds[dst + 1]))
+            if b > a:
+                plan.append((src, dst, a, b))
+    return plan
+
+
+def migrate_ranges(frame_buf, old_bounds, new_bounds, rank, dist_module, elems_per_tile):
+    """Move the accumulators of re-assigned tiles between the ranks' full-frame buffers (torch tensor, first dimension = tiles *
+    elems_per_tile in Morton order).  One batch of point-to-point transfers; returns the number of tiles this rank sent or received."""
+    ops, moved = [], 0
+    for src, dst, a, b in migration_plan(old_bounds, new_bounds):
+        piece = frame_buf[a * elems_per_tile: b * elems_per_tile]
+        if rank == src:
+            ops.append(dist_module.P2POp(dist_module.isend, piece, dst)); moved += b - a
+        elif rank == dst:
+            ops.append(dist_module.P2POp(dist_module.irecv, piece, src)); moved += b - a
+    if ops:
+        for w in dist_module.batch_isend_irecv(ops):
+            w.wait()
+    return moved

@@ -7,8 +7,11 @@ csrc/ir_lower.cpp), and ONE NCCL all-gather assembles the framebuffer: the only 
 
 Partition (sharding.py): rank r owns a contiguous range of the Morton-ordered tiles, cut so that every range costs the same.  The cost
 map is what a progressive renderer gets for free — each pass's per-rank time, exchanged with one tiny all-gather — and is refined over
-a few short balancing passes before the frame starts (their samples are discarded; they are part of the warm-up, not of the frame).
-Random streams are keyed by the global pixel index and the frame number, so the image is the same bits whatever the cut and whatever N.
+a few short balancing passes before the frame starts (their samples are discarded; they are part of the warm-up, not of the frame) and
+keeps being refined WHILE the frame accumulates: every few dispatches the ranges are re-cut from the ranks' own times and the tiles
+that change owner take their accumulators along (sharding.migrate_ranges).  Random streams are keyed by the global pixel index and the
+frame number and every pixel's samples are added in the same order onto the same running sum, so the image is the same bits whatever
+the cuts and whatever N.
 
 torch is plumbing here: device memory for the tile buffer, CUDA events, torch.distributed for NCCL.
 """
@@ -80,18 +83,18 @@ class TiledPathTracer:
         self.out_t = self.out = None
         self.set_bounds(sharding.balanced_bounds(self.cost, world))
 
-    def set_bounds(self, bounds):
-        """this rank renders tiles [bounds[rank], bounds[rank + 1]) of the Morton order; tile buffers are padded to the longest range"""
+    def set_bounds(self, bounds, clear=True):
+        """this rank renders tiles [bounds[rank], bounds[rank + 1]) of the Morton order.  The tile buffer holds the WHOLE frame in Morton
+        order (133 MB at 4K; a rank is authoritative for its own range only) plus one longest-possible range of padding, so that the
+        equal-count all-gather can always read `cap` tiles from the start of any range."""
         torch = self.torch
         self.bounds = np.asarray(bounds, np.int64)
         self.b0, self.b1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        cap = int(np.max(np.diff(self.bounds))) * self.tile * self.tile
-        if self.out_t is None or self.out_t.shape[0] != cap:
-            if self.out is not None:
-                self.out.destroy()
+        if self.out_t is None:
+            cap = 2 * self.n_tiles * self.tile * self.tile
             self.out_t = torch.zeros((cap, 4), dtype=torch.float32, device="cuda")
             self.out = self.dev.wrap_device_memory(self.out_t.data_ptr(), cap, 16, 16)
-        else:
+        elif clear:
             self.out_t.zero_()
         torch.cuda.synchronize()
 
@@ -104,7 +107,7 @@ class TiledPathTracer:
             a, b = int(edges[li]), int(edges[li + 1])
             if b == a:
                 continue
-            lane.submit([self.shader.dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view(a * tile * tile, (b - a) * tile * tile), self.accel,
+            lane.submit([self.shader.dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view((self.b0 + a) * tile * tile, (b - a) * tile * tile), self.accel,
                                                     np.array([self.width, self.height, first_frame + i, b - a], np.uint32), self.counters) for i in range(n_dispatch)])
         self.serial += 1
         for lane, join in zip(self.lanes[1:], self.joins):
@@ -136,10 +139,6 @@ class TiledPathTracer:
         for j in range(pieces_per_rank):
             piece = j * self.world + self.rank
             self.b0, self.b1 = int(edges[piece]), int(edges[piece + 1])
-            cap_needed = (self.b1 - self.b0) * self.tile * self.tile
-            if self.out_t.shape[0] < cap_needed:
-                self.bounds, self.b0, self.b1 = saved
-                return False   # tile buffer too small for a probe piece (cannot happen with equal initial ranges)
             mine.append(self.timed(lambda: self.render(1, frame0 + j)) if self.b1 > self.b0 else 0.0)
         self.bounds, self.b0, self.b1 = saved
         t = torch.tensor(mine, device="cuda", dtype=torch.float32)
@@ -165,35 +164,64 @@ class TiledPathTracer:
             ms = self.timed(lambda: self.render(dispatches, frame0 + p * dispatches))
             times = self.all_times(ms)
             history.append((max(times) / (sum(times) / len(times)), [int(x) for x in np.diff(self.bounds)], [round(t, 2) for t in times]))
-            self.cost = sharding.refine_cost(self.cost, self.bounds, times)
-            self.set_bounds(sharding.balanced_bounds(self.cost, self.world))
+            self.recut(times)   # the same path the frame takes between its portions (also warms up the point-to-point connections)
+        self.out_t.zero_()
         return history
 
     def gather(self):
-        """the one collective: all-gather of the padded per-rank tile buffers (stream-ordered after the render on the default stream)"""
+        """the one collective of the result path: all-gather of every rank's range, padded to the longest range (equal counts), read from
+        the rank's full-frame buffer (stream-ordered after the render on the default stream)"""
         torch = self.torch
+        T = self.tile * self.tile
+        cap = int(np.max(np.diff(self.bounds))) * T
+        local = self.out_t[self.b0 * T: self.b0 * T + cap]
         if self.world == 1:
-            return self.out_t[None]
-        if getattr(self, "_gathered", None) is None or self._gathered.shape[1] != self.out_t.shape[0]:
-            self._gathered = torch.empty((self.world,) + tuple(self.out_t.shape), dtype=self.out_t.dtype, device="cuda")
+            return local[None]
+        if getattr(self, "_gathered", None) is None or self._gathered.shape[1] != cap:
+            self._gathered = torch.empty((self.world, cap, 4), dtype=self.out_t.dtype, device="cuda")
         with torch.cuda.stream(self.ext):
-            self.dist.all_gather_into_tensor(self._gathered.view(-1), self.out_t.view(-1))
+            self.dist.all_gather_into_tensor(self._gathered.view(-1), local.reshape(-1))
         return self._gathered
 
-    def frame(self, spp, first_frame=0):
-        """one frame: render spp samples per pixel AND gather the framebuffer, timed as one region on the device; returns (ms, gathered)"""
+    def recut(self, times):
+        """refine the cost map from the ranks' times for the current ranges, re-cut, and move the accumulators of the tiles that change
+        owner (in-frame re-balancing); returns the number of tiles this rank sent or received"""
+        self.cost = sharding.refine_cost(self.cost, self.bounds, times)
+        new_bounds = sharding.balanced_bounds(self.cost, self.world)
+        if np.array_equal(new_bounds, self.bounds):
+            return 0
+        with self.torch.cuda.stream(self.ext):
+            moved = sharding.migrate_ranges(self.out_t, self.bounds, new_bounds, self.rank, self.dist, self.tile * self.tile)
+        self.set_bounds(new_bounds, clear=False)
+        return moved
+
+    def frame(self, spp, first_frame=0, recuts=0):
+        """one frame: render spp samples per pixel AND gather the framebuffer, timed as one region on the device; returns (ms, gathered,
+        dispatches).  recuts > 0 (world > 1): the dispatches are issued in recuts + 1 portions and the ranges are re-cut between them
+        from each portion's per-rank device time (recut()); the exchanges and migrations are inside the timed region."""
+        torch = self.torch
         n_dispatch = max(1, spp // self.spp_per_dispatch)
-        self.out_t.zero_(); self.counters_t.zero_(); self.torch.cuda.synchronize()
+        self.out_t.zero_(); self.counters_t.zero_(); torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
-        box = {}
-
-        def work():
-            self.render(n_dispatch, first_frame)
-            box["g"] = self.gather()
-        ms = self.timed(work)
-        self.torch.cuda.synchronize()
-        return ms, box["g"], n_dispatch
+        parts = 1 + (recuts if self.world > 1 else 0)
+        edges = np.linspace(0, n_dispatch, min(parts, n_dispatch) + 1).astype(int)
+        self.recut_log = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.ext)
+        for k in range(len(edges) - 1):
+            a, b = int(edges[k]), int(edges[k + 1])
+            if k + 2 == len(edges):          # last portion: nothing left to re-balance for
+                self.render(b - a, first_frame + a)
+            else:
+                ms = self.timed(lambda: self.render(b - a, first_frame + a))
+                times = self.all_times(ms)
+                moved = self.recut(times)
+                self.recut_log.append((round(max(times) / (sum(times) / len(times)), 3), moved))
+        g = self.gather()
+        e1.record(self.ext); self.s.synchronize()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), g, n_dispatch
 
     def image(self, gathered):
         return sharding.untile_ranges(gathered.cpu().numpy(), self.width, self.height, self.bounds)

@@ -141,3 +141,40 @@ def test_gloo_world2_gather_of_unequal_contiguous_ranges(tmp_path):
     want = np.stack([px, px * 2, px % 7, np.ones_like(px)], 1).astype(np.float32).reshape(h, w, 4)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"img{r}.npy"), want)
+
+
+def test_migration_plan_moves_every_reassigned_tile_exactly_once():
+    rng = np.random.default_rng(3)
+    for world in (2, 4, 8):
+        for _ in range(20):
+            n = 500
+            old = np.concatenate([[0], np.sort(rng.choice(np.arange(1, n), world - 1, replace=False)), [n]])
+            new = np.concatenate([[0], np.sort(rng.choice(np.arange(1, n), world - 1, replace=False)), [n]])
+            owner_old = np.searchsorted(old, np.arange(n), side="right") - 1
+            owner_new = np.searchsorted(new, np.arange(n), side="right") - 1
+            moved = np.zeros(n, int)
+            for src, dst, a, b in sh.migration_plan(old, new):
+                assert src != dst and np.all(owner_old[a:b] == src) and np.all(owner_new[a:b] == dst)
+                moved[a:b] += 1
+            assert np.array_equal(moved, (owner_old != owner_new).astype(int))
+
+
+def _migrate_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_tiles, per = 40, 6
+    old, new = np.array([0, 25, 40]), np.array([0, 12, 40])
+    buf = torch.full((n_tiles * per,), -1.0)                      # a rank is authoritative for its own range only
+    buf[old[rank] * per: old[rank + 1] * per] = torch.arange(old[rank] * per, old[rank + 1] * per, dtype=torch.float32) + 1000 * rank
+    moved = sh.migrate_ranges(buf, old, new, rank, dist, per)
+    assert moved == 13
+    mine = buf[new[rank] * per: new[rank + 1] * per]
+    want = torch.arange(new[rank] * per, new[rank + 1] * per, dtype=torch.float32) + 1000 * torch.from_numpy((np.arange(new[rank] * per, new[rank + 1] * per) // per >= 25).astype(np.float32))
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([bool(torch.equal(mine, want))]))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_accumulators_follow_their_tiles_when_the_ranges_are_recut(tmp_path):
+    mp.spawn(_migrate_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all(bool(np.load(tmp_path / f"ok{r}.npy")[0]) for r in range(2))

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
     ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--balance-passes", type=int, default=6, help="0: equal tile counts per rank")
+    ap.add_argument("--recuts", type=int, default=6, help="re-cuts of the ranges inside the frame (world > 1)")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's equal-count range in this single process (tuning aid)")
     ap.add_argument("--precise", action="store_true", help="compile the kernel without enable_fast_math (the frontend default is on)")
     ap.add_argument("--lowering", default="auto", choices=["auto", "direct", "wavefront"])
@@ -58,7 +59,7 @@ def main():
     if world > 1 and a.balance_passes:
         pt.probe_cost()
     history = pt.balance(a.balance_passes) if world > 1 and a.balance_passes else []
-    ms, gathered, n_dispatch = pt.frame(a.spp, 0)
+    ms, gathered, n_dispatch = pt.frame(a.spp, 0, recuts=a.recuts if world > 1 else 0)
     times = pt.all_times(ms)
     rays = pt.counters_t.clone()
     if world > 1:
@@ -71,6 +72,7 @@ def main():
                "frame_ms": round(max(times), 3), "frame_ms_per_rank": [round(t, 2) for t in times], "streams": len(pt.lanes), "block": a.block, "fast_math": not a.precise, "lowering": a.lowering,
                "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)], "balance_passes": [{"imbalance": round(h[0], 3), "tiles_per_rank": h[1], "ms_per_rank": h[2]} for h in history], "rays": total_rays,
                "mrays_per_s": round(total_rays / max(times) / 1e3, 1), "mean_radiance": round(float(rgb.mean()), 5),
+               "recuts_in_frame": [{"imbalance_before": r[0], "tiles_moved_by_rank0": r[1]} for r in getattr(pt, "recut_log", [])],
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img)}
         os.write(real_stdout, (json.dumps(res) + "\n").encode())
         if a.save:

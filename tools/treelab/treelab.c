@@ -125,8 +125,8 @@ static void build_ploc(int bits, int radius) {
 /* ---- bottom-up treelet-style improvement experiments go here ---- */
 static double sah_cost_binary(void) { double c = 0; double ra = box_area(&nodes[root].b); for (int i = 0; i < n_nodes; i++) c += box_area(&nodes[i].b) / ra; return c; }
 
-/* ---- 8-wide collapse (k_collapse's rule) ---- */
-typedef struct { box_t cb[8]; int child[8]; /* >= 0 wide node, -1 empty, <= -2: leaf, first packed prim = -(v + 2) */ int cnt[8]; } wnode_t;
+/* ---- 8-wide collapse (k_collapse's rule, including the greedy octant slot assignment and the 8-bit plane quantisation) ---- */
+typedef struct { box_t cb[8]; box_t qb[8]; int child[8]; /* >= 0 wide node, -1 empty, <= -2: leaf, first packed prim = -(v + 2) */ int cnt[8]; } wnode_t;
 static wnode_t *wn; static int n_wide; static int *packed; static int n_packed; static int leaf_max = 2;
 static void emit_leaves(int ref) { if (ref < 0) { packed[n_packed++] = order[~ref]; return; } emit_leaves(nodes[ref].left); emit_leaves(nodes[ref].right); }
 static int collapse(int ref) {
@@ -134,12 +134,24 @@ static int collapse(int ref) {
     if (ref < 0) { c[0] = ref; nc = 1; } else { c[0] = nodes[ref].left; c[1] = nodes[ref].right; nc = 2; }
     for (int phase = 0; phase < 2; phase++) { int limit = phase == 0 ? leaf_max : 1;
         while (nc < 8) { int who = -1; float best = -1; for (int i = 0; i < nc; i++) if (ref_count(c[i]) > limit) { box_t b = ref_box(c[i]); float a = box_area(&b); if (a > best) { best = a; who = i; } } if (who < 0) break; int r = c[who]; c[who] = nodes[r].left; c[nc++] = nodes[r].right; } }
+    box_t cbx[8], nb = box_empty(); for (int i = 0; i < nc; i++) { cbx[i] = ref_box(c[i]); box_grow(&nb, &cbx[i]); }
+    /* greedy slot assignment: global minimum of dot(child centre - node centre, sign_s) */
+    int slot_of[8], used = 0; for (int i = 0; i < nc; i++) slot_of[i] = -1;
+    for (int it = 0; it < nc; it++) { float best = FLT_MAX; int bc = -1, bs = -1;
+        for (int i = 0; i < nc; i++) { if (slot_of[i] >= 0) continue; float cc[3]; for (int k = 0; k < 3; k++) cc[k] = 0.5f * (cbx[i].lo[k] + cbx[i].hi[k]) - 0.5f * (nb.lo[k] + nb.hi[k]);
+            for (int sl = 0; sl < 8; sl++) { if (used >> sl & 1) continue; float cost = ((sl & 1) ? -cc[0] : cc[0]) + ((sl & 2) ? -cc[1] : cc[1]) + ((sl & 4) ? -cc[2] : cc[2]); if (cost < best) { best = cost; bc = i; bs = sl; } } }
+        slot_of[bc] = bs; used |= 1 << bs; }
     for (int i = 0; i < 8; i++) { wn[id].child[i] = -1; wn[id].cnt[i] = 0; }
-    for (int i = 0; i < nc; i++) { wn[id].cb[i] = ref_box(c[i]); if (ref_count(c[i]) > leaf_max) { int ch = collapse(c[i]); wn[id].child[i] = ch; } else { wn[id].child[i] = -(n_packed + 2); wn[id].cnt[i] = ref_count(c[i]); emit_leaves(c[i]); } }
+    float scale[3]; for (int k = 0; k < 3; k++) { float sc = (nb.hi[k] - nb.lo[k]) / 255.0f; int e; float m = frexpf(sc, &e); scale[k] = sc > 0 ? ldexpf(1.0f, m == 0.5f ? e - 1 : e) : 1e-30f; }
+    /* children are collapsed in slot order so that packed leaves and node ids follow the device's layout */
+    for (int sl = 0; sl < 8; sl++) { int i = -1; for (int j = 0; j < nc; j++) if (slot_of[j] == sl) i = j; if (i < 0) continue;
+        wn[id].cb[sl] = cbx[i];
+        for (int k = 0; k < 3; k++) { wn[id].qb[sl].lo[k] = nb.lo[k] + floorf((cbx[i].lo[k] - nb.lo[k]) / scale[k]) * scale[k]; wn[id].qb[sl].hi[k] = nb.lo[k] + ceilf((cbx[i].hi[k] - nb.lo[k]) / scale[k]) * scale[k]; }
+        if (ref_count(c[i]) > leaf_max) { int ch = collapse(c[i]); wn[id].child[sl] = ch; } else { wn[id].child[sl] = -(n_packed + 2); wn[id].cnt[sl] = ref_count(c[i]); emit_leaves(c[i]); } }
     return id;
 }
 
-/* ---- traversal: closest hit, children visited near to far ---- */
+/* ---- traversal: closest hit ---- */
 static inline int tri_hit(const float o[3], const float d[3], int prim, float *t) {
     const float *a = V[prim][0], *b = V[prim][1], *c = V[prim][2];
     float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
@@ -151,26 +163,76 @@ static inline int tri_hit(const float o[3], const float d[3], int prim, float *t
     float tt = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv; if (tt > 1e-4f && tt < *t) { *t = tt; return 1; } return 0;
 }
 static double nodes_visited, tris_tested;
-static void trace(const float o[3], const float d[3]) {
+static int opt_quant = 0, opt_postpone = 0, opt_nearest = 0, opt_gtmin = 0, opt_sorted = 0, opt_childcull = 0;
+static inline int box_hit(const box_t *b, const float o[3], const float inv[3], float tmax, float *tn) {
+    float t0 = 1e-4f, t1 = tmax; for (int k = 0; k < 3; k++) { float a = (b->lo[k] - o[k]) * inv[k], c = (b->hi[k] - o[k]) * inv[k]; if (a > c) { float x = a; a = c; c = x; } if (a > t0) t0 = a; if (c < t1) t1 = c; } *tn = t0; return t0 <= t1;
+}
+/* ideal: children near to far by entry distance, leaves of a node before its internal children */
+static void trace_ideal(const float o[3], const float d[3]) {
     float inv[3] = {1 / d[0], 1 / d[1], 1 / d[2]}; float tbest = 1e30f;
     struct { int node; float t; } stack[256]; int sp = 0; stack[sp].node = 0; stack[sp].t = 0; sp++;
     while (sp) { sp--; if (stack[sp].t > tbest) continue; const wnode_t *w = &wn[stack[sp].node]; nodes_visited++;
         int idx[8]; float te[8]; int nh = 0;
-        for (int i = 0; i < 8; i++) { if (w->child[i] == -1) continue; float t0 = 1e-4f, t1 = tbest; for (int k = 0; k < 3; k++) { float a = (w->cb[i].lo[k] - o[k]) * inv[k], b = (w->cb[i].hi[k] - o[k]) * inv[k]; if (a > b) { float x = a; a = b; b = x; } if (a > t0) t0 = a; if (b < t1) t1 = b; } if (t0 <= t1) { idx[nh] = i; te[nh] = t0; nh++; } }
+        for (int i = 0; i < 8; i++) { if (w->child[i] == -1) continue; float t0; if (box_hit(opt_quant ? &w->qb[i] : &w->cb[i], o, inv, tbest, &t0)) { idx[nh] = i; te[nh] = t0; nh++; } }
         for (int a = 1; a < nh; a++) { int ii = idx[a]; float tt = te[a]; int b = a - 1; while (b >= 0 && te[b] < tt) { idx[b + 1] = idx[b]; te[b + 1] = te[b]; b--; } idx[b + 1] = ii; te[b + 1] = tt; } /* descending: nearest last */
-        /* leaves first (they may shorten the ray), then push internal children far to near */
         for (int a = nh - 1; a >= 0; a--) { int i = idx[a]; if (w->child[i] <= -2) { int first = -(w->child[i] + 2); for (int q = 0; q < w->cnt[i]; q++) { tris_tested++; tri_hit(o, d, packed[first + q], &tbest); } } }
         for (int a = 0; a < nh; a++) { int i = idx[a]; if (w->child[i] >= 0 && te[a] <= tbest) { stack[sp].node = w->child[i]; stack[sp].t = te[a]; sp++; } }
     }
 }
+/* the device's loop (trace.cu k_trace): node group G = hit internal children of one node in octant priority, primitive group Gt = hit
+ * leaf primitives in slot order; one node step when Gt is empty, then ONE triangle; the rest of Gt is postponed (pushed) while G has work */
+typedef struct { int node; uint32_t bits; int kind; /* 0 node group: bits over priorities 0..7, 1 prim group: bits over the node's packed prims (<= 24) */ int pbase; int nearest; float tmin; float te[8]; } grp_t;
+static void trace_device(const float o[3], const float d[3]) {
+    float inv[3] = {1 / d[0], 1 / d[1], 1 / d[2]}; float tbest = 1e30f;
+    const int octinv = ((d[0] >= 0) ? 1 : 0) | ((d[1] >= 0) ? 2 : 0) | ((d[2] >= 0) ? 4 : 0);   /* bit set = positive */
+    grp_t stack[512]; int sp = 0; grp_t G = {-1, 1u << 7, 0, 0, -1, 0.f, {0}}, Gt = {0, 0, 1, 0, -1, 0.f, {0}};  /* G.node = -1: the root's pseudo parent */
+    for (;;) {
+        if (Gt.bits == 0 && G.bits != 0) {
+            int pr = 31 - __builtin_clz(G.bits);
+            if (opt_nearest && G.nearest >= 0) { pr = G.nearest; G.nearest = -1; }
+            if (opt_sorted) { float bt = FLT_MAX; for (int q = 0; q < 8; q++) if ((G.bits >> q & 1) && G.te[q] < bt) { bt = G.te[q]; pr = q; } if (bt > tbest) { G.bits = 0; goto after_node; } }
+            if (opt_childcull) { while (G.bits && G.te[31 - __builtin_clz(G.bits)] > tbest) G.bits &= ~(1u << (31 - __builtin_clz(G.bits))); if (!G.bits) goto after_node; pr = 31 - __builtin_clz(G.bits); }
+            G.bits &= ~(1u << pr);
+            int nid = G.node < 0 ? 0 : wn[G.node].child[pr ^ octinv];
+            if (G.bits) stack[sp++] = G;
+            const wnode_t *w = &wn[nid]; nodes_visited++;
+            G.node = nid; G.bits = 0; G.kind = 0; Gt.node = nid; Gt.bits = 0; Gt.kind = 1;
+            int poff = 0, pbase = -1; float te[8]; int hit[8];
+            for (int i = 0; i < 8; i++) { hit[i] = 0; if (w->child[i] == -1) continue; hit[i] = box_hit(opt_quant ? &w->qb[i] : &w->cb[i], o, inv, tbest, &te[i]); }
+            G.nearest = -1; G.tmin = FLT_MAX;
+            for (int i = 0; i < 8; i++) if (hit[i] && w->child[i] >= 0) { G.bits |= 1u << (i ^ octinv); G.te[i ^ octinv] = te[i]; if (te[i] < G.tmin) { G.tmin = te[i]; G.nearest = i ^ octinv; } }
+            for (int i = 0; i < 8; i++) { if (w->child[i] <= -2) { if (pbase < 0) pbase = -(w->child[i] + 2); if (hit[i]) for (int q = 0; q < w->cnt[i]; q++) Gt.bits |= 1u << (poff + q); poff += w->cnt[i]; } }
+            Gt.pbase = pbase;
+        }
+        after_node:
+        if (Gt.bits != 0) {
+            int b = __builtin_ctz(Gt.bits); Gt.bits &= Gt.bits - 1; tris_tested++; tri_hit(o, d, packed[Gt.pbase + b], &tbest);
+            if (opt_postpone && Gt.bits != 0 && G.bits != 0) { stack[sp++] = Gt; Gt.bits = 0; }
+        }
+        if (Gt.bits == 0 && G.bits == 0) { if (!sp) break; grp_t e = stack[--sp]; if (e.kind == 0) { if (opt_gtmin && e.tmin > tbest) continue; G = e; } else Gt = e; }
+    }
+}
+static void (*trace)(const float o[3], const float d[3]) = trace_ideal;
 
 static int n_rays; static float (*RO)[3], (*RD)[3];
-static void evaluate(const char *name) {
-    n_wide = 0; n_packed = 0; collapse(root);
+static void run_rays(const char *tag) {
     nodes_visited = tris_tested = 0;
     for (int i = 0; i < n_rays; i++) trace(RO[i], RD[i]);
-    printf("%-28s binary SAH %.1f | wide nodes %d | nodes/ray %.2f tris/ray %.2f | est. cost (250 n + 70 t) %.0f\n", name, sah_cost_binary(), n_wide, nodes_visited / n_rays, tris_tested / n_rays, (250 * nodes_visited + 70 * tris_tested) / n_rays);
+    printf("    %-44s nodes/ray %6.2f tris/ray %6.2f | est. cost (250 n + 70 t) %.0f\n", tag, nodes_visited / n_rays, tris_tested / n_rays, (250 * nodes_visited + 70 * tris_tested) / n_rays);
     fflush(stdout);
+}
+static void evaluate(const char *name) {
+    n_wide = 0; n_packed = 0; collapse(root);
+    printf("%-28s binary SAH %.1f | wide nodes %d\n", name, sah_cost_binary(), n_wide);
+    trace = trace_ideal; opt_quant = 0; run_rays("ideal order, exact boxes");
+    opt_quant = 1; run_rays("ideal order, 8-bit planes");
+    trace = trace_device; opt_postpone = 0; run_rays("device loop, octant order, no postponing");
+    opt_postpone = 1; run_rays("device loop, octant order, postponing");
+    opt_nearest = 1; run_rays("  + nearest child first");
+    opt_nearest = 0; opt_gtmin = 1; run_rays("  + group culled on pop by its min entry t");
+    opt_nearest = 1; run_rays("  + both");
+    opt_nearest = 0; opt_gtmin = 0; opt_sorted = 1; run_rays("  per-child entry t kept: sorted + culled");
+    opt_sorted = 0; opt_childcull = 1; run_rays("  per-child entry t kept: octant order + culled"); opt_childcull = 0;
 }
 
 int main(int argc, char **argv) {
