@@ -337,12 +337,12 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
     setup_s = time.perf_counter() - t0
     pt.frame(spp_per_dispatch, first_frame=50000)                  # warm-up: kernels, NCCL communicator, allocator
     if world > 1:
-        pt.probe_cost()
+        pt.cost_from_ray_counts()   # per-tile ray counts of one short pass: the cost map at tile resolution
     history = pt.balance(balance_passes) if world > 1 else []
-    recuts = 6 if world > 1 else 0
+    recuts = 3 if world > 1 else 0
     ms, gathered, n_dispatch = pt.frame(spp, first_frame=0, recuts=recuts)
     times = pt.all_times(ms)
-    rays = pt.counters_t.clone()
+    rays = pt.counters_t[:2].clone()
     if world > 1:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
     img = pt.image(gathered) if rank == 0 else None

@@ -299,6 +299,7 @@ struct FunctionEmitter {
     bool in_generic_loop = false;
     bool is_callable = false;
     int nest = 0;  // depth of enclosing If / Switch / loop / RayQuery blocks
+    bool returned_early = false;  // an Instruction::Return inside a nested block has been emitted: lc_warp_mask may name lanes that are gone
     bool wave = false;        // wavefront lowering of the kernel body (header comment)
     int lambda_depth = 0;     // inside RayQuery callbacks (C++ lambdas): no suspension points there
     int wave_sites = 0;       // suspension points emitted so far (case labels 1..)
@@ -453,9 +454,10 @@ struct FunctionEmitter {
         // Warp operations act on the lanes that reach them.  At the top level of the kernel body that is every live lane of the warp
         // (lc_warp_mask, taken at kernel entry) and the *_sync primitives wait for exactly those lanes, so the result does not depend
         // on whether the hardware has reconverged after divergent code (an If, the CAS loop inside a float atomic); inside divergent
-        // constructs and callables it is the lanes present (__activemask()).
+        // constructs and callables — and anywhere after a Return inside a nested block, whose lanes are gone — it is the lanes present
+        // (__activemask()).
         const bool is_warp_op = f.tag >= Func::WarpIsFirstActiveLane && f.tag <= Func::WarpReadFirstLane;
-        if (is_warp_op) a.insert(a.begin(), nest == 0 && !is_callable ? "lc_warp_mask" : "__activemask()");
+        if (is_warp_op) a.insert(a.begin(), nest == 0 && !is_callable && !returned_early ? "lc_warp_mask" : "__activemask()");
         switch (f.tag) {
             case Func::Add: bin("+"); break;
             case Func::Sub: bin("-"); break;
@@ -745,6 +747,7 @@ struct FunctionEmitter {
             case Instruction::Call: emit_call(n); break;
             case Instruction::Phi: decls += "    " + tname(ntype(n)) + " " + ref(n) + "{};\n"; break;
             case Instruction::Return:
+                returned_early = returned_early || nest > 0;   // lanes may have left: top-level warp operations below see __activemask()
                 if (wave && lambda_depth == 0) line("goto lc_done;");  // this dispatch id is finished; the lane takes the next one
                 else if (ins->return_) line("return " + ref(ins->return_) + ";"); else line("return;");
                 break;
@@ -854,8 +857,8 @@ struct FunctionEmitter {
 
 std::string FunctionEmitter::callable_name(const Arc<CallableModule> &arc) {
     const CallableModule *cm = arc.get();
-    g.curve_bases |= cm->module.curve_basis_set;
     if (!cm) fail("null callable");
+    g.curve_bases |= cm->module.curve_basis_set;
     auto it = g.callables.find(arc.inner);
     if (it != g.callables.end()) return it->second;
     if (cm->cpu_custom_ops.len) fail("CpuCustomOp callables cannot run on the GPU");

@@ -409,13 +409,16 @@ void launch(cudaStream_t s, const AccelView &a, const void *rays, void *out, uin
         lc.count++;
         return;
     }
-    static int blocks_per_sm = 0, sms = 0;
-    if (!blocks_per_sm) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<MODE, COUNTERS>, kTraceThreads, 0);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    // resident grid of this instantiation: a function-local static's initialiser runs once even when several host threads dispatch
+    struct Resident { int blocks_per_sm = 0, sms = 0; };
+    static const Resident res = [] {
+        Resident r; int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&r.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.blocks_per_sm, k_trace<MODE, COUNTERS>, kTraceThreads, 0);
+        if (r.blocks_per_sm < 1) r.blocks_per_sm = 1;
+        return r;
+    }();
+    const int blocks_per_sm = res.blocks_per_sm, sms = res.sms;
     unsigned long long want = (count + kTraceThreads - 1) / kTraceThreads;
     unsigned long long grid = (unsigned long long)sms * blocks_per_sm;
     if (grid > want) grid = want;

@@ -356,7 +356,7 @@ def ray_query_kernel(radius, any_hit=False):
     return k
 
 
-def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64, block=16, regenerate=False):
+def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, light, n_instances, spp_per_dispatch=32, max_depth=5, tile=64, block=16, regenerate=False, tile_counters=False):
     """BASELINE config C5: the path tracer of examples/path_tracer.rs generalised to an instanced scene and to tile sharding
     (SURVEY.md §8d / §8e).  One thread per pixel of a 64x64 tile; `tiles[k]` names the global tile a rank's k-th local tile is
     (Morton round-robin, sharding.tiles_of_rank), results accumulate in a packed per-rank tile buffer that ONE all-gather
@@ -365,7 +365,8 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
     tan_half_fov), object-space vertices go through RayTracingInstanceTransform, normals face the viewer, a constant sky, one
     emissive quad `light` = (position, u, v, emission, instance index), albedo by instance.
     Args: tiles Buffer<u32>, out Buffer<Float4>, accel, params {resolution: Uint2, frame: u32, n_local_tiles: u32},
-    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s).  `block`: edge of the square thread block.
+    counters Buffer<u64> ([0] closest-hit rays, [1] any-hit rays traced, for Mrays/s; with `tile_counters` [2 + global tile id] rays traced
+    for that tile).  `block`: edge of the square thread block.
     `regenerate`: one loop whose iteration is ONE bounce — a lane whose path ended starts its next sample at once instead of idling
     until the longest path of the warp's current sample is done (the nested sample / bounce loops of the example leave 3 of 4 lanes
     idle on C2, profiles/r01u_*).  Each pixel still consumes its random stream in the same order, so the image is bit-identical either
@@ -555,6 +556,8 @@ def tiled_path_tracer_kernel(vertex_heap_handle, index_heap_handle, camera, ligh
         out.write(slot, k.vec(k.f324, rad.x + old.x, rad.y + old.y, rad.z + old.z, old.w + 1.0))
         counters.atomic_fetch_add(0, n_closest.load().cast(k.u64))
         counters.atomic_fetch_add(1, n_any.load().cast(k.u64))
+        if tile_counters:   # rays traced per global tile: the cost map of the multi-GPU partition (sharding.balanced_bounds)
+            counters.atomic_fetch_add(k.u(2) + tile_id, (n_closest.load() + n_any.load()).cast(k.u64))
     k.body(body)
     k.finish()
     return k

@@ -66,8 +66,11 @@ class TiledPathTracer:
         camera = (tuple(map(float, cam_o)), tuple(map(float, f)), tuple(map(float, r)), tuple(map(float, u)), float(np.tan(np.radians(45.0) / 2)))
         light = (l_pos, l_u, l_v, (60.0, 54.0, 45.0), 10)
         self.kernel = examples_ir.tiled_path_tracer_kernel(self.vheap.handle.id, self.iheap.handle.id, camera, light, n_inst, spp_per_dispatch, depth, block=block)
+        # the same kernel with rays counted per tile, for the cost pass only (one more atomic per thread costs 10 % of a frame: profiles/r02u_c5_n2.jsonl)
+        self.count_kernel = examples_ir.tiled_path_tracer_kernel(self.vheap.handle.id, self.iheap.handle.id, camera, light, n_inst, spp_per_dispatch, depth, block=block, tile_counters=True) if world > 1 else None
         # enable_fast_math is the frontend's default (KernelBuildOptions, runtime/kernel.rs:556-570); hits do not depend on it (csrc/shader.cu)
         self.shader = dev.create_shader(C.addressof(self.kernel.km), fast_math=fast_math, keep=self.kernel)
+        self.count_shader = dev.create_shader(C.addressof(self.count_kernel.km), fast_math=fast_math, keep=self.count_kernel) if world > 1 else None
         # ---- tiles ----
         self.tile = sharding.TILE
         self.order_tx, self.order_ty = sharding.tile_order(width, height)
@@ -78,8 +81,9 @@ class TiledPathTracer:
         self.lanes = [self.s] + [dev.create_stream() for _ in range(max(1, streams) - 1)]
         self.joins = [dev.create_event() for _ in self.lanes[1:]]   # one timeline per side lane (a timeline event is a max counter)
         self.serial = 0
-        self.counters_t = torch.zeros(2, dtype=torch.int64, device="cuda")
-        self.counters = dev.wrap_device_memory(self.counters_t.data_ptr(), 2, 8, 8)
+        self.tile_ids = (self.order_ty * self.tiles_x + self.order_tx).astype(np.int64)   # global tile id of every Morton position
+        self.counters_t = torch.zeros(2 + self.n_tiles, dtype=torch.int64, device="cuda")   # [0] closest-hit, [1] any-hit rays, [2 + tile] rays of a tile
+        self.counters = dev.wrap_device_memory(self.counters_t.data_ptr(), 2 + self.n_tiles, 8, 8)
         self.out_t = self.out = None
         self.set_bounds(sharding.balanced_bounds(self.cost, world))
 
@@ -98,7 +102,7 @@ class TiledPathTracer:
             self.out_t.zero_()
         torch.cuda.synchronize()
 
-    def render(self, n_dispatch, first_frame):
+    def render(self, n_dispatch, first_frame, shader=None):
         """enqueue n_dispatch passes of spp_per_dispatch samples over this rank's range; the range is split over the lanes (streams) so
         that the tail of one dispatch overlaps the other lane's work; all lanes are joined into the default stream"""
         tile, n = self.tile, self.b1 - self.b0
@@ -107,7 +111,7 @@ class TiledPathTracer:
             a, b = int(edges[li]), int(edges[li + 1])
             if b == a:
                 continue
-            lane.submit([self.shader.dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view((self.b0 + a) * tile * tile, (b - a) * tile * tile), self.accel,
+            lane.submit([(shader or self.shader).dispatch_async((tile, tile * (b - a)), self.all_tile_ids.view(self.b0 + a, b - a), self.out.view((self.b0 + a) * tile * tile, (b - a) * tile * tile), self.accel,
                                                     np.array([self.width, self.height, first_frame + i, b - a], np.uint32), self.counters) for i in range(n_dispatch)])
         self.serial += 1
         for lane, join in zip(self.lanes[1:], self.joins):
@@ -156,6 +160,23 @@ class TiledPathTracer:
         self.set_bounds(sharding.balanced_bounds(self.cost, self.world))
         return True
 
+    def cost_from_ray_counts(self, dispatches=1, frame0=95000):
+        """the cost map at tile resolution from ONE short pass: every rank renders its current range, the kernel counts the rays it traced
+        per tile, the counts are summed over the ranks (each tile has one owner) and scaled, range by range, to the time that range took —
+        rays are what a tile costs, up to how expensive a ray is where the range looks"""
+        torch = self.torch
+        self.counters_t.zero_()
+        ms = self.timed(lambda: self.render(dispatches, frame0, self.count_shader))
+        times = self.all_times(ms)
+        counts = self.counters_t[2:].clone()
+        if self.world > 1:
+            self.dist.all_reduce(counts, op=self.dist.ReduceOp.SUM)
+        per_tile = counts.cpu().numpy().astype(np.float64)[self.tile_ids]   # Morton order
+        self.cost = sharding.refine_cost(np.maximum(per_tile, 1.0), self.bounds, times)
+        self.recut_to(sharding.balanced_bounds(self.cost, self.world))
+        self.counters_t.zero_(); self.out_t.zero_()
+        return times
+
     def balance(self, passes=4, dispatches=2, frame0=100000):
         """refine the cost map from per-rank times of short passes (`dispatches` dispatches each, samples discarded) and re-cut the
         ranges; returns the history [(imbalance = max / mean of the per-rank times, tiles per rank, ms per rank)]"""
@@ -183,16 +204,21 @@ class TiledPathTracer:
             self.dist.all_gather_into_tensor(self._gathered.view(-1), local.reshape(-1))
         return self._gathered
 
-    def recut(self, times):
-        """refine the cost map from the ranks' times for the current ranges, re-cut, and move the accumulators of the tiles that change
-        owner (in-frame re-balancing); returns the number of tiles this rank sent or received"""
+    def recut(self, times, threshold=1.0):
+        """refine the cost map from the ranks' times for the current ranges and, when they differ by more than `threshold` (max / mean),
+        re-cut and move the accumulators of the tiles that change owner (in-frame re-balancing); returns the tiles this rank sent or received"""
         self.cost = sharding.refine_cost(self.cost, self.bounds, times)
-        new_bounds = sharding.balanced_bounds(self.cost, self.world)
+        if max(times) / (sum(times) / len(times)) <= threshold:
+            return 0
+        return self.recut_to(sharding.balanced_bounds(self.cost, self.world))
+
+    def recut_to(self, new_bounds):
         if np.array_equal(new_bounds, self.bounds):
             return 0
         with self.torch.cuda.stream(self.ext):
             moved = sharding.migrate_ranges(self.out_t, self.bounds, new_bounds, self.rank, self.dist, self.tile * self.tile)
-        self.set_bounds(new_bounds, clear=False)
+        self.bounds = np.asarray(new_bounds, np.int64)
+        self.b0, self.b1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         return moved
 
     def frame(self, spp, first_frame=0, recuts=0):
@@ -216,7 +242,7 @@ class TiledPathTracer:
             else:
                 ms = self.timed(lambda: self.render(b - a, first_frame + a))
                 times = self.all_times(ms)
-                moved = self.recut(times)
+                moved = self.recut(times, threshold=1.02)
                 self.recut_log.append((round(max(times) / (sum(times) / len(times)), 3), moved))
         g = self.gather()
         e1.record(self.ext); self.s.synchronize()
@@ -231,7 +257,7 @@ class TiledPathTracer:
         return hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
 
     def destroy(self):
-        for r in (self.shader, self.vheap, self.iheap, self.all_tile_ids, self.out, self.counters, self.accel, self.mesh, self.quad, self.vb, self.ib, self.qvb, self.qib):
+        for r in ((self.shader, self.count_shader) if self.count_shader else (self.shader,)) + (self.vheap, self.iheap, self.all_tile_ids, self.out, self.counters, self.accel, self.mesh, self.quad, self.vb, self.ib, self.qvb, self.qib):
             r.destroy()
         for lane in self.lanes[1:]:
             lane.destroy()

@@ -26,7 +26,8 @@ def main():
     ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
     ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--balance-passes", type=int, default=6, help="0: equal tile counts per rank")
-    ap.add_argument("--recuts", type=int, default=6, help="re-cuts of the ranges inside the frame (world > 1)")
+    ap.add_argument("--recuts", type=int, default=3, help="re-cuts of the ranges inside the frame (world > 1)")
+    ap.add_argument("--also-recuts", type=int, default=-1, help="render the frame a second time with this many re-cuts (same process: A/B without a second set-up)")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's equal-count range in this single process (tuning aid)")
     ap.add_argument("--precise", action="store_true", help="compile the kernel without enable_fast_math (the frontend default is on)")
     ap.add_argument("--lowering", default="auto", choices=["auto", "direct", "wavefront"])
@@ -57,11 +58,11 @@ def main():
         return
     pt.frame(a.spp_per_dispatch, 50000)
     if world > 1 and a.balance_passes:
-        pt.probe_cost()
+        pt.cost_from_ray_counts()   # per-tile ray counts of one short pass: the cost map at tile resolution
     history = pt.balance(a.balance_passes) if world > 1 and a.balance_passes else []
     ms, gathered, n_dispatch = pt.frame(a.spp, 0, recuts=a.recuts if world > 1 else 0)
     times = pt.all_times(ms)
-    rays = pt.counters_t.clone()
+    rays = pt.counters_t[:2].clone()
     if world > 1:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
     if rank == 0:
@@ -75,6 +76,14 @@ def main():
                "recuts_in_frame": [{"imbalance_before": r[0], "tiles_moved_by_rank0": r[1]} for r in getattr(pt, "recut_log", [])],
                "spp_per_pixel_ok": bool(np.all(img[..., 3] == n_dispatch)), "image_sha256": pt.sha(img)}
         os.write(real_stdout, (json.dumps(res) + "\n").encode())
+    if a.also_recuts >= 0 and world > 1:
+        ms2, g2, _ = pt.frame(a.spp, 0, recuts=a.also_recuts)
+        t2 = pt.all_times(ms2)
+        if rank == 0:
+            img2 = pt.image(g2)
+            os.write(real_stdout, (json.dumps({"config": "c5_path_trace second frame", "recuts": a.also_recuts, "frame_ms": round(max(t2), 3), "tiles_per_rank": [int(x) for x in np.diff(pt.bounds)],
+                                               "recuts_in_frame": [{"imbalance_before": r[0], "tiles_moved_by_rank0": r[1]} for r in pt.recut_log], "image_sha256": pt.sha(img2)}) + "\n").encode())
+    if rank == 0:
         if a.save:
             np.save(a.save, rgb.astype(np.float32))
     if world > 1:
