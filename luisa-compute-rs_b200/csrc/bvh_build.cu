@@ -365,36 +365,34 @@ __global__ void __launch_bounds__(128) k_hierarchy(const K *__restrict__ keys, c
         }
     }
     if (!climbing || done) return;
+    // The climb is a chain of dependent L2 round trips per level, and the thread that arrives second is the critical path of the whole
+    // kernel.  It first LOOKS at the flag: when the sibling is already there (it fenced before it published the flag, so its half of the
+    // node is visible at L2) the level costs two dependent loads — flag, then the sibling's box together with the keys that decide the
+    // next level's parent — instead of store, fence, exchange, load.  Only a thread that finds the flag empty runs the full protocol.
+    bool parent_on_right = (left == 0) || (right != n - 1 && split_delta(keys, right) < split_delta(keys, left - 1));
     while (true) {
         const uint32_t count = right - left + 1;
-        const bool parent_on_right = (left == 0) || (right != n - 1 && split_delta(keys, right) < split_delta(keys, left - 1));
-        uint32_t parent;
-        float4 slo, shi;
-        if (parent_on_right) {  // we are the left child of internal node `right`
-            parent = right;
-            float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
-            pn[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
-            pn[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
+        const uint32_t parent = parent_on_right ? right : left - 1;   // left child of internal node `right` / right child of `left - 1`
+        float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
+        float4 *mine = parent_on_right ? pn : pn + 2;
+        const float4 *theirs = parent_on_right ? pn + 2 : pn;
+        const int my_end = parent_on_right ? (int)left : (int)right;
+        mine[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
+        mine[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
+        int other = __ldcg(&flags[parent]);
+        if (other == -1) {
             release_fence();
-            int other = atomicExch(&flags[parent], (int)left);
+            other = atomicExch(&flags[parent], my_end);
             if (other == -1) return;
-            right = (uint32_t)other;  // the sibling fenced before its exchange; its box is read at L2 (__ldcg) below
-            slo = __ldcg(pn + 2); shi = __ldcg(pn + 3);
-        } else {  // right child of internal node `left - 1`
-            parent = left - 1;
-            float4 *pn = reinterpret_cast<float4 *>(&bin[parent]);
-            pn[2] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(cur));
-            pn[3] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(count));
-            release_fence();
-            int other = atomicExch(&flags[parent], (int)right);
-            if (other == -1) return;
-            left = (uint32_t)other;
-            slo = __ldcg(pn); shi = __ldcg(pn + 1);
         }
+        if (parent_on_right) right = (uint32_t)other; else left = (uint32_t)other;
+        const float4 slo = __ldcg(theirs), shi = __ldcg(theirs + 1);
+        const bool is_root = left == 0 && right == n - 1;
+        if (!is_root) parent_on_right = (left == 0) || (right != n - 1 && split_delta(keys, right) < split_delta(keys, left - 1));  // issued before the box is consumed
         lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
         hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
         cur = parent;
-        if (left == 0 && right == n - 1) {
+        if (is_root) {
             h->root = parent; queue[0] = kQueueRoot | parent;
             h->root_lo[0] = lo.x; h->root_lo[1] = lo.y; h->root_lo[2] = lo.z;
             h->root_hi[0] = hi.x; h->root_hi[1] = hi.y; h->root_hi[2] = hi.z;
