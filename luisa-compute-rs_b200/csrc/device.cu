@@ -43,6 +43,11 @@ struct nvtx_range {
 // ---- logging / errors ------------------------------------------------------------------------
 std::atomic<void (*)(lcb_logger_message)> g_logger{nullptr};
 std::atomic<unsigned long long> g_launches{0};
+// A device keeps more than eight streams alive (the user's, its own copy / build / event lanes).  With CUDA's default of eight hardware
+// queues they alias, and a stream parked on a timeline value that is signalled later (wait before signal: legal, cpu/resource.rs:10-44) can
+// then hold up the stream that is to signal it — measured as a hang of the e2e host program.  Effective only when this
+// library is loaded before the process creates its CUDA context, which is the case for a luisa-compute-rs program.
+const int g_more_queues = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 // -1: follow AccelOption.hint; otherwise kBuilderLbvh / kBuilderPloc / kBuilderAuto for every mesh (LC_B200_BUILDER, lc_b200_set_builder)
 std::atomic<int> g_builder_override{[] { const char *e = getenv("LC_B200_BUILDER"); return !e ? -1 : (strcmp(e, "ploc") == 0 ? 1 : (strcmp(e, "auto") == 0 ? 2 : (strcmp(e, "lbvh") == 0 ? 0 : -1))); }()};
 
