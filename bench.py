@@ -339,7 +339,7 @@ def c5_leg(dev, lc, scenes, torch, dist, rank, world, spp, spp_per_dispatch, bal
     if world > 1:
         pt.cost_from_ray_counts()   # per-tile ray counts of one short pass: the cost map at tile resolution
     history = pt.balance(balance_passes) if world > 1 else []
-    recuts = 3 if world > 1 else 0
+    recuts = 0   # in-frame re-cuts (tiled_render.frame) are implemented and image-exact, but measured neutral at N = 2 / 4 and 2 % slower at N = 8 (profiles/r02u_c5_n*.jsonl)
     ms, gathered, n_dispatch = pt.frame(spp, first_frame=0, recuts=recuts)
     times = pt.all_times(ms)
     rays = pt.counters_t[:2].clone()

@@ -13,6 +13,7 @@
 #include <immintrin.h>
 #include <math.h>
 #include <pthread.h>
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -334,15 +335,29 @@ static uint32_t collapse_node(mesh *m, uint32_t bnode, uint32_t *n_wide, uint32_
     return w;
 }
 
+/* The two arrays a walk touches at random (150 MB of nodes + 40 MB of triangles for the 1 M-triangle soup) ask for huge pages: with
+ * 4 KB pages nearly every node visit is also a TLB miss. */
+static void *alloc_random_access(size_t bytes) {
+    void *p = NULL;
+    const size_t huge = (size_t)2 << 20;
+    if (bytes >= huge) {
+        if (posix_memalign(&p, huge, (bytes + huge - 1) / huge * huge) != 0) die("out of memory");
+#ifdef MADV_HUGEPAGE
+        madvise(p, (bytes + huge - 1) / huge * huge, MADV_HUGEPAGE);
+#endif
+    } else if (posix_memalign(&p, 64, bytes ? bytes : 64) != 0) die("out of memory");
+    return p;
+}
+
 static void build_wide(mesh *m) {
     if (m->ntris == 0 || m->is_curve) return;
-    if (posix_memalign((void **)&m->wide, 32, (size_t)m->n_nodes * sizeof(wnode)) != 0) die("out of memory");
-    m->packed = (ptri *)malloc(m->ntris * sizeof(ptri));
+    m->wide = (wnode *)alloc_random_access((size_t)m->n_nodes * sizeof(wnode));
+    m->packed = (ptri *)alloc_random_access(m->ntris * sizeof(ptri));
     uint32_t nw = 0, np = 0;
     collapse_node(m, 0, &nw, &np);
     m->n_wide = nw;
-    wnode *shrunk = NULL;
-    if (posix_memalign((void **)&shrunk, 32, (size_t)nw * sizeof(wnode)) == 0) { memcpy(shrunk, m->wide, (size_t)nw * sizeof(wnode)); free(m->wide); m->wide = shrunk; }
+    wnode *shrunk = (wnode *)alloc_random_access((size_t)nw * sizeof(wnode));
+    memcpy(shrunk, m->wide, (size_t)nw * sizeof(wnode)); free(m->wide); m->wide = shrunk;
 }
 
 void oracle_invert_affine(const float m[12], float inv[12]) {
@@ -1085,6 +1100,116 @@ static void truth_one(const oracle_scene *s, const oracle_ray *r, uint32_t mask,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* mode 2, closest hit, several rays in flight per thread                                 */
+/* ------------------------------------------------------------------------------------ */
+/* On incoherent rays a wide-BVH walk is a chain of cache misses (the 1 M-triangle soup's tree is 150 MB).  A thread therefore keeps
+ * WALKS rays in flight and advances them in turn, one node each: the prefetches a step issues for the children it pushed have the
+ * other rays' steps to complete in.  Per ray the sequence of nodes, triangle tests and `consider` calls is exactly the one of
+ * closest_one / mesh_closest_wide (same stack discipline), so the hits are the same bits. */
+enum { WALKS = 8, WALK_STACK = 256 };
+typedef struct walk {
+    uint64_t ray; uint32_t inst; int live, in_mesh;
+    ray_frame f; wide_ray w; const mesh *m; best_hit best;
+    int top; wide_entry stack[WALK_STACK];
+    int n_pending; uint64_t pending[8];   /* leaf children hit by the last node test: first packed triangle << 8 | count */
+} walk;
+
+/* moves the walk to the next instance it has to traverse (curves and scalar-mode meshes are finished on the spot); 0 = ray done */
+__attribute__((target("avx2,fma"))) static int walk_next_instance(walk *k, const oracle_scene *s, const oracle_ray *r, uint32_t mask) {
+    for (; k->inst < s->n_insts; k->inst++) {
+        const instance *in = &s->insts[k->inst];
+        if (!in->valid || (in->visible & mask) == 0) continue;
+        const mesh *m = &s->meshes[in->mesh];
+        xform_ray(in->inv, r->o, r->d, &k->f);
+        if (m->is_curve) { curve_closest(m, &k->f, r->tmin, r->tmax, k->inst, &k->best, NULL, 0); continue; }
+        if (m->ntris == 0) continue;
+        if (!m->wide) { mesh_closest(m, &k->f, r->tmin, r->tmax, k->inst, &k->best, 1); continue; }
+        wide_ray_setup(&k->f, &k->w);
+        k->m = m; k->top = 0; k->n_pending = 0; k->stack[k->top++] = (wide_entry){0, -INFINITY};
+        _mm_prefetch((const char *)&m->wide[0], _MM_HINT_T0);
+        k->in_mesh = 1;
+        return 1;
+    }
+    return 0;
+}
+
+__attribute__((target("avx2,fma"))) static void walk_finish(walk *k, const oracle_scene *s, const oracle_ray *r, oracle_hit *h) {
+    best_hit *best = &k->best;
+    if (best->found && best->curve) { h->inst = best->inst; h->prim = best->prim; h->u = best->u; h->v = best->v; h->t = best->t; }
+    else if (best->found) {
+        const instance *in = &s->insts[best->inst];
+        ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
+        const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best->prim, &a, &b, &c);
+        refine_bary(&f, a, b, c, &best->u, &best->v);
+        h->inst = best->inst; h->prim = best->prim; h->u = best->u; h->v = best->v; h->t = best->t;
+    }
+    else { h->inst = UINT32_MAX; h->prim = UINT32_MAX; h->u = 0.f; h->v = 0.f; h->t = r->tmax; }
+    h->pad = 0;
+}
+
+/* one node of one ray: the body of mesh_closest_wide's loop, except that the triangles of the leaf children a node test hits are only
+ * PREFETCHED here and tested at the ray's next step (they are cache misses too).  The hit is the same: the set of triangles tested can
+ * only grow (a later node is culled against a slightly older tbest), and `consider` does not depend on the order of its calls. */
+__attribute__((target("avx2,fma"))) static inline void walk_step(walk *k, const oracle_ray *r) {
+    const mesh *m = k->m;
+    for (int p = 0; p < k->n_pending; p++) {
+        const ptri *t = &m->packed[k->pending[p] >> 8];
+        const uint32_t cnt = k->pending[p] & 0xffu;
+        for (uint32_t j = 0; j < cnt; j++) {
+            float tt, u, v;
+            if (canon_tri(&k->f, r->tmin, r->tmax, t[j].v0, t[j].v1, t[j].v2, &tt, &u, &v)) consider(&k->best, tt, u, v, k->inst, t[j].prim);
+        }
+    }
+    k->n_pending = 0;
+    if (k->top == 0) return;
+    const wide_entry e = k->stack[--k->top];
+    const float tb = k->best.found ? k->best.t : r->tmax;
+    if (e.tn > tb) return;
+    const wnode *nd = &m->wide[e.node];
+    float tn[8];
+    unsigned hit = wide_node_test(nd, &k->w, r->tmin, tb, tn);
+    const int base = k->top;
+    while (hit) {
+        const int i = __builtin_ctz(hit); hit &= hit - 1;
+        if (nd->count[i] == WIDE_EMPTY) continue;
+        if (nd->count[i]) {
+            const char *pf = (const char *)&m->packed[nd->child[i]];
+            const char *pe = pf + (size_t)nd->count[i] * sizeof(ptri);
+            for (; pf < pe; pf += 64) _mm_prefetch(pf, _MM_HINT_T0);
+            _mm_prefetch(pe - 1, _MM_HINT_T0);
+            k->pending[k->n_pending++] = ((uint64_t)nd->child[i] << 8) | nd->count[i];
+        } else {
+            if (k->top + 1 > WALK_STACK) die("oracle wide BVH stack overflow");
+            int q = k->top++;
+            while (q > base && k->stack[q - 1].tn < tn[i]) { k->stack[q] = k->stack[q - 1]; q--; }
+            k->stack[q] = (wide_entry){nd->child[i], tn[i]};
+            { const char *pf = (const char *)&m->wide[nd->child[i]]; _mm_prefetch(pf, _MM_HINT_T0); _mm_prefetch(pf + 64, _MM_HINT_T0); _mm_prefetch(pf + 128, _MM_HINT_T0); _mm_prefetch(pf + 192, _MM_HINT_T0); }
+        }
+    }
+}
+
+__attribute__((target("avx2,fma"))) static void closest_block_interleaved(const oracle_scene *s, const oracle_ray *rays, uint64_t i0, uint64_t i1, uint32_t mask, oracle_hit *hits) {
+    static __thread walk *ws = NULL;
+    if (!ws && posix_memalign((void **)&ws, 64, sizeof(walk) * WALKS) != 0) die("out of memory");
+    uint64_t next = i0; int live = 0;
+    for (int a = 0; a < WALKS; a++) ws[a].live = 0;
+    for (;;) {
+        for (int a = 0; a < WALKS; a++) {
+            walk *k = &ws[a];
+            if (!k->live) {
+                if (next >= i1) continue;
+                k->ray = next++; k->inst = 0; k->live = 1; k->in_mesh = 0; memset(&k->best, 0, sizeof(k->best)); live++;
+            }
+            const oracle_ray *r = &rays[k->ray];
+            if (k->in_mesh && k->top == 0 && k->n_pending == 0) { k->in_mesh = 0; k->inst++; }   /* this instance is exhausted */
+            if (!k->in_mesh && !walk_next_instance(k, s, r, mask)) { walk_finish(k, s, r, &hits[k->ray]); k->live = 0; live--; continue; }
+            walk_step(k, r);
+        }
+        if (live == 0 && next >= i1) break;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* StreamImpl::parallel_for — stream.rs:185-209: N workers, atomic counter, block = 64    */
 /* ------------------------------------------------------------------------------------ */
 
@@ -1103,6 +1228,7 @@ static void *worker(void *arg) {
         uint64_t i0 = __atomic_fetch_add(&j->counter, 64, __ATOMIC_RELAXED);
         if (i0 >= j->n) break;
         uint64_t i1 = i0 + 64 < j->n ? i0 + 64 : j->n;
+        if (j->kind == 0 && j->mode == 2 && have_avx2()) { closest_block_interleaved(j->s, j->rays, i0, i1, j->mask, j->hits); continue; }
         for (uint64_t i = i0; i < i1; i++) {
             if (j->kind == 0) closest_one(j->s, &j->rays[i], j->mask, &j->hits[i], j->mode);
             else if (j->kind == 1) j->occ[i] = any_one(j->s, &j->rays[i], j->mask, j->mode);

@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--block", type=int, default=8, help="edge of the kernel's square thread block")
     ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--balance-passes", type=int, default=6, help="0: equal tile counts per rank")
-    ap.add_argument("--recuts", type=int, default=3, help="re-cuts of the ranges inside the frame (world > 1)")
+    ap.add_argument("--recuts", type=int, default=0, help="re-cuts of the ranges inside the frame (world > 1)")
     ap.add_argument("--also-recuts", type=int, default=-1, help="render the frame a second time with this many re-cuts (same process: A/B without a second set-up)")
     ap.add_argument("--emulate", default="", help="RANK/WORLD: render only that rank's equal-count range in this single process (tuning aid)")
     ap.add_argument("--precise", action="store_true", help="compile the kernel without enable_fast_math (the frontend default is on)")
