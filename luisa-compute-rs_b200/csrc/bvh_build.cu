@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
 }
 
 // One thread per packed slot: gather the slot's triangle (id recorded by the collapse, or kept from the last build when
-// refitting) through the index buffer and write the 48 used bytes of the record.
+// refitting) through the index buffer and write the record.
 __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, const uint32_t *__restrict__ slot_prim, PackedTri *tris, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -919,6 +919,7 @@ __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, const uint3
     o[0] = make_float4(a[0], a[1], a[2], __uint_as_float(prim));
     o[1] = make_float4(b[0], b[1], b[2], 0.f);
     o[2] = make_float4(c[0], c[1], c[2], 0.f);
+    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);  // the spare quad too: two whole sectors per record instead of a read-modify-write of the second
 }
 
 
