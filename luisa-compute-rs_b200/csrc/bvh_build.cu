@@ -1,7 +1,7 @@
-// bvh_build.cu — LBVH builder for sm_100a: primitive boxes + centroid bounds, 48-bit Morton
-// codes, onesweep sort (radix_sort.cu), fused bottom-up hierarchy emission + AABB refit with
-// atomic arrival flags (after Apetrei 2014), and collapse of the binary tree into 8-wide
-// 128-byte quantised nodes with packed 64-byte leaf triangles.
+// bvh_build.cu — BVH builder for sm_100a: primitive boxes + centroid bounds, Morton codes (32-bit keys up to 2^25
+// primitives), onesweep sort (radix_sort.cu), the binary tree either by fused bottom-up LBVH emission + AABB refit with
+// atomic arrival flags (after Apetrei 2014) or by PLOC, and its collapse — a barrier-free work queue — into 8-wide
+// 96-byte quantised nodes with packed 64-byte leaf triangles; refit of the wide tree.
 //
 // Replaces what the reference delegates to rtcCommitScene (cpu/accel.rs:258,439) /
 // optixAccelBuild (cuda_primitive.cpp:57-60).  No reference source exists for any of it.
@@ -28,7 +28,7 @@ __global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags, unsi
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
-        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->tickets = 0; h->processed = 0; h->max_depth = 0; h->error = 0;
+        h->root = 0; h->node_count = 1; h->prim_count = 0; h->emitted = 0; h->tickets = 0; h->unused0 = 0; h->max_depth = 0; h->error = 0;
         h->prim_area_sum = 0.f; h->pad2 = 0.f;
     }
     if (i < 24) h->pad_line[i] = 0;  // the host reads the header back whole

@@ -109,7 +109,7 @@ struct BuildHeader {
     uint32_t tickets;       // collapse: next wide-node id to hand out as a work ticket
     uint32_t max_depth;
     uint32_t error;         // nonzero: builder failure code
-    uint32_t processed;     // collapse: wide nodes whose children have been allocated (== node_count: the walk is over)
+    uint32_t unused0;
     float root_lo[3]; float prim_area_sum;  // sum of the primitives' box half-areas (builder choice, bvh_build.cu)
     float root_hi[3]; float pad2;
     uint32_t pad_line[24];  // keeps collapse_done out of the cache line of the allocation atomics
