@@ -244,6 +244,12 @@ class TiledPathTracer:
                 times = self.all_times(ms)
                 moved = self.recut(times, threshold=1.02)
                 self.recut_log.append((round(max(times) / (sum(times) / len(times)), 3), moved))
+        if self.world > 1 and len(self.lanes) > 2:
+            # belt and braces for the unverified combination (known issue: one 8-rank run with 4 lanes gathered tiles whose
+            # lanes had not finished although every lane is joined into the default stream by a timeline event): the host waits for the
+            # side lanes before it enqueues the gather
+            for lane in self.lanes[1:]:
+                lane.synchronize()
         g = self.gather()
         e1.record(self.ext); self.s.synchronize()
         torch.cuda.synchronize()
