@@ -24,7 +24,7 @@ constexpr int kLeafMax = LCB_LEAF_MAX;  // primitives per leaf child (unary coun
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
 
-__global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags, unsigned long long *queue) {
+__global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags, unsigned long long *queue, uint32_t n_queue) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int k = 0; k < 3; k++) { h->bounds_lo[k] = 0x7fffffff; h->bounds_hi[k] = (int)0x80000000; h->root_lo[k] = 0.f; h->root_hi[k] = 0.f; }
@@ -34,17 +34,28 @@ __global__ void k_init_header(BuildHeader *h, int *flags, uint32_t n_flags, unsi
     if (i < 24) h->pad_line[i] = 0;  // the host reads the header back whole
     if (i < 23) h->reserved[i] = 0;
     if (i == 0) h->collapse_done = 0;
-    for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) { flags[j] = -1; queue[j] = 0ull; }  // collapse work items: 0 = not published yet
+    for (uint32_t j = i; j < n_flags; j += gridDim.x * blockDim.x) { flags[j] = -1; if (j < n_queue) queue[j] = 0ull; }  // collapse work items: 0 = not published yet (wide nodes <= n_queue)
 }
 
 // block-reduce the centroid (shuffles, then one shared-memory round) and fold it into the header's ordered-int
 // bounds: 6 atomics per block instead of per warp
-__device__ __forceinline__ void reduce_centroid_bounds(float c[3], bool valid, BuildHeader *h, float area = 0.f) {
-    __shared__ float s_lo[8][3], s_hi[8][3], s_area[8];
-    float lo[3], hi[3];
-    if (!valid) area = 0.f;
+// Every box kernel is a grid-stride loop over a bounded grid (kBoxBlocks): a thread folds the centroids of its primitives into a
+// running box, the block reduces once, and the header sees 7 atomics per BLOCK OF THE GRID, not per 256 primitives — they all land on
+// one cache line of one L2 slice, and at 20 M primitives 550 k of them were most of the kernel (profiles/r02m_build_20M_launches_summary.csv).
+constexpr uint32_t kBoxBlocks = 148 * 8;
+struct CentroidAcc {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, area = 0.f;
+    __device__ __forceinline__ void add(const float c[3], float a) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) { lo[k] = valid ? c[k] : FLT_MAX; hi[k] = valid ? c[k] : -FLT_MAX; }
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], c[k]); hi[k] = fmaxf(hi[k], c[k]); }
+        area += a;
+    }
+};
+__device__ __forceinline__ void reduce_centroid_bounds(const CentroidAcc &acc, BuildHeader *h) {
+    __shared__ float s_lo[8][3], s_hi[8][3], s_area[8];
+    float lo[3], hi[3], area = acc.area;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { lo[k] = acc.lo[k]; hi[k] = acc.hi[k]; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
@@ -88,12 +99,9 @@ __device__ __forceinline__ void load_triangle(const TriangleInput &in, uint32_t 
 }
 
 __global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32_t n, PrimBox *boxes, BuildHeader *h) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    float cen[3] = {0, 0, 0};
-    float area = 0.f;
-    bool valid = i < n;
-    if (valid) {
-        float a[3], b[3], c[3];
+    CentroidAcc acc;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float a[3], b[3], c[3], cen[3];
         load_triangle(in, i, a, b, c);
         PrimBox pb;
 #pragma unroll
@@ -102,33 +110,29 @@ __global__ void __launch_bounds__(256) k_triangle_boxes(TriangleInput in, uint32
             pb.hi[k] = fmax3(a[k], b[k], c[k]);
             cen[k] = 0.5f * pb.lo[k] + 0.5f * pb.hi[k];
         }
-        pb.pad0 = pb.pad1 = 0;
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(pb.lo[0], pb.lo[1], pb.lo[2], 0.f);
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(pb.hi[0], pb.hi[1], pb.hi[2], 0.f);
         const float dx = pb.hi[0] - pb.lo[0], dy = pb.hi[1] - pb.lo[1], dz = pb.hi[2] - pb.lo[2];
-        area = dx * dy + dy * dz + dz * dx;
+        acc.add(cen, dx * dy + dy * dz + dz * dx);
     }
-    reduce_centroid_bounds(cen, valid, h, area);
+    reduce_centroid_bounds(acc, h);
 }
 
 // Procedural primitives (ProceduralPrimitiveBuild, api_types:633-641): the user's AABBs {min[3], max[3]} (rtx.rs:339-345, 24 B) are
 // the primitive boxes (GeometryImpl::build_procedural's bounds_func, cpu/accel.rs:93-104).
 __global__ void __launch_bounds__(256) k_aabb_boxes(const uint8_t *__restrict__ aabbs, uint32_t n, PrimBox *boxes, BuildHeader *h) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    float cen[3] = {0, 0, 0};
-    float area = 0.f;
-    bool valid = i < n;
-    if (valid) {
+    CentroidAcc acc;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float *a = reinterpret_cast<const float *>(aabbs + (size_t)i * 24);
-        float lo[3], hi[3];
+        float lo[3], hi[3], cen[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) { lo[k] = fminf(a[k], a[3 + k]); hi[k] = fmaxf(a[k], a[3 + k]); cen[k] = 0.5f * lo[k] + 0.5f * hi[k]; }
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-        area = dx * dy + dy * dz + dz * dx;
+        acc.add(cen, dx * dy + dy * dz + dz * dx);
     }
-    reduce_centroid_bounds(cen, valid, h, area);
+    reduce_centroid_bounds(acc, h);
 }
 
 // leaf records of a procedural BLAS: the primitive's box and id in the PackedTri slot the collapse assigned
@@ -145,20 +149,17 @@ __global__ void __launch_bounds__(256) k_pack_aabbs(const uint8_t *__restrict__ 
 
 // Curve pieces (CurveBuild): box of the two end spheres, rounded outward.
 __global__ void __launch_bounds__(256) k_curve_boxes(CurveInput in, uint32_t n, PrimBox *boxes, BuildHeader *h) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    float cen[3] = {0, 0, 0};
-    float area = 0.f;
-    bool valid = i < n;
-    if (valid) {
+    CentroidAcc acc;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 A, B;
         curve_piece(in.cps, in.cp_stride, in.segs, in.basis, i / in.pieces, i % in.pieces, A, B);
         const float ra = fabsf(A.w), rb = fabsf(B.w);
         const float pa[3] = {A.x, A.y, A.z}, pb[3] = {B.x, B.y, B.z};
-        float lo[3], hi[3];
-#pragma unroll
+        float lo[3], hi[3], cen[3];
         // the canonical cone test decides in fp32: pad by a fraction of the radius and of the piece's extent so that a ray it
         // accepts never misses the box
         const float pad = fmaxf(ra, rb) * (1.0f / 256.0f) + fmaxf(fmaxf(fabsf(pb[0] - pa[0]), fabsf(pb[1] - pa[1])), fabsf(pb[2] - pa[2])) * (1.0f / 4096.0f);
+#pragma unroll
         for (int k = 0; k < 3; k++) {
             lo[k] = __fsub_rd(fminf(__fsub_rd(pa[k], ra), __fsub_rd(pb[k], rb)), pad);
             hi[k] = __fadd_ru(fmaxf(__fadd_ru(pa[k], ra), __fadd_ru(pb[k], rb)), pad);
@@ -167,9 +168,9 @@ __global__ void __launch_bounds__(256) k_curve_boxes(CurveInput in, uint32_t n, 
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-        area = dx * dy + dy * dz + dz * dx;
+        acc.add(cen, dx * dy + dy * dz + dz * dx);
     }
-    reduce_centroid_bounds(cen, valid, h, area);
+    reduce_centroid_bounds(acc, h);
 }
 
 // leaf records of a curve BLAS: the piece's two spheres, its segment and its parameter range (CurveSeg)
@@ -237,7 +238,9 @@ __global__ void __launch_bounds__(128) k_instance_boxes(const uint32_t *active, 
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         reinterpret_cast<float4 *>(boxes)[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
-    reduce_centroid_bounds(cen, valid, h);
+    CentroidAcc acc;
+    if (valid) acc.add(cen, 0.f);
+    reduce_centroid_bounds(acc, h);
 }
 
 // orders this thread's earlier stores before its next atomic at GPU scope; what __threadfence() gives beyond that (sequential
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(kCollapseThreads, LCB_COLLAPSE_MIN_BLOCKS) k_c
     for (;;) {
         // ================= take the work item, if its parent has published it =================
         unsigned long long item = 0ull;
-        if (!exhausted && sub == 0 && t < n) item = __ldcg(queue + t);  // the queue holds n entries; a tree over n primitives has fewer wide nodes
+        if (!exhausted && sub == 0 && t < n && t < capacity) item = __ldcg(queue + t);  // min(n, capacity) entries are cleared: no wide node has an id beyond either
         item = GSHFL(item, 0);
         const bool active = item != 0ull;
         const uint32_t bnode = (uint32_t)item, depth = (uint32_t)(item >> 32) - 1u;
@@ -923,6 +926,8 @@ __global__ void __launch_bounds__(256) k_pack_tris(TriangleInput in, const uint3
 }
 
 
+static inline uint32_t box_blocks(uint32_t n) { const uint32_t b = (n + 255) / 256; return b < kBoxBlocks ? b : kBoxBlocks; }
+
 template <class Sink>
 void run_pipeline_after_boxes(cudaStream_t s, uint32_t n, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, const Sink &sink, LaunchCounter &lc, bool ploc) {
     // Morton resolution follows the primitive count: log2(n) bits only enumerate the primitives, the rest resolves non-uniform
@@ -1034,8 +1039,8 @@ BuildScratch build_scratch_layout(void *base, uint32_t n) {
 
 int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *tris, LaunchCounter &lc, int builder) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
-    k_triangle_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue, (n < capacity ? n : capacity)); lc.count++;
+    k_triangle_boxes<<<box_blocks(n), 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
     bool use_ploc = builder == kBuilderPloc;
     if (builder == kBuilderAuto && n > 1) {
         // PLOC pays off where primitives tile a surface (terrain, C4 / C5: +11 % Mrays/s) and loses to the spatial-median splits of
@@ -1058,8 +1063,8 @@ int build_blas(cudaStream_t s, uint32_t n, const TriangleInput &in, const BuildS
 
 void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
-    k_aabb_boxes<<<(n + 255) / 256, 256, 0, s>>>(aabbs, n, sc.boxes, sc.header); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue, (n < capacity ? n : capacity)); lc.count++;
+    k_aabb_boxes<<<box_blocks(n), 256, 0, s>>>(aabbs, n, sc.boxes, sc.header); lc.count++;
     uint32_t *slot_prim = reinterpret_cast<uint32_t *>(sc.flags);
     LeafSinkTriangles sink{slot_prim};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
@@ -1068,8 +1073,8 @@ void build_procedural(cudaStream_t s, uint32_t n, const uint8_t *aabbs, const Bu
 
 void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildScratch &sc, WideNode *nodes, uint32_t capacity, PackedTri *slots, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
-    k_curve_boxes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue, (n < capacity ? n : capacity)); lc.count++;
+    k_curve_boxes<<<box_blocks(n), 256, 0, s>>>(in, n, sc.boxes, sc.header); lc.count++;
     uint32_t *slot_prim = reinterpret_cast<uint32_t *>(sc.flags);
     LeafSinkTriangles sink{slot_prim};
     run_pipeline_after_boxes(s, n, sc, nodes, capacity, sink, lc, false);
@@ -1080,7 +1085,7 @@ void build_curves(cudaStream_t s, uint32_t n, const CurveInput &in, const BuildS
 void build_tlas(cudaStream_t s, uint32_t n, const uint32_t *active_ids, const InstanceRec *instances, const BuildScratch &sc, WideNode *nodes,
                 uint32_t *prim_ids, LaunchCounter &lc) {
     uint32_t init_blocks = (n + 255) / 256; if (init_blocks > 1024) init_blocks = 1024;
-    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue); lc.count++;
+    k_init_header<<<init_blocks, 256, 0, s>>>(sc.header, sc.flags, n, sc.queue, n); lc.count++;
     k_instance_boxes<<<(n + 127) / 128, 128, 0, s>>>(active_ids, n, instances, sc.boxes, sc.header); lc.count++;
     LeafSinkInstances sink{active_ids, prim_ids};
     run_pipeline_after_boxes(s, n, sc, nodes, n, sink, lc, false);  // a handful of instances: the LBVH order is as good as any; the node array holds n
