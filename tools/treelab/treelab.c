@@ -1,7 +1,7 @@
 /* treelab.c — development aid (not product, not oracle): CPU model of the device's BVH pipeline used to compare BINARY-TREE builders
  * by what matters to k_trace: wide nodes visited and triangles tested per incoherent closest-hit ray, after the same 8-wide collapse
  * (open the largest-area child until 8, spare slots split small leaves; bvh_build.cu k_collapse) and an ordered traversal.
- *   gcc -O2 -march=native -o /tmp/treelab tools/treelab/treelab.c -lm && /tmp/treelab [n_tris] [n_rays] [leaf_max]
+ *   gcc -O2 -march=native -o /tmp/treelab tools/treelab/treelab.c -lm && /tmp/treelab [n_tris] [n_rays] [leaf_max] [builders: lbvh ext sah ploc] [soup|terrain]
  * Builders: lbvh (Morton order, split at the highest differing bit = the device's k_hierarchy), sah (binned top-down, the oracle's
  * kind of tree), ploc (radius 8, the device's k_ploc_*), and lbvh+X experiments. */
 #include <float.h>
@@ -240,15 +240,34 @@ int main(int argc, char **argv) {
     const char *only = argc > 4 ? argv[4] : "";
     V = malloc(sizeof(*V) * n_tris); pbox = malloc(sizeof(box_t) * n_tris); kv = malloc(sizeof(kv_t) * n_tris); order = malloc(sizeof(int) * n_tris);
     nodes = malloc(sizeof(bnode_t) * n_tris); wn = malloc(sizeof(wnode_t) * n_tris); packed = malloc(sizeof(int) * n_tris);
+    const int terrain = argc > 5 && strstr(argv[5], "terrain");
+    if (terrain) {
+        /* nx x nx vertices over [0,1]^2, h = 0.1 * 5-octave value noise (tests/scenes.py terrain()); n_tris is rounded to 2 (nx-1)^2 */
+        int nx = (int)sqrt(n_tris / 2.0) + 1; n_tris = 2 * (nx - 1) * (nx - 1);
+        float *h = calloc((size_t)nx * nx, sizeof(float)); float amp = 0.5f; int freq = 4;
+        for (int oct = 0; oct < 5; oct++) { float *g = malloc(sizeof(float) * (freq + 2) * (freq + 2)); for (int i = 0; i < (freq + 2) * (freq + 2); i++) g[i] = rndf();
+            for (int z = 0; z < nx; z++) for (int x = 0; x < nx; x++) { float fx = (float)x / (nx - 1) * freq, fz = (float)z / (nx - 1) * freq; int ix = (int)fx < freq ? (int)fx : freq, iz = (int)fz < freq ? (int)fz : freq; float tx = fx - ix, tz = fz - iz; tx = tx * tx * (3 - 2 * tx); tz = tz * tz * (3 - 2 * tz);
+                float a = g[iz * (freq + 2) + ix] * (1 - tx) + g[iz * (freq + 2) + ix + 1] * tx, b = g[(iz + 1) * (freq + 2) + ix] * (1 - tx) + g[(iz + 1) * (freq + 2) + ix + 1] * tx; h[z * nx + x] += amp * (a * (1 - tz) + b * tz); }
+            free(g); amp *= 0.5f; freq *= 2; }
+        int t = 0;
+        for (int z = 0; z < nx - 1; z++) for (int x = 0; x < nx - 1; x++) for (int half = 0; half < 2; half++, t++) {
+            int vx[3], vz[3]; if (!half) { vx[0] = x; vz[0] = z; vx[1] = x + 1; vz[1] = z; vx[2] = x + 1; vz[2] = z + 1; } else { vx[0] = x; vz[0] = z; vx[1] = x + 1; vz[1] = z + 1; vx[2] = x; vz[2] = z + 1; }
+            box_t b = box_empty();
+            for (int v = 0; v < 3; v++) { V[t][v][0] = (float)vx[v] / (nx - 1); V[t][v][1] = 0.1f * h[vz[v] * nx + vx[v]]; V[t][v][2] = (float)vz[v] / (nx - 1); for (int k = 0; k < 3; k++) { if (V[t][v][k] < b.lo[k]) b.lo[k] = V[t][v][k]; if (V[t][v][k] > b.hi[k]) b.hi[k] = V[t][v][k]; } }
+            pbox[t] = b; }
+        free(h);
+    } else {
     const float extent = 0.01f;
     for (int i = 0; i < n_tris; i++) { float c[3], e1[3], e2[3]; for (int k = 0; k < 3; k++) { c[k] = rndf(); e1[k] = (rndf() * 2 - 1) * extent; e2[k] = (rndf() * 2 - 1) * extent; }
         box_t b = box_empty(); for (int k = 0; k < 3; k++) { V[i][0][k] = c[k] - (e1[k] + e2[k]) / 3; V[i][1][k] = V[i][0][k] + e1[k]; V[i][2][k] = V[i][0][k] + e2[k]; for (int v = 0; v < 3; v++) { if (V[i][v][k] < b.lo[k]) b.lo[k] = V[i][v][k]; if (V[i][v][k] > b.hi[k]) b.hi[k] = V[i][v][k]; } } pbox[i] = b; }
+    }
     RO = malloc(sizeof(*RO) * n_rays); RD = malloc(sizeof(*RD) * n_rays);
-    for (int i = 0; i < n_rays; i++) { for (int k = 0; k < 3; k++) RO[i][k] = rndf(); float z = rndf() * 2 - 1, phi = rndf() * 6.2831853f, r = sqrtf(fmaxf(0, 1 - z * z)); RD[i][0] = r * cosf(phi); RD[i][1] = r * sinf(phi); RD[i][2] = z; }
-    printf("soup %d triangles, %d rays, leaf_max %d\n", n_tris, n_rays, leaf_max);
+    for (int i = 0; i < n_rays; i++) { for (int k = 0; k < 3; k++) RO[i][k] = rndf(); if (terrain) RO[i][1] = RO[i][1] * 0.3f + 0.1f; /* tools/trace_bench.py's terrain rays */ float z = rndf() * 2 - 1, phi = rndf() * 6.2831853f, r = sqrtf(fmaxf(0, 1 - z * z)); RD[i][0] = r * cosf(phi); RD[i][1] = r * sinf(phi); RD[i][2] = z; }
+    printf("%s %d triangles, %d rays, leaf_max %d\n", terrain ? "terrain" : "soup", n_tris, n_rays, leaf_max);
     if (!*only || strstr(only, "lbvh")) { build_lbvh(32, 0); evaluate("lbvh 32-bit"); }
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
     if (!*only || strstr(only, "ploc")) { build_ploc(32, 8); evaluate("ploc r8"); }
+    if (strstr(only, "plocx")) { build_ploc(32, 16); evaluate("ploc r16"); build_ploc(32, 32); evaluate("ploc r32"); }
     return 0;
 }
