@@ -1112,6 +1112,7 @@ typedef struct walk {
     ray_frame f; wide_ray w; const mesh *m; best_hit best;
     int top; wide_entry stack[WALK_STACK];
     int n_pending; uint64_t pending[8];   /* leaf children hit by the last node test: first packed triangle << 8 | count */
+    const ptri *best_tri;                  /* packed copy of the winning triangle (still in cache when the ray is finished) */
 } walk;
 
 /* moves the walk to the next instance it has to traverse (curves and scalar-mode meshes are finished on the spot); 0 = ray done */
@@ -1139,7 +1140,11 @@ __attribute__((target("avx2,fma"))) static void walk_finish(walk *k, const oracl
     else if (best->found) {
         const instance *in = &s->insts[best->inst];
         ray_frame f; xform_ray(in->inv, r->o, r->d, &f);
-        const float *a, *b, *c; tri_verts(&s->meshes[in->mesh], best->prim, &a, &b, &c);
+        const float *a, *b, *c;
+        /* the winner's vertices: the packed copy the walk tested (the same floats as the mesh's, and still in cache) when it came from
+         * a wide tree, else through the index buffer as closest_one does */
+        if (k->best_tri && k->best_tri->prim == best->prim && s->meshes[in->mesh].wide) { a = k->best_tri->v0; b = k->best_tri->v1; c = k->best_tri->v2; }
+        else tri_verts(&s->meshes[in->mesh], best->prim, &a, &b, &c);
         refine_bary(&f, a, b, c, &best->u, &best->v);
         h->inst = best->inst; h->prim = best->prim; h->u = best->u; h->v = best->v; h->t = best->t;
     }
@@ -1157,7 +1162,11 @@ __attribute__((target("avx2,fma"))) static inline void walk_step(walk *k, const 
         const uint32_t cnt = k->pending[p] & 0xffu;
         for (uint32_t j = 0; j < cnt; j++) {
             float tt, u, v;
-            if (canon_tri(&k->f, r->tmin, r->tmax, t[j].v0, t[j].v1, t[j].v2, &tt, &u, &v)) consider(&k->best, tt, u, v, k->inst, t[j].prim);
+            if (canon_tri(&k->f, r->tmin, r->tmax, t[j].v0, t[j].v1, t[j].v2, &tt, &u, &v)) {
+                const int had = k->best.found; const uint32_t pi = k->best.inst, pp = k->best.prim;
+                consider(&k->best, tt, u, v, k->inst, t[j].prim);
+                if (!had || k->best.inst != pi || k->best.prim != pp) k->best_tri = &t[j];
+            }
         }
     }
     k->n_pending = 0;
@@ -1198,7 +1207,7 @@ __attribute__((target("avx2,fma"))) static void closest_block_interleaved(const 
             walk *k = &ws[a];
             if (!k->live) {
                 if (next >= i1) continue;
-                k->ray = next++; k->inst = 0; k->live = 1; k->in_mesh = 0; memset(&k->best, 0, sizeof(k->best)); live++;
+                k->ray = next++; k->inst = 0; k->live = 1; k->in_mesh = 0; k->best_tri = NULL; memset(&k->best, 0, sizeof(k->best)); live++;
             }
             const oracle_ray *r = &rays[k->ray];
             if (k->in_mesh && k->top == 0 && k->n_pending == 0) { k->in_mesh = 0; k->inst++; }   /* this instance is exhausted */
