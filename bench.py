@@ -146,7 +146,7 @@ def run_reference(args, rank):
         o.trace_closest(rays, 0xFF, ol.WIDE, 0)
     dt = (time.perf_counter() - t0) / args.steps
     v = n_sample / dt / 1e6
-    sample = f"first {n_sample} rays of the C3 batch per step against the full 1M-triangle scene; oracle port, fast mode: binned-SAH BVH collapsed 8-wide, AVX2 box tests, canonical fp32 triangle test, all host threads (not Embree: the reference's own arithmetic cannot be built here)"
+    sample = f"first {n_sample} rays of the C3 batch per step against the full 1M-triangle scene; oracle port, fast mode: binned-SAH BVH collapsed 8-wide, AVX2 box tests, eight rays in flight per thread, canonical fp32 triangle test, all host threads (not Embree: the reference's own arithmetic cannot be built here)"
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -604,7 +604,7 @@ def main():
         n_sample = min(n, 1 << 24)   # ~7 s on 16 cores: the whole batch
         v, cpu_build_s, cpu_s = cpu_leg(n_sample)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"first {n_sample} rays of the batch ({cpu_s:.1f} s) on the full 1M-triangle scene; oracle port, fast mode (SAH BVH built in {cpu_build_s:.1f} s on all threads, collapsed 8-wide, AVX2 box tests, canonical triangle test), not Embree"}
+                               "sample": f"first {n_sample} rays of the batch ({cpu_s:.1f} s) on the full 1M-triangle scene; oracle port, fast mode (SAH BVH built in {cpu_build_s:.1f} s on all threads, collapsed 8-wide, AVX2 box tests, eight rays in flight per thread, canonical triangle test), not Embree"}
 
     if rank == 0:
         emit(json.dumps(out))
