@@ -104,6 +104,44 @@ static int sah_rec(int lo, int hi) {
 }
 static void build_sah(void) { for (int i = 0; i < n_tris; i++) order[i] = i; n_nodes = 0; root = sah_rec(0, n_tris - 1); fit_boxes(root); }
 
+/* ---- hybrid (HLBVH with a SAH top, Garanzha et al. 2011): LBVH inside Morton clusters of about `target` primitives, binned SAH over the cluster roots ---- */
+static int *items; /* cluster root refs, permuted by the top-level SAH */
+static int top_sah_rec(int lo, int hi) {
+    if (lo == hi) return items[lo];
+    box_t cb = box_empty();
+    for (int i = lo; i <= hi; i++) { box_t b = ref_box(items[i]); float c[3]; for (int k = 0; k < 3; k++) c[k] = 0.5f * (b.lo[k] + b.hi[k]); box_t q = {{c[0], c[1], c[2]}, {c[0], c[1], c[2]}}; box_grow(&cb, &q); }
+    int n = hi - lo + 1, best_axis = -1, best_bin = 0; float best_cost = FLT_MAX; enum { NB = 32 };
+    for (int ax = 0; ax < 3; ax++) {
+        float ext = cb.hi[ax] - cb.lo[ax]; if (!(ext > 0)) continue;
+        box_t bins[NB]; int cnt[NB]; for (int b = 0; b < NB; b++) { bins[b] = box_empty(); cnt[b] = 0; }
+        for (int i = lo; i <= hi; i++) { box_t p = ref_box(items[i]); float c = 0.5f * (p.lo[ax] + p.hi[ax]); int b = (int)((c - cb.lo[ax]) / ext * NB); if (b >= NB) b = NB - 1; box_grow(&bins[b], &p); cnt[b] += ref_count(items[i]); }
+        float ra[NB]; box_t acc = box_empty(); int rc[NB], c2 = 0;
+        for (int b = NB - 1; b > 0; b--) { box_grow(&acc, &bins[b]); c2 += cnt[b]; ra[b] = c2 ? box_area(&acc) : 0; rc[b] = c2; }
+        acc = box_empty(); int c1 = 0;
+        for (int b = 0; b < NB - 1; b++) { box_grow(&acc, &bins[b]); c1 += cnt[b]; if (!c1 || !rc[b + 1]) continue; float cost = box_area(&acc) * c1 + ra[b + 1] * rc[b + 1]; if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; } }
+    }
+    int mid;
+    if (best_axis < 0) mid = lo + n / 2 - 1;
+    else { float ext = cb.hi[best_axis] - cb.lo[best_axis]; int i = lo, j = hi;
+        while (i <= j) { box_t p = ref_box(items[i]); float c = 0.5f * (p.lo[best_axis] + p.hi[best_axis]); int b = (int)((c - cb.lo[best_axis]) / ext * NB); if (b >= NB) b = NB - 1; if (b <= best_bin) i++; else { int t = items[i]; items[i] = items[j]; items[j] = t; j--; } }
+        mid = i - 1; if (mid < lo || mid >= hi) mid = lo + n / 2 - 1; }
+    int l = top_sah_rec(lo, mid), r = top_sah_rec(mid + 1, hi);
+    int id = n_nodes++;
+    nodes[id].left = l; nodes[id].right = r; nodes[id].count = ref_count(l) + ref_count(r); nodes[id].first = -1;
+    box_t b = ref_box(l), c = ref_box(r); box_grow(&b, &c); nodes[id].b = b;
+    return id;
+}
+static void build_hybrid(int bits, int target) {
+    morton_sort(bits, 0); n_nodes = 0;
+    int lg = 0; while ((1 << lg) < n_tris / target) lg++;
+    int shift = bits - lg; if (shift < 0) shift = 0;
+    items = malloc(sizeof(int) * n_tris); int n_items = 0;
+    for (int lo = 0; lo < n_tris;) { int hi = lo; while (hi + 1 < n_tris && (kv[hi + 1].key >> shift) == (kv[lo].key >> shift)) hi++; int r = lbvh_rec(lo, hi); fit_boxes(r); items[n_items++] = r; lo = hi + 1; }
+    root = top_sah_rec(0, n_items - 1);
+    printf("    (hybrid: %d clusters of ~%d primitives)\n", n_items, n_tris / n_items);
+    free(items);
+}
+
 /* ---- PLOC (Meister & Bittner 2018), radius r, over the Morton order ---- */
 static void build_ploc(int bits, int radius) {
     morton_sort(bits, 0); n_nodes = 0;
@@ -267,6 +305,7 @@ int main(int argc, char **argv) {
     if (!*only || strstr(only, "lbvh")) { build_lbvh(32, 0); evaluate("lbvh 32-bit"); }
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
+    if (strstr(only, "hybrid")) { int sizes[3] = {2, 8, 32}; for (int q = 0; q < 3; q++) { build_hybrid(32, sizes[q]); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + SAH top", sizes[q]); evaluate(nm); } }
     if (!*only || strstr(only, "ploc")) { build_ploc(32, 8); evaluate("ploc r8"); }
     if (strstr(only, "plocx")) { build_ploc(32, 16); evaluate("ploc r16"); build_ploc(32, 32); evaluate("ploc r32"); }
     return 0;
