@@ -143,21 +143,40 @@ static void build_hybrid(int bits, int target) {
 }
 
 /* ---- PLOC (Meister & Bittner 2018), radius r, over the Morton order ---- */
-static void build_ploc(int bits, int radius) {
-    morton_sort(bits, 0); n_nodes = 0;
-    int n = n_tris; int *ref = malloc(sizeof(int) * n), *ref2 = malloc(sizeof(int) * n), *nn = malloc(sizeof(int) * n); box_t *cb = malloc(sizeof(box_t) * n), *cb2 = malloc(sizeof(box_t) * n);
-    for (int i = 0; i < n; i++) { ref[i] = ~i; cb[i] = pbox[order[i]]; }
+static int ploc_over(int *ref, int n, int radius) {   /* agglomerates the clusters ref[0..n) (in order) into one tree; returns its root */
+    int *ref2 = malloc(sizeof(int) * n), *nn = malloc(sizeof(int) * n); box_t *cb = malloc(sizeof(box_t) * n), *cb2 = malloc(sizeof(box_t) * n);
+    for (int i = 0; i < n; i++) cb[i] = ref_box(ref[i]);
+    int *cur = ref;
     while (n > 1) {
         for (int i = 0; i < n; i++) { float best = FLT_MAX; int bj = -1; for (int j = i - radius; j <= i + radius; j++) { if (j == i || j < 0 || j >= n) continue; box_t u = cb[i]; box_grow(&u, &cb[j]); float a = box_area(&u); if (a < best) { best = a; bj = j; } } nn[i] = bj; }
         int m = 0;
         for (int i = 0; i < n; i++) {
             int j = nn[i];
-            if (j >= 0 && nn[j] == i) { if (i < j) { int id = n_nodes++; nodes[id].left = ref[i]; nodes[id].right = ref[j]; nodes[id].count = ref_count(ref[i]) + ref_count(ref[j]); nodes[id].first = -1; box_t u = cb[i]; box_grow(&u, &cb[j]); nodes[id].b = u; ref2[m] = id; cb2[m] = u; m++; } }
-            else { ref2[m] = ref[i]; cb2[m] = cb[i]; m++; }
+            if (j >= 0 && nn[j] == i) { if (i < j) { int id = n_nodes++; nodes[id].left = cur[i]; nodes[id].right = cur[j]; nodes[id].count = ref_count(cur[i]) + ref_count(cur[j]); nodes[id].first = -1; box_t u = cb[i]; box_grow(&u, &cb[j]); nodes[id].b = u; ref2[m] = id; cb2[m] = u; m++; } }
+            else { ref2[m] = cur[i]; cb2[m] = cb[i]; m++; }
         }
-        int *t = ref; ref = ref2; ref2 = t; box_t *tb = cb; cb = cb2; cb2 = tb; n = m;
+        int *t = cur; cur = ref2; ref2 = t; box_t *tb = cb; cb = cb2; cb2 = tb; n = m;
     }
-    root = ref[0]; free(ref); free(ref2); free(nn); free(cb); free(cb2);
+    int r = cur[0];
+    if (cur == ref) free(ref2); else free(cur == ref2 ? ref2 : cur);   /* one of the two scratch arrays is the caller's */
+    free(nn); free(cb); free(cb2);
+    return r;
+}
+static void build_ploc(int bits, int radius) {
+    morton_sort(bits, 0); n_nodes = 0;
+    int *ref = malloc(sizeof(int) * n_tris);
+    for (int i = 0; i < n_tris; i++) ref[i] = ~i;
+    root = ploc_over(ref, n_tris, radius);
+}
+/* LBVH inside Morton clusters, PLOC over the cluster roots: the device could do this with the kernels it has (k_hierarchy + k_ploc_* on n / 100 items) */
+static void build_hybrid_ploc(int bits, int target, int radius) {
+    morton_sort(bits, 0); n_nodes = 0;
+    int lg = 0; while ((1 << lg) < n_tris / target) lg++;
+    int shift = bits - lg; if (shift < 0) shift = 0;
+    int *ref = malloc(sizeof(int) * n_tris); int n_items = 0;
+    for (int lo = 0; lo < n_tris;) { int hi = lo; while (hi + 1 < n_tris && (kv[hi + 1].key >> shift) == (kv[lo].key >> shift)) hi++; int r = lbvh_rec(lo, hi); fit_boxes(r); ref[n_items++] = r; lo = hi + 1; }
+    printf("    (hybrid: %d clusters of ~%d primitives, PLOC r%d on top)\n", n_items, n_tris / n_items, radius);
+    root = ploc_over(ref, n_items, radius);
 }
 
 /* ---- bottom-up treelet-style improvement experiments go here ---- */
@@ -306,7 +325,8 @@ int main(int argc, char **argv) {
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
     if (strstr(only, "hybrid")) { int sizes[3] = {2, 8, 32}; for (int q = 0; q < 3; q++) { build_hybrid(32, sizes[q]); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + SAH top", sizes[q]); evaluate(nm); } }
-    if (!*only || strstr(only, "ploc")) { build_ploc(32, 8); evaluate("ploc r8"); }
+    if (strstr(only, "hploc")) { int sizes[2] = {2, 8}; for (int q = 0; q < 2; q++) { build_hybrid_ploc(32, sizes[q], 8); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + PLOC top", sizes[q]); evaluate(nm); } }
+    if (!*only || (strstr(only, "ploc") && !strstr(only, "hploc"))) { build_ploc(32, 8); evaluate("ploc r8"); }
     if (strstr(only, "plocx")) { build_ploc(32, 16); evaluate("ploc r16"); build_ploc(32, 32); evaluate("ploc r32"); }
     return 0;
 }
