@@ -104,6 +104,7 @@ static int sah_rec(int lo, int hi) {
 }
 static void build_sah(void) { for (int i = 0; i < n_tris; i++) order[i] = i; n_nodes = 0; root = sah_rec(0, n_tris - 1); fit_boxes(root); }
 
+static int ploc_over(int *ref, int n, int radius);
 /* ---- hybrid (HLBVH with a SAH top, Garanzha et al. 2011): LBVH inside Morton clusters of about `target` primitives, binned SAH over the cluster roots ---- */
 static int *items; /* cluster root refs, permuted by the top-level SAH */
 static int top_sah_rec(int lo, int hi) {
@@ -131,12 +132,13 @@ static int top_sah_rec(int lo, int hi) {
     box_t b = ref_box(l), c = ref_box(r); box_grow(&b, &c); nodes[id].b = b;
     return id;
 }
+static int g_cluster_ploc = 0;   /* 1: PLOC instead of the LBVH split rule inside the clusters */
 static void build_hybrid(int bits, int target) {
     morton_sort(bits, 0); n_nodes = 0;
     int lg = 0; while ((1 << lg) < n_tris / target) lg++;
     int shift = bits - lg; if (shift < 0) shift = 0;
     items = malloc(sizeof(int) * n_tris); int n_items = 0;
-    for (int lo = 0; lo < n_tris;) { int hi = lo; while (hi + 1 < n_tris && (kv[hi + 1].key >> shift) == (kv[lo].key >> shift)) hi++; int r = lbvh_rec(lo, hi); fit_boxes(r); items[n_items++] = r; lo = hi + 1; }
+    for (int lo = 0; lo < n_tris;) { int hi = lo; while (hi + 1 < n_tris && (kv[hi + 1].key >> shift) == (kv[lo].key >> shift)) hi++; int r; if (g_cluster_ploc && hi > lo) { int *ref = malloc(sizeof(int) * (hi - lo + 1)); for (int q = lo; q <= hi; q++) ref[q - lo] = ~q; r = ploc_over(ref, hi - lo + 1, 8); } else { r = lbvh_rec(lo, hi); fit_boxes(r); } items[n_items++] = r; lo = hi + 1; }
     root = top_sah_rec(0, n_items - 1);
     printf("    (hybrid: %d clusters of ~%d primitives)\n", n_items, n_tris / n_items);
     free(items);
@@ -325,6 +327,7 @@ int main(int argc, char **argv) {
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
     if (strstr(only, "hybrid")) { int sizes[3] = {2, 8, 32}; for (int q = 0; q < 3; q++) { build_hybrid(32, sizes[q]); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + SAH top", sizes[q]); evaluate(nm); } }
+    if (strstr(only, "hps")) { g_cluster_ploc = 1; int sizes[2] = {8, 32}; for (int q = 0; q < 2; q++) { build_hybrid(32, sizes[q]); char nm[64]; snprintf(nm, 64, "ploc clusters ~%d + SAH top", sizes[q]); evaluate(nm); } g_cluster_ploc = 0; }
     if (strstr(only, "hploc")) { int sizes[2] = {2, 8}; for (int q = 0; q < 2; q++) { build_hybrid_ploc(32, sizes[q], 8); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + PLOC top", sizes[q]); evaluate(nm); } }
     if (!*only || (strstr(only, "ploc") && !strstr(only, "hploc"))) { build_ploc(32, 8); evaluate("ploc r8"); }
     if (strstr(only, "plocx")) { build_ploc(32, 16); evaluate("ploc r16"); build_ploc(32, 32); evaluate("ploc r32"); }
