@@ -187,12 +187,13 @@ static double sah_cost_binary(void) { double c = 0; double ra = box_area(&nodes[
 /* ---- 8-wide collapse (k_collapse's rule, including the greedy octant slot assignment and the 8-bit plane quantisation) ---- */
 typedef struct { box_t cb[8]; box_t qb[8]; int child[8]; /* >= 0 wide node, -1 empty, <= -2: leaf, first packed prim = -(v + 2) */ int cnt[8]; } wnode_t;
 static wnode_t *wn; static int n_wide; static int *packed; static int n_packed; static int leaf_max = 2;
+static int open_rule = 0;   /* which child the collapse opens next: 0 largest area (the device), 1 area * count, 2 area * log2(count), 3 largest count */
 static void emit_leaves(int ref) { if (ref < 0) { packed[n_packed++] = order[~ref]; return; } emit_leaves(nodes[ref].left); emit_leaves(nodes[ref].right); }
 static int collapse(int ref) {
     int id = n_wide++; int c[8], nc;
     if (ref < 0) { c[0] = ref; nc = 1; } else { c[0] = nodes[ref].left; c[1] = nodes[ref].right; nc = 2; }
     for (int phase = 0; phase < 2; phase++) { int limit = phase == 0 ? leaf_max : 1;
-        while (nc < 8) { int who = -1; float best = -1; for (int i = 0; i < nc; i++) if (ref_count(c[i]) > limit) { box_t b = ref_box(c[i]); float a = box_area(&b); if (a > best) { best = a; who = i; } } if (who < 0) break; int r = c[who]; c[who] = nodes[r].left; c[nc++] = nodes[r].right; } }
+        while (nc < 8) { int who = -1; float best = -1; for (int i = 0; i < nc; i++) if (ref_count(c[i]) > limit) { box_t b = ref_box(c[i]); float a = box_area(&b); const float cn = (float)ref_count(c[i]); if (open_rule == 1) a *= cn; else if (open_rule == 2) a *= log2f(cn + 1.f); else if (open_rule == 3) a = cn; if (a > best) { best = a; who = i; } } if (who < 0) break; int r = c[who]; c[who] = nodes[r].left; c[nc++] = nodes[r].right; } }
     box_t cbx[8], nb = box_empty(); for (int i = 0; i < nc; i++) { cbx[i] = ref_box(c[i]); box_grow(&nb, &cbx[i]); }
     /* greedy slot assignment: global minimum of dot(child centre - node centre, sign_s) */
     int slot_of[8], used = 0; for (int i = 0; i < nc; i++) slot_of[i] = -1;
@@ -324,6 +325,7 @@ int main(int argc, char **argv) {
     for (int i = 0; i < n_rays; i++) { for (int k = 0; k < 3; k++) RO[i][k] = rndf(); if (terrain) RO[i][1] = RO[i][1] * 0.3f + 0.1f; /* tools/trace_bench.py's terrain rays */ float z = rndf() * 2 - 1, phi = rndf() * 6.2831853f, r = sqrtf(fmaxf(0, 1 - z * z)); RD[i][0] = r * cosf(phi); RD[i][1] = r * sinf(phi); RD[i][2] = z; }
     printf("%s %d triangles, %d rays, leaf_max %d\n", terrain ? "terrain" : "soup", n_tris, n_rays, leaf_max);
     if (!*only || strstr(only, "lbvh")) { build_lbvh(32, 0); evaluate("lbvh 32-bit"); }
+    if (strstr(only, "rules")) { build_lbvh(32, 0); const char *nm[4] = {"open largest area (device)", "open largest area * count", "open largest area * log2 count", "open largest count"}; for (open_rule = 0; open_rule < 4; open_rule++) evaluate(nm[open_rule]); open_rule = 0; }
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
     if (strstr(only, "hybrid")) { int sizes[3] = {2, 8, 32}; for (int q = 0; q < 3; q++) { build_hybrid(32, sizes[q]); char nm[64]; snprintf(nm, 64, "lbvh clusters ~%d + SAH top", sizes[q]); evaluate(nm); } }
