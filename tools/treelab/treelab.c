@@ -187,6 +187,7 @@ static double sah_cost_binary(void) { double c = 0; double ra = box_area(&nodes[
 /* ---- 8-wide collapse (k_collapse's rule, including the greedy octant slot assignment and the 8-bit plane quantisation) ---- */
 typedef struct { box_t cb[8]; box_t qb[8]; int child[8]; /* >= 0 wide node, -1 empty, <= -2: leaf, first packed prim = -(v + 2) */ int cnt[8]; } wnode_t;
 static wnode_t *wn; static int n_wide; static int *packed; static int n_packed; static int leaf_max = 2;
+static int slot_rule = 0;   /* slot assignment cost: 0 centroid offset . sign (the device), 1 entry corner . sign */
 static int open_rule = 0;   /* which child the collapse opens next: 0 largest area (the device), 1 area * count, 2 area * log2(count), 3 largest count */
 static void emit_leaves(int ref) { if (ref < 0) { packed[n_packed++] = order[~ref]; return; } emit_leaves(nodes[ref].left); emit_leaves(nodes[ref].right); }
 static int collapse(int ref) {
@@ -199,7 +200,9 @@ static int collapse(int ref) {
     int slot_of[8], used = 0; for (int i = 0; i < nc; i++) slot_of[i] = -1;
     for (int it = 0; it < nc; it++) { float best = FLT_MAX; int bc = -1, bs = -1;
         for (int i = 0; i < nc; i++) { if (slot_of[i] >= 0) continue; float cc[3]; for (int k = 0; k < 3; k++) cc[k] = 0.5f * (cbx[i].lo[k] + cbx[i].hi[k]) - 0.5f * (nb.lo[k] + nb.hi[k]);
-            for (int sl = 0; sl < 8; sl++) { if (used >> sl & 1) continue; float cost = ((sl & 1) ? -cc[0] : cc[0]) + ((sl & 2) ? -cc[1] : cc[1]) + ((sl & 4) ? -cc[2] : cc[2]); if (cost < best) { best = cost; bc = i; bs = sl; } } }
+            for (int sl = 0; sl < 8; sl++) { if (used >> sl & 1) continue; float cost = ((sl & 1) ? -cc[0] : cc[0]) + ((sl & 2) ? -cc[1] : cc[1]) + ((sl & 4) ? -cc[2] : cc[2]);
+                if (slot_rule == 1) { cost = 0; for (int k = 0; k < 3; k++) cost += (sl >> k & 1) ? -(cbx[i].hi[k] - nb.hi[k]) : (cbx[i].lo[k] - nb.lo[k]); }   /* slot sl is first for directions negative along the axes of its set bits: they enter at hi */
+                if (cost < best) { best = cost; bc = i; bs = sl; } } }
         slot_of[bc] = bs; used |= 1 << bs; }
     for (int i = 0; i < 8; i++) { wn[id].child[i] = -1; wn[id].cnt[i] = 0; }
     float scale[3]; for (int k = 0; k < 3; k++) { float sc = (nb.hi[k] - nb.lo[k]) / 255.0f; int e; float m = frexpf(sc, &e); scale[k] = sc > 0 ? ldexpf(1.0f, m == 0.5f ? e - 1 : e) : 1e-30f; }
@@ -325,6 +328,7 @@ int main(int argc, char **argv) {
     for (int i = 0; i < n_rays; i++) { for (int k = 0; k < 3; k++) RO[i][k] = rndf(); if (terrain) RO[i][1] = RO[i][1] * 0.3f + 0.1f; /* tools/trace_bench.py's terrain rays */ float z = rndf() * 2 - 1, phi = rndf() * 6.2831853f, r = sqrtf(fmaxf(0, 1 - z * z)); RD[i][0] = r * cosf(phi); RD[i][1] = r * sinf(phi); RD[i][2] = z; }
     printf("%s %d triangles, %d rays, leaf_max %d\n", terrain ? "terrain" : "soup", n_tris, n_rays, leaf_max);
     if (!*only || strstr(only, "lbvh")) { build_lbvh(32, 0); evaluate("lbvh 32-bit"); }
+    if (strstr(only, "slots")) { build_lbvh(32, 0); for (slot_rule = 0; slot_rule < 2; slot_rule++) evaluate(slot_rule ? "slots by entry corner" : "slots by centroid (device)"); slot_rule = 0; }
     if (strstr(only, "rules")) { build_lbvh(32, 0); const char *nm[4] = {"open largest area (device)", "open largest area * count", "open largest area * log2 count", "open largest count"}; for (open_rule = 0; open_rule < 4; open_rule++) evaluate(nm[open_rule]); open_rule = 0; }
     if (!*only || strstr(only, "ext")) { for (int e = 2; e <= 4; e++) { build_lbvh(40, e); char nm[64]; snprintf(nm, 64, "lbvh extended (size bit / %d)", e); evaluate(nm); } }
     if (!*only || strstr(only, "sah")) { build_sah(); evaluate("binned SAH"); }
